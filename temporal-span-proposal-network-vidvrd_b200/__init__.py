@@ -1,0 +1,8 @@
+"""tspn_b200 — B200-native tracklet-pair stage of TSPN.
+
+Host side: PyTorch modules with the reference's ``lib/modeling`` ``forward()`` signatures.
+Compute: hand-written sm_100a CUDA behind the C-ABI of ``include/tspn_b200.h``
+(``csrc/libtspn_b200.so``), loaded with ctypes.  There is no CPU fallback: importing the
+package works anywhere, calling an op without the library or without a B200 raises.
+"""
+__version__ = "0.1.0"
