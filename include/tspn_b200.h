@@ -1,0 +1,218 @@
+/*
+ * tspn_b200.h — C ABI of the B200-native TSPN tracklet-pair stage.
+ *
+ * One shared library (csrc/libtspn_b200.so, sm_100a only) behind plain pointers and sizes:
+ * no torch types, no C++ types, no exceptions across the boundary.  The host side that
+ * mirrors the reference's Python interface (package tspn_b200) binds these with ctypes
+ * and passes tensor.data_ptr(); INTEGRATION.md shows the stub a maintainer of the
+ * reference would add.  Each entry point names the reference interface it replaces
+ * (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   - every `d_*` pointer is DEVICE memory owned by the caller; the library never
+ *     allocates persistent memory and never frees caller memory; scratch space is a
+ *     caller-provided workspace whose size comes from the matching *_workspace_bytes();
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no hidden
+ *     synchronisation, no host reads of device data;
+ *   - return value: TSPN_OK (0) or a negative TSPN_E* code; tspn_last_error() returns
+ *     the thread-local message of the last failure;
+ *   - a device that is not compute capability 10.x makes every compute entry return
+ *     TSPN_EARCH: there is no fallback path by design;
+ *   - base pointers must be 16-byte aligned (TMA, 128-bit accesses) -> TSPN_EALIGN.
+ *
+ * Batch layout (several videos per launch)
+ *   A batch of V videos is described by the *video table*: V rows of TSPN_VT_COLS
+ *   int64, built on the host by tspn_build_video_table() from the per-video tracklet
+ *   and frame counts, then copied to the device by the caller.  With N = tracklets,
+ *   T = frames, P = N(N-1) ordered pairs of a video:
+ *     boxes   float [sum N*Tb][4]   (x1,y1,x2,y2) inclusive pixels, row of tracklet n at
+ *                                   box_off + n*Tb, Tb = T rounded up to 8 (pad = 0)
+ *     span    int32 [sum N][2]      [pstart, pend)   (lib/modeling/trajectory.py:21-22)
+ *     cls     float [sum N][C]      track_cls_logits (lib/dataset/vrdataset.py:61-83)
+ *     motion  float [sum N][4000]   4 BoW blocks of 1000 (lib/dataset/vrdataset.py:227-236)
+ *     geo     float [sum P*8*Tp]    per video [P][8][Tp], Tp = T rounded up to 4 (pad = 0)
+ *     pair row p of (s,o): s*(N-1) + o - [o>s]  (order of lib/modeling/predict.py:133-140)
+ */
+#ifndef TSPN_B200_H
+#define TSPN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSPN_ABI_VERSION 1
+
+/* error codes */
+#define TSPN_OK 0
+#define TSPN_EBADARG (-1)
+#define TSPN_ESHAPE (-2)
+#define TSPN_EALIGN (-3)
+#define TSPN_ECUDA (-4)
+#define TSPN_EARCH (-5)
+
+/* video table columns */
+#define TSPN_VT_COLS 12
+#define TSPN_VT_N 0         /* tracklets */
+#define TSPN_VT_T 1         /* frames */
+#define TSPN_VT_TP 2        /* geo row length: T rounded up to 4 */
+#define TSPN_VT_TB 3        /* box row length: T rounded up to 8 */
+#define TSPN_VT_TRK_OFF 4   /* first tracklet row (span / cls / motion) */
+#define TSPN_VT_PAIR_OFF 5  /* first pair row */
+#define TSPN_VT_GEO_OFF 6   /* first geo float */
+#define TSPN_VT_ITEM_OFF 7  /* first work item of the pair-geometry kernel */
+#define TSPN_VT_BOX_OFF 8   /* first box (in boxes, i.e. units of 16 bytes) */
+#define TSPN_VT_SCORE_OFF 9 /* first relationness score (sum of N*N) */
+
+/* totals[] written by tspn_build_video_table */
+#define TSPN_TOT_COLS 8
+#define TSPN_TOT_TRACKLETS 0
+#define TSPN_TOT_PAIRS 1
+#define TSPN_TOT_GEO_FLOATS 2
+#define TSPN_TOT_ITEMS 3
+#define TSPN_TOT_BOXES 4
+#define TSPN_TOT_SCORES 5
+#define TSPN_TOT_MAX_N 6
+#define TSPN_TOT_MAX_T 7
+
+/* geometry channels of geo[P][8][Tp] ([SPEC] s2) */
+#define TSPN_GEO_CHANNELS 8
+#define TSPN_MOTION_DIM 4000
+#define TSPN_MOTION_BLOCK 1000
+#define TSPN_REL_BINS 500
+#define TSPN_REL_DIM 3000
+
+/* flags */
+#define TSPN_VIOU_FULL 0       /* volumes over each full span: evaluation/common.py:65-106 (V2);
+                                  equals trajectory.py:127-141 (V1) when all spans are equal */
+#define TSPN_VIOU_CLIPPED 1    /* volumes over the overlap only: association.py:35-48 (V3) */
+#define TSPN_TOPK_KEEP_DIAGONAL 0    /* reference behaviour, ppn.py:84-85 (quirk Q1) */
+#define TSPN_TOPK_EXCLUDE_DIAGONAL 1 /* survivors are real pairs (sparsify mode) */
+#define TSPN_PREC_FP32_EXACT 0 /* CUDA cores, fixed k-ascending fma order: bit-reproducible */
+#define TSPN_PREC_TENSOR 1     /* tcgen05 tensor cores: bf16 (or tf32 on fp32 storage) operands,
+                                  fp32 accumulation in TMEM */
+
+/* ---- library ------------------------------------------------------------------------ */
+int tspn_version(void);
+/* copies the calling thread's last error message; returns its length */
+int tspn_last_error(char* buf, int len);
+/* TSPN_OK when the current CUDA device is compute capability 10.x, else TSPN_EARCH */
+int tspn_check_device(void);
+
+/* ---- host helper: batch layout ------------------------------------------------------- */
+/* table_host: [V][TSPN_VT_COLS] int64 (host), totals: [TSPN_TOT_COLS] int64 (host).
+ * Pure host arithmetic on sizes; no device access. */
+int tspn_build_video_table(int num_videos, const int32_t* n_tracklets, const int32_t* n_frames,
+                           int64_t* table_host, int64_t* totals);
+
+/* ---- a1: pair enumeration -------------------------------------------------------------
+ * Replaces the h5 `pairs` table (lib/dataset/vrdataset.py:208; order of predict.py:133-140).
+ * d_pairs: int64 [sum P][2] = (s, o) local tracklet indices. */
+int tspn_enumerate_pairs(const int64_t* d_table, int num_videos, int64_t total_pairs,
+                         int64_t* d_pairs, void* stream);
+
+/* ---- a3/a4/a6/a7 + [SPEC] s2/s3: all-pairs per-frame geometry and trajectory vIoU ----------
+ * Replaces cubic_iou/_intersect/_union (lib/modeling/trajectory.py:85-141) applied to all
+ * ordered pairs of each video, viou (lib/evaluation/common.py:65-106) and _traj_iou
+ * (lib/modeling/association.py:35-48, flag TSPN_VIOU_CLIPPED); adds the per-frame channels.
+ * d_geo may be NULL (reductions only).  d_workspace: tspn_pair_geo_workspace_bytes(). */
+int64_t tspn_pair_geo_workspace_bytes(int64_t total_tracklets);
+int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_items,
+                       int64_t total_tracklets, int64_t total_boxes,
+                       const float* d_boxes, const int32_t* d_span,
+                       float* d_geo, float* d_viou, float* d_tiou, int32_t* d_overlap,
+                       int flags, void* d_workspace, void* stream);
+
+/* ---- a4 matrix form: cubic_iou(bboxes1, bboxes2) -----------------------------------------
+ * lib/modeling/trajectory.py:127-141.  b1 [n1][t][4], b2 [n2][t][4] -> out [n1][n2]. */
+int tspn_cubic_iou(const float* d_b1, int n1, const float* d_b2, int n2, int t,
+                   float* d_out, void* stream);
+
+/* ---- a6 batched: viou over an explicit list of trajectory pairs ---------------------------
+ * lib/evaluation/common.py:65-106 for every (a[i], b[i]); trajectories live in a pool:
+ * trajectory j has its boxes at d_pool[d_traj_off[j] ...] for frames [span[j][0], span[j][1]). */
+int tspn_viou_pairs(const float* d_pool, const int64_t* d_traj_off, const int32_t* d_traj_span,
+                    const int32_t* d_a, const int32_t* d_b, int64_t n_pairs, int flags,
+                    float* d_out, void* stream);
+
+/* ---- a2: feature rows -------------------------------------------------------------------
+ * L1-normalise each 1000-wide BoW block (lib/dataset/vrdataset.py:227-236 with
+ * lib/utils/miscellaneous.py:32-35). */
+int tspn_normalize_motion(const float* d_motion, int64_t n_tracklets, float* d_out, void* stream);
+/* Build rows [2C | 8000 motion | 3000 relative] (lib/dataset/vrdataset.py:219-243); the last
+ * 3000 columns are the adaptive-average-pooled geometry ([SPEC] s4).  d_rows: global pair rows
+ * to build (int64, NULL = all total_pairs rows in order).  Output row stride ld_feat floats
+ * (>= 2C+11000, multiple of 4).  d_feat_bf16 (optional, may be NULL): same rows in bf16 with
+ * stride ld_bf16 (multiple of 8) for the tensor-core predicate head. */
+int tspn_assemble_features(const int64_t* d_table, int num_videos, int64_t total_pairs,
+                           const float* d_cls, int n_classes, const float* d_motion_norm,
+                           const float* d_geo, const int32_t* d_overlap,
+                           const int64_t* d_rows, int64_t n_rows,
+                           float* d_feat, int64_t ld_feat,
+                           void* d_feat_bf16, int64_t ld_bf16, void* stream);
+
+/* ---- a8/a9: relationness scoring and top-K -------------------------------------------------
+ * PPNHead.forward (lib/modeling/relpn/ppn.py:92-112): scores [sum N*N] (per video N x N,
+ * diagonal included).  weights: sub_emb.0 [H][C],[H]; sub_emb.2 [C][H],[C]; obj_emb likewise
+ * (state_dict order).  d_workspace: tspn_relationness_workspace_bytes(). */
+int64_t tspn_relationness_workspace_bytes(int64_t total_tracklets, int n_classes, int hidden);
+int tspn_relationness(const int64_t* d_table, int num_videos, int64_t total_tracklets,
+                      const float* d_cls, int n_classes, int hidden,
+                      const float* d_sub_w0, const float* d_sub_b0,
+                      const float* d_sub_w2, const float* d_sub_b2,
+                      const float* d_obj_w0, const float* d_obj_b0,
+                      const float* d_obj_w2, const float* d_obj_b2,
+                      float* d_scores, void* d_workspace, void* stream);
+/* PPN._forward_test (lib/modeling/relpn/ppn.py:79-90): per video the first min(K, N*N)
+ * flat indices s*N+o in descending score order, ties to the lower index ([SPEC] s6).
+ * d_topk_idx int64 [V][K] (-1 beyond K_eff), d_topk_score float [V][K],
+ * d_topk_row int64 [V][K] global pair row of (s,o) or -1 for s==o / padding (may be NULL). */
+int tspn_topk_pairs(const int64_t* d_table, int num_videos, const float* d_scores, int k,
+                    int flags, int64_t* d_topk_idx, float* d_topk_score, int64_t* d_topk_row,
+                    void* stream);
+
+/* ---- a14: predicate classifier -----------------------------------------------------------
+ * RelationPredictor.forward (lib/modeling/model.py:76-88): y = sigmoid(x W^T + b).
+ * x [m][ld_x] fp32 (or bf16 when x_is_bf16), W [r][f] fp32, y [m][r].
+ * TSPN_PREC_TENSOR needs the packed weights of tspn_pack_predicate_weights. */
+int64_t tspn_predicate_packed_bytes(int n_predicates, int feature_dim);
+int tspn_pack_predicate_weights(const float* d_w, int n_predicates, int feature_dim,
+                                void* d_packed, void* stream);
+int64_t tspn_predicate_workspace_bytes(int64_t m, int feature_dim, int n_predicates, int precision);
+int tspn_predicate_head(const void* d_x, int x_is_bf16, int64_t ld_x, int64_t m, int feature_dim,
+                        const float* d_w, const void* d_w_packed, const float* d_bias,
+                        int n_predicates, float* d_y, int precision, void* d_workspace,
+                        void* stream);
+
+/* ---- a11/a12 + [SPEC] s5: temporal-span head ---------------------------------------------
+ * DPNHead.forward (lib/modeling/relpn/dpn.py:55-73): Conv1d(k3,p1) -> ReLU -> Conv1d(k1).
+ * x rows are gathered: pair i reads x[d_rows[i]] (NULL = identity), each row [cin][ld_t];
+ * out [k][a2][t].  conv_w [cin][cin][3], pred_w [a2][cin]. */
+int64_t tspn_span_head_workspace_bytes(int64_t k, int cin, int t, int a2, int precision);
+int tspn_span_head(const float* d_x, const int64_t* d_rows, int64_t row_stride, int64_t ld_t,
+                   int64_t k, int cin, int t,
+                   const float* d_conv_w, const float* d_conv_b,
+                   const float* d_pred_w, const float* d_pred_b, int a2,
+                   float* d_out, int precision, void* d_workspace, void* stream);
+/* anchors of anchor_generator.py:48-104 + decode: reg [k][2a][t] -> spans int32 [k][n_loc*a][2] */
+int tspn_span_num_locations(int t, float stride);
+int tspn_span_decode(const float* d_reg, int64_t k, int n_anchors, int t,
+                     const float* d_sizes, float stride, int32_t* d_spans, void* stream);
+
+/* ---- N1: predict.py:66-117 post-processing ------------------------------------------------
+ * per video: top `topk_per_pair` predicates per pair row, then top `topk_per_video` overall;
+ * one 32-byte record per kept triplet: {score f32, s_cls, pred, o_cls, s_tid, o_tid, start,
+ * end : i32}.  d_logits [m][r] rows in the order of d_rows (global pair rows, NULL = all).
+ * d_records [V][topk_per_video][8] (int32 view), d_counts int32 [V]. */
+int tspn_postprocess(const int64_t* d_table, int num_videos, const float* d_logits,
+                     const int64_t* d_rows, const int64_t* d_row_video_off, int n_predicates,
+                     const float* d_cls, int n_classes, const int32_t* d_overlap,
+                     int topk_per_pair, int topk_per_video,
+                     int32_t* d_records, int32_t* d_counts, void* d_workspace, void* stream);
+int64_t tspn_postprocess_workspace_bytes(int64_t m, int topk_per_pair);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSPN_B200_H */

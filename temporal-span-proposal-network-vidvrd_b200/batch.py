@@ -1,0 +1,158 @@
+"""Batch layout of the pair stage: several videos per launch.
+
+The reference processes one 30-frame segment per forward (lib/modeling/predict.py:42-57,
+``TEST_BATCH_SIZE: 1``); per-video problems are far too small for a B200, so the CUDA
+entry points take a *batch* of videos described by the video table of
+``include/tspn_b200.h``.  ``HostBatch`` packs per-video arrays into pinned host buffers in
+that layout (box rows padded to a multiple of 8 frames for the TMA tile), ``DeviceBatch`` is
+its image in HBM.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (TOT_BOXES, TOT_GEO_FLOATS, TOT_ITEMS, TOT_MAX_N, TOT_MAX_T, TOT_PAIRS, TOT_SCORES,
+                   TOT_TRACKLETS, VT_BOX_OFF, VT_COLS, VT_GEO_OFF, VT_N, VT_PAIR_OFF, VT_SCORE_OFF, VT_T,
+                   VT_TB, VT_TP, VT_TRK_OFF)
+
+
+def _np(x, dtype):
+    if isinstance(x, torch.Tensor):
+        x = x.detach().cpu().numpy()
+    return np.ascontiguousarray(x, dtype=dtype)
+
+
+class HostBatch:
+    """Packed, pinned host image of a batch of videos."""
+
+    def __init__(self, boxes: Sequence, span: Sequence, cls: Optional[Sequence] = None,
+                 motion: Optional[Sequence] = None, pin: bool = True):
+        boxes = [_np(b, np.float32) for b in boxes]
+        span = [_np(s, np.int32).reshape(-1, 2) for s in span]
+        assert len(boxes) == len(span)
+        self.n = [int(b.shape[0]) for b in boxes]
+        self.t = [int(b.shape[1]) if b.ndim == 3 else 1 for b in boxes]
+        for b, s in zip(boxes, span):
+            if b.ndim != 3 or b.shape[2] != 4 or s.shape[0] != b.shape[0]:
+                raise ValueError("boxes must be [N, T, 4] with span [N, 2]; got %s / %s" % (b.shape, s.shape))
+            if s.size and (s.min() < 0 or s[:, 1].max() > b.shape[1] or (s[:, 0] > s[:, 1]).any()):
+                raise ValueError("span must satisfy 0 <= pstart <= pend <= T")
+        self.table, self.totals = _lib.build_video_table(self.n, self.t)
+        tot = self.totals
+        use_pin = pin and torch.cuda.is_available()
+
+        def alloc(shape, dtype):
+            t = torch.zeros(shape, dtype=dtype)
+            return t.pin_memory() if use_pin else t
+
+        self.boxes = alloc((int(tot[TOT_BOXES]), 4), torch.float32)
+        self.span = alloc((int(tot[TOT_TRACKLETS]), 2), torch.int32)
+        bview = self.boxes.numpy()
+        sview = self.span.numpy()
+        for v, (b, s) in enumerate(zip(boxes, span)):
+            row = self.table[v]
+            n, t, tb = int(row[VT_N]), int(row[VT_T]), int(row[VT_TB])
+            if n == 0:
+                continue
+            dst = bview[int(row[VT_BOX_OFF]):int(row[VT_BOX_OFF]) + n * tb].reshape(n, tb, 4)
+            dst[:, :t] = b
+            sview[int(row[VT_TRK_OFF]):int(row[VT_TRK_OFF]) + n] = s
+        self.cls = None
+        self.motion = None
+        if cls is not None:
+            cls = [_np(c, np.float32) for c in cls]
+            self.cls = alloc((int(tot[TOT_TRACKLETS]), int(cls[0].shape[1])), torch.float32)
+            if int(tot[TOT_TRACKLETS]):
+                self.cls.numpy()[:] = np.concatenate(cls, axis=0)
+        if motion is not None:
+            motion = [_np(m, np.float32) for m in motion]
+            self.motion = alloc((int(tot[TOT_TRACKLETS]), _lib.MOTION_DIM), torch.float32)
+            if int(tot[TOT_TRACKLETS]):
+                self.motion.numpy()[:] = np.concatenate(motion, axis=0)
+        self.table_t = torch.from_numpy(np.ascontiguousarray(self.table).reshape(-1, VT_COLS).copy())
+        if use_pin:
+            self.table_t = self.table_t.pin_memory()
+
+    @classmethod
+    def from_videos(cls, videos, pin: bool = True) -> "HostBatch":
+        """From ``tspn_b200.synth.VideoTracklets`` (or anything with boxes/span/cls/motion)."""
+        return cls([v.boxes for v in videos], [v.span for v in videos], [v.cls for v in videos],
+                   [v.motion for v in videos], pin=pin)
+
+    @property
+    def num_videos(self) -> int:
+        return len(self.n)
+
+    def h2d_bytes(self) -> int:
+        tot = self.boxes.numel() * 4 + self.span.numel() * 4 + self.table_t.numel() * 8
+        if self.cls is not None:
+            tot += self.cls.numel() * 4
+        if self.motion is not None:
+            tot += self.motion.numel() * 4
+        return int(tot)
+
+    def to_device(self, device="cuda", non_blocking: bool = True) -> "DeviceBatch":
+        return DeviceBatch(self, device, non_blocking)
+
+
+class DeviceBatch:
+    """HBM-resident batch: the pointers the C ABI consumes."""
+
+    def __init__(self, host: HostBatch, device="cuda", non_blocking: bool = True):
+        self.host = host
+        self.n, self.t = host.n, host.t
+        self.table_host, self.totals = host.table, host.totals
+        dev = torch.device(device)
+        self.device = dev
+        self.table = host.table_t.to(dev, non_blocking=non_blocking)
+        self.boxes = host.boxes.to(dev, non_blocking=non_blocking)
+        self.span = host.span.to(dev, non_blocking=non_blocking)
+        self.cls = None if host.cls is None else host.cls.to(dev, non_blocking=non_blocking)
+        self.motion = None if host.motion is None else host.motion.to(dev, non_blocking=non_blocking)
+
+    # sizes -----------------------------------------------------------------------------
+    @property
+    def num_videos(self) -> int:
+        return len(self.n)
+
+    def total(self, col: int) -> int:
+        return int(self.totals[col])
+
+    @property
+    def total_pairs(self) -> int:
+        return self.total(TOT_PAIRS)
+
+    @property
+    def total_tracklets(self) -> int:
+        return self.total(TOT_TRACKLETS)
+
+    # per-video views -----------------------------------------------------------------------
+    def pair_slice(self, v: int) -> slice:
+        off = int(self.table_host[v, VT_PAIR_OFF])
+        n = self.n[v]
+        return slice(off, off + n * max(n - 1, 0))
+
+    def tracklet_slice(self, v: int) -> slice:
+        off = int(self.table_host[v, VT_TRK_OFF])
+        return slice(off, off + self.n[v])
+
+    def score_view(self, scores: torch.Tensor, v: int) -> torch.Tensor:
+        off = int(self.table_host[v, VT_SCORE_OFF])
+        n = self.n[v]
+        return scores[off:off + n * n].view(n, n)
+
+    def geo_rows(self, geo: torch.Tensor, v: int) -> torch.Tensor:
+        """``[P, 8, Tp]`` view of video v's geometry including the row pad (Tp = T rounded up to 4)."""
+        row = self.table_host[v]
+        n, tp = int(row[VT_N]), int(row[VT_TP])
+        p = n * max(n - 1, 0)
+        off = int(row[VT_GEO_OFF])
+        return geo[off:off + p * _lib.GEO_CHANNELS * tp].view(p, _lib.GEO_CHANNELS, tp)
+
+    def geo_view(self, geo: torch.Tensor, v: int) -> torch.Tensor:
+        """``[P, 8, T]`` view of video v's geometry (the row pad to Tp is sliced off)."""
+        return self.geo_rows(geo, v)[:, :, :self.t[v]]

@@ -1,0 +1,100 @@
+"""yacs-free configuration with the reference's keys.
+
+Defaults restate lib/config/defaults.py:1-74 (yacs is not installed here and the product
+must not depend on it); ``merge_from_file`` overlays a YAML file with the same nesting as
+configs/baseline.yaml (base.py:129).  Keys the reference does not have are marked [SPEC].
+"""
+from __future__ import annotations
+
+import copy
+
+import yaml
+
+
+class CfgNode(dict):
+    """Attribute-style nested dict (the subset of yacs.CfgNode the reference uses)."""
+
+    def __init__(self, init=None):
+        super().__init__()
+        for k, v in (init or {}).items():
+            self[k] = CfgNode(v) if isinstance(v, dict) and not isinstance(v, CfgNode) else v
+
+    def __getattr__(self, name):
+        try:
+            return self[name]
+        except KeyError as e:
+            raise AttributeError(name) from e
+
+    def __setattr__(self, name, value):
+        self[name] = value
+
+    def clone(self):
+        return copy.deepcopy(self)
+
+    def merge_from_dict(self, other, _path=""):
+        for k, v in other.items():
+            if k not in self:
+                raise KeyError("Non-existent config key: %s%s" % (_path, k))
+            if isinstance(self[k], CfgNode):
+                if not isinstance(v, dict):
+                    raise TypeError("config key %s%s is a node" % (_path, k))
+                self[k].merge_from_dict(v, _path + k + ".")
+            else:
+                if isinstance(self[k], float) and isinstance(v, str):
+                    v = float(v)          # "1e-2" in baseline.yaml
+                self[k] = v
+
+    def merge_from_file(self, path):
+        with open(path) as f:
+            self.merge_from_dict(yaml.safe_load(f) or {})
+
+    def merge_from_list(self, items):
+        assert len(items) % 2 == 0
+        for key, value in zip(items[0::2], items[1::2]):
+            node = self
+            parts = key.split(".")
+            for p in parts[:-1]:
+                node = node[p]
+            if parts[-1] not in node:
+                raise KeyError("Non-existent config key: %s" % key)
+            node[parts[-1]] = value
+
+
+def get_default_cfg() -> CfgNode:
+    return CfgNode({
+        "MODEL": {"NAME": "baseline"},
+        "SOLVER": {
+            "MAX_ITER": 2000, "BASE_LR": 1e-2, "BIAS_LR_FACTOR": 2, "WEIGHT_DECAY": 5e-4, "WEIGHT_DECAY_BIAS": 0,
+            "OPTIMIZER": {"TYPE": "adam", "MOMENTUM": 0.9},
+            "SCHEDULER": {"TYPE": "warmup_multi", "MILESTONES": [1000, 1500], "GAMMA": 0.1,
+                          "WARMUP_FACTOR": 1.0 / 3, "WARMUP_ITERS": 500, "WARMUP_METHOD": "linear"},
+        },
+        "DATASET": {"TRAIN_BATCH_SIZE": 1024, "TEST_BATCH_SIZE": 1, "TRAIN_NUM_WORKERS": 0, "TEST_NUM_WORKERS": 4,
+                    "LOGIT_ONLY": False, "USE_GT_OBJ_TRAJS": False},
+        "PREDICT": {"OBJECT_NUM": 35, "PREDICATE_NUM": 132, "TOPK_PER_PAIR": 20, "TOPK_PER_SEG": 200,
+                    "FEATURE_DIM": 11070,
+                    # [SPEC] arithmetic of the heads: "fp32" = fixed-order CUDA cores (bit-reproducible),
+                    # "tensor" = tcgen05 (bf16 / tf32 operands, fp32 accumulate)
+                    "PRECISION": "fp32",
+                    # [SPEC] s7: run the heads on the top-K survivors only (False = reference, quirk Q3)
+                    "SPARSIFY": False,
+                    # [SPEC] mirror predict.py:89's wrong-row object label (quirk Q4) or fix it
+                    "FIX_OBJECT_LABEL": True},
+        "RELPN": {
+            "OBJECT_DIM": 1024,
+            "USE_PPN": True,
+            "PPN": {"NUM_PAIR_PROPOSALS": 256, "IN_CHANNELS": 35, "HIDDEN_CHANNELS": 64, "OUT_CHANNELS": 35,
+                    "BATCH_SIZE_PER_SEGMENT": 256, "POSITIVE_FRACTION": 0.5},
+            "USE_DPN": True,
+            "DPN": {"NUM_DURATION_PROPOSALS": 64, "DPN_ONLY": False, "IN_CHANNELS": 1024,
+                    "NUM_ANCHORS_PER_LOCATION": 4,
+                    # defaults.py:66-67 holds placeholders (35 / 132); the only anchors the reference ever
+                    # instantiates are anchor_generator.py:118-120: sizes (15,30,45,60), stride 7.5
+                    "ANCHOR_SIZES": [15.0, 30.0, 45.0, 60.0], "ANCHOR_STRIDE": 7.5},
+        },
+        "ETC": {"RANDOM_SEED": 0, "DISPLAY_FREQ": 1, "SAVE_FREQ": 20,
+                "MODEL_DUMP_FILE": "baseline_weights_epoch_100.pt"},
+    })
+
+
+cfg = get_default_cfg()

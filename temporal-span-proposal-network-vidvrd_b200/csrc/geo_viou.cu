@@ -1,0 +1,450 @@
+// geo_viou.cu — all-pairs per-frame geometry + trajectory vIoU (the HBM-write-bound kernel).
+//
+// Replaces, for every ordered tracklet pair of every video of a batch:
+//   _intersect/_union/cubic_iou  lib/modeling/trajectory.py:85-141          (V1)
+//   viou                         lib/evaluation/common.py:65-106            (V2, default)
+//   _traj_iou                    lib/modeling/association.py:35-48          (V3, CLIP)
+// and produces the per-frame channels of [SPEC] s2: box-centre deltas,
+// log-scale ratios, per-frame IoU, forward differences, temporal-overlap mask.
+//
+// Design (sm_100a):
+//   * work item = (video, subject s, group of 8 objects); one 128-thread CTA per item;
+//   * the two tracklets' box rows are staged chunk by chunk (512 frames + 1 halo row) into
+//     shared memory by 2-D tiled TMA (cp.async.bulk.tensor -> UTMALDG) with SWIZZLE_128B,
+//     double-buffered on mbarriers: the subject chunk is loaded once per chunk, the object
+//     chunks stream behind the compute of the previous pair;
+//   * a thread owns 4 consecutive frames: the swizzle makes its five LDS.128 box reads
+//     bank-conflict free, and every channel leaves as one 128-bit streaming store
+//     (a warp writes 512 contiguous bytes per channel row);
+//   * intersection volumes accumulate in fp64 (exact for integer boxes -> the result does
+//     not depend on the reduction order), warp-shuffle reduced over frames, combined across
+//     chunks in a fixed order;
+//   * per-tracklet volumes come from a small pre-kernel (one warp per tracklet).
+// Algorithmic bytes: 32*Tp written + 24 B of reductions per pair; boxes are re-read from L2.
+#include "common.cuh"
+
+namespace tspn {
+
+constexpr int GEO_THREADS = 128;
+constexpr int GEO_FPT = 4;
+constexpr int GEO_CHUNK = GEO_THREADS * GEO_FPT;      // 512 frames per step
+constexpr int GEO_ROWS = GEO_CHUNK / 8 + 1;           // 64 rows of 8 boxes + 1 halo row
+constexpr int GEO_TX_BYTES = GEO_ROWS * 128;          // 8320 bytes per TMA box
+constexpr int GEO_STAGE_BYTES = 9216;                 // rounded up to the 1024-B swizzle atom
+constexpr int GEO_OG = TSPN_GEO_OBJ_GROUP;
+constexpr int GEO_WARPS = GEO_THREADS / 32;
+constexpr int GEO_SMEM_BYTES = 4 * GEO_STAGE_BYTES + 1024;
+
+// box j of a chunk staged with SWIZZLE_128B: row r = j/8 (128 B), 16-byte slot (j%8) ^ (r%8)
+__device__ __forceinline__ float4 ld_box(const uint8_t* stage, int j) {
+    const int r = j >> 3;
+    const int c = (j & 7) ^ (r & 7);
+    return *reinterpret_cast<const float4*>(stage + (r << 7) + (c << 4));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+// ---- per-tracklet volume: sum over [pstart, pend) of w*h, fp64 ---------------------------------
+__global__ void __launch_bounds__(128) tracklet_volume_kernel(const int64_t* __restrict__ table, int nv,
+                                                              int64_t total_tracklets,
+                                                              const float4* __restrict__ boxes,
+                                                              const int32_t* __restrict__ span,
+                                                              double* __restrict__ vol) {
+    const int64_t trk = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (trk >= total_tracklets) return;
+    const int lane = threadIdx.x & 31;
+    const int v = find_video(table, nv, TSPN_VT_TRK_OFF, trk);
+    const int64_t* row = table + (int64_t)v * TSPN_VT_COLS;
+    const int64_t n_local = trk - row[TSPN_VT_TRK_OFF];
+    const float4* b = boxes + row[TSPN_VT_BOX_OFF] + n_local * row[TSPN_VT_TB];
+    const int ps = span[2 * trk], pe = span[2 * trk + 1];
+    double acc = 0.0;
+    for (int t = ps + lane; t < pe; t += 32) {
+        const float4 q = __ldg(b + t);
+        acc += (double)(((q.z - q.x) + 1.0f) * ((q.w - q.y) + 1.0f));
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) vol[trk] = acc;
+}
+
+// ---- the pair kernel ----------------------------------------------------------------------------
+template <bool WRITE_GEO, bool CLIP>
+__global__ void __launch_bounds__(GEO_THREADS)
+pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __restrict__ table, int nv,
+                const int32_t* __restrict__ span, const double* __restrict__ vol, float* __restrict__ geo,
+                float* __restrict__ viou, float* __restrict__ tiou, int32_t* __restrict__ overlap) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* const s_stage0 = smem;
+    uint8_t* const o_stage0 = smem + 2 * GEO_STAGE_BYTES;
+    uint64_t* const bar = reinterpret_cast<uint64_t*>(smem + 4 * GEO_STAGE_BYTES);            // [2]
+    double* const warp_part = reinterpret_cast<double*>(smem + 4 * GEO_STAGE_BYTES + 64);     // [2][WARPS][3]
+    double* const acc = warp_part + 2 * GEO_WARPS * 3;                                        // [OG][3]
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+
+    // ---- decode the work item ------------------------------------------------------------------
+    const int64_t item = blockIdx.x;
+    const int v = find_video(table, nv, TSPN_VT_ITEM_OFF, item);
+    const int64_t* row = table + (int64_t)v * TSPN_VT_COLS;
+    const int n = (int)row[TSPN_VT_N];
+    const int t_len = (int)row[TSPN_VT_T];
+    const int tp = (int)row[TSPN_VT_TP];
+    const int64_t tb = row[TSPN_VT_TB];
+    const int64_t trk_off = row[TSPN_VT_TRK_OFF];
+    const int groups = (n - 1 + GEO_OG - 1) / GEO_OG;
+    const int local = (int)(item - row[TSPN_VT_ITEM_OFF]);
+    const int s = local / groups;
+    const int k0 = (local - s * groups) * GEO_OG;
+    const int nobj = min(GEO_OG, n - 1 - k0);
+    const int nchunks = (t_len + GEO_CHUNK - 1) / GEO_CHUNK;
+    const int steps = nchunks * nobj;
+    const int64_t box_row0 = row[TSPN_VT_BOX_OFF];           // multiple of 8
+    const int64_t pair0 = row[TSPN_VT_PAIR_OFF] + (int64_t)s * (n - 1) + k0;
+    const int ps = __ldg(span + 2 * (trk_off + s)), pe = __ldg(span + 2 * (trk_off + s) + 1);
+
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        fence_mbar_init();
+    }
+    if (tid < GEO_OG * 3) acc[tid] = 0.0;
+    __syncthreads();
+
+    auto issue = [&](int q) {
+        const int c = q / nobj;
+        const int jj = q - c * nobj;
+        const int k = k0 + jj;
+        const int o = k + (k >= s ? 1 : 0);
+        const int st = q & 1;
+        mbar_expect_tx(&bar[st], jj == 0 ? 2 * GEO_TX_BYTES : GEO_TX_BYTES);
+        if (jj == 0)
+            tma_load_2d(s_stage0 + (c & 1) * GEO_STAGE_BYTES, &box_map, 0,
+                        (int)((box_row0 + (int64_t)s * tb + (int64_t)c * GEO_CHUNK) >> 3), &bar[st]);
+        tma_load_2d(o_stage0 + st * GEO_STAGE_BYTES, &box_map, 0,
+                    (int)((box_row0 + (int64_t)o * tb + (int64_t)c * GEO_CHUNK) >> 3), &bar[st]);
+    };
+    if (tid == 0) issue(0);
+
+    for (int q = 0; q < steps; ++q) {
+        const int c = q / nobj;
+        const int jj = q - c * nobj;
+        const int k = k0 + jj;
+        const int o = k + (k >= s ? 1 : 0);
+        if (tid == 0 && q + 1 < steps) issue(q + 1);
+
+        const int qs = __ldg(span + 2 * (trk_off + o)), qe = __ldg(span + 2 * (trk_off + o) + 1);
+        const int a = max(ps, qs), b = min(pe, qe);          // overlap window [a, b)
+        const int t0 = c * GEO_CHUNK + tid * GEO_FPT;        // first frame of this thread
+        const int j0 = tid * GEO_FPT;                        // ... inside the staged chunk
+
+        mbar_wait(&bar[q & 1], (q >> 1) & 1);
+
+        double sum_i = 0.0, sum_s = 0.0, sum_o = 0.0;
+        float out[TSPN_GEO_CHANNELS][GEO_FPT];
+#pragma unroll
+        for (int ch = 0; ch < TSPN_GEO_CHANNELS; ++ch)
+#pragma unroll
+            for (int i = 0; i < GEO_FPT; ++i) out[ch][i] = 0.0f;
+
+        if (t0 < b && t0 + GEO_FPT > a) {
+            const uint8_t* ss = s_stage0 + (c & 1) * GEO_STAGE_BYTES;
+            const uint8_t* os = o_stage0 + (q & 1) * GEO_STAGE_BYTES;
+            float dcx[GEO_FPT + 1], dcy[GEO_FPT + 1], wo[GEO_FPT + 1], ho[GEO_FPT + 1];
+            float rwo[GEO_FPT + 1], rho[GEO_FPT + 1];
+#pragma unroll
+            for (int i = 0; i <= GEO_FPT; ++i) {
+                const float4 sb = ld_box(ss, j0 + i);
+                const float4 ob = ld_box(os, j0 + i);
+                const float ws = (sb.z - sb.x) + 1.0f, hs = (sb.w - sb.y) + 1.0f;
+                wo[i] = (ob.z - ob.x) + 1.0f;
+                ho[i] = (ob.w - ob.y) + 1.0f;
+                rwo[i] = __frcp_rn(wo[i]);
+                rho[i] = __frcp_rn(ho[i]);
+                // centre deltas from coordinate differences: exact for integer boxes and
+                // free of the cancellation that (x1+x2)/2 - (x1'+x2')/2 would carry
+                dcx[i] = 0.5f * ((sb.x - ob.x) + (sb.z - ob.z));
+                dcy[i] = 0.5f * ((sb.y - ob.y) + (sb.w - ob.w));
+                if (i < GEO_FPT) {
+                    const int t = t0 + i;
+                    const bool in = (t >= a) && (t < b);
+                    const float iw = fmaxf((fminf(sb.z, ob.z) - fmaxf(sb.x, ob.x)) + 1.0f, 0.0f);
+                    const float ih = fmaxf((fminf(sb.w, ob.w) - fmaxf(sb.y, ob.y)) + 1.0f, 0.0f);
+                    const float inter = iw * ih;
+                    const float as = ws * hs, ao = wo[i] * ho[i];
+                    if (in) {
+                        out[0][i] = dcx[i] * rwo[i];
+                        out[1][i] = dcy[i] * rho[i];
+                        out[2][i] = log1pf((ws - wo[i]) * rwo[i]);
+                        out[3][i] = log1pf((hs - ho[i]) * rho[i]);
+                        out[4][i] = inter / ((as + ao) - inter);
+                        out[7][i] = 1.0f;
+                        sum_i += (double)inter;
+                        if (CLIP) {
+                            sum_s += (double)as;
+                            sum_o += (double)ao;
+                        }
+                    }
+                }
+            }
+            // forward differences in closed form:
+            //   c0[t+1]-c0[t] = (dcx[t+1]*wo[t] - dcx[t]*wo[t+1]) / (wo[t]*wo[t+1])
+            // (two-product compensation keeps the numerator exact to one rounding)
+#pragma unroll
+            for (int i = 0; i < GEO_FPT; ++i) {
+                const int t = t0 + i;
+                if (t >= a && t + 1 < b) {
+                    float p = dcx[i] * wo[i + 1];
+                    float e = fmaf(dcx[i], wo[i + 1], -p);
+                    out[5][i] = (fmaf(dcx[i + 1], wo[i], -p) - e) * (rwo[i] * rwo[i + 1]);
+                    p = dcy[i] * ho[i + 1];
+                    e = fmaf(dcy[i], ho[i + 1], -p);
+                    out[6][i] = (fmaf(dcy[i + 1], ho[i], -p) - e) * (rho[i] * rho[i + 1]);
+                }
+            }
+        }
+        if (WRITE_GEO && t0 < tp) {
+            float* g = geo + row[TSPN_VT_GEO_OFF] + ((int64_t)(s * (n - 1) + k) * TSPN_GEO_CHANNELS) * tp + t0;
+#pragma unroll
+            for (int ch = 0; ch < TSPN_GEO_CHANNELS; ++ch)
+                st_stream_f4(g + (int64_t)ch * tp, make_float4(out[ch][0], out[ch][1], out[ch][2], out[ch][3]));
+        }
+        // reduce the three volume sums over the chunk's frames
+        sum_i = warp_sum(sum_i);
+        if (CLIP) {
+            sum_s = warp_sum(sum_s);
+            sum_o = warp_sum(sum_o);
+        }
+        if (lane == 0) {
+            double* wp = warp_part + ((q & 1) * GEO_WARPS + warp) * 3;
+            wp[0] = sum_i;
+            wp[1] = sum_s;
+            wp[2] = sum_o;
+        }
+        __syncthreads();   // stage (q&1) may be refilled; warp_part[q&1] is complete
+        if (tid < 3) {
+            double tot = 0.0;
+#pragma unroll
+            for (int w = 0; w < GEO_WARPS; ++w) tot += warp_part[((q & 1) * GEO_WARPS + w) * 3 + tid];
+            acc[jj * 3 + tid] += tot;
+        }
+    }
+    __syncthreads();
+
+    // ---- per-pair reductions: vIoU, tIoU, overlap window ------------------------------------------
+    if (tid < nobj) {
+        const int k = k0 + tid;
+        const int o = k + (k >= s ? 1 : 0);
+        const int qs = __ldg(span + 2 * (trk_off + o)), qe = __ldg(span + 2 * (trk_off + o) + 1);
+        const int a = max(ps, qs), b = min(pe, qe);
+        const bool has = b > a;
+        const double inter = acc[tid * 3 + 0];
+        const double vs = CLIP ? acc[tid * 3 + 1] : vol[trk_off + s];
+        const double vo = CLIP ? acc[tid * 3 + 2] : vol[trk_off + o];
+        const double den = vs + vo - inter;
+        const int ov = has ? b - a : 0;
+        const int tden = (pe - ps) + (qe - qs) - ov;
+        const int64_t p = pair0 + tid;
+        viou[p] = (has && den > 0.0) ? (float)(inter / den) : 0.0f;
+        tiou[p] = (has && tden > 0) ? (float)((double)ov / (double)tden) : 0.0f;
+        overlap[2 * p] = has ? a : 0;
+        overlap[2 * p + 1] = has ? b : 0;
+    }
+}
+
+// ---- cubic_iou(bboxes1, bboxes2): one warp per matrix entry -------------------------------------
+__global__ void __launch_bounds__(128) cubic_iou_kernel(const float4* __restrict__ b1, int n1,
+                                                        const float4* __restrict__ b2, int n2, int t,
+                                                        float* __restrict__ out) {
+    const int64_t e = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (e >= (int64_t)n1 * n2) return;
+    const int lane = threadIdx.x & 31;
+    const int i = (int)(e / n2), j = (int)(e - (int64_t)i * n2);
+    const float4* p = b1 + (int64_t)i * t;
+    const float4* q = b2 + (int64_t)j * t;
+    double si = 0.0, sa = 0.0, sb = 0.0;
+    for (int f = lane; f < t; f += 32) {
+        const float4 x = __ldg(p + f), y = __ldg(q + f);
+        const float iw = fmaxf((fminf(x.z, y.z) - fmaxf(x.x, y.x)) + 1.0f, 0.0f);
+        const float ih = fmaxf((fminf(x.w, y.w) - fmaxf(x.y, y.y)) + 1.0f, 0.0f);
+        si += (double)(iw * ih);
+        sa += (double)(((x.z - x.x) + 1.0f) * ((x.w - x.y) + 1.0f));
+        sb += (double)(((y.z - y.x) + 1.0f) * ((y.w - y.y) + 1.0f));
+    }
+    si = warp_sum(si);
+    sa = warp_sum(sa);
+    sb = warp_sum(sb);
+    if (lane == 0) out[e] = (float)(si / (sa + sb - si));
+}
+
+// ---- viou over an explicit pair list (evaluation / association use) --------------------------------
+template <bool CLIP>
+__global__ void __launch_bounds__(128) viou_pairs_kernel(const float4* __restrict__ pool,
+                                                         const int64_t* __restrict__ traj_off,
+                                                         const int32_t* __restrict__ traj_span,
+                                                         const int32_t* __restrict__ ia,
+                                                         const int32_t* __restrict__ ib, int64_t n_pairs,
+                                                         float* __restrict__ out) {
+    const int64_t e = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (e >= n_pairs) return;
+    const int lane = threadIdx.x & 31;
+    const int i = ia[e], j = ib[e];
+    const int s1 = traj_span[2 * i], e1 = traj_span[2 * i + 1];
+    const int s2 = traj_span[2 * j], e2 = traj_span[2 * j + 1];
+    const float4* p = pool + traj_off[i];
+    const float4* q = pool + traj_off[j];
+    const int a = max(s1, s2), b = min(e1, e2);
+    double si = 0.0, sa = 0.0, sb = 0.0;
+    for (int f = a + lane; f < b; f += 32) {
+        const float4 x = __ldg(p + (f - s1)), y = __ldg(q + (f - s2));
+        const float iw = fmaxf((fminf(x.z, y.z) - fmaxf(x.x, y.x)) + 1.0f, 0.0f);
+        const float ih = fmaxf((fminf(x.w, y.w) - fmaxf(x.y, y.y)) + 1.0f, 0.0f);
+        si += (double)(iw * ih);
+        if (CLIP) {
+            sa += (double)(((x.z - x.x) + 1.0f) * ((x.w - x.y) + 1.0f));
+            sb += (double)(((y.z - y.x) + 1.0f) * ((y.w - y.y) + 1.0f));
+        }
+    }
+    if (!CLIP) {
+        for (int f = lane; f < e1 - s1; f += 32) {
+            const float4 x = __ldg(p + f);
+            sa += (double)(((x.z - x.x) + 1.0f) * ((x.w - x.y) + 1.0f));
+        }
+        for (int f = lane; f < e2 - s2; f += 32) {
+            const float4 y = __ldg(q + f);
+            sb += (double)(((y.z - y.x) + 1.0f) * ((y.w - y.y) + 1.0f));
+        }
+    }
+    si = warp_sum(si);
+    sa = warp_sum(sa);
+    sb = warp_sum(sb);
+    if (lane == 0) {
+        const double den = sa + sb - si;
+        out[e] = (b > a && den > 0.0) ? (float)(si / den) : 0.0f;
+    }
+}
+
+// ---- pair enumeration ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) enumerate_pairs_kernel(const int64_t* __restrict__ table, int nv,
+                                                              int64_t total_pairs, int64_t* __restrict__ pairs) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= total_pairs) return;
+    const int v = find_video(table, nv, TSPN_VT_PAIR_OFF, p);
+    const int64_t* row = table + (int64_t)v * TSPN_VT_COLS;
+    const int64_t n1 = row[TSPN_VT_N] - 1;
+    const int64_t loc = p - row[TSPN_VT_PAIR_OFF];
+    const int64_t s = loc / n1, k = loc - s * n1;
+    pairs[2 * p] = s;
+    pairs[2 * p + 1] = k + (k >= s ? 1 : 0);
+}
+
+}  // namespace tspn
+
+using namespace tspn;
+
+extern "C" {
+
+int tspn_enumerate_pairs(const int64_t* d_table, int num_videos, int64_t total_pairs, int64_t* d_pairs,
+                         void* stream) {
+    TSPN_ARCH_OK();
+    TSPN_REQUIRE(total_pairs >= 0 && num_videos >= 0, TSPN_EBADARG, "tspn_enumerate_pairs: negative size");
+    if (total_pairs == 0) return TSPN_OK;
+    TSPN_REQUIRE(d_table && d_pairs, TSPN_EBADARG, "tspn_enumerate_pairs: null pointer");
+    const int64_t blocks = (total_pairs + 255) / 256;
+    enumerate_pairs_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_table, num_videos, total_pairs,
+                                                                               d_pairs);
+    TSPN_CUDA_OK(cudaGetLastError());
+    return TSPN_OK;
+}
+
+int64_t tspn_pair_geo_workspace_bytes(int64_t total_tracklets) {
+    return (total_tracklets > 0 ? total_tracklets : 1) * (int64_t)sizeof(double);
+}
+
+int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_items, int64_t total_tracklets,
+                       int64_t total_boxes, const float* d_boxes, const int32_t* d_span, float* d_geo,
+                       float* d_viou, float* d_tiou, int32_t* d_overlap, int flags, void* d_workspace,
+                       void* stream) {
+    TSPN_ARCH_OK();
+    TSPN_REQUIRE(num_videos >= 0 && total_items >= 0 && total_tracklets >= 0 && total_boxes >= 0, TSPN_EBADARG,
+                 "tspn_pair_geo_viou: negative size");
+    if (total_items == 0) return TSPN_OK;
+    TSPN_REQUIRE(d_table && d_boxes && d_span && d_viou && d_tiou && d_overlap && d_workspace, TSPN_EBADARG,
+                 "tspn_pair_geo_viou: null pointer");
+    TSPN_REQUIRE(aligned16(d_boxes) && aligned16(d_geo) && aligned16(d_workspace), TSPN_EALIGN,
+                 "tspn_pair_geo_viou: boxes/geo/workspace must be 16-byte aligned");
+    TSPN_REQUIRE((total_boxes & 7) == 0, TSPN_ESHAPE,
+                 "tspn_pair_geo_viou: total_boxes (%lld) must be a multiple of 8 (rows padded to Tb)",
+                 (long long)total_boxes);
+    TSPN_REQUIRE(total_items < (1ll << 31), TSPN_ESHAPE, "tspn_pair_geo_viou: too many work items");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* vol = reinterpret_cast<double*>(d_workspace);
+    const bool clip = (flags & TSPN_VIOU_CLIPPED) != 0;
+    if (!clip) {
+        tracklet_volume_kernel<<<(unsigned)((total_tracklets + 3) / 4), 128, 0, st>>>(
+            d_table, num_videos, total_tracklets, reinterpret_cast<const float4*>(d_boxes), d_span, vol);
+        TSPN_CUDA_OK(cudaGetLastError());
+    }
+    // boxes viewed as a 2-D tensor: rows of 8 boxes (32 floats = 128 B)
+    CUtensorMap map;
+    const uint64_t dims[2] = {32, (uint64_t)(total_boxes / 8)};
+    const uint64_t strides[1] = {128};
+    const uint32_t box[2] = {32, (uint32_t)GEO_ROWS};
+    int rc = encode_tensor_map(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d_boxes, dims, strides, box,
+                               CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != TSPN_OK) return rc;
+
+#define TSPN_LAUNCH_GEO(W, C)                                                                              \
+    do {                                                                                                   \
+        TSPN_CUDA_OK(cudaFuncSetAttribute(pair_geo_kernel<W, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          GEO_SMEM_BYTES));                                                \
+        pair_geo_kernel<W, C><<<(unsigned)total_items, GEO_THREADS, GEO_SMEM_BYTES, st>>>(                 \
+            map, d_table, num_videos, d_span, vol, d_geo, d_viou, d_tiou, d_overlap);                      \
+    } while (0)
+    if (d_geo) {
+        if (clip) TSPN_LAUNCH_GEO(true, true); else TSPN_LAUNCH_GEO(true, false);
+    } else {
+        if (clip) TSPN_LAUNCH_GEO(false, true); else TSPN_LAUNCH_GEO(false, false);
+    }
+#undef TSPN_LAUNCH_GEO
+    TSPN_CUDA_OK(cudaGetLastError());
+    return TSPN_OK;
+}
+
+int tspn_cubic_iou(const float* d_b1, int n1, const float* d_b2, int n2, int t, float* d_out, void* stream) {
+    TSPN_ARCH_OK();
+    TSPN_REQUIRE(n1 >= 0 && n2 >= 0 && t >= 0, TSPN_EBADARG, "tspn_cubic_iou: negative size");
+    if ((int64_t)n1 * n2 == 0) return TSPN_OK;
+    TSPN_REQUIRE(d_b1 && d_b2 && d_out, TSPN_EBADARG, "tspn_cubic_iou: null pointer");
+    TSPN_REQUIRE(aligned16(d_b1) && aligned16(d_b2), TSPN_EALIGN, "tspn_cubic_iou: boxes must be 16-byte aligned");
+    const int64_t entries = (int64_t)n1 * n2;
+    cubic_iou_kernel<<<(unsigned)((entries + 3) / 4), 128, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(d_b1), n1, reinterpret_cast<const float4*>(d_b2), n2, t, d_out);
+    TSPN_CUDA_OK(cudaGetLastError());
+    return TSPN_OK;
+}
+
+int tspn_viou_pairs(const float* d_pool, const int64_t* d_traj_off, const int32_t* d_traj_span, const int32_t* d_a,
+                    const int32_t* d_b, int64_t n_pairs, int flags, float* d_out, void* stream) {
+    TSPN_ARCH_OK();
+    TSPN_REQUIRE(n_pairs >= 0, TSPN_EBADARG, "tspn_viou_pairs: negative size");
+    if (n_pairs == 0) return TSPN_OK;
+    TSPN_REQUIRE(d_pool && d_traj_off && d_traj_span && d_a && d_b && d_out, TSPN_EBADARG,
+                 "tspn_viou_pairs: null pointer");
+    TSPN_REQUIRE(aligned16(d_pool), TSPN_EALIGN, "tspn_viou_pairs: pool must be 16-byte aligned");
+    const unsigned blocks = (unsigned)((n_pairs + 3) / 4);
+    if (flags & TSPN_VIOU_CLIPPED)
+        viou_pairs_kernel<true><<<blocks, 128, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const float4*>(d_pool), d_traj_off, d_traj_span, d_a, d_b, n_pairs, d_out);
+    else
+        viou_pairs_kernel<false><<<blocks, 128, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const float4*>(d_pool), d_traj_off, d_traj_span, d_a, d_b, n_pairs, d_out);
+    TSPN_CUDA_OK(cudaGetLastError());
+    return TSPN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,266 @@
+// relationness.cu — PPNHead scores of every ordered pair and their top-K selection.
+//
+//   tspn_relationness   PPNHead.forward           lib/modeling/relpn/ppn.py:92-112
+//   tspn_topk_pairs     PPN._forward_test sort    lib/modeling/relpn/ppn.py:79-90
+//
+// Arithmetic is the fixed-order fp32 definition of DESIGN.md ("exact-order arithmetic"):
+// every linear layer is a k-ascending fma chain starting from the bias, the pair score is a
+// c-ascending fma chain from 0, the sigmoid is 1/(1+exp_det(-z)) with an exp made of
+// fma/mul/add/rint only — so the scores, and with them the top-K selection, are
+// bit-reproducible (and bit-identical to oracle/exact).  The problem is tiny (<= 21 MFLOP at
+// N=256): latency-bound, not tensor-bound; it never approaches either roofline.
+//
+// Top-K is a block-level MSD radix select (8-bit digits on the order-preserving uint32 image
+// of the score, warp-aggregated histograms) followed by an ordered compaction of the ties and
+// a bitonic sort of the K survivors: descending score, ties to the lower flat index
+// ([SPEC] s6 == torch.sort(stable=True)).
+#include "common.cuh"
+#include "exact_math.cuh"
+
+namespace tspn {
+
+// ---- embeddings: S = W2s relu(W1s x + b1s) + b2s, O likewise ---------------------------------------
+// one CTA per tracklet; threads [0,H) do the subject branch hidden units, [H,2H) the object's.
+__global__ void __launch_bounds__(128)
+ppn_embed_kernel(const float* __restrict__ cls, int C, int H, const float* __restrict__ sw0,
+                 const float* __restrict__ sb0, const float* __restrict__ sw2, const float* __restrict__ sb2,
+                 const float* __restrict__ ow0, const float* __restrict__ ob0, const float* __restrict__ ow2,
+                 const float* __restrict__ ob2, float* __restrict__ S, float* __restrict__ O) {
+    extern __shared__ float sm[];
+    float* x = sm;            // [C]
+    float* hid = sm + C;      // [2][H]
+    const int64_t trk = blockIdx.x;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) x[i] = cls[trk * C + i];
+    __syncthreads();
+    for (int u = threadIdx.x; u < 2 * H; u += blockDim.x) {
+        const int br = u / H, j = u - br * H;
+        const float* w = (br ? ow0 : sw0) + (int64_t)j * C;
+        float acc = (br ? ob0 : sb0)[j];
+        for (int i = 0; i < C; ++i) acc = __fmaf_rn(x[i], __ldg(w + i), acc);
+        hid[u] = fmaxf(acc, 0.0f);
+    }
+    __syncthreads();
+    for (int u = threadIdx.x; u < 2 * C; u += blockDim.x) {
+        const int br = u / C, c = u - br * C;
+        const float* w = (br ? ow2 : sw2) + (int64_t)c * H;
+        const float* h = hid + br * H;
+        float acc = (br ? ob2 : sb2)[c];
+        for (int j = 0; j < H; ++j) acc = __fmaf_rn(h[j], __ldg(w + j), acc);
+        (br ? O : S)[trk * C + c] = acc;
+    }
+}
+
+// ---- scores: M[s][o] = sigmoid(sum_c S[s][c] O[o][c]); one CTA per subject row ---------------------
+__global__ void __launch_bounds__(128)
+pair_scores_kernel(const int64_t* __restrict__ table, int nv, const float* __restrict__ S,
+                   const float* __restrict__ O, int C, float* __restrict__ scores) {
+    extern __shared__ float srow[];     // [C]
+    const int64_t trk = blockIdx.x;
+    const int v = find_video(table, nv, TSPN_VT_TRK_OFF, trk);
+    const int64_t* row = table + (int64_t)v * TSPN_VT_COLS;
+    const int n = (int)row[TSPN_VT_N];
+    const int64_t trk0 = row[TSPN_VT_TRK_OFF];
+    const int s = (int)(trk - trk0);
+    for (int i = threadIdx.x; i < C; i += blockDim.x) srow[i] = S[trk * C + i];
+    __syncthreads();
+    float* out = scores + row[TSPN_VT_SCORE_OFF] + (int64_t)s * n;
+    for (int o = threadIdx.x; o < n; o += blockDim.x) {
+        const float* orow = O + (trk0 + o) * C;
+        float z = 0.0f;
+        for (int c = 0; c < C; ++c) z = __fmaf_rn(srow[c], __ldg(orow + c), z);
+        out[o] = sigmoid_det(z);
+    }
+}
+
+// ---- top-K ---------------------------------------------------------------------------------------
+constexpr int TOPK_THREADS = 256;
+constexpr int TOPK_MAX_K = 1024;
+
+__device__ __forceinline__ uint32_t order_key(float f) {
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);      // larger float <=> larger key
+}
+
+__global__ void __launch_bounds__(TOPK_THREADS)
+topk_kernel(const int64_t* __restrict__ table, int nv, const float* __restrict__ scores, int K, int exclude_diag,
+            int64_t* __restrict__ out_idx, float* __restrict__ out_score, int64_t* __restrict__ out_row) {
+    __shared__ uint32_t hist[256];
+    __shared__ uint64_t sel[TOPK_MAX_K];
+    __shared__ uint32_t sh_prefix, sh_need, sh_count, sh_tie_base;
+    __shared__ uint32_t warp_cnt[TOPK_THREADS / 32];
+
+    const int v = blockIdx.x;
+    const int64_t* row = table + (int64_t)v * TSPN_VT_COLS;
+    const int n = (int)row[TSPN_VT_N];
+    const int64_t total = (int64_t)n * n;
+    const float* sc = scores + row[TSPN_VT_SCORE_OFF];
+    const int64_t cand = exclude_diag ? total - n : total;
+    const int k_eff = (int)min((int64_t)K, cand);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    int64_t* oi = out_idx + (int64_t)v * K;
+    float* os = out_score + (int64_t)v * K;
+    int64_t* orow = out_row ? out_row + (int64_t)v * K : nullptr;
+    for (int i = k_eff + tid; i < K; i += TOPK_THREADS) {
+        oi[i] = -1;
+        os[i] = 0.0f;
+        if (orow) orow[i] = -1;
+    }
+    if (k_eff == 0) return;
+
+    // -- MSD radix select: find the key of the k_eff-th largest candidate -------------------------
+    if (tid == 0) {
+        sh_prefix = 0;
+        sh_need = (uint32_t)k_eff;      // rank (1-based, from the top) still to locate
+    }
+    uint32_t prefix_mask = 0;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        hist[tid] = 0;                  // TOPK_THREADS == 256 bins
+        __syncthreads();
+        const uint32_t prefix = sh_prefix;
+        for (int64_t i = tid; i < total; i += TOPK_THREADS) {
+            if (exclude_diag && (i / n) == (i % n)) continue;
+            const uint32_t key = order_key(__ldg(sc + i));
+            if ((key & prefix_mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xffu], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t need = sh_need, d = 255;
+            for (;; --d) {              // walk the buckets from the top
+                const uint32_t c = hist[d];
+                if (c >= need) break;
+                need -= c;
+                if (d == 0) break;
+            }
+            sh_need = need;             // rank inside bucket d
+            sh_prefix = prefix | (d << shift);
+        }
+        prefix_mask |= 0xffu << shift;
+        __syncthreads();
+    }
+    const uint32_t thr = sh_prefix;     // key of the k_eff-th largest
+    const uint32_t need_ties = sh_need; // how many candidates with key == thr are kept
+    if (tid == 0) {
+        sh_count = 0;
+        sh_tie_base = 0;
+    }
+    __syncthreads();
+
+    // -- collect: everything above the threshold (any order), then the ties in index order -----------
+    const uint32_t n_above = (uint32_t)k_eff - need_ties;
+    for (int64_t base = 0; base < total; base += TOPK_THREADS) {
+        const int64_t i = base + tid;
+        bool above = false, tie = false;
+        uint32_t key = 0;
+        if (i < total && !(exclude_diag && (i / n) == (i % n))) {
+            key = order_key(__ldg(sc + i));
+            above = key > thr;
+            tie = key == thr;
+        }
+        if (above) {
+            const uint32_t slot = atomicAdd(&sh_count, 1u);
+            sel[slot] = ((uint64_t)(~key) << 32) | (uint32_t)i;
+        }
+        // ordered compaction of the ties: rank = ties with a lower flat index
+        const uint32_t bal = __ballot_sync(0xffffffffu, tie);
+        if (lane == 0) warp_cnt[warp] = __popc(bal);
+        __syncthreads();
+        uint32_t before = sh_tie_base;
+        for (int w = 0; w < warp; ++w) before += warp_cnt[w];
+        const uint32_t rank = before + __popc(bal & ((1u << lane) - 1u));
+        if (tie && rank < need_ties) sel[n_above + rank] = ((uint64_t)(~key) << 32) | (uint32_t)i;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t t = 0;
+            for (int w = 0; w < TOPK_THREADS / 32; ++w) t += warp_cnt[w];
+            sh_tie_base += t;
+        }
+        __syncthreads();
+    }
+
+    // -- bitonic sort of the survivors: ascending (~key, idx) == descending score, ascending index ----
+    int m = 1;
+    while (m < k_eff) m <<= 1;
+    for (int i = k_eff + tid; i < m; i += TOPK_THREADS) sel[i] = ~0ull;
+    __syncthreads();
+    for (int size = 2; size <= m; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = tid; i < m / 2; i += TOPK_THREADS) {
+                const int lo = 2 * i - (i & (stride - 1));
+                const int hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const uint64_t a = sel[lo], b = sel[hi];
+                if ((a > b) == up) {
+                    sel[lo] = b;
+                    sel[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < k_eff; i += TOPK_THREADS) {
+        const uint32_t flat = (uint32_t)(sel[i] & 0xffffffffu);
+        oi[i] = (int64_t)flat;
+        os[i] = __ldg(sc + flat);
+        if (orow) {
+            const int s = (int)(flat / (uint32_t)n), o = (int)(flat % (uint32_t)n);
+            orow[i] = (s == o) ? -1 : row[TSPN_VT_PAIR_OFF] + (int64_t)s * (n - 1) + o - (o > s ? 1 : 0);
+        }
+    }
+}
+
+}  // namespace tspn
+
+using namespace tspn;
+
+extern "C" {
+
+int64_t tspn_relationness_workspace_bytes(int64_t total_tracklets, int n_classes, int hidden) {
+    (void)hidden;
+    const int64_t t = total_tracklets > 0 ? total_tracklets : 1;
+    return 2 * t * (int64_t)n_classes * (int64_t)sizeof(float);
+}
+
+int tspn_relationness(const int64_t* d_table, int num_videos, int64_t total_tracklets, const float* d_cls,
+                      int n_classes, int hidden, const float* d_sub_w0, const float* d_sub_b0,
+                      const float* d_sub_w2, const float* d_sub_b2, const float* d_obj_w0, const float* d_obj_b0,
+                      const float* d_obj_w2, const float* d_obj_b2, float* d_scores, void* d_workspace,
+                      void* stream) {
+    TSPN_ARCH_OK();
+    TSPN_REQUIRE(num_videos >= 0 && total_tracklets >= 0 && n_classes > 0 && hidden > 0, TSPN_EBADARG,
+                 "tspn_relationness: bad size");
+    if (total_tracklets == 0) return TSPN_OK;
+    TSPN_REQUIRE(d_table && d_cls && d_sub_w0 && d_sub_b0 && d_sub_w2 && d_sub_b2 && d_obj_w0 && d_obj_b0 &&
+                     d_obj_w2 && d_obj_b2 && d_scores && d_workspace,
+                 TSPN_EBADARG, "tspn_relationness: null pointer");
+    TSPN_REQUIRE(n_classes <= 4096 && hidden <= 4096, TSPN_ESHAPE, "tspn_relationness: C/H too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* S = reinterpret_cast<float*>(d_workspace);
+    float* O = S + total_tracklets * n_classes;
+    const size_t sm1 = (size_t)(n_classes + 2 * hidden) * sizeof(float);
+    ppn_embed_kernel<<<(unsigned)total_tracklets, 128, sm1, st>>>(d_cls, n_classes, hidden, d_sub_w0, d_sub_b0,
+                                                                  d_sub_w2, d_sub_b2, d_obj_w0, d_obj_b0, d_obj_w2,
+                                                                  d_obj_b2, S, O);
+    TSPN_CUDA_OK(cudaGetLastError());
+    pair_scores_kernel<<<(unsigned)total_tracklets, 128, (size_t)n_classes * sizeof(float), st>>>(
+        d_table, num_videos, S, O, n_classes, d_scores);
+    TSPN_CUDA_OK(cudaGetLastError());
+    return TSPN_OK;
+}
+
+int tspn_topk_pairs(const int64_t* d_table, int num_videos, const float* d_scores, int k, int flags,
+                    int64_t* d_topk_idx, float* d_topk_score, int64_t* d_topk_row, void* stream) {
+    TSPN_ARCH_OK();
+    TSPN_REQUIRE(num_videos >= 0 && k >= 0, TSPN_EBADARG, "tspn_topk_pairs: negative size");
+    TSPN_REQUIRE(k <= TOPK_MAX_K, TSPN_ESHAPE, "tspn_topk_pairs: K=%d exceeds the supported maximum %d", k,
+                 TOPK_MAX_K);
+    if (num_videos == 0 || k == 0) return TSPN_OK;
+    TSPN_REQUIRE(d_table && d_scores && d_topk_idx && d_topk_score, TSPN_EBADARG, "tspn_topk_pairs: null pointer");
+    topk_kernel<<<(unsigned)num_videos, TOPK_THREADS, 0, (cudaStream_t)stream>>>(
+        d_table, num_videos, d_scores, k, (flags & TSPN_TOPK_EXCLUDE_DIAGONAL) ? 1 : 0, d_topk_idx, d_topk_score,
+        d_topk_row);
+    TSPN_CUDA_OK(cudaGetLastError());
+    return TSPN_OK;
+}
+
+}  // extern "C"

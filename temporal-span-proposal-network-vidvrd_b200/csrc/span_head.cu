@@ -1,0 +1,170 @@
+// span_head.cu — temporal-span head and span decode.
+//
+//   tspn_span_head     DPNHead.forward   lib/modeling/relpn/dpn.py:55-73
+//                      Conv1d(Cin->Cin, k3, p1) -> ReLU -> Conv1d(Cin->2A, k1)
+//   tspn_span_decode   anchors of lib/modeling/relpn/anchor_generator.py:48-104 applied to the
+//                      regressions, to integer frame bounds ([SPEC] s5; DPN.forward / RelNMS are
+//                      broken / a stub in the reference, relpn/dpn.py:24-28, relpn/rel_nms.py:14-15)
+//
+// TSPN_PREC_FP32_EXACT: one thread per (pair, frame); the hidden unit h[co] is the
+// (ci ascending, tap ascending) fma chain from its bias and is folded into the 2A outputs as
+// soon as it is complete (co ascending) — exactly the order of oracle/exact, no hidden tensor
+// ever exists in memory.  TSPN_PREC_TENSOR: implicit GEMM on tcgen05 (span_head_tc.cu).
+#include "common.cuh"
+#include "exact_math.cuh"
+
+namespace tspn {
+
+int span_head_tensor(const float* d_x, const int64_t* d_rows, int64_t row_stride, int64_t ld_t, int64_t k, int cin,
+                     int t, const float* d_conv_w, const float* d_conv_b, const float* d_pred_w,
+                     const float* d_pred_b, int a2, float* d_out, void* d_workspace, cudaStream_t st);
+
+constexpr int SH_THREADS = 128;
+constexpr int SH_MAX_A2 = 16;
+constexpr int SH_REG_CIN = 16;
+
+__global__ void __launch_bounds__(SH_THREADS)
+span_head_exact_kernel(const float* __restrict__ x, const int64_t* __restrict__ rows, int64_t row_stride,
+                       int64_t ld_t, int cin, int t_len, const float* __restrict__ conv_w,
+                       const float* __restrict__ conv_b, const float* __restrict__ pred_w,
+                       const float* __restrict__ pred_b, int a2, float* __restrict__ out) {
+    const int64_t p = blockIdx.y;
+    const int t = blockIdx.x * SH_THREADS + threadIdx.x;
+    if (t >= t_len) return;
+    float* o = out + p * a2 * (int64_t)t_len + t;
+    const int64_t src = rows ? rows[p] : p;
+    if (src < 0) {
+        for (int j = 0; j < a2; ++j) o[(int64_t)j * t_len] = 0.0f;
+        return;
+    }
+    const float* xr = x + src * row_stride;
+    const bool has_m = t > 0, has_p = t + 1 < t_len;
+    float acc[SH_MAX_A2];
+#pragma unroll
+    for (int j = 0; j < SH_MAX_A2; ++j) acc[j] = (j < a2) ? (pred_b ? __ldg(pred_b + j) : 0.0f) : 0.0f;
+
+    float xm[SH_REG_CIN], x0[SH_REG_CIN], xp[SH_REG_CIN];
+    const bool cached = cin <= SH_REG_CIN;
+    if (cached) {
+#pragma unroll
+        for (int ci = 0; ci < SH_REG_CIN; ++ci) {
+            if (ci < cin) {
+                const float* xc = xr + (int64_t)ci * ld_t + t;
+                xm[ci] = has_m ? __ldg(xc - 1) : 0.0f;
+                x0[ci] = __ldg(xc);
+                xp[ci] = has_p ? __ldg(xc + 1) : 0.0f;
+            }
+        }
+    }
+    for (int co = 0; co < cin; ++co) {
+        float h = conv_b ? __ldg(conv_b + co) : 0.0f;
+        const float* w = conv_w + (int64_t)co * cin * 3;
+        if (cached) {
+#pragma unroll
+            for (int ci = 0; ci < SH_REG_CIN; ++ci) {
+                if (ci < cin) {
+                    if (has_m) h = __fmaf_rn(__ldg(w + ci * 3 + 0), xm[ci], h);
+                    h = __fmaf_rn(__ldg(w + ci * 3 + 1), x0[ci], h);
+                    if (has_p) h = __fmaf_rn(__ldg(w + ci * 3 + 2), xp[ci], h);
+                }
+            }
+        } else {
+            for (int ci = 0; ci < cin; ++ci) {
+                const float* xc = xr + (int64_t)ci * ld_t + t;
+                if (has_m) h = __fmaf_rn(__ldg(w + ci * 3 + 0), __ldg(xc - 1), h);
+                h = __fmaf_rn(__ldg(w + ci * 3 + 1), __ldg(xc), h);
+                if (has_p) h = __fmaf_rn(__ldg(w + ci * 3 + 2), __ldg(xc + 1), h);
+            }
+        }
+        h = fmaxf(h, 0.0f);
+#pragma unroll
+        for (int j = 0; j < SH_MAX_A2; ++j)
+            if (j < a2) acc[j] = __fmaf_rn(__ldg(pred_w + (int64_t)j * cin + co), h, acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < SH_MAX_A2; ++j)
+        if (j < a2) o[(int64_t)j * t_len] = acc[j];
+}
+
+// [SPEC] s5, every step one correctly rounded fp32 operation (see oracle/exact).
+__global__ void __launch_bounds__(256)
+span_decode_kernel(const float* __restrict__ reg, int64_t k, int a_n, int t_len, int n_loc,
+                   const float* __restrict__ sizes, float stride, int32_t* __restrict__ spans) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = k * n_loc * a_n;
+    if (idx >= total) return;
+    const int a = (int)(idx % a_n);
+    const int l = (int)((idx / a_n) % n_loc);
+    const int64_t p = idx / ((int64_t)a_n * n_loc);
+    const float CLAMP = 4.1351666f;                     // fp32 nearest of log(1000/16)
+    const float ac = __fmul_rn((float)l, stride);
+    int col = (int)floorf(ac);
+    col = min(col, t_len - 1);
+    const float aw = __ldg(sizes + a);
+    const float dc = __ldg(reg + (p * 2 * a_n + 2 * a) * t_len + col);
+    const float dw = fminf(__ldg(reg + (p * 2 * a_n + 2 * a + 1) * t_len + col), CLAMP);
+    const float ctr = __fmaf_rn(dc, aw, ac);
+    const float w = __fmul_rn(aw, exp_det(dw));
+    const float hw = __fmul_rn(0.5f, w);
+    float lo = floorf(__fadd_rn(__fadd_rn(ctr, -hw), 0.5f));
+    float hi = floorf(__fadd_rn(__fadd_rn(ctr, hw), 0.5f));
+    lo = fminf(fmaxf(lo, 0.0f), (float)(t_len - 1));
+    hi = fminf(fmaxf(hi, __fadd_rn(lo, 1.0f)), (float)t_len);
+    spans[2 * idx] = (int32_t)lo;
+    spans[2 * idx + 1] = (int32_t)hi;
+}
+
+}  // namespace tspn
+
+using namespace tspn;
+
+extern "C" {
+
+int tspn_span_num_locations(int t, float stride) {
+    if (t <= 0 || !(stride > 0.0f)) return 0;
+    // len(torch.arange(0, T+1, step=stride)) = ceil((T+1)/stride), anchor_generator.py:50-52
+    const double q = ((double)t + 1.0) / (double)stride;
+    int n = (int)q;
+    if ((double)n < q) ++n;
+    return n;
+}
+
+int tspn_span_head(const float* d_x, const int64_t* d_rows, int64_t row_stride, int64_t ld_t, int64_t k, int cin,
+                   int t, const float* d_conv_w, const float* d_conv_b, const float* d_pred_w,
+                   const float* d_pred_b, int a2, float* d_out, int precision, void* d_workspace, void* stream) {
+    TSPN_ARCH_OK();
+    TSPN_REQUIRE(k >= 0 && cin > 0 && t > 0 && a2 > 0 && ld_t >= t && row_stride >= 0, TSPN_EBADARG,
+                 "tspn_span_head: bad size");
+    TSPN_REQUIRE(a2 <= SH_MAX_A2, TSPN_ESHAPE, "tspn_span_head: 2A=%d exceeds the supported maximum %d", a2,
+                 SH_MAX_A2);
+    if (k == 0) return TSPN_OK;
+    TSPN_REQUIRE(d_x && d_conv_w && d_pred_w && d_out, TSPN_EBADARG, "tspn_span_head: null pointer");
+    TSPN_REQUIRE(k < 65536, TSPN_ESHAPE, "tspn_span_head: k=%lld must be < 65536 per call", (long long)k);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (precision == TSPN_PREC_FP32_EXACT) {
+        dim3 grid((unsigned)((t + SH_THREADS - 1) / SH_THREADS), (unsigned)k);
+        span_head_exact_kernel<<<grid, SH_THREADS, 0, st>>>(d_x, d_rows, row_stride, ld_t, cin, t, d_conv_w,
+                                                            d_conv_b, d_pred_w, d_pred_b, a2, d_out);
+        TSPN_CUDA_OK(cudaGetLastError());
+        return TSPN_OK;
+    }
+    TSPN_REQUIRE(precision == TSPN_PREC_TENSOR, TSPN_EBADARG, "tspn_span_head: unknown precision %d", precision);
+    return span_head_tensor(d_x, d_rows, row_stride, ld_t, k, cin, t, d_conv_w, d_conv_b, d_pred_w, d_pred_b, a2,
+                            d_out, d_workspace, st);
+}
+
+int tspn_span_decode(const float* d_reg, int64_t k, int n_anchors, int t, const float* d_sizes, float stride,
+                     int32_t* d_spans, void* stream) {
+    TSPN_ARCH_OK();
+    TSPN_REQUIRE(k >= 0 && n_anchors > 0 && t > 0 && stride > 0.0f, TSPN_EBADARG, "tspn_span_decode: bad size");
+    if (k == 0) return TSPN_OK;
+    TSPN_REQUIRE(d_reg && d_sizes && d_spans, TSPN_EBADARG, "tspn_span_decode: null pointer");
+    const int n_loc = tspn_span_num_locations(t, stride);
+    const int64_t total = k * n_loc * n_anchors;
+    span_decode_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        d_reg, k, n_anchors, t, n_loc, d_sizes, stride, d_spans);
+    TSPN_CUDA_OK(cudaGetLastError());
+    return TSPN_OK;
+}
+
+}  // extern "C"

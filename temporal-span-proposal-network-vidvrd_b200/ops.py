@@ -1,0 +1,243 @@
+"""Operator layer: each function is one C-ABI entry point on torch CUDA tensors.
+
+PyTorch is plumbing here (device memory, streams); all arithmetic happens in
+``csrc/libtspn_b200.so``.  Every function enqueues on the current CUDA stream and returns
+without synchronising.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from ._lib import check, load, ptr, stream_ptr
+from .batch import DeviceBatch
+
+PREC = {"fp32": _lib.PREC_FP32_EXACT, "exact": _lib.PREC_FP32_EXACT, "fp32_exact": _lib.PREC_FP32_EXACT,
+        "tensor": _lib.PREC_TENSOR, "bf16": _lib.PREC_TENSOR, "tf32": _lib.PREC_TENSOR}
+
+
+def _cuda(t: torch.Tensor, dtype=None) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError("tspn_b200 ops need CUDA tensors (there is no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError("expected %s, got %s" % (dtype, t.dtype))
+    return t.contiguous()
+
+
+def require_device() -> None:
+    """Raise unless the current device can run the library (sm_100)."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("tspn_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    check(load().tspn_check_device(), "tspn_check_device")
+
+
+# ---------------------------------------------------------------------------------------------
+def enumerate_pairs(batch: DeviceBatch) -> torch.Tensor:
+    """``[sum P, 2]`` int64 (s, o) — the h5 ``pairs`` table (vrdataset.py:208)."""
+    out = torch.empty((batch.total_pairs, 2), dtype=torch.int64, device=batch.device)
+    check(load().tspn_enumerate_pairs(ptr(batch.table), batch.num_videos, batch.total_pairs, ptr(out),
+                                      stream_ptr()), "tspn_enumerate_pairs")
+    return out
+
+
+def pair_geometry(batch: DeviceBatch, write_geo: bool = True, clipped: bool = False,
+                  out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+    """All-pairs per-frame geometry + vIoU/tIoU/overlap (trajectory.py:85-141, common.py:65-106)."""
+    dev = batch.device
+    tot = batch.totals
+    p = batch.total_pairs
+    if out is None:
+        out = {}
+        out["geo"] = torch.empty(int(tot[_lib.TOT_GEO_FLOATS]), dtype=torch.float32, device=dev) if write_geo else None
+        out["viou"] = torch.empty(p, dtype=torch.float32, device=dev)
+        out["tiou"] = torch.empty(p, dtype=torch.float32, device=dev)
+        out["overlap"] = torch.empty((p, 2), dtype=torch.int32, device=dev)
+        ws_bytes = load().tspn_pair_geo_workspace_bytes(batch.total_tracklets)
+        out["workspace"] = torch.empty(ws_bytes // 8, dtype=torch.float64, device=dev)
+    check(load().tspn_pair_geo_viou(
+        ptr(batch.table), batch.num_videos, int(tot[_lib.TOT_ITEMS]), batch.total_tracklets,
+        int(tot[_lib.TOT_BOXES]), ptr(batch.boxes), ptr(batch.span), ptr(out.get("geo")), ptr(out["viou"]),
+        ptr(out["tiou"]), ptr(out["overlap"]), _lib.VIOU_CLIPPED if clipped else _lib.VIOU_FULL,
+        ptr(out["workspace"]), stream_ptr()), "tspn_pair_geo_viou")
+    return out
+
+
+def cubic_iou(b1: torch.Tensor, b2: torch.Tensor) -> torch.Tensor:
+    """``[n, t, 4] x [m, t, 4] -> [n, m]`` (trajectory.py:127-141)."""
+    b1, b2 = _cuda(b1, torch.float32), _cuda(b2, torch.float32)
+    if b1.dim() != 3 or b2.dim() != 3 or b1.shape[1] != b2.shape[1] or b1.shape[2] != 4 or b2.shape[2] != 4:
+        raise ValueError("cubic_iou expects [n, t, 4] and [m, t, 4]")
+    out = torch.empty((b1.shape[0], b2.shape[0]), dtype=torch.float32, device=b1.device)
+    check(load().tspn_cubic_iou(ptr(b1), b1.shape[0], ptr(b2), b2.shape[0], b1.shape[1], ptr(out), stream_ptr()),
+          "tspn_cubic_iou")
+    return out
+
+
+def viou_pairs(pool: torch.Tensor, traj_off: torch.Tensor, traj_span: torch.Tensor, a: torch.Tensor,
+               b: torch.Tensor, clipped: bool = False) -> torch.Tensor:
+    """vIoU of explicit trajectory pairs (evaluation/common.py:65-106; association.py:35-48)."""
+    pool = _cuda(pool, torch.float32)
+    out = torch.empty(a.shape[0], dtype=torch.float32, device=pool.device)
+    check(load().tspn_viou_pairs(ptr(pool), ptr(_cuda(traj_off, torch.int64)), ptr(_cuda(traj_span, torch.int32)),
+                                 ptr(_cuda(a, torch.int32)), ptr(_cuda(b, torch.int32)), a.shape[0],
+                                 _lib.VIOU_CLIPPED if clipped else _lib.VIOU_FULL, ptr(out), stream_ptr()),
+          "tspn_viou_pairs")
+    return out
+
+
+def normalize_motion(motion: torch.Tensor) -> torch.Tensor:
+    motion = _cuda(motion, torch.float32)
+    out = torch.empty_like(motion)
+    check(load().tspn_normalize_motion(ptr(motion), motion.shape[0], ptr(out), stream_ptr()),
+          "tspn_normalize_motion")
+    return out
+
+
+def feature_dim(n_classes: int) -> int:
+    return 2 * n_classes + 2 * _lib.MOTION_DIM + _lib.REL_DIM
+
+
+def padded(n: int, mult: int) -> int:
+    return (n + mult - 1) // mult * mult
+
+
+def assemble_features(batch: DeviceBatch, motion_norm: torch.Tensor, geo: torch.Tensor, overlap: torch.Tensor,
+                      rows: Optional[torch.Tensor] = None, want_fp32: bool = True, want_bf16: bool = False,
+                      out_fp32: Optional[torch.Tensor] = None, out_bf16: Optional[torch.Tensor] = None):
+    """Feature rows ``[n_rows, F]`` in the layout of vrdataset.py:219-243.
+
+    Returns ``(feat_fp32 | None, feat_bf16 | None)``; both are views ``[:, :F]`` of row-padded
+    buffers (stride multiple of 4 / 8 elements) so they can be fed to TMA.
+    """
+    c = batch.cls.shape[1]
+    f = feature_dim(c)
+    n_rows = batch.total_pairs if rows is None else int(rows.shape[0])
+    dev = batch.device
+    ld32, ld16 = padded(f, 4), padded(f, 8)
+    if want_fp32 and out_fp32 is None:
+        out_fp32 = torch.empty((n_rows, ld32), dtype=torch.float32, device=dev)
+    if want_bf16 and out_bf16 is None:
+        out_bf16 = torch.empty((n_rows, ld16), dtype=torch.bfloat16, device=dev)
+    check(load().tspn_assemble_features(
+        ptr(batch.table), batch.num_videos, batch.total_pairs, ptr(batch.cls), c, ptr(motion_norm), ptr(geo),
+        ptr(overlap), ptr(rows), n_rows, ptr(out_fp32), out_fp32.stride(0) if out_fp32 is not None else 0,
+        ptr(out_bf16), out_bf16.stride(0) if out_bf16 is not None else 0, stream_ptr()), "tspn_assemble_features")
+    return (out_fp32[:, :f] if out_fp32 is not None else None,
+            out_bf16[:, :f] if out_bf16 is not None else None)
+
+
+PPN_KEYS = ("sub_emb.0.weight", "sub_emb.0.bias", "sub_emb.2.weight", "sub_emb.2.bias",
+            "obj_emb.0.weight", "obj_emb.0.bias", "obj_emb.2.weight", "obj_emb.2.bias")
+
+
+def relationness(batch: DeviceBatch, weights, cls: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """PPNHead scores of every video, flat ``[sum N*N]`` (ppn.py:92-112).  ``weights`` is the
+    8-tuple of ``PPN_KEYS`` tensors."""
+    cls = batch.cls if cls is None else cls
+    cls = _cuda(cls, torch.float32)
+    w = [_cuda(t, torch.float32) for t in weights]
+    c, h = cls.shape[1], w[0].shape[0]
+    dev = cls.device
+    scores = torch.empty(batch.total(_lib.TOT_SCORES), dtype=torch.float32, device=dev)
+    ws = torch.empty(load().tspn_relationness_workspace_bytes(batch.total_tracklets, c, h) // 4,
+                     dtype=torch.float32, device=dev)
+    check(load().tspn_relationness(ptr(batch.table), batch.num_videos, batch.total_tracklets, ptr(cls), c, h,
+                                   *[ptr(t) for t in w], ptr(scores), ptr(ws), stream_ptr()), "tspn_relationness")
+    return scores
+
+
+def topk_pairs(batch: DeviceBatch, scores: torch.Tensor, k: int, exclude_diagonal: bool = False):
+    """Per video: flat indices ``s*N+o`` ``[V, K]`` (-1 beyond K_eff), scores, global pair rows."""
+    dev = scores.device
+    v = batch.num_videos
+    idx = torch.empty((v, k), dtype=torch.int64, device=dev)
+    val = torch.empty((v, k), dtype=torch.float32, device=dev)
+    row = torch.empty((v, k), dtype=torch.int64, device=dev)
+    check(load().tspn_topk_pairs(ptr(batch.table), v, ptr(scores), k,
+                                 _lib.TOPK_EXCLUDE_DIAGONAL if exclude_diagonal else _lib.TOPK_KEEP_DIAGONAL,
+                                 ptr(idx), ptr(val), ptr(row), stream_ptr()), "tspn_topk_pairs")
+    return idx, val, row
+
+
+def pack_predicate_weights(weight: torch.Tensor) -> torch.Tensor:
+    """One-time repack of ``rel_predictor.weight [R, F]`` for the tensor-core head."""
+    weight = _cuda(weight, torch.float32)
+    r, f = weight.shape
+    nbytes = load().tspn_predicate_packed_bytes(r, f)
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
+    check(load().tspn_pack_predicate_weights(ptr(weight), r, f, ptr(packed), stream_ptr()),
+          "tspn_pack_predicate_weights")
+    return packed
+
+
+def predicate_head(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, precision: str = "fp32",
+                   packed: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``sigmoid(x W^T + b)`` (model.py:85-88).  ``x`` may be a row-padded view (stride >= F)."""
+    if not x.is_cuda:
+        raise RuntimeError("tspn_b200 ops need CUDA tensors (there is no CPU path)")
+    prec = PREC[precision]
+    if x.stride(-1) != 1:
+        x = x.contiguous()
+    m, f = x.shape
+    r = weight.shape[0]
+    is_bf16 = x.dtype == torch.bfloat16
+    if not is_bf16 and x.dtype != torch.float32:
+        raise TypeError("x must be float32 or bfloat16")
+    y = torch.empty((m, r), dtype=torch.float32, device=x.device)
+    ws = None
+    if prec == _lib.PREC_TENSOR:
+        if packed is None:
+            packed = pack_predicate_weights(weight)
+        nbytes = load().tspn_predicate_workspace_bytes(m, f, r, prec)
+        ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=x.device)
+    check(load().tspn_predicate_head(ptr(x), int(is_bf16), x.stride(0) if m > 1 else max(f, x.stride(0)), m, f,
+                                     ptr(_cuda(weight, torch.float32)), ptr(packed),
+                                     ptr(_cuda(bias, torch.float32)), r, ptr(y), prec, ptr(ws), stream_ptr()),
+          "tspn_predicate_head")
+    return y
+
+
+def span_head(x: torch.Tensor, conv_w: torch.Tensor, conv_b: torch.Tensor, pred_w: torch.Tensor,
+              pred_b: torch.Tensor, rows: Optional[torch.Tensor] = None, t: Optional[int] = None,
+              precision: str = "fp32") -> torch.Tensor:
+    """DPNHead (dpn.py:69-73) on ``x [K, Cin, T]`` or, with ``rows``, on gathered rows of ``x``.
+
+    ``x`` may be a ``[P, Cin, Tp]`` buffer whose rows are padded to ``Tp >= t``.
+    """
+    x = _cuda(x, torch.float32)
+    if x.dim() != 3:
+        raise ValueError("span_head expects [K, Cin, T]")
+    cin, ld_t = x.shape[1], x.shape[2]
+    t = ld_t if t is None else int(t)
+    k = x.shape[0] if rows is None else int(rows.shape[0])
+    a2 = pred_w.shape[0]
+    prec = PREC[precision]
+    out = torch.empty((k, a2, t), dtype=torch.float32, device=x.device)
+    ws = None
+    if prec == _lib.PREC_TENSOR:
+        nbytes = load().tspn_span_head_workspace_bytes(k, cin, t, a2, prec)
+        ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=x.device)
+    check(load().tspn_span_head(ptr(x), ptr(rows), cin * ld_t, ld_t, k, cin, t,
+                                ptr(_cuda(conv_w, torch.float32)), ptr(_cuda(conv_b, torch.float32)),
+                                ptr(_cuda(pred_w.reshape(a2, cin), torch.float32)),
+                                ptr(_cuda(pred_b, torch.float32)), a2, ptr(out), prec, ptr(ws), stream_ptr()),
+          "tspn_span_head")
+    return out
+
+
+def span_num_locations(t: int, stride: float) -> int:
+    return int(load().tspn_span_num_locations(int(t), float(stride)))
+
+
+def span_decode(reg: torch.Tensor, sizes: torch.Tensor, stride: float) -> torch.Tensor:
+    """Regressions ``[K, 2A, T]`` -> int32 frame bounds ``[K, L*A, 2]`` ([SPEC] s5)."""
+    reg = _cuda(reg, torch.float32)
+    k, a2, t = reg.shape
+    a = a2 // 2
+    n_loc = span_num_locations(t, stride)
+    out = torch.empty((k, n_loc * a, 2), dtype=torch.int32, device=reg.device)
+    check(load().tspn_span_decode(ptr(reg), k, a, t, ptr(_cuda(sizes, torch.float32)), float(stride), ptr(out),
+                                  stream_ptr()), "tspn_span_decode")
+    return out

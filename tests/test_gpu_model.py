@@ -1,0 +1,126 @@
+"""Drop-in behaviour of the module mirrors against outputs of the unmodified reference."""
+import numpy as np
+import pytest
+import torch
+
+import tspn_b200
+from oracle import exact, features as ofeat, geometry as ogeo, heads as oheads
+from tspn_b200 import synth
+from tspn_b200.list_pair import PairList
+from tspn_b200.model import BaseModel, RelationPredictor
+from tspn_b200.relpn import DPNHead, PPNHead
+from tests.golden.make_golden import synth_features
+
+pytestmark = pytest.mark.gpu
+
+CASES = {"A": (20, 300, 35, 132, 0), "V": (12, 64, 80, 50, 2)}
+
+
+def _cfg(c, r, fdim, use_ppn, use_dpn, **kw):
+    cfg = tspn_b200.get_default_cfg()
+    cfg.PREDICT.OBJECT_NUM, cfg.PREDICT.PREDICATE_NUM, cfg.PREDICT.FEATURE_DIM = c, r, fdim
+    cfg.RELPN.PPN.IN_CHANNELS = cfg.RELPN.PPN.OUT_CHANNELS = c
+    cfg.RELPN.USE_PPN, cfg.RELPN.USE_DPN = use_ppn, use_dpn
+    cfg.RELPN.DPN.IN_CHANNELS = 8
+    for k, v in kw.items():
+        cfg.PREDICT[k] = v
+    return cfg
+
+
+@pytest.mark.parametrize("tag", ["A", "V"])
+def test_basemodel_reference_mode_cpu_in_cpu_out(golden, tag):
+    """predict.py:57: model(pair_list, _) with CPU tensors and precomputed feature rows."""
+    n, t, c, r, seed = CASES[tag]
+    fdim = synth.feature_dim(c)
+    sd = {k: torch.from_numpy(v) for k, v in synth.make_weights(c, r, fdim, seed=seed).items()}
+    vid = synth.make_video(n, t, c, seed=seed)
+    plist = PairList(torch.from_numpy(synth_features(n * (n - 1), fdim, seed)))
+    plist.add_field("tracklet_pairs", torch.from_numpy(ogeo.enumerate_pairs(n)))
+    plist.add_field("track_cls_logits", torch.from_numpy(vid.cls))
+    plist.add_field("num_tracklets", n)
+    for use_ppn in (False, True):
+        model = BaseModel(_cfg(c, r, fdim, use_ppn, False))
+        model.load_state_dict(sd)                     # the reference's 14 keys, strict
+        model.eval()
+        with torch.no_grad():
+            pp, dp, logits = model([plist], None)
+        assert dp is None and len(logits) == 1 and not logits[0].is_cuda
+        np.testing.assert_allclose(logits[0].numpy(), golden[f"basemodel_{tag}_ppn{int(use_ppn)}_logits"],
+                                   rtol=0, atol=1e-6)
+        if use_ppn:
+            ref = golden[f"basemodel_{tag}_ppn1_proposals"]
+            assert pp[0].dtype == torch.int64 and pp[0].shape == ref.shape
+            ex = exact.topk(exact.relationness(vid.cls, {k: v.numpy() for k, v in sd.items()}), 256)
+            np.testing.assert_array_equal(pp[0].numpy(), ex)              # bit-exact vs the fixed order
+            srt = np.sort(golden[f"ppn_scores_{tag}"].reshape(-1).astype(np.float64))[::-1]
+            if (srt[:-1] - srt[1:])[:len(ref)].min() > 4e-6:              # margins >> score noise
+                np.testing.assert_array_equal(pp[0].numpy(), ref)        # == the reference's selection
+        else:
+            assert pp is None
+
+
+def test_heads_module_api(golden):
+    n, t, c, r, seed = CASES["A"]
+    fdim = synth.feature_dim(c)
+    sd = {k: torch.from_numpy(v) for k, v in synth.make_weights(c, r, fdim, seed=seed).items()}
+    vid = synth.make_video(n, t, c, seed=seed)
+    head = PPNHead(c, 64, c).eval()
+    head.load_state_dict({k.split("ppn_head.")[1]: v for k, v in sd.items() if "ppn_head" in k})
+    cl = torch.from_numpy(vid.cls)
+    m = head(cl, cl)
+    np.testing.assert_allclose(m.numpy(), golden["ppn_scores_A"], atol=2e-6)
+    m2 = head(cl[:7].clone(), cl[9:].clone())                              # different subject / object sets
+    np.testing.assert_array_equal(m2.numpy(), m.numpy()[:7, 9:])
+    clf = RelationPredictor(fdim, r).eval()
+    clf.load_state_dict({k.split("classifier.")[1]: v for k, v in sd.items() if k.startswith("classifier.")})
+    y = clf(torch.from_numpy(synth_features(n * (n - 1), fdim, seed)).cuda())
+    assert y.is_cuda
+    np.testing.assert_allclose(y.cpu().numpy(), golden["rel_logits_A"], atol=1e-6)
+    dpn = DPNHead(8, 4).eval()
+    dpn.load_state_dict({k.split("dpn_head.")[1]: v for k, v in sd.items() if "dpn_head" in k})
+    x = np.random.Generator(np.random.PCG64(seed + 77)).normal(0, 1, size=(6, 8, t)).astype(np.float32)
+    np.testing.assert_allclose(dpn(torch.from_numpy(x)).numpy(), golden["dpn_reg_A"], atol=1e-6)
+
+
+@pytest.mark.parametrize("sparsify", [False, True])
+def test_basemodel_full_pair_stage(sparsify):
+    """Tracklets in, everything constructed on the GPU; two videos of different shape per call."""
+    c, r = 35, 132
+    fdim = synth.feature_dim(c)
+    sd_np = synth.make_weights(c, r, fdim, dpn_in=8, seed=1)
+    sd = {k: torch.from_numpy(v) for k, v in sd_np.items()}
+    vids = [synth.make_video(9, 120, c, seed=4), synth.make_video(20, 300, c, seed=5)]
+    pls = [PairList.from_tracklets(v.boxes, v.span, v.cls, v.motion) for v in vids]
+    model = BaseModel(_cfg(c, r, fdim, True, True, SPARSIFY=sparsify)).eval()
+    model.load_state_dict(sd)
+    with torch.no_grad():
+        pp, dp, logits = model(pls)
+    sizes, stride = model.stage_config.anchor_sizes, model.stage_config.anchor_stride
+    for i, v in enumerate(vids):
+        n = v.n_tracklets
+        geo, viou, _, ov = ogeo.pair_geometry_chunked(v.boxes, v.span)
+        feats = ofeat.assemble_features(v.cls, v.motion, ofeat.relative_block(geo, ov), ogeo.enumerate_pairs(n))
+        sc = exact.relationness(v.cls, sd_np)
+        if sparsify:
+            sc = sc.copy()
+            sc[np.arange(n), np.arange(n)] = -np.inf
+        k_eff = min(256, n * (n - 1) if sparsify else n * n)
+        order = exact.topk(sc, 256)[:k_eff]
+        np.testing.assert_array_equal(pp[i].numpy(), order)                        # pair indices bit-exact
+        s, o = order // n, order % n
+        rows = s * (n - 1) + o - (o > s)
+        want_logits = oheads.relation_predictor_f64(feats, sd_np)
+        if sparsify:
+            np.testing.assert_allclose(logits[i].numpy(), want_logits[rows], rtol=0, atol=2e-6)
+        else:
+            np.testing.assert_allclose(logits[i].numpy(), want_logits, rtol=0, atol=2e-6)
+        # spans: the GPU's own fp32 geometry through the exact-order span head -> bit-exact bounds
+        res = model.last_result
+        g32 = res.batch.geo_view(res.geom["geo"], i).cpu().numpy()
+        valid = s != o
+        reg = exact.span_head(np.ascontiguousarray(g32[np.where(valid, rows, 0)]), sd_np)
+        want_sp = exact.span_decode(reg, sizes, stride)
+        got_sp = dp[i].numpy()
+        assert got_sp.shape == want_sp.shape and got_sp.dtype == np.int32
+        np.testing.assert_array_equal(got_sp[valid], want_sp[valid])               # frame bounds bit-exact
+        np.testing.assert_allclose(res.geom["viou"][res.batch.pair_slice(i)].cpu().numpy(), viou, rtol=1e-5)
