@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py — pair-stage throughput (BASELINE.json metric: tracklet pairs scored / s).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # CPU reference arm (oracle port)
+
+A *step* is one pass of the hot path (all-pairs geometry + vIoU -> feature rows -> relationness +
+top-K -> predicate and span heads) over one batch of synthetic VidOR-shaped videos
+(N=64 tracklets, T=2000 frames, 80 classes, 50 predicates: BASELINE.json configs[2]).
+`value` counts P = N(N-1) ordered pairs per video with the inputs resident in HBM; `e2e` is the same
+metric through the host-facing call with pinned host buffers, H2D and D2H inside the timed region.
+Under torchrun each rank processes its own shard of videos (weak scaling, no data-path collective)
+and the per-video top-K triplet records are all-gathered once at the end of the step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOAD = "vidor_single"          # N=64, T=2000, C=80, R=50, K=256
+FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--videos", type=int, default=16, help="videos per GPU per step")
+    ap.add_argument("--precision", default="tensor", choices=["tensor", "fp32"])
+    ap.add_argument("--no-sparsify", action="store_true", help="heads on all P pairs (reference quirk Q3)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:  # noqa: BLE001
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for name, val in zip(names, r[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:  # noqa: BLE001
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm (oracle port of the reference's CPU path) — the only place oracle/ is executed
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_step(video, sd, topk, sizes, stride, sample_pairs=256):
+    """One video through the reference's CPU path; returns (seconds for the whole video, detail).
+
+    Geometry / feature rows are computed for a bounded sample of pairs and scaled to P; everything
+    else runs at full size.  The vIoU + per-frame geometry is the float64 oracle port ("oracle, not
+    reference": the reference has no code for the per-frame channels); relationness, sort, classifier
+    and span head are the reference's own torch CPU ops (oracle.heads.*_ref)."""
+    from oracle import features as ofeat, geometry as ogeo, heads as oheads
+    n, p = video.n_tracklets, video.n_pairs
+    pr = ogeo.enumerate_pairs(n)
+    rng = np.random.Generator(np.random.PCG64(0))
+    sel = np.sort(rng.choice(p, size=min(sample_pairs, p), replace=False))
+    det = {}
+    # numpy releases the GIL: the sampled pairs are split over all host cores
+    from concurrent.futures import ThreadPoolExecutor
+    cores = os.cpu_count() or 1
+    chunks = [c for c in np.array_split(sel, cores) if len(c)]
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        parts = list(ex.map(lambda c: ogeo.pair_geometry(video.boxes, video.span, pr[c, 0], pr[c, 1]), chunks))
+    det["geometry_viou"] = (time.perf_counter() - t0) * p / len(sel)
+    geo, viou, tiou, ov = (np.concatenate([q[j] for q in parts], axis=0) for j in range(4))
+    t0 = time.perf_counter()
+    scores = oheads.ppn_head_ref(video.cls, video.cls, sd)
+    order = torch.sort(scores.view(-1), descending=True)[1][:topk]
+    det["relationness_topk"] = time.perf_counter() - t0
+    k = int(order.shape[0])
+    ksel = sel[:min(k, len(sel))]
+    t0 = time.perf_counter()
+    rel = ofeat.relative_block(geo[:len(ksel)], ov[:len(ksel)])
+    feats = ofeat.assemble_features(video.cls, video.motion, rel, pr[ksel]).astype(np.float32)
+    det["features_topk_rows"] = (time.perf_counter() - t0) * k / len(ksel)
+    if len(ksel) < k:
+        feats = np.concatenate([feats] * (k // len(ksel) + 1), axis=0)[:k]
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        oheads.relation_predictor_ref(feats, sd)
+    det["predicate_head"] = time.perf_counter() - t0
+    x = np.ascontiguousarray(np.concatenate([geo] * (k // geo.shape[0] + 1), axis=0)[:k], dtype=np.float32)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        reg = oheads.dpn_head_ref(x, sd).numpy()
+    oheads.decode_spans_f64(reg, sizes, stride)
+    det["span_head_decode"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        logits = oheads.relation_predictor_ref(feats, sd).numpy()
+    rows = np.resize(sel, k)
+    oheads.postprocess_ref(logits, video.cls, pr[rows], 20, 200)
+    det["postprocess"] = time.perf_counter() - t0
+    return sum(det.values()), det
+
+
+def run_reference(args, rank, world):
+    """`--impl reference`: rank 0 alone times the CPU path; other ranks exit 0 without work."""
+    if rank != 0:
+        return
+    from tspn_b200 import synth
+    spec = synth.CONFIGS[WORKLOAD]
+    c, r, k = spec["classes"], spec["predicates"], spec["topk"]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = synth.make_weights(c, r, synth.feature_dim(c), dpn_in=8, seed=0)
+    sizes, stride = (16.0, 64.0, 256.0, 1024.0), 16.0
+    n, t = spec["n"][0], spec["t"][0]
+    sample = 16 * cores
+    times = []
+    for i in range(args.warmup + args.steps):
+        v = synth.make_video(n, t, c, seed=i)
+        sec, det = cpu_reference_step(v, sd, k, sizes, stride, sample_pairs=sample)
+        if i >= args.warmup:
+            times.append(sec)
+    pairs = n * (n - 1)
+    ms = 1e3 * float(np.mean(times))
+    value = pairs / (ms / 1e3)
+    line = {
+        "metric": "tracklet pairs scored/sec (N=64,T=2000)", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64 (numpy + torch CPU)", "data": "synthetic",
+        "impl": "reference",
+        "config": {"workload": "VidOR-shaped video N=64 T=2000 C=80 R=50 K=256, 1 video per step",
+                   "sparsify": True, "host_cpu_count": cores, "torch_threads": torch.get_num_threads()},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
+                         "sample": "1 video/step; geometry+feature rows on %d sampled pairs scaled to P=%d, "
+                                   "relationness/top-K/classifier/span head at full size" % (sample, pairs),
+                         "detail_s": det},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from tspn_b200 import _lib, ops, synth
+    from tspn_b200.batch import HostBatch
+    from tspn_b200.pipeline import PairStage, StageConfig
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ops.require_device()
+    spec = synth.CONFIGS[WORKLOAD]
+    c, r, k = spec["classes"], spec["predicates"], spec["topk"]
+    n, t = spec["n"][0], spec["t"][0]
+    sparsify = not args.no_sparsify
+    sizes, stride = (16.0, 64.0, 256.0, 1024.0), 16.0
+    cfg = StageConfig(n_classes=c, n_predicates=r, topk=k, use_ppn=True, use_dpn=True, sparsify=sparsify,
+                      precision=args.precision, anchor_sizes=sizes, anchor_stride=stride)
+    sd = synth.make_weights(c, r, synth.feature_dim(c), dpn_in=8, seed=0)
+    stage = PairStage(cfg)
+    stage.load_weights(sd, dev)
+    videos = [synth.make_video(n, t, c, seed=100000 * rank + i) for i in range(args.videos)]
+    host = HostBatch.from_videos(videos)
+    pairs_per_step = sum(v.n_pairs for v in videos)
+
+    # ---- resident-input steps ------------------------------------------------------------------
+    batch = host.to_device(dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)    # > 126 MB L2
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    geo_ev, step_ev = [], []
+    sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else
+                           int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
+    sampler.start()                                     # samples through warm-up, timed steps and e2e
+    launches0 = ops.launch_count()
+    for i in range(args.warmup):
+        stage.forward(batch)
+    barrier()
+    launches_per_step = (ops.launch_count() - launches0) // max(args.warmup, 1)
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()                                   # L2 flush between timed iterations (untimed)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        timers = {}
+        e0.record()
+        stage.forward(batch, timers=timers)
+        e1.record()
+        step_ev.append((e0, e1))
+        geo_ev.append(timers["geo"])
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    step_ms = [a.elapsed_time(b) for a, b in step_ev]
+    geo_ms = [a.elapsed_time(b) for a, b in geo_ev]
+    total_ms = float(sum(step_ms))
+    if world > 1:
+        tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt.item())
+    ms_per_step = total_ms / args.steps
+    value = world * pairs_per_step / (ms_per_step / 1e3)
+
+    # ---- end-to-end steps: pinned host in, pinned host out ------------------------------------
+    # Depth-2 software pipeline over three streams: the H2D copy of step i+1 and the D2H read of
+    # step i-1 overlap the kernels of step i.  Every step still moves its own inputs from pinned
+    # host memory and its own results back to pinned host memory inside the timed region.
+    s_h2d, s_d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    s_main = torch.cuda.current_stream(dev)
+    slots = [{"batch": host.to_device(dev), "h2d": torch.cuda.Event(), "done": torch.cuda.Event(),
+              "d2h": torch.cuda.Event(), "bufs": None, "keep": None} for _ in range(2)]
+    torch.cuda.synchronize()
+
+    def result_tensors(res):
+        outs = [res.topk_idx, res.topk_score, res.rel_logits, res.geom["viou"], res.geom["tiou"],
+                res.geom["overlap"], torch.cat(res.spans, dim=0), res.records, res.record_counts]
+        return outs
+
+    def issue_h2d(slot):
+        with torch.cuda.stream(s_h2d):
+            s_h2d.wait_event(slot["done"])          # the slot's previous kernels have consumed it
+            slot["batch"].copy_from(host)
+            slot["h2d"].record(s_h2d)
+
+    def e2e_loop(steps):
+        issue_h2d(slots[0])
+        for i in range(steps):
+            slot = slots[i & 1]
+            if i + 1 < steps:
+                issue_h2d(slots[(i + 1) & 1])
+            s_main.wait_event(slot["h2d"])
+            s_main.wait_event(slot["d2h"])          # the slot's previous results have left the device
+            res = stage.forward(slot["batch"])
+            outs = result_tensors(res)
+            if world > 1:                          # one collective per step: the top-K triplet records
+                gathered = torch.empty((world,) + tuple(res.records.shape), dtype=res.records.dtype, device=dev)
+                dist.all_gather_into_tensor(gathered, res.records)
+                outs.append(gathered)
+            slot["done"].record(s_main)
+            if slot["bufs"] is None:
+                slot["bufs"] = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
+            with torch.cuda.stream(s_d2h):
+                s_d2h.wait_event(slot["done"])
+                for dst, src in zip(slot["bufs"], outs):
+                    src.record_stream(s_d2h)
+                    dst.copy_(src, non_blocking=True)
+                slot["d2h"].record(s_d2h)
+            slot["keep"] = (res, outs)
+        torch.cuda.synchronize()
+
+    e2e_loop(max(args.warmup, 2))
+    barrier()
+    t0 = time.perf_counter()
+    e2e_loop(args.steps)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    e2e_value = world * pairs_per_step * args.steps / e2e_s
+    d2h = int(sum(b.numel() * b.element_size() for b in slots[0]["bufs"]))
+    clocks = sampler.stop()
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel (all-pairs geometry + vIoU) ------------------------------
+    tp, tb = (t + 3) // 4 * 4, (t + 7) // 8 * 8
+    p1 = n * (n - 1)
+    alg_bytes = args.videos * (32 * tp * p1 + 16 * p1 + 16 * n * tb + 8 * n)      # DESIGN.md, SURVEY 8d
+    geo_avg_ms = float(np.mean(geo_ms))
+    achieved = alg_bytes / (geo_avg_ms / 1e3) / 1e9
+    peak, peak_src = measured_peak()
+    line = {
+        "metric": "tracklet pairs scored/sec (N=64,T=2000)", "value": value, "unit": "pairs/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 geometry/features, f64 volume sums, %s heads" % ("bf16 tcgen05" if args.precision == "tensor"
+                                                                         else "f32 exact-order"),
+        "data": "synthetic",
+        "config": {"workload": "VidOR-shaped videos N=64 T=2000 C=80 R=50 K=256 (BASELINE.json configs[2]), "
+                               "%d videos per GPU per step" % args.videos,
+                   "videos_per_gpu": args.videos, "pairs_per_step_per_gpu": pairs_per_step, "sparsify": sparsify,
+                   "precision": args.precision, "sharding": "per video, no data-path collective",
+                   "l2": "256 MiB buffer zeroed between timed iterations (untimed); each step also writes "
+                         "%.1f GB of outputs" % (alg_bytes / 1e9),
+                   "wall_s_timed_region": t_wall,
+                   "e2e_pipeline": "depth 2: H2D(i+1) and D2H(i-1) overlap the kernels of step i",
+                   "multi_gpu_collective": "all_gather of [V,200,8] int32 triplet records per step (e2e loop)"},
+        "roofline": {"bound": "hbm", "kernel": "pair_geo_kernel (+ tracklet_volume_kernel)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                     "avg_launch_ms": geo_avg_ms, "share_of_step": geo_avg_ms / (float(np.mean(step_ms)))},
+        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": host.h2d_bytes(),
+                "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "launches_per_step": int(launches_per_step),
+        "clocks": clocks,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        sec, det = cpu_reference_step(videos[0], sd, k, sizes, stride, sample_pairs=16 * cores)
+        line["cpu_baseline"] = {"value": p1 / sec, "unit": "pairs/s", "cores": cores, "kind": "port",
+                                "sample": "1 video (P=%d); geometry+feature rows on %d sampled pairs (split over "
+                                          "%d threads) scaled to P, heads at full size; torch threads=%d"
+                                          % (p1, 16 * cores, cores, torch.get_num_threads()),
+                                "detail_s": det}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -187,11 +187,12 @@ int tspn_predicate_head(const void* d_x, int x_is_bf16, int64_t ld_x, int64_t m,
 
 /* ---- a11/a12 + [SPEC] s5: temporal-span head ---------------------------------------------
  * DPNHead.forward (lib/modeling/relpn/dpn.py:55-73): Conv1d(k3,p1) -> ReLU -> Conv1d(k1).
- * x rows are gathered: pair i reads x[d_rows[i]] (NULL = identity), each row [cin][ld_t];
- * out [k][a2][t].  conv_w [cin][cin][3], pred_w [a2][cin]. */
+ * x rows are gathered: pair i reads row d_rows[i] - row_base of x (NULL = identity, negative =
+ * padding -> zeros), each row [cin][ld_t], rows row_stride floats apart; out [k][a2][t].
+ * conv_w [cin][cin][3], pred_w [a2][cin]. */
 int64_t tspn_span_head_workspace_bytes(int64_t k, int cin, int t, int a2, int precision);
-int tspn_span_head(const float* d_x, const int64_t* d_rows, int64_t row_stride, int64_t ld_t,
-                   int64_t k, int cin, int t,
+int tspn_span_head(const float* d_x, const int64_t* d_rows, int64_t row_base, int64_t row_stride,
+                   int64_t ld_t, int64_t k, int cin, int t,
                    const float* d_conv_w, const float* d_conv_b,
                    const float* d_pred_w, const float* d_pred_b, int a2,
                    float* d_out, int precision, void* d_workspace, void* stream);
@@ -201,16 +202,21 @@ int tspn_span_decode(const float* d_reg, int64_t k, int n_anchors, int t,
                      const float* d_sizes, float stride, int32_t* d_spans, void* stream);
 
 /* ---- N1: predict.py:66-117 post-processing ------------------------------------------------
- * per video: top `topk_per_pair` predicates per pair row, then top `topk_per_video` overall;
+ * per video: top `topk_per_pair` predicates per scored row (predict.py:70-73), then top
+ * `topk_per_video` overall (predict.py:76-81), both descending with ties to the lower index;
  * one 32-byte record per kept triplet: {score f32, s_cls, pred, o_cls, s_tid, o_tid, start,
- * end : i32}.  d_logits [m][r] rows in the order of d_rows (global pair rows, NULL = all).
- * d_records [V][topk_per_video][8] (int32 view), d_counts int32 [V]. */
+ * end : i32} (start/end = the pair's temporal overlap window).
+ * d_logits [n_rows][r]; row i scores global pair row d_rows[i] (NULL = identity, -1 = padding);
+ * video v owns rows [d_row_video_off[v], d_row_video_off[v+1]) (NULL = its pair rows).
+ * flags: TSPN_POST_MIRROR_Q4 reproduces predict.py:89's wrong-row object class.
+ * d_records int32 [V][topk_per_video][8] (unused slots: score 0, ids -1), d_counts int32 [V]. */
+#define TSPN_POST_MIRROR_Q4 1
+int64_t tspn_postprocess_workspace_bytes(int64_t n_rows, int topk_per_pair);
 int tspn_postprocess(const int64_t* d_table, int num_videos, const float* d_logits,
-                     const int64_t* d_rows, const int64_t* d_row_video_off, int n_predicates,
-                     const float* d_cls, int n_classes, const int32_t* d_overlap,
-                     int topk_per_pair, int topk_per_video,
+                     const int64_t* d_rows, const int64_t* d_row_video_off, int64_t n_rows,
+                     int n_predicates, const float* d_cls, int n_classes, const int32_t* d_overlap,
+                     int topk_per_pair, int topk_per_video, int flags,
                      int32_t* d_records, int32_t* d_counts, void* d_workspace, void* stream);
-int64_t tspn_postprocess_workspace_bytes(int64_t m, int topk_per_pair);
 
 #ifdef __cplusplus
 }

@@ -51,11 +51,11 @@ SIGNATURES = {
     "tspn_predicate_workspace_bytes": (c_int64, [c_int64, c_int, c_int, c_int]),
     "tspn_predicate_head": (c_int, [P, c_int, c_int64, c_int64, c_int, P, P, P, c_int, P, c_int, P, P]),
     "tspn_span_head_workspace_bytes": (c_int64, [c_int64, c_int, c_int, c_int, c_int]),
-    "tspn_span_head": (c_int, [P, P, c_int64, c_int64, c_int64, c_int, c_int, P, P, P, P, c_int, P, c_int, P, P]),
+    "tspn_span_head": (c_int, [P, P, c_int64, c_int64, c_int64, c_int64, c_int, c_int, P, P, P, P, c_int, P, c_int, P, P]),
     "tspn_span_num_locations": (c_int, [c_int, c_float]),
     "tspn_span_decode": (c_int, [P, c_int64, c_int, c_int, P, c_float, P, P]),
     "tspn_postprocess_workspace_bytes": (c_int64, [c_int64, c_int]),
-    "tspn_postprocess": (c_int, [P, c_int, P, P, P, c_int, P, c_int, P, c_int, c_int, P, P, P, P]),
+    "tspn_postprocess": (c_int, [P, c_int, P, P, P, c_int64, c_int, P, c_int, P, c_int, c_int, c_int, P, P, P, P]),
 }
 
 _lib = None

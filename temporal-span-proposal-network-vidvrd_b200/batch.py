@@ -114,6 +114,21 @@ class DeviceBatch:
         self.cls = None if host.cls is None else host.cls.to(dev, non_blocking=non_blocking)
         self.motion = None if host.motion is None else host.motion.to(dev, non_blocking=non_blocking)
 
+    def copy_from(self, host: HostBatch) -> "DeviceBatch":
+        """Refill the device buffers from another host batch of the same layout (non-blocking, on the
+        current stream): the steady-state H2D of a serving loop."""
+        if host.n != self.n or host.t != self.t:
+            raise ValueError("copy_from needs a host batch with the same per-video shapes")
+        self.host = host
+        self.table.copy_(host.table_t, non_blocking=True)
+        self.boxes.copy_(host.boxes, non_blocking=True)
+        self.span.copy_(host.span, non_blocking=True)
+        if self.cls is not None:
+            self.cls.copy_(host.cls, non_blocking=True)
+        if self.motion is not None:
+            self.motion.copy_(host.motion, non_blocking=True)
+        return self
+
     # sizes -----------------------------------------------------------------------------
     @property
     def num_videos(self) -> int:

@@ -30,16 +30,45 @@ constexpr int GEO_FPT = 4;
 constexpr int GEO_CHUNK = GEO_THREADS * GEO_FPT;      // 512 frames per step
 constexpr int GEO_ROWS = GEO_CHUNK / 8 + 1;           // 64 rows of 8 boxes + 1 halo row
 constexpr int GEO_TX_BYTES = GEO_ROWS * 128;          // 8320 bytes per TMA box
-constexpr int GEO_STAGE_BYTES = 9216;                 // rounded up to the 1024-B swizzle atom
+constexpr int GEO_STAGE_BYTES = GEO_TX_BYTES;         // stages are packed (128-byte aligned)
 constexpr int GEO_OG = TSPN_GEO_OBJ_GROUP;
 constexpr int GEO_WARPS = GEO_THREADS / 32;
-constexpr int GEO_SMEM_BYTES = 4 * GEO_STAGE_BYTES + 1024;
+constexpr int GEO_SMEM_BYTES = 4 * GEO_STAGE_BYTES + 512;
+constexpr int GEO_MIN_CTAS = 6;                       // 6 x 33.8 KB of shared memory per SM
 
-// box j of a chunk staged with SWIZZLE_128B: row r = j/8 (128 B), 16-byte slot (j%8) ^ (r%8)
-__device__ __forceinline__ float4 ld_box(const uint8_t* stage, int j) {
-    const int r = j >> 3;
-    const int c = (j & 7) ^ (r & 7);
-    return *reinterpret_cast<const float4*>(stage + (r << 7) + (c << 4));
+// box j of a chunk staged with SWIZZLE_128B: the 16-byte slot index (address bits 4..6) is XORed
+// with address bits 7..9 of the shared-memory address, so the pattern is a function of the
+// absolute address and stages only need 128-byte alignment.
+__device__ __forceinline__ float4 ld_box(uint32_t stage_addr, int j) {
+    const uint32_t lin = stage_addr + ((uint32_t)j << 4);
+    const uint32_t phys = lin ^ (((lin >> 7) & 7u) << 4);
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(phys));
+    return v;
+}
+
+__device__ __forceinline__ float rcp_fast(float x) {          // MUFU.RCP, <= 1 ulp
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float lg2_fast(float x) {          // MUFU.LG2, abs err 2^-22.6
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// log(a / b) for a, b >= 1.  Near a == b the quotient form loses relative accuracy, so the result is
+// 2*atanh(z), z = (a-b)/(a+b), as an odd series (|z| < 0.15: truncation < 1e-9 relative); elsewhere
+// ln2 * lg2(a/b), whose absolute error is far below 1e-5 of a result that is at least 0.3.
+__device__ __forceinline__ float log_ratio(float a, float b, float rb) {
+    const float z = (a - b) * rcp_fast(a + b);
+    const float z2 = z * z;
+    float p = fmaf(z2, 1.0f / 9.0f, 1.0f / 7.0f);
+    p = fmaf(z2, p, 1.0f / 5.0f);
+    p = fmaf(z2, p, 1.0f / 3.0f);
+    const float near = 2.0f * fmaf(z * z2, p, z);
+    const float far = 0.69314718056f * lg2_fast(a * rb);
+    return fabsf(z) < 0.15f ? near : far;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -73,15 +102,15 @@ __global__ void __launch_bounds__(128) tracklet_volume_kernel(const int64_t* __r
 
 // ---- the pair kernel ----------------------------------------------------------------------------
 template <bool WRITE_GEO, bool CLIP>
-__global__ void __launch_bounds__(GEO_THREADS)
+__global__ void __launch_bounds__(GEO_THREADS, GEO_MIN_CTAS)
 pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __restrict__ table, int nv,
                 const int32_t* __restrict__ span, const double* __restrict__ vol, float* __restrict__ geo,
                 float* __restrict__ viou, float* __restrict__ tiou, int32_t* __restrict__ overlap) {
-    extern __shared__ __align__(1024) uint8_t smem[];
+    extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* const s_stage0 = smem;
     uint8_t* const o_stage0 = smem + 2 * GEO_STAGE_BYTES;
     uint64_t* const bar = reinterpret_cast<uint64_t*>(smem + 4 * GEO_STAGE_BYTES);            // [2]
-    double* const warp_part = reinterpret_cast<double*>(smem + 4 * GEO_STAGE_BYTES + 64);     // [2][WARPS][3]
+    double* const warp_part = reinterpret_cast<double*>(smem + 4 * GEO_STAGE_BYTES + 16);     // [2][WARPS][3]
     double* const acc = warp_part + 2 * GEO_WARPS * 3;                                        // [OG][3]
 
     const int tid = threadIdx.x;
@@ -144,7 +173,8 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
 
         mbar_wait(&bar[q & 1], (q >> 1) & 1);
 
-        double sum_i = 0.0, sum_s = 0.0, sum_o = 0.0;
+        // per-thread partial sums stay in fp32: 4 integer-valued products <= 4 * 2^21 < 2^24 are exact
+        float fsum_i = 0.0f, fsum_s = 0.0f, fsum_o = 0.0f;
         float out[TSPN_GEO_CHANNELS][GEO_FPT];
 #pragma unroll
         for (int ch = 0; ch < TSPN_GEO_CHANNELS; ++ch)
@@ -152,19 +182,18 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
             for (int i = 0; i < GEO_FPT; ++i) out[ch][i] = 0.0f;
 
         if (t0 < b && t0 + GEO_FPT > a) {
-            const uint8_t* ss = s_stage0 + (c & 1) * GEO_STAGE_BYTES;
-            const uint8_t* os = o_stage0 + (q & 1) * GEO_STAGE_BYTES;
+            const uint32_t ss = smem_u32(s_stage0 + (c & 1) * GEO_STAGE_BYTES);
+            const uint32_t os = smem_u32(o_stage0 + (q & 1) * GEO_STAGE_BYTES);
             float dcx[GEO_FPT + 1], dcy[GEO_FPT + 1], wo[GEO_FPT + 1], ho[GEO_FPT + 1];
             float rwo[GEO_FPT + 1], rho[GEO_FPT + 1];
 #pragma unroll
             for (int i = 0; i <= GEO_FPT; ++i) {
                 const float4 sb = ld_box(ss, j0 + i);
                 const float4 ob = ld_box(os, j0 + i);
-                const float ws = (sb.z - sb.x) + 1.0f, hs = (sb.w - sb.y) + 1.0f;
                 wo[i] = (ob.z - ob.x) + 1.0f;
                 ho[i] = (ob.w - ob.y) + 1.0f;
-                rwo[i] = __frcp_rn(wo[i]);
-                rho[i] = __frcp_rn(ho[i]);
+                rwo[i] = rcp_fast(wo[i]);
+                rho[i] = rcp_fast(ho[i]);
                 // centre deltas from coordinate differences: exact for integer boxes and
                 // free of the cancellation that (x1+x2)/2 - (x1'+x2')/2 would carry
                 dcx[i] = 0.5f * ((sb.x - ob.x) + (sb.z - ob.z));
@@ -172,6 +201,7 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
                 if (i < GEO_FPT) {
                     const int t = t0 + i;
                     const bool in = (t >= a) && (t < b);
+                    const float ws = (sb.z - sb.x) + 1.0f, hs = (sb.w - sb.y) + 1.0f;
                     const float iw = fmaxf((fminf(sb.z, ob.z) - fmaxf(sb.x, ob.x)) + 1.0f, 0.0f);
                     const float ih = fmaxf((fminf(sb.w, ob.w) - fmaxf(sb.y, ob.y)) + 1.0f, 0.0f);
                     const float inter = iw * ih;
@@ -179,14 +209,14 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
                     if (in) {
                         out[0][i] = dcx[i] * rwo[i];
                         out[1][i] = dcy[i] * rho[i];
-                        out[2][i] = log1pf((ws - wo[i]) * rwo[i]);
-                        out[3][i] = log1pf((hs - ho[i]) * rho[i]);
-                        out[4][i] = inter / ((as + ao) - inter);
+                        out[2][i] = log_ratio(ws, wo[i], rwo[i]);
+                        out[3][i] = log_ratio(hs, ho[i], rho[i]);
+                        out[4][i] = inter * rcp_fast((as + ao) - inter);
                         out[7][i] = 1.0f;
-                        sum_i += (double)inter;
+                        fsum_i += inter;
                         if (CLIP) {
-                            sum_s += (double)as;
-                            sum_o += (double)ao;
+                            fsum_s += as;
+                            fsum_o += ao;
                         }
                     }
                 }
@@ -207,6 +237,7 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
                 }
             }
         }
+        double sum_i = (double)fsum_i, sum_s = (double)fsum_s, sum_o = (double)fsum_o;
         if (WRITE_GEO && t0 < tp) {
             float* g = geo + row[TSPN_VT_GEO_OFF] + ((int64_t)(s * (n - 1) + k) * TSPN_GEO_CHANNELS) * tp + t0;
 #pragma unroll

@@ -1,0 +1,186 @@
+// postproc.cu — relation triplet records (row N1 of SURVEY.md section 8f).
+//
+//   tspn_postprocess   lib/modeling/predict.py:66-117
+//     top `topk_per_pair` (20) predicates of every scored pair  (predict.py:70-73),
+//     top `topk_per_video` (200) of those per video             (predict.py:76-81),
+//     subject / object class = argmax of the tracklet classeme  (predict.py:88-93, quirk Q4),
+//     one fixed 32-byte record per kept triplet — the payload of the multi-GPU all-gather.
+//
+// Both selections are descending with ties to the lower index ([SPEC] s6); the reference does
+// this with two full torch.sort calls and per-element Python list comprehensions.
+#include "common.cuh"
+#include "topk_block.cuh"
+
+namespace tspn {
+
+constexpr int PP_MAX_R = 256;     // predicates per row handled by one warp (8 per lane)
+
+// one warp per scored row: its topk_per_pair best predicates, in order
+__global__ void __launch_bounds__(128)
+pair_top_predicates_kernel(const float* __restrict__ logits, const int64_t* __restrict__ rows, int64_t m, int r,
+                           int tpp, float* __restrict__ cand_score, int32_t* __restrict__ cand_pred) {
+    const int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (row >= m) return;
+    const int lane = threadIdx.x & 31;
+    const float NEG_INF = __uint_as_float(0xff800000u);
+    float* cs = cand_score + row * tpp;
+    int32_t* cp = cand_pred + row * tpp;
+    if (rows && rows[row] < 0) {                 // padding row: no candidates
+        for (int j = lane; j < tpp; j += 32) {
+            cs[j] = NEG_INF;
+            cp[j] = -1;
+        }
+        return;
+    }
+    float v[PP_MAX_R / 32];
+#pragma unroll
+    for (int j = 0; j < PP_MAX_R / 32; ++j) {
+        const int c = lane + 32 * j;
+        v[j] = c < r ? __ldg(logits + row * r + c) : NEG_INF;
+    }
+    for (int it = 0; it < tpp; ++it) {
+        float best = NEG_INF;
+        int bi = 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < PP_MAX_R / 32; ++j) {
+            const int c = lane + 32 * j;
+            if (c < r && (v[j] > best || (v[j] == best && c < bi))) {
+                best = v[j];
+                bi = c;
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (ob > best || (ob == best && oi < bi)) {
+                best = ob;
+                bi = oi;
+            }
+        }
+        if (bi == 0x7fffffff) {                 // fewer than tpp predicates
+            if (lane == 0) {
+                cs[it] = NEG_INF;
+                cp[it] = -1;
+            }
+            continue;
+        }
+        if (lane == 0) {
+            cs[it] = best;
+            cp[it] = bi;
+        }
+        if ((bi & 31) == lane) {
+#pragma unroll
+            for (int j = 0; j < PP_MAX_R / 32; ++j)
+                if (j == (bi >> 5)) v[j] = NEG_INF;
+        }
+    }
+}
+
+__device__ __forceinline__ int argmax_row(const float* __restrict__ x, int c) {
+    float best = __ldg(x);
+    int bi = 0;
+    for (int i = 1; i < c; ++i) {
+        const float q = __ldg(x + i);
+        if (q > best) {
+            best = q;
+            bi = i;
+        }
+    }
+    return bi;
+}
+
+// one CTA per video: top `tpv` of its (rows x tpp) candidates -> records
+__global__ void __launch_bounds__(TOPK_THREADS)
+video_top_triplets_kernel(const int64_t* __restrict__ table, int nv, const float* __restrict__ cand_score,
+                          const int32_t* __restrict__ cand_pred, const int64_t* __restrict__ rows,
+                          const int64_t* __restrict__ row_video_off, int tpp, int tpv,
+                          const float* __restrict__ cls, int n_classes, const int32_t* __restrict__ overlap,
+                          int mirror_q4, int32_t* __restrict__ records, int32_t* __restrict__ counts) {
+    __shared__ TopkSmem sm;
+    const int v = blockIdx.x;
+    const int64_t* row = table + (int64_t)v * TSPN_VT_COLS;
+    const int n = (int)row[TSPN_VT_N];
+    const int64_t pair_off = row[TSPN_VT_PAIR_OFF];
+    const int64_t r0 = row_video_off ? row_video_off[v] : pair_off;
+    const int64_t r1 = row_video_off ? row_video_off[v + 1] : pair_off + (int64_t)n * (n > 0 ? n - 1 : 0);
+    const float* cs = cand_score + r0 * tpp;
+    const int64_t total = (r1 - r0) * tpp;
+    const int k_eff = block_topk(sm, total, tpv, [&](int64_t i) -> float { return __ldg(cs + i); });
+    int32_t* rec = records + (int64_t)v * tpv * 8;
+    for (int i = threadIdx.x; i < tpv; i += TOPK_THREADS) {
+        int32_t out[8] = {0, -1, -1, -1, -1, -1, 0, 0};
+        if (i < k_eff) {
+            const uint32_t flat = (uint32_t)(sm.sel[i] & 0xffffffffu);
+            const int64_t rr = r0 + flat / (uint32_t)tpp;
+            const int64_t gp = rows ? rows[rr] : rr;
+            const int p = (int)(gp - pair_off);
+            const int s = p / (n - 1);
+            const int k = p - s * (n - 1);
+            const int o = k + (k >= s ? 1 : 0);
+            const int64_t trk0 = row[TSPN_VT_TRK_OFF];
+            // predict.py:89 reads the object's class from pair row (N-1)*o, whose object is tracklet
+            // 0 (or 1 when o == 0): quirk Q4, reproduced only on request
+            const int o_src = mirror_q4 ? (o == 0 ? 1 : 0) : o;
+            out[0] = __float_as_int(__ldg(cs + flat));
+            out[1] = argmax_row(cls + (trk0 + s) * n_classes, n_classes);
+            out[2] = __ldg(cand_pred + r0 * tpp + flat);
+            out[3] = argmax_row(cls + (trk0 + o_src) * n_classes, n_classes);
+            out[4] = s;
+            out[5] = o;
+            out[6] = __ldg(overlap + 2 * gp);
+            out[7] = __ldg(overlap + 2 * gp + 1);
+        }
+        int4* dst = reinterpret_cast<int4*>(rec + (int64_t)i * 8);
+        dst[0] = make_int4(out[0], out[1], out[2], out[3]);
+        dst[1] = make_int4(out[4], out[5], out[6], out[7]);
+    }
+    if (threadIdx.x == 0) counts[v] = k_eff;
+}
+
+}  // namespace tspn
+
+using namespace tspn;
+
+extern "C" {
+
+int64_t tspn_postprocess_workspace_bytes(int64_t m, int topk_per_pair) {
+    if (m <= 0 || topk_per_pair <= 0) return 16;
+    return m * (int64_t)topk_per_pair * 8 + 16;
+}
+
+int tspn_postprocess(const int64_t* d_table, int num_videos, const float* d_logits, const int64_t* d_rows,
+                     const int64_t* d_row_video_off, int64_t n_rows, int n_predicates, const float* d_cls,
+                     int n_classes, const int32_t* d_overlap, int topk_per_pair, int topk_per_video, int flags,
+                     int32_t* d_records, int32_t* d_counts, void* d_workspace, void* stream) {
+    TSPN_ARCH_OK();
+    TSPN_REQUIRE(num_videos >= 0 && n_rows >= 0 && n_predicates > 0 && n_classes > 0 && topk_per_pair > 0 &&
+                     topk_per_video > 0,
+                 TSPN_EBADARG, "tspn_postprocess: bad size");
+    TSPN_REQUIRE(n_predicates <= PP_MAX_R, TSPN_ESHAPE, "tspn_postprocess: at most %d predicates", PP_MAX_R);
+    TSPN_REQUIRE(topk_per_video <= TOPK_MAX_K, TSPN_ESHAPE, "tspn_postprocess: topk_per_video must be <= %d",
+                 TOPK_MAX_K);
+    if (num_videos == 0) return TSPN_OK;
+    TSPN_REQUIRE(d_table && d_cls && d_overlap && d_records && d_counts && d_workspace && (d_logits || n_rows == 0),
+                 TSPN_EBADARG, "tspn_postprocess: null pointer");
+    TSPN_REQUIRE(aligned16(d_records) && aligned16(d_workspace), TSPN_EALIGN,
+                 "tspn_postprocess: records/workspace must be 16-byte aligned");
+    TSPN_REQUIRE(n_rows * (int64_t)topk_per_pair < (1ll << 31), TSPN_ESHAPE, "tspn_postprocess: too many candidates");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int tpp = topk_per_pair < n_predicates ? topk_per_pair : n_predicates;
+    float* cand_score = reinterpret_cast<float*>(d_workspace);
+    int32_t* cand_pred = reinterpret_cast<int32_t*>(cand_score + n_rows * tpp);
+    if (n_rows > 0) {
+        pair_top_predicates_kernel<<<(unsigned)((n_rows + 3) / 4), 128, 0, st>>>(d_logits, d_rows, n_rows,
+                                                                                n_predicates, tpp, cand_score,
+                                                                                cand_pred);
+        TSPN_CUDA_OK(cudaGetLastError());
+    }
+    video_top_triplets_kernel<<<(unsigned)num_videos, TOPK_THREADS, 0, st>>>(
+        d_table, num_videos, cand_score, cand_pred, d_rows, d_row_video_off, tpp, topk_per_video, d_cls, n_classes,
+        d_overlap, (flags & TSPN_POST_MIRROR_Q4) ? 1 : 0, d_records, d_counts);
+    TSPN_CUDA_OK(cudaGetLastError());
+    return TSPN_OK;
+}
+
+}  // extern "C"

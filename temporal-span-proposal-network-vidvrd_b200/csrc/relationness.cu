@@ -16,6 +16,7 @@
 // ([SPEC] s6 == torch.sort(stable=True)).
 #include "common.cuh"
 #include "exact_math.cuh"
+#include "topk_block.cuh"
 
 namespace tspn {
 
@@ -73,138 +74,40 @@ pair_scores_kernel(const int64_t* __restrict__ table, int nv, const float* __res
 }
 
 // ---- top-K ---------------------------------------------------------------------------------------
-constexpr int TOPK_THREADS = 256;
-constexpr int TOPK_MAX_K = 1024;
-
-__device__ __forceinline__ uint32_t order_key(float f) {
-    const uint32_t b = __float_as_uint(f);
-    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);      // larger float <=> larger key
-}
-
 __global__ void __launch_bounds__(TOPK_THREADS)
 topk_kernel(const int64_t* __restrict__ table, int nv, const float* __restrict__ scores, int K, int exclude_diag,
             int64_t* __restrict__ out_idx, float* __restrict__ out_score, int64_t* __restrict__ out_row) {
-    __shared__ uint32_t hist[256];
-    __shared__ uint64_t sel[TOPK_MAX_K];
-    __shared__ uint32_t sh_prefix, sh_need, sh_count, sh_tie_base;
-    __shared__ uint32_t warp_cnt[TOPK_THREADS / 32];
-
+    __shared__ TopkSmem sm;
     const int v = blockIdx.x;
     const int64_t* row = table + (int64_t)v * TSPN_VT_COLS;
-    const int n = (int)row[TSPN_VT_N];
+    const uint32_t n = (uint32_t)row[TSPN_VT_N];
     const int64_t total = (int64_t)n * n;
     const float* sc = scores + row[TSPN_VT_SCORE_OFF];
-    const int64_t cand = exclude_diag ? total - n : total;
-    const int k_eff = (int)min((int64_t)K, cand);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
+    const float NEG_INF = __uint_as_float(0xff800000u);
+
+    const int k_eff = block_topk(sm, total, K, [&](int64_t i) -> float {
+        const uint32_t u = (uint32_t)i;
+        if (exclude_diag && (u / n) == (u % n)) return NEG_INF;     // the diagonal is not a candidate
+        return __ldg(sc + i);
+    });
 
     int64_t* oi = out_idx + (int64_t)v * K;
     float* os = out_score + (int64_t)v * K;
     int64_t* orow = out_row ? out_row + (int64_t)v * K : nullptr;
-    for (int i = k_eff + tid; i < K; i += TOPK_THREADS) {
-        oi[i] = -1;
-        os[i] = 0.0f;
-        if (orow) orow[i] = -1;
-    }
-    if (k_eff == 0) return;
-
-    // -- MSD radix select: find the key of the k_eff-th largest candidate -------------------------
-    if (tid == 0) {
-        sh_prefix = 0;
-        sh_need = (uint32_t)k_eff;      // rank (1-based, from the top) still to locate
-    }
-    uint32_t prefix_mask = 0;
-    for (int shift = 24; shift >= 0; shift -= 8) {
-        hist[tid] = 0;                  // TOPK_THREADS == 256 bins
-        __syncthreads();
-        const uint32_t prefix = sh_prefix;
-        for (int64_t i = tid; i < total; i += TOPK_THREADS) {
-            if (exclude_diag && (i / n) == (i % n)) continue;
-            const uint32_t key = order_key(__ldg(sc + i));
-            if ((key & prefix_mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xffu], 1u);
-        }
-        __syncthreads();
-        if (tid == 0) {
-            uint32_t need = sh_need, d = 255;
-            for (;; --d) {              // walk the buckets from the top
-                const uint32_t c = hist[d];
-                if (c >= need) break;
-                need -= c;
-                if (d == 0) break;
+    for (int i = tid; i < K; i += TOPK_THREADS) {
+        if (i < k_eff) {
+            const uint32_t flat = (uint32_t)(sm.sel[i] & 0xffffffffu);
+            oi[i] = (int64_t)flat;
+            os[i] = __ldg(sc + flat);
+            if (orow) {
+                const int s = (int)(flat / n), o = (int)(flat % n);
+                orow[i] = (s == o) ? -1 : row[TSPN_VT_PAIR_OFF] + (int64_t)s * (n - 1) + o - (o > s ? 1 : 0);
             }
-            sh_need = need;             // rank inside bucket d
-            sh_prefix = prefix | (d << shift);
-        }
-        prefix_mask |= 0xffu << shift;
-        __syncthreads();
-    }
-    const uint32_t thr = sh_prefix;     // key of the k_eff-th largest
-    const uint32_t need_ties = sh_need; // how many candidates with key == thr are kept
-    if (tid == 0) {
-        sh_count = 0;
-        sh_tie_base = 0;
-    }
-    __syncthreads();
-
-    // -- collect: everything above the threshold (any order), then the ties in index order -----------
-    const uint32_t n_above = (uint32_t)k_eff - need_ties;
-    for (int64_t base = 0; base < total; base += TOPK_THREADS) {
-        const int64_t i = base + tid;
-        bool above = false, tie = false;
-        uint32_t key = 0;
-        if (i < total && !(exclude_diag && (i / n) == (i % n))) {
-            key = order_key(__ldg(sc + i));
-            above = key > thr;
-            tie = key == thr;
-        }
-        if (above) {
-            const uint32_t slot = atomicAdd(&sh_count, 1u);
-            sel[slot] = ((uint64_t)(~key) << 32) | (uint32_t)i;
-        }
-        // ordered compaction of the ties: rank = ties with a lower flat index
-        const uint32_t bal = __ballot_sync(0xffffffffu, tie);
-        if (lane == 0) warp_cnt[warp] = __popc(bal);
-        __syncthreads();
-        uint32_t before = sh_tie_base;
-        for (int w = 0; w < warp; ++w) before += warp_cnt[w];
-        const uint32_t rank = before + __popc(bal & ((1u << lane) - 1u));
-        if (tie && rank < need_ties) sel[n_above + rank] = ((uint64_t)(~key) << 32) | (uint32_t)i;
-        __syncthreads();
-        if (tid == 0) {
-            uint32_t t = 0;
-            for (int w = 0; w < TOPK_THREADS / 32; ++w) t += warp_cnt[w];
-            sh_tie_base += t;
-        }
-        __syncthreads();
-    }
-
-    // -- bitonic sort of the survivors: ascending (~key, idx) == descending score, ascending index ----
-    int m = 1;
-    while (m < k_eff) m <<= 1;
-    for (int i = k_eff + tid; i < m; i += TOPK_THREADS) sel[i] = ~0ull;
-    __syncthreads();
-    for (int size = 2; size <= m; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int i = tid; i < m / 2; i += TOPK_THREADS) {
-                const int lo = 2 * i - (i & (stride - 1));
-                const int hi = lo + stride;
-                const bool up = (lo & size) == 0;
-                const uint64_t a = sel[lo], b = sel[hi];
-                if ((a > b) == up) {
-                    sel[lo] = b;
-                    sel[hi] = a;
-                }
-            }
-            __syncthreads();
-        }
-    }
-    for (int i = tid; i < k_eff; i += TOPK_THREADS) {
-        const uint32_t flat = (uint32_t)(sel[i] & 0xffffffffu);
-        oi[i] = (int64_t)flat;
-        os[i] = __ldg(sc + flat);
-        if (orow) {
-            const int s = (int)(flat / (uint32_t)n), o = (int)(flat % (uint32_t)n);
-            orow[i] = (s == o) ? -1 : row[TSPN_VT_PAIR_OFF] + (int64_t)s * (n - 1) + o - (o > s ? 1 : 0);
+        } else {
+            oi[i] = -1;
+            os[i] = 0.0f;
+            if (orow) orow[i] = -1;
         }
     }
 }

@@ -15,7 +15,8 @@
 
 namespace tspn {
 
-int span_head_tensor(const float* d_x, const int64_t* d_rows, int64_t row_stride, int64_t ld_t, int64_t k, int cin,
+int span_head_tensor(const float* d_x, const int64_t* d_rows, int64_t row_base, int64_t row_stride, int64_t ld_t,
+                     int64_t k, int cin,
                      int t, const float* d_conv_w, const float* d_conv_b, const float* d_pred_w,
                      const float* d_pred_b, int a2, float* d_out, void* d_workspace, cudaStream_t st);
 
@@ -24,15 +25,15 @@ constexpr int SH_MAX_A2 = 16;
 constexpr int SH_REG_CIN = 16;
 
 __global__ void __launch_bounds__(SH_THREADS)
-span_head_exact_kernel(const float* __restrict__ x, const int64_t* __restrict__ rows, int64_t row_stride,
-                       int64_t ld_t, int cin, int t_len, const float* __restrict__ conv_w,
+span_head_exact_kernel(const float* __restrict__ x, const int64_t* __restrict__ rows, int64_t row_base,
+                       int64_t row_stride, int64_t ld_t, int cin, int t_len, const float* __restrict__ conv_w,
                        const float* __restrict__ conv_b, const float* __restrict__ pred_w,
                        const float* __restrict__ pred_b, int a2, float* __restrict__ out) {
     const int64_t p = blockIdx.y;
     const int t = blockIdx.x * SH_THREADS + threadIdx.x;
     if (t >= t_len) return;
     float* o = out + p * a2 * (int64_t)t_len + t;
-    const int64_t src = rows ? rows[p] : p;
+    const int64_t src = rows ? rows[p] - (rows[p] >= 0 ? row_base : 0) : p;
     if (src < 0) {
         for (int j = 0; j < a2; ++j) o[(int64_t)j * t_len] = 0.0f;
         return;
@@ -86,6 +87,102 @@ span_head_exact_kernel(const float* __restrict__ x, const int64_t* __restrict__ 
         if (j < a2) o[(int64_t)j * t_len] = acc[j];
 }
 
+// Small-channel specialisation (the pair stage feeds the 8 geometry channels): weights staged in
+// shared memory as 128-bit broadcast reads, a thread owns 4 consecutive frames (128-bit loads and
+// stores), same fma order per output as the generic kernel -> same bits.
+template <int CIN, int A2>
+__global__ void __launch_bounds__(SH_THREADS)
+span_head_small_kernel(const float* __restrict__ x, const int64_t* __restrict__ rows, int64_t row_base,
+                       int64_t row_stride, int64_t ld_t, int t_len, const float* __restrict__ conv_w,
+                       const float* __restrict__ conv_b, const float* __restrict__ pred_w,
+                       const float* __restrict__ pred_b, float* __restrict__ out) {
+    __shared__ __align__(16) float4 w_conv[CIN * CIN];      // [co][ci] -> (w0, w1, w2, -)
+    __shared__ __align__(16) float w_pred[CIN * A2];        // [co][j]
+    __shared__ float b_conv[CIN], b_pred[A2];
+    for (int i = threadIdx.x; i < CIN * CIN; i += SH_THREADS)
+        w_conv[i] = make_float4(__ldg(conv_w + i * 3), __ldg(conv_w + i * 3 + 1), __ldg(conv_w + i * 3 + 2), 0.0f);
+    for (int i = threadIdx.x; i < CIN * A2; i += SH_THREADS) {
+        const int co = i / A2, j = i - co * A2;
+        w_pred[i] = __ldg(pred_w + j * CIN + co);
+    }
+    if (threadIdx.x < CIN) b_conv[threadIdx.x] = conv_b ? __ldg(conv_b + threadIdx.x) : 0.0f;
+    if (threadIdx.x < A2) b_pred[threadIdx.x] = pred_b ? __ldg(pred_b + threadIdx.x) : 0.0f;
+    __syncthreads();
+
+    const int64_t p = blockIdx.y;
+    const int t0 = (blockIdx.x * SH_THREADS + threadIdx.x) * 4;
+    if (t0 >= t_len) return;
+    float* o = out + p * A2 * (int64_t)t_len + t0;
+    const bool vec_out = ((t_len & 3) == 0) && t0 + 3 < t_len;
+    const int64_t src = rows ? rows[p] - (rows[p] >= 0 ? row_base : 0) : p;
+    if (src < 0) {
+#pragma unroll
+        for (int j = 0; j < A2; ++j)
+            for (int i = 0; i < 4 && t0 + i < t_len; ++i) o[(int64_t)j * t_len + i] = 0.0f;
+        return;
+    }
+    const float* xr = x + src * row_stride + t0;
+    // xv[ci][0..5] = x[ci][t0-1 .. t0+4], zero outside [0, T)
+    float xv[CIN][6];
+    const bool vec_in = ((ld_t & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((row_stride & 3) == 0) &&
+                        t0 + 3 < t_len;
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) {
+        const float* xc = xr + (int64_t)ci * ld_t;
+        if (vec_in) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(xc));
+            xv[ci][1] = q.x; xv[ci][2] = q.y; xv[ci][3] = q.z; xv[ci][4] = q.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) xv[ci][1 + i] = (t0 + i < t_len) ? __ldg(xc + i) : 0.0f;
+        }
+        xv[ci][0] = t0 > 0 ? __ldg(xc - 1) : 0.0f;
+        xv[ci][5] = t0 + 4 < t_len ? __ldg(xc + 4) : 0.0f;
+    }
+    float acc[A2][4];
+#pragma unroll
+    for (int j = 0; j < A2; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[j][i] = b_pred[j];
+#pragma unroll 1
+    for (int co = 0; co < CIN; ++co) {
+        float h[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = b_conv[co];
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+            const float4 w = w_conv[co * CIN + ci];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int t = t0 + i;
+                // taps outside [0, T) are skipped, not multiplied by zero (same chain as the oracle)
+                if (t > 0) h[i] = __fmaf_rn(w.x, xv[ci][i], h[i]);
+                h[i] = __fmaf_rn(w.y, xv[ci][i + 1], h[i]);
+                if (t + 1 < t_len) h[i] = __fmaf_rn(w.z, xv[ci][i + 2], h[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = fmaxf(h[i], 0.0f);
+#pragma unroll
+        for (int j = 0; j < A2; ++j) {
+            const float wp = w_pred[co * A2 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[j][i] = __fmaf_rn(wp, h[i], acc[j][i]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < A2; ++j) {
+        float* oj = o + (int64_t)j * t_len;
+        if (vec_out) {
+            *reinterpret_cast<float4*>(oj) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (t0 + i < t_len) oj[i] = acc[j][i];
+        }
+    }
+}
+
 // [SPEC] s5, every step one correctly rounded fp32 operation (see oracle/exact).
 __global__ void __launch_bounds__(256)
 span_decode_kernel(const float* __restrict__ reg, int64_t k, int a_n, int t_len, int n_loc,
@@ -129,8 +226,8 @@ int tspn_span_num_locations(int t, float stride) {
     return n;
 }
 
-int tspn_span_head(const float* d_x, const int64_t* d_rows, int64_t row_stride, int64_t ld_t, int64_t k, int cin,
-                   int t, const float* d_conv_w, const float* d_conv_b, const float* d_pred_w,
+int tspn_span_head(const float* d_x, const int64_t* d_rows, int64_t row_base, int64_t row_stride, int64_t ld_t,
+                   int64_t k, int cin, int t, const float* d_conv_w, const float* d_conv_b, const float* d_pred_w,
                    const float* d_pred_b, int a2, float* d_out, int precision, void* d_workspace, void* stream) {
     TSPN_ARCH_OK();
     TSPN_REQUIRE(k >= 0 && cin > 0 && t > 0 && a2 > 0 && ld_t >= t && row_stride >= 0, TSPN_EBADARG,
@@ -142,14 +239,20 @@ int tspn_span_head(const float* d_x, const int64_t* d_rows, int64_t row_stride, 
     TSPN_REQUIRE(k < 65536, TSPN_ESHAPE, "tspn_span_head: k=%lld must be < 65536 per call", (long long)k);
     cudaStream_t st = (cudaStream_t)stream;
     if (precision == TSPN_PREC_FP32_EXACT) {
-        dim3 grid((unsigned)((t + SH_THREADS - 1) / SH_THREADS), (unsigned)k);
-        span_head_exact_kernel<<<grid, SH_THREADS, 0, st>>>(d_x, d_rows, row_stride, ld_t, cin, t, d_conv_w,
-                                                            d_conv_b, d_pred_w, d_pred_b, a2, d_out);
+        if (cin == 8 && a2 == 8) {
+            dim3 grid((unsigned)((t + 4 * SH_THREADS - 1) / (4 * SH_THREADS)), (unsigned)k);
+            span_head_small_kernel<8, 8><<<grid, SH_THREADS, 0, st>>>(d_x, d_rows, row_base, row_stride, ld_t, t,
+                                                                      d_conv_w, d_conv_b, d_pred_w, d_pred_b, d_out);
+        } else {
+            dim3 grid((unsigned)((t + SH_THREADS - 1) / SH_THREADS), (unsigned)k);
+            span_head_exact_kernel<<<grid, SH_THREADS, 0, st>>>(d_x, d_rows, row_base, row_stride, ld_t, cin, t,
+                                                                d_conv_w, d_conv_b, d_pred_w, d_pred_b, a2, d_out);
+        }
         TSPN_CUDA_OK(cudaGetLastError());
         return TSPN_OK;
     }
     TSPN_REQUIRE(precision == TSPN_PREC_TENSOR, TSPN_EBADARG, "tspn_span_head: unknown precision %d", precision);
-    return span_head_tensor(d_x, d_rows, row_stride, ld_t, k, cin, t, d_conv_w, d_conv_b, d_pred_w, d_pred_b, a2,
+    return span_head_tensor(d_x, d_rows, row_base, row_stride, ld_t, k, cin, t, d_conv_w, d_conv_b, d_pred_w, d_pred_b, a2,
                             d_out, d_workspace, st);
 }
 

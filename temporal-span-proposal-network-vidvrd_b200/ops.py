@@ -18,6 +18,19 @@ PREC = {"fp32": _lib.PREC_FP32_EXACT, "exact": _lib.PREC_FP32_EXACT, "fp32_exact
         "tensor": _lib.PREC_TENSOR, "bf16": _lib.PREC_TENSOR, "tf32": _lib.PREC_TENSOR}
 
 
+# kernels launched by this process through the C ABI (bench.py reports it as gpu_launches)
+_LAUNCHES = 0
+
+
+def launch_count() -> int:
+    return _LAUNCHES
+
+
+def _count(n: int) -> None:
+    global _LAUNCHES
+    _LAUNCHES += n
+
+
 def _cuda(t: torch.Tensor, dtype=None) -> torch.Tensor:
     if not t.is_cuda:
         raise RuntimeError("tspn_b200 ops need CUDA tensors (there is no CPU path)")
@@ -39,6 +52,7 @@ def enumerate_pairs(batch: DeviceBatch) -> torch.Tensor:
     out = torch.empty((batch.total_pairs, 2), dtype=torch.int64, device=batch.device)
     check(load().tspn_enumerate_pairs(ptr(batch.table), batch.num_videos, batch.total_pairs, ptr(out),
                                       stream_ptr()), "tspn_enumerate_pairs")
+    _count(1)
     return out
 
 
@@ -61,6 +75,7 @@ def pair_geometry(batch: DeviceBatch, write_geo: bool = True, clipped: bool = Fa
         int(tot[_lib.TOT_BOXES]), ptr(batch.boxes), ptr(batch.span), ptr(out.get("geo")), ptr(out["viou"]),
         ptr(out["tiou"]), ptr(out["overlap"]), _lib.VIOU_CLIPPED if clipped else _lib.VIOU_FULL,
         ptr(out["workspace"]), stream_ptr()), "tspn_pair_geo_viou")
+    _count(1 if clipped else 2)
     return out
 
 
@@ -72,6 +87,7 @@ def cubic_iou(b1: torch.Tensor, b2: torch.Tensor) -> torch.Tensor:
     out = torch.empty((b1.shape[0], b2.shape[0]), dtype=torch.float32, device=b1.device)
     check(load().tspn_cubic_iou(ptr(b1), b1.shape[0], ptr(b2), b2.shape[0], b1.shape[1], ptr(out), stream_ptr()),
           "tspn_cubic_iou")
+    _count(1)
     return out
 
 
@@ -84,6 +100,7 @@ def viou_pairs(pool: torch.Tensor, traj_off: torch.Tensor, traj_span: torch.Tens
                                  ptr(_cuda(a, torch.int32)), ptr(_cuda(b, torch.int32)), a.shape[0],
                                  _lib.VIOU_CLIPPED if clipped else _lib.VIOU_FULL, ptr(out), stream_ptr()),
           "tspn_viou_pairs")
+    _count(1)
     return out
 
 
@@ -92,6 +109,7 @@ def normalize_motion(motion: torch.Tensor) -> torch.Tensor:
     out = torch.empty_like(motion)
     check(load().tspn_normalize_motion(ptr(motion), motion.shape[0], ptr(out), stream_ptr()),
           "tspn_normalize_motion")
+    _count(1)
     return out
 
 
@@ -124,6 +142,7 @@ def assemble_features(batch: DeviceBatch, motion_norm: torch.Tensor, geo: torch.
         ptr(batch.table), batch.num_videos, batch.total_pairs, ptr(batch.cls), c, ptr(motion_norm), ptr(geo),
         ptr(overlap), ptr(rows), n_rows, ptr(out_fp32), out_fp32.stride(0) if out_fp32 is not None else 0,
         ptr(out_bf16), out_bf16.stride(0) if out_bf16 is not None else 0, stream_ptr()), "tspn_assemble_features")
+    _count(1)
     return (out_fp32[:, :f] if out_fp32 is not None else None,
             out_bf16[:, :f] if out_bf16 is not None else None)
 
@@ -145,6 +164,7 @@ def relationness(batch: DeviceBatch, weights, cls: Optional[torch.Tensor] = None
                      dtype=torch.float32, device=dev)
     check(load().tspn_relationness(ptr(batch.table), batch.num_videos, batch.total_tracklets, ptr(cls), c, h,
                                    *[ptr(t) for t in w], ptr(scores), ptr(ws), stream_ptr()), "tspn_relationness")
+    _count(2)
     return scores
 
 
@@ -158,6 +178,7 @@ def topk_pairs(batch: DeviceBatch, scores: torch.Tensor, k: int, exclude_diagona
     check(load().tspn_topk_pairs(ptr(batch.table), v, ptr(scores), k,
                                  _lib.TOPK_EXCLUDE_DIAGONAL if exclude_diagonal else _lib.TOPK_KEEP_DIAGONAL,
                                  ptr(idx), ptr(val), ptr(row), stream_ptr()), "tspn_topk_pairs")
+    _count(1)
     return idx, val, row
 
 
@@ -169,6 +190,7 @@ def pack_predicate_weights(weight: torch.Tensor) -> torch.Tensor:
     packed = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
     check(load().tspn_pack_predicate_weights(ptr(weight), r, f, ptr(packed), stream_ptr()),
           "tspn_pack_predicate_weights")
+    _count(1)
     return packed
 
 
@@ -196,12 +218,13 @@ def predicate_head(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, pr
                                      ptr(_cuda(weight, torch.float32)), ptr(packed),
                                      ptr(_cuda(bias, torch.float32)), r, ptr(y), prec, ptr(ws), stream_ptr()),
           "tspn_predicate_head")
+    _count(1 if prec == _lib.PREC_FP32_EXACT or ws is None or ws.numel() <= 16 else 2)
     return y
 
 
 def span_head(x: torch.Tensor, conv_w: torch.Tensor, conv_b: torch.Tensor, pred_w: torch.Tensor,
               pred_b: torch.Tensor, rows: Optional[torch.Tensor] = None, t: Optional[int] = None,
-              precision: str = "fp32") -> torch.Tensor:
+              precision: str = "fp32", row_base: int = 0) -> torch.Tensor:
     """DPNHead (dpn.py:69-73) on ``x [K, Cin, T]`` or, with ``rows``, on gathered rows of ``x``.
 
     ``x`` may be a ``[P, Cin, Tp]`` buffer whose rows are padded to ``Tp >= t``.
@@ -219,11 +242,12 @@ def span_head(x: torch.Tensor, conv_w: torch.Tensor, conv_b: torch.Tensor, pred_
     if prec == _lib.PREC_TENSOR:
         nbytes = load().tspn_span_head_workspace_bytes(k, cin, t, a2, prec)
         ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=x.device)
-    check(load().tspn_span_head(ptr(x), ptr(rows), cin * ld_t, ld_t, k, cin, t,
+    check(load().tspn_span_head(ptr(x), ptr(rows), int(row_base), cin * ld_t, ld_t, k, cin, t,
                                 ptr(_cuda(conv_w, torch.float32)), ptr(_cuda(conv_b, torch.float32)),
                                 ptr(_cuda(pred_w.reshape(a2, cin), torch.float32)),
                                 ptr(_cuda(pred_b, torch.float32)), a2, ptr(out), prec, ptr(ws), stream_ptr()),
           "tspn_span_head")
+    _count(1)
     return out
 
 
@@ -240,4 +264,32 @@ def span_decode(reg: torch.Tensor, sizes: torch.Tensor, stride: float) -> torch.
     out = torch.empty((k, n_loc * a, 2), dtype=torch.int32, device=reg.device)
     check(load().tspn_span_decode(ptr(reg), k, a, t, ptr(_cuda(sizes, torch.float32)), float(stride), ptr(out),
                                   stream_ptr()), "tspn_span_decode")
+    _count(1)
     return out
+
+
+RECORD_FIELDS = ("score", "s_cls", "pred", "o_cls", "s_tid", "o_tid", "start", "end")
+
+
+def postprocess(batch: DeviceBatch, logits: torch.Tensor, overlap: torch.Tensor, topk_per_pair: int = 20,
+                topk_per_video: int = 200, rows: Optional[torch.Tensor] = None,
+                row_video_off: Optional[torch.Tensor] = None, mirror_q4: bool = False):
+    """Relation triplet records (predict.py:66-117): ``records [V, topk_per_video, 8]`` int32
+    (field 0 is the fp32 score's bit pattern) and ``counts [V]`` int32."""
+    logits = _cuda(logits, torch.float32)
+    m, r = logits.shape
+    v = batch.num_videos
+    dev = logits.device
+    records = torch.empty((v, topk_per_video, 8), dtype=torch.int32, device=dev)
+    counts = torch.empty(v, dtype=torch.int32, device=dev)
+    ws = torch.empty(load().tspn_postprocess_workspace_bytes(m, topk_per_pair), dtype=torch.uint8, device=dev)
+    check(load().tspn_postprocess(ptr(batch.table), v, ptr(logits), ptr(rows), ptr(row_video_off), m, r,
+                                  ptr(batch.cls), batch.cls.shape[1], ptr(overlap), topk_per_pair, topk_per_video,
+                                  1 if mirror_q4 else 0, ptr(records), ptr(counts), ptr(ws), stream_ptr()),
+          "tspn_postprocess")
+    _count(2)
+    return records, counts
+
+
+def record_scores(records: torch.Tensor) -> torch.Tensor:
+    return records[..., 0].contiguous().view(torch.float32)

@@ -33,6 +33,10 @@ class StageConfig:
     anchor_sizes: tuple = (15.0, 30.0, 45.0, 60.0)
     anchor_stride: float = 7.5
     viou_clipped: bool = False
+    topk_per_pair: int = 20            # predict.py:70
+    topk_per_video: int = 200          # predict.py:76 (TOPK_PER_SEG)
+    records: bool = True               # build the triplet records (row N1)
+    mirror_q4: bool = False
 
     @classmethod
     def from_cfg(cls, cfg) -> "StageConfig":
@@ -55,6 +59,8 @@ class StageConfig:
                    hidden=int(rp.PPN.HIDDEN_CHANNELS), topk=int(rp.PPN.NUM_PAIR_PROPOSALS),
                    use_ppn=bool(rp.USE_PPN), use_dpn=bool(rp.USE_DPN),
                    sparsify=bool(opt(pr, "SPARSIFY", False)), precision=str(opt(pr, "PRECISION", "fp32")),
+                   topk_per_pair=int(pr.TOPK_PER_PAIR), topk_per_video=int(pr.TOPK_PER_SEG),
+                   mirror_q4=not bool(opt(pr, "FIX_OBJECT_LABEL", True)),
                    anchor_sizes=tuple(float(s) for s in sizes), anchor_stride=float(stride))
 
 
@@ -73,6 +79,8 @@ class StageResult:
     spans: Optional[List[torch.Tensor]]     # per video [K_v, L*A, 2] int32
     k_eff: List[int]
     sparsify: bool
+    records: Optional[torch.Tensor] = None      # [V, topk_per_video, 8] int32 (ops.RECORD_FIELDS)
+    record_counts: Optional[torch.Tensor] = None
 
     # per-video views -------------------------------------------------------------------
     def pair_proposals(self, v: int) -> Optional[torch.Tensor]:
@@ -91,6 +99,8 @@ class PairStage:
         self.w: Dict[str, torch.Tensor] = {}
         self.packed_cls: Optional[torch.Tensor] = None
         self.sizes_dev: Optional[torch.Tensor] = None
+        self._row_off: Optional[torch.Tensor] = None
+        self._row_off_k = None
 
     # ---- weights -------------------------------------------------------------------------
     def load_weights(self, state_dict, device="cuda") -> None:
@@ -119,12 +129,18 @@ class PairStage:
         return [min(c.topk, n * (n - 1) if c.sparsify else n * n) for n in batch.n]
 
     def forward(self, batch: DeviceBatch, features: Optional[torch.Tensor] = None,
-                heads: bool = True) -> StageResult:
+                heads: bool = True, timers: Optional[dict] = None) -> StageResult:
         """``features``: optional precomputed ``[sum P, F]`` rows (reference mode: rows loaded from
         h5, lib/modeling/predict.py:42-57); when ``None`` they are constructed on the GPU."""
         c = self.cfg
         need_geo = features is None or c.use_dpn
+        if timers is not None:      # CUDA events around the dominant kernel, on the launching stream
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         geom = ops.pair_geometry(batch, write_geo=need_geo and c.write_geo, clipped=c.viou_clipped)
+        if timers is not None:
+            ev1.record()
+            timers["geo"] = (ev0, ev1)
         scores = idx = val = row = None
         if c.use_ppn:
             scores = ops.relationness(batch, self.ppn_weights())
@@ -152,8 +168,22 @@ class PairStage:
         span_reg = spans = None
         if heads and c.use_dpn:
             span_reg, spans = self._span_heads(batch, geom, row, k_eff)
+        records = counts = None
+        if heads and c.records:
+            if sparsify:
+                if self._row_off is None or self._row_off.shape[0] != batch.num_videos + 1 \
+                        or self._row_off_k != c.topk or self._row_off.device != batch.device:
+                    self._row_off = torch.arange(batch.num_videos + 1, dtype=torch.int64,
+                                                 device=batch.device) * c.topk
+                    self._row_off_k = c.topk
+                records, counts = ops.postprocess(batch, logits, geom["overlap"], c.topk_per_pair, c.topk_per_video,
+                                                  rows=row.reshape(-1), row_video_off=self._row_off,
+                                                  mirror_q4=c.mirror_q4)
+            else:
+                records, counts = ops.postprocess(batch, logits, geom["overlap"], c.topk_per_pair, c.topk_per_video,
+                                                  mirror_q4=c.mirror_q4)
         return StageResult(batch, geom, scores, idx, val, row, feats32, feats16, logits, span_reg, spans, k_eff,
-                           sparsify)
+                           sparsify, records, counts)
 
     def _span_heads(self, batch: DeviceBatch, geom, row, k_eff):
         """DPNHead + decode on the surviving pairs of every video (rows gathered inside the kernel)."""
@@ -176,12 +206,9 @@ class PairStage:
             p0 = int(th[v0, _lib.VT_PAIR_OFF])
             p_cnt = sum(batch.n[v] * max(batch.n[v] - 1, 0) for v in vids)
             x = geo[g0:g0 + p_cnt * _lib.GEO_CHANNELS * tp].view(p_cnt, _lib.GEO_CHANNELS, tp)
-            if row is not None:
-                rsel = (row[vids[0]:vids[-1] + 1].reshape(-1))
-                rsel = torch.where(rsel >= 0, rsel - p0, rsel)
-            else:
-                rsel = None
-            reg = ops.span_head(x, cw, cb, pw, pb, rows=rsel, t=t, precision=c.precision if cw.shape[1] >= 64 else "fp32")
+            rsel = row[vids[0]:vids[-1] + 1].reshape(-1) if row is not None else None
+            reg = ops.span_head(x, cw, cb, pw, pb, rows=rsel, t=t, row_base=p0,
+                                precision=c.precision if cw.shape[1] >= 64 else "fp32")
             sp = ops.span_decode(reg, self.sizes_dev, c.anchor_stride)
             if row is not None:
                 k = row.shape[1]

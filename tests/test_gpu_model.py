@@ -124,3 +124,55 @@ def test_basemodel_full_pair_stage(sparsify):
         assert got_sp.shape == want_sp.shape and got_sp.dtype == np.int32
         np.testing.assert_array_equal(got_sp[valid], want_sp[valid])               # frame bounds bit-exact
         np.testing.assert_allclose(res.geom["viou"][res.batch.pair_slice(i)].cpu().numpy(), viou, rtol=1e-5)
+
+
+@pytest.mark.parametrize("sparsify", [False, True])
+def test_triplet_records_match_predict_py_postprocessing(sparsify):
+    """Row N1: top-20 per pair -> top-200 per video -> (score, triplet, tracklet ids), bit-exact."""
+    from tspn_b200 import ops
+    from tspn_b200.batch import HostBatch
+    from tspn_b200.pipeline import PairStage, StageConfig
+    c, r = 35, 132
+    sd = synth.make_weights(c, r, synth.feature_dim(c), dpn_in=8, seed=2)
+    vids = [synth.make_video(14, 90, c, seed=7), synth.make_video(3, 40, c, seed=8), synth.make_video(1, 5, c, seed=9)]
+    for mirror in (False, True):
+        stage = PairStage(StageConfig(n_classes=c, n_predicates=r, topk=64, sparsify=sparsify, precision="fp32",
+                                      mirror_q4=mirror))
+        stage.load_weights(sd)
+        batch = HostBatch.from_videos(vids).to_device("cuda")
+        res = stage.forward(batch)
+        torch.cuda.synchronize()
+        rec = res.records.cpu().numpy()
+        cnt = res.record_counts.cpu().numpy()
+        sc = ops.record_scores(res.records).cpu().numpy()
+        ov = res.geom["overlap"].cpu().numpy()
+        for i, v in enumerate(vids):
+            n = v.n_tracklets
+            logits = res.logits(i).cpu().numpy()
+            if logits.shape[0] == 0:
+                assert cnt[i] == 0
+                continue
+            pr = ogeo.enumerate_pairs(n)
+            if sparsify:
+                order = res.pair_proposals(i).cpu().numpy()
+                s, o = order // n, order % n
+                rows = s * (n - 1) + o - (o > s)
+                pairs = pr[rows]
+            else:
+                rows = np.arange(n * (n - 1))
+                pairs = pr
+            w_score, w_trip, w_tid = oheads.postprocess_ref(logits, v.cls, pairs, 20, 200, fix_q4=True)
+            m = len(w_score)
+            assert cnt[i] == m
+            np.testing.assert_array_equal(sc[i, :m], w_score)                       # scores bit-exact
+            np.testing.assert_array_equal(rec[i, :m, 2], w_trip[:, 1])              # predicates
+            np.testing.assert_array_equal(rec[i, :m, 4:6], w_tid)                   # tracklet ids
+            np.testing.assert_array_equal(rec[i, :m, 1], w_trip[:, 0])              # subject class
+            if mirror:       # quirk Q4: object class read from tracklet 0 (or 1 when the object is 0)
+                q4 = v.cls[np.where(w_tid[:, 1] == 0, 1, 0)].argmax(axis=1)
+                np.testing.assert_array_equal(rec[i, :m, 3], q4)
+            else:
+                np.testing.assert_array_equal(rec[i, :m, 3], w_trip[:, 2])
+            grow = res.batch.pair_slice(i).start + w_tid[:, 0] * (n - 1) + w_tid[:, 1] - (w_tid[:, 1] > w_tid[:, 0])
+            np.testing.assert_array_equal(rec[i, :m, 6:8], ov[grow])
+            assert (rec[i, m:, 1:6] == -1).all()
