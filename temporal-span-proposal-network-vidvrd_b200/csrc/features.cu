@@ -36,13 +36,39 @@ __global__ void __launch_bounds__(128) normalize_motion_kernel(const float* __re
 
 constexpr int ASM_THREADS = 256;
 
-// pooled value of geometry channel `ch` over bin `i` of the window [a, a+len)
-__device__ __forceinline__ float pooled_bin(const float* __restrict__ g_ch, int a, int len, int i) {
-    const int st = (int)(((int64_t)i * len) / TSPN_REL_BINS);
-    const int en = (int)((((int64_t)(i + 1)) * len + TSPN_REL_BINS - 1) / TSPN_REL_BINS);
-    float s = 0.0f;
-    for (int f = st; f < en; ++f) s += __ldg(g_ch + a + f);
-    return s / (float)(en - st);
+template <bool BF16>
+__device__ __forceinline__ void put(float* out, __nv_bfloat16* outb, int col, float v) {
+    if (out) out[col] = v;
+    if (BF16) outb[col] = __float2bfloat16(v);
+}
+
+// copy `n` floats (n % 4 == 0, src 16-byte aligned) to columns [col0, col0+n) of the row
+template <bool BF16>
+__device__ __forceinline__ void copy_block(const float* __restrict__ src, int n, float* out, __nv_bfloat16* outb,
+                                           int col0, bool vec32, bool vec16) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    for (int q = threadIdx.x; q < n / 4; q += ASM_THREADS) {
+        const float4 v = __ldg(s4 + q);
+        const int col = col0 + 4 * q;
+        if (out) {
+            if (vec32) {
+                *reinterpret_cast<float4*>(out + col) = v;
+            } else {
+                out[col] = v.x; out[col + 1] = v.y; out[col + 2] = v.z; out[col + 3] = v.w;
+            }
+        }
+        if (BF16) {
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+            if (vec16) {
+                uint2 pk;
+                pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+                pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(outb + col) = pk;
+            } else {
+                outb[col] = lo.x; outb[col + 1] = lo.y; outb[col + 2] = hi.x; outb[col + 3] = hi.y;
+            }
+        }
+    }
 }
 
 template <bool BF16>
@@ -58,10 +84,8 @@ assemble_kernel(const int64_t* __restrict__ table, int nv, const float* __restri
     const int C = n_classes;
     const int F = 2 * C + 2 * TSPN_MOTION_DIM + TSPN_REL_DIM;
     if (gp < 0) {                                  // padding row (e.g. K_eff < K): zeros
-        for (int col = threadIdx.x; col < F; col += ASM_THREADS) {
-            if (out) out[col] = 0.0f;
-            if (BF16) outb[col] = __float2bfloat16(0.0f);
-        }
+        for (int64_t col = threadIdx.x; col < (out ? ld_feat : 0); col += ASM_THREADS) out[col] = 0.0f;
+        for (int64_t col = threadIdx.x; col < (BF16 ? ld_bf16 : 0); col += ASM_THREADS) outb[col] = __float2bfloat16(0.0f);
         return;
     }
     const int v = find_video(table, nv, TSPN_VT_PAIR_OFF, gp);
@@ -73,32 +97,34 @@ assemble_kernel(const int64_t* __restrict__ table, int nv, const float* __restri
     const int k = p - s * (n - 1);
     const int o = k + (k >= s ? 1 : 0);
     const int64_t ts = row[TSPN_VT_TRK_OFF] + s, to = row[TSPN_VT_TRK_OFF] + o;
-    const float* cs = cls + ts * C;
-    const float* co = cls + to * C;
-    const float* ms = motion_norm + ts * TSPN_MOTION_DIM;
-    const float* mo = motion_norm + to * TSPN_MOTION_DIM;
+    const int m0 = 2 * C, m1 = m0 + TSPN_MOTION_DIM, r0 = m1 + TSPN_MOTION_DIM;
+    // ---- classemes ----
+    for (int col = threadIdx.x; col < m0; col += ASM_THREADS)
+        put<BF16>(out, outb, col, __ldg(cls + (col < C ? ts * C + col : to * C + (col - C))));
+    // ---- motion blocks: 128-bit copies when the row offset 2C allows it ----
+    const bool vec32 = (m0 & 3) == 0, vec16 = (m0 & 3) == 0;       // 16-byte (fp32) / 8-byte (bf16) stores
+    copy_block<BF16>(motion_norm + ts * TSPN_MOTION_DIM, TSPN_MOTION_DIM, out, outb, m0, vec32, vec16);
+    copy_block<BF16>(motion_norm + to * TSPN_MOTION_DIM, TSPN_MOTION_DIM, out, outb, m1, vec32, vec16);
+    // ---- relative block: bin i of every pooled channel shares its frame range ----
     const float* g = geo + row[TSPN_VT_GEO_OFF] + (int64_t)p * TSPN_GEO_CHANNELS * tp;
     const int a = __ldg(overlap + 2 * gp), b = __ldg(overlap + 2 * gp + 1);
-    const int len = b - a;
-    const int m0 = 2 * C, m1 = m0 + TSPN_MOTION_DIM, r0 = m1 + TSPN_MOTION_DIM;
-    for (int col = threadIdx.x; col < F; col += ASM_THREADS) {
-        float val;
-        if (col < C) {
-            val = __ldg(cs + col);
-        } else if (col < m0) {
-            val = __ldg(co + (col - C));
-        } else if (col < m1) {
-            val = __ldg(ms + (col - m0));
-        } else if (col < r0) {
-            val = __ldg(mo + (col - m1));
-        } else {
-            const int u = col - r0;
-            const int slot = u / TSPN_REL_BINS;             // 0..5 -> channels 0,1,2,3,5,6
-            const int ch = slot < 4 ? slot : slot + 1;
-            val = len > 0 ? pooled_bin(g + (int64_t)ch * tp, a, len, u - slot * TSPN_REL_BINS) : 0.0f;
+    const uint32_t len = b > a ? (uint32_t)(b - a) : 0u;
+    for (int i = threadIdx.x; i < TSPN_REL_BINS; i += ASM_THREADS) {
+        float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (len > 0) {
+            const uint32_t st = ((uint32_t)i * len) / TSPN_REL_BINS;              // len < 2^22: fits 32 bits
+            const uint32_t en = ((uint32_t)(i + 1) * len + TSPN_REL_BINS - 1) / TSPN_REL_BINS;
+            const float inv = 1.0f / (float)(en - st);
+#pragma unroll
+            for (int slot = 0; slot < 6; ++slot) {
+                const float* gc = g + (int64_t)(slot < 4 ? slot : slot + 1) * tp + a;
+                float sacc = 0.0f;
+                for (uint32_t f = st; f < en; ++f) sacc += __ldg(gc + f);
+                acc[slot] = sacc * inv;
+            }
         }
-        if (out) out[col] = val;
-        if (BF16) outb[col] = __float2bfloat16(val);
+#pragma unroll
+        for (int slot = 0; slot < 6; ++slot) put<BF16>(out, outb, r0 + slot * TSPN_REL_BINS + i, acc[slot]);
     }
     // zero the padding columns so that a padded row can be fed to TMA / vector loads
     if (out)

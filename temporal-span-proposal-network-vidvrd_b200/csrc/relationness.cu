@@ -51,6 +51,60 @@ ppn_embed_kernel(const float* __restrict__ cls, int C, int H, const float* __res
     }
 }
 
+// Tiled variant used when the four weight matrices fit in shared memory (C*H <= 12288): a CTA
+// stages them once, transposed so that consecutive threads read consecutive words (the per-thread
+// row walk of the kernel above is 32 cache lines per warp load), and embeds EMB_G tracklets.
+// Every output is the same k-ascending fma chain -> same bits as ppn_embed_kernel.
+constexpr int EMB_G = 8;
+constexpr int EMB_THREADS = 256;
+__global__ void __launch_bounds__(EMB_THREADS)
+ppn_embed_tiled_kernel(const float* __restrict__ cls, int64_t n_trk, int C, int H, const float* __restrict__ sw0,
+                       const float* __restrict__ sb0, const float* __restrict__ sw2,
+                       const float* __restrict__ sb2, const float* __restrict__ ow0,
+                       const float* __restrict__ ob0, const float* __restrict__ ow2,
+                       const float* __restrict__ ob2, float* __restrict__ S, float* __restrict__ O) {
+    extern __shared__ float sm[];
+    float* w0t = sm;                      // [2][C][H]   w0t[br][i][j] = W0_br[j][i]
+    float* w2t = w0t + 2 * C * H;         // [2][H][C]   w2t[br][j][c] = W2_br[c][j]
+    float* x = w2t + 2 * H * C;           // [G][C]
+    float* hid = x + EMB_G * C;           // [G][2][H]
+    const int tid = threadIdx.x;
+    const int64_t trk0 = (int64_t)blockIdx.x * EMB_G;
+    const int g_cnt = (int)min((int64_t)EMB_G, n_trk - trk0);
+    for (int e = tid; e < 2 * C * H; e += EMB_THREADS) {
+        const int br = e / (C * H), rem = e - br * C * H;
+        {   // W0_br is [H][C] row-major: element rem = j*C + i
+            const int j = rem / C, i = rem - j * C;
+            w0t[br * C * H + i * H + j] = __ldg((br ? ow0 : sw0) + rem);
+        }
+        {   // W2_br is [C][H] row-major: element rem = c*H + j
+            const int c = rem / H, j = rem - c * H;
+            w2t[br * H * C + j * C + c] = __ldg((br ? ow2 : sw2) + rem);
+        }
+    }
+    for (int e = tid; e < g_cnt * C; e += EMB_THREADS) x[e] = __ldg(cls + trk0 * C + e);
+    __syncthreads();
+    for (int u = tid; u < g_cnt * 2 * H; u += EMB_THREADS) {
+        const int g = u / (2 * H), j2 = u - g * 2 * H;
+        const int br = j2 / H, j = j2 - br * H;
+        const float* w = w0t + br * C * H + j;
+        const float* xg = x + g * C;
+        float acc = __ldg((br ? ob0 : sb0) + j);
+        for (int i = 0; i < C; ++i) acc = __fmaf_rn(xg[i], w[i * H], acc);
+        hid[u] = fmaxf(acc, 0.0f);
+    }
+    __syncthreads();
+    for (int u = tid; u < g_cnt * 2 * C; u += EMB_THREADS) {
+        const int g = u / (2 * C), c2 = u - g * 2 * C;
+        const int br = c2 / C, c = c2 - br * C;
+        const float* w = w2t + br * H * C + c;
+        const float* h = hid + (g * 2 + br) * H;
+        float acc = __ldg((br ? ob2 : sb2) + c);
+        for (int j = 0; j < H; ++j) acc = __fmaf_rn(h[j], w[j * C], acc);
+        (br ? O : S)[(trk0 + g) * C + c] = acc;
+    }
+}
+
 // ---- scores: M[s][o] = sigmoid(sum_c S[s][c] O[o][c]); one CTA per subject row ---------------------
 __global__ void __launch_bounds__(128)
 pair_scores_kernel(const int64_t* __restrict__ table, int nv, const float* __restrict__ S,
@@ -140,10 +194,19 @@ int tspn_relationness(const int64_t* d_table, int num_videos, int64_t total_trac
     cudaStream_t st = (cudaStream_t)stream;
     float* S = reinterpret_cast<float*>(d_workspace);
     float* O = S + total_tracklets * n_classes;
-    const size_t sm1 = (size_t)(n_classes + 2 * hidden) * sizeof(float);
-    ppn_embed_kernel<<<(unsigned)total_tracklets, 128, sm1, st>>>(d_cls, n_classes, hidden, d_sub_w0, d_sub_b0,
-                                                                  d_sub_w2, d_sub_b2, d_obj_w0, d_obj_b0, d_obj_w2,
-                                                                  d_obj_b2, S, O);
+    if ((int64_t)n_classes * hidden <= 12288) {
+        const size_t smt = (size_t)(4 * n_classes * hidden + EMB_G * n_classes + EMB_G * 2 * hidden) * sizeof(float);
+        TSPN_CUDA_OK(cudaFuncSetAttribute(ppn_embed_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smt));
+        ppn_embed_tiled_kernel<<<(unsigned)((total_tracklets + EMB_G - 1) / EMB_G), EMB_THREADS, smt, st>>>(
+            d_cls, total_tracklets, n_classes, hidden, d_sub_w0, d_sub_b0, d_sub_w2, d_sub_b2, d_obj_w0, d_obj_b0,
+            d_obj_w2, d_obj_b2, S, O);
+    } else {
+        const size_t sm1 = (size_t)(n_classes + 2 * hidden) * sizeof(float);
+        ppn_embed_kernel<<<(unsigned)total_tracklets, 128, sm1, st>>>(d_cls, n_classes, hidden, d_sub_w0, d_sub_b0,
+                                                                      d_sub_w2, d_sub_b2, d_obj_w0, d_obj_b0,
+                                                                      d_obj_w2, d_obj_b2, S, O);
+    }
     TSPN_CUDA_OK(cudaGetLastError());
     pair_scores_kernel<<<(unsigned)total_tracklets, 128, (size_t)n_classes * sizeof(float), st>>>(
         d_table, num_videos, S, O, n_classes, d_scores);

@@ -30,50 +30,65 @@ struct TopkSmem {
 // Candidate i in [0, total) has value value_of(i); values equal to -inf are not candidates.
 // On return sm.sel[0 .. k_eff) holds the winners sorted (low 32 bits = index); returns k_eff =
 // min(k, number of candidates).  Must be called by all TOPK_THREADS threads of the block.
+constexpr int TOPK_EPT = 4;        // consecutive candidates per thread in the collect pass
+
 template <typename ValueOf>
 __device__ int block_topk(TopkSmem& sm, int64_t total, int k, ValueOf value_of) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // -- count candidates ------------------------------------------------------------------------
-    if (tid == 0) sm.n_cand = 0;
-    __syncthreads();
-    {
-        uint32_t c = 0;
-        for (int64_t i = tid; i < total; i += TOPK_THREADS) c += order_key(value_of(i)) != KEY_NEG_INF;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
-        if (lane == 0 && c) atomicAdd(&sm.n_cand, c);
-    }
-    __syncthreads();
-    const int k_eff = (int)min((uint32_t)k, sm.n_cand);
-    if (k_eff == 0) return 0;
-    // -- radix select of the k_eff-th largest key ----------------------------------------------------
+    // -- radix select of the k_eff-th largest key (the first pass also counts the candidates) --------
     if (tid == 0) {
         sm.prefix = 0;
-        sm.need = (uint32_t)k_eff;
+        sm.need = 0;
     }
     uint32_t prefix_mask = 0;
+    int k_eff = 0;
     for (int shift = 24; shift >= 0; shift -= 8) {
         sm.hist[tid] = 0;
         __syncthreads();
         const uint32_t prefix = sm.prefix;
+        // run-length aggregation: neighbouring scores usually share their leading digits, which
+        // would otherwise serialise the shared-memory atomics on one bin
+        uint32_t run_bin = 0xffffffffu, run_cnt = 0;
         for (int64_t i = tid; i < total; i += TOPK_THREADS) {
             const uint32_t key = order_key(value_of(i));
-            if (key != KEY_NEG_INF && (key & prefix_mask) == prefix) atomicAdd(&sm.hist[(key >> shift) & 0xffu], 1u);
+            if (key != KEY_NEG_INF && (key & prefix_mask) == prefix) {
+                const uint32_t bin = (key >> shift) & 0xffu;
+                if (bin == run_bin) {
+                    ++run_cnt;
+                } else {
+                    if (run_cnt) atomicAdd(&sm.hist[run_bin], run_cnt);
+                    run_bin = bin;
+                    run_cnt = 1;
+                }
+            }
         }
+        if (run_cnt) atomicAdd(&sm.hist[run_bin], run_cnt);
         __syncthreads();
         if (tid == 0) {
+            if (shift == 24) {
+                uint32_t n_cand = 0;
+                for (int d = 0; d < 256; ++d) n_cand += sm.hist[d];
+                sm.n_cand = n_cand;
+                sm.need = min((uint32_t)k, n_cand);
+            }
             uint32_t need = sm.need, d = 255;
-            for (;; --d) {
-                const uint32_t c = sm.hist[d];
-                if (c >= need) break;
-                need -= c;
-                if (d == 0) break;
+            if (need > 0) {
+                for (;; --d) {
+                    const uint32_t c = sm.hist[d];
+                    if (c >= need) break;
+                    need -= c;
+                    if (d == 0) break;
+                }
             }
             sm.need = need;
             sm.prefix = prefix | (d << shift);
         }
         prefix_mask |= 0xffu << shift;
         __syncthreads();
+        if (shift == 24) {
+            k_eff = (int)min((uint32_t)k, sm.n_cand);
+            if (k_eff == 0) return 0;                // uniform: every thread reads the same n_cand
+        }
     }
     const uint32_t thr = sm.prefix;
     const uint32_t need_ties = sm.need;
@@ -83,24 +98,36 @@ __device__ int block_topk(TopkSmem& sm, int64_t total, int k, ValueOf value_of) 
         sm.tie_base = 0;
     }
     __syncthreads();
-    // -- collect ------------------------------------------------------------------------------------------
-    for (int64_t base = 0; base < total; base += TOPK_THREADS) {
-        const int64_t i = base + tid;
-        bool above = false, tie = false;
-        uint32_t key = 0;
-        if (i < total) {
-            key = order_key(value_of(i));
-            above = key > thr;                       // thr > KEY_NEG_INF, so -inf is never collected
-            tie = key == thr;
+    // -- collect: a thread owns TOPK_EPT consecutive candidates so that ties stay in index order ------
+    for (int64_t base = 0; base < total; base += TOPK_THREADS * TOPK_EPT) {
+        uint32_t keys[TOPK_EPT];
+        uint32_t n_tie = 0;
+#pragma unroll
+        for (int e = 0; e < TOPK_EPT; ++e) {
+            const int64_t i = base + (int64_t)tid * TOPK_EPT + e;
+            keys[e] = i < total ? order_key(value_of(i)) : KEY_NEG_INF;
+            if (keys[e] > thr) sm.sel[atomicAdd(&sm.count, 1u)] = ((uint64_t)(~keys[e]) << 32) | (uint32_t)i;
+            n_tie += keys[e] == thr;                  // thr > KEY_NEG_INF, so -inf is never collected
         }
-        if (above) sm.sel[atomicAdd(&sm.count, 1u)] = ((uint64_t)(~key) << 32) | (uint32_t)i;
-        const uint32_t bal = __ballot_sync(0xffffffffu, tie);
-        if (lane == 0) sm.warp_cnt[warp] = __popc(bal);
+        // exclusive prefix of the tie counts: within the warp by shuffles, across warps through smem
+        uint32_t incl = n_tie;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += up;
+        }
+        if (lane == 31) sm.warp_cnt[warp] = incl;
         __syncthreads();
-        uint32_t before = sm.tie_base;
-        for (int w = 0; w < warp; ++w) before += sm.warp_cnt[w];
-        const uint32_t rank = before + __popc(bal & ((1u << lane) - 1u));
-        if (tie && rank < need_ties) sm.sel[n_above + rank] = ((uint64_t)(~key) << 32) | (uint32_t)i;
+        uint32_t rank = sm.tie_base + incl - n_tie;
+        for (int w = 0; w < warp; ++w) rank += sm.warp_cnt[w];
+#pragma unroll
+        for (int e = 0; e < TOPK_EPT; ++e) {
+            if (keys[e] == thr) {
+                if (rank < need_ties)
+                    sm.sel[n_above + rank] = ((uint64_t)(~keys[e]) << 32) | (uint32_t)(base + (int64_t)tid * TOPK_EPT + e);
+                ++rank;
+            }
+        }
         __syncthreads();
         if (tid == 0) {
             uint32_t t = 0;

@@ -237,6 +237,8 @@ def span_head(x: torch.Tensor, conv_w: torch.Tensor, conv_b: torch.Tensor, pred_
     k = x.shape[0] if rows is None else int(rows.shape[0])
     a2 = pred_w.shape[0]
     prec = PREC[precision]
+    if x.numel() == 0:        # a video without pairs: every requested row is padding
+        return torch.zeros((k, a2, t), dtype=torch.float32, device=x.device)
     out = torch.empty((k, a2, t), dtype=torch.float32, device=x.device)
     ws = None
     if prec == _lib.PREC_TENSOR:
