@@ -59,48 +59,75 @@ def measured_peak():
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region.
 
-    def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+    NVML (pynvml) is polled every few milliseconds from a thread — the timed region of this bench is
+    tens of milliseconds, too short for `nvidia-smi -lms`; nvidia-smi is the fallback."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, cuda_index: int):
+        self.cuda_index = cuda_index
+        self.sm, self.mask, self.power = [], 0, []
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self.thread = None
+        self.source = None
+
+    def _nvml_loop(self, nv, handle):
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)))
+                self.mask |= int(get_reasons(handle))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(handle) / 1000.0)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.002)
+
+    def _smi_loop(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        bits = [0x8, 0x40, 0x20, 0x4]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.check_output(["nvidia-smi", "-i", str(self.cuda_index), "--query-gpu=" + q,
+                                               "--format=csv,noheader,nounits"], text=True, timeout=5)
+                r = [c.strip() for c in out.strip().split(",")]
+                self.sm.append(float(r[0]))
+                self.max_mhz = float(r[1])
+                for b, val in zip(bits, r[2:6]):
+                    if val.lower().startswith("active"):
+                        self.mask |= b
+            except Exception:  # noqa: BLE001
+                break
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
+            import pynvml as nv
+            nv.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(self.cuda_index).uuid)
+            uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+            try:
+                handle = nv.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:  # noqa: BLE001
+                handle = nv.nvmlDeviceGetHandleByUUID(uuid)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
         except Exception:  # noqa: BLE001
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.source = "nvidia-smi"
+            self.thread = threading.Thread(target=self._smi_loop, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:  # noqa: BLE001
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx = float(r[1])
-                for name, val in zip(names, r[3:7]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:  # noqa: BLE001
-                continue
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        self._stop.set()
+        if self.thread is not None:
+            self.thread.join(timeout=6)
+        reasons = sorted(name for bit, name in self.REASONS.items() if self.mask & bit)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(self.sm), "source": self.source,
+                "power_w_max": max(self.power) if self.power else None}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -235,8 +262,7 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     geo_ev, step_ev = [], []
-    sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else
-                           int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
+    sampler = ClockSampler(local_rank)
     sampler.start()                                     # samples through warm-up, timed steps and e2e
     launches0 = ops.launch_count()
     for i in range(args.warmup):

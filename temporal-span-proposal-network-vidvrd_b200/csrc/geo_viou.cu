@@ -204,8 +204,10 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
                     const float ws = (sb.z - sb.x) + 1.0f, hs = (sb.w - sb.y) + 1.0f;
                     const float iw = fmaxf((fminf(sb.z, ob.z) - fmaxf(sb.x, ob.x)) + 1.0f, 0.0f);
                     const float ih = fmaxf((fminf(sb.w, ob.w) - fmaxf(sb.y, ob.y)) + 1.0f, 0.0f);
-                    const float inter = iw * ih;
-                    const float as = ws * hs, ao = wo[i] * ho[i];
+                    // explicit rounding points: the volume sums must not depend on whether the
+                    // compiler contracts these products into the accumulation (template variants)
+                    const float inter = __fmul_rn(iw, ih);
+                    const float as = __fmul_rn(ws, hs), ao = __fmul_rn(wo[i], ho[i]);
                     if (in) {
                         out[0][i] = dcx[i] * rwo[i];
                         out[1][i] = dcy[i] * rho[i];
@@ -213,10 +215,10 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
                         out[3][i] = log_ratio(hs, ho[i], rho[i]);
                         out[4][i] = inter * rcp_fast((as + ao) - inter);
                         out[7][i] = 1.0f;
-                        fsum_i += inter;
+                        fsum_i = __fadd_rn(fsum_i, inter);
                         if (CLIP) {
-                            fsum_s += as;
-                            fsum_o += ao;
+                            fsum_s = __fadd_rn(fsum_s, as);
+                            fsum_o = __fadd_rn(fsum_o, ao);
                         }
                     }
                 }

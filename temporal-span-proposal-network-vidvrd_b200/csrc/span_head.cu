@@ -144,30 +144,49 @@ span_head_small_kernel(const float* __restrict__ x, const int64_t* __restrict__ 
     for (int j = 0; j < A2; ++j)
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[j][i] = b_pred[j];
-#pragma unroll 1
+    // interior quads (no tap leaves [0, T)) take a predicate-free path; both paths run the same
+    // chain, the edge path merely skips the taps that fall outside
+    const bool interior = t0 > 0 && t0 + 4 < t_len;
+#pragma unroll 2
     for (int co = 0; co < CIN; ++co) {
         float h[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) h[i] = b_conv[co];
+        if (interior) {
 #pragma unroll
-        for (int ci = 0; ci < CIN; ++ci) {
-            const float4 w = w_conv[co * CIN + ci];
+            for (int ci = 0; ci < CIN; ++ci) {
+                const float4 w = w_conv[co * CIN + ci];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int t = t0 + i;
-                // taps outside [0, T) are skipped, not multiplied by zero (same chain as the oracle)
-                if (t > 0) h[i] = __fmaf_rn(w.x, xv[ci][i], h[i]);
-                h[i] = __fmaf_rn(w.y, xv[ci][i + 1], h[i]);
-                if (t + 1 < t_len) h[i] = __fmaf_rn(w.z, xv[ci][i + 2], h[i]);
+                for (int i = 0; i < 4; ++i) {
+                    h[i] = __fmaf_rn(w.x, xv[ci][i], h[i]);
+                    h[i] = __fmaf_rn(w.y, xv[ci][i + 1], h[i]);
+                    h[i] = __fmaf_rn(w.z, xv[ci][i + 2], h[i]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci) {
+                const float4 w = w_conv[co * CIN + ci];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int t = t0 + i;
+                    if (t > 0) h[i] = __fmaf_rn(w.x, xv[ci][i], h[i]);
+                    h[i] = __fmaf_rn(w.y, xv[ci][i + 1], h[i]);
+                    if (t + 1 < t_len) h[i] = __fmaf_rn(w.z, xv[ci][i + 2], h[i]);
+                }
             }
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) h[i] = fmaxf(h[i], 0.0f);
+        static_assert(A2 % 4 == 0, "A2 must be a multiple of 4");
 #pragma unroll
-        for (int j = 0; j < A2; ++j) {
-            const float wp = w_pred[co * A2 + j];
+        for (int j4 = 0; j4 < A2 / 4; ++j4) {
+            const float4 wp = *reinterpret_cast<const float4*>(&w_pred[co * A2 + 4 * j4]);
+            const float wv[4] = {wp.x, wp.y, wp.z, wp.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) acc[j][i] = __fmaf_rn(wp, h[i], acc[j][i]);
+            for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[4 * j4 + jj][i] = __fmaf_rn(wv[jj], h[i], acc[4 * j4 + jj][i]);
         }
     }
 #pragma unroll

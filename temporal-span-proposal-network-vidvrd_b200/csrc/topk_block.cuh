@@ -64,24 +64,34 @@ __device__ int block_topk(TopkSmem& sm, int64_t total, int k, ValueOf value_of) 
         }
         if (run_cnt) atomicAdd(&sm.hist[run_bin], run_cnt);
         __syncthreads();
-        if (tid == 0) {
-            if (shift == 24) {
-                uint32_t n_cand = 0;
-                for (int d = 0; d < 256; ++d) n_cand += sm.hist[d];
-                sm.n_cand = n_cand;
-                sm.need = min((uint32_t)k, n_cand);
+        {
+            // parallel bucket walk: thread t owns bin 255-t; an inclusive scan from the top bin down
+            // gives, for every bin, how many candidates sit in it or above it
+            const uint32_t mine = sm.hist[255 - tid];
+            uint32_t incl = mine;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= off) incl += up;
             }
-            uint32_t need = sm.need, d = 255;
-            if (need > 0) {
-                for (;; --d) {
-                    const uint32_t c = sm.hist[d];
-                    if (c >= need) break;
-                    need -= c;
-                    if (d == 0) break;
-                }
+            if (lane == 31) sm.warp_cnt[warp] = incl;
+            __syncthreads();
+            uint32_t before = 0, total_cnt = 0;
+            for (int w = 0; w < TOPK_THREADS / 32; ++w) {
+                const uint32_t c = sm.warp_cnt[w];
+                if (w < warp) before += c;
+                total_cnt += c;
             }
-            sm.need = need;
-            sm.prefix = prefix | (d << shift);
+            incl += before;
+            const uint32_t need = (shift == 24) ? min((uint32_t)k, total_cnt) : sm.need;
+            __syncthreads();                        // everyone has read sm.need / warp_cnt
+            if (shift == 24 && tid == 0) sm.n_cand = total_cnt;
+            // the wanted bin is the first (from the top) whose inclusive count reaches `need`
+            if (need > 0 && incl >= need && incl - mine < need) {
+                sm.need = need - (incl - mine);      // rank inside the bin
+                sm.prefix = prefix | ((uint32_t)(255 - tid) << shift);
+            }
+            if (need == 0 && tid == 0) sm.need = 0;
         }
         prefix_mask |= 0xffu << shift;
         __syncthreads();
