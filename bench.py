@@ -72,6 +72,7 @@ class ClockSampler:
         self._stop = threading.Event()
         self.thread = None
         self.source = None
+        self.period = float(os.environ.get("TSPN_BENCH_CLOCK_PERIOD", "0.005"))
 
     def _nvml_loop(self, nv, handle):
         get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
@@ -83,7 +84,7 @@ class ClockSampler:
                 self.power.append(nv.nvmlDeviceGetPowerUsage(handle) / 1000.0)
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.002)
+            time.sleep(self.period)
 
     def _smi_loop(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -103,6 +104,8 @@ class ClockSampler:
                 break
 
     def start(self):
+        if os.environ.get("TSPN_BENCH_SAMPLER", "") == "off":
+            return
         try:
             import pynvml as nv
             nv.nvmlInit()
@@ -312,9 +315,12 @@ def run_ours(args, rank, world, local_rank):
             slot["batch"].copy_from(host)
             slot["h2d"].record(s_h2d)
 
+    step_marks = []
+
     def e2e_loop(steps):
         issue_h2d(slots[0])
         for i in range(steps):
+            step_marks.append(time.perf_counter())
             slot = slots[i & 1]
             if i + 1 < steps:
                 issue_h2d(slots[(i + 1) & 1])
@@ -349,6 +355,9 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
     e2e_value = world * pairs_per_step * args.steps / e2e_s
+    if os.environ.get("TSPN_BENCH_DEBUG"):
+        marks = np.diff(np.array(step_marks[-args.steps:])) * 1e3
+        sys.stderr.write("e2e host ms between step issues: %s\n" % np.array2string(marks, precision=2))
     d2h = int(sum(b.numel() * b.element_size() for b in slots[0]["bufs"]))
     clocks = sampler.stop()
 

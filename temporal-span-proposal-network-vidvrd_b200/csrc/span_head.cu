@@ -88,14 +88,17 @@ span_head_exact_kernel(const float* __restrict__ x, const int64_t* __restrict__ 
 }
 
 // Small-channel specialisation (the pair stage feeds the 8 geometry channels): weights staged in
-// shared memory as 128-bit broadcast reads, a thread owns 4 consecutive frames (128-bit loads and
-// stores), same fma order per output as the generic kernel -> same bits.
-template <int CIN, int A2>
+// shared memory as 128-bit broadcast reads, a thread owns FPT consecutive frames (vector loads and
+// stores), same fma order per output as the generic kernel -> same bits.  FPT = 2 keeps the thread
+// at ~64 registers (7 CTAs per SM): the kernel streams 64*T bytes per pair and needs the occupancy.
+template <int CIN, int A2, int FPT>
 __global__ void __launch_bounds__(SH_THREADS)
 span_head_small_kernel(const float* __restrict__ x, const int64_t* __restrict__ rows, int64_t row_base,
                        int64_t row_stride, int64_t ld_t, int t_len, const float* __restrict__ conv_w,
                        const float* __restrict__ conv_b, const float* __restrict__ pred_w,
                        const float* __restrict__ pred_b, float* __restrict__ out) {
+    static_assert(FPT == 2 || FPT == 4, "FPT must be 2 or 4");
+    static_assert(A2 % 4 == 0, "A2 must be a multiple of 4");
     __shared__ __align__(16) float4 w_conv[CIN * CIN];      // [co][ci] -> (w0, w1, w2, -)
     __shared__ __align__(16) float w_pred[CIN * A2];        // [co][j]
     __shared__ float b_conv[CIN], b_pred[A2];
@@ -110,75 +113,65 @@ span_head_small_kernel(const float* __restrict__ x, const int64_t* __restrict__ 
     __syncthreads();
 
     const int64_t p = blockIdx.y;
-    const int t0 = (blockIdx.x * SH_THREADS + threadIdx.x) * 4;
+    const int t0 = (blockIdx.x * SH_THREADS + threadIdx.x) * FPT;
     if (t0 >= t_len) return;
     float* o = out + p * A2 * (int64_t)t_len + t0;
-    const bool vec_out = ((t_len & 3) == 0) && t0 + 3 < t_len;
+    const bool full = t0 + FPT - 1 < t_len;
+    const bool vec_out = ((t_len & (FPT - 1)) == 0) && full;
     const int64_t src = rows ? rows[p] - (rows[p] >= 0 ? row_base : 0) : p;
     if (src < 0) {
 #pragma unroll
         for (int j = 0; j < A2; ++j)
-            for (int i = 0; i < 4 && t0 + i < t_len; ++i) o[(int64_t)j * t_len + i] = 0.0f;
+            for (int i = 0; i < FPT && t0 + i < t_len; ++i) o[(int64_t)j * t_len + i] = 0.0f;
         return;
     }
     const float* xr = x + src * row_stride + t0;
-    // xv[ci][0..5] = x[ci][t0-1 .. t0+4], zero outside [0, T)
-    float xv[CIN][6];
-    const bool vec_in = ((ld_t & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((row_stride & 3) == 0) &&
-                        t0 + 3 < t_len;
+    // xv[ci][0 .. FPT+1] = x[ci][t0-1 .. t0+FPT], zero outside [0, T)
+    float xv[CIN][FPT + 2];
+    const bool vec_in = ((ld_t & (FPT - 1)) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                        ((row_stride & 3) == 0) && full;
 #pragma unroll
     for (int ci = 0; ci < CIN; ++ci) {
         const float* xc = xr + (int64_t)ci * ld_t;
         if (vec_in) {
-            const float4 q = __ldg(reinterpret_cast<const float4*>(xc));
-            xv[ci][1] = q.x; xv[ci][2] = q.y; xv[ci][3] = q.z; xv[ci][4] = q.w;
+            if (FPT == 4) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(xc));
+                xv[ci][1] = q.x; xv[ci][2] = q.y; xv[ci][FPT - 1] = q.z; xv[ci][FPT] = q.w;
+            } else {
+                const float2 q = __ldg(reinterpret_cast<const float2*>(xc));
+                xv[ci][1] = q.x; xv[ci][2] = q.y;
+            }
         } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) xv[ci][1 + i] = (t0 + i < t_len) ? __ldg(xc + i) : 0.0f;
+            for (int i = 0; i < FPT; ++i) xv[ci][1 + i] = (t0 + i < t_len) ? __ldg(xc + i) : 0.0f;
         }
         xv[ci][0] = t0 > 0 ? __ldg(xc - 1) : 0.0f;
-        xv[ci][5] = t0 + 4 < t_len ? __ldg(xc + 4) : 0.0f;
+        xv[ci][FPT + 1] = t0 + FPT < t_len ? __ldg(xc + FPT) : 0.0f;
     }
-    float acc[A2][4];
+    float acc[A2][FPT];
 #pragma unroll
     for (int j = 0; j < A2; ++j)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) acc[j][i] = b_pred[j];
-    // interior quads (no tap leaves [0, T)) take a predicate-free path; both paths run the same
-    // chain, the edge path merely skips the taps that fall outside
-    const bool interior = t0 > 0 && t0 + 4 < t_len;
-#pragma unroll 2
+        for (int i = 0; i < FPT; ++i) acc[j][i] = b_pred[j];
+#pragma unroll 1
     for (int co = 0; co < CIN; ++co) {
-        float h[4];
+        float h[FPT];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) h[i] = b_conv[co];
-        if (interior) {
+        for (int i = 0; i < FPT; ++i) h[i] = b_conv[co];
 #pragma unroll
-            for (int ci = 0; ci < CIN; ++ci) {
-                const float4 w = w_conv[co * CIN + ci];
+        for (int ci = 0; ci < CIN; ++ci) {
+            const float4 w = w_conv[co * CIN + ci];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    h[i] = __fmaf_rn(w.x, xv[ci][i], h[i]);
-                    h[i] = __fmaf_rn(w.y, xv[ci][i + 1], h[i]);
-                    h[i] = __fmaf_rn(w.z, xv[ci][i + 2], h[i]);
-                }
-            }
-        } else {
-#pragma unroll
-            for (int ci = 0; ci < CIN; ++ci) {
-                const float4 w = w_conv[co * CIN + ci];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int t = t0 + i;
-                    if (t > 0) h[i] = __fmaf_rn(w.x, xv[ci][i], h[i]);
-                    h[i] = __fmaf_rn(w.y, xv[ci][i + 1], h[i]);
-                    if (t + 1 < t_len) h[i] = __fmaf_rn(w.z, xv[ci][i + 2], h[i]);
-                }
+            for (int i = 0; i < FPT; ++i) {
+                const int t = t0 + i;
+                // taps outside [0, T) are skipped, not multiplied by zero (same chain as the oracle)
+                if (t > 0) h[i] = __fmaf_rn(w.x, xv[ci][i], h[i]);
+                h[i] = __fmaf_rn(w.y, xv[ci][i + 1], h[i]);
+                if (t + 1 < t_len) h[i] = __fmaf_rn(w.z, xv[ci][i + 2], h[i]);
             }
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) h[i] = fmaxf(h[i], 0.0f);
-        static_assert(A2 % 4 == 0, "A2 must be a multiple of 4");
+        for (int i = 0; i < FPT; ++i) h[i] = fmaxf(h[i], 0.0f);
 #pragma unroll
         for (int j4 = 0; j4 < A2 / 4; ++j4) {
             const float4 wp = *reinterpret_cast<const float4*>(&w_pred[co * A2 + 4 * j4]);
@@ -186,17 +179,18 @@ span_head_small_kernel(const float* __restrict__ x, const int64_t* __restrict__ 
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) acc[4 * j4 + jj][i] = __fmaf_rn(wv[jj], h[i], acc[4 * j4 + jj][i]);
+                for (int i = 0; i < FPT; ++i) acc[4 * j4 + jj][i] = __fmaf_rn(wv[jj], h[i], acc[4 * j4 + jj][i]);
         }
     }
 #pragma unroll
     for (int j = 0; j < A2; ++j) {
         float* oj = o + (int64_t)j * t_len;
         if (vec_out) {
-            *reinterpret_cast<float4*>(oj) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+            if (FPT == 4) *reinterpret_cast<float4*>(oj) = make_float4(acc[j][0], acc[j][1], acc[j][FPT - 2], acc[j][FPT - 1]);
+            else          *reinterpret_cast<float2*>(oj) = make_float2(acc[j][0], acc[j][1]);
         } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < FPT; ++i)
                 if (t0 + i < t_len) oj[i] = acc[j][i];
         }
     }
@@ -259,9 +253,11 @@ int tspn_span_head(const float* d_x, const int64_t* d_rows, int64_t row_base, in
     cudaStream_t st = (cudaStream_t)stream;
     if (precision == TSPN_PREC_FP32_EXACT) {
         if (cin == 8 && a2 == 8) {
-            dim3 grid((unsigned)((t + 4 * SH_THREADS - 1) / (4 * SH_THREADS)), (unsigned)k);
-            span_head_small_kernel<8, 8><<<grid, SH_THREADS, 0, st>>>(d_x, d_rows, row_base, row_stride, ld_t, t,
-                                                                      d_conv_w, d_conv_b, d_pred_w, d_pred_b, d_out);
+            constexpr int FPT = 2;
+            dim3 grid((unsigned)((t + FPT * SH_THREADS - 1) / (FPT * SH_THREADS)), (unsigned)k);
+            span_head_small_kernel<8, 8, FPT><<<grid, SH_THREADS, 0, st>>>(d_x, d_rows, row_base, row_stride, ld_t,
+                                                                           t, d_conv_w, d_conv_b, d_pred_w, d_pred_b,
+                                                                           d_out);
         } else {
             dim3 grid((unsigned)((t + SH_THREADS - 1) / SH_THREADS), (unsigned)k);
             span_head_exact_kernel<<<grid, SH_THREADS, 0, st>>>(d_x, d_rows, row_base, row_stride, ld_t, cin, t,
