@@ -31,6 +31,11 @@ def _count(n: int) -> None:
     _LAUNCHES += n
 
 
+def count_launches(n: int) -> None:
+    """Account for kernels launched by a CUDA-graph replay (pipeline.GraphedStage)."""
+    _count(n)
+
+
 def _cuda(t: torch.Tensor, dtype=None) -> torch.Tensor:
     if not t.is_cuda:
         raise RuntimeError("tspn_b200 ops need CUDA tensors (there is no CPU path)")

@@ -81,6 +81,21 @@ class StageResult:
     sparsify: bool
     records: Optional[torch.Tensor] = None      # [V, topk_per_video, 8] int32 (ops.RECORD_FIELDS)
     record_counts: Optional[torch.Tensor] = None
+    span_buffers: Optional[List[torch.Tensor]] = None   # the contiguous tensors `spans` are views of
+
+    def host_outputs(self) -> Dict[str, torch.Tensor]:
+        """The tensors a caller reads back: what BaseModel.forward returns (proposals, spans, predicate
+        scores), the per-pair reductions and the triplet records."""
+        out = {"viou": self.geom["viou"], "tiou": self.geom["tiou"], "overlap": self.geom["overlap"]}
+        if self.topk_idx is not None:
+            out["topk_idx"], out["topk_score"] = self.topk_idx, self.topk_score
+        if self.rel_logits is not None:
+            out["rel_logits"] = self.rel_logits
+        for i, b in enumerate(self.span_buffers or []):
+            out["spans%d" % i] = b
+        if self.records is not None:
+            out["records"], out["record_counts"] = self.records, self.record_counts
+        return out
 
     # per-video views -------------------------------------------------------------------
     def pair_proposals(self, v: int) -> Optional[torch.Tensor]:
@@ -101,6 +116,7 @@ class PairStage:
         self.sizes_dev: Optional[torch.Tensor] = None
         self._row_off: Optional[torch.Tensor] = None
         self._row_off_k = None
+        self._side: Dict[str, torch.cuda.Stream] = {}
 
     # ---- weights -------------------------------------------------------------------------
     def load_weights(self, state_dict, device="cuda") -> None:
@@ -128,31 +144,41 @@ class PairStage:
             return [n * max(n - 1, 0) for n in batch.n]
         return [min(c.topk, n * (n - 1) if c.sparsify else n * n) for n in batch.n]
 
-    def forward(self, batch: DeviceBatch, features: Optional[torch.Tensor] = None,
-                heads: bool = True, timers: Optional[dict] = None) -> StageResult:
-        """``features``: optional precomputed ``[sum P, F]`` rows (reference mode: rows loaded from
-        h5, lib/modeling/predict.py:42-57); when ``None`` they are constructed on the GPU."""
+    # The step is three segments.  `side` (relationness + top-K, motion normalisation) depends only on
+    # the class logits / motion rows, so it runs on a second stream underneath the HBM-bound geometry
+    # kernel of `geo`; `tail` (feature rows, heads, records) joins both.  Eager `forward` forks and joins
+    # with stream events; `capture` freezes each segment into a CUDA graph (GraphedStage).
+    def _side_stream(self, device) -> torch.cuda.Stream:
+        key = str(device)
+        if self._side.get(key) is None:
+            self._side[key] = torch.cuda.Stream(device)
+        return self._side[key]
+
+    def _seg_side(self, batch: DeviceBatch, features: Optional[torch.Tensor]):
         c = self.cfg
-        need_geo = features is None or c.use_dpn
-        if timers is not None:      # CUDA events around the dominant kernel, on the launching stream
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev0.record()
-        geom = ops.pair_geometry(batch, write_geo=need_geo and c.write_geo, clipped=c.viou_clipped)
-        if timers is not None:
-            ev1.record()
-            timers["geo"] = (ev0, ev1)
-        scores = idx = val = row = None
+        scores = idx = val = row = mn = None
         if c.use_ppn:
             scores = ops.relationness(batch, self.ppn_weights())
             idx, val, row = ops.topk_pairs(batch, scores, c.topk, exclude_diagonal=c.sparsify)
+        if features is None:
+            if batch.motion is None or batch.cls is None:
+                raise ValueError("feature construction needs the cls and motion tracklet fields")
+            mn = ops.normalize_motion(batch.motion)
+        return scores, idx, val, row, mn
+
+    def _seg_geo(self, batch: DeviceBatch, features: Optional[torch.Tensor]):
+        c = self.cfg
+        need_geo = features is None or c.use_dpn
+        return ops.pair_geometry(batch, write_geo=need_geo and c.write_geo, clipped=c.viou_clipped)
+
+    def _seg_tail(self, batch: DeviceBatch, features, heads, side, geom) -> StageResult:
+        c = self.cfg
+        scores, idx, val, row, mn = side
         k_eff = self.k_effective(batch)
         sparsify = c.sparsify and c.use_ppn
         feats32 = feats16 = logits = None
         tensor = c.precision == "tensor"
         if features is None:
-            if batch.motion is None or batch.cls is None:
-                raise ValueError("feature construction needs the cls and motion tracklet fields")
-            mn = ops.normalize_motion(batch.motion)
             rows = row.reshape(-1) if sparsify else None
             feats32, feats16 = ops.assemble_features(batch, mn, geom["geo"], geom["overlap"], rows,
                                                      want_fp32=not tensor, want_bf16=tensor)
@@ -165,9 +191,9 @@ class PairStage:
             x = feats16 if feats16 is not None else feats32
             logits = ops.predicate_head(x, self.w[CLS_PREFIX + "weight"], self.w[CLS_PREFIX + "bias"],
                                         precision=c.precision, packed=self.packed_cls)
-        span_reg = spans = None
+        span_reg = spans = span_bufs = None
         if heads and c.use_dpn:
-            span_reg, spans = self._span_heads(batch, geom, row, k_eff)
+            span_reg, spans, span_bufs = self._span_heads(batch, geom, row, k_eff)
         records = counts = None
         if heads and c.records:
             if sparsify:
@@ -183,7 +209,35 @@ class PairStage:
                 records, counts = ops.postprocess(batch, logits, geom["overlap"], c.topk_per_pair, c.topk_per_video,
                                                   mirror_q4=c.mirror_q4)
         return StageResult(batch, geom, scores, idx, val, row, feats32, feats16, logits, span_reg, spans, k_eff,
-                           sparsify, records, counts)
+                           sparsify, records, counts, span_bufs)
+
+    def forward(self, batch: DeviceBatch, features: Optional[torch.Tensor] = None,
+                heads: bool = True, timers: Optional[dict] = None) -> StageResult:
+        """``features``: optional precomputed ``[sum P, F]`` rows (reference mode: rows loaded from
+        h5, lib/modeling/predict.py:42-57); when ``None`` they are constructed on the GPU.
+        ``timers``: receives ``{"geo": (start, end)}`` CUDA events around the geometry kernel."""
+        main = torch.cuda.current_stream(batch.device)
+        side_stream = self._side_stream(batch.device)
+        side_stream.wait_stream(main)                 # fork: inputs are ready on the caller's stream
+        with torch.cuda.stream(side_stream):
+            side = self._seg_side(batch, features)
+        for t in side:
+            if t is not None:
+                t.record_stream(main)                 # allocated on the side stream, consumed on main
+        if timers is not None:      # CUDA events around the dominant kernel, on the launching stream
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(main)
+        geom = self._seg_geo(batch, features)
+        if timers is not None:
+            ev1.record(main)
+            timers["geo"] = (ev0, ev1)
+        main.wait_stream(side_stream)                 # join
+        return self._seg_tail(batch, features, heads, side, geom)
+
+    def capture(self, batch: DeviceBatch, features: Optional[torch.Tensor] = None,
+                heads: bool = True) -> "GraphedStage":
+        """Freeze the step for this batch's shapes into CUDA graphs (see GraphedStage)."""
+        return GraphedStage(self, batch, features, heads)
 
     def _span_heads(self, batch: DeviceBatch, geom, row, k_eff):
         """DPNHead + decode on the surviving pairs of every video (rows gathered inside the kernel)."""
@@ -194,7 +248,7 @@ class PairStage:
             raise ValueError("the pair stage feeds the span head with the %d geometry channels; "
                              "RELPN.DPN.IN_CHANNELS must be %d (got %d)" % (_lib.GEO_CHANNELS, _lib.GEO_CHANNELS,
                                                                             cw.shape[1]))
-        regs, spans = [], []
+        regs, spans, bufs = [], [], []
         th = batch.table_host
         same_t = len(set(batch.t)) == 1
         groups = [list(range(batch.num_videos))] if same_t else [[v] for v in range(batch.num_videos)]
@@ -210,6 +264,7 @@ class PairStage:
             reg = ops.span_head(x, cw, cb, pw, pb, rows=rsel, t=t, row_base=p0,
                                 precision=c.precision if cw.shape[1] >= 64 else "fp32")
             sp = ops.span_decode(reg, self.sizes_dev, c.anchor_stride)
+            bufs.append(sp)
             if row is not None:
                 k = row.shape[1]
                 for j, v in enumerate(vids):
@@ -222,7 +277,55 @@ class PairStage:
                     regs.append(reg[off:off + pv])
                     spans.append(sp[off:off + pv])
                     off += pv
-        return regs, spans
+        return regs, spans, bufs
+
+
+class GraphedStage:
+    """The step of one fixed-shape batch as three CUDA graphs (side / geo / tail).
+
+    Launch-bound host work (13 C-ABI calls, their output allocations and tensor-map encodes) is paid
+    once at capture; a replay is three graph launches, two stream joins and - optionally - the two
+    CUDA events that time the geometry kernel.  All outputs live in the graphs' private memory pool
+    and are overwritten by every replay: ``result`` always refers to the latest one.  Refill the inputs
+    with ``batch.copy_from(host)`` (same per-video shapes) between replays.
+    """
+
+    def __init__(self, stage: PairStage, batch: DeviceBatch, features: Optional[torch.Tensor] = None,
+                 heads: bool = True):
+        self.stage, self.batch = stage, batch
+        dev = batch.device
+        self.side_stream = stage._side_stream(dev)
+        self._cap_stream = torch.cuda.Stream(dev)
+        stage.forward(batch, features=features, heads=heads)      # warm-up: lazy init outside capture
+        torch.cuda.synchronize(dev)
+        self.g_side, self.g_geo, self.g_tail = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        pool = torch.cuda.graph_pool_handle()
+        n0 = ops.launch_count()
+        with torch.cuda.graph(self.g_side, pool=pool, stream=self._cap_stream):
+            side = stage._seg_side(batch, features)
+        with torch.cuda.graph(self.g_geo, pool=pool, stream=self._cap_stream):
+            geom = stage._seg_geo(batch, features)
+        with torch.cuda.graph(self.g_tail, pool=pool, stream=self._cap_stream):
+            self.result = stage._seg_tail(batch, features, heads, side, geom)
+        self.kernels_per_replay = ops.launch_count() - n0
+        torch.cuda.synchronize(dev)
+
+    def replay(self, timers: Optional[dict] = None) -> StageResult:
+        main = torch.cuda.current_stream(self.batch.device)
+        self.side_stream.wait_stream(main)
+        with torch.cuda.stream(self.side_stream):
+            self.g_side.replay()
+        if timers is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(main)
+        self.g_geo.replay()
+        if timers is not None:
+            ev1.record(main)
+            timers["geo"] = (ev0, ev1)
+        main.wait_stream(self.side_stream)
+        self.g_tail.replay()
+        ops.count_launches(self.kernels_per_replay)
+        return self.result
 
 
 def stage_from_videos(videos, weights, config: StageConfig, device="cuda"):
