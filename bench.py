@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--no-sparsify", action="store_true", help="heads on all P pairs (reference quirk Q3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="launch every kernel from the host instead of CUDA graphs")
+    ap.add_argument("--depth", type=int, default=3, help="batches in flight in the end-to-end serving loop")
     return ap.parse_args()
 
 
@@ -260,7 +261,7 @@ def run_ours(args, rank, world, local_rank):
     # The serving loop below owns `depth` slots (device inputs + captured CUDA graphs + pinned result
     # buffers); the resident-input measurement replays slot 0's graphs on inputs already in HBM.
     group = dist.group.WORLD if world > 1 else None
-    pipe = PipelinedStage(stage, host, device=dev, depth=2, graphs=not args.eager, group=group)
+    pipe = PipelinedStage(stage, host, device=dev, depth=args.depth, graphs=not args.eager, group=group)
     slot0 = pipe.slots[0]
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)    # > 126 MB L2
     torch.cuda.synchronize()
@@ -308,7 +309,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- end-to-end steps: pinned host in, pinned host out ------------------------------------
     # tspn_b200.serving.PipelinedStage (the host-facing call): every step copies its own inputs from
     # pinned host memory and its own results back to pinned host memory inside the timed region; H2D of
-    # step i+1 and D2H of step i-1 overlap the kernels of step i (three streams, depth 2).
+    # step i+1 and D2H of step i-1 overlap the kernels of step i (three streams, --depth batches in flight).
     def e2e_loop(steps):
         n_out = 0
         for out in pipe.run(host for _ in range(steps)):
@@ -354,8 +355,9 @@ def run_ours(args, rank, world, local_rank):
                    "wall_s_timed_region": t_wall,
                    "launch": "eager C-ABI calls" if args.eager else
                              "3 CUDA-graph launches per step (side: relationness+top-K+motion norm || geo; tail)",
-                   "e2e_pipeline": "tspn_b200.serving.PipelinedStage, depth 2: H2D(i+1) and D2H(i-1) overlap the "
-                                   "kernels of step i",
+                   "e2e_pipeline": "tspn_b200.serving.PipelinedStage, depth %d: one H2D copy of the pinned input "
+                                   "arena per step; H2D(i+1..) and D2H(i-1) overlap the kernels of step i"
+                                   % args.depth,
                    "multi_gpu_collective": "all_gather of [V,200,8] int32 triplet records per step (e2e loop)"},
         "roofline": {"bound": "hbm", "kernel": "pair_geo_kernel (+ tracklet_volume_kernel)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

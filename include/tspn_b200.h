@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define TSPN_ABI_VERSION 1
+#define TSPN_ABI_VERSION 2
 
 /* error codes */
 #define TSPN_OK 0
@@ -116,10 +116,11 @@ int tspn_enumerate_pairs(const int64_t* d_table, int num_videos, int64_t total_p
  * Replaces cubic_iou/_intersect/_union (lib/modeling/trajectory.py:85-141) applied to all
  * ordered pairs of each video, viou (lib/evaluation/common.py:65-106) and _traj_iou
  * (lib/modeling/association.py:35-48, flag TSPN_VIOU_CLIPPED); adds the per-frame channels.
- * d_geo may be NULL (reductions only).  d_workspace: tspn_pair_geo_workspace_bytes(). */
-int64_t tspn_pair_geo_workspace_bytes(int64_t total_tracklets);
+ * d_geo may be NULL (reductions only).  d_workspace: tspn_pair_geo_workspace_bytes() bytes
+ * (per-tracklet volumes + per-pair fixed-point volume sums), 16-byte aligned. */
+int64_t tspn_pair_geo_workspace_bytes(int64_t total_tracklets, int64_t total_pairs);
 int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_items,
-                       int64_t total_tracklets, int64_t total_boxes,
+                       int64_t total_tracklets, int64_t total_pairs, int64_t total_boxes,
                        const float* d_boxes, const int32_t* d_span,
                        float* d_geo, float* d_viou, float* d_tiou, int32_t* d_overlap,
                        int flags, void* d_workspace, void* stream);
@@ -200,6 +201,15 @@ int tspn_span_head(const float* d_x, const int64_t* d_rows, int64_t row_base, in
 int tspn_span_num_locations(int t, float stride);
 int tspn_span_decode(const float* d_reg, int64_t k, int n_anchors, int t,
                      const float* d_sizes, float stride, int32_t* d_spans, void* stream);
+/* tspn_span_head (fp32 exact order) + tspn_span_decode fused: the head is evaluated only at the
+ * n_loc anchor columns floor(l*stride) the decode reads, the [k][2a][t] regressions never reach
+ * memory.  Same arguments as the two calls it replaces (dpn.py:55-73 + anchor_generator.py:48-104),
+ * bit-identical spans int32 [k][n_loc*a][2]. */
+int tspn_span_proposals(const float* d_x, const int64_t* d_rows, int64_t row_base, int64_t row_stride,
+                        int64_t ld_t, int64_t k, int cin, int t,
+                        const float* d_conv_w, const float* d_conv_b,
+                        const float* d_pred_w, const float* d_pred_b, int n_anchors,
+                        const float* d_sizes, float stride, int32_t* d_spans, void* stream);
 
 /* ---- N1: predict.py:66-117 post-processing ------------------------------------------------
  * per video: top `topk_per_pair` predicates per scored row (predict.py:70-73), then top

@@ -20,6 +20,9 @@ VT_N, VT_T, VT_TP, VT_TB, VT_TRK_OFF, VT_PAIR_OFF, VT_GEO_OFF, VT_ITEM_OFF, VT_B
 TOT_COLS = 8
 TOT_TRACKLETS, TOT_PAIRS, TOT_GEO_FLOATS, TOT_ITEMS, TOT_BOXES, TOT_SCORES, TOT_MAX_N, TOT_MAX_T = range(8)
 
+ABI_VERSION = 2
+GEO_OBJ_GROUP = 16        # csrc/common.cuh: objects per work item of the pair-geometry kernel
+GEO_CHUNK = 512           # ... and frames per work item
 GEO_CHANNELS = 8
 MOTION_DIM = 4000
 REL_DIM = 3000
@@ -37,8 +40,8 @@ SIGNATURES = {
     "tspn_check_device": (c_int, []),
     "tspn_build_video_table": (c_int, [c_int, POINTER(c_int32), POINTER(c_int32), POINTER(c_int64), POINTER(c_int64)]),
     "tspn_enumerate_pairs": (c_int, [P, c_int, c_int64, P, P]),
-    "tspn_pair_geo_workspace_bytes": (c_int64, [c_int64]),
-    "tspn_pair_geo_viou": (c_int, [P, c_int, c_int64, c_int64, c_int64, P, P, P, P, P, P, c_int, P, P]),
+    "tspn_pair_geo_workspace_bytes": (c_int64, [c_int64, c_int64]),
+    "tspn_pair_geo_viou": (c_int, [P, c_int, c_int64, c_int64, c_int64, c_int64, P, P, P, P, P, P, c_int, P, P]),
     "tspn_cubic_iou": (c_int, [P, c_int, P, c_int, c_int, P, P]),
     "tspn_viou_pairs": (c_int, [P, P, P, P, P, c_int64, c_int, P, P]),
     "tspn_normalize_motion": (c_int, [P, c_int64, P, P]),
@@ -54,6 +57,8 @@ SIGNATURES = {
     "tspn_span_head": (c_int, [P, P, c_int64, c_int64, c_int64, c_int64, c_int, c_int, P, P, P, P, c_int, P, c_int, P, P]),
     "tspn_span_num_locations": (c_int, [c_int, c_float]),
     "tspn_span_decode": (c_int, [P, c_int64, c_int, c_int, P, c_float, P, P]),
+    "tspn_span_proposals": (c_int, [P, P, c_int64, c_int64, c_int64, c_int64, c_int, c_int, P, P, P, P, c_int, P,
+                                    c_float, P, P]),
     "tspn_postprocess_workspace_bytes": (c_int64, [c_int64, c_int]),
     "tspn_postprocess": (c_int, [P, c_int, P, P, P, c_int64, c_int, P, c_int, P, c_int, c_int, c_int, P, P, P, P]),
 }
@@ -75,8 +80,8 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.tspn_version() != 1:
-        raise RuntimeError("libtspn_b200.so ABI version %d, expected 1" % lib.tspn_version())
+    if lib.tspn_version() != ABI_VERSION:
+        raise RuntimeError("libtspn_b200.so ABI version %d, expected %d" % (lib.tspn_version(), ABI_VERSION))
     _lib = lib
     return lib
 

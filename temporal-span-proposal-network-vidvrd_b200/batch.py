@@ -26,6 +26,34 @@ def _np(x, dtype):
     return np.ascontiguousarray(x, dtype=dtype)
 
 
+_ARENA_ALIGN = 256
+
+
+def _arena_layout(fields):
+    """``{name: (offset, shape, dtype)}`` + total bytes for the fields that are present."""
+    out, off = {}, 0
+    for f in fields:
+        if f is None:
+            continue
+        name, shape, dtype = f
+        nbytes = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        out[name] = (off, tuple(int(x) for x in shape), dtype)
+        off = (off + nbytes + _ARENA_ALIGN - 1) // _ARENA_ALIGN * _ARENA_ALIGN
+    out["bytes"] = max(off, _ARENA_ALIGN)
+    return out
+
+
+def _arena_views(arena: torch.Tensor, layout):
+    views = {}
+    for name, spec in layout.items():
+        if name == "bytes":
+            continue
+        off, shape, dtype = spec
+        nbytes = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        views[name] = arena[off:off + nbytes].view(dtype).view(shape)
+    return views
+
+
 class HostBatch:
     """Packed, pinned host image of a batch of videos."""
 
@@ -44,13 +72,25 @@ class HostBatch:
         self.table, self.totals = _lib.build_video_table(self.n, self.t)
         tot = self.totals
         use_pin = pin and torch.cuda.is_available()
-
-        def alloc(shape, dtype):
-            t = torch.zeros(shape, dtype=dtype)
-            return t.pin_memory() if use_pin else t
-
-        self.boxes = alloc((int(tot[TOT_BOXES]), 4), torch.float32)
-        self.span = alloc((int(tot[TOT_TRACKLETS]), 2), torch.int32)
+        n_trk = int(tot[TOT_TRACKLETS])
+        if cls is not None:
+            cls = [_np(c, np.float32) for c in cls]
+        if motion is not None:
+            motion = [_np(m, np.float32) for m in motion]
+        # One pinned arena holds every field (256-byte aligned segments), so that a step's inputs cross
+        # PCIe as ONE copy; the fields below are views of it.  DeviceBatch mirrors the layout in HBM.
+        self.layout = _arena_layout([
+            ("table", (len(self.n), VT_COLS), torch.int64),
+            ("boxes", (int(tot[TOT_BOXES]), 4), torch.float32),
+            ("span", (n_trk, 2), torch.int32),
+            ("cls", (n_trk, int(cls[0].shape[1])), torch.float32) if cls is not None else None,
+            ("motion", (n_trk, _lib.MOTION_DIM), torch.float32) if motion is not None else None,
+        ])
+        self.arena = torch.zeros(self.layout["bytes"], dtype=torch.uint8)
+        if use_pin:
+            self.arena = self.arena.pin_memory()
+        views = _arena_views(self.arena, self.layout)
+        self.boxes, self.span = views["boxes"], views["span"]
         bview = self.boxes.numpy()
         sview = self.span.numpy()
         for v, (b, s) in enumerate(zip(boxes, span)):
@@ -61,21 +101,14 @@ class HostBatch:
             dst = bview[int(row[VT_BOX_OFF]):int(row[VT_BOX_OFF]) + n * tb].reshape(n, tb, 4)
             dst[:, :t] = b
             sview[int(row[VT_TRK_OFF]):int(row[VT_TRK_OFF]) + n] = s
-        self.cls = None
-        self.motion = None
-        if cls is not None:
-            cls = [_np(c, np.float32) for c in cls]
-            self.cls = alloc((int(tot[TOT_TRACKLETS]), int(cls[0].shape[1])), torch.float32)
-            if int(tot[TOT_TRACKLETS]):
-                self.cls.numpy()[:] = np.concatenate(cls, axis=0)
-        if motion is not None:
-            motion = [_np(m, np.float32) for m in motion]
-            self.motion = alloc((int(tot[TOT_TRACKLETS]), _lib.MOTION_DIM), torch.float32)
-            if int(tot[TOT_TRACKLETS]):
-                self.motion.numpy()[:] = np.concatenate(motion, axis=0)
-        self.table_t = torch.from_numpy(np.ascontiguousarray(self.table).reshape(-1, VT_COLS).copy())
-        if use_pin:
-            self.table_t = self.table_t.pin_memory()
+        self.cls = views.get("cls")
+        self.motion = views.get("motion")
+        if cls is not None and n_trk:
+            self.cls.numpy()[:] = np.concatenate(cls, axis=0)
+        if motion is not None and n_trk:
+            self.motion.numpy()[:] = np.concatenate(motion, axis=0)
+        self.table_t = views["table"]
+        self.table_t.numpy()[:] = np.ascontiguousarray(self.table).reshape(-1, VT_COLS)
 
     @classmethod
     def from_videos(cls, videos, pin: bool = True) -> "HostBatch":
@@ -88,12 +121,8 @@ class HostBatch:
         return len(self.n)
 
     def h2d_bytes(self) -> int:
-        tot = self.boxes.numel() * 4 + self.span.numel() * 4 + self.table_t.numel() * 8
-        if self.cls is not None:
-            tot += self.cls.numel() * 4
-        if self.motion is not None:
-            tot += self.motion.numel() * 4
-        return int(tot)
+        """Bytes one step copies host -> device (the whole arena, alignment padding included)."""
+        return int(self.arena.numel())
 
     def to_device(self, device="cuda", non_blocking: bool = True) -> "DeviceBatch":
         return DeviceBatch(self, device, non_blocking)
@@ -108,25 +137,19 @@ class DeviceBatch:
         self.table_host, self.totals = host.table, host.totals
         dev = torch.device(device)
         self.device = dev
-        self.table = host.table_t.to(dev, non_blocking=non_blocking)
-        self.boxes = host.boxes.to(dev, non_blocking=non_blocking)
-        self.span = host.span.to(dev, non_blocking=non_blocking)
-        self.cls = None if host.cls is None else host.cls.to(dev, non_blocking=non_blocking)
-        self.motion = None if host.motion is None else host.motion.to(dev, non_blocking=non_blocking)
+        self.layout = host.layout
+        self.arena = host.arena.to(dev, non_blocking=non_blocking)        # one H2D copy
+        views = _arena_views(self.arena, self.layout)
+        self.table, self.boxes, self.span = views["table"], views["boxes"], views["span"]
+        self.cls, self.motion = views.get("cls"), views.get("motion")
 
     def copy_from(self, host: HostBatch) -> "DeviceBatch":
         """Refill the device buffers from another host batch of the same layout (non-blocking, on the
         current stream): the steady-state H2D of a serving loop."""
-        if host.n != self.n or host.t != self.t:
-            raise ValueError("copy_from needs a host batch with the same per-video shapes")
+        if host.n != self.n or host.t != self.t or host.layout != self.layout:
+            raise ValueError("copy_from needs a host batch with the same per-video shapes and fields")
         self.host = host
-        self.table.copy_(host.table_t, non_blocking=True)
-        self.boxes.copy_(host.boxes, non_blocking=True)
-        self.span.copy_(host.span, non_blocking=True)
-        if self.cls is not None:
-            self.cls.copy_(host.cls, non_blocking=True)
-        if self.motion is not None:
-            self.motion.copy_(host.motion, non_blocking=True)
+        self.arena.copy_(host.arena, non_blocking=True)                   # one H2D copy
         return self
 
     # sizes -----------------------------------------------------------------------------

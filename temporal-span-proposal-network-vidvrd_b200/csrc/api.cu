@@ -136,7 +136,8 @@ int tspn_build_video_table(int num_videos, const int32_t* n_tracklets, const int
         trk += n;
         pairs += p;
         geo += p * TSPN_GEO_CHANNELS * tp;
-        items += n >= 2 ? n * ((n - 1 + TSPN_GEO_OBJ_GROUP - 1) / TSPN_GEO_OBJ_GROUP) : 0;
+        items += n >= 2 ? n * ((n - 1 + TSPN_GEO_OBJ_GROUP - 1) / TSPN_GEO_OBJ_GROUP) *
+                              ((t + TSPN_GEO_CHUNK - 1) / TSPN_GEO_CHUNK) : 0;
         boxes += n * tb;
         scores += n * n;
         if (n > max_n) max_n = n;

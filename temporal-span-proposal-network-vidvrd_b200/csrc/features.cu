@@ -35,48 +35,50 @@ __global__ void __launch_bounds__(128) normalize_motion_kernel(const float* __re
 }
 
 constexpr int ASM_THREADS = 256;
+constexpr int ASM_TCAP = 4104;     // frames of one geometry channel staged in shared memory (4096 + alignment slack)
 
-template <bool BF16>
-__device__ __forceinline__ void put(float* out, __nv_bfloat16* outb, int col, float v) {
-    if (out) out[col] = v;
-    if (BF16) outb[col] = __float2bfloat16(v);
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&v);
 }
 
-// copy `n` floats (n % 4 == 0, src 16-byte aligned) to columns [col0, col0+n) of the row
-template <bool BF16>
-__device__ __forceinline__ void copy_block(const float* __restrict__ src, int n, float* out, __nv_bfloat16* outb,
-                                           int col0, bool vec32, bool vec16) {
-    const float4* s4 = reinterpret_cast<const float4*>(src);
-    for (int q = threadIdx.x; q < n / 4; q += ASM_THREADS) {
-        const float4 v = __ldg(s4 + q);
-        const int col = col0 + 4 * q;
-        if (out) {
-            if (vec32) {
-                *reinterpret_cast<float4*>(out + col) = v;
-            } else {
-                out[col] = v.x; out[col + 1] = v.y; out[col + 2] = v.z; out[col + 3] = v.w;
-            }
-        }
-        if (BF16) {
-            const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-            if (vec16) {
-                uint2 pk;
-                pk.x = *reinterpret_cast<const uint32_t*>(&lo);
-                pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-                *reinterpret_cast<uint2*>(outb + col) = pk;
-            } else {
-                outb[col] = lo.x; outb[col + 1] = lo.y; outb[col + 2] = hi.x; outb[col + 3] = hi.y;
-            }
-        }
+// The row as a function of the column: [0,C) subject classeme | [C,2C) object classeme | subject motion |
+// object motion | pooled relative block (shared memory) | zero padding up to the leading dimension.
+struct RowSource {
+    const float* cls_s; const float* cls_o; const float* mot_s; const float* mot_o; const float* rel;
+    int C, m0, m1, r0, F;
+    __device__ __forceinline__ float at(int col) const {
+        if (col < C) return __ldg(cls_s + col);
+        if (col < m0) return __ldg(cls_o + (col - C));
+        if (col < m1) return __ldg(mot_s + (col - m0));
+        if (col < r0) return __ldg(mot_o + (col - m1));
+        if (col < F) return rel[col - r0];
+        return 0.0f;
     }
-}
+    // four consecutive columns starting at a multiple of 4; every segment boundary is a multiple of 4
+    __device__ __forceinline__ float4 at4(int col) const {
+        if (col < C) return __ldg(reinterpret_cast<const float4*>(cls_s + col));
+        if (col < m0) return __ldg(reinterpret_cast<const float4*>(cls_o + (col - C)));
+        if (col < m1) return __ldg(reinterpret_cast<const float4*>(mot_s + (col - m0)));
+        if (col < r0) return __ldg(reinterpret_cast<const float4*>(mot_o + (col - m1)));
+        if (col < F) return *reinterpret_cast<const float4*>(rel + (col - r0));
+        return make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+};
 
+// One CTA per output row.  (1) The pair's overlap window of two geometry channels at a time is staged
+// in shared memory with coalesced 128-bit loads (the window is read exactly once from HBM) and pooled
+// into the 3 x 2 x 500 bins of the relative block, which stay in shared memory; (2) the whole row
+// leaves as aligned 128-bit stores, each thread gathering the 4 (fp32) / 8 (bf16) columns of its
+// vector from the classeme / normalised-motion rows (L2) or the pooled block.
 template <bool BF16>
 __global__ void __launch_bounds__(ASM_THREADS)
 assemble_kernel(const int64_t* __restrict__ table, int nv, const float* __restrict__ cls, int n_classes,
                 const float* __restrict__ motion_norm, const float* __restrict__ geo,
                 const int32_t* __restrict__ overlap, const int64_t* __restrict__ rows, float* __restrict__ feat,
                 int64_t ld_feat, __nv_bfloat16* __restrict__ feat_bf16, int64_t ld_bf16) {
+    __shared__ __align__(16) float s_geo[2][ASM_TCAP];
+    __shared__ __align__(16) float s_rel[TSPN_REL_DIM];
     const int64_t r = blockIdx.x;
     const int64_t gp = rows ? rows[r] : r;
     float* out = feat ? feat + r * ld_feat : nullptr;
@@ -84,8 +86,12 @@ assemble_kernel(const int64_t* __restrict__ table, int nv, const float* __restri
     const int C = n_classes;
     const int F = 2 * C + 2 * TSPN_MOTION_DIM + TSPN_REL_DIM;
     if (gp < 0) {                                  // padding row (e.g. K_eff < K): zeros
-        for (int64_t col = threadIdx.x; col < (out ? ld_feat : 0); col += ASM_THREADS) out[col] = 0.0f;
-        for (int64_t col = threadIdx.x; col < (BF16 ? ld_bf16 : 0); col += ASM_THREADS) outb[col] = __float2bfloat16(0.0f);
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (out)
+            for (int64_t q = threadIdx.x; q < ld_feat / 4; q += ASM_THREADS) reinterpret_cast<float4*>(out)[q] = z;
+        if (BF16)
+            for (int64_t q = threadIdx.x; q < ld_bf16 / 8; q += ASM_THREADS)
+                reinterpret_cast<uint4*>(outb)[q] = make_uint4(0u, 0u, 0u, 0u);
         return;
     }
     const int v = find_video(table, nv, TSPN_VT_PAIR_OFF, gp);
@@ -97,40 +103,77 @@ assemble_kernel(const int64_t* __restrict__ table, int nv, const float* __restri
     const int k = p - s * (n - 1);
     const int o = k + (k >= s ? 1 : 0);
     const int64_t ts = row[TSPN_VT_TRK_OFF] + s, to = row[TSPN_VT_TRK_OFF] + o;
-    const int m0 = 2 * C, m1 = m0 + TSPN_MOTION_DIM, r0 = m1 + TSPN_MOTION_DIM;
-    // ---- classemes ----
-    for (int col = threadIdx.x; col < m0; col += ASM_THREADS)
-        put<BF16>(out, outb, col, __ldg(cls + (col < C ? ts * C + col : to * C + (col - C))));
-    // ---- motion blocks: 128-bit copies when the row offset 2C allows it ----
-    const bool vec32 = (m0 & 3) == 0, vec16 = (m0 & 3) == 0;       // 16-byte (fp32) / 8-byte (bf16) stores
-    copy_block<BF16>(motion_norm + ts * TSPN_MOTION_DIM, TSPN_MOTION_DIM, out, outb, m0, vec32, vec16);
-    copy_block<BF16>(motion_norm + to * TSPN_MOTION_DIM, TSPN_MOTION_DIM, out, outb, m1, vec32, vec16);
+
     // ---- relative block: bin i of every pooled channel shares its frame range ----
     const float* g = geo + row[TSPN_VT_GEO_OFF] + (int64_t)p * TSPN_GEO_CHANNELS * tp;
     const int a = __ldg(overlap + 2 * gp), b = __ldg(overlap + 2 * gp + 1);
     const uint32_t len = b > a ? (uint32_t)(b - a) : 0u;
-    for (int i = threadIdx.x; i < TSPN_REL_BINS; i += ASM_THREADS) {
-        float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (len > 0) {
-            const uint32_t st = ((uint32_t)i * len) / TSPN_REL_BINS;              // len < 2^22: fits 32 bits
-            const uint32_t en = ((uint32_t)(i + 1) * len + TSPN_REL_BINS - 1) / TSPN_REL_BINS;
-            const float inv = 1.0f / (float)(en - st);
-#pragma unroll
-            for (int slot = 0; slot < 6; ++slot) {
-                const float* gc = g + (int64_t)(slot < 4 ? slot : slot + 1) * tp + a;
-                float sacc = 0.0f;
-                for (uint32_t f = st; f < en; ++f) sacc += __ldg(gc + f);
-                acc[slot] = sacc * inv;
+    const int a4 = a & ~3;
+    const int staged_frames = b - a4;
+    const bool staged = len > 0 && staged_frames <= ASM_TCAP - 4 && ((reinterpret_cast<uintptr_t>(g) & 15) == 0);
+#pragma unroll 1
+    for (int cp = 0; cp < 3; ++cp) {
+        const int ch0 = cp < 2 ? 2 * cp : 5;       // channel pairs (0,1) position, (2,3) size, (5,6) motion
+        if (staged) {
+            if (cp) __syncthreads();               // the previous pair's readers are done
+            const int nvec = (staged_frames + 3) >> 2;
+            for (int q = threadIdx.x; q < 2 * nvec; q += ASM_THREADS) {
+                const int c = q >= nvec ? 1 : 0;
+                const int qq = q - c * nvec;
+                const float4 val = __ldg(reinterpret_cast<const float4*>(g + (int64_t)(ch0 + c) * tp + a4) + qq);
+                *reinterpret_cast<float4*>(&s_geo[c][4 * qq]) = val;
             }
+            __syncthreads();
         }
-#pragma unroll
-        for (int slot = 0; slot < 6; ++slot) put<BF16>(out, outb, r0 + slot * TSPN_REL_BINS + i, acc[slot]);
+        for (int w = threadIdx.x; w < 2 * TSPN_REL_BINS; w += ASM_THREADS) {
+            const int c = w >= TSPN_REL_BINS ? 1 : 0;
+            const int i = w - c * TSPN_REL_BINS;
+            float acc = 0.0f;
+            if (len > 0) {
+                const uint32_t st = ((uint32_t)i * len) / TSPN_REL_BINS;              // len < 2^22: fits 32 bits
+                const uint32_t en = ((uint32_t)(i + 1) * len + TSPN_REL_BINS - 1) / TSPN_REL_BINS;
+                const float inv = 1.0f / (float)(en - st);
+                float sacc = 0.0f;
+                if (staged) {
+                    const float* sp = &s_geo[c][a - a4];
+                    for (uint32_t f = st; f < en; ++f) sacc += sp[f];
+                } else {
+                    const float* gc = g + (int64_t)(ch0 + c) * tp + a;
+                    for (uint32_t f = st; f < en; ++f) sacc += __ldg(gc + f);
+                }
+                acc = sacc * inv;
+            }
+            s_rel[(2 * cp + c) * TSPN_REL_BINS + i] = acc;
+        }
     }
-    // zero the padding columns so that a padded row can be fed to TMA / vector loads
-    if (out)
-        for (int64_t col = F + threadIdx.x; col < ld_feat; col += ASM_THREADS) out[col] = 0.0f;
-    if (BF16)
-        for (int64_t col = F + threadIdx.x; col < ld_bf16; col += ASM_THREADS) outb[col] = __float2bfloat16(0.0f);
+    __syncthreads();
+
+    // ---- the row, as aligned vectors ----
+    RowSource src;
+    src.cls_s = cls + ts * C; src.cls_o = cls + to * C;
+    src.mot_s = motion_norm + ts * TSPN_MOTION_DIM; src.mot_o = motion_norm + to * TSPN_MOTION_DIM;
+    src.rel = s_rel;
+    src.C = C; src.m0 = 2 * C; src.m1 = src.m0 + TSPN_MOTION_DIM; src.r0 = src.m1 + TSPN_MOTION_DIM; src.F = F;
+    const bool fast = (C & 3) == 0 && ((reinterpret_cast<uintptr_t>(cls) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(motion_norm) & 15) == 0);
+    const int ld_max = (int)max(out ? ld_feat : (int64_t)0, BF16 ? ld_bf16 : (int64_t)0);
+    for (int col = 8 * threadIdx.x; col < ld_max; col += 8 * ASM_THREADS) {
+        float4 lo, hi;
+        if (fast) {
+            lo = src.at4(col);
+            hi = src.at4(col + 4);
+        } else {
+            lo = make_float4(src.at(col), src.at(col + 1), src.at(col + 2), src.at(col + 3));
+            hi = make_float4(src.at(col + 4), src.at(col + 5), src.at(col + 6), src.at(col + 7));
+        }
+        if (out) {
+            if (col + 4 <= ld_feat) *reinterpret_cast<float4*>(out + col) = lo;
+            if (col + 8 <= ld_feat) *reinterpret_cast<float4*>(out + col + 4) = hi;
+        }
+        if (BF16 && col + 8 <= ld_bf16)
+            *reinterpret_cast<uint4*>(outb + col) = make_uint4(pack_bf16x2(lo.x, lo.y), pack_bf16x2(lo.z, lo.w),
+                                                                pack_bf16x2(hi.x, hi.y), pack_bf16x2(hi.z, hi.w));
+    }
 }
 
 }  // namespace tspn

@@ -25,16 +25,23 @@
 
 namespace tspn {
 
-constexpr int GEO_THREADS = 128;
 constexpr int GEO_FPT = 4;
-constexpr int GEO_CHUNK = GEO_THREADS * GEO_FPT;      // 512 frames per step
-constexpr int GEO_ROWS = GEO_CHUNK / 8 + 1;           // 64 rows of 8 boxes + 1 halo row
-constexpr int GEO_TX_BYTES = GEO_ROWS * 128;          // 8320 bytes per TMA box
+constexpr int GEO_CHUNK = TSPN_GEO_CHUNK;             // frames per work item
+constexpr int GEO_THREADS = GEO_CHUNK / GEO_FPT;
+constexpr int GEO_ROWS = GEO_CHUNK / 8 + 1;           // rows of 8 boxes + 1 halo row
+constexpr int GEO_TX_BYTES = GEO_ROWS * 128;          // bytes per TMA box
 constexpr int GEO_STAGE_BYTES = GEO_TX_BYTES;         // stages are packed (128-byte aligned)
 constexpr int GEO_OG = TSPN_GEO_OBJ_GROUP;
 constexpr int GEO_WARPS = GEO_THREADS / 32;
-constexpr int GEO_SMEM_BYTES = 4 * GEO_STAGE_BYTES + 512;
-constexpr int GEO_MIN_CTAS = 6;                       // 6 x 33.8 KB of shared memory per SM
+constexpr int GEO_STAGES = 1 + 2;                     // subject chunk + object ring
+// HBM absorbs this kernel's store stream best with few concurrent writers per SM
+// (tools/bench_store_pattern.cu: 7.3 TB/s at 6 CTAs x 128 threads, 6.8 TB/s unconstrained): the
+// shared-memory request pins the occupancy at GEO_MIN_CTAS.
+constexpr int GEO_MIN_CTAS = 768 / GEO_THREADS;
+constexpr int GEO_SMEM_BYTES = (GEO_STAGES * GEO_STAGE_BYTES + 1024) > (227 * 1024 / (GEO_MIN_CTAS + 1) + 1024)
+                                   ? (GEO_STAGES * GEO_STAGE_BYTES + 1024)
+                                   : (227 * 1024 / (GEO_MIN_CTAS + 1) + 1024);
+static_assert(GEO_CHUNK % 256 == 0 && GEO_THREADS <= 256, "chunk must be a multiple of 256 frames, at most 1024");
 
 // box j of a chunk staged with SWIZZLE_128B: the 16-byte slot index (address bits 4..6) is XORed
 // with address bits 7..9 of the shared-memory address, so the pattern is a function of the
@@ -77,14 +84,18 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// ---- per-tracklet volume: sum over [pstart, pend) of w*h, fp64 ---------------------------------
+// ---- pre-kernel: per-tracklet volume (sum over [pstart, pend) of w*h, fp64; one warp per tracklet)
+// and zeroing of the per-pair fixed-point accumulators --------------------------------------------
 __global__ void __launch_bounds__(128) tracklet_volume_kernel(const int64_t* __restrict__ table, int nv,
                                                               int64_t total_tracklets,
                                                               const float4* __restrict__ boxes,
                                                               const int32_t* __restrict__ span,
-                                                              double* __restrict__ vol) {
+                                                              double* __restrict__ vol, bool want_vol,
+                                                              unsigned long long* __restrict__ fx, int64_t n_fx) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_fx; i += (int64_t)gridDim.x * blockDim.x)
+        fx[i] = 0ull;
     const int64_t trk = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (trk >= total_tracklets) return;
+    if (!want_vol || trk >= total_tracklets) return;
     const int lane = threadIdx.x & 31;
     const int v = find_video(table, nv, TSPN_VT_TRK_OFF, trk);
     const int64_t* row = table + (int64_t)v * TSPN_VT_COLS;
@@ -101,20 +112,39 @@ __global__ void __launch_bounds__(128) tracklet_volume_kernel(const int64_t* __r
 }
 
 // ---- the pair kernel ----------------------------------------------------------------------------
+// Work item = (video, subject s, group of GEO_OG objects, chunk of GEO_CHUNK frames); one CTA per
+// item, chunk-fastest in the grid.  The subject chunk is staged once, the object chunks stream
+// through a 2-deep TMA ring (full/empty mbarriers, no block-wide barrier in the loop).
+//
+// Volume sums are accumulated as 64-bit fixed point (2^-16 units): a thread's fp32 partial over its 4
+// frames (exact: integer-valued products below 2^24) is converted once, the warp total is two
+// REDUX.SUM on 24-bit limbs, lane 0 adds it to the pair's shared-memory accumulator and the CTA adds
+// its chunk's total to the pair's global accumulator, all with integer atomics.  Integer addition is
+// associative, so the sums - exact for integer boxes, quantised at 2^-17 absolute per partial
+// otherwise - do not depend on any reduction or scheduling order.
+constexpr float GEO_FX_SCALE = 65536.0f;
+
+__device__ __forceinline__ unsigned long long warp_sum_fx(float v) {
+    const unsigned long long fx = __float2ull_rn(v * GEO_FX_SCALE);
+    const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)(fx & 0xffffffull));       // < 2^29
+    const unsigned hi = __reduce_add_sync(0xffffffffu, (unsigned)(fx >> 24));               // < 2^27
+    return (unsigned long long)lo + ((unsigned long long)hi << 24);
+}
+
 template <bool WRITE_GEO, bool CLIP>
 __global__ void __launch_bounds__(GEO_THREADS, GEO_MIN_CTAS)
 pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __restrict__ table, int nv,
-                const int32_t* __restrict__ span, const double* __restrict__ vol, float* __restrict__ geo,
-                float* __restrict__ viou, float* __restrict__ tiou, int32_t* __restrict__ overlap) {
+                const int32_t* __restrict__ span, float* __restrict__ geo, unsigned long long* __restrict__ fx) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* const s_stage0 = smem;
-    uint8_t* const o_stage0 = smem + 2 * GEO_STAGE_BYTES;
-    uint64_t* const bar = reinterpret_cast<uint64_t*>(smem + 4 * GEO_STAGE_BYTES);            // [2]
-    double* const warp_part = reinterpret_cast<double*>(smem + 4 * GEO_STAGE_BYTES + 16);     // [2][WARPS][3]
-    double* const acc = warp_part + 2 * GEO_WARPS * 3;                                        // [OG][3]
+    uint8_t* const s_stage = smem;
+    uint8_t* const o_stage0 = smem + GEO_STAGE_BYTES;
+    uint64_t* const full = reinterpret_cast<uint64_t*>(smem + GEO_STAGES * GEO_STAGE_BYTES);  // [2]
+    uint64_t* const empty = full + 2;                                                         // [2]
+    unsigned long long* const acc = reinterpret_cast<unsigned long long*>(empty + 2);         // [OG][3]
+    int2* const ospan = reinterpret_cast<int2*>(acc + GEO_OG * 3);                            // [OG]
 
     const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
+    const int lane = tid & 31;
 
     // ---- decode the work item ------------------------------------------------------------------
     const int64_t item = blockIdx.x;
@@ -126,52 +156,58 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
     const int64_t tb = row[TSPN_VT_TB];
     const int64_t trk_off = row[TSPN_VT_TRK_OFF];
     const int groups = (n - 1 + GEO_OG - 1) / GEO_OG;
-    const int local = (int)(item - row[TSPN_VT_ITEM_OFF]);
-    const int s = local / groups;
-    const int k0 = (local - s * groups) * GEO_OG;
-    const int nobj = min(GEO_OG, n - 1 - k0);
     const int nchunks = (t_len + GEO_CHUNK - 1) / GEO_CHUNK;
-    const int steps = nchunks * nobj;
+    const int local = (int)(item - row[TSPN_VT_ITEM_OFF]);
+    const int c = local % nchunks;
+    const int sg = local / nchunks;
+    const int s = sg / groups;
+    const int k0 = (sg - s * groups) * GEO_OG;
+    const int nobj = min(GEO_OG, n - 1 - k0);
     const int64_t box_row0 = row[TSPN_VT_BOX_OFF];           // multiple of 8
     const int64_t pair0 = row[TSPN_VT_PAIR_OFF] + (int64_t)s * (n - 1) + k0;
     const int ps = __ldg(span + 2 * (trk_off + s)), pe = __ldg(span + 2 * (trk_off + s) + 1);
 
     if (tid == 0) {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        mbar_init(&empty[0], GEO_WARPS);
+        mbar_init(&empty[1], GEO_WARPS);
         fence_mbar_init();
     }
-    if (tid < GEO_OG * 3) acc[tid] = 0.0;
+    if (tid < GEO_OG * 3) acc[tid] = 0ull;
+    if (tid < nobj) {
+        const int k = k0 + tid;
+        const int o = k + (k >= s ? 1 : 0);
+        ospan[tid] = make_int2(__ldg(span + 2 * (trk_off + o)), __ldg(span + 2 * (trk_off + o) + 1));
+    }
     __syncthreads();
 
-    auto issue = [&](int q) {
-        const int c = q / nobj;
-        const int jj = q - c * nobj;
-        const int k = k0 + jj;
+    auto issue = [&](int q) {          // thread 0: object q (and, with the first, the subject chunk)
+        const int k = k0 + q;
         const int o = k + (k >= s ? 1 : 0);
         const int st = q & 1;
-        mbar_expect_tx(&bar[st], jj == 0 ? 2 * GEO_TX_BYTES : GEO_TX_BYTES);
-        if (jj == 0)
-            tma_load_2d(s_stage0 + (c & 1) * GEO_STAGE_BYTES, &box_map, 0,
-                        (int)((box_row0 + (int64_t)s * tb + (int64_t)c * GEO_CHUNK) >> 3), &bar[st]);
+        mbar_expect_tx(&full[st], q == 0 ? 2 * GEO_TX_BYTES : GEO_TX_BYTES);
+        if (q == 0)
+            tma_load_2d(s_stage, &box_map, 0, (int)((box_row0 + (int64_t)s * tb + (int64_t)c * GEO_CHUNK) >> 3),
+                        &full[st]);
         tma_load_2d(o_stage0 + st * GEO_STAGE_BYTES, &box_map, 0,
-                    (int)((box_row0 + (int64_t)o * tb + (int64_t)c * GEO_CHUNK) >> 3), &bar[st]);
+                    (int)((box_row0 + (int64_t)o * tb + (int64_t)c * GEO_CHUNK) >> 3), &full[st]);
     };
-    if (tid == 0) issue(0);
+    if (tid == 0) {
+        issue(0);
+        if (nobj > 1) issue(1);
+    }
 
-    for (int q = 0; q < steps; ++q) {
-        const int c = q / nobj;
-        const int jj = q - c * nobj;
-        const int k = k0 + jj;
-        const int o = k + (k >= s ? 1 : 0);
-        if (tid == 0 && q + 1 < steps) issue(q + 1);
+    const int t0 = c * GEO_CHUNK + tid * GEO_FPT;            // first frame of this thread
+    const int j0 = tid * GEO_FPT;                            // ... inside the staged chunk
+    const uint32_t ss = smem_u32(s_stage);
+    float* g = WRITE_GEO ? geo + row[TSPN_VT_GEO_OFF] + ((int64_t)(s * (n - 1) + k0) * TSPN_GEO_CHANNELS) * tp + t0
+                         : nullptr;
+    for (int q = 0; q < nobj; ++q) {
+        const int2 os = ospan[q];
+        const int a = max(ps, os.x), b = min(pe, os.y);      // overlap window [a, b)
 
-        const int qs = __ldg(span + 2 * (trk_off + o)), qe = __ldg(span + 2 * (trk_off + o) + 1);
-        const int a = max(ps, qs), b = min(pe, qe);          // overlap window [a, b)
-        const int t0 = c * GEO_CHUNK + tid * GEO_FPT;        // first frame of this thread
-        const int j0 = tid * GEO_FPT;                        // ... inside the staged chunk
-
-        mbar_wait(&bar[q & 1], (q >> 1) & 1);
+        mbar_wait(&full[q & 1], (q >> 1) & 1);
 
         // per-thread partial sums stay in fp32: 4 integer-valued products <= 4 * 2^21 < 2^24 are exact
         float fsum_i = 0.0f, fsum_s = 0.0f, fsum_o = 0.0f;
@@ -182,14 +218,13 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
             for (int i = 0; i < GEO_FPT; ++i) out[ch][i] = 0.0f;
 
         if (t0 < b && t0 + GEO_FPT > a) {
-            const uint32_t ss = smem_u32(s_stage0 + (c & 1) * GEO_STAGE_BYTES);
-            const uint32_t os = smem_u32(o_stage0 + (q & 1) * GEO_STAGE_BYTES);
+            const uint32_t os_addr = smem_u32(o_stage0 + (q & 1) * GEO_STAGE_BYTES);
             float dcx[GEO_FPT + 1], dcy[GEO_FPT + 1], wo[GEO_FPT + 1], ho[GEO_FPT + 1];
             float rwo[GEO_FPT + 1], rho[GEO_FPT + 1];
 #pragma unroll
             for (int i = 0; i <= GEO_FPT; ++i) {
                 const float4 sb = ld_box(ss, j0 + i);
-                const float4 ob = ld_box(os, j0 + i);
+                const float4 ob = ld_box(os_addr, j0 + i);
                 wo[i] = (ob.z - ob.x) + 1.0f;
                 ho[i] = (ob.w - ob.y) + 1.0f;
                 rwo[i] = rcp_fast(wo[i]);
@@ -239,54 +274,75 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
                 }
             }
         }
-        double sum_i = (double)fsum_i, sum_s = (double)fsum_s, sum_o = (double)fsum_o;
+        // this warp is done reading the object stage of step q: hand it back; thread 0 refills it with
+        // object q+2 (end of the step) once every warp has done so
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[q & 1]);
+
         if (WRITE_GEO && t0 < tp) {
-            float* g = geo + row[TSPN_VT_GEO_OFF] + ((int64_t)(s * (n - 1) + k) * TSPN_GEO_CHANNELS) * tp + t0;
 #pragma unroll
             for (int ch = 0; ch < TSPN_GEO_CHANNELS; ++ch)
                 st_stream_f4(g + (int64_t)ch * tp, make_float4(out[ch][0], out[ch][1], out[ch][2], out[ch][3]));
+            g += (int64_t)TSPN_GEO_CHANNELS * tp;
         }
-        // reduce the three volume sums over the chunk's frames
-        sum_i = warp_sum(sum_i);
+        // the three volume sums over the chunk's frames (order-independent, see above)
+        const unsigned long long tot_i = warp_sum_fx(fsum_i);
+        unsigned long long tot_s = 0ull, tot_o = 0ull;
         if (CLIP) {
-            sum_s = warp_sum(sum_s);
-            sum_o = warp_sum(sum_o);
+            tot_s = warp_sum_fx(fsum_s);
+            tot_o = warp_sum_fx(fsum_o);
         }
         if (lane == 0) {
-            double* wp = warp_part + ((q & 1) * GEO_WARPS + warp) * 3;
-            wp[0] = sum_i;
-            wp[1] = sum_s;
-            wp[2] = sum_o;
+            if (tot_i) atomicAdd(&acc[q * 3 + 0], tot_i);
+            if (CLIP) {
+                if (tot_s) atomicAdd(&acc[q * 3 + 1], tot_s);
+                if (tot_o) atomicAdd(&acc[q * 3 + 2], tot_o);
+            }
         }
-        __syncthreads();   // stage (q&1) may be refilled; warp_part[q&1] is complete
-        if (tid < 3) {
-            double tot = 0.0;
-#pragma unroll
-            for (int w = 0; w < GEO_WARPS; ++w) tot += warp_part[((q & 1) * GEO_WARPS + w) * 3 + tid];
-            acc[jj * 3 + tid] += tot;
+        if (tid == 0 && q + 2 < nobj) {                      // by now the other warps have normally arrived
+            mbar_wait(&empty[q & 1], (q >> 1) & 1);
+            issue(q + 2);
         }
     }
     __syncthreads();
-
-    // ---- per-pair reductions: vIoU, tIoU, overlap window ------------------------------------------
-    if (tid < nobj) {
-        const int k = k0 + tid;
-        const int o = k + (k >= s ? 1 : 0);
-        const int qs = __ldg(span + 2 * (trk_off + o)), qe = __ldg(span + 2 * (trk_off + o) + 1);
-        const int a = max(ps, qs), b = min(pe, qe);
-        const bool has = b > a;
-        const double inter = acc[tid * 3 + 0];
-        const double vs = CLIP ? acc[tid * 3 + 1] : vol[trk_off + s];
-        const double vo = CLIP ? acc[tid * 3 + 2] : vol[trk_off + o];
-        const double den = vs + vo - inter;
-        const int ov = has ? b - a : 0;
-        const int tden = (pe - ps) + (qe - qs) - ov;
-        const int64_t p = pair0 + tid;
-        viou[p] = (has && den > 0.0) ? (float)(inter / den) : 0.0f;
-        tiou[p] = (has && tden > 0) ? (float)((double)ov / (double)tden) : 0.0f;
-        overlap[2 * p] = has ? a : 0;
-        overlap[2 * p + 1] = has ? b : 0;
+    // this chunk's contribution to the pair's sums
+    if (tid < nobj * 3) {
+        const int q = tid / 3, w = tid - 3 * q;
+        const unsigned long long val = acc[tid];
+        if (val) atomicAdd(fx + (pair0 + q) * 3 + w, val);
     }
+}
+
+// ---- post-kernel: per-pair reductions (vIoU, tIoU, overlap window) -----------------------------------
+template <bool CLIP>
+__global__ void __launch_bounds__(256)
+pair_finalize_kernel(const int64_t* __restrict__ table, int nv, int64_t total_pairs, const int32_t* __restrict__ span,
+                     const double* __restrict__ vol, const unsigned long long* __restrict__ fx,
+                     float* __restrict__ viou, float* __restrict__ tiou, int32_t* __restrict__ overlap) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= total_pairs) return;
+    const int v = find_video(table, nv, TSPN_VT_PAIR_OFF, p);
+    const int64_t* row = table + (int64_t)v * TSPN_VT_COLS;
+    const int n1 = (int)row[TSPN_VT_N] - 1;
+    const int loc = (int)(p - row[TSPN_VT_PAIR_OFF]);
+    const int s = loc / n1, k = loc - s * n1;
+    const int o = k + (k >= s ? 1 : 0);
+    const int64_t ts = row[TSPN_VT_TRK_OFF] + s, to = row[TSPN_VT_TRK_OFF] + o;
+    const int ps = __ldg(span + 2 * ts), pe = __ldg(span + 2 * ts + 1);
+    const int qs = __ldg(span + 2 * to), qe = __ldg(span + 2 * to + 1);
+    const int a = max(ps, qs), b = min(pe, qe);
+    const bool has = b > a;
+    const double inv_scale = 1.0 / (double)GEO_FX_SCALE;
+    const double inter = (double)fx[p * 3 + 0] * inv_scale;
+    const double vs = CLIP ? (double)fx[p * 3 + 1] * inv_scale : vol[ts];
+    const double vo = CLIP ? (double)fx[p * 3 + 2] * inv_scale : vol[to];
+    const double den = vs + vo - inter;
+    const int ov = has ? b - a : 0;
+    const int tden = (pe - ps) + (qe - qs) - ov;
+    viou[p] = (has && den > 0.0) ? (float)(inter / den) : 0.0f;
+    tiou[p] = (has && tden > 0) ? (float)((double)ov / (double)tden) : 0.0f;
+    overlap[2 * p] = has ? a : 0;
+    overlap[2 * p + 1] = has ? b : 0;
 }
 
 // ---- cubic_iou(bboxes1, bboxes2): one warp per matrix entry -------------------------------------
@@ -394,18 +450,22 @@ int tspn_enumerate_pairs(const int64_t* d_table, int num_videos, int64_t total_p
     return TSPN_OK;
 }
 
-int64_t tspn_pair_geo_workspace_bytes(int64_t total_tracklets) {
-    return (total_tracklets > 0 ? total_tracklets : 1) * (int64_t)sizeof(double);
+static inline int64_t geo_ws_vol_bytes(int64_t total_tracklets) {
+    return ((total_tracklets > 0 ? total_tracklets : 1) * (int64_t)sizeof(double) + 15) / 16 * 16;
+}
+
+int64_t tspn_pair_geo_workspace_bytes(int64_t total_tracklets, int64_t total_pairs) {
+    return geo_ws_vol_bytes(total_tracklets) + (total_pairs > 0 ? total_pairs : 1) * 3 * (int64_t)sizeof(uint64_t);
 }
 
 int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_items, int64_t total_tracklets,
-                       int64_t total_boxes, const float* d_boxes, const int32_t* d_span, float* d_geo,
-                       float* d_viou, float* d_tiou, int32_t* d_overlap, int flags, void* d_workspace,
+                       int64_t total_pairs, int64_t total_boxes, const float* d_boxes, const int32_t* d_span,
+                       float* d_geo, float* d_viou, float* d_tiou, int32_t* d_overlap, int flags, void* d_workspace,
                        void* stream) {
     TSPN_ARCH_OK();
-    TSPN_REQUIRE(num_videos >= 0 && total_items >= 0 && total_tracklets >= 0 && total_boxes >= 0, TSPN_EBADARG,
-                 "tspn_pair_geo_viou: negative size");
-    if (total_items == 0) return TSPN_OK;
+    TSPN_REQUIRE(num_videos >= 0 && total_items >= 0 && total_tracklets >= 0 && total_boxes >= 0 && total_pairs >= 0,
+                 TSPN_EBADARG, "tspn_pair_geo_viou: negative size");
+    if (total_items == 0 || total_pairs == 0) return TSPN_OK;
     TSPN_REQUIRE(d_table && d_boxes && d_span && d_viou && d_tiou && d_overlap && d_workspace, TSPN_EBADARG,
                  "tspn_pair_geo_viou: null pointer");
     TSPN_REQUIRE(aligned16(d_boxes) && aligned16(d_geo) && aligned16(d_workspace), TSPN_EALIGN,
@@ -416,10 +476,19 @@ int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_ite
     TSPN_REQUIRE(total_items < (1ll << 31), TSPN_ESHAPE, "tspn_pair_geo_viou: too many work items");
     cudaStream_t st = (cudaStream_t)stream;
     double* vol = reinterpret_cast<double*>(d_workspace);
+    unsigned long long* fx =
+        reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(d_workspace) + geo_ws_vol_bytes(total_tracklets));
     const bool clip = (flags & TSPN_VIOU_CLIPPED) != 0;
-    if (!clip) {
-        tracklet_volume_kernel<<<(unsigned)((total_tracklets + 3) / 4), 128, 0, st>>>(
-            d_table, num_videos, total_tracklets, reinterpret_cast<const float4*>(d_boxes), d_span, vol);
+    {
+        // volumes (one warp per tracklet) + zeroing of the fixed-point accumulators (grid-stride)
+        const int64_t blocks_vol = clip ? 0 : (total_tracklets + 3) / 4;
+        const int64_t blocks_zero = (total_pairs * 3 + 127) / 128;
+        int64_t blocks = blocks_vol > 1 ? blocks_vol : 1;
+        const int64_t cap = 8 * (int64_t)num_sms();
+        if (blocks < blocks_zero) blocks = blocks_zero < cap ? blocks_zero : (blocks > cap ? blocks : cap);
+        tracklet_volume_kernel<<<(unsigned)blocks, 128, 0, st>>>(d_table, num_videos, total_tracklets,
+                                                                reinterpret_cast<const float4*>(d_boxes), d_span, vol,
+                                                                !clip, fx, total_pairs * 3);
         TSPN_CUDA_OK(cudaGetLastError());
     }
     // boxes viewed as a 2-D tensor: rows of 8 boxes (32 floats = 128 B)
@@ -436,7 +505,7 @@ int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_ite
         TSPN_CUDA_OK(cudaFuncSetAttribute(pair_geo_kernel<W, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                           GEO_SMEM_BYTES));                                                \
         pair_geo_kernel<W, C><<<(unsigned)total_items, GEO_THREADS, GEO_SMEM_BYTES, st>>>(                 \
-            map, d_table, num_videos, d_span, vol, d_geo, d_viou, d_tiou, d_overlap);                      \
+            map, d_table, num_videos, d_span, d_geo, fx);                                                  \
     } while (0)
     if (d_geo) {
         if (clip) TSPN_LAUNCH_GEO(true, true); else TSPN_LAUNCH_GEO(true, false);
@@ -444,6 +513,14 @@ int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_ite
         if (clip) TSPN_LAUNCH_GEO(false, true); else TSPN_LAUNCH_GEO(false, false);
     }
 #undef TSPN_LAUNCH_GEO
+    TSPN_CUDA_OK(cudaGetLastError());
+    const unsigned fblocks = (unsigned)((total_pairs + 255) / 256);
+    if (clip)
+        pair_finalize_kernel<true><<<fblocks, 256, 0, st>>>(d_table, num_videos, total_pairs, d_span, vol, fx, d_viou,
+                                                            d_tiou, d_overlap);
+    else
+        pair_finalize_kernel<false><<<fblocks, 256, 0, st>>>(d_table, num_videos, total_pairs, d_span, vol, fx, d_viou,
+                                                             d_tiou, d_overlap);
     TSPN_CUDA_OK(cudaGetLastError());
     return TSPN_OK;
 }

@@ -197,6 +197,21 @@ span_head_small_kernel(const float* __restrict__ x, const int64_t* __restrict__ 
 }
 
 // [SPEC] s5, every step one correctly rounded fp32 operation (see oracle/exact).
+__device__ __forceinline__ void decode_anchor(float dc, float dw, float aw, float ac, int t_len, int32_t* lo_out,
+                                              int32_t* hi_out) {
+    const float CLAMP = 4.1351666f;                     // fp32 nearest of log(1000/16)
+    dw = fminf(dw, CLAMP);
+    const float ctr = __fmaf_rn(dc, aw, ac);
+    const float w = __fmul_rn(aw, exp_det(dw));
+    const float hw = __fmul_rn(0.5f, w);
+    float lo = floorf(__fadd_rn(__fadd_rn(ctr, -hw), 0.5f));
+    float hi = floorf(__fadd_rn(__fadd_rn(ctr, hw), 0.5f));
+    lo = fminf(fmaxf(lo, 0.0f), (float)(t_len - 1));
+    hi = fminf(fmaxf(hi, __fadd_rn(lo, 1.0f)), (float)t_len);
+    *lo_out = (int32_t)lo;
+    *hi_out = (int32_t)hi;
+}
+
 __global__ void __launch_bounds__(256)
 span_decode_kernel(const float* __restrict__ reg, int64_t k, int a_n, int t_len, int n_loc,
                    const float* __restrict__ sizes, float stride, int32_t* __restrict__ spans) {
@@ -206,22 +221,144 @@ span_decode_kernel(const float* __restrict__ reg, int64_t k, int a_n, int t_len,
     const int a = (int)(idx % a_n);
     const int l = (int)((idx / a_n) % n_loc);
     const int64_t p = idx / ((int64_t)a_n * n_loc);
-    const float CLAMP = 4.1351666f;                     // fp32 nearest of log(1000/16)
     const float ac = __fmul_rn((float)l, stride);
     int col = (int)floorf(ac);
     col = min(col, t_len - 1);
     const float aw = __ldg(sizes + a);
     const float dc = __ldg(reg + (p * 2 * a_n + 2 * a) * t_len + col);
-    const float dw = fminf(__ldg(reg + (p * 2 * a_n + 2 * a + 1) * t_len + col), CLAMP);
-    const float ctr = __fmaf_rn(dc, aw, ac);
-    const float w = __fmul_rn(aw, exp_det(dw));
-    const float hw = __fmul_rn(0.5f, w);
-    float lo = floorf(__fadd_rn(__fadd_rn(ctr, -hw), 0.5f));
-    float hi = floorf(__fadd_rn(__fadd_rn(ctr, hw), 0.5f));
-    lo = fminf(fmaxf(lo, 0.0f), (float)(t_len - 1));
-    hi = fminf(fmaxf(hi, __fadd_rn(lo, 1.0f)), (float)t_len);
-    spans[2 * idx] = (int32_t)lo;
-    spans[2 * idx + 1] = (int32_t)hi;
+    const float dw = __ldg(reg + (p * 2 * a_n + 2 * a + 1) * t_len + col);
+    int32_t lo, hi;
+    decode_anchor(dc, dw, aw, ac, t_len, &lo, &hi);
+    spans[2 * idx] = lo;
+    spans[2 * idx + 1] = hi;
+}
+
+// Fused span proposals: the head is evaluated only at the anchor columns floor(l * stride) the
+// decode reads (n_loc of the T frames), with the fma chain of span_head_*_kernel per column, and the
+// regressions are decoded in registers - the [K, 2A, T] regression tensor never exists.  One thread
+// per (pair, anchor location); bit-identical to tspn_span_head(fp32) followed by tspn_span_decode.
+template <int CIN, int A>
+__global__ void __launch_bounds__(SH_THREADS)
+span_proposals_small_kernel(const float* __restrict__ x, const int64_t* __restrict__ rows, int64_t row_base,
+                            int64_t row_stride, int64_t ld_t, int t_len, const float* __restrict__ conv_w,
+                            const float* __restrict__ conv_b, const float* __restrict__ pred_w,
+                            const float* __restrict__ pred_b, const float* __restrict__ sizes, float stride,
+                            int n_loc, int32_t* __restrict__ spans) {
+    constexpr int A2 = 2 * A;
+    __shared__ __align__(16) float4 w_conv[CIN * CIN];      // [co][ci] -> (w0, w1, w2, -)
+    __shared__ __align__(16) float w_pred[CIN * A2];        // [co][j]
+    __shared__ float b_conv[CIN], b_pred[A2];
+    for (int i = threadIdx.x; i < CIN * CIN; i += SH_THREADS)
+        w_conv[i] = make_float4(__ldg(conv_w + i * 3), __ldg(conv_w + i * 3 + 1), __ldg(conv_w + i * 3 + 2), 0.0f);
+    for (int i = threadIdx.x; i < CIN * A2; i += SH_THREADS) {
+        const int co = i / A2, j = i - co * A2;
+        w_pred[i] = __ldg(pred_w + j * CIN + co);
+    }
+    if (threadIdx.x < CIN) b_conv[threadIdx.x] = conv_b ? __ldg(conv_b + threadIdx.x) : 0.0f;
+    if (threadIdx.x < A2) b_pred[threadIdx.x] = pred_b ? __ldg(pred_b + threadIdx.x) : 0.0f;
+    __syncthreads();
+
+    const int64_t p = blockIdx.y;
+    const int l = blockIdx.x * SH_THREADS + threadIdx.x;
+    if (l >= n_loc) return;
+    const float ac = __fmul_rn((float)l, stride);
+    const int t = min((int)floorf(ac), t_len - 1);
+    const int64_t src = rows ? rows[p] - (rows[p] >= 0 ? row_base : 0) : p;
+    float acc[A2];
+    if (src < 0) {                                          // padding row: regressions are 0
+#pragma unroll
+        for (int j = 0; j < A2; ++j) acc[j] = 0.0f;
+    } else {
+        const float* xr = x + src * row_stride + t;
+        const bool has_m = t > 0, has_p = t + 1 < t_len;
+        float xv[CIN][3];
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+            const float* xc = xr + (int64_t)ci * ld_t;
+            xv[ci][0] = has_m ? __ldg(xc - 1) : 0.0f;
+            xv[ci][1] = __ldg(xc);
+            xv[ci][2] = has_p ? __ldg(xc + 1) : 0.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < A2; ++j) acc[j] = b_pred[j];
+#pragma unroll 2
+        for (int co = 0; co < CIN; ++co) {
+            float h = b_conv[co];
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci) {
+                const float4 w = w_conv[co * CIN + ci];
+                // taps outside [0, T) are skipped, not multiplied by zero (same chain as the oracle)
+                if (has_m) h = __fmaf_rn(w.x, xv[ci][0], h);
+                h = __fmaf_rn(w.y, xv[ci][1], h);
+                if (has_p) h = __fmaf_rn(w.z, xv[ci][2], h);
+            }
+            h = fmaxf(h, 0.0f);
+#pragma unroll
+            for (int j = 0; j < A2; ++j) acc[j] = __fmaf_rn(w_pred[co * A2 + j], h, acc[j]);
+        }
+    }
+    int32_t res[A2];
+#pragma unroll
+    for (int a = 0; a < A; ++a) decode_anchor(acc[2 * a], acc[2 * a + 1], __ldg(sizes + a), ac, t_len, &res[2 * a],
+                                              &res[2 * a + 1]);
+    int32_t* o = spans + (p * n_loc + l) * A2;               // [k][n_loc * A][2]
+    if (A2 % 4 == 0) {
+#pragma unroll
+        for (int q = 0; q < A2 / 4; ++q)
+            reinterpret_cast<int4*>(o)[q] = make_int4(res[4 * q], res[4 * q + 1], res[4 * q + 2], res[4 * q + 3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < A2; ++j) o[j] = res[j];
+    }
+}
+
+// any Cin / A (2A <= SH_MAX_A2): same chain, inputs re-read from L1/L2 per hidden unit
+__global__ void __launch_bounds__(SH_THREADS)
+span_proposals_generic_kernel(const float* __restrict__ x, const int64_t* __restrict__ rows, int64_t row_base,
+                              int64_t row_stride, int64_t ld_t, int cin, int t_len,
+                              const float* __restrict__ conv_w, const float* __restrict__ conv_b,
+                              const float* __restrict__ pred_w, const float* __restrict__ pred_b, int a_n,
+                              const float* __restrict__ sizes, float stride, int n_loc, int32_t* __restrict__ spans) {
+    const int64_t p = blockIdx.y;
+    const int l = blockIdx.x * SH_THREADS + threadIdx.x;
+    if (l >= n_loc) return;
+    const int a2 = 2 * a_n;
+    const float ac = __fmul_rn((float)l, stride);
+    const int t = min((int)floorf(ac), t_len - 1);
+    const int64_t src = rows ? rows[p] - (rows[p] >= 0 ? row_base : 0) : p;
+    float acc[SH_MAX_A2];
+#pragma unroll
+    for (int j = 0; j < SH_MAX_A2; ++j) acc[j] = 0.0f;
+    if (src >= 0) {
+#pragma unroll
+        for (int j = 0; j < SH_MAX_A2; ++j) acc[j] = (j < a2 && pred_b) ? __ldg(pred_b + j) : 0.0f;
+        const float* xr = x + src * row_stride + t;
+        const bool has_m = t > 0, has_p = t + 1 < t_len;
+        for (int co = 0; co < cin; ++co) {
+            float h = conv_b ? __ldg(conv_b + co) : 0.0f;
+            const float* w = conv_w + (int64_t)co * cin * 3;
+            for (int ci = 0; ci < cin; ++ci) {
+                const float* xc = xr + (int64_t)ci * ld_t;
+                if (has_m) h = __fmaf_rn(__ldg(w + ci * 3 + 0), __ldg(xc - 1), h);
+                h = __fmaf_rn(__ldg(w + ci * 3 + 1), __ldg(xc), h);
+                if (has_p) h = __fmaf_rn(__ldg(w + ci * 3 + 2), __ldg(xc + 1), h);
+            }
+            h = fmaxf(h, 0.0f);
+#pragma unroll
+            for (int j = 0; j < SH_MAX_A2; ++j)
+                if (j < a2) acc[j] = __fmaf_rn(__ldg(pred_w + (int64_t)j * cin + co), h, acc[j]);
+        }
+    }
+    int32_t* o = spans + (p * n_loc + l) * a2;
+#pragma unroll
+    for (int a = 0; a < SH_MAX_A2 / 2; ++a) {
+        if (a < a_n) {
+            int32_t lo, hi;
+            decode_anchor(acc[2 * a], acc[2 * a + 1], __ldg(sizes + a), ac, t_len, &lo, &hi);
+            o[2 * a] = lo;
+            o[2 * a + 1] = hi;
+        }
+    }
 }
 
 }  // namespace tspn
@@ -284,5 +421,33 @@ int tspn_span_decode(const float* d_reg, int64_t k, int n_anchors, int t, const 
     TSPN_CUDA_OK(cudaGetLastError());
     return TSPN_OK;
 }
+
+int tspn_span_proposals(const float* d_x, const int64_t* d_rows, int64_t row_base, int64_t row_stride, int64_t ld_t,
+                        int64_t k, int cin, int t, const float* d_conv_w, const float* d_conv_b,
+                        const float* d_pred_w, const float* d_pred_b, int n_anchors, const float* d_sizes,
+                        float stride, int32_t* d_spans, void* stream) {
+    TSPN_ARCH_OK();
+    TSPN_REQUIRE(k >= 0 && cin > 0 && t > 0 && n_anchors > 0 && ld_t >= t && row_stride >= 0 && stride > 0.0f,
+                 TSPN_EBADARG, "tspn_span_proposals: bad size");
+    TSPN_REQUIRE(2 * n_anchors <= SH_MAX_A2, TSPN_ESHAPE, "tspn_span_proposals: 2A=%d exceeds the supported maximum %d",
+                 2 * n_anchors, SH_MAX_A2);
+    if (k == 0) return TSPN_OK;
+    TSPN_REQUIRE(d_x && d_conv_w && d_pred_w && d_sizes && d_spans, TSPN_EBADARG, "tspn_span_proposals: null pointer");
+    TSPN_REQUIRE(k < 65536, TSPN_ESHAPE, "tspn_span_proposals: k=%lld must be < 65536 per call", (long long)k);
+    const int n_loc = tspn_span_num_locations(t, stride);
+    dim3 grid((unsigned)((n_loc + SH_THREADS - 1) / SH_THREADS), (unsigned)k);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cin == 8 && n_anchors == 4 && aligned16(d_spans))
+        span_proposals_small_kernel<8, 4><<<grid, SH_THREADS, 0, st>>>(d_x, d_rows, row_base, row_stride, ld_t, t,
+                                                                      d_conv_w, d_conv_b, d_pred_w, d_pred_b, d_sizes,
+                                                                      stride, n_loc, d_spans);
+    else
+        span_proposals_generic_kernel<<<grid, SH_THREADS, 0, st>>>(d_x, d_rows, row_base, row_stride, ld_t, cin, t,
+                                                                   d_conv_w, d_conv_b, d_pred_w, d_pred_b, n_anchors,
+                                                                   d_sizes, stride, n_loc, d_spans);
+    TSPN_CUDA_OK(cudaGetLastError());
+    return TSPN_OK;
+}
+
 
 }  // extern "C"

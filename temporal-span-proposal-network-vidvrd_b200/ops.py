@@ -73,14 +73,14 @@ def pair_geometry(batch: DeviceBatch, write_geo: bool = True, clipped: bool = Fa
         out["viou"] = torch.empty(p, dtype=torch.float32, device=dev)
         out["tiou"] = torch.empty(p, dtype=torch.float32, device=dev)
         out["overlap"] = torch.empty((p, 2), dtype=torch.int32, device=dev)
-        ws_bytes = load().tspn_pair_geo_workspace_bytes(batch.total_tracklets)
+        ws_bytes = load().tspn_pair_geo_workspace_bytes(batch.total_tracklets, batch.total_pairs)
         out["workspace"] = torch.empty(ws_bytes // 8, dtype=torch.float64, device=dev)
     check(load().tspn_pair_geo_viou(
-        ptr(batch.table), batch.num_videos, int(tot[_lib.TOT_ITEMS]), batch.total_tracklets,
+        ptr(batch.table), batch.num_videos, int(tot[_lib.TOT_ITEMS]), batch.total_tracklets, batch.total_pairs,
         int(tot[_lib.TOT_BOXES]), ptr(batch.boxes), ptr(batch.span), ptr(out.get("geo")), ptr(out["viou"]),
         ptr(out["tiou"]), ptr(out["overlap"]), _lib.VIOU_CLIPPED if clipped else _lib.VIOU_FULL,
         ptr(out["workspace"]), stream_ptr()), "tspn_pair_geo_viou")
-    _count(1 if clipped else 2)
+    _count(3)       # volumes + accumulator zeroing, pair kernel, per-pair finalize
     return out
 
 
@@ -254,6 +254,35 @@ def span_head(x: torch.Tensor, conv_w: torch.Tensor, conv_b: torch.Tensor, pred_
                                 ptr(_cuda(pred_w.reshape(a2, cin), torch.float32)),
                                 ptr(_cuda(pred_b, torch.float32)), a2, ptr(out), prec, ptr(ws), stream_ptr()),
           "tspn_span_head")
+    _count(1)
+    return out
+
+
+def span_proposals(x: torch.Tensor, conv_w: torch.Tensor, conv_b: torch.Tensor, pred_w: torch.Tensor,
+                   pred_b: torch.Tensor, sizes: torch.Tensor, stride: float, rows: Optional[torch.Tensor] = None,
+                   t: Optional[int] = None, row_base: int = 0) -> torch.Tensor:
+    """DPNHead (dpn.py:69-73) + anchors + decode ([SPEC] s5) in one kernel: int32 frame bounds
+    ``[K, L*A, 2]``.  The head is evaluated only at the ``L`` anchor columns the decode reads, so the
+    ``[K, 2A, T]`` regression tensor is never materialised; bit-identical to
+    ``span_decode(span_head(x, ..., precision="fp32"), sizes, stride)``."""
+    x = _cuda(x, torch.float32)
+    if x.dim() != 3:
+        raise ValueError("span_proposals expects [K, Cin, T]")
+    cin, ld_t = x.shape[1], x.shape[2]
+    t = ld_t if t is None else int(t)
+    k = x.shape[0] if rows is None else int(rows.shape[0])
+    a2 = pred_w.shape[0]
+    n_loc = span_num_locations(t, stride)
+    out = torch.empty((k, n_loc * (a2 // 2), 2), dtype=torch.int32, device=x.device)
+    if x.numel() == 0:        # a video without pairs: every requested row is padding (regressions 0)
+        x = torch.zeros((1, cin, ld_t), dtype=torch.float32, device=x.device)
+        rows = torch.full((k,), -1, dtype=torch.int64, device=x.device)
+    check(load().tspn_span_proposals(ptr(x), ptr(rows), int(row_base), cin * ld_t, ld_t, k, cin, t,
+                                     ptr(_cuda(conv_w, torch.float32)), ptr(_cuda(conv_b, torch.float32)),
+                                     ptr(_cuda(pred_w.reshape(a2, cin), torch.float32)),
+                                     ptr(_cuda(pred_b, torch.float32)), a2 // 2,
+                                     ptr(_cuda(sizes, torch.float32)), float(stride), ptr(out), stream_ptr()),
+          "tspn_span_proposals")
     _count(1)
     return out
 

@@ -37,6 +37,7 @@ class StageConfig:
     topk_per_video: int = 200          # predict.py:76 (TOPK_PER_SEG)
     records: bool = True               # build the triplet records (row N1)
     mirror_q4: bool = False
+    keep_span_reg: bool = False        # also return DPNHead's raw [K, 2A, T] regressions (two-kernel path)
 
     @classmethod
     def from_cfg(cls, cfg) -> "StageConfig":
@@ -75,7 +76,7 @@ class StageResult:
     features: Optional[torch.Tensor]        # [rows, F] fp32 view
     features_bf16: Optional[torch.Tensor]
     rel_logits: Optional[torch.Tensor]      # [rows, R]
-    span_reg: Optional[List[torch.Tensor]]  # per video [K_v, 2A, T_v]
+    span_reg: Optional[List[torch.Tensor]]  # per video [K_v, 2A, T_v] (StageConfig.keep_span_reg only)
     spans: Optional[List[torch.Tensor]]     # per video [K_v, L*A, 2] int32
     k_eff: List[int]
     sparsify: bool
@@ -261,23 +262,30 @@ class PairStage:
             p_cnt = sum(batch.n[v] * max(batch.n[v] - 1, 0) for v in vids)
             x = geo[g0:g0 + p_cnt * _lib.GEO_CHANNELS * tp].view(p_cnt, _lib.GEO_CHANNELS, tp)
             rsel = row[vids[0]:vids[-1] + 1].reshape(-1) if row is not None else None
-            reg = ops.span_head(x, cw, cb, pw, pb, rows=rsel, t=t, row_base=p0,
-                                precision=c.precision if cw.shape[1] >= 64 else "fp32")
-            sp = ops.span_decode(reg, self.sizes_dev, c.anchor_stride)
+            if c.keep_span_reg:
+                reg = ops.span_head(x, cw, cb, pw, pb, rows=rsel, t=t, row_base=p0,
+                                    precision=c.precision if cw.shape[1] >= 64 else "fp32")
+                sp = ops.span_decode(reg, self.sizes_dev, c.anchor_stride)
+            else:       # fused: the head only at the anchor columns, regressions stay in registers
+                reg = None
+                sp = ops.span_proposals(x, cw, cb, pw, pb, self.sizes_dev, c.anchor_stride, rows=rsel, t=t,
+                                        row_base=p0)
             bufs.append(sp)
             if row is not None:
                 k = row.shape[1]
                 for j, v in enumerate(vids):
-                    regs.append(reg[j * k:j * k + k_eff[v]])
+                    if reg is not None:
+                        regs.append(reg[j * k:j * k + k_eff[v]])
                     spans.append(sp[j * k:j * k + k_eff[v]])
             else:
                 off = 0
                 for v in vids:
                     pv = batch.n[v] * max(batch.n[v] - 1, 0)
-                    regs.append(reg[off:off + pv])
+                    if reg is not None:
+                        regs.append(reg[off:off + pv])
                     spans.append(sp[off:off + pv])
                     off += pv
-        return regs, spans, bufs
+        return (regs if c.keep_span_reg else None), spans, bufs
 
 
 class GraphedStage:

@@ -72,8 +72,9 @@ class DPN(nn.Module):
         sizes = torch.tensor(self.anchor_sizes, dtype=torch.float32, device=dev)
         out = []
         for v in range(batch.num_videos):
-            reg = ops.span_head(batch.geo_rows(geom["geo"], v), cw, cb, pw, pb, t=batch.t[v], precision="fp32")
-            out.append(like_input(ops.span_decode(reg, sizes, self.anchor_stride), ref.is_cuda))
+            sp = ops.span_proposals(batch.geo_rows(geom["geo"], v), cw, cb, pw, pb, sizes, self.anchor_stride,
+                                    t=batch.t[v])
+            out.append(like_input(sp, ref.is_cuda))
         return out, {}
 
 

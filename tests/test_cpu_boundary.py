@@ -33,7 +33,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert re.search(r"\bT %s\b" % name, exported), name
         getattr(lib, name)
-    assert lib.tspn_version() == 1
+    assert lib.tspn_version() == 2
 
 
 def test_sass_is_blackwell_native():
@@ -46,11 +46,11 @@ def test_sass_is_blackwell_native():
 
 
 def test_video_table_layout():
-    n, t = [20, 1, 0, 5, 2], [300, 10, 7, 37, 1]
+    n, t = [20, 1, 0, 5, 2, 40], [300, 10, 7, 37, 1, 1200]
     table, tot = _lib.build_video_table(n, t)
-    assert table.shape == (5, _lib.VT_COLS)
+    assert table.shape == (6, _lib.VT_COLS)
     trk = pairs = geo = boxes = scores = items = 0
-    for v in range(5):
+    for v in range(6):
         row = table[v]
         tp, tb = (t[v] + 3) // 4 * 4, (t[v] + 7) // 8 * 8
         assert list(row[:4]) == [n[v], t[v], tp, tb]
@@ -58,8 +58,9 @@ def test_video_table_layout():
         assert row[_lib.VT_BOX_OFF] == boxes and row[_lib.VT_SCORE_OFF] == scores and row[_lib.VT_ITEM_OFF] == items
         p = n[v] * max(n[v] - 1, 0)
         trk, pairs, geo, boxes, scores = trk + n[v], pairs + p, geo + p * 8 * tp, boxes + n[v] * tb, scores + n[v] ** 2
-        items += n[v] * ((n[v] - 1 + 7) // 8) if n[v] >= 2 else 0
-    assert list(tot[:6]) == [trk, pairs, geo, items, boxes, scores] and tot[6] == 20 and tot[7] == 300
+        groups, chunks = -(-(n[v] - 1) // _lib.GEO_OBJ_GROUP), -(-t[v] // _lib.GEO_CHUNK)
+        items += n[v] * groups * chunks if n[v] >= 2 else 0
+    assert list(tot[:6]) == [trk, pairs, geo, items, boxes, scores] and tot[6] == 40 and tot[7] == 1200
     assert boxes % 8 == 0
     with pytest.raises(RuntimeError, match="TSPN_ESHAPE"):
         _lib.build_video_table([3], [0])

@@ -252,6 +252,42 @@ def test_span_head_exact(golden, cin, k, t):
     np.testing.assert_array_equal(sub[2], got[0])
 
 
+@pytest.mark.parametrize("cin,a,k,t,stride", [(8, 4, 6, 300, 7.5), (8, 4, 3, 1, 7.5), (8, 4, 5, 2000, 16.0),
+                                              (8, 4, 2, 37, 1.0), (5, 4, 2, 60, 7.5), (8, 3, 2, 131, 4.0),
+                                              (20, 2, 2, 131, 7.5)])
+def test_span_proposals_fused_bit_exact(cin, a, k, t, stride):
+    """tspn_span_proposals == tspn_span_head(fp32) -> tspn_span_decode == the C oracle, bit for bit."""
+    sd = synth.make_weights(35, 132, 16, dpn_in=cin, n_anchors=a, seed=3)
+    rng = np.random.Generator(np.random.PCG64(cin * 1000 + t))
+    x = rng.normal(0, 1, size=(k, cin, t)).astype(np.float32)
+    p = "relpn.duration_proposal_network.dpn_head."
+    sd[p + "conv.weight"] = (sd[p + "conv.weight"] * 30).astype(np.float32)       # regressions of O(1)
+    sd[p + "duration_pred.weight"] = (sd[p + "duration_pred.weight"] * 30).astype(np.float32)
+    sd[p + "conv.bias"] = rng.normal(0, 0.1, size=cin).astype(np.float32)
+    sd[p + "duration_pred.bias"] = rng.normal(0, 0.5, size=2 * a).astype(np.float32)
+    args = [torch.from_numpy(sd[p + n]).cuda() for n in ("conv.weight", "conv.bias", "duration_pred.weight",
+                                                         "duration_pred.bias")]
+    sizes = tuple(float(4 ** (i + 1)) for i in range(a))
+    sz = torch.tensor(sizes, dtype=torch.float32).cuda()
+    xd = torch.from_numpy(x).cuda()
+    got = ops.span_proposals(xd, *args, sz, stride).cpu().numpy()
+    two = ops.span_decode(ops.span_head(xd, *args), sz, stride).cpu().numpy()
+    np.testing.assert_array_equal(got, two)
+    np.testing.assert_array_equal(got, exact.span_decode(exact.span_head(x, sd), sizes, stride))
+    if t > 1:
+        assert len(np.unique(got[..., 1] - got[..., 0])) > 1                      # not a degenerate case
+    # gathered rows of a row-padded buffer, including a padding row and a row base
+    tp = (t + 3) // 4 * 4
+    buf = torch.zeros((k, cin, tp), device="cuda")
+    buf[:, :, :t] = xd
+    rows = torch.tensor([k - 1 + 100, -1, 100], dtype=torch.int64, device="cuda")
+    sub = ops.span_proposals(buf, *args, sz, stride, rows=rows, t=t, row_base=100).cpu().numpy()
+    np.testing.assert_array_equal(sub[0], got[k - 1])
+    np.testing.assert_array_equal(sub[2], got[0])
+    zero = exact.span_decode(np.zeros((1, 2 * a, t), np.float32), sizes, stride)[0]
+    np.testing.assert_array_equal(sub[1], zero)
+
+
 @pytest.mark.parametrize("t,stride,sizes", [(60, 7.5, (15, 30, 45, 60)), (300, 7.5, (15, 30, 45, 60)),
                                             (37, 1.0, (4, 8, 16, 32)), (1, 7.5, (15, 30, 45, 60)),
                                             (2000, 16.0, (16, 64, 256, 1024))])
