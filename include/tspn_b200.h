@@ -66,7 +66,7 @@ extern "C" {
 #define TSPN_VT_SCORE_OFF 9 /* first relationness score (sum of N*N) */
 
 /* totals[] written by tspn_build_video_table */
-#define TSPN_TOT_COLS 8
+#define TSPN_TOT_COLS 10
 #define TSPN_TOT_TRACKLETS 0
 #define TSPN_TOT_PAIRS 1
 #define TSPN_TOT_GEO_FLOATS 2
@@ -75,6 +75,12 @@ extern "C" {
 #define TSPN_TOT_SCORES 5
 #define TSPN_TOT_MAX_N 6
 #define TSPN_TOT_MAX_T 7
+#define TSPN_TOT_GEO_CHUNK 8 /* frames per work item of the pair-geometry kernel: tspn_geo_chunk(max T) */
+
+/* Work items of the pair-geometry kernel: (video, subject, group of TSPN_GEO_OBJ_GROUP other
+ * tracklets, chunk of tspn_geo_chunk(max T of the batch) frames), numbered chunk-fastest; the table's
+ * TSPN_VT_ITEM_OFF column and totals[TSPN_TOT_ITEMS] count them. */
+#define TSPN_GEO_OBJ_GROUP 64
 
 /* geometry channels of geo[P][8][Tp] ([SPEC] s2) */
 #define TSPN_GEO_CHANNELS 8
@@ -105,6 +111,9 @@ int tspn_check_device(void);
  * Pure host arithmetic on sizes; no device access. */
 int tspn_build_video_table(int num_videos, const int32_t* n_tracklets, const int32_t* n_frames,
                            int64_t* table_host, int64_t* totals);
+/* 512, 1024 or 2048: the smallest chunk that covers max_t (2048 beyond); one CTA of chunk/4 threads
+ * writes whole geometry rows where it can - HBM absorbs few wide store streams best */
+int tspn_geo_chunk(int64_t max_t);
 
 /* ---- a1: pair enumeration -------------------------------------------------------------
  * Replaces the h5 `pairs` table (lib/dataset/vrdataset.py:208; order of predict.py:133-140).
@@ -119,7 +128,7 @@ int tspn_enumerate_pairs(const int64_t* d_table, int num_videos, int64_t total_p
  * d_geo may be NULL (reductions only).  d_workspace: tspn_pair_geo_workspace_bytes() bytes
  * (per-tracklet volumes + per-pair fixed-point volume sums), 16-byte aligned. */
 int64_t tspn_pair_geo_workspace_bytes(int64_t total_tracklets, int64_t total_pairs);
-int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_items,
+int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_items, int geo_chunk,
                        int64_t total_tracklets, int64_t total_pairs, int64_t total_boxes,
                        const float* d_boxes, const int32_t* d_span,
                        float* d_geo, float* d_viou, float* d_tiou, int32_t* d_overlap,

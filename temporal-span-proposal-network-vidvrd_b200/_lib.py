@@ -17,12 +17,11 @@ ERROR_NAMES = {-1: "TSPN_EBADARG", -2: "TSPN_ESHAPE", -3: "TSPN_EALIGN", -4: "TS
 
 VT_COLS = 12
 VT_N, VT_T, VT_TP, VT_TB, VT_TRK_OFF, VT_PAIR_OFF, VT_GEO_OFF, VT_ITEM_OFF, VT_BOX_OFF, VT_SCORE_OFF = range(10)
-TOT_COLS = 8
-TOT_TRACKLETS, TOT_PAIRS, TOT_GEO_FLOATS, TOT_ITEMS, TOT_BOXES, TOT_SCORES, TOT_MAX_N, TOT_MAX_T = range(8)
+TOT_COLS = 10
+TOT_TRACKLETS, TOT_PAIRS, TOT_GEO_FLOATS, TOT_ITEMS, TOT_BOXES, TOT_SCORES, TOT_MAX_N, TOT_MAX_T, TOT_GEO_CHUNK = range(9)
 
 ABI_VERSION = 2
-GEO_OBJ_GROUP = 16        # csrc/common.cuh: objects per work item of the pair-geometry kernel
-GEO_CHUNK = 512           # ... and frames per work item
+GEO_OBJ_GROUP = 64        # include/tspn_b200.h: objects per work item of the pair-geometry kernel
 GEO_CHANNELS = 8
 MOTION_DIM = 4000
 REL_DIM = 3000
@@ -41,7 +40,8 @@ SIGNATURES = {
     "tspn_build_video_table": (c_int, [c_int, POINTER(c_int32), POINTER(c_int32), POINTER(c_int64), POINTER(c_int64)]),
     "tspn_enumerate_pairs": (c_int, [P, c_int, c_int64, P, P]),
     "tspn_pair_geo_workspace_bytes": (c_int64, [c_int64, c_int64]),
-    "tspn_pair_geo_viou": (c_int, [P, c_int, c_int64, c_int64, c_int64, c_int64, P, P, P, P, P, P, c_int, P, P]),
+    "tspn_geo_chunk": (c_int, [c_int64]),
+    "tspn_pair_geo_viou": (c_int, [P, c_int, c_int64, c_int, c_int64, c_int64, c_int64, P, P, P, P, P, P, c_int, P, P]),
     "tspn_cubic_iou": (c_int, [P, c_int, P, c_int, c_int, P, P]),
     "tspn_viou_pairs": (c_int, [P, P, P, P, P, c_int64, c_int, P, P]),
     "tspn_normalize_motion": (c_int, [P, c_int64, P, P]),

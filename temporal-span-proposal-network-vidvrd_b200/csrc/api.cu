@@ -110,11 +110,16 @@ int tspn_last_error(char* buf, int len) {
 
 int tspn_check_device(void) { return tspn::check_arch(); }
 
+int tspn_geo_chunk(int64_t max_t) { return max_t <= 512 ? 512 : (max_t <= 1024 ? 1024 : 2048); }
+
 int tspn_build_video_table(int num_videos, const int32_t* n_tracklets, const int32_t* n_frames,
                            int64_t* table_host, int64_t* totals) {
     TSPN_REQUIRE(num_videos >= 0 && (num_videos == 0 || (n_tracklets && n_frames)) && table_host && totals,
                  TSPN_EBADARG, "tspn_build_video_table: null argument");
     int64_t trk = 0, pairs = 0, geo = 0, items = 0, boxes = 0, scores = 0, max_n = 0, max_t = 0;
+    for (int v = 0; v < num_videos; ++v)
+        if (n_frames[v] > max_t) max_t = n_frames[v];
+    const int64_t chunk = tspn_geo_chunk(max_t);
     for (int v = 0; v < num_videos; ++v) {
         const int64_t n = n_tracklets[v], t = n_frames[v];
         TSPN_REQUIRE(n >= 0 && t >= 1, TSPN_ESHAPE, "video %d: need N >= 0 and T >= 1 (got N=%lld T=%lld)", v,
@@ -136,12 +141,10 @@ int tspn_build_video_table(int num_videos, const int32_t* n_tracklets, const int
         trk += n;
         pairs += p;
         geo += p * TSPN_GEO_CHANNELS * tp;
-        items += n >= 2 ? n * ((n - 1 + TSPN_GEO_OBJ_GROUP - 1) / TSPN_GEO_OBJ_GROUP) *
-                              ((t + TSPN_GEO_CHUNK - 1) / TSPN_GEO_CHUNK) : 0;
+        items += n >= 2 ? n * ((n - 1 + TSPN_GEO_OBJ_GROUP - 1) / TSPN_GEO_OBJ_GROUP) * ((t + chunk - 1) / chunk) : 0;
         boxes += n * tb;
         scores += n * n;
         if (n > max_n) max_n = n;
-        if (t > max_t) max_t = t;
     }
     totals[TSPN_TOT_TRACKLETS] = trk;
     totals[TSPN_TOT_PAIRS] = pairs;
@@ -151,6 +154,7 @@ int tspn_build_video_table(int num_videos, const int32_t* n_tracklets, const int
     totals[TSPN_TOT_SCORES] = scores;
     totals[TSPN_TOT_MAX_N] = max_n;
     totals[TSPN_TOT_MAX_T] = max_t;
+    totals[TSPN_TOT_GEO_CHUNK] = chunk;
     return TSPN_OK;
 }
 

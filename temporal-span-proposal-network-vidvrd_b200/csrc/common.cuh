@@ -8,17 +8,6 @@
 
 #include "../../include/tspn_b200.h"
 
-// Work item of the pair-geometry kernel: (video, subject s, group of TSPN_GEO_OBJ_GROUP
-// consecutive "other" tracklets k, chunk of TSPN_GEO_CHUNK frames); object o = k + [k >= s],
-// pair row = s*(N-1) + k.  Items are numbered chunk-fastest, so that blocks adjacent in the grid
-// write adjacent segments of the same geometry rows (see geo_viou.cu).
-#ifndef TSPN_GEO_OBJ_GROUP
-#define TSPN_GEO_OBJ_GROUP 16
-#endif
-#ifndef TSPN_GEO_CHUNK
-#define TSPN_GEO_CHUNK 512
-#endif
-
 namespace tspn {
 
 // ---- error plumbing -------------------------------------------------------------------

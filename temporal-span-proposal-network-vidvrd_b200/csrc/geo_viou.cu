@@ -25,23 +25,36 @@
 
 namespace tspn {
 
-constexpr int GEO_FPT = 4;
-constexpr int GEO_CHUNK = TSPN_GEO_CHUNK;             // frames per work item
-constexpr int GEO_THREADS = GEO_CHUNK / GEO_FPT;
-constexpr int GEO_ROWS = GEO_CHUNK / 8 + 1;           // rows of 8 boxes + 1 halo row
-constexpr int GEO_TX_BYTES = GEO_ROWS * 128;          // bytes per TMA box
-constexpr int GEO_STAGE_BYTES = GEO_TX_BYTES;         // stages are packed (128-byte aligned)
+constexpr int GEO_FPT = 4;                            // frames per thread
 constexpr int GEO_OG = TSPN_GEO_OBJ_GROUP;
-constexpr int GEO_WARPS = GEO_THREADS / 32;
-constexpr int GEO_STAGES = 1 + 2;                     // subject chunk + object ring
-// HBM absorbs this kernel's store stream best with few concurrent writers per SM
-// (tools/bench_store_pattern.cu: 7.3 TB/s at 6 CTAs x 128 threads, 6.8 TB/s unconstrained): the
-// shared-memory request pins the occupancy at GEO_MIN_CTAS.
-constexpr int GEO_MIN_CTAS = 768 / GEO_THREADS;
-constexpr int GEO_SMEM_BYTES = (GEO_STAGES * GEO_STAGE_BYTES + 1024) > (227 * 1024 / (GEO_MIN_CTAS + 1) + 1024)
-                                   ? (GEO_STAGES * GEO_STAGE_BYTES + 1024)
-                                   : (227 * 1024 / (GEO_MIN_CTAS + 1) + 1024);
-static_assert(GEO_CHUNK % 256 == 0 && GEO_THREADS <= 256, "chunk must be a multiple of 256 frames, at most 1024");
+#ifndef TSPN_GEO_RING
+#define TSPN_GEO_RING 3
+#endif
+constexpr int GEO_RING = TSPN_GEO_RING;               // object-chunk stages in flight
+constexpr int GEO_STAGES = 1 + GEO_RING;              // subject chunk + object ring
+
+// Shape of one CTA: THREADS threads cover a chunk of 4*THREADS frames (512 / 1024 / 2048, chosen per
+// batch by tspn_geo_chunk).  HBM absorbs this kernel's store stream best as few, wide streams
+// (tools/bench_store_pattern.cu: 5.8 TB/s with 2 KB row segments from 24 warps per SM, 7.0-7.4 TB/s
+// with whole 8 KB rows from 16 warps), so a CTA writes row segments as long as the video allows and
+// the shared-memory request pins the occupancy at about 512 threads per SM.
+template <int THREADS>
+struct GeoCfg {
+    static constexpr int CHUNK = THREADS * GEO_FPT;
+    static constexpr int WARPS = THREADS / 32;
+    static constexpr int ROWS = CHUNK / 8 + 1;                    // rows of 8 boxes + 1 halo row
+    static constexpr int SPLIT = ROWS > 256 ? 2 : 1;              // a TMA box has at most 256 rows
+    static constexpr int BOX_ROWS = SPLIT == 1 ? ROWS : CHUNK / 16 + 1;   // the second box re-reads one row
+    static constexpr int TX_BYTES = SPLIT * BOX_ROWS * 128;       // bytes landing per staged chunk
+    static constexpr int STAGE_BYTES = ROWS * 128;                // stages are packed (128-byte aligned)
+    static constexpr int MIN_CTAS = THREADS >= 512 ? 1 : (THREADS == 256 ? 2 : 3);
+    // barriers, per-(object, warp) sums, per-object overlap windows
+    static constexpr int TAIL_BYTES = (2 * GEO_RING * 8 + GEO_OG * (WARPS * 3 * 8 + 8) + 127) / 128 * 128;
+    static constexpr int SMEM_USED = GEO_STAGES * STAGE_BYTES + TAIL_BYTES;
+    static constexpr int SMEM_PIN = 227 * 1024 / (MIN_CTAS + 1) + 1024;
+    static constexpr int SMEM_BYTES = SMEM_USED > SMEM_PIN ? SMEM_USED : SMEM_PIN;
+    static_assert(SMEM_BYTES * MIN_CTAS <= 227 * 1024, "the stages of MIN_CTAS CTAs must fit one SM");
+};
 
 // box j of a chunk staged with SWIZZLE_128B: the 16-byte slot index (address bits 4..6) is XORed
 // with address bits 7..9 of the shared-memory address, so the pattern is a function of the
@@ -131,17 +144,20 @@ __device__ __forceinline__ unsigned long long warp_sum_fx(float v) {
     return (unsigned long long)lo + ((unsigned long long)hi << 24);
 }
 
-template <bool WRITE_GEO, bool CLIP>
-__global__ void __launch_bounds__(GEO_THREADS, GEO_MIN_CTAS)
+template <int THREADS, bool WRITE_GEO, bool CLIP>
+__global__ void __launch_bounds__(THREADS, GeoCfg<THREADS>::MIN_CTAS)
 pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __restrict__ table, int nv,
                 const int32_t* __restrict__ span, float* __restrict__ geo, unsigned long long* __restrict__ fx) {
+    using Cfg = GeoCfg<THREADS>;
+    constexpr int GEO_CHUNK = Cfg::CHUNK, GEO_WARPS = Cfg::WARPS, GEO_STAGE_BYTES = Cfg::STAGE_BYTES;
+    constexpr int GEO_TX_BYTES = Cfg::TX_BYTES, GEO_SPLIT = Cfg::SPLIT;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* const s_stage = smem;
     uint8_t* const o_stage0 = smem + GEO_STAGE_BYTES;
-    uint64_t* const full = reinterpret_cast<uint64_t*>(smem + GEO_STAGES * GEO_STAGE_BYTES);  // [2]
-    uint64_t* const empty = full + 2;                                                         // [2]
-    unsigned long long* const acc = reinterpret_cast<unsigned long long*>(empty + 2);         // [OG][3]
-    int2* const ospan = reinterpret_cast<int2*>(acc + GEO_OG * 3);                            // [OG]
+    uint64_t* const full = reinterpret_cast<uint64_t*>(smem + GEO_STAGES * GEO_STAGE_BYTES);  // [RING]
+    uint64_t* const empty = full + GEO_RING;                                                  // [RING]
+    unsigned long long* const acc = reinterpret_cast<unsigned long long*>(empty + GEO_RING);  // [OG][WARPS][3]
+    int2* const owin = reinterpret_cast<int2*>(acc + GEO_OG * GEO_WARPS * 3);                 // [OG] overlap windows
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -165,37 +181,42 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
     const int nobj = min(GEO_OG, n - 1 - k0);
     const int64_t box_row0 = row[TSPN_VT_BOX_OFF];           // multiple of 8
     const int64_t pair0 = row[TSPN_VT_PAIR_OFF] + (int64_t)s * (n - 1) + k0;
-    const int ps = __ldg(span + 2 * (trk_off + s)), pe = __ldg(span + 2 * (trk_off + s) + 1);
 
     if (tid == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
-        mbar_init(&empty[0], GEO_WARPS);
-        mbar_init(&empty[1], GEO_WARPS);
+#pragma unroll
+        for (int i = 0; i < GEO_RING; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], GEO_WARPS);
+        }
         fence_mbar_init();
     }
-    if (tid < GEO_OG * 3) acc[tid] = 0ull;
-    if (tid < nobj) {
+    const int warp = tid >> 5;
+    if (tid < nobj) {       // the loop below touches no global or local memory besides its stores
+        const int ps = __ldg(span + 2 * (trk_off + s)), pe = __ldg(span + 2 * (trk_off + s) + 1);
         const int k = k0 + tid;
         const int o = k + (k >= s ? 1 : 0);
-        ospan[tid] = make_int2(__ldg(span + 2 * (trk_off + o)), __ldg(span + 2 * (trk_off + o) + 1));
+        const int qs = __ldg(span + 2 * (trk_off + o)), qe = __ldg(span + 2 * (trk_off + o) + 1);
+        owin[tid] = make_int2(max(ps, qs), min(pe, qe));
     }
     __syncthreads();
 
     auto issue = [&](int q) {          // thread 0: object q (and, with the first, the subject chunk)
         const int k = k0 + q;
         const int o = k + (k >= s ? 1 : 0);
-        const int st = q & 1;
+        const int st = q % GEO_RING;
         mbar_expect_tx(&full[st], q == 0 ? 2 * GEO_TX_BYTES : GEO_TX_BYTES);
-        if (q == 0)
-            tma_load_2d(s_stage, &box_map, 0, (int)((box_row0 + (int64_t)s * tb + (int64_t)c * GEO_CHUNK) >> 3),
-                        &full[st]);
-        tma_load_2d(o_stage0 + st * GEO_STAGE_BYTES, &box_map, 0,
-                    (int)((box_row0 + (int64_t)o * tb + (int64_t)c * GEO_CHUNK) >> 3), &full[st]);
+#pragma unroll
+        for (int h = 0; h < GEO_SPLIT; ++h) {                 // second half: rows CHUNK/16 .. CHUNK/8 (+ halo)
+            const int r_off = h * (GEO_CHUNK / 16);
+            if (q == 0)
+                tma_load_2d(s_stage + r_off * 128, &box_map, 0,
+                            (int)((box_row0 + (int64_t)s * tb + (int64_t)c * GEO_CHUNK) >> 3) + r_off, &full[st]);
+            tma_load_2d(o_stage0 + st * GEO_STAGE_BYTES + r_off * 128, &box_map, 0,
+                        (int)((box_row0 + (int64_t)o * tb + (int64_t)c * GEO_CHUNK) >> 3) + r_off, &full[st]);
+        }
     };
     if (tid == 0) {
-        issue(0);
-        if (nobj > 1) issue(1);
+        for (int q = 0; q < GEO_RING && q < nobj; ++q) issue(q);
     }
 
     const int t0 = c * GEO_CHUNK + tid * GEO_FPT;            // first frame of this thread
@@ -203,11 +224,12 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
     const uint32_t ss = smem_u32(s_stage);
     float* g = WRITE_GEO ? geo + row[TSPN_VT_GEO_OFF] + ((int64_t)(s * (n - 1) + k0) * TSPN_GEO_CHANNELS) * tp + t0
                          : nullptr;
+    int st = 0, ph = 0;                                      // ring stage of step q and its phase parity
     for (int q = 0; q < nobj; ++q) {
-        const int2 os = ospan[q];
-        const int a = max(ps, os.x), b = min(pe, os.y);      // overlap window [a, b)
+        const int2 win = owin[q];
+        const int a = win.x, b = win.y;                      // overlap window [a, b)
 
-        mbar_wait(&full[q & 1], (q >> 1) & 1);
+        mbar_wait(&full[st], ph);
 
         // per-thread partial sums stay in fp32: 4 integer-valued products <= 4 * 2^21 < 2^24 are exact
         float fsum_i = 0.0f, fsum_s = 0.0f, fsum_o = 0.0f;
@@ -218,7 +240,7 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
             for (int i = 0; i < GEO_FPT; ++i) out[ch][i] = 0.0f;
 
         if (t0 < b && t0 + GEO_FPT > a) {
-            const uint32_t os_addr = smem_u32(o_stage0 + (q & 1) * GEO_STAGE_BYTES);
+            const uint32_t os_addr = smem_u32(o_stage0 + st * GEO_STAGE_BYTES);
             float dcx[GEO_FPT + 1], dcy[GEO_FPT + 1], wo[GEO_FPT + 1], ho[GEO_FPT + 1];
             float rwo[GEO_FPT + 1], rho[GEO_FPT + 1];
 #pragma unroll
@@ -275,9 +297,9 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
             }
         }
         // this warp is done reading the object stage of step q: hand it back; thread 0 refills it with
-        // object q+2 (end of the step) once every warp has done so
+        // object q+RING (end of the step) once every warp has done so
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[q & 1]);
+        if (lane == 0) mbar_arrive(&empty[st]);
 
         if (WRITE_GEO && t0 < tp) {
 #pragma unroll
@@ -292,23 +314,25 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
             tot_s = warp_sum_fx(fsum_s);
             tot_o = warp_sum_fx(fsum_o);
         }
-        if (lane == 0) {
-            if (tot_i) atomicAdd(&acc[q * 3 + 0], tot_i);
-            if (CLIP) {
-                if (tot_s) atomicAdd(&acc[q * 3 + 1], tot_s);
-                if (tot_o) atomicAdd(&acc[q * 3 + 2], tot_o);
-            }
+        if (lane == 0) {          // every (object, warp) slot is written exactly once: no atomics, no zeroing
+            unsigned long long* slot = acc + (q * GEO_WARPS + warp) * 3;
+            slot[0] = tot_i;
+            slot[1] = tot_s;
+            slot[2] = tot_o;
         }
-        if (tid == 0 && q + 2 < nobj) {                      // by now the other warps have normally arrived
-            mbar_wait(&empty[q & 1], (q >> 1) & 1);
-            issue(q + 2);
+        if (tid == 0 && q + GEO_RING < nobj) {               // by now the other warps have normally arrived
+            mbar_wait(&empty[st], ph);
+            issue(q + GEO_RING);
         }
+        if (++st == GEO_RING) { st = 0; ph ^= 1; }
     }
     __syncthreads();
     // this chunk's contribution to the pair's sums
-    if (tid < nobj * 3) {
-        const int q = tid / 3, w = tid - 3 * q;
-        const unsigned long long val = acc[tid];
+    for (int i3 = tid; i3 < nobj * 3; i3 += THREADS) {
+        const int q = i3 / 3, w = i3 - 3 * q;
+        unsigned long long val = 0ull;
+#pragma unroll
+        for (int i = 0; i < GEO_WARPS; ++i) val += acc[(q * GEO_WARPS + i) * 3 + w];
         if (val) atomicAdd(fx + (pair0 + q) * 3 + w, val);
     }
 }
@@ -431,6 +455,36 @@ __global__ void __launch_bounds__(256) enumerate_pairs_kernel(const int64_t* __r
     pairs[2 * p + 1] = k + (k >= s ? 1 : 0);
 }
 
+template <int THREADS>
+static int launch_pair_geo(const int64_t* d_table, int num_videos, int64_t total_items, int64_t total_boxes,
+                           const float* d_boxes, const int32_t* d_span, float* d_geo, unsigned long long* fx,
+                           bool clip, cudaStream_t st) {
+    using Cfg = GeoCfg<THREADS>;
+    // boxes viewed as a 2-D tensor: rows of 8 boxes (32 floats = 128 B)
+    CUtensorMap map;
+    const uint64_t dims[2] = {32, (uint64_t)(total_boxes / 8)};
+    const uint64_t strides[1] = {128};
+    const uint32_t box[2] = {32, (uint32_t)Cfg::BOX_ROWS};
+    int rc = encode_tensor_map(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d_boxes, dims, strides, box,
+                               CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != TSPN_OK) return rc;
+#define TSPN_LAUNCH_GEO(W, C)                                                                                  \
+    do {                                                                                                       \
+        TSPN_CUDA_OK(cudaFuncSetAttribute(pair_geo_kernel<THREADS, W, C>,                                      \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));      \
+        pair_geo_kernel<THREADS, W, C><<<(unsigned)total_items, THREADS, Cfg::SMEM_BYTES, st>>>(               \
+            map, d_table, num_videos, d_span, d_geo, fx);                                                      \
+    } while (0)
+    if (d_geo) {
+        if (clip) TSPN_LAUNCH_GEO(true, true); else TSPN_LAUNCH_GEO(true, false);
+    } else {
+        if (clip) TSPN_LAUNCH_GEO(false, true); else TSPN_LAUNCH_GEO(false, false);
+    }
+#undef TSPN_LAUNCH_GEO
+    TSPN_CUDA_OK(cudaGetLastError());
+    return TSPN_OK;
+}
+
 }  // namespace tspn
 
 using namespace tspn;
@@ -458,8 +512,8 @@ int64_t tspn_pair_geo_workspace_bytes(int64_t total_tracklets, int64_t total_pai
     return geo_ws_vol_bytes(total_tracklets) + (total_pairs > 0 ? total_pairs : 1) * 3 * (int64_t)sizeof(uint64_t);
 }
 
-int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_items, int64_t total_tracklets,
-                       int64_t total_pairs, int64_t total_boxes, const float* d_boxes, const int32_t* d_span,
+int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_items, int geo_chunk,
+                       int64_t total_tracklets, int64_t total_pairs, int64_t total_boxes, const float* d_boxes, const int32_t* d_span,
                        float* d_geo, float* d_viou, float* d_tiou, int32_t* d_overlap, int flags, void* d_workspace,
                        void* stream) {
     TSPN_ARCH_OK();
@@ -474,6 +528,8 @@ int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_ite
                  "tspn_pair_geo_viou: total_boxes (%lld) must be a multiple of 8 (rows padded to Tb)",
                  (long long)total_boxes);
     TSPN_REQUIRE(total_items < (1ll << 31), TSPN_ESHAPE, "tspn_pair_geo_viou: too many work items");
+    TSPN_REQUIRE(geo_chunk == 512 || geo_chunk == 1024 || geo_chunk == 2048, TSPN_EBADARG,
+                 "tspn_pair_geo_viou: geo_chunk=%d (pass totals[TSPN_TOT_GEO_CHUNK] of tspn_build_video_table)", geo_chunk);
     cudaStream_t st = (cudaStream_t)stream;
     double* vol = reinterpret_cast<double*>(d_workspace);
     unsigned long long* fx =
@@ -491,29 +547,11 @@ int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_ite
                                                                 !clip, fx, total_pairs * 3);
         TSPN_CUDA_OK(cudaGetLastError());
     }
-    // boxes viewed as a 2-D tensor: rows of 8 boxes (32 floats = 128 B)
-    CUtensorMap map;
-    const uint64_t dims[2] = {32, (uint64_t)(total_boxes / 8)};
-    const uint64_t strides[1] = {128};
-    const uint32_t box[2] = {32, (uint32_t)GEO_ROWS};
-    int rc = encode_tensor_map(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d_boxes, dims, strides, box,
-                               CU_TENSOR_MAP_SWIZZLE_128B);
+    int rc = TSPN_OK;
+    if (geo_chunk == 512) rc = launch_pair_geo<128>(d_table, num_videos, total_items, total_boxes, d_boxes, d_span, d_geo, fx, clip, st);
+    else if (geo_chunk == 1024) rc = launch_pair_geo<256>(d_table, num_videos, total_items, total_boxes, d_boxes, d_span, d_geo, fx, clip, st);
+    else rc = launch_pair_geo<512>(d_table, num_videos, total_items, total_boxes, d_boxes, d_span, d_geo, fx, clip, st);
     if (rc != TSPN_OK) return rc;
-
-#define TSPN_LAUNCH_GEO(W, C)                                                                              \
-    do {                                                                                                   \
-        TSPN_CUDA_OK(cudaFuncSetAttribute(pair_geo_kernel<W, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                          GEO_SMEM_BYTES));                                                \
-        pair_geo_kernel<W, C><<<(unsigned)total_items, GEO_THREADS, GEO_SMEM_BYTES, st>>>(                 \
-            map, d_table, num_videos, d_span, d_geo, fx);                                                  \
-    } while (0)
-    if (d_geo) {
-        if (clip) TSPN_LAUNCH_GEO(true, true); else TSPN_LAUNCH_GEO(true, false);
-    } else {
-        if (clip) TSPN_LAUNCH_GEO(false, true); else TSPN_LAUNCH_GEO(false, false);
-    }
-#undef TSPN_LAUNCH_GEO
-    TSPN_CUDA_OK(cudaGetLastError());
     const unsigned fblocks = (unsigned)((total_pairs + 255) / 256);
     if (clip)
         pair_finalize_kernel<true><<<fblocks, 256, 0, st>>>(d_table, num_videos, total_pairs, d_span, vol, fx, d_viou,

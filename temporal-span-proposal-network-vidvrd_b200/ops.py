@@ -76,7 +76,8 @@ def pair_geometry(batch: DeviceBatch, write_geo: bool = True, clipped: bool = Fa
         ws_bytes = load().tspn_pair_geo_workspace_bytes(batch.total_tracklets, batch.total_pairs)
         out["workspace"] = torch.empty(ws_bytes // 8, dtype=torch.float64, device=dev)
     check(load().tspn_pair_geo_viou(
-        ptr(batch.table), batch.num_videos, int(tot[_lib.TOT_ITEMS]), batch.total_tracklets, batch.total_pairs,
+        ptr(batch.table), batch.num_videos, int(tot[_lib.TOT_ITEMS]), int(tot[_lib.TOT_GEO_CHUNK]),
+        batch.total_tracklets, batch.total_pairs,
         int(tot[_lib.TOT_BOXES]), ptr(batch.boxes), ptr(batch.span), ptr(out.get("geo")), ptr(out["viou"]),
         ptr(out["tiou"]), ptr(out["overlap"]), _lib.VIOU_CLIPPED if clipped else _lib.VIOU_FULL,
         ptr(out["workspace"]), stream_ptr()), "tspn_pair_geo_viou")

@@ -54,6 +54,35 @@ def test_pair_geometry_ragged_batch(clip):
         np.testing.assert_allclose(tiou[sl], w_tiou, rtol=1e-6, atol=0)
 
 
+@pytest.mark.parametrize("shapes,chunk", [
+    ([(20, 300, 0), (5, 37, 11), (9, 512, 8), (2, 1, 3)], 512),          # one 128-thread CTA per row segment
+    ([(7, 513, 7), (4, 1024, 9), (3, 700, 1)], 1024),                    # 256 threads
+    ([(3, 4100, 2), (70, 40, 3), (4, 2049, 4), (5, 2048, 5)], 2048),     # 512 threads; several chunks per row;
+])                                                                       # N-1 > 64: two object groups
+@pytest.mark.parametrize("clip", [False, True])
+def test_pair_geometry_kernel_shapes(shapes, chunk, clip):
+    """Every CTA shape tspn_geo_chunk selects, rows spanning several chunks (forward differences and
+    volume sums across chunk boundaries), more objects than one work item holds."""
+    vids = [synth.make_video(n, t, 35, seed=s) for n, t, s in shapes]
+    batch = _batch(vids)
+    assert int(batch.totals[_lib.TOT_GEO_CHUNK]) == chunk
+    out = ops.pair_geometry(batch, write_geo=True, clipped=clip)
+    red = ops.pair_geometry(batch, write_geo=False, clipped=clip)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(out["viou"].cpu().numpy(), red["viou"].cpu().numpy())
+    viou, tiou, ov = out["viou"].cpu().numpy(), out["tiou"].cpu().numpy(), out["overlap"].cpu().numpy()
+    for i, v in enumerate(vids):
+        sl = batch.pair_slice(i)
+        geo, w_viou, w_tiou, w_ov = _geo_oracle(v, clip)
+        got = batch.geo_rows(out["geo"], i).cpu().numpy()
+        t = v.n_frames
+        np.testing.assert_array_equal(got[:, :, t:], 0)
+        np.testing.assert_allclose(got[:, :, :t], geo, rtol=RTOL, atol=1e-12, err_msg="video %d" % i)
+        np.testing.assert_array_equal(ov[sl], w_ov)
+        np.testing.assert_allclose(viou[sl], w_viou, rtol=RTOL, atol=0)
+        np.testing.assert_allclose(tiou[sl], w_tiou, rtol=1e-6, atol=0)
+
+
 def test_pair_geometry_reductions_only_and_fractional_boxes():
     v = synth.make_video(11, 700, 35, seed=21, integer_boxes=False)
     batch = _batch([v])
