@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define TSPN_ABI_VERSION 2
+#define TSPN_ABI_VERSION 3
 
 /* error codes */
 #define TSPN_OK 0
@@ -145,6 +145,17 @@ int tspn_cubic_iou(const float* d_b1, int n1, const float* d_b2, int n2, int t,
 int tspn_viou_pairs(const float* d_pool, const int64_t* d_traj_off, const int32_t* d_traj_span,
                     const int32_t* d_a, const int32_t* d_b, int64_t n_pairs, int flags,
                     float* d_out, void* stream);
+
+/* ---- N3: the same for evaluation (lib/evaluation/visual_relation_detection.py:8-36 calls viou for
+ * every (prediction, ground truth) pair of equal triplet): per-trajectory volumes are summed once
+ * (d_workspace: tspn_viou_pairs_workspace_bytes(n_traj) bytes), each pair then reads only its overlap
+ * window; sums and the ratio stay in fp64, so for integer boxes d_out[i] is bit-identical to python's
+ * float(v_overlap) / (v1 + v2 - v_overlap) and the host-side threshold decisions cannot flip.
+ * TSPN_VIOU_CLIPPED gives association.py:35-48 (volumes over the overlap only) in fp64. */
+int64_t tspn_viou_pairs_workspace_bytes(int64_t n_traj);
+int tspn_viou_pairs_f64(const float* d_pool, const int64_t* d_traj_off, const int32_t* d_traj_span,
+                        int64_t n_traj, const int32_t* d_a, const int32_t* d_b, int64_t n_pairs,
+                        int flags, double* d_out, void* d_workspace, void* stream);
 
 /* ---- a2: feature rows -------------------------------------------------------------------
  * L1-normalise each 1000-wide BoW block (lib/dataset/vrdataset.py:227-236 with

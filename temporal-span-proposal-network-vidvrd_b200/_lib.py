@@ -20,7 +20,7 @@ VT_N, VT_T, VT_TP, VT_TB, VT_TRK_OFF, VT_PAIR_OFF, VT_GEO_OFF, VT_ITEM_OFF, VT_B
 TOT_COLS = 10
 TOT_TRACKLETS, TOT_PAIRS, TOT_GEO_FLOATS, TOT_ITEMS, TOT_BOXES, TOT_SCORES, TOT_MAX_N, TOT_MAX_T, TOT_GEO_CHUNK = range(9)
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 GEO_OBJ_GROUP = 64        # include/tspn_b200.h: objects per work item of the pair-geometry kernel
 GEO_CHANNELS = 8
 MOTION_DIM = 4000
@@ -44,6 +44,8 @@ SIGNATURES = {
     "tspn_pair_geo_viou": (c_int, [P, c_int, c_int64, c_int, c_int64, c_int64, c_int64, P, P, P, P, P, P, c_int, P, P]),
     "tspn_cubic_iou": (c_int, [P, c_int, P, c_int, c_int, P, P]),
     "tspn_viou_pairs": (c_int, [P, P, P, P, P, c_int64, c_int, P, P]),
+    "tspn_viou_pairs_workspace_bytes": (c_int64, [c_int64]),
+    "tspn_viou_pairs_f64": (c_int, [P, P, P, c_int64, P, P, c_int64, c_int, P, P, P]),
     "tspn_normalize_motion": (c_int, [P, c_int64, P, P]),
     "tspn_assemble_features": (c_int, [P, c_int, c_int64, P, c_int, P, P, P, P, c_int64, P, c_int64, P, c_int64, P]),
     "tspn_relationness_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),

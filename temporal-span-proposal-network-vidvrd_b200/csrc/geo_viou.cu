@@ -441,6 +441,70 @@ __global__ void __launch_bounds__(128) viou_pairs_kernel(const float4* __restric
     }
 }
 
+// ---- viou over an explicit pair list, evaluation form (N3): per-trajectory volumes once, then one
+// warp per pair over the overlap window only; sums and the ratio in fp64 so that the host-side
+// threshold / arg-max decisions of eval_detection_scores (visual_relation_detection.py:8-36) see
+// exactly python's float(v_overlap) / (v1 + v2 - v_overlap) for integer boxes ---------------------
+__global__ void __launch_bounds__(128) traj_volume_kernel(const float4* __restrict__ pool,
+                                                          const int64_t* __restrict__ traj_off,
+                                                          const int32_t* __restrict__ traj_span, int64_t n_traj,
+                                                          double* __restrict__ vol) {
+    const int64_t j = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (j >= n_traj) return;
+    const int lane = threadIdx.x & 31;
+    const float4* p = pool + traj_off[j];
+    const int len = traj_span[2 * j + 1] - traj_span[2 * j];
+    double acc = 0.0;
+    for (int f = lane; f < len; f += 32) {
+        const float4 x = __ldg(p + f);
+        acc += (double)((x.z - x.x) + 1.0f) * (double)((x.w - x.y) + 1.0f);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) vol[j] = acc;
+}
+
+template <bool CLIP>
+__global__ void __launch_bounds__(128) viou_pairs_f64_kernel(const float4* __restrict__ pool,
+                                                             const int64_t* __restrict__ traj_off,
+                                                             const int32_t* __restrict__ traj_span,
+                                                             const double* __restrict__ vol,
+                                                             const int32_t* __restrict__ ia,
+                                                             const int32_t* __restrict__ ib, int64_t n_pairs,
+                                                             double* __restrict__ out) {
+    const int64_t e = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (e >= n_pairs) return;
+    const int lane = threadIdx.x & 31;
+    const int i = ia[e], j = ib[e];
+    const int s1 = traj_span[2 * i], e1 = traj_span[2 * i + 1];
+    const int s2 = traj_span[2 * j], e2 = traj_span[2 * j + 1];
+    const float4* p = pool + traj_off[i] + (max(s1, s2) - s1);
+    const float4* q = pool + traj_off[j] + (max(s1, s2) - s2);
+    const int len = min(e1, e2) - max(s1, s2);
+    double si = 0.0, sa = 0.0, sb = 0.0;
+    for (int f = lane; f < len; f += 32) {
+        const float4 x = __ldg(p + f), y = __ldg(q + f);
+        const float iw = fmaxf((fminf(x.z, y.z) - fmaxf(x.x, y.x)) + 1.0f, 0.0f);
+        const float ih = fmaxf((fminf(x.w, y.w) - fmaxf(x.y, y.y)) + 1.0f, 0.0f);
+        si += (double)iw * (double)ih;
+        if (CLIP) {
+            sa += (double)((x.z - x.x) + 1.0f) * (double)((x.w - x.y) + 1.0f);
+            sb += (double)((y.z - y.x) + 1.0f) * (double)((y.w - y.y) + 1.0f);
+        }
+    }
+    si = warp_sum(si);
+    if (CLIP) {
+        sa = warp_sum(sa);
+        sb = warp_sum(sb);
+    } else {
+        sa = vol[i];
+        sb = vol[j];
+    }
+    if (lane == 0) {
+        const double den = sa + sb - si;
+        out[e] = (len > 0 && den > 0.0) ? si / den : 0.0;
+    }
+}
+
 // ---- pair enumeration ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) enumerate_pairs_kernel(const int64_t* __restrict__ table, int nv,
                                                               int64_t total_pairs, int64_t* __restrict__ pairs) {
@@ -591,6 +655,35 @@ int tspn_viou_pairs(const float* d_pool, const int64_t* d_traj_off, const int32_
     else
         viou_pairs_kernel<false><<<blocks, 128, 0, (cudaStream_t)stream>>>(
             reinterpret_cast<const float4*>(d_pool), d_traj_off, d_traj_span, d_a, d_b, n_pairs, d_out);
+    TSPN_CUDA_OK(cudaGetLastError());
+    return TSPN_OK;
+}
+
+int64_t tspn_viou_pairs_workspace_bytes(int64_t n_traj) {
+    return ((n_traj > 0 ? n_traj : 1) * (int64_t)sizeof(double) + 15) / 16 * 16;
+}
+
+int tspn_viou_pairs_f64(const float* d_pool, const int64_t* d_traj_off, const int32_t* d_traj_span, int64_t n_traj,
+                        const int32_t* d_a, const int32_t* d_b, int64_t n_pairs, int flags, double* d_out,
+                        void* d_workspace, void* stream) {
+    TSPN_ARCH_OK();
+    TSPN_REQUIRE(n_pairs >= 0 && n_traj >= 0, TSPN_EBADARG, "tspn_viou_pairs_f64: negative size");
+    if (n_pairs == 0) return TSPN_OK;
+    TSPN_REQUIRE(d_pool && d_traj_off && d_traj_span && d_a && d_b && d_out && d_workspace, TSPN_EBADARG,
+                 "tspn_viou_pairs_f64: null pointer");
+    TSPN_REQUIRE(aligned16(d_pool) && aligned16(d_workspace), TSPN_EALIGN,
+                 "tspn_viou_pairs_f64: pool/workspace must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* vol = reinterpret_cast<double*>(d_workspace);
+    const float4* pool = reinterpret_cast<const float4*>(d_pool);
+    const unsigned blocks = (unsigned)((n_pairs + 3) / 4);
+    if (flags & TSPN_VIOU_CLIPPED) {
+        viou_pairs_f64_kernel<true><<<blocks, 128, 0, st>>>(pool, d_traj_off, d_traj_span, vol, d_a, d_b, n_pairs, d_out);
+    } else {
+        traj_volume_kernel<<<(unsigned)((n_traj + 3) / 4), 128, 0, st>>>(pool, d_traj_off, d_traj_span, n_traj, vol);
+        TSPN_CUDA_OK(cudaGetLastError());
+        viou_pairs_f64_kernel<false><<<blocks, 128, 0, st>>>(pool, d_traj_off, d_traj_span, vol, d_a, d_b, n_pairs, d_out);
+    }
     TSPN_CUDA_OK(cudaGetLastError());
     return TSPN_OK;
 }

@@ -110,6 +110,23 @@ def viou_pairs(pool: torch.Tensor, traj_off: torch.Tensor, traj_span: torch.Tens
     return out
 
 
+def viou_pairs_f64(pool: torch.Tensor, traj_off: torch.Tensor, traj_span: torch.Tensor, a: torch.Tensor,
+                   b: torch.Tensor, clipped: bool = False) -> torch.Tensor:
+    """fp64 vIoU of explicit trajectory pairs with per-trajectory volumes summed once (the evaluation
+    loop of lib/evaluation/visual_relation_detection.py:8-36; association.py:35-48 when ``clipped``)."""
+    pool = _cuda(pool, torch.float32)
+    n_traj = int(traj_span.shape[0])
+    out = torch.empty(a.shape[0], dtype=torch.float64, device=pool.device)
+    ws = torch.empty(load().tspn_viou_pairs_workspace_bytes(n_traj), dtype=torch.uint8, device=pool.device)
+    check(load().tspn_viou_pairs_f64(ptr(pool), ptr(_cuda(traj_off, torch.int64)), ptr(_cuda(traj_span, torch.int32)),
+                                     n_traj, ptr(_cuda(a, torch.int32)), ptr(_cuda(b, torch.int32)), a.shape[0],
+                                     _lib.VIOU_CLIPPED if clipped else _lib.VIOU_FULL, ptr(out), ptr(ws),
+                                     stream_ptr()),
+          "tspn_viou_pairs_f64")
+    _count(1 if clipped else 2)
+    return out
+
+
 def normalize_motion(motion: torch.Tensor) -> torch.Tensor:
     motion = _cuda(motion, torch.float32)
     out = torch.empty_like(motion)

@@ -176,3 +176,147 @@ def make_weights(n_classes: int, n_predicates: int, feature_dim: int, hidden: in
 def feature_dim(n_classes: int) -> int:
     """2C classeme + 2x4000 motion BoW + 3000 relative block (vrdataset.py:219-243)."""
     return 2 * int(n_classes) + 2 * MOTION_DIM + REL_DIM
+
+
+# ---------------------------------------------------------------------------
+# Relation-level synthetic data for the rows after the pair stage (SURVEY.md 8f):
+# evaluation (N3) and greedy relational association (N2).
+# ---------------------------------------------------------------------------
+def _walk_boxes(rng, length: int, integer: bool = True) -> np.ndarray:
+    """[length, 4] inclusive-pixel boxes of one smooth random walk."""
+    cx = rng.uniform(300, FRAME_W - 300) + np.cumsum(rng.normal(0.0, 3.0, size=length))
+    cy = rng.uniform(200, FRAME_H - 200) + np.cumsum(rng.normal(0.0, 3.0, size=length))
+    w = np.clip(rng.integers(40, 300) + np.cumsum(rng.integers(-1, 2, size=length)), 16, 600)
+    h = np.clip(rng.integers(40, 300) + np.cumsum(rng.integers(-1, 2, size=length)), 16, 600)
+    x1 = np.clip(cx - 0.5 * w, 0, FRAME_W - 17)
+    y1 = np.clip(cy - 0.5 * h, 0, FRAME_H - 17)
+    b = np.stack([x1, y1, np.minimum(x1 + w - 1, FRAME_W - 1), np.minimum(y1 + h - 1, FRAME_H - 1)], axis=-1)
+    return np.rint(b) if integer else b
+
+
+def _jitter(rng, boxes: np.ndarray, amount: float, integer: bool = True) -> np.ndarray:
+    """A detector's view of a ground-truth trajectory: offset + per-frame noise proportional to size."""
+    w = boxes[:, 2] - boxes[:, 0] + 1
+    h = boxes[:, 3] - boxes[:, 1] + 1
+    off = rng.normal(0.0, amount, size=4)
+    noise = rng.normal(0.0, 0.25 * amount, size=boxes.shape)
+    scale = np.stack([w, h, w, h], axis=-1)
+    out = boxes + (off[None, :] + noise) * scale
+    out[:, 2] = np.maximum(out[:, 2], out[:, 0] + 4)
+    out[:, 3] = np.maximum(out[:, 3], out[:, 1] + 4)
+    return np.rint(out) if integer else out
+
+
+def _as_lists(boxes: np.ndarray, integer: bool):
+    return [[int(c) for c in r] for r in boxes] if integer else [[float(c) for c in r] for r in boxes]
+
+
+def make_relation_eval_case(seed: int = 0, n_videos: int = 6, max_gt: int = 12, max_pred: int = 60,
+                            max_frames: int = 240, n_objects: int = 5, n_predicates: int = 4,
+                            integer_boxes: bool = True):
+    """``(groundtruth, prediction)`` dicts in the JSON layout lib/evaluation/README.md describes and
+    ``evaluate`` (lib/evaluation/visual_relation_detection.py:64) consumes: per video a list of relations
+    ``{triplet, duration [fstart, fend), sub_traj, obj_traj}`` (+ ``score`` for predictions).  Predictions
+    are jittered / time-shifted copies of ground truth (so vIoU spreads around the 0.5 threshold),
+    wrong-triplet copies and unrelated walks; one video has no ground truth and one no predictions."""
+    rng = np.random.Generator(np.random.PCG64(seed + 15485863))
+    gt, pred = {}, {}
+    for v in range(n_videos):
+        vid = "video_%03d" % v
+        n_gt = 0 if v == n_videos - 1 else int(rng.integers(1, max_gt + 1))
+        gts = []
+        for _ in range(n_gt):
+            length = int(rng.integers(8, max_frames + 1))
+            fstart = int(rng.integers(0, max_frames))
+            sub, obj = _walk_boxes(rng, length, integer_boxes), _walk_boxes(rng, length, integer_boxes)
+            trip = ["obj%d" % rng.integers(n_objects), "pred%d" % rng.integers(n_predicates),
+                    "obj%d" % rng.integers(n_objects)]
+            gts.append({"triplet": trip, "duration": [fstart, fstart + length], "_sub": sub, "_obj": obj})
+        preds = []
+        n_pred = 0 if v == n_videos - 2 else int(rng.integers(1, max_pred + 1))
+        for _ in range(n_pred):
+            kind = rng.random()
+            if gts and kind < 0.75:
+                g = gts[int(rng.integers(len(gts)))]
+                f0, f1 = g["duration"]
+                glen = f1 - f0
+                cut0 = int(rng.integers(0, max(glen // 3, 1)))          # trim / extend in time
+                cut1 = int(rng.integers(0, max(glen // 3, 1)))
+                lo, hi = cut0, max(glen - cut1, cut0 + 1)
+                amount = float(rng.choice([0.01, 0.03, 0.06, 0.12]))
+                sub = _jitter(rng, g["_sub"][lo:hi], amount, integer_boxes)
+                obj = _jitter(rng, g["_obj"][lo:hi], amount, integer_boxes)
+                ext = int(rng.integers(0, 6))                            # a few frames past the ground truth
+                if ext:
+                    sub = np.concatenate([sub, np.repeat(sub[-1:], ext, axis=0)])
+                    obj = np.concatenate([obj, np.repeat(obj[-1:], ext, axis=0)])
+                trip = list(g["triplet"])
+                if kind > 0.65:
+                    trip[1] = "pred%d" % rng.integers(n_predicates)
+                dur = [f0 + lo, f0 + hi + ext]
+            else:
+                length = int(rng.integers(8, max_frames + 1))
+                fstart = int(rng.integers(0, max_frames))
+                sub, obj = _walk_boxes(rng, length, integer_boxes), _walk_boxes(rng, length, integer_boxes)
+                trip = ["obj%d" % rng.integers(n_objects), "pred%d" % rng.integers(n_predicates),
+                        "obj%d" % rng.integers(n_objects)]
+                dur = [fstart, fstart + length]
+            # a coarse score grid produces equal scores: the stable sort order matters
+            preds.append({"triplet": trip, "score": float(np.round(rng.random(), 2)), "duration": dur,
+                          "sub_traj": _as_lists(sub, integer_boxes), "obj_traj": _as_lists(obj, integer_boxes)})
+        gt[vid] = [{"triplet": g["triplet"], "duration": g["duration"],
+                    "sub_traj": _as_lists(g["_sub"], integer_boxes), "obj_traj": _as_lists(g["_obj"], integer_boxes)}
+                   for g in gts]
+        pred[vid] = preds
+    return gt, pred
+
+
+def make_association_case(seed: int = 0, n_segments: int = 8, n_objects: int = 5, n_classes: int = 35,
+                          n_predicates: int = 132, preds_per_segment: int = 40, seg_len: int = 30,
+                          seg_stride: int = 15, vid: str = "synthetic_video"):
+    """Input of ``greedy_relational_association`` (lib/modeling/association.py:117-175) for one video:
+
+    * ``short_term_relations``: list of ``((vid, fstart, fend), (pred_list, iou, trackid))`` with
+      ``pred_list[i] = (score array, triplet array[3], (s_tid, o_tid) array)`` as predict.py:110-117 builds;
+    * ``segment_trajs``: ``{(vid, fstart, fend): [trajectory kwargs]}`` - what
+      ``object_trajectory_proposal`` (lib/modeling/trajectory.py:161-180) would load from disk.
+
+    Objects persist over 30-frame segments with 15-frame overlap (lib/modeling/__init__.py:36-42); each
+    segment re-detects them with jitter, so the overlap-clipped vIoU of consecutive detections spreads
+    around the 0.5 merge threshold; tracklet order is shuffled per segment."""
+    rng = np.random.Generator(np.random.PCG64(seed + 32452843))
+    total = seg_stride * (n_segments - 1) + seg_len
+    walks = [_walk_boxes(rng, total, integer=False) for _ in range(n_objects)]
+    cats = rng.integers(0, n_classes, size=n_objects)
+    rel_pool = [(int(s), int(rng.integers(n_predicates)), int(o)) for s in range(n_objects) for o in range(n_objects)
+                if s != o]
+    rel_pool = [rel_pool[i] for i in rng.permutation(len(rel_pool))[:max(4, len(rel_pool) // 2)]]
+    short_term, segment_trajs = [], {}
+    for k in range(n_segments):
+        f0 = k * seg_stride
+        f1 = f0 + seg_len
+        order = rng.permutation(n_objects)
+        present = [int(o) for o in order if rng.random() < 0.9]
+        trajs = []
+        for o in present:
+            amount = float(rng.choice([0.0, 0.02, 0.05, 0.15]))
+            rois = _jitter(rng, walks[o][f0:f1], amount, integer=False) if amount else walks[o][f0:f1]
+            trajs.append(dict(pstart=f0, pend=f1, rois=[tuple(float(c) for c in r) for r in rois],
+                              score=float(rng.random()), category=int(cats[o]), classeme=[], vsig=None,
+                              gt_trackid=-1))
+        slot = {o: i for i, o in enumerate(present)}
+        plist = []
+        for _ in range(preds_per_segment):
+            s, p, o = rel_pool[int(rng.integers(len(rel_pool)))]
+            if s not in slot or o not in slot:
+                continue
+            if rng.random() < 0.15:
+                p = int(rng.integers(n_predicates))
+            plist.append((np.array(np.float32(np.round(rng.random(), 2))),
+                          np.array([int(cats[s]), p, int(cats[o])]), np.array([slot[s], slot[o]])))
+        n = len(trajs)
+        index = (vid, f0, f1)
+        short_term.append((index, (plist, np.eye(n, dtype=np.float32), np.full(n, -1))))
+        segment_trajs[index] = trajs
+    order = rng.permutation(len(short_term))          # the association sorts segments by fstart itself
+    return [short_term[i] for i in order], segment_trajs

@@ -28,6 +28,7 @@ class Trajectory:
         self.rois = deque(tuple(float(c) for c in roi) for roi in rois)
         self.score, self.category, self.classeme = score, category, classeme
         self.vsig, self.gt_trackid = vsig, gt_trackid
+        self._version = 0            # bumped by every in-place edit (association caches IoUs per version)
 
     def __lt__(self, other):
         return self.score < other.score
@@ -58,6 +59,7 @@ class Trajectory:
         else:
             self.rois.append(tuple(roi))
             self.pend += 1
+        self._version += 1
         return roi
 
     def serialize(self):
@@ -98,10 +100,12 @@ def traj_iou(trajs1: Sequence, trajs2: Sequence):
     return cubic_iou(b1, b2)
 
 
-def viou_batch(trajs, durations, pairs, clipped: bool = False) -> np.ndarray:
+def viou_batch(trajs, durations, pairs, clipped: bool = False, f64: bool = False) -> np.ndarray:
     """vIoU of many trajectory pairs in one launch (the O(#pred x #gt) loop of
     lib/evaluation/visual_relation_detection.py:8-36).  ``trajs[j]`` is a list/array of boxes on
-    ``durations[j] = (fstart, fend)``; ``pairs`` is ``[M, 2]`` indices into ``trajs``."""
+    ``durations[j] = (fstart, fend)``; ``pairs`` is ``[M, 2]`` indices into ``trajs``.  ``f64`` keeps the
+    sums and the ratio in fp64 (``tspn_viou_pairs_f64``: volumes once per trajectory) — for integer boxes
+    the values are then bit-identical to the reference's python arithmetic."""
     dev = _dev()
     lens = [len(t) for t in trajs]
     off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
@@ -114,9 +118,12 @@ def viou_batch(trajs, durations, pairs, clipped: bool = False) -> np.ndarray:
         if span[j, 1] - span[j, 0] != lens[j]:
             raise ValueError("trajectory %d: %d boxes for duration %s" % (j, lens[j], tuple(span[j])))
     pairs = np.asarray(pairs, dtype=np.int32).reshape(-1, 2)
-    out = ops.viou_pairs(torch.from_numpy(pool).to(dev), torch.from_numpy(off[:-1].copy()).to(dev),
-                         torch.from_numpy(span).to(dev), torch.from_numpy(pairs[:, 0].copy()).to(dev),
-                         torch.from_numpy(pairs[:, 1].copy()).to(dev), clipped=clipped)
+    if pairs.shape[0] == 0:
+        return np.zeros(0, dtype=np.float64 if f64 else np.float32)
+    fn = ops.viou_pairs_f64 if f64 else ops.viou_pairs
+    out = fn(torch.from_numpy(pool).to(dev), torch.from_numpy(off[:-1].copy()).to(dev),
+             torch.from_numpy(span).to(dev), torch.from_numpy(pairs[:, 0].copy()).to(dev),
+             torch.from_numpy(pairs[:, 1].copy()).to(dev), clipped=clipped)
     return out.cpu().numpy()
 
 
