@@ -45,7 +45,23 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="launch every kernel from the host instead of CUDA graphs")
     ap.add_argument("--depth", type=int, default=3, help="batches in flight in the end-to-end serving loop")
+    ap.add_argument("--compute-streams", type=int, default=1, choices=[1, 2],
+                    help="compute streams of the serving loop (2: the tail of step i overlaps the geometry of i+1)")
     return ap.parse_args()
+
+
+def measured_traffic(videos):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this
+    workload (profiles/r1_geo_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum); None when the
+    capture does not describe the requested batch."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_geo_traffic.json")) as f:
+            t = json.load(f)
+        if int(t["videos_per_launch"]) != int(videos):
+            return None
+        return float(t["dram_bytes_read"]) + float(t["dram_bytes_write"])
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def measured_peak():
@@ -261,7 +277,8 @@ def run_ours(args, rank, world, local_rank):
     # The serving loop below owns `depth` slots (device inputs + captured CUDA graphs + pinned result
     # buffers); the resident-input measurement replays slot 0's graphs on inputs already in HBM.
     group = dist.group.WORLD if world > 1 else None
-    pipe = PipelinedStage(stage, host, device=dev, depth=args.depth, graphs=not args.eager, group=group)
+    pipe = PipelinedStage(stage, host, device=dev, depth=args.depth, graphs=not args.eager, group=group,
+                          compute_streams=args.compute_streams)
     slot0 = pipe.slots[0]
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)    # > 126 MB L2
     torch.cuda.synchronize()
@@ -356,12 +373,12 @@ def run_ours(args, rank, world, local_rank):
                    "launch": "eager C-ABI calls" if args.eager else
                              "3 CUDA-graph launches per step (side: relationness+top-K+motion norm || geo; tail)",
                    "e2e_pipeline": "tspn_b200.serving.PipelinedStage, depth %d: one H2D copy of the pinned input "
-                                   "arena per step; H2D(i+1..) and D2H(i-1) overlap the kernels of step i"
-                                   % args.depth,
+                                   "arena per step; H2D(i+1..) and D2H(i-1) overlap the kernels of step i; %d compute "
+                                   "stream(s)" % (args.depth, args.compute_streams),
                    "multi_gpu_collective": "all_gather of [V,200,8] int32 triplet records per step (e2e loop)"},
         "roofline": {"bound": "hbm", "kernel": "pair_geo_kernel (+ tracklet_volume_kernel)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                     "traffic": measured_traffic(args.videos), "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                      "avg_launch_ms": geo_avg_ms, "share_of_step": geo_avg_ms / (float(np.mean(step_ms)))},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": host.h2d_bytes(),
                 "d2h_bytes_per_step": d2h},

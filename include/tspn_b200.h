@@ -93,6 +93,9 @@ extern "C" {
 #define TSPN_VIOU_FULL 0       /* volumes over each full span: evaluation/common.py:65-106 (V2);
                                   equals trajectory.py:127-141 (V1) when all spans are equal */
 #define TSPN_VIOU_CLIPPED 1    /* volumes over the overlap only: association.py:35-48 (V3) */
+#define TSPN_GEO_PERSISTENT_CTAS 2 /* tspn_pair_geo_viou: persistent CTAs with a producer warp instead of the
+                                  default one CTA per work item (same results bit for bit; measured slower,
+                                  kept for A/B timing - DESIGN.md section 4.1) */
 #define TSPN_TOPK_KEEP_DIAGONAL 0    /* reference behaviour, ppn.py:84-85 (quirk Q1) */
 #define TSPN_TOPK_EXCLUDE_DIAGONAL 1 /* survivors are real pairs (sparsify mode) */
 #define TSPN_PREC_FP32_EXACT 0 /* CUDA cores, fixed k-ascending fma order: bit-reproducible */
@@ -165,8 +168,9 @@ int tspn_normalize_motion(const float* d_motion, int64_t n_tracklets, float* d_o
  * 3000 columns are the adaptive-average-pooled geometry ([SPEC] s4).  d_rows: global pair rows
  * to build (int64, NULL = all total_pairs rows in order).  Output row stride ld_feat floats
  * (>= 2C+11000, multiple of 4).  d_feat_bf16 (optional, may be NULL): same rows in bf16 with
- * stride ld_bf16 (multiple of 8) for the tensor-core predicate head. */
-int tspn_assemble_features(const int64_t* d_table, int num_videos, int64_t total_pairs,
+ * stride ld_bf16 (multiple of 8) for the tensor-core predicate head.  max_frames =
+ * totals[TSPN_TOT_MAX_T] sizes the shared-memory staging of the pooled channels (0 = unknown). */
+int tspn_assemble_features(const int64_t* d_table, int num_videos, int64_t total_pairs, int max_frames,
                            const float* d_cls, int n_classes, const float* d_motion_norm,
                            const float* d_geo, const int32_t* d_overlap,
                            const int64_t* d_rows, int64_t n_rows,

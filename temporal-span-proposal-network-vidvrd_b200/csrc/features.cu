@@ -35,7 +35,14 @@ __global__ void __launch_bounds__(128) normalize_motion_kernel(const float* __re
 }
 
 constexpr int ASM_THREADS = 256;
-constexpr int ASM_TCAP = 4104;     // frames of one geometry channel staged in shared memory (4096 + alignment slack)
+constexpr int ASM_STAGED = 2;      // geometry channels staged per round: (0,1) position, (2,3) size, (5,6) motion
+// Shared memory of one CTA: the overlap windows of two pooled channels (cap floats each, cap = the
+// batch's longest row + alignment slack) followed by the 3000 pooled bins: 28 KB at T = 2000, i.e. eight
+// 256-thread CTAs per SM (measured: staging all six channels at once costs more in occupancy - 3 CTAs per
+// SM - than it saves in load rounds: 112 us against 88 us for the 4096 rows of the bench).  Rows longer
+// than ASM_TCAP_MAX frames are pooled straight from global memory.
+constexpr int ASM_TCAP_MAX = 16384;
+__host__ __device__ constexpr int asm_smem_bytes(int cap) { return (ASM_STAGED * cap + TSPN_REL_DIM) * 4; }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -76,9 +83,10 @@ __global__ void __launch_bounds__(ASM_THREADS)
 assemble_kernel(const int64_t* __restrict__ table, int nv, const float* __restrict__ cls, int n_classes,
                 const float* __restrict__ motion_norm, const float* __restrict__ geo,
                 const int32_t* __restrict__ overlap, const int64_t* __restrict__ rows, float* __restrict__ feat,
-                int64_t ld_feat, __nv_bfloat16* __restrict__ feat_bf16, int64_t ld_bf16) {
-    __shared__ __align__(16) float s_geo[2][ASM_TCAP];
-    __shared__ __align__(16) float s_rel[TSPN_REL_DIM];
+                int64_t ld_feat, __nv_bfloat16* __restrict__ feat_bf16, int64_t ld_bf16, int cap) {
+    extern __shared__ __align__(16) float s_dyn[];
+    float* const s_geo = s_dyn;                                 // [ASM_STAGED][cap]
+    float* const s_rel = s_dyn + (size_t)ASM_STAGED * cap;      // [TSPN_REL_DIM]
     const int64_t r = blockIdx.x;
     const int64_t gp = rows ? rows[r] : r;
     float* out = feat ? feat + r * ld_feat : nullptr;
@@ -110,18 +118,19 @@ assemble_kernel(const int64_t* __restrict__ table, int nv, const float* __restri
     const uint32_t len = b > a ? (uint32_t)(b - a) : 0u;
     const int a4 = a & ~3;
     const int staged_frames = b - a4;
-    const bool staged = len > 0 && staged_frames <= ASM_TCAP - 4 && ((reinterpret_cast<uintptr_t>(g) & 15) == 0);
+    const bool staged = len > 0 && staged_frames <= cap - 4 && ((reinterpret_cast<uintptr_t>(g) & 15) == 0);
 #pragma unroll 1
     for (int cp = 0; cp < 3; ++cp) {
         const int ch0 = cp < 2 ? 2 * cp : 5;       // channel pairs (0,1) position, (2,3) size, (5,6) motion
         if (staged) {
             if (cp) __syncthreads();               // the previous pair's readers are done
             const int nvec = (staged_frames + 3) >> 2;
-            for (int q = threadIdx.x; q < 2 * nvec; q += ASM_THREADS) {
-                const int c = q >= nvec ? 1 : 0;
-                const int qq = q - c * nvec;
-                const float4 val = __ldg(reinterpret_cast<const float4*>(g + (int64_t)(ch0 + c) * tp + a4) + qq);
-                *reinterpret_cast<float4*>(&s_geo[c][4 * qq]) = val;
+            const float4* g0 = reinterpret_cast<const float4*>(g + (int64_t)ch0 * tp + a4);
+            const float4* g1 = reinterpret_cast<const float4*>(g + (int64_t)(ch0 + 1) * tp + a4);
+            for (int q = threadIdx.x; q < nvec; q += ASM_THREADS) {
+                const float4 v0 = __ldg(g0 + q), v1 = __ldg(g1 + q);
+                *reinterpret_cast<float4*>(s_geo + 4 * q) = v0;
+                *reinterpret_cast<float4*>(s_geo + cap + 4 * q) = v1;
             }
             __syncthreads();
         }
@@ -135,7 +144,7 @@ assemble_kernel(const int64_t* __restrict__ table, int nv, const float* __restri
                 const float inv = 1.0f / (float)(en - st);
                 float sacc = 0.0f;
                 if (staged) {
-                    const float* sp = &s_geo[c][a - a4];
+                    const float* sp = s_geo + c * cap + (a - a4);
                     for (uint32_t f = st; f < en; ++f) sacc += sp[f];
                 } else {
                     const float* gc = g + (int64_t)(ch0 + c) * tp + a;
@@ -194,8 +203,8 @@ int tspn_normalize_motion(const float* d_motion, int64_t n_tracklets, float* d_o
     return TSPN_OK;
 }
 
-int tspn_assemble_features(const int64_t* d_table, int num_videos, int64_t total_pairs, const float* d_cls,
-                           int n_classes, const float* d_motion_norm, const float* d_geo,
+int tspn_assemble_features(const int64_t* d_table, int num_videos, int64_t total_pairs, int max_frames,
+                           const float* d_cls, int n_classes, const float* d_motion_norm, const float* d_geo,
                            const int32_t* d_overlap, const int64_t* d_rows, int64_t n_rows, float* d_feat,
                            int64_t ld_feat, void* d_feat_bf16, int64_t ld_bf16, void* stream) {
     TSPN_ARCH_OK();
@@ -215,15 +224,24 @@ int tspn_assemble_features(const int64_t* d_table, int num_videos, int64_t total
     TSPN_REQUIRE(aligned16(d_feat) && aligned16(d_feat_bf16), TSPN_EALIGN,
                  "tspn_assemble_features: outputs must be 16-byte aligned");
     TSPN_REQUIRE(n_rows < (1ll << 31), TSPN_ESHAPE, "tspn_assemble_features: too many rows");
+    TSPN_REQUIRE(max_frames >= 0, TSPN_EBADARG, "tspn_assemble_features: max_frames=%d", max_frames);
     cudaStream_t st = (cudaStream_t)stream;
-    if (d_feat_bf16)
-        assemble_kernel<true><<<(unsigned)n_rows, ASM_THREADS, 0, st>>>(
+    // staging capacity per pooled channel: the batch's longest row (max_frames = totals[TSPN_TOT_MAX_T];
+    // 0 = unknown -> 4096) + 8 floats of alignment slack; longer rows are pooled from global memory
+    int cap = ((max_frames > 0 ? max_frames : 4096) + 3) / 4 * 4 + 8;
+    if (cap > ASM_TCAP_MAX) cap = ASM_TCAP_MAX;
+    const int smem = asm_smem_bytes(cap);
+    if (d_feat_bf16) {
+        TSPN_CUDA_OK(cudaFuncSetAttribute(assemble_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        assemble_kernel<true><<<(unsigned)n_rows, ASM_THREADS, smem, st>>>(
             d_table, num_videos, d_cls, n_classes, d_motion_norm, d_geo, d_overlap, d_rows, d_feat, ld_feat,
-            reinterpret_cast<__nv_bfloat16*>(d_feat_bf16), ld_bf16);
-    else
-        assemble_kernel<false><<<(unsigned)n_rows, ASM_THREADS, 0, st>>>(
+            reinterpret_cast<__nv_bfloat16*>(d_feat_bf16), ld_bf16, cap);
+    } else {
+        TSPN_CUDA_OK(cudaFuncSetAttribute(assemble_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        assemble_kernel<false><<<(unsigned)n_rows, ASM_THREADS, smem, st>>>(
             d_table, num_videos, d_cls, n_classes, d_motion_norm, d_geo, d_overlap, d_rows, d_feat, ld_feat, nullptr,
-            0);
+            0, cap);
+    }
     TSPN_CUDA_OK(cudaGetLastError());
     return TSPN_OK;
 }

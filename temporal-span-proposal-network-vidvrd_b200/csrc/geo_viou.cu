@@ -97,31 +97,44 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// ---- pre-kernel: per-tracklet volume (sum over [pstart, pend) of w*h, fp64; one warp per tracklet)
-// and zeroing of the per-pair fixed-point accumulators --------------------------------------------
+// ---- pre-kernel: per-tracklet volume (sum over [pstart, pend) of w*h in fp64; one 128-thread CTA per
+// tracklet, four independent loads in flight per thread, fixed combination order) and zeroing of the
+// per-pair fixed-point accumulators (grid-stride) ---------------------------------------------------
 __global__ void __launch_bounds__(128) tracklet_volume_kernel(const int64_t* __restrict__ table, int nv,
                                                               int64_t total_tracklets,
                                                               const float4* __restrict__ boxes,
                                                               const int32_t* __restrict__ span,
                                                               double* __restrict__ vol, bool want_vol,
                                                               unsigned long long* __restrict__ fx, int64_t n_fx) {
+    __shared__ double part[4];
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_fx; i += (int64_t)gridDim.x * blockDim.x)
         fx[i] = 0ull;
-    const int64_t trk = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (!want_vol || trk >= total_tracklets) return;
-    const int lane = threadIdx.x & 31;
-    const int v = find_video(table, nv, TSPN_VT_TRK_OFF, trk);
-    const int64_t* row = table + (int64_t)v * TSPN_VT_COLS;
-    const int64_t n_local = trk - row[TSPN_VT_TRK_OFF];
-    const float4* b = boxes + row[TSPN_VT_BOX_OFF] + n_local * row[TSPN_VT_TB];
-    const int ps = span[2 * trk], pe = span[2 * trk + 1];
-    double acc = 0.0;
-    for (int t = ps + lane; t < pe; t += 32) {
-        const float4 q = __ldg(b + t);
-        acc += (double)(((q.z - q.x) + 1.0f) * ((q.w - q.y) + 1.0f));
+    if (!want_vol) return;
+    for (int64_t trk = blockIdx.x; trk < total_tracklets; trk += gridDim.x) {
+        const int v = find_video(table, nv, TSPN_VT_TRK_OFF, trk);
+        const int64_t* row = table + (int64_t)v * TSPN_VT_COLS;
+        const int64_t n_local = trk - row[TSPN_VT_TRK_OFF];
+        const float4* b = boxes + row[TSPN_VT_BOX_OFF] + n_local * row[TSPN_VT_TB];
+        const int ps = span[2 * trk], pe = span[2 * trk + 1];
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int t = ps + (int)threadIdx.x;
+        for (; t + 384 < pe; t += 512) {
+            const float4 q0 = __ldg(b + t), q1 = __ldg(b + t + 128), q2 = __ldg(b + t + 256), q3 = __ldg(b + t + 384);
+            a0 += (double)(((q0.z - q0.x) + 1.0f) * ((q0.w - q0.y) + 1.0f));
+            a1 += (double)(((q1.z - q1.x) + 1.0f) * ((q1.w - q1.y) + 1.0f));
+            a2 += (double)(((q2.z - q2.x) + 1.0f) * ((q2.w - q2.y) + 1.0f));
+            a3 += (double)(((q3.z - q3.x) + 1.0f) * ((q3.w - q3.y) + 1.0f));
+        }
+        for (; t < pe; t += 128) {
+            const float4 q = __ldg(b + t);
+            a0 += (double)(((q.z - q.x) + 1.0f) * ((q.w - q.y) + 1.0f));
+        }
+        const double w = warp_sum((a0 + a1) + (a2 + a3));
+        __syncthreads();                               // the previous tracklet's part[] has been read
+        if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = w;
+        __syncthreads();
+        if (threadIdx.x == 0) vol[trk] = (part[0] + part[1]) + (part[2] + part[3]);
     }
-    acc = warp_sum(acc);
-    if (lane == 0) vol[trk] = acc;
 }
 
 // ---- the pair kernel ----------------------------------------------------------------------------
@@ -142,6 +155,74 @@ __device__ __forceinline__ unsigned long long warp_sum_fx(float v) {
     const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)(fx & 0xffffffull));       // < 2^29
     const unsigned hi = __reduce_add_sync(0xffffffffu, (unsigned)(fx >> 24));               // < 2^27
     return (unsigned long long)lo + ((unsigned long long)hi << 24);
+}
+
+// ---- one (pair, 4 frames) step of a thread: the eight channels + the three fp32 partial sums ----------
+// per-thread partial sums stay in fp32: 4 integer-valued products <= 4 * 2^21 < 2^24 are exact
+template <bool CLIP>
+__device__ __forceinline__ void geo_step(uint32_t ss, uint32_t os_addr, int j0, int t0, int a, int b,
+                                         float (&out)[TSPN_GEO_CHANNELS][GEO_FPT], float& fsum_i, float& fsum_s,
+                                         float& fsum_o) {
+    fsum_i = 0.0f; fsum_s = 0.0f; fsum_o = 0.0f;
+#pragma unroll
+    for (int ch = 0; ch < TSPN_GEO_CHANNELS; ++ch)
+#pragma unroll
+        for (int i = 0; i < GEO_FPT; ++i) out[ch][i] = 0.0f;
+    if (!(t0 < b && t0 + GEO_FPT > a)) return;
+    float dcx[GEO_FPT + 1], dcy[GEO_FPT + 1], wo[GEO_FPT + 1], ho[GEO_FPT + 1];
+    float rwo[GEO_FPT + 1], rho[GEO_FPT + 1];
+#pragma unroll
+    for (int i = 0; i <= GEO_FPT; ++i) {
+        const float4 sb = ld_box(ss, j0 + i);
+        const float4 ob = ld_box(os_addr, j0 + i);
+        wo[i] = (ob.z - ob.x) + 1.0f;
+        ho[i] = (ob.w - ob.y) + 1.0f;
+        rwo[i] = rcp_fast(wo[i]);
+        rho[i] = rcp_fast(ho[i]);
+        // centre deltas from coordinate differences: exact for integer boxes and
+        // free of the cancellation that (x1+x2)/2 - (x1'+x2')/2 would carry
+        dcx[i] = 0.5f * ((sb.x - ob.x) + (sb.z - ob.z));
+        dcy[i] = 0.5f * ((sb.y - ob.y) + (sb.w - ob.w));
+        if (i < GEO_FPT) {
+            const int t = t0 + i;
+            const bool in = (t >= a) && (t < b);
+            const float ws = (sb.z - sb.x) + 1.0f, hs = (sb.w - sb.y) + 1.0f;
+            const float iw = fmaxf((fminf(sb.z, ob.z) - fmaxf(sb.x, ob.x)) + 1.0f, 0.0f);
+            const float ih = fmaxf((fminf(sb.w, ob.w) - fmaxf(sb.y, ob.y)) + 1.0f, 0.0f);
+            // explicit rounding points: the volume sums must not depend on whether the
+            // compiler contracts these products into the accumulation (template variants)
+            const float inter = __fmul_rn(iw, ih);
+            const float as = __fmul_rn(ws, hs), ao = __fmul_rn(wo[i], ho[i]);
+            if (in) {
+                out[0][i] = dcx[i] * rwo[i];
+                out[1][i] = dcy[i] * rho[i];
+                out[2][i] = log_ratio(ws, wo[i], rwo[i]);
+                out[3][i] = log_ratio(hs, ho[i], rho[i]);
+                out[4][i] = inter * rcp_fast((as + ao) - inter);
+                out[7][i] = 1.0f;
+                fsum_i = __fadd_rn(fsum_i, inter);
+                if (CLIP) {
+                    fsum_s = __fadd_rn(fsum_s, as);
+                    fsum_o = __fadd_rn(fsum_o, ao);
+                }
+            }
+        }
+    }
+    // forward differences in closed form:
+    //   c0[t+1]-c0[t] = (dcx[t+1]*wo[t] - dcx[t]*wo[t+1]) / (wo[t]*wo[t+1])
+    // (two-product compensation keeps the numerator exact to one rounding)
+#pragma unroll
+    for (int i = 0; i < GEO_FPT; ++i) {
+        const int t = t0 + i;
+        if (t >= a && t + 1 < b) {
+            float p = dcx[i] * wo[i + 1];
+            float e = fmaf(dcx[i], wo[i + 1], -p);
+            out[5][i] = (fmaf(dcx[i + 1], wo[i], -p) - e) * (rwo[i] * rwo[i + 1]);
+            p = dcy[i] * ho[i + 1];
+            e = fmaf(dcy[i], ho[i + 1], -p);
+            out[6][i] = (fmaf(dcy[i + 1], ho[i], -p) - e) * (rho[i] * rho[i + 1]);
+        }
+    }
 }
 
 template <int THREADS, bool WRITE_GEO, bool CLIP>
@@ -231,71 +312,9 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
 
         mbar_wait(&full[st], ph);
 
-        // per-thread partial sums stay in fp32: 4 integer-valued products <= 4 * 2^21 < 2^24 are exact
-        float fsum_i = 0.0f, fsum_s = 0.0f, fsum_o = 0.0f;
+        float fsum_i, fsum_s, fsum_o;
         float out[TSPN_GEO_CHANNELS][GEO_FPT];
-#pragma unroll
-        for (int ch = 0; ch < TSPN_GEO_CHANNELS; ++ch)
-#pragma unroll
-            for (int i = 0; i < GEO_FPT; ++i) out[ch][i] = 0.0f;
-
-        if (t0 < b && t0 + GEO_FPT > a) {
-            const uint32_t os_addr = smem_u32(o_stage0 + st * GEO_STAGE_BYTES);
-            float dcx[GEO_FPT + 1], dcy[GEO_FPT + 1], wo[GEO_FPT + 1], ho[GEO_FPT + 1];
-            float rwo[GEO_FPT + 1], rho[GEO_FPT + 1];
-#pragma unroll
-            for (int i = 0; i <= GEO_FPT; ++i) {
-                const float4 sb = ld_box(ss, j0 + i);
-                const float4 ob = ld_box(os_addr, j0 + i);
-                wo[i] = (ob.z - ob.x) + 1.0f;
-                ho[i] = (ob.w - ob.y) + 1.0f;
-                rwo[i] = rcp_fast(wo[i]);
-                rho[i] = rcp_fast(ho[i]);
-                // centre deltas from coordinate differences: exact for integer boxes and
-                // free of the cancellation that (x1+x2)/2 - (x1'+x2')/2 would carry
-                dcx[i] = 0.5f * ((sb.x - ob.x) + (sb.z - ob.z));
-                dcy[i] = 0.5f * ((sb.y - ob.y) + (sb.w - ob.w));
-                if (i < GEO_FPT) {
-                    const int t = t0 + i;
-                    const bool in = (t >= a) && (t < b);
-                    const float ws = (sb.z - sb.x) + 1.0f, hs = (sb.w - sb.y) + 1.0f;
-                    const float iw = fmaxf((fminf(sb.z, ob.z) - fmaxf(sb.x, ob.x)) + 1.0f, 0.0f);
-                    const float ih = fmaxf((fminf(sb.w, ob.w) - fmaxf(sb.y, ob.y)) + 1.0f, 0.0f);
-                    // explicit rounding points: the volume sums must not depend on whether the
-                    // compiler contracts these products into the accumulation (template variants)
-                    const float inter = __fmul_rn(iw, ih);
-                    const float as = __fmul_rn(ws, hs), ao = __fmul_rn(wo[i], ho[i]);
-                    if (in) {
-                        out[0][i] = dcx[i] * rwo[i];
-                        out[1][i] = dcy[i] * rho[i];
-                        out[2][i] = log_ratio(ws, wo[i], rwo[i]);
-                        out[3][i] = log_ratio(hs, ho[i], rho[i]);
-                        out[4][i] = inter * rcp_fast((as + ao) - inter);
-                        out[7][i] = 1.0f;
-                        fsum_i = __fadd_rn(fsum_i, inter);
-                        if (CLIP) {
-                            fsum_s = __fadd_rn(fsum_s, as);
-                            fsum_o = __fadd_rn(fsum_o, ao);
-                        }
-                    }
-                }
-            }
-            // forward differences in closed form:
-            //   c0[t+1]-c0[t] = (dcx[t+1]*wo[t] - dcx[t]*wo[t+1]) / (wo[t]*wo[t+1])
-            // (two-product compensation keeps the numerator exact to one rounding)
-#pragma unroll
-            for (int i = 0; i < GEO_FPT; ++i) {
-                const int t = t0 + i;
-                if (t >= a && t + 1 < b) {
-                    float p = dcx[i] * wo[i + 1];
-                    float e = fmaf(dcx[i], wo[i + 1], -p);
-                    out[5][i] = (fmaf(dcx[i + 1], wo[i], -p) - e) * (rwo[i] * rwo[i + 1]);
-                    p = dcy[i] * ho[i + 1];
-                    e = fmaf(dcy[i], ho[i + 1], -p);
-                    out[6][i] = (fmaf(dcy[i + 1], ho[i], -p) - e) * (rho[i] * rho[i + 1]);
-                }
-            }
-        }
+        geo_step<CLIP>(ss, smem_u32(o_stage0 + st * GEO_STAGE_BYTES), j0, t0, a, b, out, fsum_i, fsum_s, fsum_o);
         // this warp is done reading the object stage of step q: hand it back; thread 0 refills it with
         // object q+RING (end of the step) once every warp has done so
         __syncwarp();
@@ -334,6 +353,200 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
 #pragma unroll
         for (int i = 0; i < GEO_WARPS; ++i) val += acc[(q * GEO_WARPS + i) * 3 + w];
         if (val) atomicAdd(fx + (pair0 + q) * 3 + w, val);
+    }
+}
+
+// ---- the pair kernel, persistent form (opt-in: flag TSPN_GEO_PERSISTENT_CTAS) ------------------------
+// Measured alternative, NOT the default: on the bench workload (16 videos, N=64, T=2000) it runs the
+// geometry in 0.743 ms against 0.708 ms for the one-CTA-per-item kernel above, for every ring depth 2..4.
+// The 17th warp drops the register budget from 113 to 96 per thread (5 warps on one scheduler partition)
+// and the kernel is bound by store back-pressure, not by the refill latency this form removes.  It is
+// kept, bit-identical and tested, as the record of that experiment.
+// One CTA per SM slot walks the work items b, b + grid, b + 2*grid, ...; a dedicated PRODUCER warp runs
+// ahead of the consumer warps and keeps the TMA ring full across item boundaries, so that neither the
+// first loads of an item nor the refill of a stage ever wait for a consumer warp's own progress (in the
+// one-CTA-per-item kernel above thread 0 refills a stage only after its warp has finished the step, and
+// every CTA starts with an empty ring while its SM idles).  Steps are numbered globally per CTA
+// (g = 0, 1, ...): object stage g % RING, mbarrier parity (g / RING) & 1; the subject chunk of item i
+// lives in subject stage i & 1 and rides on the `full` barrier of the item's first step.  A consumer
+// warp releases a stage (and, with the last step of an item, that item's subject stage) by arriving on
+// `empty`; the producer consumes those completions strictly in step order.
+#ifndef TSPN_GEO_PRING
+#define TSPN_GEO_PRING 4
+#endif
+template <int THREADS>
+struct GeoPCfg {
+    using Base = GeoCfg<THREADS>;
+    static constexpr int RING = TSPN_GEO_PRING;
+    static constexpr int SUBJ = 2;
+    static constexpr int WARPS = Base::WARPS;
+    static constexpr int STAGE_BYTES = Base::STAGE_BYTES;
+    static constexpr int MIN_CTAS = Base::MIN_CTAS;
+    static constexpr int TAIL_BYTES = (2 * RING * 8 + GEO_OG * (WARPS * 3 * 8 + 8) + 127) / 128 * 128;
+    static constexpr int SMEM_USED = (SUBJ + RING) * STAGE_BYTES + TAIL_BYTES;
+    static constexpr int SMEM_PIN = 227 * 1024 / (MIN_CTAS + 1) + 1024;
+    static constexpr int SMEM_BYTES = SMEM_USED > SMEM_PIN ? SMEM_USED : SMEM_PIN;
+    static_assert((SMEM_BYTES + 1024) * MIN_CTAS <= 228 * 1024, "the stages of MIN_CTAS CTAs must fit one SM");
+};
+
+struct GeoItem {
+    int n, tp, s, k0, nobj, c;
+    int64_t tb, trk_off, box_row0, pair0, geo_off;
+};
+
+template <int CHUNK>
+__device__ __forceinline__ GeoItem geo_decode_item(const int64_t* __restrict__ table, int nv, int64_t item) {
+    GeoItem it;
+    const int v = find_video(table, nv, TSPN_VT_ITEM_OFF, item);
+    const int64_t* row = table + (int64_t)v * TSPN_VT_COLS;
+    it.n = (int)row[TSPN_VT_N];
+    const int t_len = (int)row[TSPN_VT_T];
+    it.tp = (int)row[TSPN_VT_TP];
+    it.tb = row[TSPN_VT_TB];
+    it.trk_off = row[TSPN_VT_TRK_OFF];
+    const int groups = (it.n - 1 + GEO_OG - 1) / GEO_OG;
+    const int nchunks = (t_len + CHUNK - 1) / CHUNK;
+    const int local = (int)(item - row[TSPN_VT_ITEM_OFF]);
+    it.c = local % nchunks;
+    const int sg = local / nchunks;
+    it.s = sg / groups;
+    it.k0 = (sg - it.s * groups) * GEO_OG;
+    it.nobj = min(GEO_OG, it.n - 1 - it.k0);
+    it.box_row0 = row[TSPN_VT_BOX_OFF];                      // multiple of 8
+    it.pair0 = row[TSPN_VT_PAIR_OFF] + (int64_t)it.s * (it.n - 1) + it.k0;
+    it.geo_off = row[TSPN_VT_GEO_OFF];
+    return it;
+}
+
+__device__ __forceinline__ void consumer_barrier(int threads) {
+    asm volatile("bar.sync 1, %0;" ::"r"(threads) : "memory");
+}
+
+template <int THREADS, bool WRITE_GEO, bool CLIP>
+__global__ void __launch_bounds__(THREADS + 32, GeoPCfg<THREADS>::MIN_CTAS)
+pair_geo_persistent_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __restrict__ table, int nv,
+                           int64_t total_items, const int32_t* __restrict__ span, float* __restrict__ geo,
+                           unsigned long long* __restrict__ fx) {
+    using Cfg = GeoCfg<THREADS>;
+    using PCfg = GeoPCfg<THREADS>;
+    constexpr int CHUNK = Cfg::CHUNK, WARPS = Cfg::WARPS, STAGE_BYTES = Cfg::STAGE_BYTES;
+    constexpr int TX_BYTES = Cfg::TX_BYTES, SPLIT = Cfg::SPLIT, RING = PCfg::RING;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* const s_stage0 = smem;                                           // [2] subject stages
+    uint8_t* const o_stage0 = smem + PCfg::SUBJ * STAGE_BYTES;                // [RING] object stages
+    uint64_t* const full = reinterpret_cast<uint64_t*>(smem + (PCfg::SUBJ + RING) * STAGE_BYTES);   // [RING]
+    uint64_t* const empty = full + RING;                                                           // [RING]
+    unsigned long long* const acc = reinterpret_cast<unsigned long long*>(empty + RING);     // [OG][WARPS][3]
+    int2* const owin = reinterpret_cast<int2*>(acc + GEO_OG * WARPS * 3);                    // [OG] overlap windows
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < RING; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], WARPS);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == WARPS) {
+        // ---- producer ---------------------------------------------------------------------------
+        if (lane != 0) return;
+        tma_prefetch_desc(&box_map);
+        uint32_t g = 0;                    // next step to load
+        uint32_t released = 0;             // steps [0, released) are known to be released by every consumer warp
+        uint32_t end_prev1 = 0, end_prev2 = 0;     // one past the last step of item i-1 / i-2
+        int parity = 0;
+        for (int64_t item = blockIdx.x; item < total_items; item += gridDim.x, parity ^= 1) {
+            const GeoItem it = geo_decode_item<CHUNK>(table, nv, item);
+            uint8_t* const s_stage = s_stage0 + parity * STAGE_BYTES;
+            for (int q = 0; q < it.nobj; ++q, ++g) {
+                uint32_t need = g >= (uint32_t)RING ? g - RING + 1 : 0u;     // object stage g % RING is free
+                if (q == 0 && end_prev2 > need) need = end_prev2;              // subject stage i & 1 is free
+                while (released < need) {
+                    mbar_wait(&empty[released % RING], (released / RING) & 1);
+                    ++released;
+                }
+                const int st = g % RING;
+                const int k = it.k0 + q;
+                const int o = k + (k >= it.s ? 1 : 0);
+                mbar_expect_tx(&full[st], q == 0 ? 2 * TX_BYTES : TX_BYTES);
+#pragma unroll
+                for (int h = 0; h < SPLIT; ++h) {                 // second half: rows CHUNK/16 .. CHUNK/8 (+ halo)
+                    const int r_off = h * (CHUNK / 16);
+                    if (q == 0)
+                        tma_load_2d(s_stage + r_off * 128, &box_map, 0,
+                                    (int)((it.box_row0 + (int64_t)it.s * it.tb + (int64_t)it.c * CHUNK) >> 3) + r_off,
+                                    &full[st]);
+                    tma_load_2d(o_stage0 + st * STAGE_BYTES + r_off * 128, &box_map, 0,
+                                (int)((it.box_row0 + (int64_t)o * it.tb + (int64_t)it.c * CHUNK) >> 3) + r_off,
+                                &full[st]);
+                }
+            }
+            end_prev2 = end_prev1;
+            end_prev1 = g;
+        }
+        return;
+    }
+
+    // ---- consumers ------------------------------------------------------------------------------
+    int st = 0, ph = 0;                                      // ring stage of the current step and its parity
+    int parity = 0;
+    for (int64_t item = blockIdx.x; item < total_items; item += gridDim.x, parity ^= 1) {
+        const GeoItem it = geo_decode_item<CHUNK>(table, nv, item);
+        if (tid < it.nobj) {
+            const int ps = __ldg(span + 2 * (it.trk_off + it.s)), pe = __ldg(span + 2 * (it.trk_off + it.s) + 1);
+            const int k = it.k0 + tid;
+            const int o = k + (k >= it.s ? 1 : 0);
+            const int qs = __ldg(span + 2 * (it.trk_off + o)), qe = __ldg(span + 2 * (it.trk_off + o) + 1);
+            owin[tid] = make_int2(max(ps, qs), min(pe, qe));
+        }
+        consumer_barrier(THREADS);           // owin visible; the previous item's acc has been reduced
+
+        const int t0 = it.c * CHUNK + tid * GEO_FPT;             // first frame of this thread
+        const int j0 = tid * GEO_FPT;                            // ... inside the staged chunk
+        const uint32_t ss = smem_u32(s_stage0 + parity * STAGE_BYTES);
+        float* g = WRITE_GEO ? geo + it.geo_off + ((int64_t)(it.s * (it.n - 1) + it.k0) * TSPN_GEO_CHANNELS) * it.tp + t0
+                             : nullptr;
+        for (int q = 0; q < it.nobj; ++q) {
+            const int2 win = owin[q];
+            mbar_wait(&full[st], ph);
+            float fsum_i, fsum_s, fsum_o;
+            float out[TSPN_GEO_CHANNELS][GEO_FPT];
+            geo_step<CLIP>(ss, smem_u32(o_stage0 + st * STAGE_BYTES), j0, t0, win.x, win.y, out, fsum_i, fsum_s, fsum_o);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st]);              // this warp is done with the stage (and subject)
+            if (WRITE_GEO && t0 < it.tp) {
+#pragma unroll
+                for (int ch = 0; ch < TSPN_GEO_CHANNELS; ++ch)
+                    st_stream_f4(g + (int64_t)ch * it.tp, make_float4(out[ch][0], out[ch][1], out[ch][2], out[ch][3]));
+                g += (int64_t)TSPN_GEO_CHANNELS * it.tp;
+            }
+            const unsigned long long tot_i = warp_sum_fx(fsum_i);
+            unsigned long long tot_s = 0ull, tot_o = 0ull;
+            if (CLIP) {
+                tot_s = warp_sum_fx(fsum_s);
+                tot_o = warp_sum_fx(fsum_o);
+            }
+            if (lane == 0) {          // every (object, warp) slot is written exactly once per item
+                unsigned long long* slot = acc + (q * WARPS + warp) * 3;
+                slot[0] = tot_i;
+                slot[1] = tot_s;
+                slot[2] = tot_o;
+            }
+            if (++st == RING) { st = 0; ph ^= 1; }
+        }
+        consumer_barrier(THREADS);           // every slot of this item is written
+        for (int i3 = tid; i3 < it.nobj * 3; i3 += THREADS) {
+            const int q = i3 / 3, w = i3 - 3 * q;
+            unsigned long long val = 0ull;
+#pragma unroll
+            for (int i = 0; i < WARPS; ++i) val += acc[(q * WARPS + i) * 3 + w];
+            if (val) atomicAdd(fx + (it.pair0 + q) * 3 + w, val);
+        }
     }
 }
 
@@ -522,8 +735,9 @@ __global__ void __launch_bounds__(256) enumerate_pairs_kernel(const int64_t* __r
 template <int THREADS>
 static int launch_pair_geo(const int64_t* d_table, int num_videos, int64_t total_items, int64_t total_boxes,
                            const float* d_boxes, const int32_t* d_span, float* d_geo, unsigned long long* fx,
-                           bool clip, cudaStream_t st) {
+                           bool clip, bool per_item, cudaStream_t st) {
     using Cfg = GeoCfg<THREADS>;
+    using PCfg = GeoPCfg<THREADS>;
     // boxes viewed as a 2-D tensor: rows of 8 boxes (32 floats = 128 B)
     CUtensorMap map;
     const uint64_t dims[2] = {32, (uint64_t)(total_boxes / 8)};
@@ -534,10 +748,19 @@ static int launch_pair_geo(const int64_t* d_table, int num_videos, int64_t total
     if (rc != TSPN_OK) return rc;
 #define TSPN_LAUNCH_GEO(W, C)                                                                                  \
     do {                                                                                                       \
-        TSPN_CUDA_OK(cudaFuncSetAttribute(pair_geo_kernel<THREADS, W, C>,                                      \
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));      \
-        pair_geo_kernel<THREADS, W, C><<<(unsigned)total_items, THREADS, Cfg::SMEM_BYTES, st>>>(               \
-            map, d_table, num_videos, d_span, d_geo, fx);                                                      \
+        if (per_item) {                                                                                        \
+            TSPN_CUDA_OK(cudaFuncSetAttribute(pair_geo_kernel<THREADS, W, C>,                                  \
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));  \
+            pair_geo_kernel<THREADS, W, C><<<(unsigned)total_items, THREADS, Cfg::SMEM_BYTES, st>>>(           \
+                map, d_table, num_videos, d_span, d_geo, fx);                                                  \
+        } else {                                                                                               \
+            const int64_t slots = (int64_t)num_sms() * PCfg::MIN_CTAS;                                         \
+            const unsigned grid = (unsigned)(total_items < slots ? total_items : slots);                       \
+            TSPN_CUDA_OK(cudaFuncSetAttribute(pair_geo_persistent_kernel<THREADS, W, C>,                       \
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg::SMEM_BYTES)); \
+            pair_geo_persistent_kernel<THREADS, W, C><<<grid, THREADS + 32, PCfg::SMEM_BYTES, st>>>(           \
+                map, d_table, num_videos, total_items, d_span, d_geo, fx);                                     \
+        }                                                                                                      \
     } while (0)
     if (d_geo) {
         if (clip) TSPN_LAUNCH_GEO(true, true); else TSPN_LAUNCH_GEO(true, false);
@@ -601,20 +824,22 @@ int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_ite
     const bool clip = (flags & TSPN_VIOU_CLIPPED) != 0;
     {
         // volumes (one warp per tracklet) + zeroing of the fixed-point accumulators (grid-stride)
-        const int64_t blocks_vol = clip ? 0 : (total_tracklets + 3) / 4;
+        const int64_t cap = 16 * (int64_t)num_sms();
+        const int64_t blocks_vol = clip ? 0 : total_tracklets;
         const int64_t blocks_zero = (total_pairs * 3 + 127) / 128;
-        int64_t blocks = blocks_vol > 1 ? blocks_vol : 1;
-        const int64_t cap = 8 * (int64_t)num_sms();
-        if (blocks < blocks_zero) blocks = blocks_zero < cap ? blocks_zero : (blocks > cap ? blocks : cap);
+        int64_t blocks = blocks_vol > blocks_zero ? blocks_vol : blocks_zero;
+        if (blocks > cap) blocks = cap;                // both loops are grid-stride
+        if (blocks < 1) blocks = 1;
         tracklet_volume_kernel<<<(unsigned)blocks, 128, 0, st>>>(d_table, num_videos, total_tracklets,
                                                                 reinterpret_cast<const float4*>(d_boxes), d_span, vol,
                                                                 !clip, fx, total_pairs * 3);
         TSPN_CUDA_OK(cudaGetLastError());
     }
     int rc = TSPN_OK;
-    if (geo_chunk == 512) rc = launch_pair_geo<128>(d_table, num_videos, total_items, total_boxes, d_boxes, d_span, d_geo, fx, clip, st);
-    else if (geo_chunk == 1024) rc = launch_pair_geo<256>(d_table, num_videos, total_items, total_boxes, d_boxes, d_span, d_geo, fx, clip, st);
-    else rc = launch_pair_geo<512>(d_table, num_videos, total_items, total_boxes, d_boxes, d_span, d_geo, fx, clip, st);
+    const bool per_item = (flags & TSPN_GEO_PERSISTENT_CTAS) == 0;
+    if (geo_chunk == 512) rc = launch_pair_geo<128>(d_table, num_videos, total_items, total_boxes, d_boxes, d_span, d_geo, fx, clip, per_item, st);
+    else if (geo_chunk == 1024) rc = launch_pair_geo<256>(d_table, num_videos, total_items, total_boxes, d_boxes, d_span, d_geo, fx, clip, per_item, st);
+    else rc = launch_pair_geo<512>(d_table, num_videos, total_items, total_boxes, d_boxes, d_span, d_geo, fx, clip, per_item, st);
     if (rc != TSPN_OK) return rc;
     const unsigned fblocks = (unsigned)((total_pairs + 255) / 256);
     if (clip)

@@ -6,6 +6,8 @@ without synchronising.
 """
 from __future__ import annotations
 
+import os
+
 from typing import Dict, Optional
 
 import torch
@@ -62,8 +64,14 @@ def enumerate_pairs(batch: DeviceBatch) -> torch.Tensor:
 
 
 def pair_geometry(batch: DeviceBatch, write_geo: bool = True, clipped: bool = False,
-                  out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
-    """All-pairs per-frame geometry + vIoU/tIoU/overlap (trajectory.py:85-141, common.py:65-106)."""
+                  out: Optional[Dict[str, torch.Tensor]] = None,
+                  persistent_ctas: Optional[bool] = None) -> Dict[str, torch.Tensor]:
+    """All-pairs per-frame geometry + vIoU/tIoU/overlap (trajectory.py:85-141, common.py:65-106).
+    ``persistent_ctas`` selects the persistent producer-warp kernel instead of the default one CTA per work
+    item (bit-identical results, measured slower; A/B timing only - default from the environment variable
+    TSPN_GEO_PERSISTENT)."""
+    if persistent_ctas is None:
+        persistent_ctas = os.environ.get("TSPN_GEO_PERSISTENT", "0") == "1"
     dev = batch.device
     tot = batch.totals
     p = batch.total_pairs
@@ -79,7 +87,8 @@ def pair_geometry(batch: DeviceBatch, write_geo: bool = True, clipped: bool = Fa
         ptr(batch.table), batch.num_videos, int(tot[_lib.TOT_ITEMS]), int(tot[_lib.TOT_GEO_CHUNK]),
         batch.total_tracklets, batch.total_pairs,
         int(tot[_lib.TOT_BOXES]), ptr(batch.boxes), ptr(batch.span), ptr(out.get("geo")), ptr(out["viou"]),
-        ptr(out["tiou"]), ptr(out["overlap"]), _lib.VIOU_CLIPPED if clipped else _lib.VIOU_FULL,
+        ptr(out["tiou"]), ptr(out["overlap"]),
+        (_lib.VIOU_CLIPPED if clipped else _lib.VIOU_FULL) | (_lib.GEO_PERSISTENT_CTAS if persistent_ctas else 0),
         ptr(out["workspace"]), stream_ptr()), "tspn_pair_geo_viou")
     _count(3)       # volumes + accumulator zeroing, pair kernel, per-pair finalize
     return out
@@ -162,7 +171,8 @@ def assemble_features(batch: DeviceBatch, motion_norm: torch.Tensor, geo: torch.
     if want_bf16 and out_bf16 is None:
         out_bf16 = torch.empty((n_rows, ld16), dtype=torch.bfloat16, device=dev)
     check(load().tspn_assemble_features(
-        ptr(batch.table), batch.num_videos, batch.total_pairs, ptr(batch.cls), c, ptr(motion_norm), ptr(geo),
+        ptr(batch.table), batch.num_videos, batch.total_pairs, int(batch.totals[_lib.TOT_MAX_T]), ptr(batch.cls), c,
+        ptr(motion_norm), ptr(geo),
         ptr(overlap), ptr(rows), n_rows, ptr(out_fp32), out_fp32.stride(0) if out_fp32 is not None else 0,
         ptr(out_bf16), out_bf16.stride(0) if out_bf16 is not None else 0, stream_ptr()), "tspn_assemble_features")
     _count(1)

@@ -179,6 +179,16 @@ class PairStage:
         sparsify = c.sparsify and c.use_ppn
         feats32 = feats16 = logits = None
         tensor = c.precision == "tensor"
+        # The span head (HBM-bound reads of the surviving geometry rows) runs on the side stream underneath
+        # the feature-row -> predicate-head chain (issue- / latency-bound), joined before the records.
+        span_reg = spans = span_bufs = None
+        main = torch.cuda.current_stream(batch.device)
+        side_stream = self._side_stream(batch.device)
+        fork_spans = heads and c.use_dpn
+        if fork_spans:
+            side_stream.wait_stream(main)
+            with torch.cuda.stream(side_stream):
+                span_reg, spans, span_bufs = self._span_heads(batch, geom, row, k_eff)
         if features is None:
             rows = row.reshape(-1) if sparsify else None
             feats32, feats16 = ops.assemble_features(batch, mn, geom["geo"], geom["overlap"], rows,
@@ -192,9 +202,6 @@ class PairStage:
             x = feats16 if feats16 is not None else feats32
             logits = ops.predicate_head(x, self.w[CLS_PREFIX + "weight"], self.w[CLS_PREFIX + "bias"],
                                         precision=c.precision, packed=self.packed_cls)
-        span_reg = spans = span_bufs = None
-        if heads and c.use_dpn:
-            span_reg, spans, span_bufs = self._span_heads(batch, geom, row, k_eff)
         records = counts = None
         if heads and c.records:
             if sparsify:
@@ -209,6 +216,11 @@ class PairStage:
             else:
                 records, counts = ops.postprocess(batch, logits, geom["overlap"], c.topk_per_pair, c.topk_per_video,
                                                   mirror_q4=c.mirror_q4)
+        if fork_spans:
+            main.wait_stream(side_stream)
+            if not torch.cuda.is_current_stream_capturing():
+                for tns in (span_bufs or []) + (span_reg or []):
+                    tns.record_stream(main)          # allocated on the side stream, read on the caller's
         return StageResult(batch, geom, scores, idx, val, row, feats32, feats16, logits, span_reg, spans, k_eff,
                            sparsify, records, counts, span_bufs)
 
@@ -302,7 +314,7 @@ class GraphedStage:
                  heads: bool = True):
         self.stage, self.batch = stage, batch
         dev = batch.device
-        self.side_stream = stage._side_stream(dev)
+        self.side_stream = torch.cuda.Stream(dev)     # own stream: replays of different slots may overlap
         self._cap_stream = torch.cuda.Stream(dev)
         stage.forward(batch, features=features, heads=heads)      # warm-up: lazy init outside capture
         torch.cuda.synchronize(dev)

@@ -5,9 +5,10 @@ The reference's driver (lib/modeling/predict.py:42-57) feeds one ``PairList`` at
 launch- and PCIe-latency-bound, so the serving loop works on *batches of videos* and keeps
 ``depth`` of them in flight over three streams:
 
-    h2d stream :  H2D(i+1) ......................
-    main stream:  kernels(i)  (3 CUDA-graph launches, see pipeline.GraphedStage)
-    d2h stream :  D2H(i-1) ......................
+    h2d stream    :  H2D(i+1) ......................
+    compute stream:  kernels(i)  (3 CUDA-graph launches, see pipeline.GraphedStage); two compute streams
+                     alternate, so the tail of step i overlaps the geometry kernel of step i+1
+    d2h stream    :  D2H(i-1) ......................
 
 Every slot owns its device input buffers, its captured graphs (and therefore its output buffers) and
 its pinned host result buffers, so nothing is allocated in steady state.  With ``group`` the per-video
@@ -44,9 +45,13 @@ class PipelinedStage:
     ``template`` (the graphs are captured for them)."""
 
     def __init__(self, stage: PairStage, template: HostBatch, device="cuda", depth: int = 2, graphs: bool = True,
-                 group=None):
+                 group=None, compute_streams: int = 1):
         self.stage, self.device, self.depth, self.group = stage, torch.device(device), int(depth), group
         self.main = torch.cuda.current_stream(self.device)
+        # Two compute streams, used alternately: the latency-bound tail of step i (feature rows, heads,
+        # records - it leaves most of the HBM bandwidth idle) runs underneath the HBM-bound geometry kernel
+        # of step i+1.  Slots never share buffers, so the only ordering needed is per slot (events below).
+        self.compute = [torch.cuda.Stream(self.device) for _ in range(2 if int(depth) > 1 and compute_streams > 1 else 1)]
         self.s_h2d, self.s_d2h = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
         self.slots: List[_Slot] = [_Slot(stage, template, self.device, graphs) for _ in range(self.depth)]
         self._next = 0
@@ -63,7 +68,7 @@ class PipelinedStage:
             self.s_h2d.wait_event(slot.kernels_done)     # the slot's previous kernels have consumed its inputs
             slot.batch.copy_from(host)
             slot.h2d_done.record(self.s_h2d)
-        main = self.main
+        main = self.compute[i % len(self.compute)]
         with torch.cuda.stream(main):
             main.wait_event(slot.h2d_done)
             main.wait_event(slot.d2h_done)               # the slot's previous results have left the device

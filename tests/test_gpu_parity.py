@@ -83,6 +83,31 @@ def test_pair_geometry_kernel_shapes(shapes, chunk, clip):
         np.testing.assert_allclose(tiou[sl], w_tiou, rtol=1e-6, atol=0)
 
 
+@pytest.mark.parametrize("shapes", [
+    RAGGED,                                                               # ragged batch incl. N = 0 / 1 videos
+    [(20, 300, 0), (5, 37, 11), (9, 512, 8), (2, 1, 3)],                  # 128-thread CTAs
+    [(7, 513, 7), (4, 1024, 9), (3, 700, 1)],                             # 256-thread CTAs
+    [(3, 4100, 2), (70, 40, 3), (4, 2049, 4), (5, 2048, 5)],              # 512-thread CTAs, two object groups
+    [(2, 9, 1)] * 700,                                                    # 1400 one-object items: more items than
+                                                                          # CTA slots, every item shorter than the ring
+    [(3, 600, 4), (2, 2100, 5), (40, 2100, 6)],                           # items of 1, 2 and 39 objects interleaved
+])
+@pytest.mark.parametrize("clip", [False, True])
+def test_persistent_and_per_item_kernels_are_bit_identical(shapes, clip):
+    """The opt-in persistent kernel (producer warp, TMA ring carried across work items) against the
+    default one-CTA-per-item kernel: every output bit for bit."""
+    vids = [synth.make_video(n, t, 35, seed=s) for n, t, s in shapes]
+    batch = _batch(vids)
+    a = ops.pair_geometry(batch, write_geo=True, clipped=clip, persistent_ctas=True)
+    b = ops.pair_geometry(batch, write_geo=True, clipped=clip, persistent_ctas=False)
+    c = ops.pair_geometry(batch, write_geo=False, clipped=clip, persistent_ctas=True)
+    torch.cuda.synchronize()
+    for key in ("geo", "viou", "tiou", "overlap"):
+        assert torch.equal(a[key], b[key]), key
+    for key in ("viou", "tiou", "overlap"):
+        assert torch.equal(a[key], c[key]), key
+
+
 def test_pair_geometry_reductions_only_and_fractional_boxes():
     v = synth.make_video(11, 700, 35, seed=21, integer_boxes=False)
     batch = _batch([v])
