@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="launch every kernel from the host instead of CUDA graphs")
     ap.add_argument("--depth", type=int, default=3, help="batches in flight in the end-to-end serving loop")
+    ap.add_argument("--three-graphs", action="store_true",
+                    help="replay the step as three CUDA graphs joined on the host instead of one graph")
     ap.add_argument("--compute-streams", type=int, default=1, choices=[1, 2],
                     help="compute streams of the serving loop (2: the tail of step i overlaps the geometry of i+1)")
     return ap.parse_args()
@@ -243,7 +245,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -278,7 +280,7 @@ def run_ours(args, rank, world, local_rank):
     # buffers); the resident-input measurement replays slot 0's graphs on inputs already in HBM.
     group = dist.group.WORLD if world > 1 else None
     pipe = PipelinedStage(stage, host, device=dev, depth=args.depth, graphs=not args.eager, group=group,
-                          compute_streams=args.compute_streams)
+                          compute_streams=args.compute_streams, single_graph=not args.three_graphs)
     slot0 = pipe.slots[0]
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)    # > 126 MB L2
     torch.cuda.synchronize()
@@ -293,7 +295,7 @@ def run_ours(args, rank, world, local_rank):
             return slot0.graphed.replay(timers=timers)
         return stage.forward(slot0.batch, timers=timers)
 
-    geo_ev, step_ev = [], []
+    geo_ms, step_ms = [], []
     sampler = ClockSampler(local_rank)
     sampler.start()                                     # samples through warm-up, timed steps and e2e
     launches0 = ops.launch_count()
@@ -309,12 +311,13 @@ def run_ours(args, rank, world, local_rank):
         e0.record()
         one_step(timers=timers)
         e1.record()
-        step_ev.append((e0, e1))
-        geo_ev.append(timers["geo"])
+        # the single-graph replay times the geometry kernel with external event nodes that the next
+        # replay re-records: read them now (the steps are separated by the untimed L2 flush anyway)
+        e1.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
+        geo_ms.append(timers["geo"][0].elapsed_time(timers["geo"][1]))
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    step_ms = [a.elapsed_time(b) for a, b in step_ev]
-    geo_ms = [a.elapsed_time(b) for a, b in geo_ev]
     total_ms = float(sum(step_ms))
     if world > 1:
         tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
@@ -371,7 +374,10 @@ def run_ours(args, rank, world, local_rank):
                          "%.1f GB of outputs" % (alg_bytes / 1e9),
                    "wall_s_timed_region": t_wall,
                    "launch": "eager C-ABI calls" if args.eager else
-                             "3 CUDA-graph launches per step (side: relationness+top-K+motion norm || geo; tail)",
+                             ("3 CUDA-graph launches per step (side: relationness+top-K+motion norm || geo; tail)"
+                              if args.three_graphs else
+                              "1 CUDA-graph launch per step (forks inside the graph: relationness+top-K+motion "
+                              "norm || geometry; span head || feature rows -> predicate head -> records)"),
                    "e2e_pipeline": "tspn_b200.serving.PipelinedStage, depth %d: one H2D copy of the pinned input "
                                    "arena per step; H2D(i+1..) and D2H(i-1) overlap the kernels of step i; %d compute "
                                    "stream(s)" % (args.depth, args.compute_streams),
@@ -395,10 +401,26 @@ def run_ours(args, rank, world, local_rank):
                                           "%d threads) scaled to P, heads at full size; torch threads=%d"
                                           % (p1, 16 * cores, cores, torch.get_num_threads()),
                                 "detail_s": det}
-    print(json.dumps(line))
+    emit(line)
+
+
+_JSON_OUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line of the run, on the process's original stdout."""
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    # Libraries write to fd 1 behind python's back (NCCL prints its version banner there under torchrun):
+    # keep the real stdout for the JSON line only and send everything else to stderr.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

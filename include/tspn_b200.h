@@ -154,11 +154,15 @@ int tspn_viou_pairs(const float* d_pool, const int64_t* d_traj_off, const int32_
  * (d_workspace: tspn_viou_pairs_workspace_bytes(n_traj) bytes), each pair then reads only its overlap
  * window; sums and the ratio stay in fp64, so for integer boxes d_out[i] is bit-identical to python's
  * float(v_overlap) / (v1 + v2 - v_overlap) and the host-side threshold decisions cannot flip.
- * TSPN_VIOU_CLIPPED gives association.py:35-48 (volumes over the overlap only) in fp64. */
+ * TSPN_VIOU_CLIPPED gives association.py:35-48 (volumes over the overlap only) in fp64.
+ * d_traj_len (int32 [n_traj], may be NULL = duration length): number of boxes of each trajectory.  The
+ * reference sums a trajectory's volume over its whole box list (common.py:100-105), and association
+ * emits relations whose lists are longer than their duration (shared trajectories extended by other
+ * relations' merges); the overlap window still comes from the durations, so len >= duration is required. */
 int64_t tspn_viou_pairs_workspace_bytes(int64_t n_traj);
 int tspn_viou_pairs_f64(const float* d_pool, const int64_t* d_traj_off, const int32_t* d_traj_span,
-                        int64_t n_traj, const int32_t* d_a, const int32_t* d_b, int64_t n_pairs,
-                        int flags, double* d_out, void* d_workspace, void* stream);
+                        const int32_t* d_traj_len, int64_t n_traj, const int32_t* d_a, const int32_t* d_b,
+                        int64_t n_pairs, int flags, double* d_out, void* d_workspace, void* stream);
 
 /* ---- a2: feature rows -------------------------------------------------------------------
  * L1-normalise each 1000-wide BoW block (lib/dataset/vrdataset.py:227-236 with

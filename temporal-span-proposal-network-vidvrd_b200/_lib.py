@@ -46,7 +46,7 @@ SIGNATURES = {
     "tspn_cubic_iou": (c_int, [P, c_int, P, c_int, c_int, P, P]),
     "tspn_viou_pairs": (c_int, [P, P, P, P, P, c_int64, c_int, P, P]),
     "tspn_viou_pairs_workspace_bytes": (c_int64, [c_int64]),
-    "tspn_viou_pairs_f64": (c_int, [P, P, P, c_int64, P, P, c_int64, c_int, P, P, P]),
+    "tspn_viou_pairs_f64": (c_int, [P, P, P, P, c_int64, P, P, c_int64, c_int, P, P, P]),
     "tspn_normalize_motion": (c_int, [P, c_int64, P, P]),
     "tspn_assemble_features": (c_int, [P, c_int, c_int64, c_int, P, c_int, P, P, P, P, c_int64, P, c_int64, P, c_int64, P]),
     "tspn_relationness_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),

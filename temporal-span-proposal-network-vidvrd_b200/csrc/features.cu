@@ -134,6 +134,9 @@ assemble_kernel(const int64_t* __restrict__ table, int nv, const float* __restri
             }
             __syncthreads();
         }
+        // every bin spans at most ceil(len / 500) + 1 frames: a CTA-uniform trip count with a predicated
+        // body instead of a per-thread loop bound (frames are still added in ascending order)
+        const int max_w = (int)((len + TSPN_REL_BINS - 1) / TSPN_REL_BINS) + 1;
         for (int w = threadIdx.x; w < 2 * TSPN_REL_BINS; w += ASM_THREADS) {
             const int c = w >= TSPN_REL_BINS ? 1 : 0;
             const int i = w - c * TSPN_REL_BINS;
@@ -144,8 +147,11 @@ assemble_kernel(const int64_t* __restrict__ table, int nv, const float* __restri
                 const float inv = 1.0f / (float)(en - st);
                 float sacc = 0.0f;
                 if (staged) {
-                    const float* sp = s_geo + c * cap + (a - a4);
-                    for (uint32_t f = st; f < en; ++f) sacc += sp[f];
+                    const float* sp = s_geo + c * cap + (a - a4) + st;
+                    const int cnt = (int)(en - st);
+#pragma unroll 2
+                    for (int j = 0; j < max_w; ++j)
+                        if (j < cnt) sacc += sp[j];
                 } else {
                     const float* gc = g + (int64_t)(ch0 + c) * tp + a;
                     for (uint32_t f = st; f < en; ++f) sacc += __ldg(gc + f);

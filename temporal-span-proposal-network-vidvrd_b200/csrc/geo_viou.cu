@@ -32,6 +32,10 @@ constexpr int GEO_OG = TSPN_GEO_OBJ_GROUP;
 #endif
 constexpr int GEO_RING = TSPN_GEO_RING;               // object-chunk stages in flight
 constexpr int GEO_STAGES = 1 + GEO_RING;              // subject chunk + object ring
+#ifndef TSPN_GEO_ROTATE
+#define TSPN_GEO_ROTATE 1
+#endif
+constexpr bool GEO_ROTATE = TSPN_GEO_ROTATE != 0;     // rotate the warps' frame blocks with the object index
 
 // Shape of one CTA: THREADS threads cover a chunk of 4*THREADS frames (512 / 1024 / 2048, chosen per
 // batch by tspn_geo_chunk).  HBM absorbs this kernel's store stream best as few, wide streams
@@ -300,15 +304,21 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
         for (int q = 0; q < GEO_RING && q < nobj; ++q) issue(q);
     }
 
-    const int t0 = c * GEO_CHUNK + tid * GEO_FPT;            // first frame of this thread
-    const int j0 = tid * GEO_FPT;                            // ... inside the staged chunk
     const uint32_t ss = smem_u32(s_stage);
-    float* g = WRITE_GEO ? geo + row[TSPN_VT_GEO_OFF] + ((int64_t)(s * (n - 1) + k0) * TSPN_GEO_CHANNELS) * tp + t0
+    float* g = WRITE_GEO ? geo + row[TSPN_VT_GEO_OFF] + ((int64_t)(s * (n - 1) + k0) * TSPN_GEO_CHANNELS) * tp +
+                               (int64_t)c * GEO_CHUNK
                          : nullptr;
     int st = 0, ph = 0;                                      // ring stage of step q and its phase parity
     for (int q = 0; q < nobj; ++q) {
         const int2 win = owin[q];
         const int a = win.x, b = win.y;                      // overlap window [a, b)
+        // Frame ownership rotates with the object: warp w covers the 128-frame block (w + q) mod WARPS.
+        // Frames inside the overlap window cost ~10x the frames outside it, and the window sits mostly in
+        // the middle of the video, so a fixed block per warp would make the same warps the slow ones for
+        // every object of the item while the others idle at the ring (the stage advances with the
+        // slowest warp).
+        const int j0 = (((warp + (GEO_ROTATE ? q : 0)) & (GEO_WARPS - 1)) * 32 + lane) * GEO_FPT;   // inside the chunk
+        const int t0 = c * GEO_CHUNK + j0;                   // first frame of this thread
 
         mbar_wait(&full[st], ph);
 
@@ -320,10 +330,12 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[st]);
 
-        if (WRITE_GEO && t0 < tp) {
+        if (WRITE_GEO) {
+            if (t0 < tp) {
 #pragma unroll
-            for (int ch = 0; ch < TSPN_GEO_CHANNELS; ++ch)
-                st_stream_f4(g + (int64_t)ch * tp, make_float4(out[ch][0], out[ch][1], out[ch][2], out[ch][3]));
+                for (int ch = 0; ch < TSPN_GEO_CHANNELS; ++ch)
+                    st_stream_f4(g + (int64_t)ch * tp + j0, make_float4(out[ch][0], out[ch][1], out[ch][2], out[ch][3]));
+            }
             g += (int64_t)TSPN_GEO_CHANNELS * tp;
         }
         // the three volume sums over the chunk's frames (order-independent, see above)
@@ -506,23 +518,27 @@ pair_geo_persistent_kernel(const __grid_constant__ CUtensorMap box_map, const in
         }
         consumer_barrier(THREADS);           // owin visible; the previous item's acc has been reduced
 
-        const int t0 = it.c * CHUNK + tid * GEO_FPT;             // first frame of this thread
-        const int j0 = tid * GEO_FPT;                            // ... inside the staged chunk
         const uint32_t ss = smem_u32(s_stage0 + parity * STAGE_BYTES);
-        float* g = WRITE_GEO ? geo + it.geo_off + ((int64_t)(it.s * (it.n - 1) + it.k0) * TSPN_GEO_CHANNELS) * it.tp + t0
+        float* g = WRITE_GEO ? geo + it.geo_off + ((int64_t)(it.s * (it.n - 1) + it.k0) * TSPN_GEO_CHANNELS) * it.tp +
+                                   (int64_t)it.c * CHUNK
                              : nullptr;
         for (int q = 0; q < it.nobj; ++q) {
             const int2 win = owin[q];
+            const int j0 = (((warp + (GEO_ROTATE ? q : 0)) & (WARPS - 1)) * 32 + lane) * GEO_FPT;   // rotating blocks
+            const int t0 = it.c * CHUNK + j0;
             mbar_wait(&full[st], ph);
             float fsum_i, fsum_s, fsum_o;
             float out[TSPN_GEO_CHANNELS][GEO_FPT];
             geo_step<CLIP>(ss, smem_u32(o_stage0 + st * STAGE_BYTES), j0, t0, win.x, win.y, out, fsum_i, fsum_s, fsum_o);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[st]);              // this warp is done with the stage (and subject)
-            if (WRITE_GEO && t0 < it.tp) {
+            if (WRITE_GEO) {
+                if (t0 < it.tp) {
 #pragma unroll
-                for (int ch = 0; ch < TSPN_GEO_CHANNELS; ++ch)
-                    st_stream_f4(g + (int64_t)ch * it.tp, make_float4(out[ch][0], out[ch][1], out[ch][2], out[ch][3]));
+                    for (int ch = 0; ch < TSPN_GEO_CHANNELS; ++ch)
+                        st_stream_f4(g + (int64_t)ch * it.tp + j0,
+                                     make_float4(out[ch][0], out[ch][1], out[ch][2], out[ch][3]));
+                }
                 g += (int64_t)TSPN_GEO_CHANNELS * it.tp;
             }
             const unsigned long long tot_i = warp_sum_fx(fsum_i);
@@ -660,13 +676,15 @@ __global__ void __launch_bounds__(128) viou_pairs_kernel(const float4* __restric
 // exactly python's float(v_overlap) / (v1 + v2 - v_overlap) for integer boxes ---------------------
 __global__ void __launch_bounds__(128) traj_volume_kernel(const float4* __restrict__ pool,
                                                           const int64_t* __restrict__ traj_off,
-                                                          const int32_t* __restrict__ traj_span, int64_t n_traj,
+                                                          const int32_t* __restrict__ traj_span,
+                                                          const int32_t* __restrict__ traj_len, int64_t n_traj,
                                                           double* __restrict__ vol) {
     const int64_t j = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (j >= n_traj) return;
     const int lane = threadIdx.x & 31;
     const float4* p = pool + traj_off[j];
-    const int len = traj_span[2 * j + 1] - traj_span[2 * j];
+    // common.py:100-105 sums the volume over the whole box LIST, which may be longer than the duration
+    const int len = traj_len ? traj_len[j] : traj_span[2 * j + 1] - traj_span[2 * j];
     double acc = 0.0;
     for (int f = lane; f < len; f += 32) {
         const float4 x = __ldg(p + f);
@@ -888,9 +906,9 @@ int64_t tspn_viou_pairs_workspace_bytes(int64_t n_traj) {
     return ((n_traj > 0 ? n_traj : 1) * (int64_t)sizeof(double) + 15) / 16 * 16;
 }
 
-int tspn_viou_pairs_f64(const float* d_pool, const int64_t* d_traj_off, const int32_t* d_traj_span, int64_t n_traj,
-                        const int32_t* d_a, const int32_t* d_b, int64_t n_pairs, int flags, double* d_out,
-                        void* d_workspace, void* stream) {
+int tspn_viou_pairs_f64(const float* d_pool, const int64_t* d_traj_off, const int32_t* d_traj_span,
+                        const int32_t* d_traj_len, int64_t n_traj, const int32_t* d_a, const int32_t* d_b,
+                        int64_t n_pairs, int flags, double* d_out, void* d_workspace, void* stream) {
     TSPN_ARCH_OK();
     TSPN_REQUIRE(n_pairs >= 0 && n_traj >= 0, TSPN_EBADARG, "tspn_viou_pairs_f64: negative size");
     if (n_pairs == 0) return TSPN_OK;
@@ -905,7 +923,8 @@ int tspn_viou_pairs_f64(const float* d_pool, const int64_t* d_traj_off, const in
     if (flags & TSPN_VIOU_CLIPPED) {
         viou_pairs_f64_kernel<true><<<blocks, 128, 0, st>>>(pool, d_traj_off, d_traj_span, vol, d_a, d_b, n_pairs, d_out);
     } else {
-        traj_volume_kernel<<<(unsigned)((n_traj + 3) / 4), 128, 0, st>>>(pool, d_traj_off, d_traj_span, n_traj, vol);
+        traj_volume_kernel<<<(unsigned)((n_traj + 3) / 4), 128, 0, st>>>(pool, d_traj_off, d_traj_span, d_traj_len, n_traj,
+                                                                          vol);
         TSPN_CUDA_OK(cudaGetLastError());
         viou_pairs_f64_kernel<false><<<blocks, 128, 0, st>>>(pool, d_traj_off, d_traj_span, vol, d_a, d_b, n_pairs, d_out);
     }

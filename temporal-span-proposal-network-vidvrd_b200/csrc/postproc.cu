@@ -15,7 +15,8 @@ namespace tspn {
 
 constexpr int PP_MAX_R = 256;     // predicates per row handled by one warp (8 per lane)
 
-// one warp per scored row: its topk_per_pair best predicates, in order
+// one warp per scored row: its topk_per_pair best predicates, in order; SLOTS = ceil(r / 32) values per lane
+template <int SLOTS>
 __global__ void __launch_bounds__(128)
 pair_top_predicates_kernel(const float* __restrict__ logits, const int64_t* __restrict__ rows, int64_t m, int r,
                            int tpp, float* __restrict__ cand_score, int32_t* __restrict__ cand_pred) {
@@ -32,9 +33,9 @@ pair_top_predicates_kernel(const float* __restrict__ logits, const int64_t* __re
         }
         return;
     }
-    float v[PP_MAX_R / 32];
+    float v[SLOTS];
 #pragma unroll
-    for (int j = 0; j < PP_MAX_R / 32; ++j) {
+    for (int j = 0; j < SLOTS; ++j) {
         const int c = lane + 32 * j;
         v[j] = c < r ? __ldg(logits + row * r + c) : NEG_INF;
     }
@@ -42,7 +43,7 @@ pair_top_predicates_kernel(const float* __restrict__ logits, const int64_t* __re
         float best = NEG_INF;
         int bi = 0x7fffffff;
 #pragma unroll
-        for (int j = 0; j < PP_MAX_R / 32; ++j) {
+        for (int j = 0; j < SLOTS; ++j) {
             const int c = lane + 32 * j;
             if (c < r && (v[j] > best || (v[j] == best && c < bi))) {
                 best = v[j];
@@ -71,7 +72,7 @@ pair_top_predicates_kernel(const float* __restrict__ logits, const int64_t* __re
         }
         if ((bi & 31) == lane) {
 #pragma unroll
-            for (int j = 0; j < PP_MAX_R / 32; ++j)
+            for (int j = 0; j < SLOTS; ++j)
                 if (j == (bi >> 5)) v[j] = NEG_INF;
         }
     }
@@ -90,6 +91,31 @@ __device__ __forceinline__ int argmax_row(const float* __restrict__ x, int c) {
     return bi;
 }
 
+constexpr int PP_LABEL_CAP = 1024;     // tracklet labels of one video kept in shared memory
+
+// arg-max of one classeme row by a warp: largest value, ties to the lower index (torch.argmax)
+__device__ __forceinline__ int warp_argmax_row(const float* __restrict__ x, int c, int lane) {
+    float best = __uint_as_float(0xff800000u);
+    int bi = 0x7fffffff;
+    for (int i = lane; i < c; i += 32) {
+        const float q = __ldg(x + i);
+        if (q > best) {           // ascending i within a lane: the first maximum wins
+            best = q;
+            bi = i;
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+        if (ob > best || (ob == best && oi < bi)) {
+            best = ob;
+            bi = oi;
+        }
+    }
+    return bi == 0x7fffffff ? 0 : bi;      // all -inf / NaN rows: index 0, like the sequential scan
+}
+
 // one CTA per video: top `tpv` of its (rows x tpp) candidates -> records
 __global__ void __launch_bounds__(TOPK_THREADS)
 video_top_triplets_kernel(const int64_t* __restrict__ table, int nv, const float* __restrict__ cand_score,
@@ -98,9 +124,18 @@ video_top_triplets_kernel(const int64_t* __restrict__ table, int nv, const float
                           const float* __restrict__ cls, int n_classes, const int32_t* __restrict__ overlap,
                           int mirror_q4, int32_t* __restrict__ records, int32_t* __restrict__ counts) {
     __shared__ TopkSmem sm;
+    __shared__ int s_label[PP_LABEL_CAP];
     const int v = blockIdx.x;
     const int64_t* row = table + (int64_t)v * TSPN_VT_COLS;
     const int n = (int)row[TSPN_VT_N];
+    // the class label of every tracklet of the video, once (predict.py:88-93 takes the arg-max per kept
+    // triplet; 2 x 200 sequential scans of C values were the bulk of this kernel's latency)
+    const bool labels_cached = n <= PP_LABEL_CAP;
+    if (labels_cached) {
+        const float* cls_v = cls + row[TSPN_VT_TRK_OFF] * n_classes;
+        for (int j = threadIdx.x >> 5; j < n; j += TOPK_THREADS / 32)
+            s_label[j] = warp_argmax_row(cls_v + (int64_t)j * n_classes, n_classes, threadIdx.x & 31);
+    }                                       // block_topk synchronises before the labels are read
     const int64_t pair_off = row[TSPN_VT_PAIR_OFF];
     const int64_t r0 = row_video_off ? row_video_off[v] : pair_off;
     const int64_t r1 = row_video_off ? row_video_off[v + 1] : pair_off + (int64_t)n * (n > 0 ? n - 1 : 0);
@@ -123,9 +158,9 @@ video_top_triplets_kernel(const int64_t* __restrict__ table, int nv, const float
             // 0 (or 1 when o == 0): quirk Q4, reproduced only on request
             const int o_src = mirror_q4 ? (o == 0 ? 1 : 0) : o;
             out[0] = __float_as_int(__ldg(cs + flat));
-            out[1] = argmax_row(cls + (trk0 + s) * n_classes, n_classes);
+            out[1] = labels_cached ? s_label[s] : argmax_row(cls + (trk0 + s) * n_classes, n_classes);
             out[2] = __ldg(cand_pred + r0 * tpp + flat);
-            out[3] = argmax_row(cls + (trk0 + o_src) * n_classes, n_classes);
+            out[3] = labels_cached ? s_label[o_src] : argmax_row(cls + (trk0 + o_src) * n_classes, n_classes);
             out[4] = s;
             out[5] = o;
             out[6] = __ldg(overlap + 2 * gp);
@@ -171,9 +206,16 @@ int tspn_postprocess(const int64_t* d_table, int num_videos, const float* d_logi
     float* cand_score = reinterpret_cast<float*>(d_workspace);
     int32_t* cand_pred = reinterpret_cast<int32_t*>(cand_score + n_rows * tpp);
     if (n_rows > 0) {
-        pair_top_predicates_kernel<<<(unsigned)((n_rows + 3) / 4), 128, 0, st>>>(d_logits, d_rows, n_rows,
-                                                                                n_predicates, tpp, cand_score,
-                                                                                cand_pred);
+        const unsigned blocks = (unsigned)((n_rows + 3) / 4);
+#define TSPN_LAUNCH_PTP(S)                                                                                        \
+    pair_top_predicates_kernel<S><<<blocks, 128, 0, st>>>(d_logits, d_rows, n_rows, n_predicates, tpp, cand_score, \
+                                                          cand_pred)
+        if (n_predicates <= 32) TSPN_LAUNCH_PTP(1);
+        else if (n_predicates <= 64) TSPN_LAUNCH_PTP(2);
+        else if (n_predicates <= 128) TSPN_LAUNCH_PTP(4);
+        else if (n_predicates <= 160) TSPN_LAUNCH_PTP(5);
+        else TSPN_LAUNCH_PTP(8);
+#undef TSPN_LAUNCH_PTP
         TSPN_CUDA_OK(cudaGetLastError());
     }
     video_top_triplets_kernel<<<(unsigned)num_videos, TOPK_THREADS, 0, st>>>(

@@ -120,14 +120,16 @@ def viou_pairs(pool: torch.Tensor, traj_off: torch.Tensor, traj_span: torch.Tens
 
 
 def viou_pairs_f64(pool: torch.Tensor, traj_off: torch.Tensor, traj_span: torch.Tensor, a: torch.Tensor,
-                   b: torch.Tensor, clipped: bool = False) -> torch.Tensor:
+                   b: torch.Tensor, clipped: bool = False, traj_len: Optional[torch.Tensor] = None) -> torch.Tensor:
     """fp64 vIoU of explicit trajectory pairs with per-trajectory volumes summed once (the evaluation
-    loop of lib/evaluation/visual_relation_detection.py:8-36; association.py:35-48 when ``clipped``)."""
+    loop of lib/evaluation/visual_relation_detection.py:8-36; association.py:35-48 when ``clipped``).
+    ``traj_len``: boxes per trajectory when a list is longer than its duration (volumes run over the list)."""
     pool = _cuda(pool, torch.float32)
     n_traj = int(traj_span.shape[0])
     out = torch.empty(a.shape[0], dtype=torch.float64, device=pool.device)
     ws = torch.empty(load().tspn_viou_pairs_workspace_bytes(n_traj), dtype=torch.uint8, device=pool.device)
     check(load().tspn_viou_pairs_f64(ptr(pool), ptr(_cuda(traj_off, torch.int64)), ptr(_cuda(traj_span, torch.int32)),
+                                     ptr(_cuda(traj_len, torch.int32)) if traj_len is not None else None,
                                      n_traj, ptr(_cuda(a, torch.int32)), ptr(_cuda(b, torch.int32)), a.shape[0],
                                      _lib.VIOU_CLIPPED if clipped else _lib.VIOU_FULL, ptr(out), ptr(ws),
                                      stream_ptr()),

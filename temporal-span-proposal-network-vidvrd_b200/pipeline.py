@@ -248,9 +248,9 @@ class PairStage:
         return self._seg_tail(batch, features, heads, side, geom)
 
     def capture(self, batch: DeviceBatch, features: Optional[torch.Tensor] = None,
-                heads: bool = True) -> "GraphedStage":
-        """Freeze the step for this batch's shapes into CUDA graphs (see GraphedStage)."""
-        return GraphedStage(self, batch, features, heads)
+                heads: bool = True, single: bool = True) -> "GraphedStage":
+        """Freeze the step for this batch's shapes into a CUDA graph (see GraphedStage)."""
+        return GraphedStage(self, batch, features, heads, single=single)
 
     def _span_heads(self, batch: DeviceBatch, geom, row, k_eff):
         """DPNHead + decode on the surviving pairs of every video (rows gathered inside the kernel)."""
@@ -301,37 +301,66 @@ class PairStage:
 
 
 class GraphedStage:
-    """The step of one fixed-shape batch as three CUDA graphs (side / geo / tail).
+    """The step of one fixed-shape batch as ONE CUDA graph (``single=True``, default) or as three
+    (side / geo / tail, joined with stream events on the host).
 
     Launch-bound host work (13 C-ABI calls, their output allocations and tensor-map encodes) is paid
-    once at capture; a replay is three graph launches, two stream joins and - optionally - the two
-    CUDA events that time the geometry kernel.  All outputs live in the graphs' private memory pool
-    and are overwritten by every replay: ``result`` always refers to the latest one.  Refill the inputs
-    with ``batch.copy_from(host)`` (same per-video shapes) between replays.
+    once at capture.  In the single graph the side branch (relationness + top-K, motion normalisation)
+    and the span-head branch are forks inside the graph, and the two events that time the geometry kernel
+    are *external* event-record nodes (``torch.cuda.Event(external=True)``): every replay re-records
+    them, so ``timers["geo"]`` must be read (after a synchronize) before the next replay.  All outputs live
+    in the graph's private memory pool and are overwritten by every replay: ``result`` always refers to
+    the latest one.  Refill the inputs with ``batch.copy_from(host)`` (same per-video shapes) between
+    replays.
     """
 
     def __init__(self, stage: PairStage, batch: DeviceBatch, features: Optional[torch.Tensor] = None,
-                 heads: bool = True):
+                 heads: bool = True, single: bool = True):
         self.stage, self.batch = stage, batch
         dev = batch.device
         self.side_stream = torch.cuda.Stream(dev)     # own stream: replays of different slots may overlap
         self._cap_stream = torch.cuda.Stream(dev)
         stage.forward(batch, features=features, heads=heads)      # warm-up: lazy init outside capture
         torch.cuda.synchronize(dev)
-        self.g_side, self.g_geo, self.g_tail = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        self.single = bool(single)
         pool = torch.cuda.graph_pool_handle()
         n0 = ops.launch_count()
-        with torch.cuda.graph(self.g_side, pool=pool, stream=self._cap_stream):
-            side = stage._seg_side(batch, features)
-        with torch.cuda.graph(self.g_geo, pool=pool, stream=self._cap_stream):
-            geom = stage._seg_geo(batch, features)
-        with torch.cuda.graph(self.g_tail, pool=pool, stream=self._cap_stream):
-            self.result = stage._seg_tail(batch, features, heads, side, geom)
+        if self.single:
+            self.graph = torch.cuda.CUDAGraph()
+            self.ev_geo = (torch.cuda.Event(enable_timing=True, external=True),
+                           torch.cuda.Event(enable_timing=True, external=True))
+            fork = stage._side_stream(dev)
+            with torch.cuda.graph(self.graph, pool=pool, stream=self._cap_stream):
+                cap = torch.cuda.current_stream(dev)
+                fork.wait_stream(cap)
+                with torch.cuda.stream(fork):
+                    side = stage._seg_side(batch, features)
+                self.ev_geo[0].record(cap)
+                geom = stage._seg_geo(batch, features)
+                self.ev_geo[1].record(cap)
+                cap.wait_stream(fork)
+                self.result = stage._seg_tail(batch, features, heads, side, geom)
+        else:
+            self.g_side, self.g_geo, self.g_tail = (torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(),
+                                                    torch.cuda.CUDAGraph())
+            with torch.cuda.graph(self.g_side, pool=pool, stream=self._cap_stream):
+                side = stage._seg_side(batch, features)
+            with torch.cuda.graph(self.g_geo, pool=pool, stream=self._cap_stream):
+                geom = stage._seg_geo(batch, features)
+            with torch.cuda.graph(self.g_tail, pool=pool, stream=self._cap_stream):
+                self.result = stage._seg_tail(batch, features, heads, side, geom)
         self.kernels_per_replay = ops.launch_count() - n0
+        self.graph_launches = 1 if self.single else 3
         torch.cuda.synchronize(dev)
 
     def replay(self, timers: Optional[dict] = None) -> StageResult:
         main = torch.cuda.current_stream(self.batch.device)
+        if self.single:
+            self.graph.replay()
+            if timers is not None:
+                timers["geo"] = self.ev_geo          # valid until the next replay
+            ops.count_launches(self.kernels_per_replay)
+            return self.result
         self.side_stream.wait_stream(main)
         with torch.cuda.stream(self.side_stream):
             self.g_side.replay()

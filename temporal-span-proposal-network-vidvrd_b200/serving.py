@@ -26,10 +26,10 @@ from .pipeline import GraphedStage, PairStage
 
 
 class _Slot:
-    def __init__(self, stage: PairStage, template: HostBatch, device, graphs: bool):
+    def __init__(self, stage: PairStage, template: HostBatch, device, graphs: bool, single_graph: bool = True):
         self.batch: DeviceBatch = template.to_device(device, non_blocking=False)
         torch.cuda.synchronize(device)
-        self.graphed: Optional[GraphedStage] = stage.capture(self.batch) if graphs else None
+        self.graphed: Optional[GraphedStage] = stage.capture(self.batch, single=single_graph) if graphs else None
         self.h2d_done = torch.cuda.Event()
         self.kernels_done = torch.cuda.Event()
         self.d2h_done = torch.cuda.Event()
@@ -45,7 +45,7 @@ class PipelinedStage:
     ``template`` (the graphs are captured for them)."""
 
     def __init__(self, stage: PairStage, template: HostBatch, device="cuda", depth: int = 2, graphs: bool = True,
-                 group=None, compute_streams: int = 1):
+                 group=None, compute_streams: int = 1, single_graph: bool = True):
         self.stage, self.device, self.depth, self.group = stage, torch.device(device), int(depth), group
         self.main = torch.cuda.current_stream(self.device)
         # Two compute streams, used alternately: the latency-bound tail of step i (feature rows, heads,
@@ -53,7 +53,7 @@ class PipelinedStage:
         # of step i+1.  Slots never share buffers, so the only ordering needed is per slot (events below).
         self.compute = [torch.cuda.Stream(self.device) for _ in range(2 if int(depth) > 1 and compute_streams > 1 else 1)]
         self.s_h2d, self.s_d2h = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
-        self.slots: List[_Slot] = [_Slot(stage, template, self.device, graphs) for _ in range(self.depth)]
+        self.slots: List[_Slot] = [_Slot(stage, template, self.device, graphs, single_graph) for _ in range(self.depth)]
         self._next = 0
         self._gathered: List[Optional[torch.Tensor]] = [None] * self.depth
 

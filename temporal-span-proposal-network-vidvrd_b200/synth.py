@@ -320,3 +320,21 @@ def make_association_case(seed: int = 0, n_segments: int = 8, n_objects: int = 5
         segment_trajs[index] = trajs
     order = rng.permutation(len(short_term))          # the association sorts segments by fstart itself
     return [short_term[i] for i in order], segment_trajs
+
+
+def make_gt_from_relations(relations, seed: int = 0, keep_every: int = 3):
+    """Ground truth derived from serialized video relations (the output of greedy association): every
+    ``keep_every``-th relation, its box lists cut to the duration and shifted by 0-3 pixels.  Used to
+    evaluate association output, whose box lists can be LONGER than their durations (shared trajectories
+    extended by other relations' merges) - the case lib/evaluation/common.py:100-105 sums volumes over."""
+    rng = np.random.Generator(np.random.PCG64(seed + 49979687))
+    out = []
+    for i, r in enumerate(relations):
+        if i % keep_every:
+            continue
+        n = r["duration"][1] - r["duration"][0]
+        shift = float(rng.integers(0, 4))
+        out.append({"triplet": list(r["triplet"]), "duration": list(r["duration"]),
+                    "sub_traj": [[float(c) + shift for c in b] for b in r["sub_traj"][:n]],
+                    "obj_traj": [[float(c) - shift for c in b] for b in r["obj_traj"][:n]]})
+    return out

@@ -114,16 +114,26 @@ def viou_batch(trajs, durations, pairs, clipped: bool = False, f64: bool = False
         if lens[j]:
             pool[off[j]:off[j + 1]] = np.asarray(t, dtype=np.float32).reshape(-1, 4)
     span = np.asarray(durations, dtype=np.int32).reshape(-1, 2)
-    for j in range(len(trajs)):
-        if span[j, 1] - span[j, 0] != lens[j]:
-            raise ValueError("trajectory %d: %d boxes for duration %s" % (j, lens[j], tuple(span[j])))
+    dur = span[:, 1] - span[:, 0]
+    lens_a = np.asarray(lens, dtype=np.int32)
+    longer = bool((lens_a != dur).any())
+    if longer and (not f64 or clipped or (lens_a < dur).any()):
+        # common.py:100-105 sums volumes over the whole box list, so a list LONGER than its duration is
+        # meaningful (association emits such relations) - supported by the fp64 entry point only; a
+        # shorter list makes the reference index out of range
+        j = int(np.nonzero(lens_a != dur)[0][0])
+        raise ValueError("trajectory %d: %d boxes for duration %s" % (j, lens[j], tuple(span[j])))
     pairs = np.asarray(pairs, dtype=np.int32).reshape(-1, 2)
     if pairs.shape[0] == 0:
         return np.zeros(0, dtype=np.float64 if f64 else np.float32)
-    fn = ops.viou_pairs_f64 if f64 else ops.viou_pairs
-    out = fn(torch.from_numpy(pool).to(dev), torch.from_numpy(off[:-1].copy()).to(dev),
-             torch.from_numpy(span).to(dev), torch.from_numpy(pairs[:, 0].copy()).to(dev),
-             torch.from_numpy(pairs[:, 1].copy()).to(dev), clipped=clipped)
+    args = (torch.from_numpy(pool).to(dev), torch.from_numpy(off[:-1].copy()).to(dev),
+            torch.from_numpy(span).to(dev), torch.from_numpy(pairs[:, 0].copy()).to(dev),
+            torch.from_numpy(pairs[:, 1].copy()).to(dev))
+    if f64:
+        out = ops.viou_pairs_f64(*args, clipped=clipped,
+                                 traj_len=torch.from_numpy(lens_a).to(dev) if longer else None)
+    else:
+        out = ops.viou_pairs(*args, clipped=clipped)
     return out.cpu().numpy()
 
 

@@ -109,6 +109,21 @@ def main():
         out[f"assoc_{tag}_cap7_triplet"], out[f"assoc_{tag}_cap7_score"] = trip, score
         out[f"assoc_{tag}_cap7_duration"] = dur
         print(tag, "relations", len(score), "merged", int((dur[:, 1] - dur[:, 0] > 30).sum()))
+        # evaluation of association output: box lists longer than their durations (common.py:100-105)
+        rels = assoc.greedy_relational_association(NameOnlyDataset(), short_term, max_traj_num_in_clip=100)
+        rels = [dict(r, sub_traj=[list(b) for b in r["sub_traj"]], obj_traj=[list(b) for b in r["obj_traj"]])
+                for r in rels]
+        gt = {"synthetic_video": synth.make_gt_from_relations(rels, seed=kw["seed"])}
+        pred = {"synthetic_video": rels}
+        with contextlib.redirect_stdout(io.StringIO()):
+            mean_ap, rec_at_n, mprec_at_n = evaluate(gt, pred)
+        p_, r_, h_ = eval_detection_scores(gt["synthetic_video"], rels, 0.5)
+        out[f"assoc_{tag}_eval_mean_ap"] = np.float64(mean_ap)
+        out[f"assoc_{tag}_eval_rec_at_n"] = np.array([rec_at_n[k] for k in (50, 100, 1000)], dtype=np.float64)
+        out[f"assoc_{tag}_eval_hit_scores"] = h_
+        longer = sum(len(r["sub_traj"]) != r["duration"][1] - r["duration"][0] for r in rels)
+        print(tag, "eval of association output: mAP", mean_ap, "hits", int(np.isfinite(h_).sum()), "of", len(h_),
+              "relations with list != duration:", longer)
 
     path = os.path.join(HERE, "relations_outputs.npz")
     np.savez_compressed(path, **out)

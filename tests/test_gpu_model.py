@@ -178,8 +178,9 @@ def test_triplet_records_match_predict_py_postprocessing(sparsify):
             assert (rec[i, m:, 1:6] == -1).all()
 
 
+@pytest.mark.parametrize("single", [True, False])
 @pytest.mark.parametrize("precision", ["fp32", "tensor"])
-def test_graphed_and_pipelined_stage_match_eager(precision):
+def test_graphed_and_pipelined_stage_match_eager(precision, single):
     """CUDA-graph replay and the pinned-host serving loop return exactly what the eager call returns,
     for every batch fed through the same slots (stale state would show up on the second batch)."""
     from tspn_b200.batch import HostBatch
@@ -199,15 +200,18 @@ def test_graphed_and_pipelined_stage_match_eager(precision):
         want.append({k: v.cpu().clone() for k, v in res.host_outputs().items()})
     # graph replay on refilled inputs
     batch = hosts[0].to_device("cuda")
-    graphed = stage.capture(batch)
+    graphed = stage.capture(batch, single=single)
+    timers = {}
     for h, w in zip(hosts, want):
         batch.copy_from(h)
-        res = graphed.replay()
+        res = graphed.replay(timers=timers)
         torch.cuda.synchronize()
+        assert timers["geo"][0].elapsed_time(timers["geo"][1]) > 0.0     # the geometry kernel's own events
         for k, v in res.host_outputs().items():
             assert torch.equal(v.cpu(), w[k]), k
     # pinned-host pipeline, two batches in flight
-    pipe = PipelinedStage(stage, hosts[0], device="cuda", depth=2)
+    pipe = PipelinedStage(stage, hosts[0], device="cuda", depth=2, single_graph=single,
+                          compute_streams=2 if single else 1)
     got = [{k: v.clone() for k, v in out.items()} for out in pipe.run(iter(hosts))]
     assert len(got) == len(want)
     for g, w in zip(got, want):

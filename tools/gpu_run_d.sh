@@ -1,0 +1,14 @@
+set -x
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/d_pytest.log 2>&1; echo "pytest rc=$?"
+tail -15 gpurun_out/d_pytest.log
+summ() { python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); r=d['roofline']
+print('$1: geo %.4f ms  %.0f GB/s  frac %.3f | step %.4f ms value %.2fM e2e %.2fM' % (r['avg_launch_ms'], r['achieved'], r['frac'], d['ms_per_step'], d['value']/1e6, d['e2e']['value']/1e6))
+"; }
+timeout 300 python bench.py --no-cpu-baseline --steps 40 2> gpurun_out/d.err | tee gpurun_out/d_bench_1g.json | summ one_graph
+timeout 300 python bench.py --no-cpu-baseline --steps 40 --three-graphs 2>> gpurun_out/d.err | tee gpurun_out/d_bench_3g.json | summ three_graphs
+timeout 300 python bench.py --no-cpu-baseline --steps 40 --compute-streams 2 2>> gpurun_out/d.err | tee gpurun_out/d_bench_1g_cs2.json | summ one_graph_cs2
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/d_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --eager > gpurun_out/d_b_ncu.log 2>&1
+tail -5 gpurun_out/d.err
