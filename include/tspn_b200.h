@@ -93,9 +93,9 @@ extern "C" {
 #define TSPN_VIOU_FULL 0       /* volumes over each full span: evaluation/common.py:65-106 (V2);
                                   equals trajectory.py:127-141 (V1) when all spans are equal */
 #define TSPN_VIOU_CLIPPED 1    /* volumes over the overlap only: association.py:35-48 (V3) */
-#define TSPN_GEO_PERSISTENT_CTAS 2 /* tspn_pair_geo_viou: persistent CTAs with a producer warp instead of the
-                                  default one CTA per work item (same results bit for bit; measured slower,
-                                  kept for A/B timing - DESIGN.md section 4.1) */
+#define TSPN_GEO_DENSE_CTAS 2   /* tspn_pair_geo_viou: 1024 threads per SM with a 2-stage TMA ring and 64 registers
+                                  instead of the default ~512 threads per SM, 3 stages, 103 registers (same
+                                  results bit for bit; measured slower, kept for A/B - DESIGN.md section 4.1) */
 #define TSPN_TOPK_KEEP_DIAGONAL 0    /* reference behaviour, ppn.py:84-85 (quirk Q1) */
 #define TSPN_TOPK_EXCLUDE_DIAGONAL 1 /* survivors are real pairs (sparsify mode) */
 #define TSPN_PREC_FP32_EXACT 0 /* CUDA cores, fixed k-ascending fma order: bit-reproducible */

@@ -26,7 +26,7 @@ GEO_CHANNELS = 8
 MOTION_DIM = 4000
 REL_DIM = 3000
 VIOU_FULL, VIOU_CLIPPED = 0, 1
-GEO_PERSISTENT_CTAS = 2
+GEO_DENSE_CTAS = 2
 TOPK_KEEP_DIAGONAL, TOPK_EXCLUDE_DIAGONAL = 0, 1
 PREC_FP32_EXACT, PREC_TENSOR = 0, 1
 

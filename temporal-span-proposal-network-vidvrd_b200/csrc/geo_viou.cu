@@ -30,8 +30,7 @@ constexpr int GEO_OG = TSPN_GEO_OBJ_GROUP;
 #ifndef TSPN_GEO_RING
 #define TSPN_GEO_RING 3
 #endif
-constexpr int GEO_RING = TSPN_GEO_RING;               // object-chunk stages in flight
-constexpr int GEO_STAGES = 1 + GEO_RING;              // subject chunk + object ring
+constexpr int GEO_RING = TSPN_GEO_RING;               // object-chunk stages in flight (non-dense shape)
 #ifndef TSPN_GEO_ROTATE
 #define TSPN_GEO_ROTATE 1
 #endif
@@ -39,25 +38,34 @@ constexpr bool GEO_ROTATE = TSPN_GEO_ROTATE != 0;     // rotate the warps' frame
 
 // Shape of one CTA: THREADS threads cover a chunk of 4*THREADS frames (512 / 1024 / 2048, chosen per
 // batch by tspn_geo_chunk).  HBM absorbs this kernel's store stream best as few, wide streams
-// (tools/bench_store_pattern.cu: 5.8 TB/s with 2 KB row segments from 24 warps per SM, 7.0-7.4 TB/s
-// with whole 8 KB rows from 16 warps), so a CTA writes row segments as long as the video allows and
-// the shared-memory request pins the occupancy at about 512 threads per SM.
-template <int THREADS>
+// (tools/bench_store_pattern.cu, store-only kernels with this address pattern: 5.8 TB/s with 2 KB row
+// segments, 7.0-7.4 TB/s with whole 8 KB rows), so a CTA writes row segments as long as the video allows.
+// Two occupancy shapes:
+//   DENSE = false  (default) ~512 threads per SM (one 512-thread CTA), 3-stage object ring, 103 registers;
+//   DENSE = true   (flag TSPN_GEO_DENSE_CTAS) 1024 threads per SM (two 512-thread CTAs), 2-stage ring, 64
+//                  registers (64 B of spills): twice the warps to cover the LDS / MUFU / TMA latencies
+//                  between a warp's store bursts.  Measured on the bench workload: 0.919 ms against
+//                  0.707 ms for the default - kept, bit-identical and tested, as the record of that A/B
+//                  (profiles/r1_geo_kernel_forms_ab.md).
+// The shared-memory request pins the occupancy.
+template <int THREADS, bool DENSE>
 struct GeoCfg {
     static constexpr int CHUNK = THREADS * GEO_FPT;
     static constexpr int WARPS = THREADS / 32;
+    static constexpr int RING = DENSE ? 2 : GEO_RING;             // object-chunk stages in flight
+    static constexpr int STAGES = 1 + RING;                       // subject chunk + object ring
     static constexpr int ROWS = CHUNK / 8 + 1;                    // rows of 8 boxes + 1 halo row
     static constexpr int SPLIT = ROWS > 256 ? 2 : 1;              // a TMA box has at most 256 rows
     static constexpr int BOX_ROWS = SPLIT == 1 ? ROWS : CHUNK / 16 + 1;   // the second box re-reads one row
     static constexpr int TX_BYTES = SPLIT * BOX_ROWS * 128;       // bytes landing per staged chunk
     static constexpr int STAGE_BYTES = ROWS * 128;                // stages are packed (128-byte aligned)
-    static constexpr int MIN_CTAS = THREADS >= 512 ? 1 : (THREADS == 256 ? 2 : 3);
-    // barriers, per-(object, warp) sums, per-object overlap windows
-    static constexpr int TAIL_BYTES = (2 * GEO_RING * 8 + GEO_OG * (WARPS * 3 * 8 + 8) + 127) / 128 * 128;
-    static constexpr int SMEM_USED = GEO_STAGES * STAGE_BYTES + TAIL_BYTES;
+    static constexpr int MIN_CTAS = DENSE ? 1024 / THREADS : (THREADS >= 512 ? 1 : (THREADS == 256 ? 2 : 3));
+    // barriers, per-object fixed-point sums, per-object overlap windows
+    static constexpr int TAIL_BYTES = (2 * RING * 8 + GEO_OG * (3 * 8 + 8) + 127) / 128 * 128;
+    static constexpr int SMEM_USED = STAGES * STAGE_BYTES + TAIL_BYTES;
     static constexpr int SMEM_PIN = 227 * 1024 / (MIN_CTAS + 1) + 1024;
     static constexpr int SMEM_BYTES = SMEM_USED > SMEM_PIN ? SMEM_USED : SMEM_PIN;
-    static_assert(SMEM_BYTES * MIN_CTAS <= 227 * 1024, "the stages of MIN_CTAS CTAs must fit one SM");
+    static_assert((SMEM_BYTES + 1024) * MIN_CTAS <= 228 * 1024, "the stages of MIN_CTAS CTAs must fit one SM");
 };
 
 // box j of a chunk staged with SWIZZLE_128B: the 16-byte slot index (address bits 4..6) is XORed
@@ -229,20 +237,20 @@ __device__ __forceinline__ void geo_step(uint32_t ss, uint32_t os_addr, int j0, 
     }
 }
 
-template <int THREADS, bool WRITE_GEO, bool CLIP>
-__global__ void __launch_bounds__(THREADS, GeoCfg<THREADS>::MIN_CTAS)
+template <int THREADS, bool WRITE_GEO, bool CLIP, bool DENSE>
+__global__ void __launch_bounds__(THREADS, GeoCfg<THREADS, DENSE>::MIN_CTAS)
 pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __restrict__ table, int nv,
                 const int32_t* __restrict__ span, float* __restrict__ geo, unsigned long long* __restrict__ fx) {
-    using Cfg = GeoCfg<THREADS>;
+    using Cfg = GeoCfg<THREADS, DENSE>;
     constexpr int GEO_CHUNK = Cfg::CHUNK, GEO_WARPS = Cfg::WARPS, GEO_STAGE_BYTES = Cfg::STAGE_BYTES;
-    constexpr int GEO_TX_BYTES = Cfg::TX_BYTES, GEO_SPLIT = Cfg::SPLIT;
+    constexpr int GEO_TX_BYTES = Cfg::TX_BYTES, GEO_SPLIT = Cfg::SPLIT, RING = Cfg::RING;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* const s_stage = smem;
     uint8_t* const o_stage0 = smem + GEO_STAGE_BYTES;
-    uint64_t* const full = reinterpret_cast<uint64_t*>(smem + GEO_STAGES * GEO_STAGE_BYTES);  // [RING]
-    uint64_t* const empty = full + GEO_RING;                                                  // [RING]
-    unsigned long long* const acc = reinterpret_cast<unsigned long long*>(empty + GEO_RING);  // [OG][WARPS][3]
-    int2* const owin = reinterpret_cast<int2*>(acc + GEO_OG * GEO_WARPS * 3);                 // [OG] overlap windows
+    uint64_t* const full = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * GEO_STAGE_BYTES);   // [RING]
+    uint64_t* const empty = full + RING;                                                       // [RING]
+    unsigned long long* const acc = reinterpret_cast<unsigned long long*>(empty + RING);       // [OG][3]
+    int2* const owin = reinterpret_cast<int2*>(acc + GEO_OG * 3);                              // [OG] overlap windows
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -269,7 +277,7 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
 
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < GEO_RING; ++i) {
+        for (int i = 0; i < RING; ++i) {
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], GEO_WARPS);
         }
@@ -283,12 +291,13 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
         const int qs = __ldg(span + 2 * (trk_off + o)), qe = __ldg(span + 2 * (trk_off + o) + 1);
         owin[tid] = make_int2(max(ps, qs), min(pe, qe));
     }
+    for (int i = tid; i < GEO_OG * 3; i += THREADS) acc[i] = 0ull;
     __syncthreads();
 
     auto issue = [&](int q) {          // thread 0: object q (and, with the first, the subject chunk)
         const int k = k0 + q;
         const int o = k + (k >= s ? 1 : 0);
-        const int st = q % GEO_RING;
+        const int st = q % RING;
         mbar_expect_tx(&full[st], q == 0 ? 2 * GEO_TX_BYTES : GEO_TX_BYTES);
 #pragma unroll
         for (int h = 0; h < GEO_SPLIT; ++h) {                 // second half: rows CHUNK/16 .. CHUNK/8 (+ halo)
@@ -301,7 +310,7 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
         }
     };
     if (tid == 0) {
-        for (int q = 0; q < GEO_RING && q < nobj; ++q) issue(q);
+        for (int q = 0; q < RING && q < nobj; ++q) issue(q);
     }
 
     const uint32_t ss = smem_u32(s_stage);
@@ -338,231 +347,32 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
             }
             g += (int64_t)TSPN_GEO_CHANNELS * tp;
         }
-        // the three volume sums over the chunk's frames (order-independent, see above)
+        // the three volume sums over the chunk's frames: integer adds, so neither the warp reduction nor
+        // the order of the shared-memory atomics below can change the result
         const unsigned long long tot_i = warp_sum_fx(fsum_i);
         unsigned long long tot_s = 0ull, tot_o = 0ull;
         if (CLIP) {
             tot_s = warp_sum_fx(fsum_s);
             tot_o = warp_sum_fx(fsum_o);
         }
-        if (lane == 0) {          // every (object, warp) slot is written exactly once: no atomics, no zeroing
-            unsigned long long* slot = acc + (q * GEO_WARPS + warp) * 3;
-            slot[0] = tot_i;
-            slot[1] = tot_s;
-            slot[2] = tot_o;
+        if (lane == 0) {
+            if (tot_i) atomicAdd(acc + q * 3, tot_i);
+            if (CLIP) {
+                if (tot_s) atomicAdd(acc + q * 3 + 1, tot_s);
+                if (tot_o) atomicAdd(acc + q * 3 + 2, tot_o);
+            }
         }
-        if (tid == 0 && q + GEO_RING < nobj) {               // by now the other warps have normally arrived
+        if (tid == 0 && q + RING < nobj) {                   // by now the other warps have normally arrived
             mbar_wait(&empty[st], ph);
-            issue(q + GEO_RING);
+            issue(q + RING);
         }
-        if (++st == GEO_RING) { st = 0; ph ^= 1; }
+        if (++st == RING) { st = 0; ph ^= 1; }
     }
     __syncthreads();
     // this chunk's contribution to the pair's sums
     for (int i3 = tid; i3 < nobj * 3; i3 += THREADS) {
-        const int q = i3 / 3, w = i3 - 3 * q;
-        unsigned long long val = 0ull;
-#pragma unroll
-        for (int i = 0; i < GEO_WARPS; ++i) val += acc[(q * GEO_WARPS + i) * 3 + w];
-        if (val) atomicAdd(fx + (pair0 + q) * 3 + w, val);
-    }
-}
-
-// ---- the pair kernel, persistent form (opt-in: flag TSPN_GEO_PERSISTENT_CTAS) ------------------------
-// Measured alternative, NOT the default: on the bench workload (16 videos, N=64, T=2000) it runs the
-// geometry in 0.743 ms against 0.708 ms for the one-CTA-per-item kernel above, for every ring depth 2..4.
-// The 17th warp drops the register budget from 113 to 96 per thread (5 warps on one scheduler partition)
-// and the kernel is bound by store back-pressure, not by the refill latency this form removes.  It is
-// kept, bit-identical and tested, as the record of that experiment.
-// One CTA per SM slot walks the work items b, b + grid, b + 2*grid, ...; a dedicated PRODUCER warp runs
-// ahead of the consumer warps and keeps the TMA ring full across item boundaries, so that neither the
-// first loads of an item nor the refill of a stage ever wait for a consumer warp's own progress (in the
-// one-CTA-per-item kernel above thread 0 refills a stage only after its warp has finished the step, and
-// every CTA starts with an empty ring while its SM idles).  Steps are numbered globally per CTA
-// (g = 0, 1, ...): object stage g % RING, mbarrier parity (g / RING) & 1; the subject chunk of item i
-// lives in subject stage i & 1 and rides on the `full` barrier of the item's first step.  A consumer
-// warp releases a stage (and, with the last step of an item, that item's subject stage) by arriving on
-// `empty`; the producer consumes those completions strictly in step order.
-#ifndef TSPN_GEO_PRING
-#define TSPN_GEO_PRING 4
-#endif
-template <int THREADS>
-struct GeoPCfg {
-    using Base = GeoCfg<THREADS>;
-    static constexpr int RING = TSPN_GEO_PRING;
-    static constexpr int SUBJ = 2;
-    static constexpr int WARPS = Base::WARPS;
-    static constexpr int STAGE_BYTES = Base::STAGE_BYTES;
-    static constexpr int MIN_CTAS = Base::MIN_CTAS;
-    static constexpr int TAIL_BYTES = (2 * RING * 8 + GEO_OG * (WARPS * 3 * 8 + 8) + 127) / 128 * 128;
-    static constexpr int SMEM_USED = (SUBJ + RING) * STAGE_BYTES + TAIL_BYTES;
-    static constexpr int SMEM_PIN = 227 * 1024 / (MIN_CTAS + 1) + 1024;
-    static constexpr int SMEM_BYTES = SMEM_USED > SMEM_PIN ? SMEM_USED : SMEM_PIN;
-    static_assert((SMEM_BYTES + 1024) * MIN_CTAS <= 228 * 1024, "the stages of MIN_CTAS CTAs must fit one SM");
-};
-
-struct GeoItem {
-    int n, tp, s, k0, nobj, c;
-    int64_t tb, trk_off, box_row0, pair0, geo_off;
-};
-
-template <int CHUNK>
-__device__ __forceinline__ GeoItem geo_decode_item(const int64_t* __restrict__ table, int nv, int64_t item) {
-    GeoItem it;
-    const int v = find_video(table, nv, TSPN_VT_ITEM_OFF, item);
-    const int64_t* row = table + (int64_t)v * TSPN_VT_COLS;
-    it.n = (int)row[TSPN_VT_N];
-    const int t_len = (int)row[TSPN_VT_T];
-    it.tp = (int)row[TSPN_VT_TP];
-    it.tb = row[TSPN_VT_TB];
-    it.trk_off = row[TSPN_VT_TRK_OFF];
-    const int groups = (it.n - 1 + GEO_OG - 1) / GEO_OG;
-    const int nchunks = (t_len + CHUNK - 1) / CHUNK;
-    const int local = (int)(item - row[TSPN_VT_ITEM_OFF]);
-    it.c = local % nchunks;
-    const int sg = local / nchunks;
-    it.s = sg / groups;
-    it.k0 = (sg - it.s * groups) * GEO_OG;
-    it.nobj = min(GEO_OG, it.n - 1 - it.k0);
-    it.box_row0 = row[TSPN_VT_BOX_OFF];                      // multiple of 8
-    it.pair0 = row[TSPN_VT_PAIR_OFF] + (int64_t)it.s * (it.n - 1) + it.k0;
-    it.geo_off = row[TSPN_VT_GEO_OFF];
-    return it;
-}
-
-__device__ __forceinline__ void consumer_barrier(int threads) {
-    asm volatile("bar.sync 1, %0;" ::"r"(threads) : "memory");
-}
-
-template <int THREADS, bool WRITE_GEO, bool CLIP>
-__global__ void __launch_bounds__(THREADS + 32, GeoPCfg<THREADS>::MIN_CTAS)
-pair_geo_persistent_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __restrict__ table, int nv,
-                           int64_t total_items, const int32_t* __restrict__ span, float* __restrict__ geo,
-                           unsigned long long* __restrict__ fx) {
-    using Cfg = GeoCfg<THREADS>;
-    using PCfg = GeoPCfg<THREADS>;
-    constexpr int CHUNK = Cfg::CHUNK, WARPS = Cfg::WARPS, STAGE_BYTES = Cfg::STAGE_BYTES;
-    constexpr int TX_BYTES = Cfg::TX_BYTES, SPLIT = Cfg::SPLIT, RING = PCfg::RING;
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* const s_stage0 = smem;                                           // [2] subject stages
-    uint8_t* const o_stage0 = smem + PCfg::SUBJ * STAGE_BYTES;                // [RING] object stages
-    uint64_t* const full = reinterpret_cast<uint64_t*>(smem + (PCfg::SUBJ + RING) * STAGE_BYTES);   // [RING]
-    uint64_t* const empty = full + RING;                                                           // [RING]
-    unsigned long long* const acc = reinterpret_cast<unsigned long long*>(empty + RING);     // [OG][WARPS][3]
-    int2* const owin = reinterpret_cast<int2*>(acc + GEO_OG * WARPS * 3);                    // [OG] overlap windows
-
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
-    if (tid == 0) {
-#pragma unroll
-        for (int i = 0; i < RING; ++i) {
-            mbar_init(&full[i], 1);
-            mbar_init(&empty[i], WARPS);
-        }
-        fence_mbar_init();
-    }
-    __syncthreads();
-
-    if (warp == WARPS) {
-        // ---- producer ---------------------------------------------------------------------------
-        if (lane != 0) return;
-        tma_prefetch_desc(&box_map);
-        uint32_t g = 0;                    // next step to load
-        uint32_t released = 0;             // steps [0, released) are known to be released by every consumer warp
-        uint32_t end_prev1 = 0, end_prev2 = 0;     // one past the last step of item i-1 / i-2
-        int parity = 0;
-        for (int64_t item = blockIdx.x; item < total_items; item += gridDim.x, parity ^= 1) {
-            const GeoItem it = geo_decode_item<CHUNK>(table, nv, item);
-            uint8_t* const s_stage = s_stage0 + parity * STAGE_BYTES;
-            for (int q = 0; q < it.nobj; ++q, ++g) {
-                uint32_t need = g >= (uint32_t)RING ? g - RING + 1 : 0u;     // object stage g % RING is free
-                if (q == 0 && end_prev2 > need) need = end_prev2;              // subject stage i & 1 is free
-                while (released < need) {
-                    mbar_wait(&empty[released % RING], (released / RING) & 1);
-                    ++released;
-                }
-                const int st = g % RING;
-                const int k = it.k0 + q;
-                const int o = k + (k >= it.s ? 1 : 0);
-                mbar_expect_tx(&full[st], q == 0 ? 2 * TX_BYTES : TX_BYTES);
-#pragma unroll
-                for (int h = 0; h < SPLIT; ++h) {                 // second half: rows CHUNK/16 .. CHUNK/8 (+ halo)
-                    const int r_off = h * (CHUNK / 16);
-                    if (q == 0)
-                        tma_load_2d(s_stage + r_off * 128, &box_map, 0,
-                                    (int)((it.box_row0 + (int64_t)it.s * it.tb + (int64_t)it.c * CHUNK) >> 3) + r_off,
-                                    &full[st]);
-                    tma_load_2d(o_stage0 + st * STAGE_BYTES + r_off * 128, &box_map, 0,
-                                (int)((it.box_row0 + (int64_t)o * it.tb + (int64_t)it.c * CHUNK) >> 3) + r_off,
-                                &full[st]);
-                }
-            }
-            end_prev2 = end_prev1;
-            end_prev1 = g;
-        }
-        return;
-    }
-
-    // ---- consumers ------------------------------------------------------------------------------
-    int st = 0, ph = 0;                                      // ring stage of the current step and its parity
-    int parity = 0;
-    for (int64_t item = blockIdx.x; item < total_items; item += gridDim.x, parity ^= 1) {
-        const GeoItem it = geo_decode_item<CHUNK>(table, nv, item);
-        if (tid < it.nobj) {
-            const int ps = __ldg(span + 2 * (it.trk_off + it.s)), pe = __ldg(span + 2 * (it.trk_off + it.s) + 1);
-            const int k = it.k0 + tid;
-            const int o = k + (k >= it.s ? 1 : 0);
-            const int qs = __ldg(span + 2 * (it.trk_off + o)), qe = __ldg(span + 2 * (it.trk_off + o) + 1);
-            owin[tid] = make_int2(max(ps, qs), min(pe, qe));
-        }
-        consumer_barrier(THREADS);           // owin visible; the previous item's acc has been reduced
-
-        const uint32_t ss = smem_u32(s_stage0 + parity * STAGE_BYTES);
-        float* g = WRITE_GEO ? geo + it.geo_off + ((int64_t)(it.s * (it.n - 1) + it.k0) * TSPN_GEO_CHANNELS) * it.tp +
-                                   (int64_t)it.c * CHUNK
-                             : nullptr;
-        for (int q = 0; q < it.nobj; ++q) {
-            const int2 win = owin[q];
-            const int j0 = (((warp + (GEO_ROTATE ? q : 0)) & (WARPS - 1)) * 32 + lane) * GEO_FPT;   // rotating blocks
-            const int t0 = it.c * CHUNK + j0;
-            mbar_wait(&full[st], ph);
-            float fsum_i, fsum_s, fsum_o;
-            float out[TSPN_GEO_CHANNELS][GEO_FPT];
-            geo_step<CLIP>(ss, smem_u32(o_stage0 + st * STAGE_BYTES), j0, t0, win.x, win.y, out, fsum_i, fsum_s, fsum_o);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[st]);              // this warp is done with the stage (and subject)
-            if (WRITE_GEO) {
-                if (t0 < it.tp) {
-#pragma unroll
-                    for (int ch = 0; ch < TSPN_GEO_CHANNELS; ++ch)
-                        st_stream_f4(g + (int64_t)ch * it.tp + j0,
-                                     make_float4(out[ch][0], out[ch][1], out[ch][2], out[ch][3]));
-                }
-                g += (int64_t)TSPN_GEO_CHANNELS * it.tp;
-            }
-            const unsigned long long tot_i = warp_sum_fx(fsum_i);
-            unsigned long long tot_s = 0ull, tot_o = 0ull;
-            if (CLIP) {
-                tot_s = warp_sum_fx(fsum_s);
-                tot_o = warp_sum_fx(fsum_o);
-            }
-            if (lane == 0) {          // every (object, warp) slot is written exactly once per item
-                unsigned long long* slot = acc + (q * WARPS + warp) * 3;
-                slot[0] = tot_i;
-                slot[1] = tot_s;
-                slot[2] = tot_o;
-            }
-            if (++st == RING) { st = 0; ph ^= 1; }
-        }
-        consumer_barrier(THREADS);           // every slot of this item is written
-        for (int i3 = tid; i3 < it.nobj * 3; i3 += THREADS) {
-            const int q = i3 / 3, w = i3 - 3 * q;
-            unsigned long long val = 0ull;
-#pragma unroll
-            for (int i = 0; i < WARPS; ++i) val += acc[(q * WARPS + i) * 3 + w];
-            if (val) atomicAdd(fx + (it.pair0 + q) * 3 + w, val);
-        }
+        const unsigned long long val = acc[i3];
+        if (val) atomicAdd(fx + pair0 * 3 + i3, val);
     }
 }
 
@@ -750,12 +560,11 @@ __global__ void __launch_bounds__(256) enumerate_pairs_kernel(const int64_t* __r
     pairs[2 * p + 1] = k + (k >= s ? 1 : 0);
 }
 
-template <int THREADS>
+template <int THREADS, bool DENSE>
 static int launch_pair_geo(const int64_t* d_table, int num_videos, int64_t total_items, int64_t total_boxes,
                            const float* d_boxes, const int32_t* d_span, float* d_geo, unsigned long long* fx,
-                           bool clip, bool per_item, cudaStream_t st) {
-    using Cfg = GeoCfg<THREADS>;
-    using PCfg = GeoPCfg<THREADS>;
+                           bool clip, cudaStream_t st) {
+    using Cfg = GeoCfg<THREADS, DENSE>;
     // boxes viewed as a 2-D tensor: rows of 8 boxes (32 floats = 128 B)
     CUtensorMap map;
     const uint64_t dims[2] = {32, (uint64_t)(total_boxes / 8)};
@@ -766,19 +575,10 @@ static int launch_pair_geo(const int64_t* d_table, int num_videos, int64_t total
     if (rc != TSPN_OK) return rc;
 #define TSPN_LAUNCH_GEO(W, C)                                                                                  \
     do {                                                                                                       \
-        if (per_item) {                                                                                        \
-            TSPN_CUDA_OK(cudaFuncSetAttribute(pair_geo_kernel<THREADS, W, C>,                                  \
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));  \
-            pair_geo_kernel<THREADS, W, C><<<(unsigned)total_items, THREADS, Cfg::SMEM_BYTES, st>>>(           \
-                map, d_table, num_videos, d_span, d_geo, fx);                                                  \
-        } else {                                                                                               \
-            const int64_t slots = (int64_t)num_sms() * PCfg::MIN_CTAS;                                         \
-            const unsigned grid = (unsigned)(total_items < slots ? total_items : slots);                       \
-            TSPN_CUDA_OK(cudaFuncSetAttribute(pair_geo_persistent_kernel<THREADS, W, C>,                       \
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg::SMEM_BYTES)); \
-            pair_geo_persistent_kernel<THREADS, W, C><<<grid, THREADS + 32, PCfg::SMEM_BYTES, st>>>(           \
-                map, d_table, num_videos, total_items, d_span, d_geo, fx);                                     \
-        }                                                                                                      \
+        TSPN_CUDA_OK(cudaFuncSetAttribute(pair_geo_kernel<THREADS, W, C, DENSE>,                               \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));      \
+        pair_geo_kernel<THREADS, W, C, DENSE><<<(unsigned)total_items, THREADS, Cfg::SMEM_BYTES, st>>>(        \
+            map, d_table, num_videos, d_span, d_geo, fx);                                                      \
     } while (0)
     if (d_geo) {
         if (clip) TSPN_LAUNCH_GEO(true, true); else TSPN_LAUNCH_GEO(true, false);
@@ -854,10 +654,16 @@ int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_ite
         TSPN_CUDA_OK(cudaGetLastError());
     }
     int rc = TSPN_OK;
-    const bool per_item = (flags & TSPN_GEO_PERSISTENT_CTAS) == 0;
-    if (geo_chunk == 512) rc = launch_pair_geo<128>(d_table, num_videos, total_items, total_boxes, d_boxes, d_span, d_geo, fx, clip, per_item, st);
-    else if (geo_chunk == 1024) rc = launch_pair_geo<256>(d_table, num_videos, total_items, total_boxes, d_boxes, d_span, d_geo, fx, clip, per_item, st);
-    else rc = launch_pair_geo<512>(d_table, num_videos, total_items, total_boxes, d_boxes, d_span, d_geo, fx, clip, per_item, st);
+    const bool dense = (flags & TSPN_GEO_DENSE_CTAS) != 0;
+#define TSPN_GEO_SHAPE(T)                                                                                          \
+    (dense ? launch_pair_geo<T, true>(d_table, num_videos, total_items, total_boxes, d_boxes, d_span, d_geo, fx,   \
+                                      clip, st)                                                                    \
+           : launch_pair_geo<T, false>(d_table, num_videos, total_items, total_boxes, d_boxes, d_span, d_geo, fx,  \
+                                       clip, st))
+    if (geo_chunk == 512) rc = TSPN_GEO_SHAPE(128);
+    else if (geo_chunk == 1024) rc = TSPN_GEO_SHAPE(256);
+    else rc = TSPN_GEO_SHAPE(512);
+#undef TSPN_GEO_SHAPE
     if (rc != TSPN_OK) return rc;
     const unsigned fblocks = (unsigned)((total_pairs + 255) / 256);
     if (clip)

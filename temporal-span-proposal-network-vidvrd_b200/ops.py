@@ -65,13 +65,13 @@ def enumerate_pairs(batch: DeviceBatch) -> torch.Tensor:
 
 def pair_geometry(batch: DeviceBatch, write_geo: bool = True, clipped: bool = False,
                   out: Optional[Dict[str, torch.Tensor]] = None,
-                  persistent_ctas: Optional[bool] = None) -> Dict[str, torch.Tensor]:
+                  dense_ctas: Optional[bool] = None) -> Dict[str, torch.Tensor]:
     """All-pairs per-frame geometry + vIoU/tIoU/overlap (trajectory.py:85-141, common.py:65-106).
-    ``persistent_ctas`` selects the persistent producer-warp kernel instead of the default one CTA per work
-    item (bit-identical results, measured slower; A/B timing only - default from the environment variable
-    TSPN_GEO_PERSISTENT)."""
-    if persistent_ctas is None:
-        persistent_ctas = os.environ.get("TSPN_GEO_PERSISTENT", "0") == "1"
+    ``dense_ctas`` selects the 1024-threads-per-SM shape of the kernel (2-stage ring, 64 registers) instead of
+    the default ~512 threads per SM (bit-identical results, measured slower; A/B timing only - default from
+    the environment variable TSPN_GEO_DENSE)."""
+    if dense_ctas is None:
+        dense_ctas = os.environ.get("TSPN_GEO_DENSE", "0") == "1"
     dev = batch.device
     tot = batch.totals
     p = batch.total_pairs
@@ -88,7 +88,7 @@ def pair_geometry(batch: DeviceBatch, write_geo: bool = True, clipped: bool = Fa
         batch.total_tracklets, batch.total_pairs,
         int(tot[_lib.TOT_BOXES]), ptr(batch.boxes), ptr(batch.span), ptr(out.get("geo")), ptr(out["viou"]),
         ptr(out["tiou"]), ptr(out["overlap"]),
-        (_lib.VIOU_CLIPPED if clipped else _lib.VIOU_FULL) | (_lib.GEO_PERSISTENT_CTAS if persistent_ctas else 0),
+        (_lib.VIOU_CLIPPED if clipped else _lib.VIOU_FULL) | (_lib.GEO_DENSE_CTAS if dense_ctas else 0),
         ptr(out["workspace"]), stream_ptr()), "tspn_pair_geo_viou")
     _count(3)       # volumes + accumulator zeroing, pair kernel, per-pair finalize
     return out

@@ -88,19 +88,19 @@ def test_pair_geometry_kernel_shapes(shapes, chunk, clip):
     [(20, 300, 0), (5, 37, 11), (9, 512, 8), (2, 1, 3)],                  # 128-thread CTAs
     [(7, 513, 7), (4, 1024, 9), (3, 700, 1)],                             # 256-thread CTAs
     [(3, 4100, 2), (70, 40, 3), (4, 2049, 4), (5, 2048, 5)],              # 512-thread CTAs, two object groups
-    [(2, 9, 1)] * 700,                                                    # 1400 one-object items: more items than
-                                                                          # CTA slots, every item shorter than the ring
+    [(2, 9, 1)] * 700,                                                    # 1400 one-object items, each shorter than
+                                                                          # the TMA ring
     [(3, 600, 4), (2, 2100, 5), (40, 2100, 6)],                           # items of 1, 2 and 39 objects interleaved
 ])
 @pytest.mark.parametrize("clip", [False, True])
-def test_persistent_and_per_item_kernels_are_bit_identical(shapes, clip):
-    """The opt-in persistent kernel (producer warp, TMA ring carried across work items) against the
-    default one-CTA-per-item kernel: every output bit for bit."""
+def test_dense_and_sparse_kernel_shapes_are_bit_identical(shapes, clip):
+    """The two occupancy shapes of the pair-geometry kernel (1024 threads per SM / 2-stage ring / 64 registers
+    against ~512 threads / 3-stage ring): every output bit for bit."""
     vids = [synth.make_video(n, t, 35, seed=s) for n, t, s in shapes]
     batch = _batch(vids)
-    a = ops.pair_geometry(batch, write_geo=True, clipped=clip, persistent_ctas=True)
-    b = ops.pair_geometry(batch, write_geo=True, clipped=clip, persistent_ctas=False)
-    c = ops.pair_geometry(batch, write_geo=False, clipped=clip, persistent_ctas=True)
+    a = ops.pair_geometry(batch, write_geo=True, clipped=clip, dense_ctas=False)
+    b = ops.pair_geometry(batch, write_geo=True, clipped=clip, dense_ctas=True)
+    c = ops.pair_geometry(batch, write_geo=False, clipped=clip, dense_ctas=False)
     torch.cuda.synchronize()
     for key in ("geo", "viou", "tiou", "overlap"):
         assert torch.equal(a[key], b[key]), key
