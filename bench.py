@@ -45,9 +45,11 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="launch every kernel from the host instead of CUDA graphs")
     ap.add_argument("--depth", type=int, default=3, help="batches in flight in the end-to-end serving loop")
+    ap.add_argument("--fp32-transport", action="store_true",
+                    help="ship boxes / motion histograms as fp32 instead of the lossless compact u16 / u8 form")
     ap.add_argument("--three-graphs", action="store_true",
                     help="replay the step as three CUDA graphs joined on the host instead of one graph")
-    ap.add_argument("--compute-streams", type=int, default=1, choices=[1, 2],
+    ap.add_argument("--compute-streams", type=int, default=2, choices=[1, 2],
                     help="compute streams of the serving loop (2: the tail of step i overlaps the geometry of i+1)")
     return ap.parse_args()
 
@@ -272,7 +274,7 @@ def run_ours(args, rank, world, local_rank):
     stage = PairStage(cfg)
     stage.load_weights(sd, dev)
     videos = [synth.make_video(n, t, c, seed=100000 * rank + i) for i in range(args.videos)]
-    host = HostBatch.from_videos(videos)
+    host = HostBatch.from_videos(videos, compact=not args.fp32_transport)
     pairs_per_step = sum(v.n_pairs for v in videos)
 
     # ---- resident-input steps ------------------------------------------------------------------
@@ -381,8 +383,10 @@ def run_ours(args, rank, world, local_rank):
                    "e2e_pipeline": "tspn_b200.serving.PipelinedStage, depth %d: one H2D copy of the pinned input "
                                    "arena per step; H2D(i+1..) and D2H(i-1) overlap the kernels of step i; %d compute "
                                    "stream(s)" % (args.depth, args.compute_streams),
+                   "h2d_transport": "u16 boxes + u8 motion counts (lossless for these inputs), expanded on the device"
+                                    if host.boxes_compact and host.motion_compact else "fp32",
                    "multi_gpu_collective": "all_gather of [V,200,8] int32 triplet records per step (e2e loop)"},
-        "roofline": {"bound": "hbm", "kernel": "pair_geo_kernel (+ tracklet_volume_kernel)",
+        "roofline": {"bound": "hbm", "kernel": "pair_geo_kernel (CUDA events immediately around this launch)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": measured_traffic(args.videos), "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                      "avg_launch_ms": geo_avg_ms, "share_of_step": geo_avg_ms / (float(np.mean(step_ms)))},

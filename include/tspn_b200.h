@@ -96,6 +96,12 @@ extern "C" {
 #define TSPN_GEO_DENSE_CTAS 2   /* tspn_pair_geo_viou: 1024 threads per SM with a 2-stage TMA ring and 64 registers
                                   instead of the default ~512 threads per SM, 3 stages, 103 registers (same
                                   results bit for bit; measured slower, kept for A/B - DESIGN.md section 4.1) */
+/* tspn_pair_geo_viou runs three kernels: PRE (per-tracklet volumes + zeroing of the per-pair sums), MAIN (the
+ * pair kernel), POST (per-pair vIoU / tIoU / overlap).  With none of these bits set all three run; a caller
+ * that wants to time the pair kernel alone issues the phases as separate calls (same arguments). */
+#define TSPN_GEO_PHASE_PRE 8
+#define TSPN_GEO_PHASE_MAIN 16
+#define TSPN_GEO_PHASE_POST 32
 #define TSPN_TOPK_KEEP_DIAGONAL 0    /* reference behaviour, ppn.py:84-85 (quirk Q1) */
 #define TSPN_TOPK_EXCLUDE_DIAGONAL 1 /* survivors are real pairs (sparsify mode) */
 #define TSPN_PREC_FP32_EXACT 0 /* CUDA cores, fixed k-ascending fma order: bit-reproducible */
@@ -168,6 +174,11 @@ int tspn_viou_pairs_f64(const float* d_pool, const int64_t* d_traj_off, const in
  * L1-normalise each 1000-wide BoW block (lib/dataset/vrdataset.py:227-236 with
  * lib/utils/miscellaneous.py:32-35). */
 int tspn_normalize_motion(const float* d_motion, int64_t n_tracklets, float* d_out, void* stream);
+/* Compact host->device transport (batch.py packs these when the values allow it, losslessly): motion
+ * histograms as u8 counts [n][4000] (normalised exactly like tspn_normalize_motion: the integer sum is
+ * exact), boxes as u16 pixel coordinates [n_boxes][4] expanded to the fp32 layout the kernels read. */
+int tspn_normalize_motion_u8(const uint8_t* d_motion, int64_t n_tracklets, float* d_out, void* stream);
+int tspn_unpack_boxes_u16(const uint16_t* d_src, int64_t n_boxes, float* d_dst, void* stream);
 /* Build rows [2C | 8000 motion | 3000 relative] (lib/dataset/vrdataset.py:219-243); the last
  * 3000 columns are the adaptive-average-pooled geometry ([SPEC] s4).  d_rows: global pair rows
  * to build (int64, NULL = all total_pairs rows in order).  Output row stride ld_feat floats

@@ -27,6 +27,7 @@ MOTION_DIM = 4000
 REL_DIM = 3000
 VIOU_FULL, VIOU_CLIPPED = 0, 1
 GEO_DENSE_CTAS = 2
+GEO_PHASE_PRE, GEO_PHASE_MAIN, GEO_PHASE_POST = 8, 16, 32
 TOPK_KEEP_DIAGONAL, TOPK_EXCLUDE_DIAGONAL = 0, 1
 PREC_FP32_EXACT, PREC_TENSOR = 0, 1
 
@@ -48,6 +49,8 @@ SIGNATURES = {
     "tspn_viou_pairs_workspace_bytes": (c_int64, [c_int64]),
     "tspn_viou_pairs_f64": (c_int, [P, P, P, P, c_int64, P, P, c_int64, c_int, P, P, P]),
     "tspn_normalize_motion": (c_int, [P, c_int64, P, P]),
+    "tspn_normalize_motion_u8": (c_int, [P, c_int64, P, P]),
+    "tspn_unpack_boxes_u16": (c_int, [P, c_int64, P, P]),
     "tspn_assemble_features": (c_int, [P, c_int, c_int64, c_int, P, c_int, P, P, P, P, c_int64, P, c_int64, P, c_int64, P]),
     "tspn_relationness_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
     "tspn_relationness": (c_int, [P, c_int, c_int64, P, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P]),

@@ -58,7 +58,12 @@ class HostBatch:
     """Packed, pinned host image of a batch of videos."""
 
     def __init__(self, boxes: Sequence, span: Sequence, cls: Optional[Sequence] = None,
-                 motion: Optional[Sequence] = None, pin: bool = True):
+                 motion: Optional[Sequence] = None, pin: bool = True, compact: bool = True):
+        """``compact``: ship boxes as u16 pixel coordinates and motion histograms as u8 counts when every
+        value is exactly representable (integer boxes in [0, 65535], integer counts in [0, 255]) - lossless,
+        expanded on the device by ``tspn_unpack_boxes_u16`` / ``tspn_normalize_motion_u8``; otherwise (or
+        with ``compact=False``) the fields travel as fp32.  The serving loop is PCIe-bound, and these two
+        fields are 99 % of a batch's bytes."""
         boxes = [_np(b, np.float32) for b in boxes]
         span = [_np(s, np.int32).reshape(-1, 2) for s in span]
         assert len(boxes) == len(span)
@@ -77,21 +82,27 @@ class HostBatch:
             cls = [_np(c, np.float32) for c in cls]
         if motion is not None:
             motion = [_np(m, np.float32) for m in motion]
+        def exact_ints(arrays, hi):
+            return all(a.size == 0 or (a.min() >= 0 and a.max() <= hi and np.array_equal(a, np.rint(a)))
+                       for a in arrays)
+        self.boxes_compact = bool(compact) and exact_ints(boxes, 65535)
+        self.motion_compact = bool(compact) and motion is not None and exact_ints(motion, 255)
         # One pinned arena holds every field (256-byte aligned segments), so that a step's inputs cross
         # PCIe as ONE copy; the fields below are views of it.  DeviceBatch mirrors the layout in HBM.
         self.layout = _arena_layout([
             ("table", (len(self.n), VT_COLS), torch.int64),
-            ("boxes", (int(tot[TOT_BOXES]), 4), torch.float32),
+            ("boxes", (int(tot[TOT_BOXES]), 4), torch.int16 if self.boxes_compact else torch.float32),
             ("span", (n_trk, 2), torch.int32),
             ("cls", (n_trk, int(cls[0].shape[1])), torch.float32) if cls is not None else None,
-            ("motion", (n_trk, _lib.MOTION_DIM), torch.float32) if motion is not None else None,
+            ("motion", (n_trk, _lib.MOTION_DIM), torch.uint8 if self.motion_compact else torch.float32)
+            if motion is not None else None,
         ])
         self.arena = torch.zeros(self.layout["bytes"], dtype=torch.uint8)
         if use_pin:
             self.arena = self.arena.pin_memory()
         views = _arena_views(self.arena, self.layout)
-        self.boxes, self.span = views["boxes"], views["span"]
-        bview = self.boxes.numpy()
+        self.boxes, self.span = views["boxes"], views["span"]     # boxes: fp32, or the u16 bit patterns (int16 view)
+        bview = self.boxes.numpy().view(np.uint16) if self.boxes_compact else self.boxes.numpy()
         sview = self.span.numpy()
         for v, (b, s) in enumerate(zip(boxes, span)):
             row = self.table[v]
@@ -111,10 +122,10 @@ class HostBatch:
         self.table_t.numpy()[:] = np.ascontiguousarray(self.table).reshape(-1, VT_COLS)
 
     @classmethod
-    def from_videos(cls, videos, pin: bool = True) -> "HostBatch":
+    def from_videos(cls, videos, pin: bool = True, compact: bool = True) -> "HostBatch":
         """From ``tspn_b200.synth.VideoTracklets`` (or anything with boxes/span/cls/motion)."""
         return cls([v.boxes for v in videos], [v.span for v in videos], [v.cls for v in videos],
-                   [v.motion for v in videos], pin=pin)
+                   [v.motion for v in videos], pin=pin, compact=compact)
 
     @property
     def num_videos(self) -> int:
@@ -140,8 +151,26 @@ class DeviceBatch:
         self.layout = host.layout
         self.arena = host.arena.to(dev, non_blocking=non_blocking)        # one H2D copy
         views = _arena_views(self.arena, self.layout)
-        self.table, self.boxes, self.span = views["table"], views["boxes"], views["span"]
-        self.cls, self.motion = views.get("cls"), views.get("motion")
+        self.table, self.span = views["table"], views["span"]
+        self.cls, self.motion = views.get("cls"), views.get("motion")     # motion: fp32, or u8 counts (compact)
+        if host.boxes_compact:
+            # u16 coordinates in the arena, expanded right behind the copy (same stream) into this fp32 buffer -
+            # the layout the kernels and the TMA tensor map read.  The expansion belongs to the upload, not to
+            # the step: in the serving loop it runs on the H2D stream, off the kernels' critical path.
+            self.boxes_u16 = views["boxes"]
+            self.boxes = torch.empty(self.boxes_u16.shape, dtype=torch.float32, device=dev)
+            self._unpack()
+        else:
+            self.boxes_u16 = None
+            self.boxes = views["boxes"]
+
+    def _unpack(self) -> None:
+        if self.boxes_u16 is not None and self.boxes.shape[0] > 0:
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.load().tspn_unpack_boxes_u16(self.boxes_u16.data_ptr(), self.boxes.shape[0],
+                                                             self.boxes.data_ptr(),
+                                                             torch.cuda.current_stream(self.device).cuda_stream),
+                           "tspn_unpack_boxes_u16")
 
     def copy_from(self, host: HostBatch) -> "DeviceBatch":
         """Refill the device buffers from another host batch of the same layout (non-blocking, on the
@@ -150,6 +179,7 @@ class DeviceBatch:
             raise ValueError("copy_from needs a host batch with the same per-video shapes and fields")
         self.host = host
         self.arena.copy_(host.arena, non_blocking=True)                   # one H2D copy
+        self._unpack()
         return self
 
     # sizes -----------------------------------------------------------------------------

@@ -34,6 +34,39 @@ __global__ void __launch_bounds__(128) normalize_motion_kernel(const float* __re
     for (int i = lane; i < TSPN_MOTION_BLOCK; i += 32) dst[i] = __ldg(src + i) / s;
 }
 
+// u8 counts -> L1-normalised fp32 blocks (compact transport of the motion histograms, see batch.py)
+__global__ void __launch_bounds__(128) normalize_motion_u8_kernel(const uint8_t* __restrict__ motion, int64_t n_blocks,
+                                                                  float* __restrict__ out) {
+    const int64_t blk = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (blk >= n_blocks) return;
+    const int lane = threadIdx.x & 31;
+    const uint8_t* src = motion + blk * TSPN_MOTION_BLOCK;       // 1000 bytes: 4-byte aligned
+    float* dst = out + blk * TSPN_MOTION_BLOCK;
+    // integer counts: the fp32 sum is exact (<= 255 000) and equals the reference's sum of |x| in any order
+    uint32_t isum = 0;
+    for (int i = lane; i < TSPN_MOTION_BLOCK / 4; i += 32) {
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(src) + i);
+        isum += (w & 0xffu) + ((w >> 8) & 0xffu) + ((w >> 16) & 0xffu) + (w >> 24);
+    }
+    isum = __reduce_add_sync(0xffffffffu, isum);
+    const float s = isum ? (float)isum : 1.0f;                   // miscellaneous.py:34 - empty histograms stay zero
+    for (int i = lane; i < TSPN_MOTION_BLOCK / 4; i += 32) {
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(src) + i);
+        const float4 v = make_float4((float)(w & 0xffu) / s, (float)((w >> 8) & 0xffu) / s,
+                                     (float)((w >> 16) & 0xffu) / s, (float)(w >> 24) / s);
+        *reinterpret_cast<float4*>(dst + 4 * i) = v;
+    }
+}
+
+// u16 pixel coordinates -> fp32 boxes (compact transport of integer boxes)
+__global__ void __launch_bounds__(256) unpack_boxes_u16_kernel(const uint2* __restrict__ src, int64_t n_boxes,
+                                                               float4* __restrict__ dst) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_boxes; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint2 w = __ldg(src + i);
+        dst[i] = make_float4((float)(w.x & 0xffffu), (float)(w.x >> 16), (float)(w.y & 0xffffu), (float)(w.y >> 16));
+    }
+}
+
 constexpr int ASM_THREADS = 256;
 constexpr int ASM_STAGED = 2;      // geometry channels staged per round: (0,1) position, (2,3) size, (5,6) motion
 // Shared memory of one CTA: the overlap windows of two pooled channels (cap floats each, cap = the
@@ -205,6 +238,36 @@ int tspn_normalize_motion(const float* d_motion, int64_t n_tracklets, float* d_o
     const int64_t n_blocks = n_tracklets * (TSPN_MOTION_DIM / TSPN_MOTION_BLOCK);
     normalize_motion_kernel<<<(unsigned)((n_blocks + 3) / 4), 128, 0, (cudaStream_t)stream>>>(d_motion, n_blocks,
                                                                                               d_out);
+    TSPN_CUDA_OK(cudaGetLastError());
+    return TSPN_OK;
+}
+
+int tspn_normalize_motion_u8(const uint8_t* d_motion, int64_t n_tracklets, float* d_out, void* stream) {
+    TSPN_ARCH_OK();
+    TSPN_REQUIRE(n_tracklets >= 0, TSPN_EBADARG, "tspn_normalize_motion_u8: negative size");
+    if (n_tracklets == 0) return TSPN_OK;
+    TSPN_REQUIRE(d_motion && d_out, TSPN_EBADARG, "tspn_normalize_motion_u8: null pointer");
+    TSPN_REQUIRE((reinterpret_cast<uintptr_t>(d_motion) & 3u) == 0 && aligned16(d_out), TSPN_EALIGN,
+                 "tspn_normalize_motion_u8: motion must be 4-byte and out 16-byte aligned");
+    const int64_t n_blocks = n_tracklets * (TSPN_MOTION_DIM / TSPN_MOTION_BLOCK);
+    normalize_motion_u8_kernel<<<(unsigned)((n_blocks + 3) / 4), 128, 0, (cudaStream_t)stream>>>(d_motion, n_blocks,
+                                                                                                 d_out);
+    TSPN_CUDA_OK(cudaGetLastError());
+    return TSPN_OK;
+}
+
+int tspn_unpack_boxes_u16(const uint16_t* d_src, int64_t n_boxes, float* d_dst, void* stream) {
+    TSPN_ARCH_OK();
+    TSPN_REQUIRE(n_boxes >= 0, TSPN_EBADARG, "tspn_unpack_boxes_u16: negative size");
+    if (n_boxes == 0) return TSPN_OK;
+    TSPN_REQUIRE(d_src && d_dst, TSPN_EBADARG, "tspn_unpack_boxes_u16: null pointer");
+    TSPN_REQUIRE((reinterpret_cast<uintptr_t>(d_src) & 7u) == 0 && aligned16(d_dst), TSPN_EALIGN,
+                 "tspn_unpack_boxes_u16: src must be 8-byte and dst 16-byte aligned");
+    int64_t blocks = (n_boxes + 255) / 256;
+    const int64_t cap = 16 * (int64_t)num_sms();
+    if (blocks > cap) blocks = cap;
+    unpack_boxes_u16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint2*>(d_src), n_boxes, reinterpret_cast<float4*>(d_dst));
     TSPN_CUDA_OK(cudaGetLastError());
     return TSPN_OK;
 }

@@ -640,8 +640,10 @@ int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_ite
     unsigned long long* fx =
         reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(d_workspace) + geo_ws_vol_bytes(total_tracklets));
     const bool clip = (flags & TSPN_VIOU_CLIPPED) != 0;
-    {
-        // volumes (one warp per tracklet) + zeroing of the fixed-point accumulators (grid-stride)
+    const int phases = flags & (TSPN_GEO_PHASE_PRE | TSPN_GEO_PHASE_MAIN | TSPN_GEO_PHASE_POST);
+    const bool all = phases == 0;
+    if (all || (phases & TSPN_GEO_PHASE_PRE)) {
+        // volumes (one CTA per tracklet) + zeroing of the fixed-point accumulators (grid-stride)
         const int64_t cap = 16 * (int64_t)num_sms();
         const int64_t blocks_vol = clip ? 0 : total_tracklets;
         const int64_t blocks_zero = (total_pairs * 3 + 127) / 128;
@@ -653,26 +655,30 @@ int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_ite
                                                                 !clip, fx, total_pairs * 3);
         TSPN_CUDA_OK(cudaGetLastError());
     }
-    int rc = TSPN_OK;
-    const bool dense = (flags & TSPN_GEO_DENSE_CTAS) != 0;
+    if (all || (phases & TSPN_GEO_PHASE_MAIN)) {
+        int rc = TSPN_OK;
+        const bool dense = (flags & TSPN_GEO_DENSE_CTAS) != 0;
 #define TSPN_GEO_SHAPE(T)                                                                                          \
     (dense ? launch_pair_geo<T, true>(d_table, num_videos, total_items, total_boxes, d_boxes, d_span, d_geo, fx,   \
                                       clip, st)                                                                    \
            : launch_pair_geo<T, false>(d_table, num_videos, total_items, total_boxes, d_boxes, d_span, d_geo, fx,  \
                                        clip, st))
-    if (geo_chunk == 512) rc = TSPN_GEO_SHAPE(128);
-    else if (geo_chunk == 1024) rc = TSPN_GEO_SHAPE(256);
-    else rc = TSPN_GEO_SHAPE(512);
+        if (geo_chunk == 512) rc = TSPN_GEO_SHAPE(128);
+        else if (geo_chunk == 1024) rc = TSPN_GEO_SHAPE(256);
+        else rc = TSPN_GEO_SHAPE(512);
 #undef TSPN_GEO_SHAPE
-    if (rc != TSPN_OK) return rc;
-    const unsigned fblocks = (unsigned)((total_pairs + 255) / 256);
-    if (clip)
-        pair_finalize_kernel<true><<<fblocks, 256, 0, st>>>(d_table, num_videos, total_pairs, d_span, vol, fx, d_viou,
-                                                            d_tiou, d_overlap);
-    else
-        pair_finalize_kernel<false><<<fblocks, 256, 0, st>>>(d_table, num_videos, total_pairs, d_span, vol, fx, d_viou,
-                                                             d_tiou, d_overlap);
-    TSPN_CUDA_OK(cudaGetLastError());
+        if (rc != TSPN_OK) return rc;
+    }
+    if (all || (phases & TSPN_GEO_PHASE_POST)) {
+        const unsigned fblocks = (unsigned)((total_pairs + 255) / 256);
+        if (clip)
+            pair_finalize_kernel<true><<<fblocks, 256, 0, st>>>(d_table, num_videos, total_pairs, d_span, vol, fx,
+                                                                d_viou, d_tiou, d_overlap);
+        else
+            pair_finalize_kernel<false><<<fblocks, 256, 0, st>>>(d_table, num_videos, total_pairs, d_span, vol, fx,
+                                                                 d_viou, d_tiou, d_overlap);
+        TSPN_CUDA_OK(cudaGetLastError());
+    }
     return TSPN_OK;
 }
 

@@ -65,8 +65,10 @@ def enumerate_pairs(batch: DeviceBatch) -> torch.Tensor:
 
 def pair_geometry(batch: DeviceBatch, write_geo: bool = True, clipped: bool = False,
                   out: Optional[Dict[str, torch.Tensor]] = None,
-                  dense_ctas: Optional[bool] = None) -> Dict[str, torch.Tensor]:
+                  dense_ctas: Optional[bool] = None, events=None) -> Dict[str, torch.Tensor]:
     """All-pairs per-frame geometry + vIoU/tIoU/overlap (trajectory.py:85-141, common.py:65-106).
+    ``events``: a pair of CUDA events recorded immediately before and after the pair kernel itself (the
+    volume pre-kernel and the per-pair finalize are issued as separate phases around them).
     ``dense_ctas`` selects the 1024-threads-per-SM shape of the kernel (2-stage ring, 64 registers) instead of
     the default ~512 threads per SM (bit-identical results, measured slower; A/B timing only - default from
     the environment variable TSPN_GEO_DENSE)."""
@@ -83,13 +85,24 @@ def pair_geometry(batch: DeviceBatch, write_geo: bool = True, clipped: bool = Fa
         out["overlap"] = torch.empty((p, 2), dtype=torch.int32, device=dev)
         ws_bytes = load().tspn_pair_geo_workspace_bytes(batch.total_tracklets, batch.total_pairs)
         out["workspace"] = torch.empty(ws_bytes // 8, dtype=torch.float64, device=dev)
-    check(load().tspn_pair_geo_viou(
-        ptr(batch.table), batch.num_videos, int(tot[_lib.TOT_ITEMS]), int(tot[_lib.TOT_GEO_CHUNK]),
-        batch.total_tracklets, batch.total_pairs,
-        int(tot[_lib.TOT_BOXES]), ptr(batch.boxes), ptr(batch.span), ptr(out.get("geo")), ptr(out["viou"]),
-        ptr(out["tiou"]), ptr(out["overlap"]),
-        (_lib.VIOU_CLIPPED if clipped else _lib.VIOU_FULL) | (_lib.GEO_DENSE_CTAS if dense_ctas else 0),
-        ptr(out["workspace"]), stream_ptr()), "tspn_pair_geo_viou")
+    flags = (_lib.VIOU_CLIPPED if clipped else _lib.VIOU_FULL) | (_lib.GEO_DENSE_CTAS if dense_ctas else 0)
+
+    def call(phase):
+        check(load().tspn_pair_geo_viou(
+            ptr(batch.table), batch.num_videos, int(tot[_lib.TOT_ITEMS]), int(tot[_lib.TOT_GEO_CHUNK]),
+            batch.total_tracklets, batch.total_pairs,
+            int(tot[_lib.TOT_BOXES]), ptr(batch.boxes), ptr(batch.span), ptr(out.get("geo")), ptr(out["viou"]),
+            ptr(out["tiou"]), ptr(out["overlap"]), flags | phase, ptr(out["workspace"]), stream_ptr()),
+            "tspn_pair_geo_viou")
+    if events is None:
+        call(0)
+    else:
+        stream = torch.cuda.current_stream(dev)
+        call(_lib.GEO_PHASE_PRE)
+        events[0].record(stream)
+        call(_lib.GEO_PHASE_MAIN)
+        events[1].record(stream)
+        call(_lib.GEO_PHASE_POST)
     _count(3)       # volumes + accumulator zeroing, pair kernel, per-pair finalize
     return out
 
@@ -139,6 +152,15 @@ def viou_pairs_f64(pool: torch.Tensor, traj_off: torch.Tensor, traj_span: torch.
 
 
 def normalize_motion(motion: torch.Tensor) -> torch.Tensor:
+    """L1-normalise the four 1000-wide BoW blocks of every tracklet (vrdataset.py:227-236); ``motion`` is
+    fp32 ``[n, 4000]`` or the compact u8 counts of ``HostBatch(compact=True)``."""
+    if motion.dtype == torch.uint8:
+        motion = _cuda(motion, torch.uint8)
+        out = torch.empty(motion.shape, dtype=torch.float32, device=motion.device)
+        check(load().tspn_normalize_motion_u8(ptr(motion), motion.shape[0], ptr(out), stream_ptr()),
+              "tspn_normalize_motion_u8")
+        _count(1)
+        return out
     motion = _cuda(motion, torch.float32)
     out = torch.empty_like(motion)
     check(load().tspn_normalize_motion(ptr(motion), motion.shape[0], ptr(out), stream_ptr()),

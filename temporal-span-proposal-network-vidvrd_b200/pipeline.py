@@ -167,10 +167,10 @@ class PairStage:
             mn = ops.normalize_motion(batch.motion)
         return scores, idx, val, row, mn
 
-    def _seg_geo(self, batch: DeviceBatch, features: Optional[torch.Tensor]):
+    def _seg_geo(self, batch: DeviceBatch, features: Optional[torch.Tensor], events=None):
         c = self.cfg
         need_geo = features is None or c.use_dpn
-        return ops.pair_geometry(batch, write_geo=need_geo and c.write_geo, clipped=c.viou_clipped)
+        return ops.pair_geometry(batch, write_geo=need_geo and c.write_geo, clipped=c.viou_clipped, events=events)
 
     def _seg_tail(self, batch: DeviceBatch, features, heads, side, geom) -> StageResult:
         c = self.cfg
@@ -237,13 +237,11 @@ class PairStage:
         for t in side:
             if t is not None:
                 t.record_stream(main)                 # allocated on the side stream, consumed on main
+        events = None
         if timers is not None:      # CUDA events around the dominant kernel, on the launching stream
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev0.record(main)
-        geom = self._seg_geo(batch, features)
-        if timers is not None:
-            ev1.record(main)
-            timers["geo"] = (ev0, ev1)
+            events = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            timers["geo"] = events
+        geom = self._seg_geo(batch, features, events=events)
         main.wait_stream(side_stream)                 # join
         return self._seg_tail(batch, features, heads, side, geom)
 
@@ -325,19 +323,18 @@ class GraphedStage:
         self.single = bool(single)
         pool = torch.cuda.graph_pool_handle()
         n0 = ops.launch_count()
+        # the pair kernel's own timing: external event-record nodes inside the graph
+        self.ev_geo = (torch.cuda.Event(enable_timing=True, external=True),
+                       torch.cuda.Event(enable_timing=True, external=True))
         if self.single:
             self.graph = torch.cuda.CUDAGraph()
-            self.ev_geo = (torch.cuda.Event(enable_timing=True, external=True),
-                           torch.cuda.Event(enable_timing=True, external=True))
             fork = stage._side_stream(dev)
             with torch.cuda.graph(self.graph, pool=pool, stream=self._cap_stream):
                 cap = torch.cuda.current_stream(dev)
                 fork.wait_stream(cap)
                 with torch.cuda.stream(fork):
                     side = stage._seg_side(batch, features)
-                self.ev_geo[0].record(cap)
-                geom = stage._seg_geo(batch, features)
-                self.ev_geo[1].record(cap)
+                geom = stage._seg_geo(batch, features, events=self.ev_geo)
                 cap.wait_stream(fork)
                 self.result = stage._seg_tail(batch, features, heads, side, geom)
         else:
@@ -346,7 +343,7 @@ class GraphedStage:
             with torch.cuda.graph(self.g_side, pool=pool, stream=self._cap_stream):
                 side = stage._seg_side(batch, features)
             with torch.cuda.graph(self.g_geo, pool=pool, stream=self._cap_stream):
-                geom = stage._seg_geo(batch, features)
+                geom = stage._seg_geo(batch, features, events=self.ev_geo)
             with torch.cuda.graph(self.g_tail, pool=pool, stream=self._cap_stream):
                 self.result = stage._seg_tail(batch, features, heads, side, geom)
         self.kernels_per_replay = ops.launch_count() - n0
@@ -364,13 +361,9 @@ class GraphedStage:
         self.side_stream.wait_stream(main)
         with torch.cuda.stream(self.side_stream):
             self.g_side.replay()
-        if timers is not None:
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev0.record(main)
         self.g_geo.replay()
         if timers is not None:
-            ev1.record(main)
-            timers["geo"] = (ev0, ev1)
+            timers["geo"] = self.ev_geo          # external event nodes inside g_geo; valid until the next replay
         main.wait_stream(self.side_stream)
         self.g_tail.replay()
         ops.count_launches(self.kernels_per_replay)

@@ -45,7 +45,7 @@ class PipelinedStage:
     ``template`` (the graphs are captured for them)."""
 
     def __init__(self, stage: PairStage, template: HostBatch, device="cuda", depth: int = 2, graphs: bool = True,
-                 group=None, compute_streams: int = 1, single_graph: bool = True):
+                 group=None, compute_streams: int = 2, single_graph: bool = True):
         self.stage, self.device, self.depth, self.group = stage, torch.device(device), int(depth), group
         self.main = torch.cuda.current_stream(self.device)
         # Two compute streams, used alternately: the latency-bound tail of step i (feature rows, heads,

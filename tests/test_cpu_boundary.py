@@ -71,7 +71,7 @@ def test_video_table_layout():
 
 def test_host_batch_packing():
     vids = [synth.make_video(4, 10, 35, seed=1), synth.make_video(0, 3, 35, seed=2), synth.make_video(3, 17, 35, seed=3)]
-    hb = HostBatch.from_videos(vids, pin=False)
+    hb = HostBatch.from_videos(vids, pin=False, compact=False)
     assert hb.boxes.shape == (4 * 16 + 3 * 24, 4) and hb.span.shape == (7, 2)
     b = hb.boxes.numpy()
     np.testing.assert_array_equal(b[:64].reshape(4, 16, 4)[:, :10], vids[0].boxes)
@@ -79,6 +79,17 @@ def test_host_batch_packing():
     np.testing.assert_array_equal(b[64:].reshape(3, 24, 4)[:, :17], vids[2].boxes)
     np.testing.assert_array_equal(hb.cls.numpy()[4:], vids[2].cls)
     assert hb.h2d_bytes() > 0
+    # compact transport: integer boxes as u16, integer motion counts as u8 - lossless, fewer bytes
+    hc = HostBatch.from_videos(vids, pin=False)
+    assert hc.boxes_compact and hc.motion_compact and hc.h2d_bytes() < hb.h2d_bytes() // 2
+    np.testing.assert_array_equal(hc.boxes.numpy().view(np.uint16).astype(np.float32), b)
+    np.testing.assert_array_equal(hc.motion.numpy().astype(np.float32), hb.motion.numpy())
+    np.testing.assert_array_equal(hc.cls.numpy(), hb.cls.numpy())
+    # values that are not exactly representable travel as fp32
+    frac = synth.make_video(3, 9, 35, seed=4, integer_boxes=False)
+    frac.motion[0, 0] = 0.5
+    hf = HostBatch.from_videos([frac], pin=False)
+    assert not hf.boxes_compact and not hf.motion_compact and hf.boxes.dtype == torch.float32
     with pytest.raises(ValueError):
         HostBatch([np.zeros((2, 5, 4), np.float32)], [np.array([[0, 6], [0, 5]], np.int32)], pin=False)
 

@@ -218,3 +218,30 @@ def test_graphed_and_pipelined_stage_match_eager(precision, single):
         assert set(g) == set(w)
         for k in w:
             assert torch.equal(g[k], w[k]), k
+
+
+def test_compact_transport_is_lossless():
+    """u16 boxes + u8 motion counts (the default transport when the values allow it) against fp32 transport:
+    every output of the stage bit for bit."""
+    from tspn_b200.batch import HostBatch
+    from tspn_b200.pipeline import PairStage, StageConfig
+    c, r = 35, 132
+    sd = synth.make_weights(c, r, synth.feature_dim(c), dpn_in=8, seed=3)
+    vids = [synth.make_video(n, t, c, seed=40 + i) for i, (n, t) in enumerate([(9, 120), (14, 300), (2, 5), (5, 77)])]
+    vids[1].motion[3, :1000] = 0                       # an empty histogram block stays zero
+    vids[1].motion[4, 7] = 255
+    for precision in ("fp32", "tensor"):
+        stage = PairStage(StageConfig(n_classes=c, n_predicates=r, topk=64, sparsify=True, precision=precision))
+        stage.load_weights(sd, "cuda")
+        outs = []
+        for compact in (True, False):
+            host = HostBatch.from_videos(vids, compact=compact)
+            assert host.boxes_compact == compact and host.motion_compact == compact
+            res = stage.forward(host.to_device("cuda"))
+            torch.cuda.synchronize()
+            outs.append(({k: v.cpu() for k, v in res.host_outputs().items()}, res.geom["geo"].cpu(),
+                         host.h2d_bytes()))
+        assert outs[0][2] < 0.5 * outs[1][2]
+        assert torch.equal(outs[0][1], outs[1][1])
+        for k in outs[1][0]:
+            assert torch.equal(outs[0][0][k], outs[1][0][k]), k
