@@ -358,3 +358,43 @@ def test_span_decode_bit_exact(t, stride, sizes):
     assert np.abs(got - f64).max() <= 1 and (got != f64).mean() < 0.01
     anc = oheads.grid_anchors(t, sizes, stride)
     assert anc.shape[0] == got.shape[1]
+
+
+def test_c_abi_error_codes_on_the_device():
+    """Error behaviour of the boundary on a real device: negative return code + thread-local message,
+    nothing launched, no exception across the ABI (the Python wrapper raises RuntimeError)."""
+    lib = _lib.load()
+    v = synth.make_video(4, 40, 35, seed=1)
+    batch = _batch([v])
+    out = ops.pair_geometry(batch, write_geo=True)
+    torch.cuda.synchronize()
+    tot = batch.totals
+    args = [batch.table.data_ptr(), 1, int(tot[_lib.TOT_ITEMS]), int(tot[_lib.TOT_GEO_CHUNK]), batch.total_tracklets,
+            batch.total_pairs, int(tot[_lib.TOT_BOXES]), batch.boxes.data_ptr(), batch.span.data_ptr(),
+            out["geo"].data_ptr(), out["viou"].data_ptr(), out["tiou"].data_ptr(), out["overlap"].data_ptr(), 0,
+            out["workspace"].data_ptr(), _lib.stream_ptr()]
+
+    def call(**patch):
+        a = list(args)
+        for i, val in patch.items():
+            a[int(i[1:])] = val
+        return lib.tspn_pair_geo_viou(*a)
+    assert call() == _lib.TSPN_OK
+    assert call(_7=None) == _lib.TSPN_EBADARG and "null pointer" in _lib.last_error()
+    assert call(_7=batch.boxes.data_ptr() + 4) == _lib.TSPN_EALIGN
+    assert call(_6=int(tot[_lib.TOT_BOXES]) + 1) == _lib.TSPN_ESHAPE
+    assert call(_3=777) == _lib.TSPN_EBADARG and "geo_chunk" in _lib.last_error()
+    assert call(_2=-1) == _lib.TSPN_EBADARG
+    assert call(_2=0) == _lib.TSPN_OK                                   # empty batch: nothing to do
+    with pytest.raises(RuntimeError, match="TSPN_EBADARG"):
+        _lib.check(call(_8=None), "tspn_pair_geo_viou")
+    # top-K: k beyond the supported block size, predicate head: tensor precision without packed weights
+    scores = torch.rand(16, device="cuda")
+    idx = torch.empty((1, 2000), dtype=torch.int64, device="cuda")
+    val = torch.empty((1, 2000), dtype=torch.float32, device="cuda")
+    assert lib.tspn_topk_pairs(batch.table.data_ptr(), 1, scores.data_ptr(), 2000, 0, idx.data_ptr(), val.data_ptr(),
+                               None, _lib.stream_ptr()) < 0
+    torch.cuda.synchronize()                                            # no sticky CUDA error was left behind
+    again = ops.pair_geometry(batch, write_geo=True)
+    torch.cuda.synchronize()
+    assert torch.equal(again["geo"], out["geo"])
