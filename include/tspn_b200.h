@@ -225,6 +225,31 @@ int tspn_predicate_head(const void* d_x, int x_is_bf16, int64_t ld_x, int64_t m,
                         int n_predicates, float* d_y, int precision, void* d_workspace,
                         void* stream);
 
+/* ---- a14 decomposed (TSPN_PREC_TENSOR, features built on the GPU) --------------------------------------
+ * The classifier is linear in the feature row [cls_s | cls_o | motion_s | motion_o | relative], so
+ *   x W^T = A_s[subject] + A_o[object] + rel(pair) W_rel^T
+ * with per-TRACKLET terms A_s = [cls | motion_norm] W_s^T, A_o = [cls | motion_norm] W_o^T (W_s / W_o: the
+ * columns of rel_predictor.weight that multiply the subject / object blocks).  The [rows, F] feature matrix
+ * then never has to exist: 2 x 3000 bytes per scored pair instead of 2 x (2C + 11000).
+ *   tspn_tracklet_rows      [n][ld] bf16 rows [cls | L1-normalised motion | 0] (motion fp32 or u8 counts)
+ *   tspn_predicate_head_affine   y = act(x Wp^T + bias + row_bias[row]) on tcgen05; Wp from
+ *                           tspn_pack_predicate_weights; bias / row_bias may be NULL; flags TSPN_AFFINE_RAW
+ *                           skips the sigmoid (used for the tracklet terms: Wp = W_s, then Wp = W_o)
+ *   tspn_assemble_relative  per scored row: the pooled 3000-wide relative block in bf16 ([SPEC] s4) and the
+ *                           bias row A_s[s] + A_o[o] gathered from d_terms_subject / d_terms_object [n_tracklets][R]
+ *                           (padding rows: zeros).  Workspace of the head: tspn_predicate_workspace_bytes. */
+#define TSPN_AFFINE_RAW 1
+int tspn_tracklet_rows(const float* d_cls, int n_classes, const void* d_motion, int motion_is_u8,
+                       int64_t n_tracklets, void* d_out_bf16, int64_t ld, void* stream);
+int tspn_predicate_head_affine(const void* d_x, int x_is_bf16, int64_t ld_x, int64_t m, int feature_dim,
+                               const void* d_w_packed, const float* d_bias, const float* d_row_bias,
+                               int64_t ld_row_bias, int n_outputs, float* d_y, int flags, void* d_workspace,
+                               void* stream);
+int tspn_assemble_relative(const int64_t* d_table, int num_videos, int64_t total_pairs, int max_frames,
+                           const float* d_geo, const int32_t* d_overlap, const int64_t* d_rows, int64_t n_rows,
+                           void* d_rel_bf16, int64_t ld_rel, const float* d_terms_subject,
+                           const float* d_terms_object, int n_outputs, float* d_row_bias, void* stream);
+
 /* ---- a11/a12 + [SPEC] s5: temporal-span head ---------------------------------------------
  * DPNHead.forward (lib/modeling/relpn/dpn.py:55-73): Conv1d(k3,p1) -> ReLU -> Conv1d(k1).
  * x rows are gathered: pair i reads row d_rows[i] - row_base of x (NULL = identity, negative =

@@ -30,6 +30,7 @@ GEO_DENSE_CTAS = 2
 GEO_PHASE_PRE, GEO_PHASE_MAIN, GEO_PHASE_POST = 8, 16, 32
 TOPK_KEEP_DIAGONAL, TOPK_EXCLUDE_DIAGONAL = 0, 1
 PREC_FP32_EXACT, PREC_TENSOR = 0, 1
+AFFINE_RAW = 1
 
 P = c_void_p      # device pointers travel as integers (tensor.data_ptr())
 
@@ -59,6 +60,9 @@ SIGNATURES = {
     "tspn_pack_predicate_weights": (c_int, [P, c_int, c_int, P, P]),
     "tspn_predicate_workspace_bytes": (c_int64, [c_int64, c_int, c_int, c_int]),
     "tspn_predicate_head": (c_int, [P, c_int, c_int64, c_int64, c_int, P, P, P, c_int, P, c_int, P, P]),
+    "tspn_tracklet_rows": (c_int, [P, c_int, P, c_int, c_int64, P, c_int64, P]),
+    "tspn_predicate_head_affine": (c_int, [P, c_int, c_int64, c_int64, c_int, P, P, P, c_int64, c_int, P, c_int, P, P]),
+    "tspn_assemble_relative": (c_int, [P, c_int, c_int64, c_int, P, P, P, c_int64, P, c_int64, P, P, c_int, P, P]),
     "tspn_span_head_workspace_bytes": (c_int64, [c_int64, c_int, c_int, c_int, c_int]),
     "tspn_span_head": (c_int, [P, P, c_int64, c_int64, c_int64, c_int64, c_int, c_int, P, P, P, P, c_int, P, c_int, P, P]),
     "tspn_span_num_locations": (c_int, [c_int, c_float]),

@@ -67,6 +67,35 @@ __global__ void __launch_bounds__(256) unpack_boxes_u16_kernel(const uint2* __re
     }
 }
 
+// Tracklet rows for the decomposed predicate head: [cls (C) | L1-normalised motion (4000) | 0-pad] in bf16,
+// one CTA of 128 threads per tracklet (warp w normalises BoW block w).  MOTION_U8: compact transport.
+template <bool MOTION_U8>
+__global__ void __launch_bounds__(128) tracklet_rows_kernel(const float* __restrict__ cls, int n_classes,
+                                                            const void* __restrict__ motion, int64_t n_tracklets,
+                                                            __nv_bfloat16* __restrict__ out, int64_t ld) {
+    const int64_t trk = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __nv_bfloat16* dst = out + trk * ld;
+    for (int i = threadIdx.x; i < n_classes; i += 128) dst[i] = __float2bfloat16(__ldg(cls + trk * n_classes + i));
+    for (int64_t i = n_classes + TSPN_MOTION_DIM + threadIdx.x; i < ld; i += 128) dst[i] = __float2bfloat16(0.0f);
+    __nv_bfloat16* md = dst + n_classes + warp * TSPN_MOTION_BLOCK;
+    if (MOTION_U8) {
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(motion) + trk * TSPN_MOTION_DIM + warp * TSPN_MOTION_BLOCK;
+        uint32_t isum = 0;
+        for (int i = lane; i < TSPN_MOTION_BLOCK; i += 32) isum += __ldg(src + i);
+        isum = __reduce_add_sync(0xffffffffu, isum);
+        const float s = isum ? (float)isum : 1.0f;
+        for (int i = lane; i < TSPN_MOTION_BLOCK; i += 32) md[i] = __float2bfloat16((float)__ldg(src + i) / s);
+    } else {
+        const float* src = reinterpret_cast<const float*>(motion) + trk * TSPN_MOTION_DIM + warp * TSPN_MOTION_BLOCK;
+        float s = 0.0f;
+        for (int i = lane; i < TSPN_MOTION_BLOCK; i += 32) s += fabsf(__ldg(src + i));
+        s = warp_sum_f(s);
+        if (s == 0.0f) s = 1.0f;
+        for (int i = lane; i < TSPN_MOTION_BLOCK; i += 32) md[i] = __float2bfloat16(__ldg(src + i) / s);
+    }
+}
+
 constexpr int ASM_THREADS = 256;
 constexpr int ASM_STAGED = 2;      // geometry channels staged per round: (0,1) position, (2,3) size, (5,6) motion
 // Shared memory of one CTA: the overlap windows of two pooled channels (cap floats each, cap = the
@@ -111,7 +140,10 @@ struct RowSource {
 // into the 3 x 2 x 500 bins of the relative block, which stay in shared memory; (2) the whole row
 // leaves as aligned 128-bit stores, each thread gathering the 4 (fp32) / 8 (bf16) columns of its
 // vector from the classeme / normalised-motion rows (L2) or the pooled block.
-template <bool BF16>
+// REL_ONLY (decomposed predicate head): the row is just the pooled relative block in bf16, and the CTA also
+// emits the row's bias  A_s[subject] + A_o[object]  from the per-tracklet terms (cls = A_s [Ntrk][R],
+// motion_norm = A_o [Ntrk][R], n_classes = R, feat = the [rows][R] bias rows).
+template <bool BF16, bool REL_ONLY = false>
 __global__ void __launch_bounds__(ASM_THREADS)
 assemble_kernel(const int64_t* __restrict__ table, int nv, const float* __restrict__ cls, int n_classes,
                 const float* __restrict__ motion_norm, const float* __restrict__ geo,
@@ -126,6 +158,12 @@ assemble_kernel(const int64_t* __restrict__ table, int nv, const float* __restri
     __nv_bfloat16* outb = BF16 ? feat_bf16 + r * ld_bf16 : nullptr;
     const int C = n_classes;
     const int F = 2 * C + 2 * TSPN_MOTION_DIM + TSPN_REL_DIM;
+    if (REL_ONLY && gp < 0) {                      // padding row: zero relative block, zero bias row
+        for (int64_t q = threadIdx.x; q < ld_bf16 / 8; q += ASM_THREADS)
+            reinterpret_cast<uint4*>(outb)[q] = make_uint4(0u, 0u, 0u, 0u);
+        for (int c = threadIdx.x; c < C; c += ASM_THREADS) out[c] = 0.0f;
+        return;
+    }
     if (gp < 0) {                                  // padding row (e.g. K_eff < K): zeros
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
         if (out)
@@ -196,6 +234,19 @@ assemble_kernel(const int64_t* __restrict__ table, int nv, const float* __restri
     }
     __syncthreads();
 
+    if (REL_ONLY) {
+        for (int col = 8 * threadIdx.x; col < (int)ld_bf16; col += 8 * ASM_THREADS) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = col + j < TSPN_REL_DIM ? s_rel[col + j] : 0.0f;
+            *reinterpret_cast<uint4*>(outb + col) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                                pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        }
+        const float* a_s = cls + ts * C;                     // A_s of the subject tracklet
+        const float* a_o = motion_norm + to * C;             // A_o of the object tracklet
+        for (int c = threadIdx.x; c < C; c += ASM_THREADS) out[c] = __ldg(a_s + c) + __ldg(a_o + c);
+        return;
+    }
     // ---- the row, as aligned vectors ----
     RowSource src;
     src.cls_s = cls + ts * C; src.cls_o = cls + to * C;
@@ -268,6 +319,53 @@ int tspn_unpack_boxes_u16(const uint16_t* d_src, int64_t n_boxes, float* d_dst, 
     if (blocks > cap) blocks = cap;
     unpack_boxes_u16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const uint2*>(d_src), n_boxes, reinterpret_cast<float4*>(d_dst));
+    TSPN_CUDA_OK(cudaGetLastError());
+    return TSPN_OK;
+}
+
+int tspn_tracklet_rows(const float* d_cls, int n_classes, const void* d_motion, int motion_is_u8,
+                       int64_t n_tracklets, void* d_out_bf16, int64_t ld, void* stream) {
+    TSPN_ARCH_OK();
+    TSPN_REQUIRE(n_tracklets >= 0 && n_classes > 0, TSPN_EBADARG, "tspn_tracklet_rows: bad size");
+    if (n_tracklets == 0) return TSPN_OK;
+    TSPN_REQUIRE(d_cls && d_motion && d_out_bf16, TSPN_EBADARG, "tspn_tracklet_rows: null pointer");
+    TSPN_REQUIRE(ld >= n_classes + TSPN_MOTION_DIM && (ld & 7) == 0, TSPN_ESHAPE,
+                 "tspn_tracklet_rows: ld=%lld must be >= C+4000 and a multiple of 8", (long long)ld);
+    TSPN_REQUIRE(aligned16(d_out_bf16), TSPN_EALIGN, "tspn_tracklet_rows: output must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (motion_is_u8)
+        tracklet_rows_kernel<true><<<(unsigned)n_tracklets, 128, 0, st>>>(d_cls, n_classes, d_motion, n_tracklets,
+                                                                          reinterpret_cast<__nv_bfloat16*>(d_out_bf16), ld);
+    else
+        tracklet_rows_kernel<false><<<(unsigned)n_tracklets, 128, 0, st>>>(d_cls, n_classes, d_motion, n_tracklets,
+                                                                           reinterpret_cast<__nv_bfloat16*>(d_out_bf16), ld);
+    TSPN_CUDA_OK(cudaGetLastError());
+    return TSPN_OK;
+}
+
+int tspn_assemble_relative(const int64_t* d_table, int num_videos, int64_t total_pairs, int max_frames,
+                           const float* d_geo, const int32_t* d_overlap, const int64_t* d_rows, int64_t n_rows,
+                           void* d_rel_bf16, int64_t ld_rel, const float* d_terms_subject,
+                           const float* d_terms_object, int n_outputs, float* d_row_bias, void* stream) {
+    TSPN_ARCH_OK();
+    TSPN_REQUIRE(num_videos >= 0 && total_pairs >= 0 && n_rows >= 0 && n_outputs > 0 && max_frames >= 0, TSPN_EBADARG,
+                 "tspn_assemble_relative: bad size");
+    if (!d_rows) n_rows = total_pairs;
+    if (n_rows == 0) return TSPN_OK;
+    TSPN_REQUIRE(d_table && d_geo && d_overlap && d_rel_bf16 && d_terms_subject && d_terms_object && d_row_bias,
+                 TSPN_EBADARG,
+                 "tspn_assemble_relative: null pointer");
+    TSPN_REQUIRE(ld_rel >= TSPN_REL_DIM && (ld_rel & 7) == 0, TSPN_ESHAPE,
+                 "tspn_assemble_relative: ld_rel=%lld must be >= 3000 and a multiple of 8", (long long)ld_rel);
+    TSPN_REQUIRE(aligned16(d_rel_bf16), TSPN_EALIGN, "tspn_assemble_relative: output must be 16-byte aligned");
+    TSPN_REQUIRE(n_rows < (1ll << 31), TSPN_ESHAPE, "tspn_assemble_relative: too many rows");
+    int cap = ((max_frames > 0 ? max_frames : 4096) + 3) / 4 * 4 + 8;
+    if (cap > ASM_TCAP_MAX) cap = ASM_TCAP_MAX;
+    const int smem = asm_smem_bytes(cap);
+    TSPN_CUDA_OK(cudaFuncSetAttribute(assemble_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    assemble_kernel<true, true><<<(unsigned)n_rows, ASM_THREADS, smem, (cudaStream_t)stream>>>(
+        d_table, num_videos, d_terms_subject, n_outputs, d_terms_object, d_geo, d_overlap, d_rows, d_row_bias, n_outputs,
+        reinterpret_cast<__nv_bfloat16*>(d_rel_bf16), ld_rel, cap);
     TSPN_CUDA_OK(cudaGetLastError());
     return TSPN_OK;
 }

@@ -12,8 +12,8 @@
 namespace tspn {
 
 int predicate_head_tensor(const void* d_x, int x_is_bf16, int64_t ld_x, int64_t m, int feature_dim,
-                          const void* d_w_packed, const float* d_bias, int n_predicates, float* d_y,
-                          void* d_workspace, cudaStream_t st);
+                          const void* d_w_packed, const float* d_bias, const float* d_row_bias, int64_t ld_rb, int raw,
+                          int n_predicates, float* d_y, void* d_workspace, cudaStream_t st);
 
 constexpr int PX_BM = 64, PX_BN = 64, PX_BK = 16, PX_THREADS = 256;
 
@@ -119,8 +119,24 @@ int tspn_predicate_head(const void* d_x, int x_is_bf16, int64_t ld_x, int64_t m,
     }
     TSPN_REQUIRE(precision == TSPN_PREC_TENSOR, TSPN_EBADARG, "tspn_predicate_head: unknown precision %d", precision);
     TSPN_REQUIRE(d_w_packed, TSPN_EBADARG, "tspn_predicate_head: tensor mode needs tspn_pack_predicate_weights output");
-    return predicate_head_tensor(d_x, x_is_bf16, ld_x, m, feature_dim, d_w_packed, d_bias, n_predicates, d_y,
-                                 d_workspace, st);
+    return predicate_head_tensor(d_x, x_is_bf16, ld_x, m, feature_dim, d_w_packed, d_bias, nullptr, 0, 0, n_predicates,
+                                 d_y, d_workspace, st);
+}
+
+int tspn_predicate_head_affine(const void* d_x, int x_is_bf16, int64_t ld_x, int64_t m, int feature_dim,
+                               const void* d_w_packed, const float* d_bias, const float* d_row_bias,
+                               int64_t ld_row_bias, int n_outputs, float* d_y, int flags, void* d_workspace,
+                               void* stream) {
+    TSPN_ARCH_OK();
+    TSPN_REQUIRE(m >= 0 && feature_dim > 0 && n_outputs > 0 && ld_x >= feature_dim, TSPN_EBADARG,
+                 "tspn_predicate_head_affine: bad size (m=%lld f=%d r=%d ld=%lld)", (long long)m, feature_dim,
+                 n_outputs, (long long)ld_x);
+    if (m == 0) return TSPN_OK;
+    TSPN_REQUIRE(d_x && d_y && d_w_packed, TSPN_EBADARG, "tspn_predicate_head_affine: null pointer");
+    TSPN_REQUIRE(!d_row_bias || ld_row_bias >= n_outputs, TSPN_ESHAPE,
+                 "tspn_predicate_head_affine: ld_row_bias=%lld < %d", (long long)ld_row_bias, n_outputs);
+    return predicate_head_tensor(d_x, x_is_bf16, ld_x, m, feature_dim, d_w_packed, d_bias, d_row_bias, ld_row_bias,
+                                 (flags & TSPN_AFFINE_RAW) ? 1 : 0, n_outputs, d_y, d_workspace, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -43,7 +43,8 @@ template <bool BF16>
 __global__ void __launch_bounds__(PT_THREADS, 1)
 predicate_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, int64_t m,
                     int r, int rpad, int num_kblocks, int kb_per_split, int stages, uint32_t tmem_cols,
-                    const float* __restrict__ bias, float* __restrict__ y, float* __restrict__ partial) {
+                    const float* __restrict__ bias, const float* __restrict__ row_bias, int64_t ld_rb, int raw,
+                    float* __restrict__ y, float* __restrict__ partial) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int stage_a = PT_BM * PT_SLAB;
     const int stage_bytes = stage_a + rpad * PT_SLAB;
@@ -126,8 +127,9 @@ predicate_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                     for (int j = 0; j < 16; ++j) {
                         const int c = c0 + j;
                         if (c < r) {
-                            const float z = v[j] + (bias ? __ldg(bias + c) : 0.0f);
-                            y[row * r + c] = 1.0f / (1.0f + __expf(-z));
+                            const float z = v[j] + (bias ? __ldg(bias + c) : 0.0f) +
+                                            (row_bias ? __ldg(row_bias + row * ld_rb + c) : 0.0f);
+                            y[row * r + c] = raw ? z : 1.0f / (1.0f + __expf(-z));
                         }
                     }
                 }
@@ -147,17 +149,19 @@ predicate_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     }
 }
 
-// sum the split-K partials in split order, add bias, sigmoid
+// sum the split-K partials in split order, add bias (+ per-row bias), sigmoid (unless raw)
 __global__ void __launch_bounds__(256)
 predicate_reduce_kernel(const float* __restrict__ partial, int splits, int64_t mpad, int rpad, int64_t m, int r,
-                        const float* __restrict__ bias, float* __restrict__ y) {
+                        const float* __restrict__ bias, const float* __restrict__ row_bias, int64_t ld_rb, int raw,
+                        float* __restrict__ y) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= m * r) return;
     const int64_t row = idx / r;
     const int c = (int)(idx - row * r);
     float z = bias ? __ldg(bias + c) : 0.0f;
     for (int s = 0; s < splits; ++s) z += __ldg(partial + ((int64_t)s * mpad + row) * rpad + c);
-    y[idx] = 1.0f / (1.0f + __expf(-z));
+    if (row_bias) z += __ldg(row_bias + row * ld_rb + c);
+    y[idx] = raw ? z : 1.0f / (1.0f + __expf(-z));
 }
 
 // packed weights: [bf16 Rpad x Kpad16] then [fp32 Rpad x Kpad32], zero padded
@@ -180,8 +184,8 @@ static int64_t packed_bf16_bytes(int r, int f) { return (int64_t)pt_rpad(r) * pt
 static int64_t packed_f32_bytes(int r, int f) { return (int64_t)pt_rpad(r) * pt_kpad(f, 4) * 4; }
 
 int predicate_head_tensor(const void* d_x, int x_is_bf16, int64_t ld_x, int64_t m, int feature_dim,
-                          const void* d_w_packed, const float* d_bias, int n_predicates, float* d_y,
-                          void* d_workspace, cudaStream_t st) {
+                          const void* d_w_packed, const float* d_bias, const float* d_row_bias, int64_t ld_rb, int raw,
+                          int n_predicates, float* d_y, void* d_workspace, cudaStream_t st) {
     const int r = n_predicates, f = feature_dim;
     const int rpad = pt_rpad(r);
     TSPN_REQUIRE(rpad <= 256, TSPN_ESHAPE, "tensor predicate head supports at most 256 predicates (got %d)", r);
@@ -233,20 +237,21 @@ int predicate_head_tensor(const void* d_x, int x_is_bf16, int64_t ld_x, int64_t 
         TSPN_CUDA_OK(cudaFuncSetAttribute(predicate_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem_bytes));
         predicate_tc_kernel<true><<<grid, PT_THREADS, smem_bytes, st>>>(map_x, map_w, m, r, rpad, num_kblocks,
-                                                                        kb_per_split, stages, tmem_cols, d_bias, d_y,
-                                                                        partial);
+                                                                        kb_per_split, stages, tmem_cols, d_bias,
+                                                                        d_row_bias, ld_rb, raw, d_y, partial);
     } else {
         TSPN_CUDA_OK(cudaFuncSetAttribute(predicate_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem_bytes));
         predicate_tc_kernel<false><<<grid, PT_THREADS, smem_bytes, st>>>(map_x, map_w, m, r, rpad, num_kblocks,
-                                                                         kb_per_split, stages, tmem_cols, d_bias, d_y,
-                                                                         partial);
+                                                                         kb_per_split, stages, tmem_cols, d_bias,
+                                                                         d_row_bias, ld_rb, raw, d_y, partial);
     }
     TSPN_CUDA_OK(cudaGetLastError());
     if (eff_splits > 1) {
         const int64_t total = m * r;
         predicate_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, eff_splits, mtiles * PT_BM,
-                                                                                 rpad, m, r, d_bias, d_y);
+                                                                                 rpad, m, r, d_bias, d_row_bias, ld_rb, raw,
+                                                                                 d_y);
         TSPN_CUDA_OK(cudaGetLastError());
     }
     return TSPN_OK;

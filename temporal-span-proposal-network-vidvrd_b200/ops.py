@@ -279,6 +279,61 @@ def predicate_head(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, pr
     return y
 
 
+def tracklet_rows(batch: DeviceBatch) -> torch.Tensor:
+    """``[n_tracklets, ld]`` bf16 rows ``[cls | L1-normalised motion | 0]`` for the decomposed predicate head."""
+    c = int(batch.cls.shape[1])
+    ld = (c + _lib.MOTION_DIM + 7) // 8 * 8
+    n = batch.total_tracklets
+    out = torch.empty((n, ld), dtype=torch.bfloat16, device=batch.device)
+    motion = batch.motion
+    check(load().tspn_tracklet_rows(ptr(_cuda(batch.cls, torch.float32)), c, ptr(motion),
+                                    int(motion.dtype == torch.uint8), n, ptr(out), ld, stream_ptr()),
+          "tspn_tracklet_rows")
+    _count(1)
+    return out
+
+
+def predicate_head_affine(x: torch.Tensor, packed: torch.Tensor, n_outputs: int, bias: Optional[torch.Tensor] = None,
+                          row_bias: Optional[torch.Tensor] = None, raw: bool = False,
+                          k_dim: Optional[int] = None) -> torch.Tensor:
+    """``act(x Wp^T + bias + row_bias[row])`` on the tensor cores (``tspn_predicate_head_affine``); ``packed``
+    from ``pack_predicate_weights`` of the ``[n_outputs, k_dim]`` weight slice; ``raw`` skips the sigmoid."""
+    x = _cuda(x)
+    m = x.shape[0]
+    f = int(k_dim if k_dim is not None else x.shape[1])
+    is_bf16 = x.dtype == torch.bfloat16
+    if not is_bf16 and x.dtype != torch.float32:
+        raise TypeError("x must be float32 or bfloat16")
+    y = torch.empty((m, n_outputs), dtype=torch.float32, device=x.device)
+    nbytes = load().tspn_predicate_workspace_bytes(m, f, n_outputs, _lib.PREC_TENSOR)
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=x.device)
+    check(load().tspn_predicate_head_affine(
+        ptr(x), int(is_bf16), x.stride(0) if m > 1 else max(f, x.stride(0)), m, f, ptr(packed),
+        ptr(_cuda(bias, torch.float32)) if bias is not None else None,
+        ptr(_cuda(row_bias, torch.float32)) if row_bias is not None else None,
+        row_bias.stride(0) if row_bias is not None else 0, n_outputs, ptr(y), _lib.AFFINE_RAW if raw else 0, ptr(ws),
+        stream_ptr()), "tspn_predicate_head_affine")
+    _count(1 if ws.numel() <= 16 else 2)
+    return y
+
+
+def assemble_relative(batch: DeviceBatch, geo: torch.Tensor, overlap: torch.Tensor, rows: Optional[torch.Tensor],
+                      terms_subject: torch.Tensor, terms_object: torch.Tensor):
+    """Per scored row the pooled relative block (bf16 ``[n_rows, 3000]``, [SPEC] s4) and the bias row
+    ``A_s[subject] + A_o[object]`` gathered from the per-tracklet terms (``[n_tracklets, R]`` each)."""
+    dev = batch.device
+    n_rows = int(rows.shape[0]) if rows is not None else batch.total_pairs
+    r = int(terms_subject.shape[1])
+    rel = torch.empty((n_rows, _lib.REL_DIM), dtype=torch.bfloat16, device=dev)
+    row_bias = torch.empty((n_rows, r), dtype=torch.float32, device=dev)
+    check(load().tspn_assemble_relative(
+        ptr(batch.table), batch.num_videos, batch.total_pairs, int(batch.totals[_lib.TOT_MAX_T]), ptr(geo), ptr(overlap),
+        ptr(rows), n_rows, ptr(rel), rel.stride(0), ptr(_cuda(terms_subject, torch.float32)),
+        ptr(_cuda(terms_object, torch.float32)), r, ptr(row_bias), stream_ptr()), "tspn_assemble_relative")
+    _count(1)
+    return rel, row_bias
+
+
 def span_head(x: torch.Tensor, conv_w: torch.Tensor, conv_b: torch.Tensor, pred_w: torch.Tensor,
               pred_b: torch.Tensor, rows: Optional[torch.Tensor] = None, t: Optional[int] = None,
               precision: str = "fp32", row_base: int = 0) -> torch.Tensor:

@@ -38,6 +38,7 @@ class StageConfig:
     records: bool = True               # build the triplet records (row N1)
     mirror_q4: bool = False
     keep_span_reg: bool = False        # also return DPNHead's raw [K, 2A, T] regressions (two-kernel path)
+    materialize_features: bool = False  # tensor precision: also build the [rows, F] rows (see PairStage._decomposed)
 
     @classmethod
     def from_cfg(cls, cfg) -> "StageConfig":
@@ -130,9 +131,19 @@ class PairStage:
             k = k[7:] if k.startswith("module.") else k      # lib/utils/serialize.py:13-20
             t = v if isinstance(v, torch.Tensor) else torch.as_tensor(v)
             self.w[k] = t.detach().to(dev, torch.float32).contiguous()
-        self.packed_cls = None
+        self.packed_cls = self.packed_sub = self.packed_obj = self.packed_rel = None
         if self.cfg.precision == "tensor" and (CLS_PREFIX + "weight") in self.w:
-            self.packed_cls = ops.pack_predicate_weights(self.w[CLS_PREFIX + "weight"])
+            w = self.w[CLS_PREFIX + "weight"]
+            self.packed_cls = ops.pack_predicate_weights(w)
+            c, md = self.cfg.n_classes, _lib.MOTION_DIM
+            if w.shape[1] == 2 * c + 2 * md + _lib.REL_DIM:
+                # decomposed head (include/tspn_b200.h, a14 decomposed): per-tracklet slices W_s, W_o over
+                # [cls | motion] and the slice that multiplies the pooled relative block
+                w_s = torch.cat([w[:, :c], w[:, 2 * c:2 * c + md]], dim=1)
+                w_o = torch.cat([w[:, c:2 * c], w[:, 2 * c + md:2 * c + 2 * md]], dim=1)
+                self.packed_sub = ops.pack_predicate_weights(w_s.contiguous())
+                self.packed_obj = ops.pack_predicate_weights(w_o.contiguous())
+                self.packed_rel = ops.pack_predicate_weights(w[:, 2 * c + 2 * md:].contiguous())
         self.sizes_dev = torch.tensor(self.cfg.anchor_sizes, dtype=torch.float32, device=dev)
 
     def ppn_weights(self):
@@ -164,8 +175,22 @@ class PairStage:
         if features is None:
             if batch.motion is None or batch.cls is None:
                 raise ValueError("feature construction needs the cls and motion tracklet fields")
-            mn = ops.normalize_motion(batch.motion)
+            if self._decomposed(features):
+                # per-tracklet terms of the decomposed head: A_s = [cls | motion_norm] W_s^T, A_o likewise
+                x_trk = ops.tracklet_rows(batch)
+                kd = c.n_classes + _lib.MOTION_DIM
+                mn = (ops.predicate_head_affine(x_trk, self.packed_sub, c.n_predicates, raw=True, k_dim=kd),
+                      ops.predicate_head_affine(x_trk, self.packed_obj, c.n_predicates, raw=True, k_dim=kd))
+            else:
+                mn = ops.normalize_motion(batch.motion)
         return scores, idx, val, row, mn
+
+    def _decomposed(self, features) -> bool:
+        """Tensor precision with features built on the GPU: the classifier is evaluated as
+        ``A_s[s] + A_o[o] + rel(pair) W_rel^T`` and the ``[rows, F]`` feature matrix is never materialised
+        (``StageConfig.materialize_features`` forces the rows into existence: one GEMM over F instead)."""
+        return (features is None and self.cfg.precision == "tensor" and self.packed_rel is not None
+                and not self.cfg.materialize_features)
 
     def _seg_geo(self, batch: DeviceBatch, features: Optional[torch.Tensor], events=None):
         c = self.cfg
@@ -189,7 +214,14 @@ class PairStage:
             side_stream.wait_stream(main)
             with torch.cuda.stream(side_stream):
                 span_reg, spans, span_bufs = self._span_heads(batch, geom, row, k_eff)
-        if features is None:
+        decomposed = self._decomposed(features)
+        if decomposed:
+            rows = row.reshape(-1) if sparsify else None
+            rel16, row_bias = ops.assemble_relative(batch, geom["geo"], geom["overlap"], rows, mn[0], mn[1])
+            if heads:
+                logits = ops.predicate_head_affine(rel16, self.packed_rel, c.n_predicates,
+                                                   bias=self.w[CLS_PREFIX + "bias"], row_bias=row_bias)
+        elif features is None:
             rows = row.reshape(-1) if sparsify else None
             feats32, feats16 = ops.assemble_features(batch, mn, geom["geo"], geom["overlap"], rows,
                                                      want_fp32=not tensor, want_bf16=tensor)
@@ -198,7 +230,7 @@ class PairStage:
             if sparsify:
                 sel = row.reshape(-1)
                 feats32 = torch.where((sel >= 0)[:, None], features[sel.clamp_min(0)], features.new_zeros(()))
-        if heads:
+        if heads and not decomposed:
             x = feats16 if feats16 is not None else feats32
             logits = ops.predicate_head(x, self.w[CLS_PREFIX + "weight"], self.w[CLS_PREFIX + "bias"],
                                         precision=c.precision, packed=self.packed_cls)
@@ -235,8 +267,9 @@ class PairStage:
         with torch.cuda.stream(side_stream):
             side = self._seg_side(batch, features)
         for t in side:
-            if t is not None:
-                t.record_stream(main)                 # allocated on the side stream, consumed on main
+            for u in (t if isinstance(t, tuple) else (t,)):
+                if u is not None:
+                    u.record_stream(main)             # allocated on the side stream, consumed on main
         events = None
         if timers is not None:      # CUDA events around the dominant kernel, on the launching stream
             events = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -340,11 +373,13 @@ class GraphedStage:
         else:
             self.g_side, self.g_geo, self.g_tail = (torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(),
                                                     torch.cuda.CUDAGraph())
-            with torch.cuda.graph(self.g_side, pool=pool, stream=self._cap_stream):
+            # g_side and g_geo replay CONCURRENTLY (different streams): they must not share a memory pool, or a
+            # temporary freed at the end of one capture is handed to the other and both write it at replay
+            with torch.cuda.graph(self.g_side, stream=self._cap_stream):
                 side = stage._seg_side(batch, features)
-            with torch.cuda.graph(self.g_geo, pool=pool, stream=self._cap_stream):
+            with torch.cuda.graph(self.g_geo, stream=self._cap_stream):
                 geom = stage._seg_geo(batch, features, events=self.ev_geo)
-            with torch.cuda.graph(self.g_tail, pool=pool, stream=self._cap_stream):
+            with torch.cuda.graph(self.g_tail, stream=self._cap_stream):
                 self.result = stage._seg_tail(batch, features, heads, side, geom)
         self.kernels_per_replay = ops.launch_count() - n0
         self.graph_launches = 1 if self.single else 3

@@ -74,3 +74,92 @@ def test_span_head_tensor(cin, k, t, a):
     np.testing.assert_array_equal(sub[0], got[k - 1])
     np.testing.assert_array_equal(sub[1], 0)
     np.testing.assert_array_equal(sub[2], got[0])
+
+
+def test_decomposed_predicate_head_pieces():
+    """tspn_tracklet_rows, tspn_predicate_head_affine (raw) and tspn_assemble_relative against their float64
+    definitions: x W^T = A_s[s] + A_o[o] + rel W_rel^T."""
+    from oracle import features as ofeat, geometry as ogeo
+    from tspn_b200.batch import HostBatch
+    c, r = 35, 132
+    vids = [synth.make_video(7, 90, c, seed=3), synth.make_video(4, 33, c, seed=4)]
+    vids[0].motion[2, :1000] = 0
+    sd = synth.make_weights(c, r, synth.feature_dim(c), dpn_in=8, seed=5)
+    w = sd["classifier.rel_predictor.weight"].astype(np.float64)
+    for compact in (True, False):
+        batch = HostBatch.from_videos(vids, compact=compact).to_device("cuda")
+        rows_t = ops.tracklet_rows(batch)
+        torch.cuda.synchronize()
+        cls = np.concatenate([v.cls for v in vids])
+        mn = np.concatenate([np.concatenate([ofeat.l1_normalize_ref(v.motion[:, k * 1000:(k + 1) * 1000]) for k in range(4)], axis=1)
+                             for v in vids])
+        want_rows = np.concatenate([cls, mn], axis=1)
+        got_rows = rows_t.float().cpu().numpy()
+        assert got_rows.shape[1] % 8 == 0 and (got_rows[:, c + 4000:] == 0).all()
+        np.testing.assert_allclose(got_rows[:, :c + 4000], want_rows, rtol=2 ** -8, atol=1e-30)      # bf16 rounding
+    wt = torch.from_numpy(sd["classifier.rel_predictor.weight"]).cuda()
+    w_s = torch.cat([wt[:, :c], wt[:, 2 * c:2 * c + 4000]], dim=1)
+    w_o = torch.cat([wt[:, c:2 * c], wt[:, 2 * c + 4000:2 * c + 8000]], dim=1)
+    terms = torch.cat([ops.predicate_head_affine(rows_t, ops.pack_predicate_weights(ws_.contiguous()), r, raw=True,
+                                                 k_dim=c + 4000) for ws_ in (w_s, w_o)], dim=1)
+    torch.cuda.synchronize()
+    want_terms = np.concatenate([want_rows @ np.concatenate([w[:, :c], w[:, 2 * c:2 * c + 4000]], axis=1).T,
+                                 want_rows @ np.concatenate([w[:, c:2 * c], w[:, 2 * c + 4000:2 * c + 8000]], axis=1).T], axis=1)
+    np.testing.assert_allclose(terms.cpu().numpy(), want_terms, rtol=0, atol=2e-3)
+    geom = ops.pair_geometry(batch, write_geo=True)
+    n_pairs = batch.total_pairs
+    sel = torch.tensor([0, 5, -1, n_pairs - 1, 17, -1, 41], dtype=torch.int64, device="cuda")
+    rel16, row_bias = ops.assemble_relative(batch, geom["geo"], geom["overlap"], sel, terms[:, :r].contiguous(),
+                                            terms[:, r:].contiguous())
+    torch.cuda.synchronize()
+    got_rel, got_rb, tm = rel16.float().cpu().numpy(), row_bias.cpu().numpy(), terms.cpu().numpy()
+    for i, gp in enumerate(sel.tolist()):
+        if gp < 0:
+            assert (got_rel[i] == 0).all() and (got_rb[i] == 0).all()
+            continue
+        vi = 0 if gp < vids[0].n_pairs else 1
+        v = vids[vi]
+        p = gp - (0 if vi == 0 else vids[0].n_pairs)
+        pr = ogeo.enumerate_pairs(v.n_tracklets)[p]
+        g, _, _, ov = ogeo.pair_geometry(v.boxes, v.span, pr[None, 0], pr[None, 1])
+        want_rel = ofeat.relative_block(g, ov)[0]
+        scale = np.abs(want_rel).mean() + 1e-12
+        assert np.abs(got_rel[i] - want_rel).max() <= 2 ** -7 * max(np.abs(want_rel).max(), scale)
+        t0 = 0 if vi == 0 else vids[0].n_tracklets
+        np.testing.assert_array_equal(got_rb[i], tm[t0 + pr[0], :r] + tm[t0 + pr[1], r:])
+
+
+@pytest.mark.parametrize("sparsify", [True, False])
+def test_decomposed_head_matches_materialised_rows_and_oracle(sparsify):
+    """Whole stage, tensor precision: the decomposed classifier against the one-GEMM-over-F form
+    (StageConfig.materialize_features) and against the float64 oracle (1e-2 absolute, BASELINE.json)."""
+    from oracle import features as ofeat, geometry as ogeo, heads as oheads
+    from tspn_b200.batch import HostBatch
+    from tspn_b200.pipeline import PairStage, StageConfig
+    c, r, k = 35, 132, 40
+    vids = [synth.make_video(9, 120, c, seed=11), synth.make_video(3, 64, c, seed=12), synth.make_video(6, 200, c, seed=13)]
+    sd = synth.make_weights(c, r, synth.feature_dim(c), dpn_in=8, seed=2)
+    res = {}
+    for mat in (False, True):
+        stage = PairStage(StageConfig(n_classes=c, n_predicates=r, topk=k, sparsify=sparsify, precision="tensor",
+                                      materialize_features=mat))
+        stage.load_weights(sd, "cuda")
+        batch = HostBatch.from_videos(vids).to_device("cuda")
+        res[mat] = stage.forward(batch)
+        torch.cuda.synchronize()
+        assert (res[mat].features_bf16 is not None) == mat
+    assert torch.equal(res[False].topk_idx, res[True].topk_idx)
+    for i, v in enumerate(vids):
+        a, b = res[False].logits(i).cpu().numpy(), res[True].logits(i).cpu().numpy()
+        assert a.shape == b.shape and np.abs(a - b).max() <= 5e-3
+        n = v.n_tracklets
+        geo, _, _, ov = ogeo.pair_geometry_chunked(v.boxes, v.span)
+        feats = ofeat.assemble_features(v.cls, v.motion, ofeat.relative_block(geo, ov), ogeo.enumerate_pairs(n))
+        if sparsify:
+            order = res[False].pair_proposals(i).cpu().numpy()
+            s, o = order // n, order % n
+            feats = feats[s * (n - 1) + o - (o > s)]
+        want = oheads.relation_predictor_f64(feats, sd)
+        np.testing.assert_allclose(a, want, rtol=0, atol=1e-2)
+    # records are built from the decomposed logits
+    assert res[False].records.shape == res[True].records.shape
