@@ -104,6 +104,7 @@ constexpr int ASM_STAGED = 2;      // geometry channels staged per round: (0,1) 
 // SM - than it saves in load rounds: 112 us against 88 us for the 4096 rows of the bench).  Rows longer
 // than ASM_TCAP_MAX frames are pooled straight from global memory.
 constexpr int ASM_TCAP_MAX = 16384;
+constexpr int ASM_INV_TAB = 32;     // bin widths with a tabulated reciprocal
 __host__ __device__ constexpr int asm_smem_bytes(int cap) { return (ASM_STAGED * cap + TSPN_REL_DIM) * 4; }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -190,6 +191,11 @@ assemble_kernel(const int64_t* __restrict__ table, int nv, const float* __restri
     const int a4 = a & ~3;
     const int staged_frames = b - a4;
     const bool staged = len > 0 && staged_frames <= cap - 4 && ((reinterpret_cast<uintptr_t>(g) & 15) == 0);
+    // 1 / (frames per bin) for the few bin widths that occur (one IEEE division per width instead of one per
+    // bin: the division was 15 % of this kernel's instructions)
+    __shared__ float s_inv[ASM_INV_TAB];
+    if (threadIdx.x < ASM_INV_TAB) s_inv[threadIdx.x] = 1.0f / (float)(threadIdx.x ? threadIdx.x : 1);
+    if (!staged) __syncthreads();                  // the staged path synchronises before the table is read
 #pragma unroll 1
     for (int cp = 0; cp < 3; ++cp) {
         const int ch0 = cp < 2 ? 2 * cp : 5;       // channel pairs (0,1) position, (2,3) size, (5,6) motion
@@ -215,7 +221,8 @@ assemble_kernel(const int64_t* __restrict__ table, int nv, const float* __restri
             if (len > 0) {
                 const uint32_t st = ((uint32_t)i * len) / TSPN_REL_BINS;              // len < 2^22: fits 32 bits
                 const uint32_t en = ((uint32_t)(i + 1) * len + TSPN_REL_BINS - 1) / TSPN_REL_BINS;
-                const float inv = 1.0f / (float)(en - st);
+                const uint32_t width = en - st;
+                const float inv = width < ASM_INV_TAB ? s_inv[width] : 1.0f / (float)width;
                 float sacc = 0.0f;
                 if (staged) {
                     const float* sp = s_geo + c * cap + (a - a4) + st;

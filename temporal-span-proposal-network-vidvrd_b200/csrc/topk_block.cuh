@@ -13,6 +13,7 @@ namespace tspn {
 
 constexpr int TOPK_THREADS = 256;
 constexpr int TOPK_MAX_K = 1024;
+constexpr int TOPK_CACHE = 8192;          // candidates whose keys are kept in shared memory across the passes
 
 __device__ __forceinline__ uint32_t order_key(float f) {
     const uint32_t b = __float_as_uint(f);
@@ -23,6 +24,7 @@ constexpr uint32_t KEY_NEG_INF = 0x007FFFFFu;               // order_key(-inf): 
 struct TopkSmem {
     uint32_t hist[256];
     uint64_t sel[TOPK_MAX_K];
+    uint32_t keys[TOPK_CACHE];
     uint32_t prefix, need, count, tie_base, n_cand;
     uint32_t warp_cnt[TOPK_THREADS / 32];
 };
@@ -35,6 +37,15 @@ constexpr int TOPK_EPT = 4;        // consecutive candidates per thread in the c
 template <typename ValueOf>
 __device__ int block_topk(TopkSmem& sm, int64_t total, int k, ValueOf value_of) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // The candidates are read five times (four radix passes + the collect pass).  Up to TOPK_CACHE of them
+    // (one video's N*N relationness scores up to N = 90, or 256 pairs x 20 predicates) are converted to keys
+    // once and kept in shared memory; larger problems re-read global memory (L2) every pass.
+    const bool cached = total <= TOPK_CACHE;
+    if (cached) {
+        for (int64_t i = tid; i < total; i += TOPK_THREADS) sm.keys[i] = order_key(value_of(i));
+        __syncthreads();
+    }
+    auto key_of = [&](int64_t i) -> uint32_t { return cached ? sm.keys[i] : order_key(value_of(i)); };
     // -- radix select of the k_eff-th largest key (the first pass also counts the candidates) --------
     if (tid == 0) {
         sm.prefix = 0;
@@ -50,7 +61,7 @@ __device__ int block_topk(TopkSmem& sm, int64_t total, int k, ValueOf value_of) 
         // would otherwise serialise the shared-memory atomics on one bin
         uint32_t run_bin = 0xffffffffu, run_cnt = 0;
         for (int64_t i = tid; i < total; i += TOPK_THREADS) {
-            const uint32_t key = order_key(value_of(i));
+            const uint32_t key = key_of(i);
             if (key != KEY_NEG_INF && (key & prefix_mask) == prefix) {
                 const uint32_t bin = (key >> shift) & 0xffu;
                 if (bin == run_bin) {
@@ -115,7 +126,7 @@ __device__ int block_topk(TopkSmem& sm, int64_t total, int k, ValueOf value_of) 
 #pragma unroll
         for (int e = 0; e < TOPK_EPT; ++e) {
             const int64_t i = base + (int64_t)tid * TOPK_EPT + e;
-            keys[e] = i < total ? order_key(value_of(i)) : KEY_NEG_INF;
+            keys[e] = i < total ? key_of(i) : KEY_NEG_INF;
             if (keys[e] > thr) sm.sel[atomicAdd(&sm.count, 1u)] = ((uint64_t)(~keys[e]) << 32) | (uint32_t)i;
             n_tie += keys[e] == thr;                  // thr > KEY_NEG_INF, so -inf is never collected
         }
