@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define TSPN_ABI_VERSION 3
+#define TSPN_ABI_VERSION 4
 
 /* error codes */
 #define TSPN_OK 0
@@ -80,7 +80,9 @@ extern "C" {
 /* Work items of the pair-geometry kernel: (video, subject, group of TSPN_GEO_OBJ_GROUP other
  * tracklets, chunk of tspn_geo_chunk(max T of the batch) frames), numbered chunk-fastest; the table's
  * TSPN_VT_ITEM_OFF column and totals[TSPN_TOT_ITEMS] count them. */
+#ifndef TSPN_GEO_OBJ_GROUP
 #define TSPN_GEO_OBJ_GROUP 64
+#endif
 
 /* geometry channels of geo[P][8][Tp] ([SPEC] s2) */
 #define TSPN_GEO_CHANNELS 8
@@ -102,6 +104,11 @@ extern "C" {
 #define TSPN_GEO_PHASE_PRE 8
 #define TSPN_GEO_PHASE_MAIN 16
 #define TSPN_GEO_PHASE_POST 32
+/* The caller asserts that every video of the batch fits one chunk (totals[TSPN_TOT_MAX_T] <=
+ * totals[TSPN_TOT_GEO_CHUNK]): every pair's sums then have a single writer, PRE does not zero them, and PRE
+ * (per-tracklet volumes only) may be issued on another stream concurrently with MAIN; POST needs both.  MAIN
+ * writes d_overlap; POST writes d_viou / d_tiou.  Pass the flag to every phase of the call. */
+#define TSPN_GEO_SINGLE_CHUNK 64
 #define TSPN_TOPK_KEEP_DIAGONAL 0    /* reference behaviour, ppn.py:84-85 (quirk Q1) */
 #define TSPN_TOPK_EXCLUDE_DIAGONAL 1 /* survivors are real pairs (sparsify mode) */
 #define TSPN_PREC_FP32_EXACT 0 /* CUDA cores, fixed k-ascending fma order: bit-reproducible */
@@ -184,7 +191,8 @@ int tspn_unpack_boxes_u16(const uint16_t* d_src, int64_t n_boxes, float* d_dst, 
  * to build (int64, NULL = all total_pairs rows in order).  Output row stride ld_feat floats
  * (>= 2C+11000, multiple of 4).  d_feat_bf16 (optional, may be NULL): same rows in bf16 with
  * stride ld_bf16 (multiple of 8) for the tensor-core predicate head.  max_frames =
- * totals[TSPN_TOT_MAX_T] sizes the shared-memory staging of the pooled channels (0 = unknown). */
+ * totals[TSPN_TOT_MAX_T] (0 = unknown; validated, otherwise unused since ABI 4: the pooled channels are
+ * read straight from global memory). */
 int tspn_assemble_features(const int64_t* d_table, int num_videos, int64_t total_pairs, int max_frames,
                            const float* d_cls, int n_classes, const float* d_motion_norm,
                            const float* d_geo, const int32_t* d_overlap,

@@ -20,7 +20,7 @@ VT_N, VT_T, VT_TP, VT_TB, VT_TRK_OFF, VT_PAIR_OFF, VT_GEO_OFF, VT_ITEM_OFF, VT_B
 TOT_COLS = 10
 TOT_TRACKLETS, TOT_PAIRS, TOT_GEO_FLOATS, TOT_ITEMS, TOT_BOXES, TOT_SCORES, TOT_MAX_N, TOT_MAX_T, TOT_GEO_CHUNK = range(9)
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 GEO_OBJ_GROUP = 64        # include/tspn_b200.h: objects per work item of the pair-geometry kernel
 GEO_CHANNELS = 8
 MOTION_DIM = 4000
@@ -28,6 +28,7 @@ REL_DIM = 3000
 VIOU_FULL, VIOU_CLIPPED = 0, 1
 GEO_DENSE_CTAS = 2
 GEO_PHASE_PRE, GEO_PHASE_MAIN, GEO_PHASE_POST = 8, 16, 32
+GEO_SINGLE_CHUNK = 64
 TOPK_KEEP_DIAGONAL, TOPK_EXCLUDE_DIAGONAL = 0, 1
 PREC_FP32_EXACT, PREC_TENSOR = 0, 1
 AFFINE_RAW = 1

@@ -125,6 +125,29 @@ __device__ __forceinline__ void st_stream_f4(float* p, float4 v) {
                  : "memory");
 }
 
+__device__ __forceinline__ void st_stream_f2(float* p, float2 v) {
+    asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+// 1-D bulk store shared -> global, tracked by the issuing thread's bulk async-group (SASS: UBLKCP);
+// both addresses 16-byte aligned, bytes a multiple of 16.  HINT = 2 adds an L2 evict_first policy.
+template <int HINT = 1>
+__device__ __forceinline__ void bulk_store_1d(void* gdst, const void* smem_src, uint32_t bytes) {
+    if (HINT == 2) {
+        uint64_t policy;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                     ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes), "l"(policy) : "memory");
+    } else {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// the calling thread's bulk stores have finished READING shared memory (the source may be overwritten)
+__device__ __forceinline__ void bulk_wait_read0() {
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 // ---- host: tensor maps ---------------------------------------------------------------------
 // cuTensorMapEncodeTiled resolved through cudaGetDriverEntryPoint (no link-time libcuda).
 int encode_tensor_map(CUtensorMap* map, CUtensorMapDataType dtype, uint32_t rank, const void* base,

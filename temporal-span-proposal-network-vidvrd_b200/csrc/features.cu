@@ -97,15 +97,8 @@ __global__ void __launch_bounds__(128) tracklet_rows_kernel(const float* __restr
 }
 
 constexpr int ASM_THREADS = 256;
-constexpr int ASM_STAGED = 2;      // geometry channels staged per round: (0,1) position, (2,3) size, (5,6) motion
-// Shared memory of one CTA: the overlap windows of two pooled channels (cap floats each, cap = the
-// batch's longest row + alignment slack) followed by the 3000 pooled bins: 28 KB at T = 2000, i.e. eight
-// 256-thread CTAs per SM (measured: staging all six channels at once costs more in occupancy - 3 CTAs per
-// SM - than it saves in load rounds: 112 us against 88 us for the 4096 rows of the bench).  Rows longer
-// than ASM_TCAP_MAX frames are pooled straight from global memory.
-constexpr int ASM_TCAP_MAX = 16384;
+constexpr int ASM_POOLED = 6;       // pooled geometry channels: (0,1) position, (2,3) size, (5,6) motion
 constexpr int ASM_INV_TAB = 32;     // bin widths with a tabulated reciprocal
-__host__ __device__ constexpr int asm_smem_bytes(int cap) { return (ASM_STAGED * cap + TSPN_REL_DIM) * 4; }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -136,11 +129,14 @@ struct RowSource {
     }
 };
 
-// One CTA per output row.  (1) The pair's overlap window of two geometry channels at a time is staged
-// in shared memory with coalesced 128-bit loads (the window is read exactly once from HBM) and pooled
-// into the 3 x 2 x 500 bins of the relative block, which stay in shared memory; (2) the whole row
-// leaves as aligned 128-bit stores, each thread gathering the 4 (fp32) / 8 (bf16) columns of its
-// vector from the classeme / normalised-motion rows (L2) or the pooled block.
+// One CTA per output row.  (1) Bin i of every pooled channel covers the same frames of the pair's overlap
+// window, so a thread owns bin i of all six channels: one index computation, six independent load streams
+// straight from global memory (a warp's 32 bins are one contiguous run of frames per channel; the bins'
+// later frames hit the lines the first ones brought into L1), frames added in ascending order; the 3 x 2 x
+// 500 bins go to shared memory.  No staging round trips and no barrier until the block is complete - the
+// staged form this replaces spent 14 k warp-instructions per row on load/sync/pool rounds.  (2) The whole
+// row leaves as aligned 128-bit stores, each thread gathering the 4 (fp32) / 8 (bf16) columns of its vector
+// from the classeme / normalised-motion rows (L2) or the pooled block.
 // REL_ONLY (decomposed predicate head): the row is just the pooled relative block in bf16, and the CTA also
 // emits the row's bias  A_s[subject] + A_o[object]  from the per-tracklet terms (cls = A_s [Ntrk][R],
 // motion_norm = A_o [Ntrk][R], n_classes = R, feat = the [rows][R] bias rows).
@@ -149,10 +145,9 @@ __global__ void __launch_bounds__(ASM_THREADS)
 assemble_kernel(const int64_t* __restrict__ table, int nv, const float* __restrict__ cls, int n_classes,
                 const float* __restrict__ motion_norm, const float* __restrict__ geo,
                 const int32_t* __restrict__ overlap, const int64_t* __restrict__ rows, float* __restrict__ feat,
-                int64_t ld_feat, __nv_bfloat16* __restrict__ feat_bf16, int64_t ld_bf16, int cap) {
-    extern __shared__ __align__(16) float s_dyn[];
-    float* const s_geo = s_dyn;                                 // [ASM_STAGED][cap]
-    float* const s_rel = s_dyn + (size_t)ASM_STAGED * cap;      // [TSPN_REL_DIM]
+                int64_t ld_feat, __nv_bfloat16* __restrict__ feat_bf16, int64_t ld_bf16) {
+    __shared__ __align__(16) float s_rel[TSPN_REL_DIM];
+    __shared__ float s_inv[ASM_INV_TAB];
     const int64_t r = blockIdx.x;
     const int64_t gp = rows ? rows[r] : r;
     float* out = feat ? feat + r * ld_feat : nullptr;
@@ -184,60 +179,43 @@ assemble_kernel(const int64_t* __restrict__ table, int nv, const float* __restri
     const int o = k + (k >= s ? 1 : 0);
     const int64_t ts = row[TSPN_VT_TRK_OFF] + s, to = row[TSPN_VT_TRK_OFF] + o;
 
-    // ---- relative block: bin i of every pooled channel shares its frame range ----
-    const float* g = geo + row[TSPN_VT_GEO_OFF] + (int64_t)p * TSPN_GEO_CHANNELS * tp;
+    // ---- relative block ----
     const int a = __ldg(overlap + 2 * gp), b = __ldg(overlap + 2 * gp + 1);
     const uint32_t len = b > a ? (uint32_t)(b - a) : 0u;
-    const int a4 = a & ~3;
-    const int staged_frames = b - a4;
-    const bool staged = len > 0 && staged_frames <= cap - 4 && ((reinterpret_cast<uintptr_t>(g) & 15) == 0);
-    // 1 / (frames per bin) for the few bin widths that occur (one IEEE division per width instead of one per
-    // bin: the division was 15 % of this kernel's instructions)
-    __shared__ float s_inv[ASM_INV_TAB];
+    // the six pooled channel rows, at the first frame of the window
+    const float* g0 = geo + row[TSPN_VT_GEO_OFF] + (int64_t)p * TSPN_GEO_CHANNELS * tp + a;
+    const float* g1 = g0 + tp;
+    const float* g2 = g0 + 2 * (int64_t)tp;
+    const float* g3 = g0 + 3 * (int64_t)tp;
+    const float* g5 = g0 + 5 * (int64_t)tp;
+    const float* g6 = g0 + 6 * (int64_t)tp;
+    // 1 / (frames per bin) for the few bin widths that occur (one IEEE division per width instead of one per bin)
     if (threadIdx.x < ASM_INV_TAB) s_inv[threadIdx.x] = 1.0f / (float)(threadIdx.x ? threadIdx.x : 1);
-    if (!staged) __syncthreads();                  // the staged path synchronises before the table is read
-#pragma unroll 1
-    for (int cp = 0; cp < 3; ++cp) {
-        const int ch0 = cp < 2 ? 2 * cp : 5;       // channel pairs (0,1) position, (2,3) size, (5,6) motion
-        if (staged) {
-            if (cp) __syncthreads();               // the previous pair's readers are done
-            const int nvec = (staged_frames + 3) >> 2;
-            const float4* g0 = reinterpret_cast<const float4*>(g + (int64_t)ch0 * tp + a4);
-            const float4* g1 = reinterpret_cast<const float4*>(g + (int64_t)(ch0 + 1) * tp + a4);
-            for (int q = threadIdx.x; q < nvec; q += ASM_THREADS) {
-                const float4 v0 = __ldg(g0 + q), v1 = __ldg(g1 + q);
-                *reinterpret_cast<float4*>(s_geo + 4 * q) = v0;
-                *reinterpret_cast<float4*>(s_geo + cap + 4 * q) = v1;
-            }
-            __syncthreads();
-        }
-        // every bin spans at most ceil(len / 500) + 1 frames: a CTA-uniform trip count with a predicated
-        // body instead of a per-thread loop bound (frames are still added in ascending order)
-        const int max_w = (int)((len + TSPN_REL_BINS - 1) / TSPN_REL_BINS) + 1;
-        for (int w = threadIdx.x; w < 2 * TSPN_REL_BINS; w += ASM_THREADS) {
-            const int c = w >= TSPN_REL_BINS ? 1 : 0;
-            const int i = w - c * TSPN_REL_BINS;
-            float acc = 0.0f;
-            if (len > 0) {
-                const uint32_t st = ((uint32_t)i * len) / TSPN_REL_BINS;              // len < 2^22: fits 32 bits
-                const uint32_t en = ((uint32_t)(i + 1) * len + TSPN_REL_BINS - 1) / TSPN_REL_BINS;
-                const uint32_t width = en - st;
-                const float inv = width < ASM_INV_TAB ? s_inv[width] : 1.0f / (float)width;
-                float sacc = 0.0f;
-                if (staged) {
-                    const float* sp = s_geo + c * cap + (a - a4) + st;
-                    const int cnt = (int)(en - st);
+    __syncthreads();
+    for (int i = threadIdx.x; i < TSPN_REL_BINS; i += ASM_THREADS) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a5 = 0.f, a6 = 0.f;
+        if (len > 0) {
+            const uint32_t st = ((uint32_t)i * len) / TSPN_REL_BINS;              // len < 2^22: fits 32 bits
+            const uint32_t en = ((uint32_t)(i + 1) * len + TSPN_REL_BINS - 1) / TSPN_REL_BINS;
+            const uint32_t width = en - st;
+            const float inv = width < ASM_INV_TAB ? s_inv[width] : 1.0f / (float)width;
 #pragma unroll 2
-                    for (int j = 0; j < max_w; ++j)
-                        if (j < cnt) sacc += sp[j];
-                } else {
-                    const float* gc = g + (int64_t)(ch0 + c) * tp + a;
-                    for (uint32_t f = st; f < en; ++f) sacc += __ldg(gc + f);
-                }
-                acc = sacc * inv;
+            for (uint32_t f = st; f < en; ++f) {                                  // ascending frames
+                a0 += __ldg(g0 + f);
+                a1 += __ldg(g1 + f);
+                a2 += __ldg(g2 + f);
+                a3 += __ldg(g3 + f);
+                a5 += __ldg(g5 + f);
+                a6 += __ldg(g6 + f);
             }
-            s_rel[(2 * cp + c) * TSPN_REL_BINS + i] = acc;
+            a0 *= inv; a1 *= inv; a2 *= inv; a3 *= inv; a5 *= inv; a6 *= inv;
         }
+        s_rel[0 * TSPN_REL_BINS + i] = a0;
+        s_rel[1 * TSPN_REL_BINS + i] = a1;
+        s_rel[2 * TSPN_REL_BINS + i] = a2;
+        s_rel[3 * TSPN_REL_BINS + i] = a3;
+        s_rel[4 * TSPN_REL_BINS + i] = a5;
+        s_rel[5 * TSPN_REL_BINS + i] = a6;
     }
     __syncthreads();
 
@@ -366,13 +344,9 @@ int tspn_assemble_relative(const int64_t* d_table, int num_videos, int64_t total
                  "tspn_assemble_relative: ld_rel=%lld must be >= 3000 and a multiple of 8", (long long)ld_rel);
     TSPN_REQUIRE(aligned16(d_rel_bf16), TSPN_EALIGN, "tspn_assemble_relative: output must be 16-byte aligned");
     TSPN_REQUIRE(n_rows < (1ll << 31), TSPN_ESHAPE, "tspn_assemble_relative: too many rows");
-    int cap = ((max_frames > 0 ? max_frames : 4096) + 3) / 4 * 4 + 8;
-    if (cap > ASM_TCAP_MAX) cap = ASM_TCAP_MAX;
-    const int smem = asm_smem_bytes(cap);
-    TSPN_CUDA_OK(cudaFuncSetAttribute(assemble_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    assemble_kernel<true, true><<<(unsigned)n_rows, ASM_THREADS, smem, (cudaStream_t)stream>>>(
+    assemble_kernel<true, true><<<(unsigned)n_rows, ASM_THREADS, 0, (cudaStream_t)stream>>>(
         d_table, num_videos, d_terms_subject, n_outputs, d_terms_object, d_geo, d_overlap, d_rows, d_row_bias, n_outputs,
-        reinterpret_cast<__nv_bfloat16*>(d_rel_bf16), ld_rel, cap);
+        reinterpret_cast<__nv_bfloat16*>(d_rel_bf16), ld_rel);
     TSPN_CUDA_OK(cudaGetLastError());
     return TSPN_OK;
 }
@@ -400,21 +374,14 @@ int tspn_assemble_features(const int64_t* d_table, int num_videos, int64_t total
     TSPN_REQUIRE(n_rows < (1ll << 31), TSPN_ESHAPE, "tspn_assemble_features: too many rows");
     TSPN_REQUIRE(max_frames >= 0, TSPN_EBADARG, "tspn_assemble_features: max_frames=%d", max_frames);
     cudaStream_t st = (cudaStream_t)stream;
-    // staging capacity per pooled channel: the batch's longest row (max_frames = totals[TSPN_TOT_MAX_T];
-    // 0 = unknown -> 4096) + 8 floats of alignment slack; longer rows are pooled from global memory
-    int cap = ((max_frames > 0 ? max_frames : 4096) + 3) / 4 * 4 + 8;
-    if (cap > ASM_TCAP_MAX) cap = ASM_TCAP_MAX;
-    const int smem = asm_smem_bytes(cap);
     if (d_feat_bf16) {
-        TSPN_CUDA_OK(cudaFuncSetAttribute(assemble_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        assemble_kernel<true><<<(unsigned)n_rows, ASM_THREADS, smem, st>>>(
+        assemble_kernel<true><<<(unsigned)n_rows, ASM_THREADS, 0, st>>>(
             d_table, num_videos, d_cls, n_classes, d_motion_norm, d_geo, d_overlap, d_rows, d_feat, ld_feat,
-            reinterpret_cast<__nv_bfloat16*>(d_feat_bf16), ld_bf16, cap);
+            reinterpret_cast<__nv_bfloat16*>(d_feat_bf16), ld_bf16);
     } else {
-        TSPN_CUDA_OK(cudaFuncSetAttribute(assemble_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        assemble_kernel<false><<<(unsigned)n_rows, ASM_THREADS, smem, st>>>(
+        assemble_kernel<false><<<(unsigned)n_rows, ASM_THREADS, 0, st>>>(
             d_table, num_videos, d_cls, n_classes, d_motion_norm, d_geo, d_overlap, d_rows, d_feat, ld_feat, nullptr,
-            0, cap);
+            0);
     }
     TSPN_CUDA_OK(cudaGetLastError());
     return TSPN_OK;

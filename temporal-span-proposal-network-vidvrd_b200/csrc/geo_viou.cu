@@ -8,24 +8,26 @@
 // log-scale ratios, per-frame IoU, forward differences, temporal-overlap mask.
 //
 // Design (sm_100a):
-//   * work item = (video, subject s, group of 8 objects); one 128-thread CTA per item;
-//   * the two tracklets' box rows are staged chunk by chunk (512 frames + 1 halo row) into
-//     shared memory by 2-D tiled TMA (cp.async.bulk.tensor -> UTMALDG) with SWIZZLE_128B,
-//     double-buffered on mbarriers: the subject chunk is loaded once per chunk, the object
-//     chunks stream behind the compute of the previous pair;
-//   * a thread owns 4 consecutive frames: the swizzle makes its five LDS.128 box reads
-//     bank-conflict free, and every channel leaves as one 128-bit streaming store
-//     (a warp writes 512 contiguous bytes per channel row);
-//   * intersection volumes accumulate in fp64 (exact for integer boxes -> the result does
-//     not depend on the reduction order), warp-shuffle reduced over frames, combined across
-//     chunks in a fixed order;
-//   * per-tracklet volumes come from a small pre-kernel (one warp per tracklet).
+//   * work item = (video, subject s, group of <= 64 objects, chunk of 512 / 1024 / 2048 frames);
+//     one CTA per item;
+//   * the two tracklets' box rows are staged chunk by chunk (chunk + 1 halo row of 8 boxes) into
+//     shared memory by 2-D tiled TMA (cp.async.bulk.tensor -> UTMALDG) with SWIZZLE_128B into a
+//     ring on full/empty mbarriers: the subject chunk is loaded once per item, the object chunks
+//     stream behind the compute of the previous objects;
+//   * a thread owns 4 (or 2) consecutive frames: the swizzle makes its LDS.128 box reads
+//     bank-conflict free, and every channel leaves as one vector streaming store (a warp writes
+//     512 contiguous bytes per channel row) - or, with TSPN_GEO_TMA_STORE, through a per-warp
+//     shared-memory tile that leaves as 1-D bulk stores (cp.async.bulk.global.shared::cta);
+//   * intersection volumes accumulate as 64-bit fixed point (exact for integer boxes; integer
+//     adds -> the result does not depend on any reduction or scheduling order);
+//   * per-tracklet volumes come from a small pre-kernel (one CTA per tracklet), vIoU / tIoU from a
+//     small post-kernel; the pair kernel itself writes the overlap windows.
 // Algorithmic bytes: 32*Tp written + 24 B of reductions per pair; boxes are re-read from L2.
 #include "common.cuh"
 
 namespace tspn {
 
-constexpr int GEO_FPT = 4;                            // frames per thread
+constexpr int GEO_FPT = 4;                            // frames per thread (default shapes)
 constexpr int GEO_OG = TSPN_GEO_OBJ_GROUP;
 #ifndef TSPN_GEO_RING
 #define TSPN_GEO_RING 3
@@ -35,6 +37,12 @@ constexpr int GEO_RING = TSPN_GEO_RING;               // object-chunk stages in 
 #define TSPN_GEO_ROTATE 1
 #endif
 constexpr bool GEO_ROTATE = TSPN_GEO_ROTATE != 0;     // rotate the warps' frame blocks with the object index
+#ifndef TSPN_GEO_TMA_STORE
+#define TSPN_GEO_TMA_STORE 0                          // 1: bulk stores from shared memory, 2: + L2 evict_first hint
+#endif
+#ifndef TSPN_GEO_WIDE
+#define TSPN_GEO_WIDE 0                               // 1: the 2048-frame shape is 1024 threads x 2 frames
+#endif
 
 // Shape of one CTA: THREADS threads cover a chunk of 4*THREADS frames (512 / 1024 / 2048, chosen per
 // batch by tspn_geo_chunk).  HBM absorbs this kernel's store stream best as few, wide streams
@@ -48,9 +56,9 @@ constexpr bool GEO_ROTATE = TSPN_GEO_ROTATE != 0;     // rotate the warps' frame
 //                  0.707 ms for the default - kept, bit-identical and tested, as the record of that A/B
 //                  (profiles/r1_geo_kernel_forms_ab.md).
 // The shared-memory request pins the occupancy.
-template <int THREADS, bool DENSE>
+template <int THREADS, bool DENSE, int FPT = GEO_FPT>
 struct GeoCfg {
-    static constexpr int CHUNK = THREADS * GEO_FPT;
+    static constexpr int CHUNK = THREADS * FPT;
     static constexpr int WARPS = THREADS / 32;
     static constexpr int RING = DENSE ? 2 : GEO_RING;             // object-chunk stages in flight
     static constexpr int STAGES = 1 + RING;                       // subject chunk + object ring
@@ -62,7 +70,10 @@ struct GeoCfg {
     static constexpr int MIN_CTAS = DENSE ? 1024 / THREADS : (THREADS >= 512 ? 1 : (THREADS == 256 ? 2 : 3));
     // barriers, per-object fixed-point sums, per-object overlap windows
     static constexpr int TAIL_BYTES = (2 * RING * 8 + GEO_OG * (3 * 8 + 8) + 127) / 128 * 128;
-    static constexpr int SMEM_USED = STAGES * STAGE_BYTES + TAIL_BYTES;
+    // TSPN_GEO_TMA_STORE: the channels leave through a per-warp shared-memory tile as 1-D bulk stores
+    static constexpr bool BULK_OUT = !DENSE && (TSPN_GEO_TMA_STORE != 0);
+    static constexpr int OUT_BYTES = BULK_OUT ? WARPS * TSPN_GEO_CHANNELS * 32 * FPT * 4 : 0;
+    static constexpr int SMEM_USED = STAGES * STAGE_BYTES + TAIL_BYTES + OUT_BYTES;
     static constexpr int SMEM_PIN = 227 * 1024 / (MIN_CTAS + 1) + 1024;
     static constexpr int SMEM_BYTES = SMEM_USED > SMEM_PIN ? SMEM_USED : SMEM_PIN;
     static_assert((SMEM_BYTES + 1024) * MIN_CTAS <= 228 * 1024, "the stages of MIN_CTAS CTAs must fit one SM");
@@ -171,7 +182,7 @@ __device__ __forceinline__ unsigned long long warp_sum_fx(float v) {
 
 // ---- one (pair, 4 frames) step of a thread: the eight channels + the three fp32 partial sums ----------
 // per-thread partial sums stay in fp32: 4 integer-valued products <= 4 * 2^21 < 2^24 are exact
-template <bool CLIP>
+template <bool CLIP, int GEO_FPT>
 __device__ __forceinline__ void geo_step(uint32_t ss, uint32_t os_addr, int j0, int t0, int a, int b,
                                          float (&out)[TSPN_GEO_CHANNELS][GEO_FPT], float& fsum_i, float& fsum_s,
                                          float& fsum_o) {
@@ -237,13 +248,16 @@ __device__ __forceinline__ void geo_step(uint32_t ss, uint32_t os_addr, int j0, 
     }
 }
 
-template <int THREADS, bool WRITE_GEO, bool CLIP, bool DENSE>
-__global__ void __launch_bounds__(THREADS, GeoCfg<THREADS, DENSE>::MIN_CTAS)
+template <int THREADS, bool WRITE_GEO, bool CLIP, bool DENSE, int FPT>
+__global__ void __launch_bounds__(THREADS, GeoCfg<THREADS, DENSE, FPT>::MIN_CTAS)
 pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __restrict__ table, int nv,
-                const int32_t* __restrict__ span, float* __restrict__ geo, unsigned long long* __restrict__ fx) {
-    using Cfg = GeoCfg<THREADS, DENSE>;
+                const int32_t* __restrict__ span, float* __restrict__ geo, unsigned long long* __restrict__ fx,
+                int32_t* __restrict__ overlap) {
+    using Cfg = GeoCfg<THREADS, DENSE, FPT>;
     constexpr int GEO_CHUNK = Cfg::CHUNK, GEO_WARPS = Cfg::WARPS, GEO_STAGE_BYTES = Cfg::STAGE_BYTES;
     constexpr int GEO_TX_BYTES = Cfg::TX_BYTES, GEO_SPLIT = Cfg::SPLIT, RING = Cfg::RING;
+    constexpr int GEO_FPT = FPT;
+    constexpr bool BULK_OUT = WRITE_GEO && Cfg::BULK_OUT;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* const s_stage = smem;
     uint8_t* const o_stage0 = smem + GEO_STAGE_BYTES;
@@ -251,6 +265,9 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
     uint64_t* const empty = full + RING;                                                       // [RING]
     unsigned long long* const acc = reinterpret_cast<unsigned long long*>(empty + RING);       // [OG][3]
     int2* const owin = reinterpret_cast<int2*>(acc + GEO_OG * 3);                              // [OG] overlap windows
+    // BULK_OUT: one [8 channels][32 * FPT frames] output tile per warp, behind the staging area
+    float* const out_tile = reinterpret_cast<float*>(smem + Cfg::STAGES * GEO_STAGE_BYTES + Cfg::TAIL_BYTES) +
+                            (threadIdx.x >> 5) * (TSPN_GEO_CHANNELS * 32 * FPT);
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -333,17 +350,45 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
 
         float fsum_i, fsum_s, fsum_o;
         float out[TSPN_GEO_CHANNELS][GEO_FPT];
-        geo_step<CLIP>(ss, smem_u32(o_stage0 + st * GEO_STAGE_BYTES), j0, t0, a, b, out, fsum_i, fsum_s, fsum_o);
+        geo_step<CLIP, GEO_FPT>(ss, smem_u32(o_stage0 + st * GEO_STAGE_BYTES), j0, t0, a, b, out, fsum_i, fsum_s,
+                                fsum_o);
         // this warp is done reading the object stage of step q: hand it back; thread 0 refills it with
         // object q+RING (end of the step) once every warp has done so
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[st]);
 
-        if (WRITE_GEO) {
+        if (BULK_OUT) {
+            // the warp's 32*FPT frames of every channel go through its shared-memory tile and leave as eight
+            // 1-D bulk stores (lane ch issues channel ch): the LSU sees conflict-free STS.128 only, the
+            // registers are free as soon as the tile is written, and the TMA engine owns the HBM stream
+            if (lane < TSPN_GEO_CHANNELS) bulk_wait_read0();     // the previous step's stores have read the tile
+            __syncwarp();
+#pragma unroll
+            for (int ch = 0; ch < TSPN_GEO_CHANNELS; ++ch) {
+                float* dst = out_tile + ch * (32 * GEO_FPT) + lane * GEO_FPT;
+                if (GEO_FPT == 4)
+                    *reinterpret_cast<float4*>(dst) = make_float4(out[ch][0], out[ch][1], out[ch][2], out[ch][GEO_FPT - 1]);
+                else
+                    *reinterpret_cast<float2*>(dst) = make_float2(out[ch][0], out[ch][1]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            const int jw = j0 - lane * GEO_FPT;                  // the warp's first frame inside the chunk
+            const int left = tp - (c * GEO_CHUNK + jw);          // frames of the row at or after it
+            if (lane < TSPN_GEO_CHANNELS && left > 0)
+                bulk_store_1d<TSPN_GEO_TMA_STORE>(g + (int64_t)lane * tp + jw, out_tile + lane * (32 * GEO_FPT),
+                              (uint32_t)min(left, 32 * GEO_FPT) * 4u);
+            g += (int64_t)TSPN_GEO_CHANNELS * tp;
+        } else if (WRITE_GEO) {
             if (t0 < tp) {
 #pragma unroll
-                for (int ch = 0; ch < TSPN_GEO_CHANNELS; ++ch)
-                    st_stream_f4(g + (int64_t)ch * tp + j0, make_float4(out[ch][0], out[ch][1], out[ch][2], out[ch][3]));
+                for (int ch = 0; ch < TSPN_GEO_CHANNELS; ++ch) {
+                    if (GEO_FPT == 4)
+                        st_stream_f4(g + (int64_t)ch * tp + j0,
+                                     make_float4(out[ch][0], out[ch][1], out[ch][2], out[ch][GEO_FPT - 1]));
+                    else
+                        st_stream_f2(g + (int64_t)ch * tp + j0, make_float2(out[ch][0], out[ch][1]));
+                }
             }
             g += (int64_t)TSPN_GEO_CHANNELS * tp;
         }
@@ -368,20 +413,30 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
         }
         if (++st == RING) { st = 0; ph ^= 1; }
     }
+    if (BULK_OUT && lane < TSPN_GEO_CHANNELS) bulk_wait_read0();   // the tile outlives the CTA's last stores
     __syncthreads();
-    // this chunk's contribution to the pair's sums
+    // this chunk's contribution to the pair's sums: a video that fits one chunk has exactly one writer per
+    // pair, which stores (no zeroing of the accumulators needed); otherwise integer atomics onto zeroed sums
     for (int i3 = tid; i3 < nobj * 3; i3 += THREADS) {
         const unsigned long long val = acc[i3];
-        if (val) atomicAdd(fx + pair0 * 3 + i3, val);
+        if (nchunks == 1) fx[pair0 * 3 + i3] = val;
+        else if (val) atomicAdd(fx + pair0 * 3 + i3, val);
+    }
+    // the pairs' temporal overlap windows ([SPEC] s3): written here so that feature assembly and the records
+    // do not wait for the per-pair finalize
+    if (c == 0 && tid < nobj) {
+        const int2 w = owin[tid];
+        const bool has = w.y > w.x;
+        *reinterpret_cast<int2*>(overlap + 2 * (pair0 + tid)) = make_int2(has ? w.x : 0, has ? w.y : 0);
     }
 }
 
-// ---- post-kernel: per-pair reductions (vIoU, tIoU, overlap window) -----------------------------------
+// ---- post-kernel: per-pair reductions (vIoU, tIoU; the pair kernel writes the overlap windows) ----------
 template <bool CLIP>
 __global__ void __launch_bounds__(256)
 pair_finalize_kernel(const int64_t* __restrict__ table, int nv, int64_t total_pairs, const int32_t* __restrict__ span,
                      const double* __restrict__ vol, const unsigned long long* __restrict__ fx,
-                     float* __restrict__ viou, float* __restrict__ tiou, int32_t* __restrict__ overlap) {
+                     float* __restrict__ viou, float* __restrict__ tiou) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= total_pairs) return;
     const int v = find_video(table, nv, TSPN_VT_PAIR_OFF, p);
@@ -404,8 +459,6 @@ pair_finalize_kernel(const int64_t* __restrict__ table, int nv, int64_t total_pa
     const int tden = (pe - ps) + (qe - qs) - ov;
     viou[p] = (has && den > 0.0) ? (float)(inter / den) : 0.0f;
     tiou[p] = (has && tden > 0) ? (float)((double)ov / (double)tden) : 0.0f;
-    overlap[2 * p] = has ? a : 0;
-    overlap[2 * p + 1] = has ? b : 0;
 }
 
 // ---- cubic_iou(bboxes1, bboxes2): one warp per matrix entry -------------------------------------
@@ -560,11 +613,11 @@ __global__ void __launch_bounds__(256) enumerate_pairs_kernel(const int64_t* __r
     pairs[2 * p + 1] = k + (k >= s ? 1 : 0);
 }
 
-template <int THREADS, bool DENSE>
+template <int THREADS, bool DENSE, int FPT = GEO_FPT>
 static int launch_pair_geo(const int64_t* d_table, int num_videos, int64_t total_items, int64_t total_boxes,
                            const float* d_boxes, const int32_t* d_span, float* d_geo, unsigned long long* fx,
-                           bool clip, cudaStream_t st) {
-    using Cfg = GeoCfg<THREADS, DENSE>;
+                           int32_t* d_overlap, bool clip, cudaStream_t st) {
+    using Cfg = GeoCfg<THREADS, DENSE, FPT>;
     // boxes viewed as a 2-D tensor: rows of 8 boxes (32 floats = 128 B)
     CUtensorMap map;
     const uint64_t dims[2] = {32, (uint64_t)(total_boxes / 8)};
@@ -575,10 +628,10 @@ static int launch_pair_geo(const int64_t* d_table, int num_videos, int64_t total
     if (rc != TSPN_OK) return rc;
 #define TSPN_LAUNCH_GEO(W, C)                                                                                  \
     do {                                                                                                       \
-        TSPN_CUDA_OK(cudaFuncSetAttribute(pair_geo_kernel<THREADS, W, C, DENSE>,                               \
+        TSPN_CUDA_OK(cudaFuncSetAttribute(pair_geo_kernel<THREADS, W, C, DENSE, FPT>,                          \
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));      \
-        pair_geo_kernel<THREADS, W, C, DENSE><<<(unsigned)total_items, THREADS, Cfg::SMEM_BYTES, st>>>(        \
-            map, d_table, num_videos, d_span, d_geo, fx);                                                      \
+        pair_geo_kernel<THREADS, W, C, DENSE, FPT><<<(unsigned)total_items, THREADS, Cfg::SMEM_BYTES, st>>>(   \
+            map, d_table, num_videos, d_span, d_geo, fx, d_overlap);                                           \
     } while (0)
     if (d_geo) {
         if (clip) TSPN_LAUNCH_GEO(true, true); else TSPN_LAUNCH_GEO(true, false);
@@ -642,17 +695,20 @@ int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_ite
     const bool clip = (flags & TSPN_VIOU_CLIPPED) != 0;
     const int phases = flags & (TSPN_GEO_PHASE_PRE | TSPN_GEO_PHASE_MAIN | TSPN_GEO_PHASE_POST);
     const bool all = phases == 0;
-    if (all || (phases & TSPN_GEO_PHASE_PRE)) {
+    // TSPN_GEO_SINGLE_CHUNK: every video fits one chunk, so every pair's sums have exactly one writer, which
+    // stores them: nothing to zero, and PRE (then volumes only) may run concurrently with MAIN
+    const bool single_chunk = (flags & TSPN_GEO_SINGLE_CHUNK) != 0;
+    if ((all || (phases & TSPN_GEO_PHASE_PRE)) && !(single_chunk && clip)) {
         // volumes (one CTA per tracklet) + zeroing of the fixed-point accumulators (grid-stride)
         const int64_t cap = 16 * (int64_t)num_sms();
         const int64_t blocks_vol = clip ? 0 : total_tracklets;
-        const int64_t blocks_zero = (total_pairs * 3 + 127) / 128;
+        const int64_t blocks_zero = single_chunk ? 0 : (total_pairs * 3 + 127) / 128;
         int64_t blocks = blocks_vol > blocks_zero ? blocks_vol : blocks_zero;
         if (blocks > cap) blocks = cap;                // both loops are grid-stride
         if (blocks < 1) blocks = 1;
         tracklet_volume_kernel<<<(unsigned)blocks, 128, 0, st>>>(d_table, num_videos, total_tracklets,
                                                                 reinterpret_cast<const float4*>(d_boxes), d_span, vol,
-                                                                !clip, fx, total_pairs * 3);
+                                                                !clip, fx, single_chunk ? 0 : total_pairs * 3);
         TSPN_CUDA_OK(cudaGetLastError());
     }
     if (all || (phases & TSPN_GEO_PHASE_MAIN)) {
@@ -660,11 +716,15 @@ int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_ite
         const bool dense = (flags & TSPN_GEO_DENSE_CTAS) != 0;
 #define TSPN_GEO_SHAPE(T)                                                                                          \
     (dense ? launch_pair_geo<T, true>(d_table, num_videos, total_items, total_boxes, d_boxes, d_span, d_geo, fx,   \
-                                      clip, st)                                                                    \
+                                      d_overlap, clip, st)                                                         \
            : launch_pair_geo<T, false>(d_table, num_videos, total_items, total_boxes, d_boxes, d_span, d_geo, fx,  \
-                                       clip, st))
+                                       d_overlap, clip, st))
         if (geo_chunk == 512) rc = TSPN_GEO_SHAPE(128);
         else if (geo_chunk == 1024) rc = TSPN_GEO_SHAPE(256);
+#if TSPN_GEO_WIDE
+        else if (!dense) rc = launch_pair_geo<1024, false, 2>(d_table, num_videos, total_items, total_boxes, d_boxes,
+                                                              d_span, d_geo, fx, d_overlap, clip, st);
+#endif
         else rc = TSPN_GEO_SHAPE(512);
 #undef TSPN_GEO_SHAPE
         if (rc != TSPN_OK) return rc;
@@ -673,10 +733,10 @@ int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_ite
         const unsigned fblocks = (unsigned)((total_pairs + 255) / 256);
         if (clip)
             pair_finalize_kernel<true><<<fblocks, 256, 0, st>>>(d_table, num_videos, total_pairs, d_span, vol, fx,
-                                                                d_viou, d_tiou, d_overlap);
+                                                                d_viou, d_tiou);
         else
             pair_finalize_kernel<false><<<fblocks, 256, 0, st>>>(d_table, num_videos, total_pairs, d_span, vol, fx,
-                                                                 d_viou, d_tiou, d_overlap);
+                                                                 d_viou, d_tiou);
         TSPN_CUDA_OK(cudaGetLastError());
     }
     return TSPN_OK;

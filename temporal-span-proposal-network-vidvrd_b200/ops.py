@@ -63,6 +63,46 @@ def enumerate_pairs(batch: DeviceBatch) -> torch.Tensor:
     return out
 
 
+def single_chunk(batch: DeviceBatch) -> bool:
+    """Every video of the batch fits one chunk of the pair kernel (include/tspn_b200.h, TSPN_GEO_SINGLE_CHUNK)."""
+    tot = batch.totals
+    return int(tot[_lib.TOT_MAX_T]) <= int(tot[_lib.TOT_GEO_CHUNK])
+
+
+def pair_geometry_outputs(batch: DeviceBatch, write_geo: bool = True) -> Dict[str, torch.Tensor]:
+    """Caller-owned outputs and workspace of ``tspn_pair_geo_viou`` for this batch."""
+    dev, tot, p = batch.device, batch.totals, batch.total_pairs
+    out = {}
+    out["geo"] = torch.empty(int(tot[_lib.TOT_GEO_FLOATS]), dtype=torch.float32, device=dev) if write_geo else None
+    out["viou"] = torch.empty(p, dtype=torch.float32, device=dev)
+    out["tiou"] = torch.empty(p, dtype=torch.float32, device=dev)
+    out["overlap"] = torch.empty((p, 2), dtype=torch.int32, device=dev)
+    ws_bytes = load().tspn_pair_geo_workspace_bytes(batch.total_tracklets, batch.total_pairs)
+    out["workspace"] = torch.empty(ws_bytes // 8, dtype=torch.float64, device=dev)
+    return out
+
+
+def pair_geometry_phase(batch: DeviceBatch, out: Dict[str, torch.Tensor], phase: int, clipped: bool = False,
+                        dense_ctas: Optional[bool] = None) -> None:
+    """One phase of ``tspn_pair_geo_viou`` on the current stream: ``_lib.GEO_PHASE_PRE`` (per-tracklet volumes,
+    and zeroing of the per-pair sums unless the batch is single-chunk), ``GEO_PHASE_MAIN`` (the pair kernel:
+    geometry rows, fixed-point sums, overlap windows), ``GEO_PHASE_POST`` (vIoU / tIoU), or 0 for all three.
+    On a single-chunk batch PRE may run on another stream concurrently with MAIN; POST needs both."""
+    if dense_ctas is None:
+        dense_ctas = os.environ.get("TSPN_GEO_DENSE", "0") == "1"
+    tot = batch.totals
+    flags = (_lib.VIOU_CLIPPED if clipped else _lib.VIOU_FULL) | (_lib.GEO_DENSE_CTAS if dense_ctas else 0)
+    if single_chunk(batch):
+        flags |= _lib.GEO_SINGLE_CHUNK
+    check(load().tspn_pair_geo_viou(
+        ptr(batch.table), batch.num_videos, int(tot[_lib.TOT_ITEMS]), int(tot[_lib.TOT_GEO_CHUNK]),
+        batch.total_tracklets, batch.total_pairs,
+        int(tot[_lib.TOT_BOXES]), ptr(batch.boxes), ptr(batch.span), ptr(out.get("geo")), ptr(out["viou"]),
+        ptr(out["tiou"]), ptr(out["overlap"]), flags | phase, ptr(out["workspace"]), stream_ptr()),
+        "tspn_pair_geo_viou")
+    _count(3 if phase == 0 else 1)      # volumes (+ accumulator zeroing), pair kernel, per-pair finalize
+
+
 def pair_geometry(batch: DeviceBatch, write_geo: bool = True, clipped: bool = False,
                   out: Optional[Dict[str, torch.Tensor]] = None,
                   dense_ctas: Optional[bool] = None, events=None) -> Dict[str, torch.Tensor]:
@@ -72,38 +112,17 @@ def pair_geometry(batch: DeviceBatch, write_geo: bool = True, clipped: bool = Fa
     ``dense_ctas`` selects the 1024-threads-per-SM shape of the kernel (2-stage ring, 64 registers) instead of
     the default ~512 threads per SM (bit-identical results, measured slower; A/B timing only - default from
     the environment variable TSPN_GEO_DENSE)."""
-    if dense_ctas is None:
-        dense_ctas = os.environ.get("TSPN_GEO_DENSE", "0") == "1"
-    dev = batch.device
-    tot = batch.totals
-    p = batch.total_pairs
     if out is None:
-        out = {}
-        out["geo"] = torch.empty(int(tot[_lib.TOT_GEO_FLOATS]), dtype=torch.float32, device=dev) if write_geo else None
-        out["viou"] = torch.empty(p, dtype=torch.float32, device=dev)
-        out["tiou"] = torch.empty(p, dtype=torch.float32, device=dev)
-        out["overlap"] = torch.empty((p, 2), dtype=torch.int32, device=dev)
-        ws_bytes = load().tspn_pair_geo_workspace_bytes(batch.total_tracklets, batch.total_pairs)
-        out["workspace"] = torch.empty(ws_bytes // 8, dtype=torch.float64, device=dev)
-    flags = (_lib.VIOU_CLIPPED if clipped else _lib.VIOU_FULL) | (_lib.GEO_DENSE_CTAS if dense_ctas else 0)
-
-    def call(phase):
-        check(load().tspn_pair_geo_viou(
-            ptr(batch.table), batch.num_videos, int(tot[_lib.TOT_ITEMS]), int(tot[_lib.TOT_GEO_CHUNK]),
-            batch.total_tracklets, batch.total_pairs,
-            int(tot[_lib.TOT_BOXES]), ptr(batch.boxes), ptr(batch.span), ptr(out.get("geo")), ptr(out["viou"]),
-            ptr(out["tiou"]), ptr(out["overlap"]), flags | phase, ptr(out["workspace"]), stream_ptr()),
-            "tspn_pair_geo_viou")
+        out = pair_geometry_outputs(batch, write_geo)
     if events is None:
-        call(0)
+        pair_geometry_phase(batch, out, 0, clipped, dense_ctas)
     else:
-        stream = torch.cuda.current_stream(dev)
-        call(_lib.GEO_PHASE_PRE)
+        stream = torch.cuda.current_stream(batch.device)
+        pair_geometry_phase(batch, out, _lib.GEO_PHASE_PRE, clipped, dense_ctas)
         events[0].record(stream)
-        call(_lib.GEO_PHASE_MAIN)
+        pair_geometry_phase(batch, out, _lib.GEO_PHASE_MAIN, clipped, dense_ctas)
         events[1].record(stream)
-        call(_lib.GEO_PHASE_POST)
-    _count(3)       # volumes + accumulator zeroing, pair kernel, per-pair finalize
+        pair_geometry_phase(batch, out, _lib.GEO_PHASE_POST, clipped, dense_ctas)
     return out
 
 

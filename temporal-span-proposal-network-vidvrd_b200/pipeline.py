@@ -192,10 +192,29 @@ class PairStage:
         return (features is None and self.cfg.precision == "tensor" and self.packed_rel is not None
                 and not self.cfg.materialize_features)
 
-    def _seg_geo(self, batch: DeviceBatch, features: Optional[torch.Tensor], events=None):
+    # The geometry call is three phases (include/tspn_b200.h): PRE (per-tracklet volumes; zeroing of the
+    # per-pair sums when a video spans several chunks), MAIN (the pair kernel) and POST (vIoU / tIoU).  Only
+    # MAIN is on the critical path: on a single-chunk batch PRE runs on the side stream under MAIN, and POST
+    # always runs on the side stream under the tail (feature rows and records read the overlap windows, which
+    # MAIN writes; vIoU / tIoU are outputs only).
+    def _geo_alloc(self, batch: DeviceBatch, features: Optional[torch.Tensor]):
         c = self.cfg
         need_geo = features is None or c.use_dpn
-        return ops.pair_geometry(batch, write_geo=need_geo and c.write_geo, clipped=c.viou_clipped, events=events)
+        return ops.pair_geometry_outputs(batch, write_geo=need_geo and c.write_geo)
+
+    def _seg_pre(self, batch: DeviceBatch, geom) -> None:
+        ops.pair_geometry_phase(batch, geom, _lib.GEO_PHASE_PRE, clipped=self.cfg.viou_clipped)
+
+    def _seg_geo(self, batch: DeviceBatch, geom, events=None, with_pre: bool = False):
+        stream = torch.cuda.current_stream(batch.device)
+        if with_pre:
+            self._seg_pre(batch, geom)
+        if events is not None:
+            events[0].record(stream)
+        ops.pair_geometry_phase(batch, geom, _lib.GEO_PHASE_MAIN, clipped=self.cfg.viou_clipped)
+        if events is not None:
+            events[1].record(stream)
+        return geom
 
     def _seg_tail(self, batch: DeviceBatch, features, heads, side, geom) -> StageResult:
         c = self.cfg
@@ -210,9 +229,10 @@ class PairStage:
         main = torch.cuda.current_stream(batch.device)
         side_stream = self._side_stream(batch.device)
         fork_spans = heads and c.use_dpn
-        if fork_spans:
-            side_stream.wait_stream(main)
-            with torch.cuda.stream(side_stream):
+        side_stream.wait_stream(main)
+        with torch.cuda.stream(side_stream):
+            ops.pair_geometry_phase(batch, geom, _lib.GEO_PHASE_POST, clipped=c.viou_clipped)
+            if fork_spans:
                 span_reg, spans, span_bufs = self._span_heads(batch, geom, row, k_eff)
         decomposed = self._decomposed(features)
         if decomposed:
@@ -248,11 +268,10 @@ class PairStage:
             else:
                 records, counts = ops.postprocess(batch, logits, geom["overlap"], c.topk_per_pair, c.topk_per_video,
                                                   mirror_q4=c.mirror_q4)
-        if fork_spans:
-            main.wait_stream(side_stream)
-            if not torch.cuda.is_current_stream_capturing():
-                for tns in (span_bufs or []) + (span_reg or []):
-                    tns.record_stream(main)          # allocated on the side stream, read on the caller's
+        main.wait_stream(side_stream)
+        if fork_spans and not torch.cuda.is_current_stream_capturing():
+            for tns in (span_bufs or []) + (span_reg or []):
+                tns.record_stream(main)          # allocated on the side stream, read on the caller's
         return StageResult(batch, geom, scores, idx, val, row, feats32, feats16, logits, span_reg, spans, k_eff,
                            sparsify, records, counts, span_bufs)
 
@@ -263,8 +282,12 @@ class PairStage:
         ``timers``: receives ``{"geo": (start, end)}`` CUDA events around the geometry kernel."""
         main = torch.cuda.current_stream(batch.device)
         side_stream = self._side_stream(batch.device)
+        geom = self._geo_alloc(batch, features)
+        pre_aside = ops.single_chunk(batch)           # PRE under MAIN (see _seg_geo)
         side_stream.wait_stream(main)                 # fork: inputs are ready on the caller's stream
         with torch.cuda.stream(side_stream):
+            if pre_aside:
+                self._seg_pre(batch, geom)
             side = self._seg_side(batch, features)
         for t in side:
             for u in (t if isinstance(t, tuple) else (t,)):
@@ -274,7 +297,7 @@ class PairStage:
         if timers is not None:      # CUDA events around the dominant kernel, on the launching stream
             events = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             timers["geo"] = events
-        geom = self._seg_geo(batch, features, events=events)
+        self._seg_geo(batch, geom, events=events, with_pre=not pre_aside)
         main.wait_stream(side_stream)                 # join
         return self._seg_tail(batch, features, heads, side, geom)
 
@@ -359,6 +382,10 @@ class GraphedStage:
         # the pair kernel's own timing: external event-record nodes inside the graph
         self.ev_geo = (torch.cuda.Event(enable_timing=True, external=True),
                        torch.cuda.Event(enable_timing=True, external=True))
+        # the geometry outputs are allocated outside the graphs: the PRE phase (side branch) and the pair kernel
+        # (main branch) both write into them
+        geom = stage._geo_alloc(batch, features)
+        pre_aside = ops.single_chunk(batch)
         if self.single:
             self.graph = torch.cuda.CUDAGraph()
             fork = stage._side_stream(dev)
@@ -366,8 +393,10 @@ class GraphedStage:
                 cap = torch.cuda.current_stream(dev)
                 fork.wait_stream(cap)
                 with torch.cuda.stream(fork):
+                    if pre_aside:
+                        stage._seg_pre(batch, geom)
                     side = stage._seg_side(batch, features)
-                geom = stage._seg_geo(batch, features, events=self.ev_geo)
+                stage._seg_geo(batch, geom, events=self.ev_geo, with_pre=not pre_aside)
                 cap.wait_stream(fork)
                 self.result = stage._seg_tail(batch, features, heads, side, geom)
         else:
@@ -376,9 +405,11 @@ class GraphedStage:
             # g_side and g_geo replay CONCURRENTLY (different streams): they must not share a memory pool, or a
             # temporary freed at the end of one capture is handed to the other and both write it at replay
             with torch.cuda.graph(self.g_side, stream=self._cap_stream):
+                if pre_aside:
+                    stage._seg_pre(batch, geom)
                 side = stage._seg_side(batch, features)
             with torch.cuda.graph(self.g_geo, stream=self._cap_stream):
-                geom = stage._seg_geo(batch, features, events=self.ev_geo)
+                stage._seg_geo(batch, geom, events=self.ev_geo, with_pre=not pre_aside)
             with torch.cuda.graph(self.g_tail, stream=self._cap_stream):
                 self.result = stage._seg_tail(batch, features, heads, side, geom)
         self.kernels_per_replay = ops.launch_count() - n0

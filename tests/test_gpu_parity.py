@@ -108,6 +108,45 @@ def test_dense_and_sparse_kernel_shapes_are_bit_identical(shapes, clip):
         assert torch.equal(a[key], c[key]), key
 
 
+@pytest.mark.parametrize("shapes", [
+    [(20, 300, 0), (5, 37, 11), (9, 512, 8), (2, 1, 3), (1, 9, 4), (0, 5, 5)],      # single chunk (512)
+    [(12, 2000, 1), (70, 1500, 2)],                                                # single chunk (2048), two groups
+    [(3, 4100, 2), (4, 2049, 4), (5, 2048, 5)],                                    # several chunks per row
+])
+@pytest.mark.parametrize("clip", [False, True])
+def test_pair_geometry_phases_on_two_streams_and_stale_sums(shapes, clip):
+    """The three phases of tspn_pair_geo_viou issued the way the pipeline issues them - PRE on a side stream under
+    MAIN when every video fits one chunk (TSPN_GEO_SINGLE_CHUNK: single-writer sums are stored, nothing is
+    zeroed), POST on the side stream after both - onto outputs that still hold another batch's sums and
+    windows: bit-identical to the one-call form on fresh outputs."""
+    vids = [synth.make_video(n, t, 35, seed=s) for n, t, s in shapes]
+    batch = _batch(vids)
+    want = ops.pair_geometry(batch, write_geo=True, clipped=clip)
+    out = ops.pair_geometry_outputs(batch, write_geo=True)
+    for key in ("viou", "tiou"):
+        out[key].fill_(float("nan"))
+    out["overlap"].fill_(-7)
+    out["workspace"].view(torch.int64).fill_(0x0123456789abcdef)         # stale volumes and per-pair sums
+    torch.cuda.synchronize()
+    main, side = torch.cuda.current_stream(), torch.cuda.Stream()
+    aside = ops.single_chunk(batch)
+    assert aside == all(t <= 2048 for _, t, _ in shapes)
+    side.wait_stream(main)
+    if aside:
+        with torch.cuda.stream(side):
+            ops.pair_geometry_phase(batch, out, _lib.GEO_PHASE_PRE, clipped=clip)
+    else:
+        ops.pair_geometry_phase(batch, out, _lib.GEO_PHASE_PRE, clipped=clip)
+    ops.pair_geometry_phase(batch, out, _lib.GEO_PHASE_MAIN, clipped=clip)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        ops.pair_geometry_phase(batch, out, _lib.GEO_PHASE_POST, clipped=clip)
+    main.wait_stream(side)
+    torch.cuda.synchronize()
+    for key in ("geo", "viou", "tiou", "overlap"):
+        assert torch.equal(want[key], out[key]), key
+
+
 def test_pair_geometry_reductions_only_and_fractional_boxes():
     v = synth.make_video(11, 700, 35, seed=21, integer_boxes=False)
     batch = _batch([v])

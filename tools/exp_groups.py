@@ -55,7 +55,7 @@ def capture(groups, geo_streams, tail_priority):
         for g, b in enumerate(batches):
             s = s_geo[g % geo_streams]
             with torch.cuda.stream(s):
-                geoms.append(stage._seg_geo(b, None))
+                geoms.append(stage._seg_geo(b, stage._geo_alloc(b, None), with_pre=True))
                 e = torch.cuda.Event()
                 e.record(s)
                 ev_geo.append(e)
