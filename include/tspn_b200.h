@@ -81,7 +81,7 @@ extern "C" {
  * tracklets, chunk of tspn_geo_chunk(max T of the batch) frames), numbered chunk-fastest; the table's
  * TSPN_VT_ITEM_OFF column and totals[TSPN_TOT_ITEMS] count them. */
 #ifndef TSPN_GEO_OBJ_GROUP
-#define TSPN_GEO_OBJ_GROUP 64
+#define TSPN_GEO_OBJ_GROUP 32
 #endif
 
 /* geometry channels of geo[P][8][Tp] ([SPEC] s2) */
@@ -109,6 +109,11 @@ extern "C" {
  * (per-tracklet volumes only) may be issued on another stream concurrently with MAIN; POST needs both.  MAIN
  * writes d_overlap; POST writes d_viou / d_tiou.  Pass the flag to every phase of the call. */
 #define TSPN_GEO_SINGLE_CHUNK 64
+/* MAIN as persistent CTAs (one per SM slot for the whole launch) that pull work items from a queue in the
+ * workspace, instead of one CTA per work item: same results bit for bit.  Kernels issued concurrently on
+ * other streams can then only co-reside with the pair kernel's CTAs - they can never take over an SM between
+ * two of its CTAs and lock the next one out. */
+#define TSPN_GEO_PERSISTENT 128
 #define TSPN_TOPK_KEEP_DIAGONAL 0    /* reference behaviour, ppn.py:84-85 (quirk Q1) */
 #define TSPN_TOPK_EXCLUDE_DIAGONAL 1 /* survivors are real pairs (sparsify mode) */
 #define TSPN_PREC_FP32_EXACT 0 /* CUDA cores, fixed k-ascending fma order: bit-reproducible */
@@ -247,6 +252,11 @@ int tspn_predicate_head(const void* d_x, int x_is_bf16, int64_t ld_x, int64_t m,
  *                           bias row A_s[s] + A_o[o] gathered from d_terms_subject / d_terms_object [n_tracklets][R]
  *                           (padding rows: zeros).  Workspace of the head: tspn_predicate_workspace_bytes. */
 #define TSPN_AFFINE_RAW 1
+/* The call runs on a side stream underneath a kernel that keeps every SM occupied (the pair-geometry kernel:
+ * one CTA with 134 KB of shared memory and 53 K registers per SM): a 3-stage TMA ring (<= 80 KB) and at most 4
+ * K-splits, so that its CTAs co-reside with that kernel's instead of each waiting for - and then holding - a
+ * whole SM.  Same results as without the flag up to the split-K summation order. */
+#define TSPN_AFFINE_BACKGROUND 2
 int tspn_tracklet_rows(const float* d_cls, int n_classes, const void* d_motion, int motion_is_u8,
                        int64_t n_tracklets, void* d_out_bf16, int64_t ld, void* stream);
 int tspn_predicate_head_affine(const void* d_x, int x_is_bf16, int64_t ld_x, int64_t m, int feature_dim,
@@ -283,11 +293,32 @@ int tspn_span_proposals(const float* d_x, const int64_t* d_rows, int64_t row_bas
                         const float* d_pred_w, const float* d_pred_b, int n_anchors,
                         const float* d_sizes, float stride, int32_t* d_spans, void* stream);
 
+/* ---- surviving pairs: relative block + bias row + span proposals, recomputed from the boxes ------------
+ * For every row the top-K kept (d_rows: global pair rows, [V][rows_per_video], -1 = padding) this produces
+ * exactly what tspn_assemble_relative and tspn_span_proposals produce from the stored geometry rows of
+ * tspn_pair_geo_viou - bit for bit (same per-frame device code, same summation orders) - but from the boxes:
+ * it does not depend on the all-pairs kernel and is shaped to co-reside with it (128 threads, <= 96
+ * registers, 32*(max_frames+4) bytes of shared memory), so the heads of the K survivors run on a
+ * side stream underneath the HBM-bound all-pairs kernel instead of re-reading 64 KB per row behind it.
+ * d_spans (may be NULL: no span head) int32 [n_rows][ld_spans]: row r holds [locations(T_v) * A][2] frame
+ * bounds of its video, zero-filled up to ld_spans >= locations(max_frames) * 2A.  Span weights as for
+ * tspn_span_proposals with Cin = 8.  tspn_survivor_rows_supported: n_anchors == 4 and the tile of
+ * max_frames frames fits shared memory; otherwise use the two stored-row entry points. */
+int tspn_survivor_rows_supported(int max_frames, int n_anchors);
+int tspn_survivor_rows(const int64_t* d_table, int num_videos, int max_frames, const float* d_boxes,
+                       const int32_t* d_span, const int64_t* d_rows, int64_t n_rows, int64_t rows_per_video,
+                       void* d_rel_bf16, int64_t ld_rel, const float* d_terms_subject,
+                       const float* d_terms_object, int n_outputs, float* d_row_bias,
+                       const float* d_conv_w, const float* d_conv_b, const float* d_pred_w,
+                       const float* d_pred_b, int n_anchors, const float* d_sizes, float stride,
+                       int32_t* d_spans, int64_t ld_spans, void* stream);
+
 /* ---- N1: predict.py:66-117 post-processing ------------------------------------------------
  * per video: top `topk_per_pair` predicates per scored row (predict.py:70-73), then top
  * `topk_per_video` overall (predict.py:76-81), both descending with ties to the lower index;
  * one 32-byte record per kept triplet: {score f32, s_cls, pred, o_cls, s_tid, o_tid, start,
- * end : i32} (start/end = the pair's temporal overlap window).
+ * end : i32} (start/end = the pair's temporal overlap window, read from d_overlap [P][2] - or, when that
+ * is NULL, derived from the tracklet spans d_span, so that the records need not wait for the pair kernel).
  * d_logits [n_rows][r]; row i scores global pair row d_rows[i] (NULL = identity, -1 = padding);
  * video v owns rows [d_row_video_off[v], d_row_video_off[v+1]) (NULL = its pair rows).
  * flags: TSPN_POST_MIRROR_Q4 reproduces predict.py:89's wrong-row object class.
@@ -297,7 +328,7 @@ int64_t tspn_postprocess_workspace_bytes(int64_t n_rows, int topk_per_pair);
 int tspn_postprocess(const int64_t* d_table, int num_videos, const float* d_logits,
                      const int64_t* d_rows, const int64_t* d_row_video_off, int64_t n_rows,
                      int n_predicates, const float* d_cls, int n_classes, const int32_t* d_overlap,
-                     int topk_per_pair, int topk_per_video, int flags,
+                     const int32_t* d_span, int topk_per_pair, int topk_per_video, int flags,
                      int32_t* d_records, int32_t* d_counts, void* d_workspace, void* stream);
 
 #ifdef __cplusplus

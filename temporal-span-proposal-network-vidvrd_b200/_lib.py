@@ -21,7 +21,7 @@ TOT_COLS = 10
 TOT_TRACKLETS, TOT_PAIRS, TOT_GEO_FLOATS, TOT_ITEMS, TOT_BOXES, TOT_SCORES, TOT_MAX_N, TOT_MAX_T, TOT_GEO_CHUNK = range(9)
 
 ABI_VERSION = 4
-GEO_OBJ_GROUP = 64        # include/tspn_b200.h: objects per work item of the pair-geometry kernel
+GEO_OBJ_GROUP = 32        # include/tspn_b200.h: objects per work item of the pair-geometry kernel
 GEO_CHANNELS = 8
 MOTION_DIM = 4000
 REL_DIM = 3000
@@ -29,9 +29,11 @@ VIOU_FULL, VIOU_CLIPPED = 0, 1
 GEO_DENSE_CTAS = 2
 GEO_PHASE_PRE, GEO_PHASE_MAIN, GEO_PHASE_POST = 8, 16, 32
 GEO_SINGLE_CHUNK = 64
+GEO_PERSISTENT = 128
 TOPK_KEEP_DIAGONAL, TOPK_EXCLUDE_DIAGONAL = 0, 1
 PREC_FP32_EXACT, PREC_TENSOR = 0, 1
 AFFINE_RAW = 1
+AFFINE_BACKGROUND = 2
 
 P = c_void_p      # device pointers travel as integers (tensor.data_ptr())
 
@@ -71,7 +73,10 @@ SIGNATURES = {
     "tspn_span_proposals": (c_int, [P, P, c_int64, c_int64, c_int64, c_int64, c_int, c_int, P, P, P, P, c_int, P,
                                     c_float, P, P]),
     "tspn_postprocess_workspace_bytes": (c_int64, [c_int64, c_int]),
-    "tspn_postprocess": (c_int, [P, c_int, P, P, P, c_int64, c_int, P, c_int, P, c_int, c_int, c_int, P, P, P, P]),
+    "tspn_postprocess": (c_int, [P, c_int, P, P, P, c_int64, c_int, P, c_int, P, P, c_int, c_int, c_int, P, P, P, P]),
+    "tspn_survivor_rows_supported": (c_int, [c_int, c_int]),
+    "tspn_survivor_rows": (c_int, [P, c_int, c_int, P, P, P, c_int64, c_int64, P, c_int64, P, P, c_int, P, P, P, P, P,
+                                   c_int, P, c_float, P, c_int64, P]),
 }
 
 _lib = None

@@ -125,27 +125,17 @@ __device__ __forceinline__ void st_stream_f4(float* p, float4 v) {
                  : "memory");
 }
 
-__device__ __forceinline__ void st_stream_f2(float* p, float2 v) {
-    asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
-}
-// 1-D bulk store shared -> global, tracked by the issuing thread's bulk async-group (SASS: UBLKCP);
-// both addresses 16-byte aligned, bytes a multiple of 16.  HINT = 2 adds an L2 evict_first policy.
-template <int HINT = 1>
-__device__ __forceinline__ void bulk_store_1d(void* gdst, const void* smem_src, uint32_t bytes) {
-    if (HINT == 2) {
-        uint64_t policy;
-        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
-                     ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes), "l"(policy) : "memory");
-    } else {
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                     ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
-    }
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-// the calling thread's bulk stores have finished READING shared memory (the source may be overwritten)
-__device__ __forceinline__ void bulk_wait_read0() {
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+
+// ---- host: shared-memory carve-out ------------------------------------------------------------
+// An SM's L1 / shared-memory split is a per-SM mode that only changes when the SM is idle.  The pair kernel needs
+// 134 KB per CTA; left to the driver that means a 164 KB carve-out, i.e. 29 KB for anything that wants to
+// co-reside with it - and a kernel preferring another split waits for (or takes over) whole SMs.  Every kernel
+// of the pair stage therefore asks for the maximum carve-out (228 KB): the pair kernel leaves 93 KB per SM to the
+// side stream's kernels, and no launch ever makes an SM drain to switch modes.
+template <typename Kernel>
+inline void prefer_max_smem(Kernel kernel) {
+    cudaFuncSetAttribute(reinterpret_cast<const void*>(kernel), cudaFuncAttributePreferredSharedMemoryCarveout,
+                         (int)cudaSharedmemCarveoutMaxShared);
 }
 
 // ---- host: tensor maps ---------------------------------------------------------------------

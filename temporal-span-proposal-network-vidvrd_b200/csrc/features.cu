@@ -318,6 +318,8 @@ int tspn_tracklet_rows(const float* d_cls, int n_classes, const void* d_motion, 
                  "tspn_tracklet_rows: ld=%lld must be >= C+4000 and a multiple of 8", (long long)ld);
     TSPN_REQUIRE(aligned16(d_out_bf16), TSPN_EALIGN, "tspn_tracklet_rows: output must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
+    prefer_max_smem(tracklet_rows_kernel<true>);
+    prefer_max_smem(tracklet_rows_kernel<false>);
     if (motion_is_u8)
         tracklet_rows_kernel<true><<<(unsigned)n_tracklets, 128, 0, st>>>(d_cls, n_classes, d_motion, n_tracklets,
                                                                           reinterpret_cast<__nv_bfloat16*>(d_out_bf16), ld);
@@ -344,6 +346,7 @@ int tspn_assemble_relative(const int64_t* d_table, int num_videos, int64_t total
                  "tspn_assemble_relative: ld_rel=%lld must be >= 3000 and a multiple of 8", (long long)ld_rel);
     TSPN_REQUIRE(aligned16(d_rel_bf16), TSPN_EALIGN, "tspn_assemble_relative: output must be 16-byte aligned");
     TSPN_REQUIRE(n_rows < (1ll << 31), TSPN_ESHAPE, "tspn_assemble_relative: too many rows");
+    prefer_max_smem((assemble_kernel<true, true>));
     assemble_kernel<true, true><<<(unsigned)n_rows, ASM_THREADS, 0, (cudaStream_t)stream>>>(
         d_table, num_videos, d_terms_subject, n_outputs, d_terms_object, d_geo, d_overlap, d_rows, d_row_bias, n_outputs,
         reinterpret_cast<__nv_bfloat16*>(d_rel_bf16), ld_rel);

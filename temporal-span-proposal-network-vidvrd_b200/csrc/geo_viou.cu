@@ -14,20 +14,19 @@
 //     shared memory by 2-D tiled TMA (cp.async.bulk.tensor -> UTMALDG) with SWIZZLE_128B into a
 //     ring on full/empty mbarriers: the subject chunk is loaded once per item, the object chunks
 //     stream behind the compute of the previous objects;
-//   * a thread owns 4 (or 2) consecutive frames: the swizzle makes its LDS.128 box reads
-//     bank-conflict free, and every channel leaves as one vector streaming store (a warp writes
-//     512 contiguous bytes per channel row) - or, with TSPN_GEO_TMA_STORE, through a per-warp
-//     shared-memory tile that leaves as 1-D bulk stores (cp.async.bulk.global.shared::cta);
+//   * a thread owns 4 consecutive frames: the swizzle makes its five LDS.128 box reads
+//     bank-conflict free, and every channel leaves as one 128-bit streaming store (a warp writes
+//     512 contiguous bytes per channel row);
 //   * intersection volumes accumulate as 64-bit fixed point (exact for integer boxes; integer
 //     adds -> the result does not depend on any reduction or scheduling order);
 //   * per-tracklet volumes come from a small pre-kernel (one CTA per tracklet), vIoU / tIoU from a
 //     small post-kernel; the pair kernel itself writes the overlap windows.
 // Algorithmic bytes: 32*Tp written + 24 B of reductions per pair; boxes are re-read from L2.
 #include "common.cuh"
+#include "geo_math.cuh"
 
 namespace tspn {
 
-constexpr int GEO_FPT = 4;                            // frames per thread (default shapes)
 constexpr int GEO_OG = TSPN_GEO_OBJ_GROUP;
 #ifndef TSPN_GEO_RING
 #define TSPN_GEO_RING 3
@@ -37,12 +36,6 @@ constexpr int GEO_RING = TSPN_GEO_RING;               // object-chunk stages in 
 #define TSPN_GEO_ROTATE 1
 #endif
 constexpr bool GEO_ROTATE = TSPN_GEO_ROTATE != 0;     // rotate the warps' frame blocks with the object index
-#ifndef TSPN_GEO_TMA_STORE
-#define TSPN_GEO_TMA_STORE 0                          // 1: bulk stores from shared memory, 2: + L2 evict_first hint
-#endif
-#ifndef TSPN_GEO_WIDE
-#define TSPN_GEO_WIDE 0                               // 1: the 2048-frame shape is 1024 threads x 2 frames
-#endif
 
 // Shape of one CTA: THREADS threads cover a chunk of 4*THREADS frames (512 / 1024 / 2048, chosen per
 // batch by tspn_geo_chunk).  HBM absorbs this kernel's store stream best as few, wide streams
@@ -56,9 +49,9 @@ constexpr bool GEO_ROTATE = TSPN_GEO_ROTATE != 0;     // rotate the warps' frame
 //                  0.707 ms for the default - kept, bit-identical and tested, as the record of that A/B
 //                  (profiles/r1_geo_kernel_forms_ab.md).
 // The shared-memory request pins the occupancy.
-template <int THREADS, bool DENSE, int FPT = GEO_FPT>
+template <int THREADS, bool DENSE>
 struct GeoCfg {
-    static constexpr int CHUNK = THREADS * FPT;
+    static constexpr int CHUNK = THREADS * GEO_FPT;
     static constexpr int WARPS = THREADS / 32;
     static constexpr int RING = DENSE ? 2 : GEO_RING;             // object-chunk stages in flight
     static constexpr int STAGES = 1 + RING;                       // subject chunk + object ring
@@ -69,50 +62,15 @@ struct GeoCfg {
     static constexpr int STAGE_BYTES = ROWS * 128;                // stages are packed (128-byte aligned)
     static constexpr int MIN_CTAS = DENSE ? 1024 / THREADS : (THREADS >= 512 ? 1 : (THREADS == 256 ? 2 : 3));
     // barriers, per-object fixed-point sums, per-object overlap windows
-    static constexpr int TAIL_BYTES = (2 * RING * 8 + GEO_OG * (3 * 8 + 8) + 127) / 128 * 128;
-    // TSPN_GEO_TMA_STORE: the channels leave through a per-warp shared-memory tile as 1-D bulk stores
-    static constexpr bool BULK_OUT = !DENSE && (TSPN_GEO_TMA_STORE != 0);
-    static constexpr int OUT_BYTES = BULK_OUT ? WARPS * TSPN_GEO_CHANNELS * 32 * FPT * 4 : 0;
-    static constexpr int SMEM_USED = STAGES * STAGE_BYTES + TAIL_BYTES + OUT_BYTES;
-    static constexpr int SMEM_PIN = 227 * 1024 / (MIN_CTAS + 1) + 1024;
+    static constexpr int TAIL_BYTES = (2 * RING * 8 + GEO_OG * (3 * 8 + 8) + 16 + 127) / 128 * 128;
+    static constexpr int SMEM_USED = STAGES * STAGE_BYTES + TAIL_BYTES;
+    // the 512-thread shape is already limited to one CTA per SM by its registers (16 warps x 104): no padding,
+    // every byte it does not use is left to co-resident kernels of the side stream
+    static constexpr int SMEM_PIN = (THREADS >= 512 && !DENSE) ? 0 : 227 * 1024 / (MIN_CTAS + 1) + 1024;
     static constexpr int SMEM_BYTES = SMEM_USED > SMEM_PIN ? SMEM_USED : SMEM_PIN;
     static_assert((SMEM_BYTES + 1024) * MIN_CTAS <= 228 * 1024, "the stages of MIN_CTAS CTAs must fit one SM");
 };
 
-// box j of a chunk staged with SWIZZLE_128B: the 16-byte slot index (address bits 4..6) is XORed
-// with address bits 7..9 of the shared-memory address, so the pattern is a function of the
-// absolute address and stages only need 128-byte alignment.
-__device__ __forceinline__ float4 ld_box(uint32_t stage_addr, int j) {
-    const uint32_t lin = stage_addr + ((uint32_t)j << 4);
-    const uint32_t phys = lin ^ (((lin >> 7) & 7u) << 4);
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(phys));
-    return v;
-}
-
-__device__ __forceinline__ float rcp_fast(float x) {          // MUFU.RCP, <= 1 ulp
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float lg2_fast(float x) {          // MUFU.LG2, abs err 2^-22.6
-    float r;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-// log(a / b) for a, b >= 1.  Near a == b the quotient form loses relative accuracy, so the result is
-// 2*atanh(z), z = (a-b)/(a+b), as an odd series (|z| < 0.15: truncation < 1e-9 relative); elsewhere
-// ln2 * lg2(a/b), whose absolute error is far below 1e-5 of a result that is at least 0.3.
-__device__ __forceinline__ float log_ratio(float a, float b, float rb) {
-    const float z = (a - b) * rcp_fast(a + b);
-    const float z2 = z * z;
-    float p = fmaf(z2, 1.0f / 9.0f, 1.0f / 7.0f);
-    p = fmaf(z2, p, 1.0f / 5.0f);
-    p = fmaf(z2, p, 1.0f / 3.0f);
-    const float near = 2.0f * fmaf(z * z2, p, z);
-    const float far = 0.69314718056f * lg2_fast(a * rb);
-    return fabsf(z) < 0.15f ? near : far;
-}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -180,84 +138,15 @@ __device__ __forceinline__ unsigned long long warp_sum_fx(float v) {
     return (unsigned long long)lo + ((unsigned long long)hi << 24);
 }
 
-// ---- one (pair, 4 frames) step of a thread: the eight channels + the three fp32 partial sums ----------
-// per-thread partial sums stay in fp32: 4 integer-valued products <= 4 * 2^21 < 2^24 are exact
-template <bool CLIP, int GEO_FPT>
-__device__ __forceinline__ void geo_step(uint32_t ss, uint32_t os_addr, int j0, int t0, int a, int b,
-                                         float (&out)[TSPN_GEO_CHANNELS][GEO_FPT], float& fsum_i, float& fsum_s,
-                                         float& fsum_o) {
-    fsum_i = 0.0f; fsum_s = 0.0f; fsum_o = 0.0f;
-#pragma unroll
-    for (int ch = 0; ch < TSPN_GEO_CHANNELS; ++ch)
-#pragma unroll
-        for (int i = 0; i < GEO_FPT; ++i) out[ch][i] = 0.0f;
-    if (!(t0 < b && t0 + GEO_FPT > a)) return;
-    float dcx[GEO_FPT + 1], dcy[GEO_FPT + 1], wo[GEO_FPT + 1], ho[GEO_FPT + 1];
-    float rwo[GEO_FPT + 1], rho[GEO_FPT + 1];
-#pragma unroll
-    for (int i = 0; i <= GEO_FPT; ++i) {
-        const float4 sb = ld_box(ss, j0 + i);
-        const float4 ob = ld_box(os_addr, j0 + i);
-        wo[i] = (ob.z - ob.x) + 1.0f;
-        ho[i] = (ob.w - ob.y) + 1.0f;
-        rwo[i] = rcp_fast(wo[i]);
-        rho[i] = rcp_fast(ho[i]);
-        // centre deltas from coordinate differences: exact for integer boxes and
-        // free of the cancellation that (x1+x2)/2 - (x1'+x2')/2 would carry
-        dcx[i] = 0.5f * ((sb.x - ob.x) + (sb.z - ob.z));
-        dcy[i] = 0.5f * ((sb.y - ob.y) + (sb.w - ob.w));
-        if (i < GEO_FPT) {
-            const int t = t0 + i;
-            const bool in = (t >= a) && (t < b);
-            const float ws = (sb.z - sb.x) + 1.0f, hs = (sb.w - sb.y) + 1.0f;
-            const float iw = fmaxf((fminf(sb.z, ob.z) - fmaxf(sb.x, ob.x)) + 1.0f, 0.0f);
-            const float ih = fmaxf((fminf(sb.w, ob.w) - fmaxf(sb.y, ob.y)) + 1.0f, 0.0f);
-            // explicit rounding points: the volume sums must not depend on whether the
-            // compiler contracts these products into the accumulation (template variants)
-            const float inter = __fmul_rn(iw, ih);
-            const float as = __fmul_rn(ws, hs), ao = __fmul_rn(wo[i], ho[i]);
-            if (in) {
-                out[0][i] = dcx[i] * rwo[i];
-                out[1][i] = dcy[i] * rho[i];
-                out[2][i] = log_ratio(ws, wo[i], rwo[i]);
-                out[3][i] = log_ratio(hs, ho[i], rho[i]);
-                out[4][i] = inter * rcp_fast((as + ao) - inter);
-                out[7][i] = 1.0f;
-                fsum_i = __fadd_rn(fsum_i, inter);
-                if (CLIP) {
-                    fsum_s = __fadd_rn(fsum_s, as);
-                    fsum_o = __fadd_rn(fsum_o, ao);
-                }
-            }
-        }
-    }
-    // forward differences in closed form:
-    //   c0[t+1]-c0[t] = (dcx[t+1]*wo[t] - dcx[t]*wo[t+1]) / (wo[t]*wo[t+1])
-    // (two-product compensation keeps the numerator exact to one rounding)
-#pragma unroll
-    for (int i = 0; i < GEO_FPT; ++i) {
-        const int t = t0 + i;
-        if (t >= a && t + 1 < b) {
-            float p = dcx[i] * wo[i + 1];
-            float e = fmaf(dcx[i], wo[i + 1], -p);
-            out[5][i] = (fmaf(dcx[i + 1], wo[i], -p) - e) * (rwo[i] * rwo[i + 1]);
-            p = dcy[i] * ho[i + 1];
-            e = fmaf(dcy[i], ho[i + 1], -p);
-            out[6][i] = (fmaf(dcy[i + 1], ho[i], -p) - e) * (rho[i] * rho[i + 1]);
-        }
-    }
-}
 
-template <int THREADS, bool WRITE_GEO, bool CLIP, bool DENSE, int FPT>
-__global__ void __launch_bounds__(THREADS, GeoCfg<THREADS, DENSE, FPT>::MIN_CTAS)
+template <int THREADS, bool WRITE_GEO, bool CLIP, bool DENSE>
+__global__ void __launch_bounds__(THREADS, GeoCfg<THREADS, DENSE>::MIN_CTAS)
 pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __restrict__ table, int nv,
                 const int32_t* __restrict__ span, float* __restrict__ geo, unsigned long long* __restrict__ fx,
-                int32_t* __restrict__ overlap) {
-    using Cfg = GeoCfg<THREADS, DENSE, FPT>;
+                int32_t* __restrict__ overlap, unsigned int* __restrict__ queue, unsigned int total_items) {
+    using Cfg = GeoCfg<THREADS, DENSE>;
     constexpr int GEO_CHUNK = Cfg::CHUNK, GEO_WARPS = Cfg::WARPS, GEO_STAGE_BYTES = Cfg::STAGE_BYTES;
     constexpr int GEO_TX_BYTES = Cfg::TX_BYTES, GEO_SPLIT = Cfg::SPLIT, RING = Cfg::RING;
-    constexpr int GEO_FPT = FPT;
-    constexpr bool BULK_OUT = WRITE_GEO && Cfg::BULK_OUT;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* const s_stage = smem;
     uint8_t* const o_stage0 = smem + GEO_STAGE_BYTES;
@@ -265,32 +154,11 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
     uint64_t* const empty = full + RING;                                                       // [RING]
     unsigned long long* const acc = reinterpret_cast<unsigned long long*>(empty + RING);       // [OG][3]
     int2* const owin = reinterpret_cast<int2*>(acc + GEO_OG * 3);                              // [OG] overlap windows
-    // BULK_OUT: one [8 channels][32 * FPT frames] output tile per warp, behind the staging area
-    float* const out_tile = reinterpret_cast<float*>(smem + Cfg::STAGES * GEO_STAGE_BYTES + Cfg::TAIL_BYTES) +
-                            (threadIdx.x >> 5) * (TSPN_GEO_CHANNELS * 32 * FPT);
+    unsigned int* const s_item = reinterpret_cast<unsigned int*>(owin + GEO_OG);               // next work item
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-
-    // ---- decode the work item ------------------------------------------------------------------
-    const int64_t item = blockIdx.x;
-    const int v = find_video(table, nv, TSPN_VT_ITEM_OFF, item);
-    const int64_t* row = table + (int64_t)v * TSPN_VT_COLS;
-    const int n = (int)row[TSPN_VT_N];
-    const int t_len = (int)row[TSPN_VT_T];
-    const int tp = (int)row[TSPN_VT_TP];
-    const int64_t tb = row[TSPN_VT_TB];
-    const int64_t trk_off = row[TSPN_VT_TRK_OFF];
-    const int groups = (n - 1 + GEO_OG - 1) / GEO_OG;
-    const int nchunks = (t_len + GEO_CHUNK - 1) / GEO_CHUNK;
-    const int local = (int)(item - row[TSPN_VT_ITEM_OFF]);
-    const int c = local % nchunks;
-    const int sg = local / nchunks;
-    const int s = sg / groups;
-    const int k0 = (sg - s * groups) * GEO_OG;
-    const int nobj = min(GEO_OG, n - 1 - k0);
-    const int64_t box_row0 = row[TSPN_VT_BOX_OFF];           // multiple of 8
-    const int64_t pair0 = row[TSPN_VT_PAIR_OFF] + (int64_t)s * (n - 1) + k0;
+    const int warp = tid >> 5;
 
     if (tid == 0) {
 #pragma unroll
@@ -300,7 +168,46 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
         }
         fence_mbar_init();
     }
-    const int warp = tid >> 5;
+    const uint32_t ss = smem_u32(s_stage);
+    // Ring steps of this CTA so far.  Step g uses stage g % RING in its (g / RING)-th use: the consumers wait for
+    // `full` with parity (g / RING) & 1, the producer refills a stage once `empty` has completed its previous use.
+    // The count runs on across work items, so a persistent CTA never re-initialises a barrier.
+    unsigned int g0 = 0;
+
+    // One work item per CTA (queue == nullptr: item = blockIdx.x), or PERSISTENT CTAs - one per SM slot for the
+    // whole launch - that pull items from a global queue.  Persistent CTAs never leave their SM, so kernels of a
+    // concurrent stream can only ever co-reside with them (in the registers / shared memory they leave free)
+    // instead of taking over SMs between two CTAs and locking the next one out.
+    for (;;) {
+    unsigned int item;
+    if (queue) {
+        if (tid == 0) *s_item = atomicAdd(queue, 1u);
+        __syncthreads();
+        item = *s_item;
+        if (item >= total_items) break;
+    } else {
+        item = blockIdx.x;
+    }
+
+    // ---- decode the work item ------------------------------------------------------------------
+    const int v = find_video(table, nv, TSPN_VT_ITEM_OFF, (int64_t)item);
+    const int64_t* row = table + (int64_t)v * TSPN_VT_COLS;
+    const int n = (int)row[TSPN_VT_N];
+    const int t_len = (int)row[TSPN_VT_T];
+    const int tp = (int)row[TSPN_VT_TP];
+    const int64_t tb = row[TSPN_VT_TB];
+    const int64_t trk_off = row[TSPN_VT_TRK_OFF];
+    const int groups = (n - 1 + GEO_OG - 1) / GEO_OG;
+    const int nchunks = (t_len + GEO_CHUNK - 1) / GEO_CHUNK;
+    const int local = (int)((int64_t)item - row[TSPN_VT_ITEM_OFF]);
+    const int c = local % nchunks;
+    const int sg = local / nchunks;
+    const int s = sg / groups;
+    const int k0 = (sg - s * groups) * GEO_OG;
+    const int nobj = min(GEO_OG, n - 1 - k0);
+    const int64_t box_row0 = row[TSPN_VT_BOX_OFF];           // multiple of 8
+    const int64_t pair0 = row[TSPN_VT_PAIR_OFF] + (int64_t)s * (n - 1) + k0;
+
     if (tid < nobj) {       // the loop below touches no global or local memory besides its stores
         const int ps = __ldg(span + 2 * (trk_off + s)), pe = __ldg(span + 2 * (trk_off + s) + 1);
         const int k = k0 + tid;
@@ -314,7 +221,10 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
     auto issue = [&](int q) {          // thread 0: object q (and, with the first, the subject chunk)
         const int k = k0 + q;
         const int o = k + (k >= s ? 1 : 0);
-        const int st = q % RING;
+        const unsigned int g = g0 + (unsigned int)q;
+        const int st = (int)(g % RING);
+        // the stage's previous use (ring step g - RING) has been read by every warp
+        if (g >= (unsigned int)RING) mbar_wait(&empty[st], ((g / RING) - 1u) & 1u);
         mbar_expect_tx(&full[st], q == 0 ? 2 * GEO_TX_BYTES : GEO_TX_BYTES);
 #pragma unroll
         for (int h = 0; h < GEO_SPLIT; ++h) {                 // second half: rows CHUNK/16 .. CHUNK/8 (+ halo)
@@ -330,11 +240,11 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
         for (int q = 0; q < RING && q < nobj; ++q) issue(q);
     }
 
-    const uint32_t ss = smem_u32(s_stage);
     float* g = WRITE_GEO ? geo + row[TSPN_VT_GEO_OFF] + ((int64_t)(s * (n - 1) + k0) * TSPN_GEO_CHANNELS) * tp +
                                (int64_t)c * GEO_CHUNK
                          : nullptr;
-    int st = 0, ph = 0;                                      // ring stage of step q and its phase parity
+    int st = (int)(g0 % RING);                               // ring stage of step q and its phase parity
+    int ph = (int)((g0 / RING) & 1u);
     for (int q = 0; q < nobj; ++q) {
         const int2 win = owin[q];
         const int a = win.x, b = win.y;                      // overlap window [a, b)
@@ -350,45 +260,19 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
 
         float fsum_i, fsum_s, fsum_o;
         float out[TSPN_GEO_CHANNELS][GEO_FPT];
-        geo_step<CLIP, GEO_FPT>(ss, smem_u32(o_stage0 + st * GEO_STAGE_BYTES), j0, t0, a, b, out, fsum_i, fsum_s,
-                                fsum_o);
+        const uint32_t os_addr = smem_u32(o_stage0 + st * GEO_STAGE_BYTES);
+        geo_step<CLIP>([ss](int j) { return ld_box(ss, j); }, [os_addr](int j) { return ld_box(os_addr, j); }, j0, t0,
+                       a, b, out, fsum_i, fsum_s, fsum_o);
         // this warp is done reading the object stage of step q: hand it back; thread 0 refills it with
         // object q+RING (end of the step) once every warp has done so
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[st]);
 
-        if (BULK_OUT) {
-            // the warp's 32*FPT frames of every channel go through its shared-memory tile and leave as eight
-            // 1-D bulk stores (lane ch issues channel ch): the LSU sees conflict-free STS.128 only, the
-            // registers are free as soon as the tile is written, and the TMA engine owns the HBM stream
-            if (lane < TSPN_GEO_CHANNELS) bulk_wait_read0();     // the previous step's stores have read the tile
-            __syncwarp();
-#pragma unroll
-            for (int ch = 0; ch < TSPN_GEO_CHANNELS; ++ch) {
-                float* dst = out_tile + ch * (32 * GEO_FPT) + lane * GEO_FPT;
-                if (GEO_FPT == 4)
-                    *reinterpret_cast<float4*>(dst) = make_float4(out[ch][0], out[ch][1], out[ch][2], out[ch][GEO_FPT - 1]);
-                else
-                    *reinterpret_cast<float2*>(dst) = make_float2(out[ch][0], out[ch][1]);
-            }
-            fence_proxy_async();
-            __syncwarp();
-            const int jw = j0 - lane * GEO_FPT;                  // the warp's first frame inside the chunk
-            const int left = tp - (c * GEO_CHUNK + jw);          // frames of the row at or after it
-            if (lane < TSPN_GEO_CHANNELS && left > 0)
-                bulk_store_1d<TSPN_GEO_TMA_STORE>(g + (int64_t)lane * tp + jw, out_tile + lane * (32 * GEO_FPT),
-                              (uint32_t)min(left, 32 * GEO_FPT) * 4u);
-            g += (int64_t)TSPN_GEO_CHANNELS * tp;
-        } else if (WRITE_GEO) {
+        if (WRITE_GEO) {
             if (t0 < tp) {
 #pragma unroll
-                for (int ch = 0; ch < TSPN_GEO_CHANNELS; ++ch) {
-                    if (GEO_FPT == 4)
-                        st_stream_f4(g + (int64_t)ch * tp + j0,
-                                     make_float4(out[ch][0], out[ch][1], out[ch][2], out[ch][GEO_FPT - 1]));
-                    else
-                        st_stream_f2(g + (int64_t)ch * tp + j0, make_float2(out[ch][0], out[ch][1]));
-                }
+                for (int ch = 0; ch < TSPN_GEO_CHANNELS; ++ch)
+                    st_stream_f4(g + (int64_t)ch * tp + j0, make_float4(out[ch][0], out[ch][1], out[ch][2], out[ch][3]));
             }
             g += (int64_t)TSPN_GEO_CHANNELS * tp;
         }
@@ -407,13 +291,10 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
                 if (tot_o) atomicAdd(acc + q * 3 + 2, tot_o);
             }
         }
-        if (tid == 0 && q + RING < nobj) {                   // by now the other warps have normally arrived
-            mbar_wait(&empty[st], ph);
-            issue(q + RING);
-        }
+        if (tid == 0 && q + RING < nobj) issue(q + RING);    // by now the other warps have normally arrived
         if (++st == RING) { st = 0; ph ^= 1; }
     }
-    if (BULK_OUT && lane < TSPN_GEO_CHANNELS) bulk_wait_read0();   // the tile outlives the CTA's last stores
+    g0 += (unsigned int)nobj;
     __syncthreads();
     // this chunk's contribution to the pair's sums: a video that fits one chunk has exactly one writer per
     // pair, which stores (no zeroing of the accumulators needed); otherwise integer atomics onto zeroed sums
@@ -428,6 +309,8 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
         const int2 w = owin[tid];
         const bool has = w.y > w.x;
         *reinterpret_cast<int2*>(overlap + 2 * (pair0 + tid)) = make_int2(has ? w.x : 0, has ? w.y : 0);
+    }
+    if (!queue) break;
     }
 }
 
@@ -613,11 +496,11 @@ __global__ void __launch_bounds__(256) enumerate_pairs_kernel(const int64_t* __r
     pairs[2 * p + 1] = k + (k >= s ? 1 : 0);
 }
 
-template <int THREADS, bool DENSE, int FPT = GEO_FPT>
+template <int THREADS, bool DENSE>
 static int launch_pair_geo(const int64_t* d_table, int num_videos, int64_t total_items, int64_t total_boxes,
                            const float* d_boxes, const int32_t* d_span, float* d_geo, unsigned long long* fx,
-                           int32_t* d_overlap, bool clip, cudaStream_t st) {
-    using Cfg = GeoCfg<THREADS, DENSE, FPT>;
+                           int32_t* d_overlap, unsigned int* d_queue, bool clip, cudaStream_t st) {
+    using Cfg = GeoCfg<THREADS, DENSE>;
     // boxes viewed as a 2-D tensor: rows of 8 boxes (32 floats = 128 B)
     CUtensorMap map;
     const uint64_t dims[2] = {32, (uint64_t)(total_boxes / 8)};
@@ -626,12 +509,19 @@ static int launch_pair_geo(const int64_t* d_table, int num_videos, int64_t total
     int rc = encode_tensor_map(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d_boxes, dims, strides, box,
                                CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != TSPN_OK) return rc;
+    unsigned grid = (unsigned)total_items;
+    if (d_queue) {                      // persistent: one CTA per SM slot, items from the queue
+        const int64_t slots = (int64_t)num_sms() * Cfg::MIN_CTAS;
+        if (slots < total_items) grid = (unsigned)slots;
+        TSPN_CUDA_OK(cudaMemsetAsync(d_queue, 0, sizeof(unsigned int), st));
+    }
 #define TSPN_LAUNCH_GEO(W, C)                                                                                  \
     do {                                                                                                       \
-        TSPN_CUDA_OK(cudaFuncSetAttribute(pair_geo_kernel<THREADS, W, C, DENSE, FPT>,                          \
+        TSPN_CUDA_OK(cudaFuncSetAttribute(pair_geo_kernel<THREADS, W, C, DENSE>,                               \
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));      \
-        pair_geo_kernel<THREADS, W, C, DENSE, FPT><<<(unsigned)total_items, THREADS, Cfg::SMEM_BYTES, st>>>(   \
-            map, d_table, num_videos, d_span, d_geo, fx, d_overlap);                                           \
+        prefer_max_smem(pair_geo_kernel<THREADS, W, C, DENSE>);                                                \
+        pair_geo_kernel<THREADS, W, C, DENSE><<<grid, THREADS, Cfg::SMEM_BYTES, st>>>(                         \
+            map, d_table, num_videos, d_span, d_geo, fx, d_overlap, d_queue, (unsigned)total_items);           \
     } while (0)
     if (d_geo) {
         if (clip) TSPN_LAUNCH_GEO(true, true); else TSPN_LAUNCH_GEO(true, false);
@@ -667,7 +557,8 @@ static inline int64_t geo_ws_vol_bytes(int64_t total_tracklets) {
 }
 
 int64_t tspn_pair_geo_workspace_bytes(int64_t total_tracklets, int64_t total_pairs) {
-    return geo_ws_vol_bytes(total_tracklets) + (total_pairs > 0 ? total_pairs : 1) * 3 * (int64_t)sizeof(uint64_t);
+    // per-tracklet volumes | per-pair fixed-point sums | the persistent kernel's work-item queue
+    return geo_ws_vol_bytes(total_tracklets) + (total_pairs > 0 ? total_pairs : 1) * 3 * (int64_t)sizeof(uint64_t) + 16;
 }
 
 int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_items, int geo_chunk,
@@ -706,6 +597,7 @@ int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_ite
         int64_t blocks = blocks_vol > blocks_zero ? blocks_vol : blocks_zero;
         if (blocks > cap) blocks = cap;                // both loops are grid-stride
         if (blocks < 1) blocks = 1;
+        prefer_max_smem(tracklet_volume_kernel);
         tracklet_volume_kernel<<<(unsigned)blocks, 128, 0, st>>>(d_table, num_videos, total_tracklets,
                                                                 reinterpret_cast<const float4*>(d_boxes), d_span, vol,
                                                                 !clip, fx, single_chunk ? 0 : total_pairs * 3);
@@ -714,23 +606,23 @@ int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_ite
     if (all || (phases & TSPN_GEO_PHASE_MAIN)) {
         int rc = TSPN_OK;
         const bool dense = (flags & TSPN_GEO_DENSE_CTAS) != 0;
+        unsigned int* queue = (flags & TSPN_GEO_PERSISTENT) ? reinterpret_cast<unsigned int*>(fx + total_pairs * 3)
+                                                            : nullptr;
 #define TSPN_GEO_SHAPE(T)                                                                                          \
     (dense ? launch_pair_geo<T, true>(d_table, num_videos, total_items, total_boxes, d_boxes, d_span, d_geo, fx,   \
-                                      d_overlap, clip, st)                                                         \
+                                      d_overlap, queue, clip, st)                                                  \
            : launch_pair_geo<T, false>(d_table, num_videos, total_items, total_boxes, d_boxes, d_span, d_geo, fx,  \
-                                       d_overlap, clip, st))
+                                       d_overlap, queue, clip, st))
         if (geo_chunk == 512) rc = TSPN_GEO_SHAPE(128);
         else if (geo_chunk == 1024) rc = TSPN_GEO_SHAPE(256);
-#if TSPN_GEO_WIDE
-        else if (!dense) rc = launch_pair_geo<1024, false, 2>(d_table, num_videos, total_items, total_boxes, d_boxes,
-                                                              d_span, d_geo, fx, d_overlap, clip, st);
-#endif
         else rc = TSPN_GEO_SHAPE(512);
 #undef TSPN_GEO_SHAPE
         if (rc != TSPN_OK) return rc;
     }
     if (all || (phases & TSPN_GEO_PHASE_POST)) {
         const unsigned fblocks = (unsigned)((total_pairs + 255) / 256);
+        prefer_max_smem(pair_finalize_kernel<true>);
+        prefer_max_smem(pair_finalize_kernel<false>);
         if (clip)
             pair_finalize_kernel<true><<<fblocks, 256, 0, st>>>(d_table, num_videos, total_pairs, d_span, vol, fx,
                                                                 d_viou, d_tiou);

@@ -117,12 +117,13 @@ __device__ __forceinline__ int warp_argmax_row(const float* __restrict__ x, int 
 }
 
 // one CTA per video: top `tpv` of its (rows x tpp) candidates -> records
-__global__ void __launch_bounds__(TOPK_THREADS)
+__global__ void __launch_bounds__(TOPK_THREADS, 5)      // <= 48 registers: co-resides with the pair kernel
 video_top_triplets_kernel(const int64_t* __restrict__ table, int nv, const float* __restrict__ cand_score,
                           const int32_t* __restrict__ cand_pred, const int64_t* __restrict__ rows,
                           const int64_t* __restrict__ row_video_off, int tpp, int tpv,
                           const float* __restrict__ cls, int n_classes, const int32_t* __restrict__ overlap,
-                          int mirror_q4, int32_t* __restrict__ records, int32_t* __restrict__ counts) {
+                          const int32_t* __restrict__ span, int mirror_q4, int32_t* __restrict__ records,
+                          int32_t* __restrict__ counts) {
     __shared__ TopkSmem sm;
     __shared__ int s_label[PP_LABEL_CAP];
     const int v = blockIdx.x;
@@ -163,8 +164,16 @@ video_top_triplets_kernel(const int64_t* __restrict__ table, int nv, const float
             out[3] = labels_cached ? s_label[o_src] : argmax_row(cls + (trk0 + o_src) * n_classes, n_classes);
             out[4] = s;
             out[5] = o;
-            out[6] = __ldg(overlap + 2 * gp);
-            out[7] = __ldg(overlap + 2 * gp + 1);
+            if (overlap) {
+                out[6] = __ldg(overlap + 2 * gp);
+                out[7] = __ldg(overlap + 2 * gp + 1);
+            } else {                 // the same window from the two tracklet spans ([SPEC] s3)
+                const int ps = __ldg(span + 2 * (trk0 + s)), pe = __ldg(span + 2 * (trk0 + s) + 1);
+                const int qs = __ldg(span + 2 * (trk0 + o)), qe = __ldg(span + 2 * (trk0 + o) + 1);
+                const int wa = max(ps, qs), wb = min(pe, qe);
+                out[6] = wb > wa ? wa : 0;
+                out[7] = wb > wa ? wb : 0;
+            }
         }
         int4* dst = reinterpret_cast<int4*>(rec + (int64_t)i * 8);
         dst[0] = make_int4(out[0], out[1], out[2], out[3]);
@@ -186,8 +195,9 @@ int64_t tspn_postprocess_workspace_bytes(int64_t m, int topk_per_pair) {
 
 int tspn_postprocess(const int64_t* d_table, int num_videos, const float* d_logits, const int64_t* d_rows,
                      const int64_t* d_row_video_off, int64_t n_rows, int n_predicates, const float* d_cls,
-                     int n_classes, const int32_t* d_overlap, int topk_per_pair, int topk_per_video, int flags,
-                     int32_t* d_records, int32_t* d_counts, void* d_workspace, void* stream) {
+                     int n_classes, const int32_t* d_overlap, const int32_t* d_span, int topk_per_pair,
+                     int topk_per_video, int flags, int32_t* d_records, int32_t* d_counts, void* d_workspace,
+                     void* stream) {
     TSPN_ARCH_OK();
     TSPN_REQUIRE(num_videos >= 0 && n_rows >= 0 && n_predicates > 0 && n_classes > 0 && topk_per_pair > 0 &&
                      topk_per_video > 0,
@@ -196,7 +206,8 @@ int tspn_postprocess(const int64_t* d_table, int num_videos, const float* d_logi
     TSPN_REQUIRE(topk_per_video <= TOPK_MAX_K, TSPN_ESHAPE, "tspn_postprocess: topk_per_video must be <= %d",
                  TOPK_MAX_K);
     if (num_videos == 0) return TSPN_OK;
-    TSPN_REQUIRE(d_table && d_cls && d_overlap && d_records && d_counts && d_workspace && (d_logits || n_rows == 0),
+    TSPN_REQUIRE(d_table && d_cls && (d_overlap || d_span) && d_records && d_counts && d_workspace &&
+                     (d_logits || n_rows == 0),
                  TSPN_EBADARG, "tspn_postprocess: null pointer");
     TSPN_REQUIRE(aligned16(d_records) && aligned16(d_workspace), TSPN_EALIGN,
                  "tspn_postprocess: records/workspace must be 16-byte aligned");
@@ -207,9 +218,12 @@ int tspn_postprocess(const int64_t* d_table, int num_videos, const float* d_logi
     int32_t* cand_pred = reinterpret_cast<int32_t*>(cand_score + n_rows * tpp);
     if (n_rows > 0) {
         const unsigned blocks = (unsigned)((n_rows + 3) / 4);
-#define TSPN_LAUNCH_PTP(S)                                                                                        \
-    pair_top_predicates_kernel<S><<<blocks, 128, 0, st>>>(d_logits, d_rows, n_rows, n_predicates, tpp, cand_score, \
-                                                          cand_pred)
+#define TSPN_LAUNCH_PTP(S)                                                                                            \
+    do {                                                                                                             \
+        prefer_max_smem(pair_top_predicates_kernel<S>);                                                              \
+        pair_top_predicates_kernel<S><<<blocks, 128, 0, st>>>(d_logits, d_rows, n_rows, n_predicates, tpp, cand_score, \
+                                                              cand_pred);                                            \
+    } while (0)
         if (n_predicates <= 32) TSPN_LAUNCH_PTP(1);
         else if (n_predicates <= 64) TSPN_LAUNCH_PTP(2);
         else if (n_predicates <= 128) TSPN_LAUNCH_PTP(4);
@@ -218,9 +232,10 @@ int tspn_postprocess(const int64_t* d_table, int num_videos, const float* d_logi
 #undef TSPN_LAUNCH_PTP
         TSPN_CUDA_OK(cudaGetLastError());
     }
+    prefer_max_smem(video_top_triplets_kernel);
     video_top_triplets_kernel<<<(unsigned)num_videos, TOPK_THREADS, 0, st>>>(
         d_table, num_videos, cand_score, cand_pred, d_rows, d_row_video_off, tpp, topk_per_video, d_cls, n_classes,
-        d_overlap, (flags & TSPN_POST_MIRROR_Q4) ? 1 : 0, d_records, d_counts);
+        d_overlap, d_span, (flags & TSPN_POST_MIRROR_Q4) ? 1 : 0, d_records, d_counts);
     TSPN_CUDA_OK(cudaGetLastError());
     return TSPN_OK;
 }

@@ -12,7 +12,7 @@
 namespace tspn {
 
 int predicate_head_tensor(const void* d_x, int x_is_bf16, int64_t ld_x, int64_t m, int feature_dim,
-                          const void* d_w_packed, const float* d_bias, const float* d_row_bias, int64_t ld_rb, int raw,
+                          const void* d_w_packed, const float* d_bias, const float* d_row_bias, int64_t ld_rb, int flags,
                           int n_predicates, float* d_y, void* d_workspace, cudaStream_t st);
 
 constexpr int PX_BM = 64, PX_BN = 64, PX_BK = 16, PX_THREADS = 256;
@@ -136,7 +136,7 @@ int tspn_predicate_head_affine(const void* d_x, int x_is_bf16, int64_t ld_x, int
     TSPN_REQUIRE(!d_row_bias || ld_row_bias >= n_outputs, TSPN_ESHAPE,
                  "tspn_predicate_head_affine: ld_row_bias=%lld < %d", (long long)ld_row_bias, n_outputs);
     return predicate_head_tensor(d_x, x_is_bf16, ld_x, m, feature_dim, d_w_packed, d_bias, d_row_bias, ld_row_bias,
-                                 (flags & TSPN_AFFINE_RAW) ? 1 : 0, n_outputs, d_y, d_workspace, (cudaStream_t)stream);
+                                 flags, n_outputs, d_y, d_workspace, (cudaStream_t)stream);
 }
 
 }  // extern "C"

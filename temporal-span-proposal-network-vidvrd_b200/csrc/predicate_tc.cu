@@ -40,7 +40,9 @@ static int pt_splits(int64_t m, int num_kblocks) {
 }
 
 template <bool BF16>
-__global__ void __launch_bounds__(PT_THREADS, 1)
+// <= 48 registers: 6 warps are allocated as 8 (warp allocation granularity 4), and 8 x 32 x 48 registers is what
+// the pair kernel's 16 warps x 104 registers leave free on an SM (co-residency, TSPN_AFFINE_BACKGROUND)
+__global__ void __launch_bounds__(PT_THREADS, 7)
 predicate_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, int64_t m,
                     int r, int rpad, int num_kblocks, int kb_per_split, int stages, uint32_t tmem_cols,
                     const float* __restrict__ bias, const float* __restrict__ row_bias, int64_t ld_rb, int raw,
@@ -184,9 +186,11 @@ static int64_t packed_bf16_bytes(int r, int f) { return (int64_t)pt_rpad(r) * pt
 static int64_t packed_f32_bytes(int r, int f) { return (int64_t)pt_rpad(r) * pt_kpad(f, 4) * 4; }
 
 int predicate_head_tensor(const void* d_x, int x_is_bf16, int64_t ld_x, int64_t m, int feature_dim,
-                          const void* d_w_packed, const float* d_bias, const float* d_row_bias, int64_t ld_rb, int raw,
+                          const void* d_w_packed, const float* d_bias, const float* d_row_bias, int64_t ld_rb, int flags,
                           int n_predicates, float* d_y, void* d_workspace, cudaStream_t st) {
     const int r = n_predicates, f = feature_dim;
+    const int raw = (flags & TSPN_AFFINE_RAW) ? 1 : 0;
+    const bool background = (flags & TSPN_AFFINE_BACKGROUND) != 0;
     const int rpad = pt_rpad(r);
     TSPN_REQUIRE(rpad <= 256, TSPN_ESHAPE, "tensor predicate head supports at most 256 predicates (got %d)", r);
     const int elem = x_is_bf16 ? 2 : 4;
@@ -197,7 +201,8 @@ int predicate_head_tensor(const void* d_x, int x_is_bf16, int64_t ld_x, int64_t 
     TSPN_REQUIRE(m < (1ll << 31) - PT_BM, TSPN_ESHAPE, "tensor predicate head: too many rows");
     const int k_elems = PT_SLAB / elem;
     const int num_kblocks = (f + k_elems - 1) / k_elems;
-    const int splits = pt_splits(m, num_kblocks);
+    int splits = pt_splits(m, num_kblocks);
+    if (background && splits > 4) splits = 4;           // few long-lived CTAs next to the foreground kernel's
     const int kb_per_split = (num_kblocks + splits - 1) / splits;
     const int eff_splits = (num_kblocks + kb_per_split - 1) / kb_per_split;
     const int64_t mtiles = (m + PT_BM - 1) / PT_BM;
@@ -207,6 +212,7 @@ int predicate_head_tensor(const void* d_x, int x_is_bf16, int64_t ld_x, int64_t 
     const int stage_bytes = PT_BM * PT_SLAB + rpad * PT_SLAB;
     int stages = PT_SMEM_BUDGET / stage_bytes;
     if (stages > 8) stages = 8;
+    if (background && stages > 3) stages = 3;           // <= 80 KB: fits beside a 134 KB foreground CTA
     if (stages > kb_per_split) stages = kb_per_split < 2 ? 2 : kb_per_split;
     const size_t smem_bytes = (size_t)stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16;
     uint32_t tmem_cols = 32;
@@ -236,12 +242,14 @@ int predicate_head_tensor(const void* d_x, int x_is_bf16, int64_t ld_x, int64_t 
     if (x_is_bf16) {
         TSPN_CUDA_OK(cudaFuncSetAttribute(predicate_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem_bytes));
+        prefer_max_smem(predicate_tc_kernel<true>);
         predicate_tc_kernel<true><<<grid, PT_THREADS, smem_bytes, st>>>(map_x, map_w, m, r, rpad, num_kblocks,
                                                                         kb_per_split, stages, tmem_cols, d_bias,
                                                                         d_row_bias, ld_rb, raw, d_y, partial);
     } else {
         TSPN_CUDA_OK(cudaFuncSetAttribute(predicate_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smem_bytes));
+        prefer_max_smem(predicate_tc_kernel<false>);
         predicate_tc_kernel<false><<<grid, PT_THREADS, smem_bytes, st>>>(map_x, map_w, m, r, rpad, num_kblocks,
                                                                          kb_per_split, stages, tmem_cols, d_bias,
                                                                          d_row_bias, ld_rb, raw, d_y, partial);
@@ -249,6 +257,7 @@ int predicate_head_tensor(const void* d_x, int x_is_bf16, int64_t ld_x, int64_t 
     TSPN_CUDA_OK(cudaGetLastError());
     if (eff_splits > 1) {
         const int64_t total = m * r;
+        prefer_max_smem(predicate_reduce_kernel);
         predicate_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, eff_splits, mtiles * PT_BM,
                                                                                  rpad, m, r, d_bias, d_row_bias, ld_rb, raw,
                                                                                  d_y);

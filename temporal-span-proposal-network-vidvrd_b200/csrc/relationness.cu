@@ -198,16 +198,19 @@ int tspn_relationness(const int64_t* d_table, int num_videos, int64_t total_trac
         const size_t smt = (size_t)(4 * n_classes * hidden + EMB_G * n_classes + EMB_G * 2 * hidden) * sizeof(float);
         TSPN_CUDA_OK(cudaFuncSetAttribute(ppn_embed_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smt));
+        prefer_max_smem(ppn_embed_tiled_kernel);
         ppn_embed_tiled_kernel<<<(unsigned)((total_tracklets + EMB_G - 1) / EMB_G), EMB_THREADS, smt, st>>>(
             d_cls, total_tracklets, n_classes, hidden, d_sub_w0, d_sub_b0, d_sub_w2, d_sub_b2, d_obj_w0, d_obj_b0,
             d_obj_w2, d_obj_b2, S, O);
     } else {
         const size_t sm1 = (size_t)(n_classes + 2 * hidden) * sizeof(float);
+        prefer_max_smem(ppn_embed_kernel);
         ppn_embed_kernel<<<(unsigned)total_tracklets, 128, sm1, st>>>(d_cls, n_classes, hidden, d_sub_w0, d_sub_b0,
                                                                       d_sub_w2, d_sub_b2, d_obj_w0, d_obj_b0,
                                                                       d_obj_w2, d_obj_b2, S, O);
     }
     TSPN_CUDA_OK(cudaGetLastError());
+    prefer_max_smem(pair_scores_kernel);
     pair_scores_kernel<<<(unsigned)total_tracklets, 128, (size_t)n_classes * sizeof(float), st>>>(
         d_table, num_videos, S, O, n_classes, d_scores);
     TSPN_CUDA_OK(cudaGetLastError());
@@ -222,6 +225,7 @@ int tspn_topk_pairs(const int64_t* d_table, int num_videos, const float* d_score
                  TOPK_MAX_K);
     if (num_videos == 0 || k == 0) return TSPN_OK;
     TSPN_REQUIRE(d_table && d_scores && d_topk_idx && d_topk_score, TSPN_EBADARG, "tspn_topk_pairs: null pointer");
+    prefer_max_smem(topk_kernel);
     topk_kernel<<<(unsigned)num_videos, TOPK_THREADS, 0, (cudaStream_t)stream>>>(
         d_table, num_videos, d_scores, k, (flags & TSPN_TOPK_EXCLUDE_DIAGONAL) ? 1 : 0, d_topk_idx, d_topk_score,
         d_topk_row);

@@ -12,6 +12,7 @@
 // ever exists in memory.  TSPN_PREC_TENSOR: implicit GEMM on tcgen05 (span_head_tc.cu).
 #include "common.cuh"
 #include "exact_math.cuh"
+#include "span_math.cuh"
 
 namespace tspn {
 
@@ -196,22 +197,6 @@ span_head_small_kernel(const float* __restrict__ x, const int64_t* __restrict__ 
     }
 }
 
-// [SPEC] s5, every step one correctly rounded fp32 operation (see oracle/exact).
-__device__ __forceinline__ void decode_anchor(float dc, float dw, float aw, float ac, int t_len, int32_t* lo_out,
-                                              int32_t* hi_out) {
-    const float CLAMP = 4.1351666f;                     // fp32 nearest of log(1000/16)
-    dw = fminf(dw, CLAMP);
-    const float ctr = __fmaf_rn(dc, aw, ac);
-    const float w = __fmul_rn(aw, exp_det(dw));
-    const float hw = __fmul_rn(0.5f, w);
-    float lo = floorf(__fadd_rn(__fadd_rn(ctr, -hw), 0.5f));
-    float hi = floorf(__fadd_rn(__fadd_rn(ctr, hw), 0.5f));
-    lo = fminf(fmaxf(lo, 0.0f), (float)(t_len - 1));
-    hi = fminf(fmaxf(hi, __fadd_rn(lo, 1.0f)), (float)t_len);
-    *lo_out = (int32_t)lo;
-    *hi_out = (int32_t)hi;
-}
-
 __global__ void __launch_bounds__(256)
 span_decode_kernel(const float* __restrict__ reg, int64_t k, int a_n, int t_len, int n_loc,
                    const float* __restrict__ sizes, float stride, int32_t* __restrict__ spans) {
@@ -264,10 +249,12 @@ span_proposals_small_kernel(const float* __restrict__ x, const int64_t* __restri
     const float ac = __fmul_rn((float)l, stride);
     const int t = min((int)floorf(ac), t_len - 1);
     const int64_t src = rows ? rows[p] - (rows[p] >= 0 ? row_base : 0) : p;
-    float acc[A2];
+    int32_t res[A2];
     if (src < 0) {                                          // padding row: regressions are 0
+        float zero[A2];
 #pragma unroll
-        for (int j = 0; j < A2; ++j) acc[j] = 0.0f;
+        for (int j = 0; j < A2; ++j) zero[j] = 0.0f;
+        span_decode_location<A>(zero, sizes, ac, t_len, res);
     } else {
         const float* xr = x + src * row_stride + t;
         const bool has_m = t > 0, has_p = t + 1 < t_len;
@@ -279,28 +266,8 @@ span_proposals_small_kernel(const float* __restrict__ x, const int64_t* __restri
             xv[ci][1] = __ldg(xc);
             xv[ci][2] = has_p ? __ldg(xc + 1) : 0.0f;
         }
-#pragma unroll
-        for (int j = 0; j < A2; ++j) acc[j] = b_pred[j];
-#pragma unroll 2
-        for (int co = 0; co < CIN; ++co) {
-            float h = b_conv[co];
-#pragma unroll
-            for (int ci = 0; ci < CIN; ++ci) {
-                const float4 w = w_conv[co * CIN + ci];
-                // taps outside [0, T) are skipped, not multiplied by zero (same chain as the oracle)
-                if (has_m) h = __fmaf_rn(w.x, xv[ci][0], h);
-                h = __fmaf_rn(w.y, xv[ci][1], h);
-                if (has_p) h = __fmaf_rn(w.z, xv[ci][2], h);
-            }
-            h = fmaxf(h, 0.0f);
-#pragma unroll
-            for (int j = 0; j < A2; ++j) acc[j] = __fmaf_rn(w_pred[co * A2 + j], h, acc[j]);
-        }
+        span_location<CIN, A>(xv, has_m, has_p, w_conv, w_pred, b_conv, b_pred, sizes, ac, t_len, res);
     }
-    int32_t res[A2];
-#pragma unroll
-    for (int a = 0; a < A; ++a) decode_anchor(acc[2 * a], acc[2 * a + 1], __ldg(sizes + a), ac, t_len, &res[2 * a],
-                                              &res[2 * a + 1]);
     int32_t* o = spans + (p * n_loc + l) * A2;               // [k][n_loc * A][2]
     if (A2 % 4 == 0) {
 #pragma unroll

@@ -1,0 +1,236 @@
+// survivors.cu — everything the heads need from a SURVIVING pair, recomputed from the boxes.
+//
+//   tspn_survivor_rows   for every row the top-K kept (lib/modeling/relpn/ppn.py:79-90):
+//     * the pooled 3 x 2 x 500 relative block of its feature row ([SPEC] s4; the last 3000 columns of
+//       lib/dataset/vrdataset.py:219-243) in bf16 + the bias row A_s[subject] + A_o[object] of the
+//       decomposed predicate head (include/tspn_b200.h, a14 decomposed) - what tspn_assemble_relative
+//       produces from the stored geometry rows;
+//     * the decoded temporal-span proposals (DPNHead, lib/modeling/relpn/dpn.py:55-73, at the anchor
+//       columns + [SPEC] s5 decode) - what tspn_span_proposals produces from the stored geometry rows.
+//
+// Why recompute: the stored rows of the K survivors are 64 KB each (268 MB per 4096 rows); reading them
+// back right after the all-pairs kernel has written 4 GB through the L2 makes the feature / span kernels
+// HBM-bound behind it (measured: 86 us + 59 us on the critical path of a 0.87 ms step).  The boxes of
+// the two tracklets are 2 x 32 KB and L2-resident, the per-frame math is ~3 instructions per frame, and
+// nothing here depends on the all-pairs kernel - so this kernel, the predicate head and the records run
+// on the side stream UNDERNEATH the all-pairs kernel: a CTA is shaped (128 threads = 4 warps x 96 registers,
+// 64 KB of shared memory at T = 2000) to co-reside with that kernel's 512-thread / 104-register / 131 KB CTA.
+//
+// The per-frame values come from the same device function as the all-pairs kernel (geo_math.cuh), the
+// pooling adds frames in ascending order like assemble_kernel, the span chain is span_math.cuh: every
+// output is bit-identical to the stored-rows path (tests/test_gpu_tensor.py).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "geo_math.cuh"
+#include "span_math.cuh"
+
+namespace tspn {
+
+constexpr int SV_THREADS = 128;
+constexpr int SV_CHUNK = SV_THREADS * GEO_FPT;          // frames per pass
+constexpr int SV_CIN = TSPN_GEO_CHANNELS;
+constexpr int SV_INV_TAB = 32;
+constexpr int SV_SMEM_MAX = 200 * 1024;
+
+__host__ __device__ __forceinline__ int span_locations(int t, float stride) {
+    // len(torch.arange(0, T+1, step=stride)) = ceil((T+1)/stride), anchor_generator.py:50-52
+    const double q = ((double)t + 1.0) / (double)stride;
+    int n = (int)q;
+    if ((double)n < q) ++n;
+    return n;
+}
+
+template <int A>
+__global__ void __launch_bounds__(SV_THREADS, 5)
+survivor_rows_kernel(const int64_t* __restrict__ table, int nv, const float4* __restrict__ boxes,
+                     const int32_t* __restrict__ span, const int64_t* __restrict__ rows, int64_t rows_per_video,
+                     __nv_bfloat16* __restrict__ rel, int64_t ld_rel, const float* __restrict__ terms_s,
+                     const float* __restrict__ terms_o, int n_out, float* __restrict__ row_bias,
+                     const float* __restrict__ conv_w, const float* __restrict__ conv_b,
+                     const float* __restrict__ pred_w, const float* __restrict__ pred_b,
+                     const float* __restrict__ sizes, float stride, int32_t* __restrict__ spans, int64_t ld_spans,
+                     int cap) {
+    constexpr int A2 = 2 * A;
+    extern __shared__ __align__(128) uint8_t smem[];
+    float* const tile = reinterpret_cast<float*>(smem);                           // [8][cap], frame - a4
+    __shared__ __align__(16) float4 w_conv[SV_CIN * SV_CIN];                      // [co][ci] -> (w0, w1, w2, -)
+    __shared__ __align__(16) float w_pred[SV_CIN * A2];                           // [co][j]
+    __shared__ float b_conv[SV_CIN], b_pred[A2];
+    __shared__ float s_inv[SV_INV_TAB];
+
+    const int tid = threadIdx.x;
+    const int64_t r = blockIdx.x;
+    const int64_t gp = rows[r];
+    const int v = gp >= 0 ? find_video(table, nv, TSPN_VT_PAIR_OFF, gp) : (int)(r / rows_per_video);
+    const int64_t* row = table + (int64_t)v * TSPN_VT_COLS;
+    const int t_len = (int)row[TSPN_VT_T];
+    __nv_bfloat16* outb = rel + r * ld_rel;
+    float* bias_row = row_bias + r * n_out;
+    int32_t* sp_row = spans ? spans + r * ld_spans : nullptr;
+    const int n_loc = spans ? span_locations(t_len, stride) : 0;
+
+    if (spans) {
+        for (int i = tid; i < SV_CIN * SV_CIN; i += SV_THREADS)
+            w_conv[i] = make_float4(__ldg(conv_w + i * 3), __ldg(conv_w + i * 3 + 1), __ldg(conv_w + i * 3 + 2), 0.0f);
+        for (int i = tid; i < SV_CIN * A2; i += SV_THREADS) {
+            const int co = i / A2, j = i - co * A2;
+            w_pred[i] = __ldg(pred_w + j * SV_CIN + co);
+        }
+        if (tid < SV_CIN) b_conv[tid] = conv_b ? __ldg(conv_b + tid) : 0.0f;
+        if (tid < A2) b_pred[tid] = pred_b ? __ldg(pred_b + tid) : 0.0f;
+        // columns of the span buffer beyond this video's locations (a batch is sized for its longest video)
+        for (int64_t i = (int64_t)n_loc * A2 + tid; i < ld_spans; i += SV_THREADS) sp_row[i] = 0;
+    }
+    if (tid < SV_INV_TAB) s_inv[tid] = 1.0f / (float)(tid ? tid : 1);
+
+    if (gp < 0) {                                  // padding row (K_eff < K): zero block, zero bias, zero regressions
+        for (int64_t q = tid; q < ld_rel; q += SV_THREADS) outb[q] = __float2bfloat16(0.0f);
+        for (int c = tid; c < n_out; c += SV_THREADS) bias_row[c] = 0.0f;
+        for (int l = tid; l < n_loc; l += SV_THREADS) {
+            float zero[A2];
+            int32_t res[A2];
+#pragma unroll
+            for (int j = 0; j < A2; ++j) zero[j] = 0.0f;
+            span_decode_location<A>(zero, sizes, __fmul_rn((float)l, stride), t_len, res);
+#pragma unroll
+            for (int j = 0; j < A2; ++j) sp_row[l * A2 + j] = res[j];
+        }
+        return;
+    }
+    const int n = (int)row[TSPN_VT_N];
+    const int64_t tb = row[TSPN_VT_TB];
+    const int p = (int)(gp - row[TSPN_VT_PAIR_OFF]);
+    const int s = p / (n - 1);
+    const int k = p - s * (n - 1);
+    const int o = k + (k >= s ? 1 : 0);
+    const int64_t ts = row[TSPN_VT_TRK_OFF] + s, to = row[TSPN_VT_TRK_OFF] + o;
+    const int ps = __ldg(span + 2 * ts), pe = __ldg(span + 2 * ts + 1);
+    const int qs = __ldg(span + 2 * to), qe = __ldg(span + 2 * to + 1);
+    const int a = max(ps, qs), b = min(pe, qe);                 // temporal overlap window [a, b)
+    const uint32_t len = b > a ? (uint32_t)(b - a) : 0u;
+    const int a4 = a & ~3;
+
+    // ---- the eight channels over the window, 512 frames per pass, into the shared-memory tile ----
+    // The boxes come straight from global memory (L2 / L1: a thread's five boxes per tracklet are 80 contiguous
+    // bytes, its neighbour's start 64 bytes later) - no staging, no barrier between the passes.
+    const float4* bs = boxes + row[TSPN_VT_BOX_OFF] + (int64_t)s * tb;
+    const float4* bo = boxes + row[TSPN_VT_BOX_OFF] + (int64_t)o * tb;
+    const int last = (int)tb - 1;                               // frames >= b are masked: any in-row box will do
+    const int n_pass = len ? (b - a4 + SV_CHUNK - 1) / SV_CHUNK : 0;
+    for (int pass = 0; pass < n_pass; ++pass) {
+        const int f0 = a4 + pass * SV_CHUNK;
+        const int j0 = tid * GEO_FPT;
+        float out[TSPN_GEO_CHANNELS][GEO_FPT];
+        float fi, fs, fo;
+        geo_step<false>([bs, f0, last](int j) { return __ldg(bs + min(f0 + j, last)); },
+                        [bo, f0, last](int j) { return __ldg(bo + min(f0 + j, last)); }, j0, f0 + j0, a, b, out, fi, fs,
+                        fo);
+        const int col = pass * SV_CHUNK + j0;                   // frame - a4
+        if (col < cap) {
+#pragma unroll
+            for (int ch = 0; ch < TSPN_GEO_CHANNELS; ++ch)
+                *reinterpret_cast<float4*>(tile + (size_t)ch * cap + col) =
+                    make_float4(out[ch][0], out[ch][1], out[ch][2], out[ch][3]);
+        }
+    }
+    __syncthreads();
+
+    // ---- relative block: bin i of the six pooled channels (0,1 | 2,3 | 5,6) shares its frame range ----
+    const float* w0 = tile + (a - a4);
+    for (int i = tid; i < TSPN_REL_BINS; i += SV_THREADS) {
+        float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (len > 0) {
+            const uint32_t st = ((uint32_t)i * len) / TSPN_REL_BINS;              // len < 2^22: fits 32 bits
+            const uint32_t en = ((uint32_t)(i + 1) * len + TSPN_REL_BINS - 1) / TSPN_REL_BINS;
+            const uint32_t width = en - st;
+            const float inv = width < SV_INV_TAB ? s_inv[width] : 1.0f / (float)width;
+            for (uint32_t f = st; f < en; ++f) {                                  // ascending frames
+                acc[0] += w0[f];
+                acc[1] += w0[(size_t)cap + f];
+                acc[2] += w0[2 * (size_t)cap + f];
+                acc[3] += w0[3 * (size_t)cap + f];
+                acc[4] += w0[5 * (size_t)cap + f];
+                acc[5] += w0[6 * (size_t)cap + f];
+            }
+#pragma unroll
+            for (int c = 0; c < 6; ++c) acc[c] *= inv;
+        }
+#pragma unroll
+        for (int c = 0; c < 6; ++c) outb[c * TSPN_REL_BINS + i] = __float2bfloat16(acc[c]);
+    }
+    for (int64_t q = TSPN_REL_DIM + tid; q < ld_rel; q += SV_THREADS) outb[q] = __float2bfloat16(0.0f);
+    {
+        const float* a_s = terms_s + ts * n_out;                 // A_s of the subject tracklet
+        const float* a_o = terms_o + to * n_out;                 // A_o of the object tracklet
+        for (int c = tid; c < n_out; c += SV_THREADS) bias_row[c] = __ldg(a_s + c) + __ldg(a_o + c);
+    }
+
+    // ---- span proposals: the head at the anchor columns floor(l * stride), decoded in registers ----
+    for (int l = tid; l < n_loc; l += SV_THREADS) {
+        const float ac = __fmul_rn((float)l, stride);
+        const int t = min((int)floorf(ac), t_len - 1);
+        const bool has_m = t > 0, has_p = t + 1 < t_len;
+        float xv[SV_CIN][3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const int f = t - 1 + d;
+            const bool in = f >= a && f < b;                     // every channel is 0 outside the window
+#pragma unroll
+            for (int ci = 0; ci < SV_CIN; ++ci) xv[ci][d] = in ? tile[(size_t)ci * cap + (f - a4)] : 0.0f;
+        }
+        int32_t res[A2];
+        span_location<SV_CIN, A>(xv, has_m, has_p, w_conv, w_pred, b_conv, b_pred, sizes, ac, t_len, res);
+#pragma unroll
+        for (int j = 0; j < A2; ++j) sp_row[l * A2 + j] = res[j];
+    }
+}
+
+}  // namespace tspn
+
+using namespace tspn;
+
+extern "C" {
+
+int tspn_survivor_rows_supported(int max_frames, int n_anchors) {
+    const int64_t cap = ((int64_t)max_frames + 3) / 4 * 4 + 4;
+    return n_anchors == 4 && max_frames > 0 && (int64_t)TSPN_GEO_CHANNELS * cap * 4 <= SV_SMEM_MAX;
+}
+
+int tspn_survivor_rows(const int64_t* d_table, int num_videos, int max_frames, const float* d_boxes,
+                       const int32_t* d_span, const int64_t* d_rows, int64_t n_rows, int64_t rows_per_video,
+                       void* d_rel_bf16, int64_t ld_rel, const float* d_terms_subject, const float* d_terms_object,
+                       int n_outputs, float* d_row_bias, const float* d_conv_w, const float* d_conv_b,
+                       const float* d_pred_w, const float* d_pred_b, int n_anchors, const float* d_sizes, float stride,
+                       int32_t* d_spans, int64_t ld_spans, void* stream) {
+    TSPN_ARCH_OK();
+    TSPN_REQUIRE(num_videos >= 0 && n_rows >= 0 && n_outputs > 0 && max_frames > 0 && rows_per_video > 0, TSPN_EBADARG,
+                 "tspn_survivor_rows: bad size");
+    if (n_rows == 0) return TSPN_OK;
+    TSPN_REQUIRE(d_table && d_boxes && d_span && d_rows && d_rel_bf16 && d_terms_subject && d_terms_object && d_row_bias,
+                 TSPN_EBADARG, "tspn_survivor_rows: null pointer");
+    TSPN_REQUIRE(ld_rel >= TSPN_REL_DIM, TSPN_ESHAPE, "tspn_survivor_rows: ld_rel=%lld must be >= 3000", (long long)ld_rel);
+    TSPN_REQUIRE(aligned16(d_boxes), TSPN_EALIGN, "tspn_survivor_rows: boxes must be 16-byte aligned");
+    TSPN_REQUIRE(n_rows < (1ll << 31), TSPN_ESHAPE, "tspn_survivor_rows: too many rows");
+    TSPN_REQUIRE(tspn_survivor_rows_supported(max_frames, d_spans ? n_anchors : 4), TSPN_ESHAPE,
+                 "tspn_survivor_rows: max_frames=%d / n_anchors=%d not supported (use tspn_assemble_relative + "
+                 "tspn_span_proposals)", max_frames, n_anchors);
+    if (d_spans) {
+        TSPN_REQUIRE(d_conv_w && d_pred_w && d_sizes && stride > 0.0f, TSPN_EBADARG,
+                     "tspn_survivor_rows: span head weights / anchors missing");
+        TSPN_REQUIRE(ld_spans >= (int64_t)span_locations(max_frames, stride) * 2 * n_anchors, TSPN_ESHAPE,
+                     "tspn_survivor_rows: ld_spans=%lld < locations(max_frames) * 2A", (long long)ld_spans);
+    }
+    const int cap = (max_frames + 3) / 4 * 4 + 4;
+    const int smem = TSPN_GEO_CHANNELS * cap * 4;
+    TSPN_CUDA_OK(cudaFuncSetAttribute(survivor_rows_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    prefer_max_smem(survivor_rows_kernel<4>);
+    survivor_rows_kernel<4><<<(unsigned)n_rows, SV_THREADS, smem, (cudaStream_t)stream>>>(
+        d_table, num_videos, reinterpret_cast<const float4*>(d_boxes), d_span, d_rows, rows_per_video,
+        reinterpret_cast<__nv_bfloat16*>(d_rel_bf16), ld_rel, d_terms_subject, d_terms_object, n_outputs, d_row_bias,
+        d_conv_w, d_conv_b, d_pred_w, d_pred_b, d_sizes, stride, d_spans, ld_spans, cap);
+    TSPN_CUDA_OK(cudaGetLastError());
+    return TSPN_OK;
+}
+
+}  // extern "C"

@@ -83,7 +83,7 @@ def pair_geometry_outputs(batch: DeviceBatch, write_geo: bool = True) -> Dict[st
 
 
 def pair_geometry_phase(batch: DeviceBatch, out: Dict[str, torch.Tensor], phase: int, clipped: bool = False,
-                        dense_ctas: Optional[bool] = None) -> None:
+                        dense_ctas: Optional[bool] = None, persistent: Optional[bool] = None) -> None:
     """One phase of ``tspn_pair_geo_viou`` on the current stream: ``_lib.GEO_PHASE_PRE`` (per-tracklet volumes,
     and zeroing of the per-pair sums unless the batch is single-chunk), ``GEO_PHASE_MAIN`` (the pair kernel:
     geometry rows, fixed-point sums, overlap windows), ``GEO_PHASE_POST`` (vIoU / tIoU), or 0 for all three.
@@ -94,6 +94,10 @@ def pair_geometry_phase(batch: DeviceBatch, out: Dict[str, torch.Tensor], phase:
     flags = (_lib.VIOU_CLIPPED if clipped else _lib.VIOU_FULL) | (_lib.GEO_DENSE_CTAS if dense_ctas else 0)
     if single_chunk(batch):
         flags |= _lib.GEO_SINGLE_CHUNK
+    if persistent is None:
+        persistent = os.environ.get("TSPN_GEO_PERSISTENT", "1") == "1"
+    if persistent and not dense_ctas:
+        flags |= _lib.GEO_PERSISTENT
     check(load().tspn_pair_geo_viou(
         ptr(batch.table), batch.num_videos, int(tot[_lib.TOT_ITEMS]), int(tot[_lib.TOT_GEO_CHUNK]),
         batch.total_tracklets, batch.total_pairs,
@@ -105,24 +109,26 @@ def pair_geometry_phase(batch: DeviceBatch, out: Dict[str, torch.Tensor], phase:
 
 def pair_geometry(batch: DeviceBatch, write_geo: bool = True, clipped: bool = False,
                   out: Optional[Dict[str, torch.Tensor]] = None,
-                  dense_ctas: Optional[bool] = None, events=None) -> Dict[str, torch.Tensor]:
+                  dense_ctas: Optional[bool] = None, events=None,
+                  persistent: Optional[bool] = None) -> Dict[str, torch.Tensor]:
     """All-pairs per-frame geometry + vIoU/tIoU/overlap (trajectory.py:85-141, common.py:65-106).
     ``events``: a pair of CUDA events recorded immediately before and after the pair kernel itself (the
     volume pre-kernel and the per-pair finalize are issued as separate phases around them).
     ``dense_ctas`` selects the 1024-threads-per-SM shape of the kernel (2-stage ring, 64 registers) instead of
     the default ~512 threads per SM (bit-identical results, measured slower; A/B timing only - default from
-    the environment variable TSPN_GEO_DENSE)."""
+    the environment variable TSPN_GEO_DENSE).  ``persistent``: the pair kernel as persistent CTAs pulling work
+    items from a queue (default, TSPN_GEO_PERSISTENT) or one CTA per work item; bit-identical."""
     if out is None:
         out = pair_geometry_outputs(batch, write_geo)
     if events is None:
-        pair_geometry_phase(batch, out, 0, clipped, dense_ctas)
+        pair_geometry_phase(batch, out, 0, clipped, dense_ctas, persistent)
     else:
         stream = torch.cuda.current_stream(batch.device)
-        pair_geometry_phase(batch, out, _lib.GEO_PHASE_PRE, clipped, dense_ctas)
+        pair_geometry_phase(batch, out, _lib.GEO_PHASE_PRE, clipped, dense_ctas, persistent)
         events[0].record(stream)
-        pair_geometry_phase(batch, out, _lib.GEO_PHASE_MAIN, clipped, dense_ctas)
+        pair_geometry_phase(batch, out, _lib.GEO_PHASE_MAIN, clipped, dense_ctas, persistent)
         events[1].record(stream)
-        pair_geometry_phase(batch, out, _lib.GEO_PHASE_POST, clipped, dense_ctas)
+        pair_geometry_phase(batch, out, _lib.GEO_PHASE_POST, clipped, dense_ctas, persistent)
     return out
 
 
@@ -314,9 +320,10 @@ def tracklet_rows(batch: DeviceBatch) -> torch.Tensor:
 
 def predicate_head_affine(x: torch.Tensor, packed: torch.Tensor, n_outputs: int, bias: Optional[torch.Tensor] = None,
                           row_bias: Optional[torch.Tensor] = None, raw: bool = False,
-                          k_dim: Optional[int] = None) -> torch.Tensor:
+                          k_dim: Optional[int] = None, background: bool = False) -> torch.Tensor:
     """``act(x Wp^T + bias + row_bias[row])`` on the tensor cores (``tspn_predicate_head_affine``); ``packed``
-    from ``pack_predicate_weights`` of the ``[n_outputs, k_dim]`` weight slice; ``raw`` skips the sigmoid."""
+    from ``pack_predicate_weights`` of the ``[n_outputs, k_dim]`` weight slice; ``raw`` skips the sigmoid;
+    ``background``: small-footprint launch for a side stream under the pair kernel (TSPN_AFFINE_BACKGROUND)."""
     x = _cuda(x)
     m = x.shape[0]
     f = int(k_dim if k_dim is not None else x.shape[1])
@@ -330,7 +337,8 @@ def predicate_head_affine(x: torch.Tensor, packed: torch.Tensor, n_outputs: int,
         ptr(x), int(is_bf16), x.stride(0) if m > 1 else max(f, x.stride(0)), m, f, ptr(packed),
         ptr(_cuda(bias, torch.float32)) if bias is not None else None,
         ptr(_cuda(row_bias, torch.float32)) if row_bias is not None else None,
-        row_bias.stride(0) if row_bias is not None else 0, n_outputs, ptr(y), _lib.AFFINE_RAW if raw else 0, ptr(ws),
+        row_bias.stride(0) if row_bias is not None else 0, n_outputs, ptr(y),
+        (_lib.AFFINE_RAW if raw else 0) | (_lib.AFFINE_BACKGROUND if background else 0), ptr(ws),
         stream_ptr()), "tspn_predicate_head_affine")
     _count(1 if ws.numel() <= 16 else 2)
     return y
@@ -351,6 +359,40 @@ def assemble_relative(batch: DeviceBatch, geo: torch.Tensor, overlap: torch.Tens
         ptr(_cuda(terms_object, torch.float32)), r, ptr(row_bias), stream_ptr()), "tspn_assemble_relative")
     _count(1)
     return rel, row_bias
+
+
+def survivor_rows_supported(batch: DeviceBatch, n_anchors: int) -> bool:
+    return bool(load().tspn_survivor_rows_supported(int(batch.totals[_lib.TOT_MAX_T]), int(n_anchors)))
+
+
+def survivor_rows(batch: DeviceBatch, rows: torch.Tensor, terms_subject: torch.Tensor, terms_object: torch.Tensor,
+                  span_weights=None, sizes: Optional[torch.Tensor] = None, stride: float = 0.0):
+    """``tspn_survivor_rows``: for the surviving rows ``rows [V, K]`` (global pair rows, -1 = padding) the pooled
+    relative block (bf16 ``[V*K, 3000]``), the bias rows ``A_s[s] + A_o[o]`` and - with ``span_weights =
+    (conv_w, conv_b, pred_w, pred_b)`` - the decoded span proposals ``[V*K, L_max * A, 2]`` int32, all
+    recomputed from the boxes (bit-identical to ``assemble_relative`` / ``span_proposals`` on stored rows)."""
+    dev = batch.device
+    rows = _cuda(rows, torch.int64)
+    k = int(rows.shape[1])
+    n_rows = int(rows.numel())
+    r = int(terms_subject.shape[1])
+    max_t = int(batch.totals[_lib.TOT_MAX_T])
+    rel = torch.empty((n_rows, _lib.REL_DIM), dtype=torch.bfloat16, device=dev)
+    row_bias = torch.empty((n_rows, r), dtype=torch.float32, device=dev)
+    spans, a_n, ld_spans = None, 4, 0
+    cw = cb = pw = pb = None
+    if span_weights is not None:
+        cw, cb, pw, pb = (_cuda(w, torch.float32) if w is not None else None for w in span_weights)
+        a_n = pw.shape[0] // 2
+        ld_spans = span_num_locations(max_t, stride) * a_n * 2
+        spans = torch.empty((n_rows, ld_spans // 2, 2), dtype=torch.int32, device=dev)
+    check(load().tspn_survivor_rows(
+        ptr(batch.table), batch.num_videos, max_t, ptr(batch.boxes), ptr(batch.span), ptr(rows), n_rows, k,
+        ptr(rel), rel.stride(0), ptr(_cuda(terms_subject, torch.float32)), ptr(_cuda(terms_object, torch.float32)), r,
+        ptr(row_bias), ptr(cw), ptr(cb), ptr(pw), ptr(pb), a_n, ptr(_cuda(sizes, torch.float32)) if sizes is not None
+        else None, float(stride), ptr(spans), ld_spans, stream_ptr()), "tspn_survivor_rows")
+    _count(1)
+    return rel, row_bias, spans
 
 
 def span_head(x: torch.Tensor, conv_w: torch.Tensor, conv_b: torch.Tensor, pred_w: torch.Tensor,
@@ -433,11 +475,12 @@ def span_decode(reg: torch.Tensor, sizes: torch.Tensor, stride: float) -> torch.
 RECORD_FIELDS = ("score", "s_cls", "pred", "o_cls", "s_tid", "o_tid", "start", "end")
 
 
-def postprocess(batch: DeviceBatch, logits: torch.Tensor, overlap: torch.Tensor, topk_per_pair: int = 20,
+def postprocess(batch: DeviceBatch, logits: torch.Tensor, overlap: Optional[torch.Tensor], topk_per_pair: int = 20,
                 topk_per_video: int = 200, rows: Optional[torch.Tensor] = None,
                 row_video_off: Optional[torch.Tensor] = None, mirror_q4: bool = False):
     """Relation triplet records (predict.py:66-117): ``records [V, topk_per_video, 8]`` int32
-    (field 0 is the fp32 score's bit pattern) and ``counts [V]`` int32."""
+    (field 0 is the fp32 score's bit pattern) and ``counts [V]`` int32.  ``overlap=None``: the windows are
+    derived from the tracklet spans (no dependence on the pair kernel's outputs)."""
     logits = _cuda(logits, torch.float32)
     m, r = logits.shape
     v = batch.num_videos
@@ -446,7 +489,8 @@ def postprocess(batch: DeviceBatch, logits: torch.Tensor, overlap: torch.Tensor,
     counts = torch.empty(v, dtype=torch.int32, device=dev)
     ws = torch.empty(load().tspn_postprocess_workspace_bytes(m, topk_per_pair), dtype=torch.uint8, device=dev)
     check(load().tspn_postprocess(ptr(batch.table), v, ptr(logits), ptr(rows), ptr(row_video_off), m, r,
-                                  ptr(batch.cls), batch.cls.shape[1], ptr(overlap), topk_per_pair, topk_per_video,
+                                  ptr(batch.cls), batch.cls.shape[1], ptr(overlap), ptr(batch.span), topk_per_pair,
+                                  topk_per_video,
                                   1 if mirror_q4 else 0, ptr(records), ptr(counts), ptr(ws), stream_ptr()),
           "tspn_postprocess")
     _count(2)

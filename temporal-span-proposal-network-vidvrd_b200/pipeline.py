@@ -7,6 +7,7 @@ kernel launches on the current stream and no host synchronisation.
 from __future__ import annotations
 
 import dataclasses
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -110,6 +111,16 @@ class StageResult:
         return self.rel_logits[self.batch.pair_slice(v)]
 
 
+def side_priority() -> int:
+    """Priority of the side branch's stream (-1 = high, the default).  The pair kernel keeps every SM full
+    (one 512-thread CTA each, 134 KB of shared memory), so a side-branch CTA only starts when a pair CTA
+    retires.  At equal priority the block scheduler hands the freed SM to the next pending pair CTA and the
+    side branch (relationness, top-K, per-tracklet predicate terms - ~130 us of small kernels) is left for
+    the pair kernel's last wave, i.e. back on the critical path; at high priority it claims the first SMs
+    that free up and is done long before the pair kernel ends.  Captured kernel nodes keep the priority."""
+    return int(os.environ.get("TSPN_SIDE_PRIORITY", "-1"))
+
+
 class PairStage:
     def __init__(self, config: StageConfig):
         self.cfg = config
@@ -160,30 +171,84 @@ class PairStage:
     # the class logits / motion rows, so it runs on a second stream underneath the HBM-bound geometry
     # kernel of `geo`; `tail` (feature rows, heads, records) joins both.  Eager `forward` forks and joins
     # with stream events; `capture` freezes each segment into a CUDA graph (GraphedStage).
-    def _side_stream(self, device) -> torch.cuda.Stream:
-        key = str(device)
+    def _side_stream(self, device, which: int = 0) -> torch.cuda.Stream:
+        key = "%s/%d" % (device, which)
         if self._side.get(key) is None:
-            self._side[key] = torch.cuda.Stream(device)
+            self._side[key] = torch.cuda.Stream(device, priority=side_priority())
         return self._side[key]
 
-    def _seg_side(self, batch: DeviceBatch, features: Optional[torch.Tensor]):
+    def _survivor_path(self, batch: DeviceBatch, features, heads: bool) -> bool:
+        """Heads of the K survivors entirely on the side branch, from the boxes (csrc/survivors.cu): tensor
+        precision + sparsify, features built on the GPU, and a batch the kernel supports."""
         c = self.cfg
-        scores = idx = val = row = mn = None
+        if not (heads and c.use_ppn and c.sparsify and self._decomposed(features)) or c.keep_span_reg:
+            return False
+        if os.environ.get("TSPN_SURVIVOR_PATH", "1") != "1":
+            return False
+        a_n = 4
+        if c.use_dpn:
+            cw, pw = self.w[DPN_PREFIX + "conv.weight"], self.w[DPN_PREFIX + "duration_pred.weight"]
+            if cw.shape[1] != _lib.GEO_CHANNELS:
+                return False                            # _span_heads raises the descriptive error
+            a_n = pw.shape[0] // 2
+        return batch.total_pairs > 0 and ops.survivor_rows_supported(batch, a_n)
+
+    def _seg_side(self, batch: DeviceBatch, features: Optional[torch.Tensor], heads: bool = False):
+        c = self.cfg
+        scores = idx = val = row = mn = early = None
+        if features is None and (batch.motion is None or batch.cls is None):
+            raise ValueError("feature construction needs the cls and motion tracklet fields")
+        # Two independent chains - relationness -> top-K, and the per-tracklet inputs of the predicate head - each
+        # a string of small latency-bound kernels that co-reside with the pair kernel: they run side by side
+        # on two streams and join before anything that needs both.
+        cur = torch.cuda.current_stream(batch.device)
+        second = self._side_stream(batch.device, 1)
+        second.wait_stream(cur)
+        with torch.cuda.stream(second):
+            if features is None:
+                if self._decomposed(features):
+                    # per-tracklet terms of the decomposed head: A_s = [cls | motion_norm] W_s^T, A_o likewise
+                    x_trk = ops.tracklet_rows(batch)
+                    kd = c.n_classes + _lib.MOTION_DIM
+                    mn = (ops.predicate_head_affine(x_trk, self.packed_sub, c.n_predicates, raw=True, k_dim=kd,
+                                                    background=True),
+                          ops.predicate_head_affine(x_trk, self.packed_obj, c.n_predicates, raw=True, k_dim=kd,
+                                                    background=True))
+                else:
+                    mn = ops.normalize_motion(batch.motion)
         if c.use_ppn:
             scores = ops.relationness(batch, self.ppn_weights())
             idx, val, row = ops.topk_pairs(batch, scores, c.topk, exclude_diagonal=c.sparsify)
-        if features is None:
-            if batch.motion is None or batch.cls is None:
-                raise ValueError("feature construction needs the cls and motion tracklet fields")
-            if self._decomposed(features):
-                # per-tracklet terms of the decomposed head: A_s = [cls | motion_norm] W_s^T, A_o likewise
-                x_trk = ops.tracklet_rows(batch)
-                kd = c.n_classes + _lib.MOTION_DIM
-                mn = (ops.predicate_head_affine(x_trk, self.packed_sub, c.n_predicates, raw=True, k_dim=kd),
-                      ops.predicate_head_affine(x_trk, self.packed_obj, c.n_predicates, raw=True, k_dim=kd))
-            else:
-                mn = ops.normalize_motion(batch.motion)
-        return scores, idx, val, row, mn
+        cur.wait_stream(second)
+        if mn is not None and not torch.cuda.is_current_stream_capturing():
+            for u in (mn if isinstance(mn, tuple) else (mn,)):
+                u.record_stream(cur)                  # allocated on the second side stream, consumed on this one
+        if self._survivor_path(batch, features, heads):
+            # nothing below reads an output of the pair kernel: relative block, bias rows and span proposals
+            # come from the boxes, the record windows from the spans - the whole chain stays on this branch
+            sw = None
+            if c.use_dpn:
+                sw = (self.w[DPN_PREFIX + "conv.weight"], self.w[DPN_PREFIX + "conv.bias"],
+                      self.w[DPN_PREFIX + "duration_pred.weight"], self.w[DPN_PREFIX + "duration_pred.bias"])
+            rel16, row_bias, sp = ops.survivor_rows(batch, row, mn[0], mn[1], span_weights=sw, sizes=self.sizes_dev,
+                                                    stride=c.anchor_stride)
+            logits = ops.predicate_head_affine(rel16, self.packed_rel, c.n_predicates, bias=self.w[CLS_PREFIX + "bias"],
+                                               row_bias=row_bias, background=True)
+            records = counts = None
+            if c.records:
+                records, counts = ops.postprocess(batch, logits, None, c.topk_per_pair, c.topk_per_video,
+                                                  rows=row.reshape(-1), row_video_off=self._row_offsets(batch),
+                                                  mirror_q4=c.mirror_q4)
+            early = {"logits": logits, "records": records, "counts": counts, "spans": sp}
+        return scores, idx, val, row, mn, early
+
+    def _row_offsets(self, batch: DeviceBatch) -> torch.Tensor:
+        """First scored row of every video in sparsify mode ([V + 1] int64: v * K); built once, outside any capture."""
+        key = (batch.num_videos, self.cfg.topk, str(batch.device))
+        if self._row_off is None or self._row_off_k != key:
+            self._row_off = torch.arange(batch.num_videos + 1, dtype=torch.int64, device=batch.device) * self.cfg.topk
+            self._row_off_k = key
+        return self._row_off
 
     def _decomposed(self, features) -> bool:
         """Tensor precision with features built on the GPU: the classifier is evaluated as
@@ -218,9 +283,26 @@ class PairStage:
 
     def _seg_tail(self, batch: DeviceBatch, features, heads, side, geom) -> StageResult:
         c = self.cfg
-        scores, idx, val, row, mn = side
+        scores, idx, val, row, mn, early = side
         k_eff = self.k_effective(batch)
         sparsify = c.sparsify and c.use_ppn
+        if early is not None:
+            # survivor path: the heads already ran on the side branch; only the per-pair finalize is left
+            main = torch.cuda.current_stream(batch.device)
+            side_stream = self._side_stream(batch.device)
+            side_stream.wait_stream(main)
+            with torch.cuda.stream(side_stream):
+                ops.pair_geometry_phase(batch, geom, _lib.GEO_PHASE_POST, clipped=c.viou_clipped)
+            main.wait_stream(side_stream)
+            spans = span_bufs = None
+            sp = early["spans"]
+            if sp is not None:
+                k, a_n = row.shape[1], sp.shape[1] // ops.span_num_locations(max(batch.t), c.anchor_stride)
+                spans = [sp[v * k:v * k + k_eff[v], :ops.span_num_locations(batch.t[v], c.anchor_stride) * a_n]
+                         for v in range(batch.num_videos)]
+                span_bufs = [sp]
+            return StageResult(batch, geom, scores, idx, val, row, None, None, early["logits"], None, spans, k_eff,
+                               sparsify, early["records"], early["counts"], span_bufs)
         feats32 = feats16 = logits = None
         tensor = c.precision == "tensor"
         # The span head (HBM-bound reads of the surviving geometry rows) runs on the side stream underneath
@@ -257,13 +339,8 @@ class PairStage:
         records = counts = None
         if heads and c.records:
             if sparsify:
-                if self._row_off is None or self._row_off.shape[0] != batch.num_videos + 1 \
-                        or self._row_off_k != c.topk or self._row_off.device != batch.device:
-                    self._row_off = torch.arange(batch.num_videos + 1, dtype=torch.int64,
-                                                 device=batch.device) * c.topk
-                    self._row_off_k = c.topk
                 records, counts = ops.postprocess(batch, logits, geom["overlap"], c.topk_per_pair, c.topk_per_video,
-                                                  rows=row.reshape(-1), row_video_off=self._row_off,
+                                                  rows=row.reshape(-1), row_video_off=self._row_offsets(batch),
                                                   mirror_q4=c.mirror_q4)
             else:
                 records, counts = ops.postprocess(batch, logits, geom["overlap"], c.topk_per_pair, c.topk_per_video,
@@ -288,9 +365,9 @@ class PairStage:
         with torch.cuda.stream(side_stream):
             if pre_aside:
                 self._seg_pre(batch, geom)
-            side = self._seg_side(batch, features)
+            side = self._seg_side(batch, features, heads)
         for t in side:
-            for u in (t if isinstance(t, tuple) else (t,)):
+            for u in (t if isinstance(t, tuple) else tuple(t.values()) if isinstance(t, dict) else (t,)):
                 if u is not None:
                     u.record_stream(main)             # allocated on the side stream, consumed on main
         events = None
@@ -372,7 +449,8 @@ class GraphedStage:
                  heads: bool = True, single: bool = True):
         self.stage, self.batch = stage, batch
         dev = batch.device
-        self.side_stream = torch.cuda.Stream(dev)     # own stream: replays of different slots may overlap
+        self.side_stream = torch.cuda.Stream(dev, priority=side_priority())   # own stream: replays of different
+                                                                              # slots may overlap
         self._cap_stream = torch.cuda.Stream(dev)
         stage.forward(batch, features=features, heads=heads)      # warm-up: lazy init outside capture
         torch.cuda.synchronize(dev)
@@ -395,7 +473,7 @@ class GraphedStage:
                 with torch.cuda.stream(fork):
                     if pre_aside:
                         stage._seg_pre(batch, geom)
-                    side = stage._seg_side(batch, features)
+                    side = stage._seg_side(batch, features, heads)
                 stage._seg_geo(batch, geom, events=self.ev_geo, with_pre=not pre_aside)
                 cap.wait_stream(fork)
                 self.result = stage._seg_tail(batch, features, heads, side, geom)
@@ -407,7 +485,7 @@ class GraphedStage:
             with torch.cuda.graph(self.g_side, stream=self._cap_stream):
                 if pre_aside:
                     stage._seg_pre(batch, geom)
-                side = stage._seg_side(batch, features)
+                side = stage._seg_side(batch, features, heads)
             with torch.cuda.graph(self.g_geo, stream=self._cap_stream):
                 stage._seg_geo(batch, geom, events=self.ev_geo, with_pre=not pre_aside)
             with torch.cuda.graph(self.g_tail, stream=self._cap_stream):

@@ -63,7 +63,7 @@ def test_video_table_layout():
         items += n[v] * groups * chunks if n[v] >= 2 else 0
     assert list(tot[:6]) == [trk, pairs, geo, items, boxes, scores] and tot[6] == 40 and tot[7] == 1200 and tot[8] == 2048
     assert [_lib.load().tspn_geo_chunk(x) for x in (1, 512, 513, 1024, 1025, 5000)] == [512, 512, 1024, 1024, 2048, 2048]
-    assert _lib.build_video_table([70, 3], [300, 20])[1][_lib.TOT_ITEMS] == 70 * 2 + 3      # two groups of <= 64
+    assert _lib.build_video_table([70, 3], [300, 20])[1][_lib.TOT_ITEMS] == 70 * 3 + 3      # three groups of <= 32
     assert boxes % 8 == 0
     with pytest.raises(RuntimeError, match="TSPN_ESHAPE"):
         _lib.build_video_table([3], [0])

@@ -95,15 +95,18 @@ def test_pair_geometry_kernel_shapes(shapes, chunk, clip):
 @pytest.mark.parametrize("clip", [False, True])
 def test_dense_and_sparse_kernel_shapes_are_bit_identical(shapes, clip):
     """The two occupancy shapes of the pair-geometry kernel (1024 threads per SM / 2-stage ring / 64 registers
-    against ~512 threads / 3-stage ring): every output bit for bit."""
+    against ~512 threads / 3-stage ring) and its two scheduling forms (persistent CTAs pulling work items from a
+    queue - the ring phases run on across items - against one CTA per work item): every output bit for bit."""
     vids = [synth.make_video(n, t, 35, seed=s) for n, t, s in shapes]
     batch = _batch(vids)
-    a = ops.pair_geometry(batch, write_geo=True, clipped=clip, dense_ctas=False)
-    b = ops.pair_geometry(batch, write_geo=True, clipped=clip, dense_ctas=True)
-    c = ops.pair_geometry(batch, write_geo=False, clipped=clip, dense_ctas=False)
+    a = ops.pair_geometry(batch, write_geo=True, clipped=clip, dense_ctas=False, persistent=True)
+    b = ops.pair_geometry(batch, write_geo=True, clipped=clip, dense_ctas=True, persistent=False)
+    c = ops.pair_geometry(batch, write_geo=False, clipped=clip, dense_ctas=False, persistent=True)
+    d = ops.pair_geometry(batch, write_geo=True, clipped=clip, dense_ctas=False, persistent=False)
     torch.cuda.synchronize()
     for key in ("geo", "viou", "tiou", "overlap"):
         assert torch.equal(a[key], b[key]), key
+        assert torch.equal(a[key], d[key]), key
     for key in ("viou", "tiou", "overlap"):
         assert torch.equal(a[key], c[key]), key
 

@@ -163,3 +163,109 @@ def test_decomposed_head_matches_materialised_rows_and_oracle(sparsify):
         np.testing.assert_allclose(a, want, rtol=0, atol=1e-2)
     # records are built from the decomposed logits
     assert res[False].records.shape == res[True].records.shape
+
+
+@pytest.mark.parametrize("shapes,k", [
+    ([(9, 120, 11), (3, 64, 12), (6, 700, 13), (1, 30, 14), (2, 5, 15)], 24),     # ragged: padding rows, N = 1, tiny T
+    ([(12, 2000, 1), (40, 1500, 2)], 96),                                          # bench-shaped rows (4 passes)
+    ([(5, 2500, 3), (4, 513, 4)], 20),                                             # tile longer than 2048 frames
+])
+def test_survivor_rows_bit_identical_to_stored_rows(shapes, k):
+    """tspn_survivor_rows (relative block, bias rows and span proposals recomputed from the boxes) against
+    tspn_assemble_relative + tspn_span_proposals on the geometry rows the all-pairs kernel stored: every output
+    bit for bit, including padding rows and videos shorter than the batch's longest."""
+    from tspn_b200.batch import HostBatch
+    c, r = 35, 50
+    vids = [synth.make_video(n, t, c, seed=s) for n, t, s in shapes]
+    vids[0].span[1] = (0, 3)                                   # some pairs without temporal overlap
+    vids[0].span[2] = (vids[0].n_frames - 2, vids[0].n_frames)
+    sd = synth.make_weights(c, r, synth.feature_dim(c), dpn_in=8, seed=5)
+    batch = HostBatch.from_videos(vids).to_device("cuda")
+    rng = np.random.Generator(np.random.PCG64(k))
+    rows = np.full((len(vids), k), -1, dtype=np.int64)
+    off = 0
+    for i, v in enumerate(vids):
+        kk = min(k, v.n_pairs)
+        rows[i, :kk] = off + rng.permutation(v.n_pairs)[:kk]
+        off += v.n_pairs
+    rows_d = torch.from_numpy(rows).cuda()
+    n_trk = batch.total_tracklets
+    terms = torch.from_numpy(rng.normal(size=(2, n_trk, r)).astype(np.float32)).cuda()
+    sw = tuple(torch.from_numpy(sd["relpn.duration_proposal_network.dpn_head." + key]).cuda()
+               for key in ("conv.weight", "conv.bias", "duration_pred.weight", "duration_pred.bias"))
+    sizes = torch.tensor([16.0, 64.0, 256.0, 1024.0], device="cuda")
+    stride = 16.0
+    assert ops.survivor_rows_supported(batch, 4)
+    rel, bias, spans = ops.survivor_rows(batch, rows_d, terms[0], terms[1], span_weights=sw, sizes=sizes, stride=stride)
+    geom = ops.pair_geometry(batch, write_geo=True)
+    want_rel, want_bias = ops.assemble_relative(batch, geom["geo"], geom["overlap"], rows_d.reshape(-1), terms[0], terms[1])
+    torch.cuda.synchronize()
+    assert torch.equal(rel.view(torch.int16), want_rel.view(torch.int16))
+    assert torch.equal(bias, want_bias)
+    a_n = 4
+    l_max = ops.span_num_locations(max(batch.t), stride)
+    assert spans.shape == (rows.size, l_max * a_n, 2)
+    for i, v in enumerate(vids):
+        t, tp = v.n_frames, (v.n_frames + 3) // 4 * 4
+        l_v = ops.span_num_locations(t, stride)
+        got = spans[i * k:(i + 1) * k]
+        assert (got[:, l_v * a_n:] == 0).all()
+        if v.n_pairs == 0:
+            x = torch.zeros((1, 8, tp), device="cuda")
+            want = ops.span_proposals(x, *sw, sizes, stride, rows=torch.full((k,), -1, dtype=torch.int64, device="cuda"),
+                                      t=t, row_base=0)
+        else:
+            p0 = batch.pair_slice(i).start
+            x = batch.geo_rows(geom["geo"], i)
+            want = ops.span_proposals(x, *sw, sizes, stride, rows=rows_d[i], t=t, row_base=p0)
+        torch.cuda.synchronize()
+        assert torch.equal(got[:, :l_v * a_n], want), "video %d" % i
+
+
+@pytest.mark.parametrize("use_dpn", [True, False])
+def test_stage_survivor_path_equals_stored_row_path(use_dpn, monkeypatch):
+    """The whole stage (tensor precision, sparsify) with the heads of the survivors on the side branch
+    (tspn_survivor_rows -> affine head -> records, nothing waits for the pair kernel) against the path that
+    reads the stored geometry rows after it: logits to split-K summation order, everything else bit for bit;
+    eager and captured."""
+    from tspn_b200.batch import HostBatch
+    from tspn_b200.pipeline import PairStage, StageConfig
+    c, r, k = 35, 50, 40
+    vids = [synth.make_video(9, 120, c, seed=11), synth.make_video(3, 64, c, seed=12), synth.make_video(6, 700, c, seed=13),
+            synth.make_video(1, 40, c, seed=14)]
+    sd = synth.make_weights(c, r, synth.feature_dim(c), dpn_in=8, seed=2)
+    cfg = StageConfig(n_classes=c, n_predicates=r, topk=k, sparsify=True, precision="tensor", use_dpn=use_dpn,
+                      anchor_sizes=(16.0, 64.0, 256.0, 1024.0), anchor_stride=16.0)
+    out = {}
+    for mode in ("0", "1", "graph"):
+        monkeypatch.setenv("TSPN_SURVIVOR_PATH", "0" if mode == "0" else "1")
+        stage = PairStage(cfg)
+        stage.load_weights(sd, "cuda")
+        batch = HostBatch.from_videos(vids).to_device("cuda")
+        assert stage._survivor_path(batch, None, True) == (mode != "0")
+        if mode == "graph":
+            g = stage.capture(batch)
+            g.replay()
+            res = g.replay()
+        else:
+            res = stage.forward(batch)
+        torch.cuda.synchronize()
+        out[mode] = res
+    a = out["0"]
+    for mode in ("1", "graph"):
+        b = out[mode]
+        assert torch.equal(a.topk_idx, b.topk_idx) and torch.equal(a.topk_row, b.topk_row)
+        for key in ("viou", "tiou", "overlap", "geo"):
+            assert torch.equal(a.geom[key], b.geom[key]), key
+        assert (a.rel_logits - b.rel_logits).abs().max().item() <= 5e-6
+        for i in range(len(vids)):
+            if use_dpn:
+                assert torch.equal(a.spans[i], b.spans[i]), i
+            else:
+                assert b.spans is None
+        # records: same triplets unless two scores are closer than the summation-order noise
+        sa, sb = ops.record_scores(a.records), ops.record_scores(b.records)
+        assert torch.equal(a.record_counts, b.record_counts)
+        assert (sa - sb).abs().max().item() <= 5e-6
+        same = (a.records[..., 1:] == b.records[..., 1:]).all(dim=-1)
+        assert same.float().mean().item() > 0.98
