@@ -298,12 +298,18 @@ int tspn_span_proposals(const float* d_x, const int64_t* d_rows, int64_t row_bas
  * exactly what tspn_assemble_relative and tspn_span_proposals produce from the stored geometry rows of
  * tspn_pair_geo_viou - bit for bit (same per-frame device code, same summation orders) - but from the boxes:
  * it does not depend on the all-pairs kernel and is shaped to co-reside with it (128 threads, <= 96
- * registers, 32*(max_frames+4) bytes of shared memory), so the heads of the K survivors run on a
+ * registers, 16 KB of shared memory per 512 frames of max_frames + 8 KB), so the heads of the K survivors run on a
  * side stream underneath the HBM-bound all-pairs kernel instead of re-reading 64 KB per row behind it.
  * d_spans (may be NULL: no span head) int32 [n_rows][ld_spans]: row r holds [locations(T_v) * A][2] frame
  * bounds of its video, zero-filled up to ld_spans >= locations(max_frames) * 2A.  Span weights as for
  * tspn_span_proposals with Cin = 8.  tspn_survivor_rows_supported: n_anchors == 4 and the tile of
  * max_frames frames fits shared memory; otherwise use the two stored-row entry points. */
+/* d_terms_subject / d_terms_object / d_row_bias may all be NULL: the bias rows then come from
+ * tspn_gather_pair_terms (d_row_bias [n_rows][n_outputs] = A_s[subject] + A_o[object], zeros for padding rows;
+ * d_rows NULL = all pair rows in order), so that the recomputation need not wait for the per-tracklet terms. */
+int tspn_gather_pair_terms(const int64_t* d_table, int num_videos, const int64_t* d_rows, int64_t n_rows,
+                           const float* d_terms_subject, const float* d_terms_object, int n_outputs,
+                           float* d_row_bias, void* stream);
 int tspn_survivor_rows_supported(int max_frames, int n_anchors);
 int tspn_survivor_rows(const int64_t* d_table, int num_videos, int max_frames, const float* d_boxes,
                        const int32_t* d_span, const int64_t* d_rows, int64_t n_rows, int64_t rows_per_video,

@@ -75,6 +75,7 @@ SIGNATURES = {
     "tspn_postprocess_workspace_bytes": (c_int64, [c_int64, c_int]),
     "tspn_postprocess": (c_int, [P, c_int, P, P, P, c_int64, c_int, P, c_int, P, P, c_int, c_int, c_int, P, P, P, P]),
     "tspn_survivor_rows_supported": (c_int, [c_int, c_int]),
+    "tspn_gather_pair_terms": (c_int, [P, c_int, P, c_int64, P, P, c_int, P, P]),
     "tspn_survivor_rows": (c_int, [P, c_int, c_int, P, P, P, c_int64, c_int64, P, c_int64, P, P, c_int, P, P, P, P, P,
                                    c_int, P, c_float, P, c_int64, P]),
 }

@@ -14,7 +14,7 @@
 // the two tracklets are 2 x 32 KB and L2-resident, the per-frame math is ~3 instructions per frame, and
 // nothing here depends on the all-pairs kernel - so this kernel, the predicate head and the records run
 // on the side stream UNDERNEATH the all-pairs kernel: a CTA is shaped (128 threads = 4 warps x 96 registers,
-// 64 KB of shared memory at T = 2000) to co-reside with that kernel's 512-thread / 104-register / 131 KB CTA.
+// 72 KB of shared memory at T = 2000) to co-reside with that kernel's 512-thread / 104-register / 131 KB CTA.
 //
 // The per-frame values come from the same device function as the all-pairs kernel (geo_math.cuh), the
 // pooling adds frames in ascending order like assemble_kernel, the span chain is span_math.cuh: every
@@ -28,7 +28,11 @@
 namespace tspn {
 
 constexpr int SV_THREADS = 128;
-constexpr int SV_CHUNK = SV_THREADS * GEO_FPT;          // frames per pass
+constexpr int SV_CHUNK = SV_THREADS * GEO_FPT;          // frames per pass = frames per shared-memory block
+constexpr int SV_BLOCK_BYTES = SV_CHUNK * 32;           // a block: 512 subject boxes | 512 object boxes (16 KB), later
+                                                        // overwritten in place by its [8 channels][512 frames] tile
+constexpr int SV_HALF = SV_CHUNK * 16;                  // offset of the object boxes inside a block
+constexpr int SV_HALO_BYTES = SV_HALF + 128;            // one more (subject, object) frame behind the last block
 constexpr int SV_CIN = TSPN_GEO_CHANNELS;
 constexpr int SV_INV_TAB = 32;
 constexpr int SV_SMEM_MAX = 200 * 1024;
@@ -41,6 +45,16 @@ __host__ __device__ __forceinline__ int span_locations(int t, float stride) {
     return n;
 }
 
+// column `col` (= frame - a4) of channel `ch` in the blocked tile
+__device__ __forceinline__ float& tile_at(float* tile, int ch, int col) {
+    return tile[(col >> 9) * (SV_BLOCK_BYTES / 4) + ch * SV_CHUNK + (col & (SV_CHUNK - 1))];
+}
+// 16-byte async copy global -> shared (SASS: LDGSTS), L2 only
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ uint32_t swizzle128(uint32_t lin) { return lin ^ (((lin >> 7) & 7u) << 4); }
+
 template <int A>
 __global__ void __launch_bounds__(SV_THREADS, 5)
 survivor_rows_kernel(const int64_t* __restrict__ table, int nv, const float4* __restrict__ boxes,
@@ -49,11 +63,10 @@ survivor_rows_kernel(const int64_t* __restrict__ table, int nv, const float4* __
                      const float* __restrict__ terms_o, int n_out, float* __restrict__ row_bias,
                      const float* __restrict__ conv_w, const float* __restrict__ conv_b,
                      const float* __restrict__ pred_w, const float* __restrict__ pred_b,
-                     const float* __restrict__ sizes, float stride, int32_t* __restrict__ spans, int64_t ld_spans,
-                     int cap) {
+                     const float* __restrict__ sizes, float stride, int32_t* __restrict__ spans, int64_t ld_spans) {
     constexpr int A2 = 2 * A;
     extern __shared__ __align__(128) uint8_t smem[];
-    float* const tile = reinterpret_cast<float*>(smem);                           // [8][cap], frame - a4
+    float* const tile = reinterpret_cast<float*>(smem);       // [block][8][512]: column = frame - a4 (see tile_at)
     __shared__ __align__(16) float4 w_conv[SV_CIN * SV_CIN];                      // [co][ci] -> (w0, w1, w2, -)
     __shared__ __align__(16) float w_pred[SV_CIN * A2];                           // [co][j]
     __shared__ float b_conv[SV_CIN], b_pred[A2];
@@ -66,7 +79,7 @@ survivor_rows_kernel(const int64_t* __restrict__ table, int nv, const float4* __
     const int64_t* row = table + (int64_t)v * TSPN_VT_COLS;
     const int t_len = (int)row[TSPN_VT_T];
     __nv_bfloat16* outb = rel + r * ld_rel;
-    float* bias_row = row_bias + r * n_out;
+    float* bias_row = row_bias ? row_bias + r * n_out : nullptr;
     int32_t* sp_row = spans ? spans + r * ld_spans : nullptr;
     const int n_loc = spans ? span_locations(t_len, stride) : 0;
 
@@ -86,7 +99,8 @@ survivor_rows_kernel(const int64_t* __restrict__ table, int nv, const float4* __
 
     if (gp < 0) {                                  // padding row (K_eff < K): zero block, zero bias, zero regressions
         for (int64_t q = tid; q < ld_rel; q += SV_THREADS) outb[q] = __float2bfloat16(0.0f);
-        for (int c = tid; c < n_out; c += SV_THREADS) bias_row[c] = 0.0f;
+        if (row_bias)
+            for (int c = tid; c < n_out; c += SV_THREADS) bias_row[c] = 0.0f;
         for (int l = tid; l < n_loc; l += SV_THREADS) {
             float zero[A2];
             int32_t res[A2];
@@ -112,32 +126,50 @@ survivor_rows_kernel(const int64_t* __restrict__ table, int nv, const float4* __
     const int a4 = a & ~3;
 
     // ---- the eight channels over the window, 512 frames per pass, into the shared-memory tile ----
-    // The boxes come straight from global memory (L2 / L1: a thread's five boxes per tracklet are 80 contiguous
-    // bytes, its neighbour's start 64 bytes later) - no staging, no barrier between the passes.
+    // All boxes of the window (both tracklets, + one halo frame) are fetched up front with 16-byte async copies:
+    // one memory round trip per row instead of one per pass - under the all-pairs kernel's store stream an L2 hit
+    // takes microseconds, and the 4 warps of this CTA cannot hide four of them in a row.  Block p of shared
+    // memory holds the 512 subject and 512 object boxes of pass p (128-byte swizzle, as the all-pairs kernel's
+    // TMA stages: conflict-free LDS.128 at a 64-byte thread stride); once every thread has its boxes in
+    // registers, the block is overwritten in place by the pass's [8][512] tile - same 16 KB.
     const float4* bs = boxes + row[TSPN_VT_BOX_OFF] + (int64_t)s * tb;
     const float4* bo = boxes + row[TSPN_VT_BOX_OFF] + (int64_t)o * tb;
     const int last = (int)tb - 1;                               // frames >= b are masked: any in-row box will do
     const int n_pass = len ? (b - a4 + SV_CHUNK - 1) / SV_CHUNK : 0;
+    const uint32_t base = smem_u32(smem);
+    if (n_pass) {
+        for (int idx = tid; idx < n_pass * SV_CHUNK + 1; idx += SV_THREADS) {
+            const int f = min(a4 + idx, last);
+            const uint32_t lin = base + (uint32_t)(idx >> 9) * SV_BLOCK_BYTES + (uint32_t)(idx & (SV_CHUNK - 1)) * 16u;
+            cp_async16(swizzle128(lin), bs + f);
+            cp_async16(swizzle128(lin + SV_HALF), bo + f);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+    }
     for (int pass = 0; pass < n_pass; ++pass) {
-        const int f0 = a4 + pass * SV_CHUNK;
         const int j0 = tid * GEO_FPT;
         float out[TSPN_GEO_CHANNELS][GEO_FPT];
         float fi, fs, fo;
-        geo_step<false>([bs, f0, last](int j) { return __ldg(bs + min(f0 + j, last)); },
-                        [bo, f0, last](int j) { return __ldg(bo + min(f0 + j, last)); }, j0, f0 + j0, a, b, out, fi, fs,
-                        fo);
-        const int col = pass * SV_CHUNK + j0;                   // frame - a4
-        if (col < cap) {
+        // box j of this pass: j = 512 is the first frame of the next block (or the halo slot)
+        auto load_s = [base, pass](int j) {
+            return ld_box(base + (uint32_t)(pass + (j >> 9)) * SV_BLOCK_BYTES, j & (SV_CHUNK - 1));
+        };
+        auto load_o = [base, pass](int j) {
+            return ld_box(base + (uint32_t)(pass + (j >> 9)) * SV_BLOCK_BYTES + SV_HALF, j & (SV_CHUNK - 1));
+        };
+        geo_step<false>(load_s, load_o, j0, a4 + pass * SV_CHUNK + j0, a, b, out, fi, fs, fo);
+        __syncthreads();                                        // every thread of the pass holds its boxes
 #pragma unroll
-            for (int ch = 0; ch < TSPN_GEO_CHANNELS; ++ch)
-                *reinterpret_cast<float4*>(tile + (size_t)ch * cap + col) =
-                    make_float4(out[ch][0], out[ch][1], out[ch][2], out[ch][3]);
-        }
+        for (int ch = 0; ch < TSPN_GEO_CHANNELS; ++ch)
+            *reinterpret_cast<float4*>(&tile_at(tile, ch, pass * SV_CHUNK + j0)) =
+                make_float4(out[ch][0], out[ch][1], out[ch][2], out[ch][3]);
     }
     __syncthreads();
 
     // ---- relative block: bin i of the six pooled channels (0,1 | 2,3 | 5,6) shares its frame range ----
-    const float* w0 = tile + (a - a4);
+    const int w0 = a - a4;                                      // column of the window's first frame
     for (int i = tid; i < TSPN_REL_BINS; i += SV_THREADS) {
         float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (len > 0) {
@@ -146,12 +178,13 @@ survivor_rows_kernel(const int64_t* __restrict__ table, int nv, const float4* __
             const uint32_t width = en - st;
             const float inv = width < SV_INV_TAB ? s_inv[width] : 1.0f / (float)width;
             for (uint32_t f = st; f < en; ++f) {                                  // ascending frames
-                acc[0] += w0[f];
-                acc[1] += w0[(size_t)cap + f];
-                acc[2] += w0[2 * (size_t)cap + f];
-                acc[3] += w0[3 * (size_t)cap + f];
-                acc[4] += w0[5 * (size_t)cap + f];
-                acc[5] += w0[6 * (size_t)cap + f];
+                const float* x = &tile_at(tile, 0, w0 + (int)f);
+                acc[0] += x[0];
+                acc[1] += x[SV_CHUNK];
+                acc[2] += x[2 * SV_CHUNK];
+                acc[3] += x[3 * SV_CHUNK];
+                acc[4] += x[5 * SV_CHUNK];
+                acc[5] += x[6 * SV_CHUNK];
             }
 #pragma unroll
             for (int c = 0; c < 6; ++c) acc[c] *= inv;
@@ -160,7 +193,7 @@ survivor_rows_kernel(const int64_t* __restrict__ table, int nv, const float4* __
         for (int c = 0; c < 6; ++c) outb[c * TSPN_REL_BINS + i] = __float2bfloat16(acc[c]);
     }
     for (int64_t q = TSPN_REL_DIM + tid; q < ld_rel; q += SV_THREADS) outb[q] = __float2bfloat16(0.0f);
-    {
+    if (row_bias) {
         const float* a_s = terms_s + ts * n_out;                 // A_s of the subject tracklet
         const float* a_o = terms_o + to * n_out;                 // A_o of the object tracklet
         for (int c = tid; c < n_out; c += SV_THREADS) bias_row[c] = __ldg(a_s + c) + __ldg(a_o + c);
@@ -177,7 +210,7 @@ survivor_rows_kernel(const int64_t* __restrict__ table, int nv, const float4* __
             const int f = t - 1 + d;
             const bool in = f >= a && f < b;                     // every channel is 0 outside the window
 #pragma unroll
-            for (int ci = 0; ci < SV_CIN; ++ci) xv[ci][d] = in ? tile[(size_t)ci * cap + (f - a4)] : 0.0f;
+            for (int ci = 0; ci < SV_CIN; ++ci) xv[ci][d] = in ? tile_at(tile, ci, f - a4) : 0.0f;
         }
         int32_t res[A2];
         span_location<SV_CIN, A>(xv, has_m, has_p, w_conv, w_pred, b_conv, b_pred, sizes, ac, t_len, res);
@@ -186,15 +219,60 @@ survivor_rows_kernel(const int64_t* __restrict__ table, int nv, const float4* __
     }
 }
 
+// bias rows of the decomposed predicate head on their own: one warp per scored row
+__global__ void __launch_bounds__(128)
+gather_pair_terms_kernel(const int64_t* __restrict__ table, int nv, const int64_t* __restrict__ rows, int64_t n_rows,
+                         const float* __restrict__ terms_s, const float* __restrict__ terms_o, int n_out,
+                         float* __restrict__ row_bias) {
+    const int64_t r = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (r >= n_rows) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t gp = rows ? rows[r] : r;
+    float* dst = row_bias + r * n_out;
+    if (gp < 0) {
+        for (int c = lane; c < n_out; c += 32) dst[c] = 0.0f;
+        return;
+    }
+    const int v = find_video(table, nv, TSPN_VT_PAIR_OFF, gp);
+    const int64_t* row = table + (int64_t)v * TSPN_VT_COLS;
+    const int n = (int)row[TSPN_VT_N];
+    const int p = (int)(gp - row[TSPN_VT_PAIR_OFF]);
+    const int s = p / (n - 1);
+    const int k = p - s * (n - 1);
+    const int o = k + (k >= s ? 1 : 0);
+    const float* a_s = terms_s + (row[TSPN_VT_TRK_OFF] + s) * n_out;
+    const float* a_o = terms_o + (row[TSPN_VT_TRK_OFF] + o) * n_out;
+    for (int c = lane; c < n_out; c += 32) dst[c] = __ldg(a_s + c) + __ldg(a_o + c);
+}
+
 }  // namespace tspn
 
 using namespace tspn;
 
 extern "C" {
 
+// shared memory of one CTA: the blocks that cover a window of up to max_frames + 3 frames + the halo slot
+static int64_t sv_smem_bytes(int max_frames) {
+    return (((int64_t)max_frames + 3 + SV_CHUNK - 1) / SV_CHUNK) * SV_BLOCK_BYTES + SV_HALO_BYTES;
+}
+
 int tspn_survivor_rows_supported(int max_frames, int n_anchors) {
-    const int64_t cap = ((int64_t)max_frames + 3) / 4 * 4 + 4;
-    return n_anchors == 4 && max_frames > 0 && (int64_t)TSPN_GEO_CHANNELS * cap * 4 <= SV_SMEM_MAX;
+    return n_anchors == 4 && max_frames > 0 && sv_smem_bytes(max_frames) <= SV_SMEM_MAX;
+}
+
+int tspn_gather_pair_terms(const int64_t* d_table, int num_videos, const int64_t* d_rows, int64_t n_rows,
+                           const float* d_terms_subject, const float* d_terms_object, int n_outputs, float* d_row_bias,
+                           void* stream) {
+    TSPN_ARCH_OK();
+    TSPN_REQUIRE(num_videos >= 0 && n_rows >= 0 && n_outputs > 0, TSPN_EBADARG, "tspn_gather_pair_terms: bad size");
+    if (n_rows == 0) return TSPN_OK;
+    TSPN_REQUIRE(d_table && d_terms_subject && d_terms_object && d_row_bias, TSPN_EBADARG,
+                 "tspn_gather_pair_terms: null pointer");
+    prefer_max_smem(gather_pair_terms_kernel);
+    gather_pair_terms_kernel<<<(unsigned)((n_rows + 3) / 4), 128, 0, (cudaStream_t)stream>>>(
+        d_table, num_videos, d_rows, n_rows, d_terms_subject, d_terms_object, n_outputs, d_row_bias);
+    TSPN_CUDA_OK(cudaGetLastError());
+    return TSPN_OK;
 }
 
 int tspn_survivor_rows(const int64_t* d_table, int num_videos, int max_frames, const float* d_boxes,
@@ -207,8 +285,9 @@ int tspn_survivor_rows(const int64_t* d_table, int num_videos, int max_frames, c
     TSPN_REQUIRE(num_videos >= 0 && n_rows >= 0 && n_outputs > 0 && max_frames > 0 && rows_per_video > 0, TSPN_EBADARG,
                  "tspn_survivor_rows: bad size");
     if (n_rows == 0) return TSPN_OK;
-    TSPN_REQUIRE(d_table && d_boxes && d_span && d_rows && d_rel_bf16 && d_terms_subject && d_terms_object && d_row_bias,
-                 TSPN_EBADARG, "tspn_survivor_rows: null pointer");
+    TSPN_REQUIRE(d_table && d_boxes && d_span && d_rows && d_rel_bf16, TSPN_EBADARG, "tspn_survivor_rows: null pointer");
+    TSPN_REQUIRE(!d_row_bias || (d_terms_subject && d_terms_object), TSPN_EBADARG,
+                 "tspn_survivor_rows: bias rows need the per-tracklet terms");
     TSPN_REQUIRE(ld_rel >= TSPN_REL_DIM, TSPN_ESHAPE, "tspn_survivor_rows: ld_rel=%lld must be >= 3000", (long long)ld_rel);
     TSPN_REQUIRE(aligned16(d_boxes), TSPN_EALIGN, "tspn_survivor_rows: boxes must be 16-byte aligned");
     TSPN_REQUIRE(n_rows < (1ll << 31), TSPN_ESHAPE, "tspn_survivor_rows: too many rows");
@@ -221,14 +300,13 @@ int tspn_survivor_rows(const int64_t* d_table, int num_videos, int max_frames, c
         TSPN_REQUIRE(ld_spans >= (int64_t)span_locations(max_frames, stride) * 2 * n_anchors, TSPN_ESHAPE,
                      "tspn_survivor_rows: ld_spans=%lld < locations(max_frames) * 2A", (long long)ld_spans);
     }
-    const int cap = (max_frames + 3) / 4 * 4 + 4;
-    const int smem = TSPN_GEO_CHANNELS * cap * 4;
+    const int smem = (int)sv_smem_bytes(max_frames);
     TSPN_CUDA_OK(cudaFuncSetAttribute(survivor_rows_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     prefer_max_smem(survivor_rows_kernel<4>);
     survivor_rows_kernel<4><<<(unsigned)n_rows, SV_THREADS, smem, (cudaStream_t)stream>>>(
         d_table, num_videos, reinterpret_cast<const float4*>(d_boxes), d_span, d_rows, rows_per_video,
         reinterpret_cast<__nv_bfloat16*>(d_rel_bf16), ld_rel, d_terms_subject, d_terms_object, n_outputs, d_row_bias,
-        d_conv_w, d_conv_b, d_pred_w, d_pred_b, d_sizes, stride, d_spans, ld_spans, cap);
+        d_conv_w, d_conv_b, d_pred_w, d_pred_b, d_sizes, stride, d_spans, ld_spans);
     TSPN_CUDA_OK(cudaGetLastError());
     return TSPN_OK;
 }

@@ -365,20 +365,39 @@ def survivor_rows_supported(batch: DeviceBatch, n_anchors: int) -> bool:
     return bool(load().tspn_survivor_rows_supported(int(batch.totals[_lib.TOT_MAX_T]), int(n_anchors)))
 
 
-def survivor_rows(batch: DeviceBatch, rows: torch.Tensor, terms_subject: torch.Tensor, terms_object: torch.Tensor,
-                  span_weights=None, sizes: Optional[torch.Tensor] = None, stride: float = 0.0):
+def gather_pair_terms(batch: DeviceBatch, rows: Optional[torch.Tensor], terms_subject: torch.Tensor,
+                      terms_object: torch.Tensor) -> torch.Tensor:
+    """Bias rows of the decomposed predicate head: ``A_s[subject] + A_o[object]`` per scored row (zeros for
+    padding rows)."""
+    n_rows = int(rows.numel()) if rows is not None else batch.total_pairs
+    r = int(terms_subject.shape[1])
+    out = torch.empty((n_rows, r), dtype=torch.float32, device=batch.device)
+    check(load().tspn_gather_pair_terms(ptr(batch.table), batch.num_videos,
+                                        ptr(_cuda(rows, torch.int64)) if rows is not None else None, n_rows,
+                                        ptr(_cuda(terms_subject, torch.float32)), ptr(_cuda(terms_object, torch.float32)),
+                                        r, ptr(out), stream_ptr()), "tspn_gather_pair_terms")
+    _count(1)
+    return out
+
+
+def survivor_rows(batch: DeviceBatch, rows: torch.Tensor, terms_subject: Optional[torch.Tensor] = None,
+                  terms_object: Optional[torch.Tensor] = None, span_weights=None, sizes: Optional[torch.Tensor] = None,
+                  stride: float = 0.0):
     """``tspn_survivor_rows``: for the surviving rows ``rows [V, K]`` (global pair rows, -1 = padding) the pooled
     relative block (bf16 ``[V*K, 3000]``), the bias rows ``A_s[s] + A_o[o]`` and - with ``span_weights =
     (conv_w, conv_b, pred_w, pred_b)`` - the decoded span proposals ``[V*K, L_max * A, 2]`` int32, all
-    recomputed from the boxes (bit-identical to ``assemble_relative`` / ``span_proposals`` on stored rows)."""
+    recomputed from the boxes (bit-identical to ``assemble_relative`` / ``span_proposals`` on stored rows).
+    Without the terms no bias rows are produced (``gather_pair_terms`` builds them separately)."""
     dev = batch.device
     rows = _cuda(rows, torch.int64)
     k = int(rows.shape[1])
     n_rows = int(rows.numel())
-    r = int(terms_subject.shape[1])
     max_t = int(batch.totals[_lib.TOT_MAX_T])
     rel = torch.empty((n_rows, _lib.REL_DIM), dtype=torch.bfloat16, device=dev)
-    row_bias = torch.empty((n_rows, r), dtype=torch.float32, device=dev)
+    row_bias, r = None, 1
+    if terms_subject is not None:
+        r = int(terms_subject.shape[1])
+        row_bias = torch.empty((n_rows, r), dtype=torch.float32, device=dev)
     spans, a_n, ld_spans = None, 4, 0
     cw = cb = pw = pb = None
     if span_weights is not None:
@@ -388,7 +407,8 @@ def survivor_rows(batch: DeviceBatch, rows: torch.Tensor, terms_subject: torch.T
         spans = torch.empty((n_rows, ld_spans // 2, 2), dtype=torch.int32, device=dev)
     check(load().tspn_survivor_rows(
         ptr(batch.table), batch.num_videos, max_t, ptr(batch.boxes), ptr(batch.span), ptr(rows), n_rows, k,
-        ptr(rel), rel.stride(0), ptr(_cuda(terms_subject, torch.float32)), ptr(_cuda(terms_object, torch.float32)), r,
+        ptr(rel), rel.stride(0), ptr(_cuda(terms_subject, torch.float32)) if terms_subject is not None else None,
+        ptr(_cuda(terms_object, torch.float32)) if terms_object is not None else None, r,
         ptr(row_bias), ptr(cw), ptr(cb), ptr(pw), ptr(pb), a_n, ptr(_cuda(sizes, torch.float32)) if sizes is not None
         else None, float(stride), ptr(spans), ld_spans, stream_ptr()), "tspn_survivor_rows")
     _count(1)

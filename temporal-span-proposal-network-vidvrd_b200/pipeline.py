@@ -172,9 +172,11 @@ class PairStage:
     # kernel of `geo`; `tail` (feature rows, heads, records) joins both.  Eager `forward` forks and joins
     # with stream events; `capture` freezes each segment into a CUDA graph (GraphedStage).
     def _side_stream(self, device, which: int = 0) -> torch.cuda.Stream:
+        """Stream 0: relationness -> top-K -> surviving-pair heads (the long chain: high priority); stream 1: the
+        per-tracklet predicate terms and the per-pair finalize (default priority)."""
         key = "%s/%d" % (device, which)
         if self._side.get(key) is None:
-            self._side[key] = torch.cuda.Stream(device, priority=side_priority())
+            self._side[key] = torch.cuda.Stream(device, priority=side_priority() if which == 0 else 0)
         return self._side[key]
 
     def _survivor_path(self, batch: DeviceBatch, features, heads: bool) -> bool:
@@ -219,19 +221,24 @@ class PairStage:
         if c.use_ppn:
             scores = ops.relationness(batch, self.ppn_weights())
             idx, val, row = ops.topk_pairs(batch, scores, c.topk, exclude_diagonal=c.sparsify)
-        cur.wait_stream(second)
-        if mn is not None and not torch.cuda.is_current_stream_capturing():
-            for u in (mn if isinstance(mn, tuple) else (mn,)):
-                u.record_stream(cur)                  # allocated on the second side stream, consumed on this one
-        if self._survivor_path(batch, features, heads):
-            # nothing below reads an output of the pair kernel: relative block, bias rows and span proposals
-            # come from the boxes, the record windows from the spans - the whole chain stays on this branch
+        survivors = self._survivor_path(batch, features, heads)
+        if survivors:
+            # nothing below reads an output of the pair kernel: relative block and span proposals come from the
+            # boxes, the record windows from the spans - the whole chain stays on this branch.  The recomputation
+            # (the longest kernel of the branch) needs only the top-K rows, so it starts before the per-tracklet
+            # terms of the other chain are done; this stream has the higher priority for the SM slots the pair
+            # kernel leaves free.
             sw = None
             if c.use_dpn:
                 sw = (self.w[DPN_PREFIX + "conv.weight"], self.w[DPN_PREFIX + "conv.bias"],
                       self.w[DPN_PREFIX + "duration_pred.weight"], self.w[DPN_PREFIX + "duration_pred.bias"])
-            rel16, row_bias, sp = ops.survivor_rows(batch, row, mn[0], mn[1], span_weights=sw, sizes=self.sizes_dev,
-                                                    stride=c.anchor_stride)
+            rel16, _, sp = ops.survivor_rows(batch, row, span_weights=sw, sizes=self.sizes_dev, stride=c.anchor_stride)
+        cur.wait_stream(second)
+        if mn is not None and not torch.cuda.is_current_stream_capturing():
+            for u in (mn if isinstance(mn, tuple) else (mn,)):
+                u.record_stream(cur)                  # allocated on the second side stream, consumed on this one
+        if survivors:
+            row_bias = ops.gather_pair_terms(batch, row.reshape(-1), mn[0], mn[1])
             logits = ops.predicate_head_affine(rel16, self.packed_rel, c.n_predicates, bias=self.w[CLS_PREFIX + "bias"],
                                                row_bias=row_bias, background=True)
             records = counts = None
@@ -281,19 +288,25 @@ class PairStage:
             events[1].record(stream)
         return geom
 
-    def _seg_tail(self, batch: DeviceBatch, features, heads, side, geom) -> StageResult:
+    def _seg_post(self, batch: DeviceBatch, geom) -> None:
+        """vIoU / tIoU on the second side stream, ordered after the pair kernel only (call right after _seg_geo,
+        before the caller's stream joins the heads' chain); _seg_tail(post_done=True) joins it."""
+        main = torch.cuda.current_stream(batch.device)
+        second = self._side_stream(batch.device, 1)
+        second.wait_stream(main)
+        with torch.cuda.stream(second):
+            ops.pair_geometry_phase(batch, geom, _lib.GEO_PHASE_POST, clipped=self.cfg.viou_clipped)
+
+    def _seg_tail(self, batch: DeviceBatch, features, heads, side, geom, post_done: bool = False) -> StageResult:
         c = self.cfg
         scores, idx, val, row, mn, early = side
         k_eff = self.k_effective(batch)
         sparsify = c.sparsify and c.use_ppn
         if early is not None:
             # survivor path: the heads already ran on the side branch; only the per-pair finalize is left
-            main = torch.cuda.current_stream(batch.device)
-            side_stream = self._side_stream(batch.device)
-            side_stream.wait_stream(main)
-            with torch.cuda.stream(side_stream):
-                ops.pair_geometry_phase(batch, geom, _lib.GEO_PHASE_POST, clipped=c.viou_clipped)
-            main.wait_stream(side_stream)
+            if not post_done:
+                self._seg_post(batch, geom)
+            torch.cuda.current_stream(batch.device).wait_stream(self._side_stream(batch.device, 1))
             spans = span_bufs = None
             sp = early["spans"]
             if sp is not None:
@@ -375,8 +388,11 @@ class PairStage:
             events = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             timers["geo"] = events
         self._seg_geo(batch, geom, events=events, with_pre=not pre_aside)
+        early = side[5] is not None
+        if early:
+            self._seg_post(batch, geom)               # under the heads' chain, not behind it
         main.wait_stream(side_stream)                 # join
-        return self._seg_tail(batch, features, heads, side, geom)
+        return self._seg_tail(batch, features, heads, side, geom, post_done=early)
 
     def capture(self, batch: DeviceBatch, features: Optional[torch.Tensor] = None,
                 heads: bool = True, single: bool = True) -> "GraphedStage":
@@ -475,8 +491,11 @@ class GraphedStage:
                         stage._seg_pre(batch, geom)
                     side = stage._seg_side(batch, features, heads)
                 stage._seg_geo(batch, geom, events=self.ev_geo, with_pre=not pre_aside)
+                early = side[5] is not None
+                if early:
+                    stage._seg_post(batch, geom)
                 cap.wait_stream(fork)
-                self.result = stage._seg_tail(batch, features, heads, side, geom)
+                self.result = stage._seg_tail(batch, features, heads, side, geom, post_done=early)
         else:
             self.g_side, self.g_geo, self.g_tail = (torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(),
                                                     torch.cuda.CUDAGraph())

@@ -202,6 +202,11 @@ def test_survivor_rows_bit_identical_to_stored_rows(shapes, k):
     torch.cuda.synchronize()
     assert torch.equal(rel.view(torch.int16), want_rel.view(torch.int16))
     assert torch.equal(bias, want_bias)
+    rel2, none, spans2 = ops.survivor_rows(batch, rows_d, span_weights=sw, sizes=sizes, stride=stride)   # no terms
+    bias2 = ops.gather_pair_terms(batch, rows_d.reshape(-1), terms[0], terms[1])
+    torch.cuda.synchronize()
+    assert none is None and torch.equal(rel2.view(torch.int16), rel.view(torch.int16)) and torch.equal(spans2, spans)
+    assert torch.equal(bias2, want_bias)
     a_n = 4
     l_max = ops.span_num_locations(max(batch.t), stride)
     assert spans.shape == (rows.size, l_max * a_n, 2)
