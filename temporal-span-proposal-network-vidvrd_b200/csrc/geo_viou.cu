@@ -496,6 +496,10 @@ __global__ void __launch_bounds__(256) enumerate_pairs_kernel(const int64_t* __r
     pairs[2 * p + 1] = k + (k >= s ? 1 : 0);
 }
 
+__global__ void reset_queue_kernel(unsigned int* __restrict__ queue) {
+    if (threadIdx.x == 0) *queue = 0u;
+}
+
 template <int THREADS, bool DENSE>
 static int launch_pair_geo(const int64_t* d_table, int num_videos, int64_t total_items, int64_t total_boxes,
                            const float* d_boxes, const int32_t* d_span, float* d_geo, unsigned long long* fx,
@@ -513,7 +517,8 @@ static int launch_pair_geo(const int64_t* d_table, int num_videos, int64_t total
     if (d_queue) {                      // persistent: one CTA per SM slot, items from the queue
         const int64_t slots = (int64_t)num_sms() * Cfg::MIN_CTAS;
         if (slots < total_items) grid = (unsigned)slots;
-        TSPN_CUDA_OK(cudaMemsetAsync(d_queue, 0, sizeof(unsigned int), st));
+        reset_queue_kernel<<<1, 32, 0, st>>>(d_queue);      // (a kernel, not a memset node: compute-sanitizer's
+                                                            // initcheck does not see memset nodes of a replayed graph)
     }
 #define TSPN_LAUNCH_GEO(W, C)                                                                                  \
     do {                                                                                                       \

@@ -133,9 +133,35 @@ video_top_triplets_kernel(const int64_t* __restrict__ table, int nv, const float
     // triplet; 2 x 200 sequential scans of C values were the bulk of this kernel's latency)
     const bool labels_cached = n <= PP_LABEL_CAP;
     if (labels_cached) {
+        // four lanes per tracklet: 64 tracklets per round of the block, every lane's loads independent (one memory
+        // round trip per round instead of one per tracklet and warp); largest value, ties to the lower index
         const float* cls_v = cls + row[TSPN_VT_TRK_OFF] * n_classes;
-        for (int j = threadIdx.x >> 5; j < n; j += TOPK_THREADS / 32)
-            s_label[j] = warp_argmax_row(cls_v + (int64_t)j * n_classes, n_classes, threadIdx.x & 31);
+        const int sub = threadIdx.x & 3;
+        for (int j0 = 0; j0 < n; j0 += TOPK_THREADS / 4) {
+            const int j = j0 + (threadIdx.x >> 2);
+            float best = __uint_as_float(0xff800000u);
+            int bi = 0x7fffffff;
+            if (j < n) {
+                const float* x = cls_v + (int64_t)j * n_classes;
+                for (int i = sub; i < n_classes; i += 4) {
+                    const float q = __ldg(x + i);
+                    if (q > best) {           // ascending i within a lane: the first maximum wins
+                        best = q;
+                        bi = i;
+                    }
+                }
+            }
+#pragma unroll
+            for (int off = 1; off < 4; off <<= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                if (ob > best || (ob == best && oi < bi)) {
+                    best = ob;
+                    bi = oi;
+                }
+            }
+            if (j < n && sub == 0) s_label[j] = bi == 0x7fffffff ? 0 : bi;   // all -inf / NaN rows: index 0
+        }
     }                                       // block_topk synchronises before the labels are read
     const int64_t pair_off = row[TSPN_VT_PAIR_OFF];
     const int64_t r0 = row_video_off ? row_video_off[v] : pair_off;

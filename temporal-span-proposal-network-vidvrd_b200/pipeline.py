@@ -205,7 +205,25 @@ class PairStage:
         # on two streams and join before anything that needs both.
         cur = torch.cuda.current_stream(batch.device)
         second = self._side_stream(batch.device, 1)
-        second.wait_stream(cur)
+        second.wait_stream(cur)                       # fork
+        if c.use_ppn:
+            scores = ops.relationness(batch, self.ppn_weights())
+            idx, val, row = ops.topk_pairs(batch, scores, c.topk, exclude_diagonal=c.sparsify)
+        survivors = self._survivor_path(batch, features, heads)
+        rel16 = sp = row_bias = None
+        if survivors:
+            # nothing below reads an output of the pair kernel: relative block and span proposals come from the
+            # boxes, the record windows from the spans - the whole chain stays on this branch.  The recomputation
+            # (the longest kernel of the branch) needs only the top-K rows, so it starts before the per-tracklet
+            # terms of the other chain are done; this stream has the higher priority for the SM slots the pair
+            # kernel leaves free.
+            topk_done = torch.cuda.Event()
+            topk_done.record(cur)
+            sw = None
+            if c.use_dpn:
+                sw = (self.w[DPN_PREFIX + "conv.weight"], self.w[DPN_PREFIX + "conv.bias"],
+                      self.w[DPN_PREFIX + "duration_pred.weight"], self.w[DPN_PREFIX + "duration_pred.bias"])
+            rel16, _, sp = ops.survivor_rows(batch, row, span_weights=sw, sizes=self.sizes_dev, stride=c.anchor_stride)
         with torch.cuda.stream(second):
             if features is None:
                 if self._decomposed(features):
@@ -218,27 +236,17 @@ class PairStage:
                                                     background=True))
                 else:
                     mn = ops.normalize_motion(batch.motion)
-        if c.use_ppn:
-            scores = ops.relationness(batch, self.ppn_weights())
-            idx, val, row = ops.topk_pairs(batch, scores, c.topk, exclude_diagonal=c.sparsify)
-        survivors = self._survivor_path(batch, features, heads)
+            if survivors:
+                second.wait_event(topk_done)          # the bias rows need the terms and the top-K rows only
+                row_bias = ops.gather_pair_terms(batch, row.reshape(-1), mn[0], mn[1])
+        cur.wait_stream(second)                       # join
+        if not torch.cuda.is_current_stream_capturing():
+            for u in (mn if isinstance(mn, tuple) else (mn,)) + (row_bias,):
+                if u is not None:
+                    u.record_stream(cur)              # allocated on the second side stream, consumed on this one
+            if row is not None:
+                row.record_stream(second)
         if survivors:
-            # nothing below reads an output of the pair kernel: relative block and span proposals come from the
-            # boxes, the record windows from the spans - the whole chain stays on this branch.  The recomputation
-            # (the longest kernel of the branch) needs only the top-K rows, so it starts before the per-tracklet
-            # terms of the other chain are done; this stream has the higher priority for the SM slots the pair
-            # kernel leaves free.
-            sw = None
-            if c.use_dpn:
-                sw = (self.w[DPN_PREFIX + "conv.weight"], self.w[DPN_PREFIX + "conv.bias"],
-                      self.w[DPN_PREFIX + "duration_pred.weight"], self.w[DPN_PREFIX + "duration_pred.bias"])
-            rel16, _, sp = ops.survivor_rows(batch, row, span_weights=sw, sizes=self.sizes_dev, stride=c.anchor_stride)
-        cur.wait_stream(second)
-        if mn is not None and not torch.cuda.is_current_stream_capturing():
-            for u in (mn if isinstance(mn, tuple) else (mn,)):
-                u.record_stream(cur)                  # allocated on the second side stream, consumed on this one
-        if survivors:
-            row_bias = ops.gather_pair_terms(batch, row.reshape(-1), mn[0], mn[1])
             logits = ops.predicate_head_affine(rel16, self.packed_rel, c.n_predicates, bias=self.w[CLS_PREFIX + "bias"],
                                                row_bias=row_bias, background=True)
             records = counts = None

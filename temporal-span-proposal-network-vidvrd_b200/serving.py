@@ -53,6 +53,10 @@ class PipelinedStage:
         # of step i+1.  Slots never share buffers, so the only ordering needed is per slot (events below).
         self.compute = [torch.cuda.Stream(self.device) for _ in range(2 if int(depth) > 1 and compute_streams > 1 else 1)]
         self.s_h2d, self.s_d2h = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
+        # The collective has its own stream: only the D2H of the gathered records waits for it.  On a compute stream
+        # it would hold up the next step behind an NCCL kernel that cannot co-reside with the persistent pair
+        # kernel of the step running on the other compute stream.
+        self.s_comm = torch.cuda.Stream(self.device) if group is not None else None
         self.slots: List[_Slot] = [_Slot(stage, template, self.device, graphs, single_graph) for _ in range(self.depth)]
         self._next = 0
         self._gathered: List[Optional[torch.Tensor]] = [None] * self.depth
@@ -74,19 +78,24 @@ class PipelinedStage:
             main.wait_event(slot.d2h_done)               # the slot's previous results have left the device
             res = slot.graphed.replay() if slot.graphed is not None else self.stage.forward(slot.batch)
             outs = res.host_outputs()
-            if self.group is not None:                   # the one collective: top-K triplet records
-                import torch.distributed as dist
-                world = dist.get_world_size(self.group)
-                if self._gathered[i] is None:
-                    self._gathered[i] = torch.empty((world,) + tuple(res.records.shape), dtype=res.records.dtype,
-                                                    device=self.device)
-                dist.all_gather_into_tensor(self._gathered[i], res.records, group=self.group)
-                outs["records_all_ranks"] = self._gathered[i]
             slot.kernels_done.record(main)
+        work = None
+        if self.group is not None:                       # the one collective: top-K triplet records
+            import torch.distributed as dist
+            world = dist.get_world_size(self.group)
+            if self._gathered[i] is None:
+                self._gathered[i] = torch.empty((world,) + tuple(res.records.shape), dtype=res.records.dtype,
+                                                device=self.device)
+            with torch.cuda.stream(self.s_comm):
+                self.s_comm.wait_event(slot.kernels_done)
+                work = dist.all_gather_into_tensor(self._gathered[i], res.records, group=self.group, async_op=True)
+            outs["records_all_ranks"] = self._gathered[i]
         if slot.host_out is None:
             slot.host_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in outs.items()}
         with torch.cuda.stream(self.s_d2h):
             self.s_d2h.wait_event(slot.kernels_done)
+            if work is not None:
+                work.wait()                              # this stream waits for the all-gather, nobody else does
             for k, src in outs.items():
                 if slot.graphed is None:
                     src.record_stream(self.s_d2h)
