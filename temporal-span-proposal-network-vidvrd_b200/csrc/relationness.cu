@@ -64,9 +64,12 @@ ppn_embed_tiled_kernel(const float* __restrict__ cls, int64_t n_trk, int C, int 
                        const float* __restrict__ ob0, const float* __restrict__ ow2,
                        const float* __restrict__ ob2, float* __restrict__ S, float* __restrict__ O) {
     extern __shared__ float sm[];
-    float* w0t = sm;                      // [2][C][H]   w0t[br][i][j] = W0_br[j][i]
-    float* w2t = w0t + 2 * C * H;         // [2][H][C]   w2t[br][j][c] = W2_br[c][j]
-    float* x = w2t + 2 * H * C;           // [G][C]
+    // rows padded by one word: the transposing stores of the staging loop (consecutive threads write a column)
+    // would otherwise all hit one bank (stride H = 64 words) or two (stride C = 80)
+    const int HP = H + 1, CP = C + 1;
+    float* w0t = sm;                      // [2][C][HP]  w0t[br][i][j] = W0_br[j][i]
+    float* w2t = w0t + 2 * C * HP;        // [2][H][CP]  w2t[br][j][c] = W2_br[c][j]
+    float* x = w2t + 2 * H * CP;          // [G][C]
     float* hid = x + EMB_G * C;           // [G][2][H]
     const int tid = threadIdx.x;
     const int64_t trk0 = (int64_t)blockIdx.x * EMB_G;
@@ -75,11 +78,11 @@ ppn_embed_tiled_kernel(const float* __restrict__ cls, int64_t n_trk, int C, int 
         const int br = e / (C * H), rem = e - br * C * H;
         {   // W0_br is [H][C] row-major: element rem = j*C + i
             const int j = rem / C, i = rem - j * C;
-            w0t[br * C * H + i * H + j] = __ldg((br ? ow0 : sw0) + rem);
+            w0t[br * C * HP + i * HP + j] = __ldg((br ? ow0 : sw0) + rem);
         }
         {   // W2_br is [C][H] row-major: element rem = c*H + j
             const int c = rem / H, j = rem - c * H;
-            w2t[br * H * C + j * C + c] = __ldg((br ? ow2 : sw2) + rem);
+            w2t[br * H * CP + j * CP + c] = __ldg((br ? ow2 : sw2) + rem);
         }
     }
     for (int e = tid; e < g_cnt * C; e += EMB_THREADS) x[e] = __ldg(cls + trk0 * C + e);
@@ -87,20 +90,20 @@ ppn_embed_tiled_kernel(const float* __restrict__ cls, int64_t n_trk, int C, int 
     for (int u = tid; u < g_cnt * 2 * H; u += EMB_THREADS) {
         const int g = u / (2 * H), j2 = u - g * 2 * H;
         const int br = j2 / H, j = j2 - br * H;
-        const float* w = w0t + br * C * H + j;
+        const float* w = w0t + br * C * HP + j;
         const float* xg = x + g * C;
         float acc = __ldg((br ? ob0 : sb0) + j);
-        for (int i = 0; i < C; ++i) acc = __fmaf_rn(xg[i], w[i * H], acc);
+        for (int i = 0; i < C; ++i) acc = __fmaf_rn(xg[i], w[i * HP], acc);
         hid[u] = fmaxf(acc, 0.0f);
     }
     __syncthreads();
     for (int u = tid; u < g_cnt * 2 * C; u += EMB_THREADS) {
         const int g = u / (2 * C), c2 = u - g * 2 * C;
         const int br = c2 / C, c = c2 - br * C;
-        const float* w = w2t + br * H * C + c;
+        const float* w = w2t + br * H * CP + c;
         const float* h = hid + (g * 2 + br) * H;
         float acc = __ldg((br ? ob2 : sb2) + c);
-        for (int j = 0; j < H; ++j) acc = __fmaf_rn(h[j], w[j * C], acc);
+        for (int j = 0; j < H; ++j) acc = __fmaf_rn(h[j], w[j * CP], acc);
         (br ? O : S)[(trk0 + g) * C + c] = acc;
     }
 }
@@ -195,7 +198,8 @@ int tspn_relationness(const int64_t* d_table, int num_videos, int64_t total_trac
     float* S = reinterpret_cast<float*>(d_workspace);
     float* O = S + total_tracklets * n_classes;
     if ((int64_t)n_classes * hidden <= 12288) {
-        const size_t smt = (size_t)(4 * n_classes * hidden + EMB_G * n_classes + EMB_G * 2 * hidden) * sizeof(float);
+        const size_t smt = (size_t)(2 * n_classes * (hidden + 1) + 2 * hidden * (n_classes + 1) + EMB_G * n_classes +
+                                    EMB_G * 2 * hidden) * sizeof(float);
         TSPN_CUDA_OK(cudaFuncSetAttribute(ppn_embed_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smt));
         prefer_max_smem(ppn_embed_tiled_kernel);
