@@ -167,10 +167,13 @@ class PairStage:
             return [n * max(n - 1, 0) for n in batch.n]
         return [min(c.topk, n * (n - 1) if c.sparsify else n * n) for n in batch.n]
 
-    # The step is three segments.  `side` (relationness + top-K, motion normalisation) depends only on
-    # the class logits / motion rows, so it runs on a second stream underneath the HBM-bound geometry
-    # kernel of `geo`; `tail` (feature rows, heads, records) joins both.  Eager `forward` forks and joins
-    # with stream events; `capture` freezes each segment into a CUDA graph (GraphedStage).
+    # The step is three segments.  `side` depends only on the tracklet inputs (class logits, motion rows, boxes,
+    # spans), so it runs on side streams underneath the HBM-bound all-pairs kernel of `geo`: relationness + top-K
+    # and the per-tracklet predicate terms always; on the survivor path (tensor precision + sparsify, the bench
+    # path) also the surviving pairs' relative features and span proposals recomputed from the boxes, the predicate
+    # head and the records - then `tail` only finalises vIoU / tIoU and joins.  Otherwise `tail` builds the feature
+    # rows from the stored geometry rows and runs the heads behind `geo`.  Eager `forward` forks and joins with
+    # stream events; `capture` freezes the step into one CUDA graph (GraphedStage).
     def _side_stream(self, device, which: int = 0) -> torch.cuda.Stream:
         """Stream 0: relationness -> top-K -> surviving-pair heads (the long chain: high priority); stream 1: the
         per-tracklet predicate terms and the per-pair finalize (default priority)."""
@@ -459,13 +462,14 @@ class GraphedStage:
     """The step of one fixed-shape batch as ONE CUDA graph (``single=True``, default) or as three
     (side / geo / tail, joined with stream events on the host).
 
-    Launch-bound host work (13 C-ABI calls, their output allocations and tensor-map encodes) is paid
-    once at capture.  In the single graph the side branch (relationness + top-K, motion normalisation)
-    and the span-head branch are forks inside the graph, and the two events that time the geometry kernel
-    are *external* event-record nodes (``torch.cuda.Event(external=True)``): every replay re-records
-    them, so ``timers["geo"]`` must be read (after a synchronize) before the next replay.  All outputs live
-    in the graph's private memory pool and are overwritten by every replay: ``result`` always refers to
-    the latest one.  Refill the inputs with ``batch.copy_from(host)`` (same per-video shapes) between
+    Launch-bound host work (17 C-ABI calls, their output allocations and tensor-map encodes) is paid
+    once at capture.  In the single graph the side branches (stream 0: relationness -> top-K -> surviving-pair
+    rows -> predicate head -> records; stream 1: per-tracklet predicate terms, volumes, vIoU finalize) are forks
+    inside the graph, and the two events that time the all-pairs kernel are *external* event-record nodes
+    (``torch.cuda.Event(external=True)``): every replay re-records them, so ``timers["geo"]`` must be read
+    (after a synchronize) before the next replay.  The geometry outputs are allocated once, before the
+    capture; all other outputs live in the graph's private memory pool; every replay overwrites both:
+    ``result`` always refers to the latest one.  Refill the inputs with ``batch.copy_from(host)`` (same per-video shapes) between
     replays.
     """
 

@@ -6,14 +6,14 @@ launch- and PCIe-latency-bound, so the serving loop works on *batches of videos*
 ``depth`` of them in flight over three streams:
 
     h2d stream    :  H2D(i+1) ......................
-    compute stream:  kernels(i)  (3 CUDA-graph launches, see pipeline.GraphedStage); two compute streams
-                     alternate, so the tail of step i overlaps the geometry kernel of step i+1
+    compute stream:  kernels(i)  (one CUDA-graph launch, see pipeline.GraphedStage); two compute streams
+                     alternate, so the end of step i overlaps the start of step i+1
     d2h stream    :  D2H(i-1) ......................
 
 Every slot owns its device input buffers, its captured graphs (and therefore its output buffers) and
 its pinned host result buffers, so nothing is allocated in steady state.  With ``group`` the per-video
 triplet records are all-gathered across ranks after the kernels of each step (the one collective of
-the path, sharding.py).
+the path, sharding.py) on a stream of their own: only the D2H copy of the gathered records waits for it.
 """
 from __future__ import annotations
 
