@@ -114,6 +114,11 @@ extern "C" {
  * other streams can then only co-reside with the pair kernel's CTAs - they can never take over an SM between
  * two of its CTAs and lock the next one out. */
 #define TSPN_GEO_PERSISTENT 128
+/* With TSPN_GEO_PERSISTENT: leave that many SM slots free ((n) << TSPN_GEO_RESERVE_SHIFT, n <= 255).  Kernels of
+ * concurrent streams run several times slower beside a pair CTA than on an SM of their own; a handful of free SMs
+ * lets a side branch finish under the pair kernel at a small cost to it (bench workload, 148 SMs: 8 free SMs =
+ * +1 % pair-kernel time, -1.7 % step time). */
+#define TSPN_GEO_RESERVE_SHIFT 16
 #define TSPN_TOPK_KEEP_DIAGONAL 0    /* reference behaviour, ppn.py:84-85 (quirk Q1) */
 #define TSPN_TOPK_EXCLUDE_DIAGONAL 1 /* survivors are real pairs (sparsify mode) */
 #define TSPN_PREC_FP32_EXACT 0 /* CUDA cores, fixed k-ascending fma order: bit-reproducible */
@@ -224,6 +229,21 @@ int tspn_relationness(const int64_t* d_table, int num_videos, int64_t total_trac
 int tspn_topk_pairs(const int64_t* d_table, int num_videos, const float* d_scores, int k,
                     int flags, int64_t* d_topk_idx, float* d_topk_score, int64_t* d_topk_row,
                     void* stream);
+
+/* a8 + a9 in two launches instead of three: the embedding kernel, then one CTA per video that computes the
+ * video's N x N scores from the embeddings in shared memory, writes them and selects the top K from the keys it
+ * has just produced.  Same outputs, bit for bit, as tspn_relationness followed by tspn_topk_pairs (k == 0: scores
+ * are NOT produced - use tspn_relationness).  Supported when max_tracklets^2 <= 8192 (max_tracklets =
+ * totals[TSPN_TOT_MAX_N]); otherwise use the two entry points above. */
+int tspn_relationness_topk_supported(int max_tracklets, int n_classes);
+int tspn_relationness_topk(const int64_t* d_table, int num_videos, int64_t total_tracklets, int max_tracklets,
+                           const float* d_cls, int n_classes, int hidden,
+                           const float* d_sub_w0, const float* d_sub_b0,
+                           const float* d_sub_w2, const float* d_sub_b2,
+                           const float* d_obj_w0, const float* d_obj_b0,
+                           const float* d_obj_w2, const float* d_obj_b2,
+                           float* d_scores, int k, int flags, int64_t* d_topk_idx, float* d_topk_score,
+                           int64_t* d_topk_row, void* d_workspace, void* stream);
 
 /* ---- a14: predicate classifier -----------------------------------------------------------
  * RelationPredictor.forward (lib/modeling/model.py:76-88): y = sigmoid(x W^T + b).

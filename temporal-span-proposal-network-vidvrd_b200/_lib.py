@@ -30,6 +30,7 @@ GEO_DENSE_CTAS = 2
 GEO_PHASE_PRE, GEO_PHASE_MAIN, GEO_PHASE_POST = 8, 16, 32
 GEO_SINGLE_CHUNK = 64
 GEO_PERSISTENT = 128
+GEO_RESERVE_SHIFT = 16
 TOPK_KEEP_DIAGONAL, TOPK_EXCLUDE_DIAGONAL = 0, 1
 PREC_FP32_EXACT, PREC_TENSOR = 0, 1
 AFFINE_RAW = 1
@@ -59,6 +60,9 @@ SIGNATURES = {
     "tspn_relationness_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
     "tspn_relationness": (c_int, [P, c_int, c_int64, P, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P]),
     "tspn_topk_pairs": (c_int, [P, c_int, P, c_int, c_int, P, P, P, P]),
+    "tspn_relationness_topk_supported": (c_int, [c_int, c_int]),
+    "tspn_relationness_topk": (c_int, [P, c_int, c_int64, c_int, P, c_int, c_int, P, P, P, P, P, P, P, P, P, c_int, c_int,
+                                       P, P, P, P, P]),
     "tspn_predicate_packed_bytes": (c_int64, [c_int, c_int]),
     "tspn_pack_predicate_weights": (c_int, [P, c_int, c_int, P, P]),
     "tspn_predicate_workspace_bytes": (c_int64, [c_int64, c_int, c_int, c_int]),

@@ -503,7 +503,7 @@ __global__ void reset_queue_kernel(unsigned int* __restrict__ queue) {
 template <int THREADS, bool DENSE>
 static int launch_pair_geo(const int64_t* d_table, int num_videos, int64_t total_items, int64_t total_boxes,
                            const float* d_boxes, const int32_t* d_span, float* d_geo, unsigned long long* fx,
-                           int32_t* d_overlap, unsigned int* d_queue, bool clip, cudaStream_t st) {
+                           int32_t* d_overlap, unsigned int* d_queue, int reserve, bool clip, cudaStream_t st) {
     using Cfg = GeoCfg<THREADS, DENSE>;
     // boxes viewed as a 2-D tensor: rows of 8 boxes (32 floats = 128 B)
     CUtensorMap map;
@@ -515,7 +515,8 @@ static int launch_pair_geo(const int64_t* d_table, int num_videos, int64_t total
     if (rc != TSPN_OK) return rc;
     unsigned grid = (unsigned)total_items;
     if (d_queue) {                      // persistent: one CTA per SM slot, items from the queue
-        const int64_t slots = (int64_t)num_sms() * Cfg::MIN_CTAS;
+        int64_t slots = (int64_t)num_sms() * Cfg::MIN_CTAS - reserve;      // SM slots left to concurrent streams
+        if (slots < 1) slots = 1;
         if (slots < total_items) grid = (unsigned)slots;
         reset_queue_kernel<<<1, 32, 0, st>>>(d_queue);      // (a kernel, not a memset node: compute-sanitizer's
                                                             // initcheck does not see memset nodes of a replayed graph)
@@ -613,11 +614,12 @@ int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_ite
         const bool dense = (flags & TSPN_GEO_DENSE_CTAS) != 0;
         unsigned int* queue = (flags & TSPN_GEO_PERSISTENT) ? reinterpret_cast<unsigned int*>(fx + total_pairs * 3)
                                                             : nullptr;
+        const int reserve = (flags >> TSPN_GEO_RESERVE_SHIFT) & 0xff;
 #define TSPN_GEO_SHAPE(T)                                                                                          \
     (dense ? launch_pair_geo<T, true>(d_table, num_videos, total_items, total_boxes, d_boxes, d_span, d_geo, fx,   \
-                                      d_overlap, queue, clip, st)                                                  \
+                                      d_overlap, queue, reserve, clip, st)                                         \
            : launch_pair_geo<T, false>(d_table, num_videos, total_items, total_boxes, d_boxes, d_span, d_geo, fx,  \
-                                       d_overlap, queue, clip, st))
+                                       d_overlap, queue, reserve, clip, st))
         if (geo_chunk == 512) rc = TSPN_GEO_SHAPE(128);
         else if (geo_chunk == 1024) rc = TSPN_GEO_SHAPE(256);
         else rc = TSPN_GEO_SHAPE(512);

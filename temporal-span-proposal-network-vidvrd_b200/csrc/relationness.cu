@@ -169,6 +169,93 @@ topk_kernel(const int64_t* __restrict__ table, int nv, const float* __restrict__
     }
 }
 
+// ---- scores + top-K of one video in one CTA ------------------------------------------------------------
+// The video's subject and object embeddings are staged in shared memory (rows padded by one word: thread i
+// walks row o = i % n conflict-free, row s = i / n is a broadcast), every score is computed once - the same
+// c-ascending fma chain as pair_scores_kernel - written to the scores tensor and handed to the block top-K as
+// the key it caches.  One launch and one pass over the embeddings instead of two kernels with the scores going
+// through memory in between: this pair sits on the chain that decides when the surviving-pair kernel can start.
+// Needs n * n <= TOPK_CACHE (block_topk then evaluates every candidate exactly once).
+__global__ void __launch_bounds__(TOPK_THREADS, 5)
+scores_topk_kernel(const int64_t* __restrict__ table, int nv, const float* __restrict__ S,
+                   const float* __restrict__ O, int C, float* __restrict__ scores, int K, int exclude_diag,
+                   int64_t* __restrict__ out_idx, float* __restrict__ out_score, int64_t* __restrict__ out_row) {
+    __shared__ TopkSmem sm;
+    extern __shared__ float emb[];      // [2][n][C + 1]
+    const int v = blockIdx.x;
+    const int64_t* row = table + (int64_t)v * TSPN_VT_COLS;
+    const uint32_t n = (uint32_t)row[TSPN_VT_N];
+    const int64_t trk0 = row[TSPN_VT_TRK_OFF];
+    const int64_t total = (int64_t)n * n;
+    const int tid = threadIdx.x;
+    const int CP = C + 1;
+    float* const ss = emb;
+    float* const oo = emb + (size_t)n * CP;
+    for (int e = tid; e < (int)n * C; e += TOPK_THREADS) {
+        const int r = e / C, c = e - r * C;
+        ss[r * CP + c] = S[trk0 * C + e];
+        oo[r * CP + c] = O[trk0 * C + e];
+    }
+    __syncthreads();
+    float* const sc = scores + row[TSPN_VT_SCORE_OFF];
+    const float NEG_INF = __uint_as_float(0xff800000u);
+
+    const int k_eff = block_topk(sm, total, K, [&](int64_t i) -> float {
+        const uint32_t u = (uint32_t)i;
+        const uint32_t s = u / n, o = u - s * n;
+        const float* sr = ss + s * CP;
+        const float* orow = oo + o * CP;
+        float z = 0.0f;
+        for (int c = 0; c < C; ++c) z = __fmaf_rn(sr[c], orow[c], z);
+        const float val = sigmoid_det(z);
+        sc[i] = val;
+        return (exclude_diag && s == o) ? NEG_INF : val;            // the diagonal is scored but not a candidate
+    });
+
+    int64_t* oi = out_idx + (int64_t)v * K;
+    float* os = out_score + (int64_t)v * K;
+    int64_t* orow = out_row ? out_row + (int64_t)v * K : nullptr;
+    for (int i = tid; i < K; i += TOPK_THREADS) {
+        if (i < k_eff) {
+            const uint32_t flat = (uint32_t)(sm.sel[i] & 0xffffffffu);
+            oi[i] = (int64_t)flat;
+            os[i] = sc[flat];                   // written by this CTA before block_topk's barriers
+            if (orow) {
+                const int s = (int)(flat / n), o = (int)(flat % n);
+                orow[i] = (s == o) ? -1 : row[TSPN_VT_PAIR_OFF] + (int64_t)s * (n - 1) + o - (o > s ? 1 : 0);
+            }
+        } else {
+            oi[i] = -1;
+            os[i] = 0.0f;
+            if (orow) orow[i] = -1;
+        }
+    }
+}
+
+static int launch_embeddings(int64_t total_tracklets, const float* d_cls, int n_classes, int hidden,
+                             const float* d_sub_w0, const float* d_sub_b0, const float* d_sub_w2, const float* d_sub_b2,
+                             const float* d_obj_w0, const float* d_obj_b0, const float* d_obj_w2, const float* d_obj_b2,
+                             float* S, float* O, cudaStream_t st) {
+    if ((int64_t)n_classes * hidden <= 12288) {
+        const size_t smt = (size_t)(2 * n_classes * (hidden + 1) + 2 * hidden * (n_classes + 1) + EMB_G * n_classes +
+                                    EMB_G * 2 * hidden) * sizeof(float);
+        TSPN_CUDA_OK(cudaFuncSetAttribute(ppn_embed_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smt));
+        prefer_max_smem(ppn_embed_tiled_kernel);
+        ppn_embed_tiled_kernel<<<(unsigned)((total_tracklets + EMB_G - 1) / EMB_G), EMB_THREADS, smt, st>>>(
+            d_cls, total_tracklets, n_classes, hidden, d_sub_w0, d_sub_b0, d_sub_w2, d_sub_b2, d_obj_w0, d_obj_b0,
+            d_obj_w2, d_obj_b2, S, O);
+    } else {
+        const size_t sm1 = (size_t)(n_classes + 2 * hidden) * sizeof(float);
+        prefer_max_smem(ppn_embed_kernel);
+        ppn_embed_kernel<<<(unsigned)total_tracklets, 128, sm1, st>>>(d_cls, n_classes, hidden, d_sub_w0, d_sub_b0,
+                                                                      d_sub_w2, d_sub_b2, d_obj_w0, d_obj_b0,
+                                                                      d_obj_w2, d_obj_b2, S, O);
+    }
+    TSPN_CUDA_OK(cudaGetLastError());
+    return TSPN_OK;
+}
+
 }  // namespace tspn
 
 using namespace tspn;
@@ -197,26 +284,57 @@ int tspn_relationness(const int64_t* d_table, int num_videos, int64_t total_trac
     cudaStream_t st = (cudaStream_t)stream;
     float* S = reinterpret_cast<float*>(d_workspace);
     float* O = S + total_tracklets * n_classes;
-    if ((int64_t)n_classes * hidden <= 12288) {
-        const size_t smt = (size_t)(2 * n_classes * (hidden + 1) + 2 * hidden * (n_classes + 1) + EMB_G * n_classes +
-                                    EMB_G * 2 * hidden) * sizeof(float);
-        TSPN_CUDA_OK(cudaFuncSetAttribute(ppn_embed_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)smt));
-        prefer_max_smem(ppn_embed_tiled_kernel);
-        ppn_embed_tiled_kernel<<<(unsigned)((total_tracklets + EMB_G - 1) / EMB_G), EMB_THREADS, smt, st>>>(
-            d_cls, total_tracklets, n_classes, hidden, d_sub_w0, d_sub_b0, d_sub_w2, d_sub_b2, d_obj_w0, d_obj_b0,
-            d_obj_w2, d_obj_b2, S, O);
-    } else {
-        const size_t sm1 = (size_t)(n_classes + 2 * hidden) * sizeof(float);
-        prefer_max_smem(ppn_embed_kernel);
-        ppn_embed_kernel<<<(unsigned)total_tracklets, 128, sm1, st>>>(d_cls, n_classes, hidden, d_sub_w0, d_sub_b0,
-                                                                      d_sub_w2, d_sub_b2, d_obj_w0, d_obj_b0,
-                                                                      d_obj_w2, d_obj_b2, S, O);
+    {
+        const int rc = launch_embeddings(total_tracklets, d_cls, n_classes, hidden, d_sub_w0, d_sub_b0, d_sub_w2, d_sub_b2,
+                                         d_obj_w0, d_obj_b0, d_obj_w2, d_obj_b2, S, O, st);
+        if (rc != TSPN_OK) return rc;
     }
-    TSPN_CUDA_OK(cudaGetLastError());
     prefer_max_smem(pair_scores_kernel);
     pair_scores_kernel<<<(unsigned)total_tracklets, 128, (size_t)n_classes * sizeof(float), st>>>(
         d_table, num_videos, S, O, n_classes, d_scores);
+    TSPN_CUDA_OK(cudaGetLastError());
+    return TSPN_OK;
+}
+
+int tspn_relationness_topk_supported(int max_tracklets, int n_classes) {
+    return max_tracklets > 0 && (int64_t)max_tracklets * max_tracklets <= TOPK_CACHE &&
+           2 * (int64_t)max_tracklets * (n_classes + 1) * 4 <= 160 * 1024;
+}
+
+int tspn_relationness_topk(const int64_t* d_table, int num_videos, int64_t total_tracklets, int max_tracklets,
+                           const float* d_cls, int n_classes, int hidden, const float* d_sub_w0,
+                           const float* d_sub_b0, const float* d_sub_w2, const float* d_sub_b2, const float* d_obj_w0,
+                           const float* d_obj_b0, const float* d_obj_w2, const float* d_obj_b2, float* d_scores, int k,
+                           int flags, int64_t* d_topk_idx, float* d_topk_score, int64_t* d_topk_row, void* d_workspace,
+                           void* stream) {
+    TSPN_ARCH_OK();
+    TSPN_REQUIRE(num_videos >= 0 && total_tracklets >= 0 && n_classes > 0 && hidden > 0 && k >= 0, TSPN_EBADARG,
+                 "tspn_relationness_topk: bad size");
+    TSPN_REQUIRE(k <= TOPK_MAX_K, TSPN_ESHAPE, "tspn_relationness_topk: K=%d exceeds the supported maximum %d", k,
+                 TOPK_MAX_K);
+    if (num_videos == 0) return TSPN_OK;
+    TSPN_REQUIRE(tspn_relationness_topk_supported(max_tracklets, n_classes), TSPN_ESHAPE,
+                 "tspn_relationness_topk: max_tracklets=%d not supported (use tspn_relationness + tspn_topk_pairs)",
+                 max_tracklets);
+    TSPN_REQUIRE(d_table && d_sub_w0 && d_sub_b0 && d_sub_w2 && d_sub_b2 && d_obj_w0 && d_obj_b0 && d_obj_w2 && d_obj_b2 &&
+                     d_workspace && d_topk_idx && d_topk_score && (total_tracklets == 0 || (d_cls && d_scores)),
+                 TSPN_EBADARG, "tspn_relationness_topk: null pointer");
+    TSPN_REQUIRE(n_classes <= 4096 && hidden <= 4096, TSPN_ESHAPE, "tspn_relationness_topk: C/H too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* S = reinterpret_cast<float*>(d_workspace);
+    float* O = S + total_tracklets * n_classes;
+    if (total_tracklets > 0) {
+        const int rc = launch_embeddings(total_tracklets, d_cls, n_classes, hidden, d_sub_w0, d_sub_b0, d_sub_w2, d_sub_b2,
+                                         d_obj_w0, d_obj_b0, d_obj_w2, d_obj_b2, S, O, st);
+        if (rc != TSPN_OK) return rc;
+    }
+    if (k == 0) return TSPN_OK;
+    const size_t smem = 2 * (size_t)max_tracklets * (n_classes + 1) * sizeof(float);
+    TSPN_CUDA_OK(cudaFuncSetAttribute(scores_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    prefer_max_smem(scores_topk_kernel);
+    scores_topk_kernel<<<(unsigned)num_videos, TOPK_THREADS, smem, st>>>(
+        d_table, num_videos, S, O, n_classes, d_scores, k, (flags & TSPN_TOPK_EXCLUDE_DIAGONAL) ? 1 : 0, d_topk_idx,
+        d_topk_score, d_topk_row);
     TSPN_CUDA_OK(cudaGetLastError());
     return TSPN_OK;
 }

@@ -83,11 +83,13 @@ def pair_geometry_outputs(batch: DeviceBatch, write_geo: bool = True) -> Dict[st
 
 
 def pair_geometry_phase(batch: DeviceBatch, out: Dict[str, torch.Tensor], phase: int, clipped: bool = False,
-                        dense_ctas: Optional[bool] = None, persistent: Optional[bool] = None) -> None:
+                        dense_ctas: Optional[bool] = None, persistent: Optional[bool] = None,
+                        reserve_sms: int = 0) -> None:
     """One phase of ``tspn_pair_geo_viou`` on the current stream: ``_lib.GEO_PHASE_PRE`` (per-tracklet volumes,
     and zeroing of the per-pair sums unless the batch is single-chunk), ``GEO_PHASE_MAIN`` (the pair kernel:
     geometry rows, fixed-point sums, overlap windows), ``GEO_PHASE_POST`` (vIoU / tIoU), or 0 for all three.
-    On a single-chunk batch PRE may run on another stream concurrently with MAIN; POST needs both."""
+    On a single-chunk batch PRE may run on another stream concurrently with MAIN; POST needs both.
+    ``reserve_sms``: SM slots the persistent pair kernel leaves to concurrent streams (TSPN_GEO_RESERVE_SHIFT)."""
     if dense_ctas is None:
         dense_ctas = os.environ.get("TSPN_GEO_DENSE", "0") == "1"
     tot = batch.totals
@@ -97,7 +99,7 @@ def pair_geometry_phase(batch: DeviceBatch, out: Dict[str, torch.Tensor], phase:
     if persistent is None:
         persistent = os.environ.get("TSPN_GEO_PERSISTENT", "1") == "1"
     if persistent and not dense_ctas:
-        flags |= _lib.GEO_PERSISTENT
+        flags |= _lib.GEO_PERSISTENT | (max(0, min(int(reserve_sms), 255)) << _lib.GEO_RESERVE_SHIFT)
     check(load().tspn_pair_geo_viou(
         ptr(batch.table), batch.num_videos, int(tot[_lib.TOT_ITEMS]), int(tot[_lib.TOT_GEO_CHUNK]),
         batch.total_tracklets, batch.total_pairs,
@@ -248,6 +250,32 @@ def relationness(batch: DeviceBatch, weights, cls: Optional[torch.Tensor] = None
                                    *[ptr(t) for t in w], ptr(scores), ptr(ws), stream_ptr()), "tspn_relationness")
     _count(2)
     return scores
+
+
+def relationness_topk_supported(batch: DeviceBatch) -> bool:
+    return bool(load().tspn_relationness_topk_supported(int(batch.totals[_lib.TOT_MAX_N]), int(batch.cls.shape[1])))
+
+
+def relationness_topk(batch: DeviceBatch, weights, k: int, exclude_diagonal: bool = False):
+    """``relationness`` + ``topk_pairs`` in two launches (``tspn_relationness_topk``): the scores of a video are
+    computed, written and ranked by one CTA.  Returns ``(scores, idx, val, row)``, bit-identical to the two calls."""
+    cls = _cuda(batch.cls, torch.float32)
+    w = [_cuda(t, torch.float32) for t in weights]
+    c, h = cls.shape[1], w[0].shape[0]
+    dev, v = cls.device, batch.num_videos
+    scores = torch.empty(batch.total(_lib.TOT_SCORES), dtype=torch.float32, device=dev)
+    ws = torch.empty(load().tspn_relationness_workspace_bytes(batch.total_tracklets, c, h) // 4,
+                     dtype=torch.float32, device=dev)
+    idx = torch.empty((v, k), dtype=torch.int64, device=dev)
+    val = torch.empty((v, k), dtype=torch.float32, device=dev)
+    row = torch.empty((v, k), dtype=torch.int64, device=dev)
+    check(load().tspn_relationness_topk(
+        ptr(batch.table), v, batch.total_tracklets, int(batch.totals[_lib.TOT_MAX_N]), ptr(cls), c, h,
+        *[ptr(t) for t in w], ptr(scores), k,
+        _lib.TOPK_EXCLUDE_DIAGONAL if exclude_diagonal else _lib.TOPK_KEEP_DIAGONAL, ptr(idx), ptr(val), ptr(row),
+        ptr(ws), stream_ptr()), "tspn_relationness_topk")
+    _count(2)
+    return scores, idx, val, row
 
 
 def topk_pairs(batch: DeviceBatch, scores: torch.Tensor, k: int, exclude_diagonal: bool = False):

@@ -40,6 +40,8 @@ class StageConfig:
     mirror_q4: bool = False
     keep_span_reg: bool = False        # also return DPNHead's raw [K, 2A, T] regressions (two-kernel path)
     materialize_features: bool = False  # tensor precision: also build the [rows, F] rows (see PairStage._decomposed)
+    geo_reserve_sms: int = 8           # survivor path: SMs the persistent pair kernel leaves to the side branches
+                                       # (measured on the bench workload: 0 -> 0.748 ms, 8 -> 0.735 ms, 16 -> 0.751 ms)
 
     @classmethod
     def from_cfg(cls, cfg) -> "StageConfig":
@@ -179,7 +181,8 @@ class PairStage:
         per-tracklet predicate terms and the per-pair finalize (default priority)."""
         key = "%s/%d" % (device, which)
         if self._side.get(key) is None:
-            self._side[key] = torch.cuda.Stream(device, priority=side_priority() if which == 0 else 0)
+            prio = side_priority() if which == 0 else int(os.environ.get("TSPN_SIDE1_PRIORITY", "0"))
+            self._side[key] = torch.cuda.Stream(device, priority=prio)
         return self._side[key]
 
     def _survivor_path(self, batch: DeviceBatch, features, heads: bool) -> bool:
@@ -210,8 +213,13 @@ class PairStage:
         second = self._side_stream(batch.device, 1)
         second.wait_stream(cur)                       # fork
         if c.use_ppn:
-            scores = ops.relationness(batch, self.ppn_weights())
-            idx, val, row = ops.topk_pairs(batch, scores, c.topk, exclude_diagonal=c.sparsify)
+            if c.topk > 0 and batch.cls is not None and ops.relationness_topk_supported(batch) \
+                    and os.environ.get("TSPN_FUSED_TOPK", "1") == "1":
+                scores, idx, val, row = ops.relationness_topk(batch, self.ppn_weights(), c.topk,
+                                                              exclude_diagonal=c.sparsify)
+            else:
+                scores = ops.relationness(batch, self.ppn_weights())
+                idx, val, row = ops.topk_pairs(batch, scores, c.topk, exclude_diagonal=c.sparsify)
         survivors = self._survivor_path(batch, features, heads)
         rel16 = sp = row_bias = None
         if survivors:
@@ -288,13 +296,14 @@ class PairStage:
     def _seg_pre(self, batch: DeviceBatch, geom) -> None:
         ops.pair_geometry_phase(batch, geom, _lib.GEO_PHASE_PRE, clipped=self.cfg.viou_clipped)
 
-    def _seg_geo(self, batch: DeviceBatch, geom, events=None, with_pre: bool = False):
+    def _seg_geo(self, batch: DeviceBatch, geom, events=None, with_pre: bool = False, reserve_sms: int = 0):
         stream = torch.cuda.current_stream(batch.device)
         if with_pre:
             self._seg_pre(batch, geom)
         if events is not None:
             events[0].record(stream)
-        ops.pair_geometry_phase(batch, geom, _lib.GEO_PHASE_MAIN, clipped=self.cfg.viou_clipped)
+        ops.pair_geometry_phase(batch, geom, _lib.GEO_PHASE_MAIN, clipped=self.cfg.viou_clipped,
+                                reserve_sms=reserve_sms)
         if events is not None:
             events[1].record(stream)
         return geom
@@ -398,8 +407,9 @@ class PairStage:
         if timers is not None:      # CUDA events around the dominant kernel, on the launching stream
             events = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             timers["geo"] = events
-        self._seg_geo(batch, geom, events=events, with_pre=not pre_aside)
         early = side[5] is not None
+        self._seg_geo(batch, geom, events=events, with_pre=not pre_aside,
+                      reserve_sms=self.cfg.geo_reserve_sms if early else 0)
         if early:
             self._seg_post(batch, geom)               # under the heads' chain, not behind it
         main.wait_stream(side_stream)                 # join
@@ -502,8 +512,9 @@ class GraphedStage:
                     if pre_aside:
                         stage._seg_pre(batch, geom)
                     side = stage._seg_side(batch, features, heads)
-                stage._seg_geo(batch, geom, events=self.ev_geo, with_pre=not pre_aside)
                 early = side[5] is not None
+                stage._seg_geo(batch, geom, events=self.ev_geo, with_pre=not pre_aside,
+                               reserve_sms=stage.cfg.geo_reserve_sms if early else 0)
                 if early:
                     stage._seg_post(batch, geom)
                 cap.wait_stream(fork)
@@ -518,7 +529,8 @@ class GraphedStage:
                     stage._seg_pre(batch, geom)
                 side = stage._seg_side(batch, features, heads)
             with torch.cuda.graph(self.g_geo, stream=self._cap_stream):
-                stage._seg_geo(batch, geom, events=self.ev_geo, with_pre=not pre_aside)
+                stage._seg_geo(batch, geom, events=self.ev_geo, with_pre=not pre_aside,
+                               reserve_sms=stage.cfg.geo_reserve_sms if side[5] is not None else 0)
             with torch.cuda.graph(self.g_tail, stream=self._cap_stream):
                 self.result = stage._seg_tail(batch, features, heads, side, geom)
         self.kernels_per_replay = ops.launch_count() - n0

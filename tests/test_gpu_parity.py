@@ -440,3 +440,40 @@ def test_c_abi_error_codes_on_the_device():
     again = ops.pair_geometry(batch, write_geo=True)
     torch.cuda.synchronize()
     assert torch.equal(again["geo"], out["geo"])
+
+
+@pytest.mark.parametrize("exclude", [False, True])
+@pytest.mark.parametrize("k", [256, 7, 1024])
+def test_fused_scores_topk_equals_the_two_calls(exclude, k):
+    """tspn_relationness_topk (one CTA per video computes, writes and ranks the video's scores) against
+    tspn_relationness followed by tspn_topk_pairs: scores, indices, top scores and pair rows bit for bit, on a
+    ragged batch with empty, one-tracklet and 90-tracklet (8100 candidates: the cache limit) videos."""
+    c = 35
+    shapes = [(20, 30, 0), (0, 5, 1), (1, 9, 2), (2, 4, 3), (64, 16, 4), (90, 8, 5), (33, 12, 6)]
+    vids = [synth.make_video(n, t, c, seed=s) for n, t, s in shapes]
+    sd = synth.make_weights(c, 50, synth.feature_dim(c), dpn_in=8, seed=3)
+    w = [torch.from_numpy(sd["relpn.pair_proposal_network.ppn_head." + key]).cuda() for key in ops.PPN_KEYS]
+    batch = _batch(vids)
+    assert ops.relationness_topk_supported(batch)
+    scores = ops.relationness(batch, w)
+    idx, val, row = ops.topk_pairs(batch, scores, k, exclude_diagonal=exclude)
+    f_scores, f_idx, f_val, f_row = ops.relationness_topk(batch, w, k, exclude_diagonal=exclude)
+    torch.cuda.synchronize()
+    assert torch.equal(scores, f_scores)
+    assert torch.equal(idx, f_idx) and torch.equal(val, f_val) and torch.equal(row, f_row)
+    big = _batch([synth.make_video(91, 4, c, seed=7)])
+    assert not ops.relationness_topk_supported(big)
+
+
+def test_pair_geometry_with_reserved_sms_is_bit_identical():
+    """The persistent pair kernel with SM slots left free for concurrent streams (TSPN_GEO_RESERVE_SHIFT) - fewer
+    CTAs pulling from the same work-item queue - against the full grid."""
+    vids = [synth.make_video(n, t, 35, seed=s) for n, t, s in [(40, 700, 1), (9, 2100, 2), (3, 64, 3)]]
+    batch = _batch(vids)
+    want = ops.pair_geometry(batch, write_geo=True)
+    for reserve in (8, 140, 255):
+        out = ops.pair_geometry_outputs(batch, write_geo=True)
+        ops.pair_geometry_phase(batch, out, 0, reserve_sms=reserve)
+        torch.cuda.synchronize()
+        for key in ("geo", "viou", "tiou", "overlap"):
+            assert torch.equal(want[key], out[key]), (reserve, key)
