@@ -180,3 +180,54 @@ def test_ragged_config_batches(name, videos, check):
         sc = exact.relationness(v.cls, sd)
         sc[np.arange(n), np.arange(n)] = -np.inf
         np.testing.assert_array_equal(res.pair_proposals(int(i)).cpu().numpy(), exact.topk(sc, k)[:min(k, n * (n - 1))])
+
+
+@pytest.mark.parametrize("name,videos", [("vidor_single", 3), ("vidor_val", 24)])
+def test_bench_path_full_size(name, videos, monkeypatch):
+    """The bench path (tensor precision, sparsify: heads of the survivors recomputed from the boxes on the side
+    branches, persistent pair kernel with reserved SMs, fused scores + top-K) at BASELINE.json sizes - configs[2]
+    (N=64, T=2000) and a ragged slice of configs[3] - against the stored-geometry-row path of the same stage: span
+    proposals, proposals and reductions bit for bit, predicate scores to the split-K summation order; and against
+    the float64 oracle on sampled rows (1e-2 absolute, BASELINE.json)."""
+    from oracle import features as ofeat, heads as oheads
+    spec = synth.CONFIGS[name]
+    c, r, k = spec["classes"], spec["predicates"], spec["topk"]
+    vids = synth.make_config(name, seed=5, videos=videos)
+    sd = synth.make_weights(c, r, synth.feature_dim(c), dpn_in=8, seed=0)
+    cfg = StageConfig(n_classes=c, n_predicates=r, topk=k, sparsify=True, precision="tensor",
+                      anchor_sizes=(16.0, 64.0, 256.0, 1024.0), anchor_stride=16.0)
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("TSPN_SURVIVOR_PATH", mode)
+        monkeypatch.setenv("TSPN_FUSED_TOPK", mode)
+        stage = PairStage(cfg)
+        stage.load_weights(sd, "cuda")
+        batch = HostBatch.from_videos(vids).to_device("cuda")
+        g = stage.capture(batch)
+        g.replay()
+        res[mode] = g.replay()
+        torch.cuda.synchronize()
+    a, b = res["0"], res["1"]
+    assert torch.equal(a.topk_idx, b.topk_idx) and torch.equal(a.topk_score, b.topk_score)
+    assert torch.equal(a.scores, b.scores)
+    for key in ("viou", "tiou", "overlap"):
+        assert torch.equal(a.geom[key], b.geom[key]), key
+    assert (a.rel_logits - b.rel_logits).abs().max().item() <= 5e-6
+    assert torch.equal(a.record_counts, b.record_counts)
+    for i in range(len(vids)):
+        assert torch.equal(a.spans[i], b.spans[i]), i
+    rng = np.random.Generator(np.random.PCG64(2))
+    for i in rng.choice(len(vids), size=min(3, len(vids)), replace=False):
+        v = vids[int(i)]
+        n = v.n_tracklets
+        if n < 2:
+            continue
+        order = b.pair_proposals(int(i)).cpu().numpy()
+        pick = np.sort(rng.choice(len(order), size=min(8, len(order)), replace=False))
+        s, o = order[pick] // n, order[pick] % n
+        geo, _, _, ov = ogeo.pair_geometry(v.boxes, v.span, s, o)
+        feats = ofeat.assemble_features(v.cls, v.motion, ofeat.relative_block(geo, ov), np.stack([s, o], axis=1))
+        want = oheads.relation_predictor_f64(feats, sd)
+        np.testing.assert_allclose(b.logits(int(i)).cpu().numpy()[pick], want, rtol=0, atol=1e-2)
+    del res, a, b
+    torch.cuda.empty_cache()
