@@ -55,7 +55,10 @@ ppn_embed_kernel(const float* __restrict__ cls, int C, int H, const float* __res
 // stages them once, transposed so that consecutive threads read consecutive words (the per-thread
 // row walk of the kernel above is 32 cache lines per warp load), and embeds EMB_G tracklets.
 // Every output is the same k-ascending fma chain -> same bits as ppn_embed_kernel.
-constexpr int EMB_G = 8;
+#ifndef TSPN_EMB_G
+#define TSPN_EMB_G 8
+#endif
+constexpr int EMB_G = TSPN_EMB_G;
 constexpr int EMB_THREADS = 256;
 __global__ void __launch_bounds__(EMB_THREADS)
 ppn_embed_tiled_kernel(const float* __restrict__ cls, int64_t n_trk, int C, int H, const float* __restrict__ sw0,
