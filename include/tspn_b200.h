@@ -152,7 +152,9 @@ int tspn_enumerate_pairs(const int64_t* d_table, int num_videos, int64_t total_p
  * ordered pairs of each video, viou (lib/evaluation/common.py:65-106) and _traj_iou
  * (lib/modeling/association.py:35-48, flag TSPN_VIOU_CLIPPED); adds the per-frame channels.
  * d_geo may be NULL (reductions only).  d_workspace: tspn_pair_geo_workspace_bytes() bytes
- * (per-tracklet volumes + per-pair fixed-point volume sums), 16-byte aligned. */
+ * (per-tracklet volumes + per-pair fixed-point volume sums + the persistent kernel's work-item queue),
+ * 16-byte aligned.  Outputs by phase (flags below): MAIN writes d_geo and d_overlap, POST writes d_viou and
+ * d_tiou from the sums MAIN left in the workspace and the volumes of PRE. */
 int64_t tspn_pair_geo_workspace_bytes(int64_t total_tracklets, int64_t total_pairs);
 int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_items, int geo_chunk,
                        int64_t total_tracklets, int64_t total_pairs, int64_t total_boxes,
