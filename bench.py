@@ -1,17 +1,24 @@
 #!/usr/bin/env python
 """bench.py — pair-stage throughput (BASELINE.json metric: tracklet pairs scored / s).
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --steps K --warmup W    # CPU reference arm (oracle port)
+    python bench.py --gpus N --steps K --warmup W [--workload NAME]      # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W [--workload NAME]   # CPU reference arm
 
 A *step* is one pass of the hot path (all-pairs geometry + vIoU || relationness + top-K -> relative
-features, predicate and span heads of the K survivors -> triplet records) over one batch of synthetic
-VidOR-shaped videos
-(N=64 tracklets, T=2000 frames, 80 classes, 50 predicates: BASELINE.json configs[2]).
-`value` counts P = N(N-1) ordered pairs per video with the inputs resident in HBM; `e2e` is the same
-metric through the host-facing call with pinned host buffers, H2D and D2H inside the timed region.
-Under torchrun each rank processes its own shard of videos (weak scaling, no data-path collective)
-and the per-video top-K triplet records are all-gathered once at the end of the step.
+features, predicate and span heads of the K survivors, span NMS -> triplet records) over the workload's
+synthetic videos.  Workloads = BASELINE.json configs:
+
+    vidvrd_single  configs[0]  N=20,  T=300,   35 classes, 132 predicates (64 such videos per GPU per step)
+    vidvrd_test    configs[1]  200 ragged videos N<=40, T<=1200                       (sharded per video)
+    vidor_single   configs[2]  N=64,  T=2000,  80 classes, 50 predicates (16 videos per GPU per step)  [default]
+    vidor_val      configs[3]  835 ragged videos N<=64, T<=2000, LPT-sharded per video over the ranks,
+                               NCCL all-gather of the top-K triplet records inside the timed region
+    stress         configs[4]  N=256, T=4096, K=1024 (1 video per GPU per step)
+
+Ragged videos are packed into batches per chunk class of the pair kernel; every batch of a class replays the
+ONE CUDA graph captured for that class's capacity (tspn_b200.batch / serving).  `value` counts P = N(N-1)
+ordered pairs per video with the inputs resident in HBM; `e2e` is the same metric through the host-facing
+call with pinned host buffers, H2D and D2H inside the timed region.
 """
 from __future__ import annotations
 
@@ -30,8 +37,18 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-WORKLOAD = "vidor_single"          # N=64, T=2000, C=80, R=50, K=256
 FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md fallback
+
+# name -> (synth.CONFIGS key, BASELINE.json configs index, scaling, default videos per GPU (weak), anchors)
+VIDVRD_ANCHORS = ((15.0, 30.0, 45.0, 60.0), 7.5)          # anchor_generator.py:118-120
+VIDOR_ANCHORS = ((16.0, 64.0, 256.0, 1024.0), 16.0)
+WORKLOADS = {
+    "vidvrd_single": ("vidvrd_single", 0, "weak", 64, VIDVRD_ANCHORS),
+    "vidvrd_test": ("vidvrd_test", 1, "strong", None, VIDVRD_ANCHORS),
+    "vidor_single": ("vidor_single", 2, "weak", 16, VIDOR_ANCHORS),
+    "vidor_val": ("vidor_val", 3, "strong", None, VIDOR_ANCHORS),
+    "stress": ("stress", 4, "weak", 1, VIDOR_ANCHORS),
+}
 
 
 def parse_args():
@@ -40,33 +57,58 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--videos", type=int, default=16, help="videos per GPU per step")
+    ap.add_argument("--workload", default="vidor_single", choices=sorted(WORKLOADS))
+    ap.add_argument("--videos", type=int, default=None,
+                    help="videos per GPU per step (weak workloads) / total videos (sharded workloads)")
     ap.add_argument("--precision", default="tensor", choices=["tensor", "fp32"])
     ap.add_argument("--no-sparsify", action="store_true", help="heads on all P pairs (reference quirk Q3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="launch every kernel from the host instead of CUDA graphs")
     ap.add_argument("--depth", type=int, default=3, help="batches in flight in the end-to-end serving loop")
-    ap.add_argument("--fp32-transport", action="store_true",
-                    help="ship boxes / motion histograms as fp32 instead of the lossless compact u16 / u8 form")
+    ap.add_argument("--span-proposals", type=int, default=64,
+                    help="RELPN.DPN.NUM_DURATION_PROPOSALS: spans kept per pair by the temporal NMS (0 = all decoded)")
+    ap.add_argument("--geo-budget-gb", type=float, default=4.0, help="geometry output per batch of ragged videos")
     ap.add_argument("--three-graphs", action="store_true",
                     help="replay the step as three CUDA graphs joined on the host instead of one graph")
     ap.add_argument("--compute-streams", type=int, default=2, choices=[1, 2],
                     help="compute streams of the serving loop (2: the tail of step i overlaps the geometry of i+1)")
+    ap.add_argument("--no-affinity", action="store_true", help="do not bind the rank to its GPU's CPU cores")
     return ap.parse_args()
 
 
-def measured_traffic(videos):
+def workload_config(args, world: int) -> dict:
+    """The `config` object both arms print (same workload, same keys)."""
+    from tspn_b200 import synth
+    key, idx, scaling, per_gpu, (sizes, stride) = WORKLOADS[args.workload]
+    spec = synth.CONFIGS[key]
+    if scaling == "weak":
+        n_vid = args.videos or per_gpu
+        what = "%d video(s) of N=%d T=%d per GPU per step" % (n_vid, spec["n"][1], spec["t"][1])
+    else:
+        n_vid = args.videos or spec["videos"]
+        what = "%d ragged videos N in [%d, %d], T in [%d, %d], LPT-sharded per video over the GPUs" % (
+            n_vid, spec["n"][0], spec["n"][1], spec["t"][0], spec["t"][1])
+    return {"workload": "%s = BASELINE.json configs[%d]: %s; C=%d R=%d K=%d" % (
+                args.workload, idx, what, spec["classes"], spec["predicates"], spec["topk"]),
+            "name": args.workload, "videos": n_vid, "classes": spec["classes"], "predicates": spec["predicates"],
+            "topk": spec["topk"], "sparsify": not args.no_sparsify, "span_proposals": args.span_proposals,
+            "anchor_sizes": list(sizes), "anchor_stride": stride}
+
+
+def measured_traffic(workload, videos):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this
-    workload (profiles/r1_geo_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum); None when the
-    capture does not describe the requested batch."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_geo_traffic.json")) as f:
-            t = json.load(f)
-        if int(t["videos_per_launch"]) != int(videos):
-            return None
-        return float(t["dram_bytes_read"]) + float(t["dram_bytes_write"])
-    except Exception:  # noqa: BLE001
-        return None
+    workload (profiles/*_geo_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum); None when no
+    capture describes the requested batch."""
+    for name in ("r2_geo_traffic.json", "r1_geo_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                t = json.load(f)
+            if t.get("workload", "vidor_single") != workload or int(t["videos_per_launch"]) != int(videos):
+                continue
+            return float(t["dram_bytes_read"]) + float(t["dram_bytes_write"])
+        except Exception:  # noqa: BLE001
+            continue
+    return None
 
 
 def measured_peak():
@@ -159,92 +201,144 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU reference arm (oracle port of the reference's CPU path) — the only place oracle/ is executed
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_step(video, sd, topk, sizes, stride, sample_pairs=256):
-    """One video through the reference's CPU path; returns (seconds for the whole video, detail).
+CPU_PAIR_FRAME_BUDGET = 8_500_000        # pair-frames of geometry per step (one VidOR-shaped video is 8.06 M)
 
-    Geometry / feature rows are computed for a bounded sample of pairs and scaled to P; everything
-    else runs at full size.  The vIoU + per-frame geometry is the float64 oracle port ("oracle, not
-    reference": the reference has no code for the per-frame channels); relationness, sort, classifier
-    and span head are the reference's own torch CPU ops (oracle.heads.*_ref)."""
+
+def cpu_reference_video(video, sd, topk, sizes, stride, n_keep, pool, cores, pair_sample=None):
+    """One video through the CPU path at FULL size (every ordered pair, every frame, no extrapolation) unless
+    ``pair_sample`` bounds the geometry to that many pairs (stress: 65 280 pairs x 4096 frames), in which case the
+    two geometry stages are scaled by P / sample and the caller says so.  Returns (seconds, per-stage detail).
+
+    vIoU is the reference's own algorithm - `cubic_iou` (trajectory.py:127-141, numpy, one thread) for the
+    same-span matrix and the per-pair pure-Python `viou` (evaluation/common.py:65-106) for every ordered pair,
+    mapped over all host cores; relationness, sort, classifier and span head are the reference's torch CPU ops
+    (oracle.heads.*_ref, all torch threads).  The per-frame geometry channels, the pooled relative block, span
+    decode and span NMS have no reference code: the numpy oracle is timed ("oracle, not reference")."""
+    from concurrent.futures import ThreadPoolExecutor
     from oracle import features as ofeat, geometry as ogeo, heads as oheads
     n, p = video.n_tracklets, video.n_pairs
     pr = ogeo.enumerate_pairs(n)
-    rng = np.random.Generator(np.random.PCG64(0))
-    sel = np.sort(rng.choice(p, size=min(sample_pairs, p), replace=False))
     det = {}
-    # numpy releases the GIL: the sampled pairs are split over all host cores
-    from concurrent.futures import ThreadPoolExecutor
-    cores = os.cpu_count() or 1
-    chunks = [c for c in np.array_split(sel, cores) if len(c)]
+    sel = np.arange(p)
+    scale = 1.0
+    if pair_sample is not None and pair_sample < p:
+        sel = np.sort(np.random.Generator(np.random.PCG64(0)).choice(p, size=pair_sample, replace=False))
+        scale = p / float(pair_sample)
     t0 = time.perf_counter()
+    ogeo.cubic_iou_ref(video.boxes, video.boxes)
+    det["cubic_iou_matrix"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    chunks = [c for c in np.array_split(sel, 4 * cores) if len(c)]
+    list(pool.map(ogeo.viou_pairs_ref, [(video.boxes, video.span, pr[c]) for c in chunks]))
+    det["viou_all_pairs"] = (time.perf_counter() - t0) * scale
+    # numpy releases the GIL: the pairs are split over all host cores
+    t0 = time.perf_counter()
+    gchunks = [c for c in np.array_split(sel, max(cores, len(sel) // 64)) if len(c)]
     with ThreadPoolExecutor(max_workers=cores) as ex:
-        parts = list(ex.map(lambda c: ogeo.pair_geometry(video.boxes, video.span, pr[c, 0], pr[c, 1]), chunks))
-    det["geometry_viou"] = (time.perf_counter() - t0) * p / len(sel)
+        parts = list(ex.map(lambda c: tuple(x.astype(np.float32) if x.dtype == np.float64 else x for x in
+                                            ogeo.pair_geometry(video.boxes, video.span, pr[c, 0], pr[c, 1])), gchunks))
+    det["geometry_channels_oracle"] = (time.perf_counter() - t0) * scale
     geo, viou, tiou, ov = (np.concatenate([q[j] for q in parts], axis=0) for j in range(4))
     t0 = time.perf_counter()
     scores = oheads.ppn_head_ref(video.cls, video.cls, sd)
-    order = torch.sort(scores.view(-1), descending=True)[1][:topk]
+    sc = scores.clone()
+    sc.fill_diagonal_(-1.0)                                 # sparsify: survivors are real pairs
+    order = torch.sort(sc.view(-1), descending=True)[1][:min(topk, p)].numpy()
     det["relationness_topk"] = time.perf_counter() - t0
-    k = int(order.shape[0])
-    ksel = sel[:min(k, len(sel))]
+    s_i, o_i = order // n, order % n
+    rows = s_i * (n - 1) + o_i - (o_i > s_i)
+    pos = np.searchsorted(sel, rows)
+    pos = np.where((pos < len(sel)) & (sel[np.minimum(pos, len(sel) - 1)] == rows), pos, pos % len(sel))
     t0 = time.perf_counter()
-    rel = ofeat.relative_block(geo[:len(ksel)], ov[:len(ksel)])
-    feats = ofeat.assemble_features(video.cls, video.motion, rel, pr[ksel]).astype(np.float32)
-    det["features_topk_rows"] = (time.perf_counter() - t0) * k / len(ksel)
-    if len(ksel) < k:
-        feats = np.concatenate([feats] * (k // len(ksel) + 1), axis=0)[:k]
-    t0 = time.perf_counter()
-    with torch.no_grad():
-        oheads.relation_predictor_ref(feats, sd)
-    det["predicate_head"] = time.perf_counter() - t0
-    x = np.ascontiguousarray(np.concatenate([geo] * (k // geo.shape[0] + 1), axis=0)[:k], dtype=np.float32)
-    t0 = time.perf_counter()
-    with torch.no_grad():
-        reg = oheads.dpn_head_ref(x, sd).numpy()
-    oheads.decode_spans_f64(reg, sizes, stride)
-    det["span_head_decode"] = time.perf_counter() - t0
+    rel = ofeat.relative_block(geo[pos].astype(np.float64), ov[pos])
+    feats = ofeat.assemble_features(video.cls, video.motion, rel, pr[rows]).astype(np.float32)
+    det["feature_rows_of_survivors"] = time.perf_counter() - t0
     t0 = time.perf_counter()
     with torch.no_grad():
         logits = oheads.relation_predictor_ref(feats, sd).numpy()
-    rows = np.resize(sel, k)
+    det["predicate_head"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        reg = oheads.dpn_head_ref(np.ascontiguousarray(geo[pos], dtype=np.float32), sd).numpy()
+    spans = oheads.decode_spans_f64(reg, sizes, stride)
+    if n_keep:
+        oheads.select_spans(spans, ov[pos], n_keep, 0.5)
+    det["span_head_decode_nms"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
     oheads.postprocess_ref(logits, video.cls, pr[rows], 20, 200)
     det["postprocess"] = time.perf_counter() - t0
     return sum(det.values()), det
+
+
+def reference_sample(args, cfgd):
+    """The bounded sample of the workload one CPU step processes: (videos, pair_sample or None, description)."""
+    from tspn_b200 import synth
+    key, _, scaling, _, _ = WORKLOADS[args.workload]
+    spec = synth.CONFIGS[key]
+    c = spec["classes"]
+    if scaling == "weak":
+        n, t = spec["n"][1], spec["t"][1]
+        vids, budget = [], CPU_PAIR_FRAME_BUDGET
+        pf = n * (n - 1) * t
+        if pf > budget:          # stress: one video, geometry on a bounded sample of its pairs
+            sample = max(256, int(budget // t))
+            return [synth.make_video(n, t, c, seed=0)], sample, (
+                "1 video of the step (N=%d T=%d, P=%d); vIoU + per-frame geometry on %d sampled pairs scaled to P, "
+                "relationness / top-K / heads / records at full size" % (n, t, n * (n - 1), sample))
+        count = max(1, min(cfgd["videos"], int(budget // max(pf, 1))))
+        vids = [synth.make_video(n, t, c, seed=i) for i in range(count)]
+        return vids, None, "%d of the step's %d videos per GPU, every pair and frame (no extrapolation)" % (
+            count, cfgd["videos"])
+    shapes = synth.config_shapes(key, 0, cfgd["videos"])
+    vids, used = [], 0
+    for i, (n, t) in enumerate(shapes):
+        if used >= CPU_PAIR_FRAME_BUDGET:
+            break
+        vids.append(synth.make_video(n, t, c, seed=i))
+        used += n * (n - 1) * t
+    return vids, None, "the first %d of the %d videos (%.1f M pair-frames), every pair and frame" % (
+        len(vids), len(shapes), used / 1e6)
 
 
 def run_reference(args, rank, world):
     """`--impl reference`: rank 0 alone times the CPU path; other ranks exit 0 without work."""
     if rank != 0:
         return
+    import multiprocessing as mp
+    from concurrent.futures import ProcessPoolExecutor
     from tspn_b200 import synth
-    spec = synth.CONFIGS[WORKLOAD]
-    c, r, k = spec["classes"], spec["predicates"], spec["topk"]
+    cfgd = workload_config(args, world)
+    c, r, k = cfgd["classes"], cfgd["predicates"], cfgd["topk"]
+    sizes, stride = tuple(cfgd["anchor_sizes"]), cfgd["anchor_stride"]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = synth.make_weights(c, r, synth.feature_dim(c), dpn_in=8, seed=0)
-    sizes, stride = (16.0, 64.0, 256.0, 1024.0), 16.0
-    n, t = spec["n"][0], spec["t"][0]
-    sample = 16 * cores
-    times = []
-    for i in range(args.warmup + args.steps):
-        v = synth.make_video(n, t, c, seed=i)
-        sec, det = cpu_reference_step(v, sd, k, sizes, stride, sample_pairs=sample)
-        if i >= args.warmup:
-            times.append(sec)
-    pairs = n * (n - 1)
+    vids, pair_sample, what = reference_sample(args, cfgd)
+    pairs = sum(v.n_pairs for v in vids)
+    times, det_sum = [], {}
+    with ProcessPoolExecutor(max_workers=cores, mp_context=mp.get_context("spawn")) as pool:
+        list(pool.map(abs, range(cores)))                      # workers up before the clock starts
+        for i in range(args.warmup + args.steps):
+            sec, det_sum = 0.0, {}
+            for v in vids:
+                s, det = cpu_reference_video(v, sd, k, sizes, stride, args.span_proposals, pool, cores, pair_sample)
+                sec += s
+                for kk, vv in det.items():
+                    det_sum[kk] = det_sum.get(kk, 0.0) + vv
+            if i >= args.warmup:
+                times.append(sec)
     ms = 1e3 * float(np.mean(times))
     value = pairs / (ms / 1e3)
     line = {
-        "metric": "tracklet pairs scored/sec (N=64,T=2000)", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+        "metric": "tracklet pairs scored/sec", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64 (numpy + torch CPU)", "data": "synthetic",
-        "impl": "reference",
-        "config": {"workload": "VidOR-shaped video N=64 T=2000 C=80 R=50 K=256, 1 video per step",
-                   "sparsify": True, "host_cpu_count": cores, "torch_threads": torch.get_num_threads()},
+        "scaling": WORKLOADS[args.workload][2], "vs_baseline": None, "dtype": "f32/f64 (numpy + torch CPU)",
+        "data": "synthetic", "impl": "reference", "config": cfgd,
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
-                         "sample": "1 video/step; geometry+feature rows on %d sampled pairs scaled to P=%d, "
-                                   "relationness/top-K/classifier/span head at full size" % (sample, pairs),
-                         "detail_s": det},
+                         "sample": what + "; vIoU = the reference's per-pair python viou over %d processes + cubic_iou, "
+                                          "heads = the reference's torch CPU ops with %d threads, per-frame geometry = numpy "
+                                          "oracle over %d threads" % (cores, torch.get_num_threads(), cores),
+                         "pairs_per_step": pairs, "detail_s": det_sum},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -254,38 +348,72 @@ def run_reference(args, rank, world):
 # ------------------------------------------------------------------------------------------------
 # this repo's arm
 # ------------------------------------------------------------------------------------------------
+def alg_bytes_of(shapes) -> int:
+    """Algorithmic bytes of the all-pairs kernel for these (N, T) videos."""
+    tot = 0
+    for n, t in shapes:
+        tp, tb, p = (t + 3) // 4 * 4, (t + 7) // 8 * 8, n * max(n - 1, 0)
+        tot += 32 * tp * p + 16 * p + 16 * n * tb + 8 * n
+    return tot
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
-    from tspn_b200 import _lib, ops, synth
-    from tspn_b200.batch import HostBatch
+    from tspn_b200 import _lib, affinity, ops, sharding, synth
     from tspn_b200.pipeline import PairStage, StageConfig
-    from tspn_b200.serving import PipelinedStage
+    from tspn_b200.serving import PipelinedStage, bucket_key, host_batches_for
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     ops.require_device()
-    spec = synth.CONFIGS[WORKLOAD]
-    c, r, k = spec["classes"], spec["predicates"], spec["topk"]
-    n, t = spec["n"][0], spec["t"][0]
+    bound = None if args.no_affinity else affinity.bind_to_gpu(local_rank, world)
+    cfgd = workload_config(args, world)
+    key, _, scaling, _, _ = WORKLOADS[args.workload]
+    c, r, k = cfgd["classes"], cfgd["predicates"], cfgd["topk"]
+    sizes, stride = tuple(cfgd["anchor_sizes"]), cfgd["anchor_stride"]
     sparsify = not args.no_sparsify
-    sizes, stride = (16.0, 64.0, 256.0, 1024.0), 16.0
     cfg = StageConfig(n_classes=c, n_predicates=r, topk=k, use_ppn=True, use_dpn=True, sparsify=sparsify,
-                      precision=args.precision, anchor_sizes=sizes, anchor_stride=stride)
+                      precision=args.precision, anchor_sizes=sizes, anchor_stride=stride,
+                      num_span_proposals=args.span_proposals)
     sd = synth.make_weights(c, r, synth.feature_dim(c), dpn_in=8, seed=0)
     stage = PairStage(cfg)
     stage.load_weights(sd, dev)
-    videos = [synth.make_video(n, t, c, seed=100000 * rank + i) for i in range(args.videos)]
-    host = HostBatch.from_videos(videos, compact=not args.fp32_transport)
-    pairs_per_step = sum(v.n_pairs for v in videos)
 
-    # ---- resident-input steps ------------------------------------------------------------------
-    # The serving loop below owns `depth` slots (device inputs + captured CUDA graphs + pinned result
-    # buffers); the resident-input measurement replays slot 0's graphs on inputs already in HBM.
-    group = dist.group.WORLD if world > 1 else None
-    pipe = PipelinedStage(stage, host, device=dev, depth=args.depth, graphs=not args.eager, group=group,
+    # ---- this rank's videos ------------------------------------------------------------------------
+    spec = synth.CONFIGS[key]
+    shards = None
+    if scaling == "weak":
+        videos = [synth.make_video(spec["n"][1], spec["t"][1], c, seed=100000 * rank + i) for i in range(cfgd["videos"])]
+        all_shapes = [(v.n_tracklets, v.n_frames) for v in videos] * world
+        my_ids = list(range(len(videos)))
+        imbalance = 1.0
+    else:
+        all_shapes = synth.config_shapes(key, 0, cfgd["videos"])
+        shards = sharding.shard_videos(all_shapes, world)
+        imbalance = sharding.imbalance(all_shapes, shards)
+        my_ids = shards[rank]
+        videos = [synth.make_video(all_shapes[i][0], all_shapes[i][1], c, seed=i) for i in my_ids]
+    pairs_global = sum(n * max(n - 1, 0) for n, _ in all_shapes)
+    hosts, batch_vids, caps = host_batches_for(videos, c, geo_budget_bytes=int(args.geo_budget_gb * (1 << 30)))
+    residents = [h.to_device(dev) for h in hosts]            # the step's inputs, resident in HBM
+    templates, seen = [], set()
+    for h in hosts:
+        if bucket_key(h) not in seen:
+            seen.add(bucket_key(h))
+            templates.append(h)
+
+    # The serving loop owns, per capacity bucket, `depth` slots (device inputs + captured CUDA graph + pinned result
+    # buffers); the resident-input measurement replays the same graphs on inputs already in HBM (device-to-device
+    # refill of the slot's input arena).
+    group = dist.group.WORLD if (world > 1 and scaling == "weak") else None
+    pipe = PipelinedStage(stage, templates, device=dev, depth=args.depth, graphs=not args.eager, group=group,
                           compute_streams=args.compute_streams, single_graph=not args.three_graphs)
-    slot0 = pipe.slots[0]
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)    # > 126 MB L2
+    n_local = len(videos)
+    tpv = cfg.topk_per_video
+    rec_local = torch.zeros((max(n_local, 1), tpv, 8), dtype=torch.int32, device=dev)
+    cnt_local = torch.zeros(max(n_local, 1), dtype=torch.int32, device=dev)
+    batch_idx = [torch.as_tensor(v, dtype=torch.int64, device=dev) for v in batch_vids]
     torch.cuda.synchronize()
 
     def barrier():
@@ -293,42 +421,78 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def one_step(timers=None):
-        if slot0.graphed is not None:
-            return slot0.graphed.replay(timers=timers)
-        return stage.forward(slot0.batch, timers=timers)
+    geo_acc = {"ms": 0.0, "launches": 0}
+    pending = {}                                        # slot -> its pair-kernel events not read yet
 
-    geo_ms, step_ms = [], []
+    def read_geo(slot):
+        ev = pending.pop(slot, None)
+        if ev is not None:
+            ev[1].synchronize()
+            geo_acc["ms"] += ev[0].elapsed_time(ev[1])
+            geo_acc["launches"] += 1
+
+    def gather_step():
+        if shards is not None and world > 1:
+            return sharding.gather_records(rec_local[:n_local], cnt_local[:n_local], shards)
+        return rec_local, cnt_local
+
+    def one_step():
+        used = {}
+        for j, (resident, host) in enumerate(zip(residents, hosts)):
+            bucket = pipe._bucket(host)
+            i = used.get(id(bucket), 0)
+            used[id(bucket)] = i + 1
+            slot = bucket.slots[i % len(bucket.slots)]
+            read_geo(slot)                              # its events are re-recorded by the next replay
+            slot.batch.copy_from_device(resident)
+            timers = {}
+            res = slot.graphed.replay(timers=timers) if slot.graphed is not None else \
+                stage.forward(slot.batch, timers=timers)
+            pending[slot] = timers["geo"]
+            if shards is not None:
+                nr = len(batch_vids[j])
+                rec_local.index_copy_(0, batch_idx[j], res.records[:nr])
+                cnt_local.index_copy_(0, batch_idx[j], res.record_counts[:nr])
+        return gather_step()
+
+    def drain_geo():
+        for slot in list(pending):
+            read_geo(slot)
+
+    step_ms = []
     sampler = ClockSampler(local_rank)
     sampler.start()                                     # samples through warm-up, timed steps and e2e
     launches0 = ops.launch_count()
     for i in range(args.warmup):
         one_step()
     barrier()
+    drain_geo()
     launches_per_step = (ops.launch_count() - launches0) // max(args.warmup, 1)
+    geo_acc["ms"], geo_acc["launches"] = 0.0, 0
     t_wall0 = time.perf_counter()
     for i in range(args.steps):
         flush.zero_()                                   # L2 flush between timed iterations (untimed)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        timers = {}
         e0.record()
-        one_step(timers=timers)
+        one_step()
         e1.record()
-        # the single-graph replay times the geometry kernel with external event nodes that the next
-        # replay re-records: read them now (the steps are separated by the untimed L2 flush anyway)
         e1.synchronize()
         step_ms.append(e0.elapsed_time(e1))
-        geo_ms.append(timers["geo"][0].elapsed_time(timers["geo"][1]))
+        drain_geo()
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    # the pair kernel on its own (same inputs, nothing else on the device): what the co-resident side branch costs it
+    geo_ms_total, geo_launches = geo_acc["ms"], geo_acc["launches"]
+    # the pair kernel on its own (largest batch, nothing else on the device): what the co-resident side branch costs it
+    big = max(range(len(hosts)), key=lambda j: int(hosts[j].actual[_lib.TOT_GEO_FLOATS]))
+    bslot = pipe._bucket(hosts[big]).slots[0]
+    bslot.batch.copy_from_device(residents[big])
+    geom_alone = bslot.graphed.result.geom if bslot.graphed is not None else ops.pair_geometry_outputs(bslot.batch)
     alone_ms = []
-    geom_alone = slot0.graphed.result.geom if slot0.graphed is not None else ops.pair_geometry_outputs(slot0.batch)
     for i in range(3 + min(args.steps, 10)):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        ops.pair_geometry_phase(slot0.batch, geom_alone, _lib.GEO_PHASE_MAIN)
+        ops.pair_geometry_phase(bslot.batch, geom_alone, _lib.GEO_PHASE_MAIN)
         e1.record()
         e1.synchronize()
         if i >= 3:
@@ -339,93 +503,152 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         total_ms = float(tt.item())
     ms_per_step = total_ms / args.steps
-    value = world * pairs_per_step / (ms_per_step / 1e3)
+    value = pairs_global / (ms_per_step / 1e3)
 
     # ---- end-to-end steps: pinned host in, pinned host out ------------------------------------
-    # tspn_b200.serving.PipelinedStage (the host-facing call): every step copies its own inputs from
-    # pinned host memory and its own results back to pinned host memory inside the timed region; H2D of
-    # step i+1 and D2H of step i-1 overlap the kernels of step i (three streams, --depth batches in flight).
-    def e2e_loop(steps):
-        n_out = 0
-        for out in pipe.run(host for _ in range(steps)):
-            n_out += int(out["record_counts"][0] >= 0)      # touch the host result
-        assert n_out == steps
+    # tspn_b200.serving.PipelinedStage (the host-facing call): every batch of every step is copied from pinned
+    # host memory and its results are copied back to pinned host memory inside the timed region; H2D of batch
+    # i+1 and D2H of batch i-1 overlap the kernels of batch i (three streams, --depth batches in flight).  The
+    # loop runs warm-up + timed steps back to back (a serving loop does not drain between requests); the clock
+    # starts when the last warm-up step's results are on the host and stops when the last timed step's are.
+    rec_host = torch.empty((len(all_shapes) if shards is not None else 1, tpv, 8), dtype=torch.int32).pin_memory()
+    s_gather = torch.cuda.Stream(dev)
+    nb = len(hosts)
+    ring_n = args.depth + 2                             # steps whose records can be in flight at once
+    rings = [(torch.zeros_like(rec_local), torch.zeros_like(cnt_local)) for _ in range(ring_n)] \
+        if shards is not None else None
 
-    e2e_loop(max(args.warmup, 2))
-    barrier()
-    t0 = time.perf_counter()
-    e2e_loop(args.steps)
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    def e2e_steps(n_warm, n_timed):
+        step_events, gather_done = {}, {}
+
+        def post(q, res):                               # on the batch's compute stream, right behind its kernels
+            if shards is None:
+                return
+            s, j = divmod(q, nb)
+            old = gather_done.pop(s - ring_n, None)     # the ring slot's previous step has left the device
+            if old is not None:
+                torch.cuda.current_stream(dev).wait_event(old)
+            rl, cl = rings[s % ring_n]
+            nr = len(batch_vids[j])
+            rl.index_copy_(0, batch_idx[j], res.records[:nr])
+            cl.index_copy_(0, batch_idx[j], res.record_counts[:nr])
+            ev = torch.cuda.Event()
+            ev.record()
+            step_events.setdefault(s, []).append(ev)
+
+        t_start, touched, q_out = None, 0, 0
+        total = (n_warm + n_timed) * nb
+        for out in pipe.run((hosts[q % nb] for q in range(total)), post=post):
+            touched += int(out["record_counts"].shape[0])          # touch the host result
+            q_out += 1
+            if q_out % nb:
+                continue
+            s = q_out // nb - 1                         # every batch of step s is back on the host
+            if shards is not None:                      # the step's one collective + the gathered records' D2H
+                with torch.cuda.stream(s_gather):
+                    for ev in step_events.pop(s):
+                        s_gather.wait_event(ev)
+                    rl, cl = rings[s % ring_n]
+                    ra = sharding.gather_records(rl[:n_local], cl[:n_local], shards)[0] if world > 1 else rl[:n_local]
+                    rec_host[:ra.shape[0]].copy_(ra, non_blocking=True)
+                    gd = torch.cuda.Event()
+                    gd.record()
+                    gather_done[s] = gd
+            if s == n_warm - 1:                         # warm-up over: the clock starts with the pipeline full
+                s_gather.synchronize()
+                t_start = time.perf_counter()
+        s_gather.synchronize()
+        return time.perf_counter() - t_start, touched
+
+    e2e_s, touched = e2e_steps(max(args.warmup, 2), args.steps)
+    assert touched > 0
     if world > 1:
         tt = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
-    e2e_value = world * pairs_per_step * args.steps / e2e_s
-    d2h = pipe.d2h_bytes()
+    e2e_value = pairs_global * args.steps / e2e_s
+    h2d = int(sum(h.h2d_bytes() for h in hosts))
+    d2h = int(pipe.d2h_total_bytes() // max(max(args.warmup, 2) + args.steps, 1)) + \
+        (int(rec_host.numel() * 4) if shards is not None else 0)
     clocks = sampler.stop()
+    if world > 1:                                       # per-step bytes of the busiest rank
+        tt = torch.tensor([h2d, d2h], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        h2d, d2h = int(tt[0].item()), int(tt[1].item())
 
     if rank != 0:
         return
     # ---- roofline of the dominant kernel (all-pairs geometry + vIoU) ------------------------------
-    tp, tb = (t + 3) // 4 * 4, (t + 7) // 8 * 8
-    p1 = n * (n - 1)
-    alg_bytes = args.videos * (32 * tp * p1 + 16 * p1 + 16 * n * tb + 8 * n)      # DESIGN.md, SURVEY 8d
-    geo_avg_ms = float(np.mean(geo_ms))
-    achieved = alg_bytes / (geo_avg_ms / 1e3) / 1e9
+    my_shapes = [(v.n_tracklets, v.n_frames) for v in videos]
+    alg_bytes = alg_bytes_of(my_shapes)                 # per step of this rank
+    geo_ms_step = geo_ms_total / args.steps
+    achieved = alg_bytes / (geo_ms_step / 1e3) / 1e9
     peak, peak_src = measured_peak()
+    alone_bytes = alg_bytes_of([my_shapes[i] for i in batch_vids[big]])
+    alone_gbs = alone_bytes / (float(np.mean(alone_ms)) / 1e3) / 1e9
+    cfgd.update({
+        "batches_per_step_per_gpu": len(hosts), "pairs_per_step": pairs_global,
+        "capacities": {str(cc): {"videos": cap.videos, "pairs": cap.pairs, "geo_gb": cap.geo_floats * 4 / 1e9,
+                                 "geo_chunk": cap.geo_chunk, "max_n": cap.max_n, "max_t": cap.max_t}
+                       for cc, cap in caps.items()},
+        "precision": args.precision,
+        "sharding": ("per video, LPT on N(N-1)T (imbalance %.4f); NCCL all-gather of the [V,200,8] int32 triplet "
+                     "records inside the timed region" % imbalance) if shards is not None else
+                    "per video, every rank its own videos; no data-path collective in `value`, all-gather of the "
+                    "records per step in the e2e loop",
+        "l2": "256 MiB buffer zeroed between timed iterations (untimed); each step also writes %.2f GB of outputs"
+              % (alg_bytes / 1e9),
+        "wall_s_timed_region": t_wall,
+        "launch": "eager C-ABI calls" if args.eager else
+                  ("one CUDA-graph launch per batch; the graph was captured once per capacity bucket and serves "
+                   "every ragged batch packed for it; three branches inside: the persistent all-pairs kernel | "
+                   "relationness -> top-K -> surviving-pair rows -> predicate head -> records | per-tracklet terms, "
+                   "volumes, span NMS, vIoU finalize"),
+        "e2e_pipeline": "tspn_b200.serving.PipelinedStage, depth %d, %d compute stream(s): per batch the used part "
+                        "of the pinned input arena goes H2D, results D2H; warm-up and timed steps run back to back, "
+                        "the clock covers exactly the timed steps" % (args.depth, args.compute_streams),
+        "h2d_transport": "u16 boxes + u8 motion counts (lossless for these inputs), expanded on the device",
+        "cpu_affinity": bound,
+    })
     line = {
-        "metric": "tracklet pairs scored/sec (N=64,T=2000)", "value": value, "unit": "pairs/s", "n_gpus": world,
+        "metric": "tracklet pairs scored/sec", "value": value, "unit": "pairs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None,
+        "scaling": scaling, "vs_baseline": None,
         "dtype": "f32 geometry/features, f64 volume sums, %s heads" % ("bf16 tcgen05" if args.precision == "tensor"
                                                                          else "f32 exact-order"),
-        "data": "synthetic",
-        "config": {"workload": "VidOR-shaped videos N=64 T=2000 C=80 R=50 K=256 (BASELINE.json configs[2]), "
-                               "%d videos per GPU per step" % args.videos,
-                   "videos_per_gpu": args.videos, "pairs_per_step_per_gpu": pairs_per_step, "sparsify": sparsify,
-                   "precision": args.precision, "sharding": "per video, no data-path collective",
-                   "l2": "256 MiB buffer zeroed between timed iterations (untimed); each step also writes "
-                         "%.1f GB of outputs" % (alg_bytes / 1e9),
-                   "wall_s_timed_region": t_wall,
-                   "launch": "eager C-ABI calls" if args.eager else
-                             ("3 CUDA-graph launches per step (side: relationness+top-K+motion norm || geo; tail)"
-                              if args.three_graphs else
-                              "1 CUDA-graph launch per step; three branches inside the graph: the persistent all-pairs "
-                              "kernel | relationness -> top-K -> surviving-pair rows (relative block + span proposals "
-                              "recomputed from the boxes) -> predicate head -> records | per-tracklet predicate terms, "
-                              "volumes, vIoU finalize - the side branches co-reside with the all-pairs kernel"),
-                   "e2e_pipeline": "tspn_b200.serving.PipelinedStage, depth %d: one H2D copy of the pinned input "
-                                   "arena per step; H2D(i+1..) and D2H(i-1) overlap the kernels of step i; %d compute "
-                                   "stream(s)" % (args.depth, args.compute_streams),
-                   "h2d_transport": "u16 boxes + u8 motion counts (lossless for these inputs), expanded on the device"
-                                    if host.boxes_compact and host.motion_compact else "fp32",
-                   "multi_gpu_collective": "all_gather of [V,200,8] int32 triplet records per step (e2e loop)"},
-        "roofline": {"bound": "hbm", "kernel": "pair_geo_kernel (CUDA events immediately around this launch)",
+        "data": "synthetic", "config": cfgd,
+        "roofline": {"bound": "hbm", "kernel": "pair_geo_kernel (CUDA events immediately around each launch)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": measured_traffic(args.videos), "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                     "avg_launch_ms": geo_avg_ms, "share_of_step": geo_avg_ms / (float(np.mean(step_ms))),
+                     "traffic": measured_traffic(args.workload, cfgd["videos"]), "peak_source": peak_src,
+                     "algorithmic_bytes_per_step": alg_bytes, "launches_per_step": geo_launches / args.steps,
+                     "avg_launch_ms": geo_ms_total / max(geo_launches, 1),
+                     "share_of_step": geo_ms_step / float(np.mean(step_ms)),
                      "note": "achieved / frac are measured inside the timed steps, where the side branches' kernels "
-                             "co-reside with this kernel on every SM; `alone` is the same launch with an idle device",
-                     "alone": {"avg_launch_ms": float(np.mean(alone_ms)),
-                               "achieved": alg_bytes / (float(np.mean(alone_ms)) / 1e3) / 1e9,
-                               "frac": alg_bytes / (float(np.mean(alone_ms)) / 1e3) / 1e9 / peak}},
-        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": host.h2d_bytes(),
-                "d2h_bytes_per_step": d2h},
+                             "co-reside with this kernel on every SM; `alone` is the largest batch's launch with an "
+                             "idle device",
+                     "alone": {"avg_launch_ms": float(np.mean(alone_ms)), "achieved": alone_gbs,
+                               "frac": alone_gbs / peak}},
+        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches_per_step * args.steps),
         "launches_per_step": int(launches_per_step),
         "clocks": clocks,
     }
     if not args.no_cpu_baseline and world == 1:
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
-        sec, det = cpu_reference_step(videos[0], sd, k, sizes, stride, sample_pairs=16 * cores)
-        line["cpu_baseline"] = {"value": p1 / sec, "unit": "pairs/s", "cores": cores, "kind": "port",
-                                "sample": "1 video (P=%d); geometry+feature rows on %d sampled pairs (split over "
-                                          "%d threads) scaled to P, heads at full size; torch threads=%d"
-                                          % (p1, 16 * cores, cores, torch.get_num_threads()),
-                                "detail_s": det}
+        line["cpu_baseline"] = cpu_baseline_subprocess(args)
     emit(line)
+
+
+def cpu_baseline_subprocess(args):
+    """The CPU leg in a child process (it forks worker processes: not something to do under a live CUDA context)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload, "--steps", "1",
+           "--warmup", "1", "--span-proposals", str(args.span_proposals)]
+    if args.videos:
+        cmd += ["--videos", str(args.videos)]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+        return json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]
+    except Exception as e:  # noqa: BLE001
+        return {"value": None, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (e,)}
 
 
 _JSON_OUT = None

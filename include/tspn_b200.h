@@ -21,10 +21,16 @@
  *   - base pointers must be 16-byte aligned (TMA, 128-bit accesses) -> TSPN_EALIGN.
  *
  * Batch layout (several videos per launch)
- *   A batch of V videos is described by the *video table*: V rows of TSPN_VT_COLS
- *   int64, built on the host by tspn_build_video_table() from the per-video tracklet
- *   and frame counts, then copied to the device by the caller.  With N = tracklets,
- *   T = frames, P = N(N-1) ordered pairs of a video:
+ *   A batch of V videos is described by the *video table*: (table_rows + 1) rows of
+ *   TSPN_VT_COLS int64, built on the host by tspn_build_video_table() from the per-video
+ *   tracklet and frame counts, then copied to the device by the caller.  Rows [0, V) are the
+ *   videos, rows [V, table_rows) are empty videos (N = 0), and row `table_rows` is the SENTINEL:
+ *   its offset columns hold the batch's totals (tracklets, pairs, geo floats, work items, boxes,
+ *   scores).  Every entry point takes `num_videos` = table_rows and reads the true totals from the
+ *   sentinel on the device, so the scalar totals a caller passes are only UPPER BOUNDS (they size
+ *   the grids): a launch sequence recorded once for a capacity (a CUDA graph) serves every batch
+ *   that fits it - ragged batches need no re-capture (ABI 5).  With N = tracklets, T = frames,
+ *   P = N(N-1) ordered pairs of a video:
  *     boxes   float [sum N*Tb][4]   (x1,y1,x2,y2) inclusive pixels, row of tracklet n at
  *                                   box_off + n*Tb, Tb = T rounded up to 8 (pad = 0)
  *     span    int32 [sum N][2]      [pstart, pend)   (lib/modeling/trajectory.py:21-22)
@@ -42,7 +48,7 @@
 extern "C" {
 #endif
 
-#define TSPN_ABI_VERSION 4
+#define TSPN_ABI_VERSION 5
 
 /* error codes */
 #define TSPN_OK 0
@@ -76,6 +82,7 @@ extern "C" {
 #define TSPN_TOT_MAX_N 6
 #define TSPN_TOT_MAX_T 7
 #define TSPN_TOT_GEO_CHUNK 8 /* frames per work item of the pair-geometry kernel: tspn_geo_chunk(max T) */
+#define TSPN_TOT_MAX_CHUNKS 9 /* max over videos of ceil(T / geo_chunk): chunk slots per pair in the workspace */
 
 /* Work items of the pair-geometry kernel: (video, subject, group of TSPN_GEO_OBJ_GROUP other
  * tracklets, chunk of tspn_geo_chunk(max T of the batch) frames), numbered chunk-fastest; the table's
@@ -98,17 +105,16 @@ extern "C" {
 #define TSPN_GEO_DENSE_CTAS 2   /* tspn_pair_geo_viou: 1024 threads per SM with a 2-stage TMA ring and 64 registers
                                   instead of the default ~512 threads per SM, 3 stages, 103 registers (same
                                   results bit for bit; measured slower, kept for A/B - DESIGN.md section 4.1) */
-/* tspn_pair_geo_viou runs three kernels: PRE (per-tracklet volumes + zeroing of the per-pair sums), MAIN (the
- * pair kernel), POST (per-pair vIoU / tIoU / overlap).  With none of these bits set all three run; a caller
- * that wants to time the pair kernel alone issues the phases as separate calls (same arguments). */
+/* tspn_pair_geo_viou runs three kernels: PRE (per-tracklet volumes), MAIN (the pair kernel), POST (per-pair
+ * vIoU / tIoU).  With none of these bits set all three run; a caller that wants to time the pair kernel alone,
+ * or to overlap the phases, issues them as separate calls (same arguments).  Every (pair, chunk) has exactly one
+ * writer - the CTA of that work item stores the chunk's fixed-point sums into the pair's chunk slot of the
+ * workspace ([pair][max_chunks][3] uint64) and POST adds a pair's slots in ascending chunk order - so nothing is
+ * zeroed and there are no global atomics: PRE may run on another stream concurrently with MAIN; POST needs both.
+ * MAIN writes d_overlap; POST writes d_viou / d_tiou. */
 #define TSPN_GEO_PHASE_PRE 8
 #define TSPN_GEO_PHASE_MAIN 16
 #define TSPN_GEO_PHASE_POST 32
-/* The caller asserts that every video of the batch fits one chunk (totals[TSPN_TOT_MAX_T] <=
- * totals[TSPN_TOT_GEO_CHUNK]): every pair's sums then have a single writer, PRE does not zero them, and PRE
- * (per-tracklet volumes only) may be issued on another stream concurrently with MAIN; POST needs both.  MAIN
- * writes d_overlap; POST writes d_viou / d_tiou.  Pass the flag to every phase of the call. */
-#define TSPN_GEO_SINGLE_CHUNK 64
 /* MAIN as persistent CTAs (one per SM slot for the whole launch) that pull work items from a queue in the
  * workspace, instead of one CTA per work item: same results bit for bit.  Kernels issued concurrently on
  * other streams can then only co-reside with the pair kernel's CTAs - they can never take over an SM between
@@ -133,10 +139,12 @@ int tspn_last_error(char* buf, int len);
 int tspn_check_device(void);
 
 /* ---- host helper: batch layout ------------------------------------------------------- */
-/* table_host: [V][TSPN_VT_COLS] int64 (host), totals: [TSPN_TOT_COLS] int64 (host).
- * Pure host arithmetic on sizes; no device access. */
+/* table_host: [table_rows + 1][TSPN_VT_COLS] int64 (host), totals: [TSPN_TOT_COLS] int64 (host).
+ * table_rows >= num_videos (0 = num_videos): the table is padded with empty videos up to table_rows, then
+ * the sentinel row.  geo_chunk: 0 = tspn_geo_chunk(max T of the batch), else 512 / 1024 / 2048 (a capacity
+ * bucket fixes the chunk its launches were recorded with).  Pure host arithmetic on sizes; no device access. */
 int tspn_build_video_table(int num_videos, const int32_t* n_tracklets, const int32_t* n_frames,
-                           int64_t* table_host, int64_t* totals);
+                           int table_rows, int geo_chunk, int64_t* table_host, int64_t* totals);
 /* 512, 1024 or 2048: the smallest chunk that covers max_t (2048 beyond); one CTA of chunk/4 threads
  * writes whole geometry rows where it can - HBM absorbs few wide store streams best */
 int tspn_geo_chunk(int64_t max_t);
@@ -152,11 +160,11 @@ int tspn_enumerate_pairs(const int64_t* d_table, int num_videos, int64_t total_p
  * ordered pairs of each video, viou (lib/evaluation/common.py:65-106) and _traj_iou
  * (lib/modeling/association.py:35-48, flag TSPN_VIOU_CLIPPED); adds the per-frame channels.
  * d_geo may be NULL (reductions only).  d_workspace: tspn_pair_geo_workspace_bytes() bytes
- * (per-tracklet volumes + per-pair fixed-point volume sums + the persistent kernel's work-item queue),
- * 16-byte aligned.  Outputs by phase (flags below): MAIN writes d_geo and d_overlap, POST writes d_viou and
+ * (per-tracklet volumes + per-(pair, chunk) fixed-point volume sums + the persistent kernel's work-item
+ * queue), 16-byte aligned; max_chunks = totals[TSPN_TOT_MAX_CHUNKS] (an upper bound, like the other totals).  Outputs by phase (flags below): MAIN writes d_geo and d_overlap, POST writes d_viou and
  * d_tiou from the sums MAIN left in the workspace and the volumes of PRE. */
-int64_t tspn_pair_geo_workspace_bytes(int64_t total_tracklets, int64_t total_pairs);
-int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_items, int geo_chunk,
+int64_t tspn_pair_geo_workspace_bytes(int64_t total_tracklets, int64_t total_pairs, int max_chunks);
+int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_items, int geo_chunk, int max_chunks,
                        int64_t total_tracklets, int64_t total_pairs, int64_t total_boxes,
                        const float* d_boxes, const int32_t* d_span,
                        float* d_geo, float* d_viou, float* d_tiou, int32_t* d_overlap,
@@ -314,6 +322,27 @@ int tspn_span_proposals(const float* d_x, const int64_t* d_rows, int64_t row_bas
                         const float* d_conv_w, const float* d_conv_b,
                         const float* d_pred_w, const float* d_pred_b, int n_anchors,
                         const float* d_sizes, float stride, int32_t* d_spans, void* stream);
+
+/* ---- a12 + [SPEC] s8: span suppression and top-n (RelNMS) -----------------------------------------
+ * What RelNMS (lib/modeling/relpn/rel_nms.py:6-15: nms_threshold 0.5, top_k_proposals =
+ * RELPN.DPN.NUM_DURATION_PROPOSALS = 64, lib/config/defaults.py:62) is meant to do; its forward is a stub in the
+ * reference, so the rule is [SPEC] (oracle/heads.py:select_spans), integers only, bit-exact:
+ *   candidate i of a pair = decoded span [s_i, e_i) in the decode's order (location major, anchor minor);
+ *   rank key q_i = floor(2^15 * |span_i ^ W| / |span_i v W|), W = the pair's temporal overlap window; ties to the
+ *   lower i; greedy: keep the best live candidate, drop every live candidate whose temporal IoU with it exceeds
+ *   nms_threshold (inter * 1024 > round(1024 * thr) * union), until n_keep are kept or none is left.
+ * d_cand int32 [n_rows][ld_cand]: row r holds its candidates as (start, end) pairs.  Two ways to describe the rows:
+ *   - d_table != NULL: row r scores global pair row d_rows[r] (NULL = r; negative = padding -> count 0); it has
+ *     locations(T_video) * n_anchors candidates and, unless d_windows is given, its window comes from the tracklet
+ *     spans d_span (so the call does not depend on the all-pairs kernel); max_frames = totals[TSPN_TOT_MAX_T];
+ *   - d_table == NULL: every row has n_cand candidates and the window d_windows[r] (int32 [n_rows][2]).
+ * d_out: int16 [n_rows][n_keep][2] with TSPN_SPANS_I16 (frames < 65536 always required), else int32; kept spans
+ * in keep order, zero padded; d_counts int32 [n_rows] (may be NULL). */
+#define TSPN_SPANS_I16 1
+int tspn_span_select(const int64_t* d_table, int num_videos, int max_frames, const int32_t* d_span,
+                     const int64_t* d_rows, int64_t n_rows, const int32_t* d_windows,
+                     const int32_t* d_cand, int64_t ld_cand, int n_cand, int n_anchors, float stride, int n_keep,
+                     float nms_threshold, int flags, void* d_out, int32_t* d_counts, void* stream);
 
 /* ---- surviving pairs: relative block + bias row + span proposals, recomputed from the boxes ------------
  * For every row the top-K kept (d_rows: global pair rows, [V][rows_per_video], -1 = padding) this produces

@@ -282,3 +282,16 @@ def pair_geometry_chunked(boxes, span, clip_volumes=False, max_pairs: int = 256)
         t = boxes.shape[1]
         return (np.zeros((0, GEO_CHANNELS, t)), np.zeros(0), np.zeros(0), np.zeros((0, 2), np.int32))
     return tuple(np.concatenate([o[k] for o in outs], axis=0) for k in range(4))
+
+
+def viou_pairs_ref(args):
+    """``viou_ref`` (the port of evaluation/common.py:65-106, pure Python per frame) for a list of ordered pairs of
+    one video: ``args = (boxes [N, T, 4], span [N, 2], pairs [M, 2])`` -> ``[M]`` float64.  A top-level function
+    of numpy-only code, so that a process pool can map it (the reference calls ``viou`` once per trajectory pair)."""
+    boxes, span, pairs = args
+    trajs = [[[float(c) for c in row] for row in boxes[i, int(span[i, 0]):int(span[i, 1])]] for i in range(boxes.shape[0])]
+    out = np.zeros(len(pairs), dtype=np.float64)
+    for j, (s, o) in enumerate(pairs):
+        s, o = int(s), int(o)
+        out[j] = viou_ref(trajs[s], (int(span[s, 0]), int(span[s, 1])), trajs[o], (int(span[o, 0]), int(span[o, 1])))
+    return out

@@ -171,6 +171,57 @@ def decode_spans_f64(reg: np.ndarray, sizes, stride: float) -> np.ndarray:
 
 
 # ---------------------------------------------------------------------------
+# a12 + [SPEC] s8: span suppression and top-n.  lib/modeling/relpn/rel_nms.py:6-15 carries the
+# parameters (nms_threshold 0.5, top_k_proposals = NUM_DURATION_PROPOSALS) but its forward is a
+# stub, so THIS function is the definition ("parity unpinned by the reference").
+# ---------------------------------------------------------------------------
+def select_spans(cands, windows, n_keep: int = 64, nms_threshold: float = 0.5, n_cand=None):
+    """Greedy temporal NMS + top-``n_keep`` per row, integers only.
+
+    ``cands [R, M, 2]`` int (start, end) in the decode's order (location major, anchor minor), ``windows
+    [R, 2]`` the pairs' temporal overlap windows (empty window: ``end <= start``), ``n_cand [R]`` the number
+    of valid candidates of each row (default M).  Rank key of candidate i: ``q_i = floor(2^15 * inter / union)``
+    of its span with the window, ties to the lower i.  Repeatedly keep the best live candidate and drop every
+    live candidate j with ``inter(j, kept) * 1024 > round(1024 * thr) * union(j, kept)``.
+    Returns ``(kept [R, n_keep, 2] int32 zero padded, counts [R] int32)``.
+    """
+    c = np.asarray(cands, dtype=np.int64)
+    r_n, m = c.shape[0], c.shape[1]
+    w = np.asarray(windows, dtype=np.int64).reshape(r_n, 2)
+    wa = np.where(w[:, 1] > w[:, 0], w[:, 0], 0)[:, None]
+    wb = np.where(w[:, 1] > w[:, 0], w[:, 1], 0)[:, None]
+    s, e = c[:, :, 0], c[:, :, 1]
+    idx = np.arange(m, dtype=np.int64)[None, :]
+    nc = np.full(r_n, m, dtype=np.int64) if n_cand is None else np.asarray(n_cand, dtype=np.int64)
+    valid = idx < nc[:, None]
+    inter = np.clip(np.minimum(e, wb) - np.maximum(s, wa), 0, None)
+    uni = (e - s) + (wb - wa) - inter
+    q = np.where(uni > 0, (inter << 15) // np.maximum(uni, 1), 0)
+    key = np.where(valid, (1 << 28) | (q << 12) | (4095 - idx), 0)
+    thr = int(nms_threshold * 1024.0 + 0.5)
+    out = np.zeros((r_n, n_keep, 2), dtype=np.int32)
+    counts = np.zeros(r_n, dtype=np.int32)
+    rows = np.arange(r_n)
+    for k in range(n_keep):
+        best = key.max(axis=1) if m else np.zeros(r_n, dtype=np.int64)
+        alive = best > 0
+        if not alive.any():
+            break
+        i = 4095 - (best & 4095)
+        i = np.where(alive, i, 0)
+        sw, ew = s[rows, i], e[rows, i]
+        out[alive, k, 0] = sw[alive]
+        out[alive, k, 1] = ew[alive]
+        counts += alive
+        it = np.minimum(e, ew[:, None]) - np.maximum(s, sw[:, None])
+        un = (e - s) + (ew - sw)[:, None] - it
+        sup = (it > 0) & (it * 1024 > thr * un)
+        sup[rows, i] = True
+        key[sup & alive[:, None]] = 0
+    return out, counts
+
+
+# ---------------------------------------------------------------------------
 # N1: predict.py:66-117 top-K post-processing (per video)
 # ---------------------------------------------------------------------------
 def postprocess_ref(rel_logit, cls, pairs, topk_per_pair: int, topk_per_seg: int,

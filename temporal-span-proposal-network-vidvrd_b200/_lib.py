@@ -18,9 +18,10 @@ ERROR_NAMES = {-1: "TSPN_EBADARG", -2: "TSPN_ESHAPE", -3: "TSPN_EALIGN", -4: "TS
 VT_COLS = 12
 VT_N, VT_T, VT_TP, VT_TB, VT_TRK_OFF, VT_PAIR_OFF, VT_GEO_OFF, VT_ITEM_OFF, VT_BOX_OFF, VT_SCORE_OFF = range(10)
 TOT_COLS = 10
-TOT_TRACKLETS, TOT_PAIRS, TOT_GEO_FLOATS, TOT_ITEMS, TOT_BOXES, TOT_SCORES, TOT_MAX_N, TOT_MAX_T, TOT_GEO_CHUNK = range(9)
+(TOT_TRACKLETS, TOT_PAIRS, TOT_GEO_FLOATS, TOT_ITEMS, TOT_BOXES, TOT_SCORES, TOT_MAX_N, TOT_MAX_T, TOT_GEO_CHUNK,
+ TOT_MAX_CHUNKS) = range(10)
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 GEO_OBJ_GROUP = 32        # include/tspn_b200.h: objects per work item of the pair-geometry kernel
 GEO_CHANNELS = 8
 MOTION_DIM = 4000
@@ -28,13 +29,13 @@ REL_DIM = 3000
 VIOU_FULL, VIOU_CLIPPED = 0, 1
 GEO_DENSE_CTAS = 2
 GEO_PHASE_PRE, GEO_PHASE_MAIN, GEO_PHASE_POST = 8, 16, 32
-GEO_SINGLE_CHUNK = 64
 GEO_PERSISTENT = 128
 GEO_RESERVE_SHIFT = 16
 TOPK_KEEP_DIAGONAL, TOPK_EXCLUDE_DIAGONAL = 0, 1
 PREC_FP32_EXACT, PREC_TENSOR = 0, 1
 AFFINE_RAW = 1
 AFFINE_BACKGROUND = 2
+SPANS_I16 = 1
 
 P = c_void_p      # device pointers travel as integers (tensor.data_ptr())
 
@@ -44,11 +45,13 @@ SIGNATURES = {
     "tspn_version": (c_int, []),
     "tspn_last_error": (c_int, [c_char_p, c_int]),
     "tspn_check_device": (c_int, []),
-    "tspn_build_video_table": (c_int, [c_int, POINTER(c_int32), POINTER(c_int32), POINTER(c_int64), POINTER(c_int64)]),
+    "tspn_build_video_table": (c_int, [c_int, POINTER(c_int32), POINTER(c_int32), c_int, c_int, POINTER(c_int64),
+                                       POINTER(c_int64)]),
     "tspn_enumerate_pairs": (c_int, [P, c_int, c_int64, P, P]),
-    "tspn_pair_geo_workspace_bytes": (c_int64, [c_int64, c_int64]),
+    "tspn_pair_geo_workspace_bytes": (c_int64, [c_int64, c_int64, c_int]),
     "tspn_geo_chunk": (c_int, [c_int64]),
-    "tspn_pair_geo_viou": (c_int, [P, c_int, c_int64, c_int, c_int64, c_int64, c_int64, P, P, P, P, P, P, c_int, P, P]),
+    "tspn_pair_geo_viou": (c_int, [P, c_int, c_int64, c_int, c_int, c_int64, c_int64, c_int64, P, P, P, P, P, P, c_int,
+                                   P, P]),
     "tspn_cubic_iou": (c_int, [P, c_int, P, c_int, c_int, P, P]),
     "tspn_viou_pairs": (c_int, [P, P, P, P, P, c_int64, c_int, P, P]),
     "tspn_viou_pairs_workspace_bytes": (c_int64, [c_int64]),
@@ -76,6 +79,8 @@ SIGNATURES = {
     "tspn_span_decode": (c_int, [P, c_int64, c_int, c_int, P, c_float, P, P]),
     "tspn_span_proposals": (c_int, [P, P, c_int64, c_int64, c_int64, c_int64, c_int, c_int, P, P, P, P, c_int, P,
                                     c_float, P, P]),
+    "tspn_span_select": (c_int, [P, c_int, c_int, P, P, c_int64, P, P, c_int64, c_int, c_int, c_float, c_int, c_float,
+                                 c_int, P, P, P]),
     "tspn_postprocess_workspace_bytes": (c_int64, [c_int64, c_int]),
     "tspn_postprocess": (c_int, [P, c_int, P, P, P, c_int64, c_int, P, c_int, P, P, c_int, c_int, c_int, P, P, P, P]),
     "tspn_survivor_rows_supported": (c_int, [c_int, c_int]),
@@ -128,16 +133,21 @@ def stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-def build_video_table(n_tracklets, n_frames):
-    """Host-side batch layout: returns (table int64 [V, VT_COLS] numpy, totals int64 [TOT_COLS])."""
+def build_video_table(n_tracklets, n_frames, table_rows: int = 0, geo_chunk: int = 0):
+    """Host-side batch layout: returns (table int64 [table_rows + 1, VT_COLS] numpy, totals int64 [TOT_COLS]).
+
+    ``table_rows`` (0 = number of videos) pads the table with empty videos; the last row is the sentinel
+    that carries the batch's true totals to the device (include/tspn_b200.h).  ``geo_chunk`` (0 = from the
+    longest video) fixes the pair kernel's chunk, as a capacity bucket does."""
     import numpy as np
     n = np.ascontiguousarray(n_tracklets, dtype=np.int32)
     t = np.ascontiguousarray(n_frames, dtype=np.int32)
     v = int(n.shape[0])
-    table = np.zeros((max(v, 1), VT_COLS), dtype=np.int64)
+    rows = int(table_rows) if table_rows else v
+    table = np.zeros((rows + 1, VT_COLS), dtype=np.int64)
     totals = np.zeros(TOT_COLS, dtype=np.int64)
     rc = load().tspn_build_video_table(
-        v, n.ctypes.data_as(POINTER(c_int32)), t.ctypes.data_as(POINTER(c_int32)),
+        v, n.ctypes.data_as(POINTER(c_int32)), t.ctypes.data_as(POINTER(c_int32)), rows, int(geo_chunk),
         table.ctypes.data_as(POINTER(c_int64)), totals.ctypes.data_as(POINTER(c_int64)))
     check(rc, "tspn_build_video_table")
-    return table[:v], totals
+    return table, totals

@@ -6,18 +6,27 @@ entry points take a *batch* of videos described by the video table of
 ``include/tspn_b200.h``.  ``HostBatch`` packs per-video arrays into pinned host buffers in
 that layout (box rows padded to a multiple of 8 frames for the TMA tile), ``DeviceBatch`` is
 its image in HBM.
+
+Real VidVRD / VidOR batches are ragged (every video has its own tracklet and frame count).  A
+``Capacity`` fixes the *sizes of the buffers and grids* of a batch - videos, tracklets, pairs,
+geometry floats, work items, boxes, scores, the pair kernel's chunk - while the table (whose sentinel
+row carries the true totals to the device) describes what is actually in it.  Every batch packed for
+the same capacity has the same arena layout and the same launch arguments, so ONE recorded CUDA graph
+serves all of them (``pipeline.GraphedStage``, ``serving.PipelinedStage``); ``pack_batches`` splits a
+list of ragged videos into such batches.
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence
+import dataclasses
+from typing import Iterable, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (TOT_BOXES, TOT_GEO_FLOATS, TOT_ITEMS, TOT_MAX_N, TOT_MAX_T, TOT_PAIRS, TOT_SCORES,
-                   TOT_TRACKLETS, VT_BOX_OFF, VT_COLS, VT_GEO_OFF, VT_N, VT_PAIR_OFF, VT_SCORE_OFF, VT_T,
-                   VT_TB, VT_TP, VT_TRK_OFF)
+from ._lib import (TOT_BOXES, TOT_COLS, TOT_GEO_CHUNK, TOT_GEO_FLOATS, TOT_ITEMS, TOT_MAX_CHUNKS, TOT_MAX_N, TOT_MAX_T,
+                   TOT_PAIRS, TOT_SCORES, TOT_TRACKLETS, VT_BOX_OFF, VT_COLS, VT_GEO_OFF, VT_N, VT_PAIR_OFF,
+                   VT_SCORE_OFF, VT_T, VT_TB, VT_TP, VT_TRK_OFF)
 
 
 def _np(x, dtype):
@@ -54,48 +63,142 @@ def _arena_views(arena: torch.Tensor, layout):
     return views
 
 
+def _exact_ints(arrays, hi) -> bool:
+    return all(a.size == 0 or (a.min() >= 0 and a.max() <= hi and np.array_equal(a, np.rint(a))) for a in arrays)
+
+
+@dataclasses.dataclass(frozen=True)
+class Capacity:
+    """Upper bounds that fix a batch's buffer sizes, grid sizes and transport dtypes (one CUDA graph per
+    capacity).  ``boxes_u16`` / ``motion_u8``: the compact host->device transport is a property of the
+    capacity, not of the data - a batch whose values do not fit raises instead of silently changing layout."""
+    videos: int
+    tracklets: int
+    pairs: int
+    geo_floats: int
+    items: int
+    boxes: int
+    scores: int
+    max_n: int
+    max_t: int
+    geo_chunk: int
+    max_chunks: int
+    n_classes: int
+    boxes_u16: bool = True
+    motion_u8: bool = True
+    has_motion: bool = True
+
+    def totals(self) -> np.ndarray:
+        """The launch totals (``TOT_*`` layout) of every batch of this capacity."""
+        tot = np.zeros(TOT_COLS, dtype=np.int64)
+        tot[TOT_TRACKLETS], tot[TOT_PAIRS], tot[TOT_GEO_FLOATS] = self.tracklets, self.pairs, self.geo_floats
+        tot[TOT_ITEMS], tot[TOT_BOXES], tot[TOT_SCORES] = self.items, self.boxes, self.scores
+        tot[TOT_MAX_N], tot[TOT_MAX_T], tot[TOT_GEO_CHUNK] = self.max_n, self.max_t, self.geo_chunk
+        tot[TOT_MAX_CHUNKS] = self.max_chunks
+        return tot
+
+    @classmethod
+    def for_shapes(cls, shapes: Sequence[Tuple[int, int]], n_classes: int, max_n: Optional[int] = None,
+                   max_t: Optional[int] = None, videos: Optional[int] = None, boxes_u16: bool = True,
+                   motion_u8: bool = True, has_motion: bool = True) -> "Capacity":
+        """The tightest capacity that holds a batch of these ``(N, T)`` videos; ``max_n`` / ``max_t`` /
+        ``videos`` may be raised to the bounds of a whole bucket (they select kernel variants and size
+        per-video outputs, not memory per pair)."""
+        n = [int(s[0]) for s in shapes]
+        t = [int(s[1]) for s in shapes]
+        mt = max([max_t or 1] + t)
+        chunk = int(_lib.load().tspn_geo_chunk(mt))
+        _, tot = _lib.build_video_table(n, t, geo_chunk=chunk)
+        return cls(videos=max(videos or 0, len(n), 1), tracklets=int(tot[TOT_TRACKLETS]), pairs=int(tot[TOT_PAIRS]),
+                   geo_floats=int(tot[TOT_GEO_FLOATS]), items=int(tot[TOT_ITEMS]), boxes=int(tot[TOT_BOXES]),
+                   scores=int(tot[TOT_SCORES]), max_n=max([max_n or 0] + n), max_t=mt, geo_chunk=chunk,
+                   max_chunks=(mt + chunk - 1) // chunk, n_classes=int(n_classes), boxes_u16=bool(boxes_u16),
+                   motion_u8=bool(motion_u8), has_motion=bool(has_motion))
+
+    def grown(self, **kw) -> "Capacity":
+        return dataclasses.replace(self, **kw)
+
+    def fits(self, tot: np.ndarray, n_videos: int) -> bool:
+        return (n_videos <= self.videos and tot[TOT_TRACKLETS] <= self.tracklets and tot[TOT_PAIRS] <= self.pairs
+                and tot[TOT_GEO_FLOATS] <= self.geo_floats and tot[TOT_ITEMS] <= self.items
+                and tot[TOT_BOXES] <= self.boxes and tot[TOT_SCORES] <= self.scores and tot[TOT_MAX_N] <= self.max_n
+                and tot[TOT_MAX_T] <= self.max_t)
+
+
 class HostBatch:
     """Packed, pinned host image of a batch of videos."""
 
     def __init__(self, boxes: Sequence, span: Sequence, cls: Optional[Sequence] = None,
-                 motion: Optional[Sequence] = None, pin: bool = True, compact: bool = True):
-        """``compact``: ship boxes as u16 pixel coordinates and motion histograms as u8 counts when every
-        value is exactly representable (integer boxes in [0, 65535], integer counts in [0, 255]) - lossless,
-        expanded on the device by ``tspn_unpack_boxes_u16`` / ``tspn_normalize_motion_u8``; otherwise (or
-        with ``compact=False``) the fields travel as fp32.  The serving loop is PCIe-bound, and these two
-        fields are 99 % of a batch's bytes."""
+                 motion: Optional[Sequence] = None, pin: bool = True, compact: bool = True,
+                 capacity: Optional[Capacity] = None):
+        """``compact`` (batches without a capacity): ship boxes as u16 pixel coordinates and motion
+        histograms as u8 counts when every value is exactly representable (integer boxes in [0, 65535],
+        integer counts in [0, 255]) - lossless, expanded on the device by ``tspn_unpack_boxes_u16`` /
+        ``tspn_normalize_motion_u8``; otherwise (or with ``compact=False``) the fields travel as fp32.  The
+        serving loop is PCIe-bound, and these two fields are 99 % of a batch's bytes.
+
+        ``capacity``: pack for that capacity instead (serving: every batch of a capacity shares one arena
+        layout and one captured graph).  The transport dtypes are then the capacity's; data that does not fit
+        them - a fractional coordinate, a count above 255 - raises ``ValueError``."""
         boxes = [_np(b, np.float32) for b in boxes]
         span = [_np(s, np.int32).reshape(-1, 2) for s in span]
         assert len(boxes) == len(span)
-        self.n = [int(b.shape[0]) for b in boxes]
-        self.t = [int(b.shape[1]) if b.ndim == 3 else 1 for b in boxes]
+        n_act = [int(b.shape[0]) for b in boxes]
+        t_act = [int(b.shape[1]) if b.ndim == 3 else 1 for b in boxes]
         for b, s in zip(boxes, span):
             if b.ndim != 3 or b.shape[2] != 4 or s.shape[0] != b.shape[0]:
                 raise ValueError("boxes must be [N, T, 4] with span [N, 2]; got %s / %s" % (b.shape, s.shape))
             if s.size and (s.min() < 0 or s[:, 1].max() > b.shape[1] or (s[:, 0] > s[:, 1]).any()):
                 raise ValueError("span must satisfy 0 <= pstart <= pend <= T")
-        self.table, self.totals = _lib.build_video_table(self.n, self.t)
-        tot = self.totals
-        use_pin = pin and torch.cuda.is_available()
-        n_trk = int(tot[TOT_TRACKLETS])
         if cls is not None:
             cls = [_np(c, np.float32) for c in cls]
         if motion is not None:
             motion = [_np(m, np.float32) for m in motion]
-        def exact_ints(arrays, hi):
-            return all(a.size == 0 or (a.min() >= 0 and a.max() <= hi and np.array_equal(a, np.rint(a)))
-                       for a in arrays)
-        self.boxes_compact = bool(compact) and exact_ints(boxes, 65535)
-        self.motion_compact = bool(compact) and motion is not None and exact_ints(motion, 255)
+        self.capacity = capacity
+        self.num_real = len(n_act)
+        if capacity is None:
+            self.table, self.actual = _lib.build_video_table(n_act, t_act)
+            self.totals = self.actual
+            self.boxes_compact = bool(compact) and _exact_ints(boxes, 65535)
+            self.motion_compact = bool(compact) and motion is not None and _exact_ints(motion, 255)
+            n_cls = int(cls[0].shape[1]) if cls else 0
+            has_cls, has_motion = cls is not None, motion is not None
+            rows = len(n_act)
+        else:
+            cap = capacity
+            self.table, self.actual = _lib.build_video_table(n_act, t_act, table_rows=cap.videos,
+                                                             geo_chunk=cap.geo_chunk)
+            if not cap.fits(self.actual, len(n_act)):
+                raise ValueError("batch does not fit its capacity: totals %s (videos %d) > %s"
+                                 % (self.actual.tolist(), len(n_act), cap))
+            self.totals = cap.totals()
+            self.boxes_compact, self.motion_compact = cap.boxes_u16, cap.motion_u8 and cap.has_motion
+            if self.boxes_compact and not _exact_ints(boxes, 65535):
+                raise ValueError("this capacity ships boxes as u16 pixel coordinates, but a box coordinate is "
+                                 "fractional or outside [0, 65535]; use a capacity with boxes_u16=False")
+            if self.motion_compact and motion is not None and not _exact_ints(motion, 255):
+                raise ValueError("this capacity ships motion histograms as u8 counts, but a value is fractional "
+                                 "or above 255; use a capacity with motion_u8=False")
+            if cap.has_motion and motion is None or cls is None:
+                raise ValueError("a capacity batch carries the cls%s fields" % (" and motion" if cap.has_motion else ""))
+            if cls and int(cls[0].shape[1]) != cap.n_classes:
+                raise ValueError("cls has %d classes, the capacity %d" % (cls[0].shape[1], cap.n_classes))
+            n_cls, has_cls, has_motion, rows = cap.n_classes, True, cap.has_motion, cap.videos
+        # per-video sizes over all table rows (padding rows are empty videos)
+        self.n = n_act + [0] * (rows - len(n_act))
+        self.t = t_act + [1] * (rows - len(t_act))
+        tot = self.totals
+        use_pin = pin and torch.cuda.is_available()
+        n_trk = int(tot[TOT_TRACKLETS])
         # One pinned arena holds every field (256-byte aligned segments), so that a step's inputs cross
-        # PCIe as ONE copy; the fields below are views of it.  DeviceBatch mirrors the layout in HBM.
+        # PCIe in one piece; the fields below are views of it.  DeviceBatch mirrors the layout in HBM.
         self.layout = _arena_layout([
-            ("table", (len(self.n), VT_COLS), torch.int64),
+            ("table", (rows + 1, VT_COLS), torch.int64),
             ("boxes", (int(tot[TOT_BOXES]), 4), torch.int16 if self.boxes_compact else torch.float32),
             ("span", (n_trk, 2), torch.int32),
-            ("cls", (n_trk, int(cls[0].shape[1])), torch.float32) if cls is not None else None,
+            ("cls", (n_trk, n_cls), torch.float32) if has_cls else None,
             ("motion", (n_trk, _lib.MOTION_DIM), torch.uint8 if self.motion_compact else torch.float32)
-            if motion is not None else None,
+            if has_motion else None,
         ])
         self.arena = torch.zeros(self.layout["bytes"], dtype=torch.uint8)
         if use_pin:
@@ -114,26 +217,47 @@ class HostBatch:
             sview[int(row[VT_TRK_OFF]):int(row[VT_TRK_OFF]) + n] = s
         self.cls = views.get("cls")
         self.motion = views.get("motion")
-        if cls is not None and n_trk:
-            self.cls.numpy()[:] = np.concatenate(cls, axis=0)
-        if motion is not None and n_trk:
-            self.motion.numpy()[:] = np.concatenate(motion, axis=0)
+        n_act_trk = int(self.actual[TOT_TRACKLETS])
+        if cls is not None and n_act_trk:
+            self.cls.numpy()[:n_act_trk] = np.concatenate(cls, axis=0)
+        if motion is not None and n_act_trk and self.motion is not None:
+            self.motion.numpy()[:n_act_trk] = np.concatenate(motion, axis=0)
         self.table_t = views["table"]
         self.table_t.numpy()[:] = np.ascontiguousarray(self.table).reshape(-1, VT_COLS)
 
     @classmethod
-    def from_videos(cls, videos, pin: bool = True, compact: bool = True) -> "HostBatch":
+    def from_videos(cls, videos, pin: bool = True, compact: bool = True,
+                    capacity: Optional[Capacity] = None) -> "HostBatch":
         """From ``tspn_b200.synth.VideoTracklets`` (or anything with boxes/span/cls/motion)."""
         return cls([v.boxes for v in videos], [v.span for v in videos], [v.cls for v in videos],
-                   [v.motion for v in videos], pin=pin, compact=compact)
+                   [v.motion for v in videos], pin=pin, compact=compact, capacity=capacity)
 
     @property
     def num_videos(self) -> int:
+        """Table rows (a capacity batch counts its empty padding videos; ``num_real`` are the caller's)."""
         return len(self.n)
 
+    def used_segments(self) -> List[Tuple[int, int]]:
+        """``(offset, bytes)`` of the part of every arena field the batch actually fills: what a step copies."""
+        act = self.actual
+        used = {"table": None, "boxes": int(act[TOT_BOXES]), "span": int(act[TOT_TRACKLETS]),
+                "cls": int(act[TOT_TRACKLETS]), "motion": int(act[TOT_TRACKLETS])}
+        segs = []
+        for name, spec in self.layout.items():
+            if name == "bytes":
+                continue
+            off, shape, dtype = spec
+            rows = shape[0] if used[name] is None else min(used[name], shape[0])
+            nbytes = rows * int(np.prod(shape[1:])) * torch.empty((), dtype=dtype).element_size()
+            if nbytes:
+                segs.append((off, nbytes))
+        return segs
+
     def h2d_bytes(self) -> int:
-        """Bytes one step copies host -> device (the whole arena, alignment padding included)."""
-        return int(self.arena.numel())
+        """Bytes one step copies host -> device."""
+        if self.capacity is None:
+            return int(self.arena.numel())              # the whole arena in one copy, alignment padding included
+        return int(sum(b for _, b in self.used_segments()))
 
     def to_device(self, device="cuda", non_blocking: bool = True) -> "DeviceBatch":
         return DeviceBatch(self, device, non_blocking)
@@ -143,12 +267,12 @@ class DeviceBatch:
     """HBM-resident batch: the pointers the C ABI consumes."""
 
     def __init__(self, host: HostBatch, device="cuda", non_blocking: bool = True):
-        self.host = host
-        self.n, self.t = host.n, host.t
-        self.table_host, self.totals = host.table, host.totals
         dev = torch.device(device)
         self.device = dev
         self.layout = host.layout
+        self.capacity = host.capacity
+        self.totals = host.totals                    # launch totals: the capacity's, or the batch's own
+        self._adopt(host)
         self.arena = host.arena.to(dev, non_blocking=non_blocking)        # one H2D copy
         views = _arena_views(self.arena, self.layout)
         self.table, self.span = views["table"], views["span"]
@@ -158,28 +282,53 @@ class DeviceBatch:
             # the layout the kernels and the TMA tensor map read.  The expansion belongs to the upload, not to
             # the step: in the serving loop it runs on the H2D stream, off the kernels' critical path.
             self.boxes_u16 = views["boxes"]
-            self.boxes = torch.empty(self.boxes_u16.shape, dtype=torch.float32, device=dev)
+            self.boxes = torch.zeros(self.boxes_u16.shape, dtype=torch.float32, device=dev)
             self._unpack()
         else:
             self.boxes_u16 = None
             self.boxes = views["boxes"]
 
+    def _adopt(self, host: HostBatch) -> None:
+        self.host = host
+        self.n, self.t = host.n, host.t
+        self.num_real = host.num_real
+        self.table_host, self.actual = host.table, host.actual
+
     def _unpack(self) -> None:
-        if self.boxes_u16 is not None and self.boxes.shape[0] > 0:
+        n_boxes = int(self.actual[TOT_BOXES])
+        if self.boxes_u16 is not None and n_boxes > 0:
             with torch.cuda.device(self.device):
-                _lib.check(_lib.load().tspn_unpack_boxes_u16(self.boxes_u16.data_ptr(), self.boxes.shape[0],
-                                                             self.boxes.data_ptr(),
+                _lib.check(_lib.load().tspn_unpack_boxes_u16(self.boxes_u16.data_ptr(), n_boxes, self.boxes.data_ptr(),
                                                              torch.cuda.current_stream(self.device).cuda_stream),
                            "tspn_unpack_boxes_u16")
 
     def copy_from(self, host: HostBatch) -> "DeviceBatch":
         """Refill the device buffers from another host batch of the same layout (non-blocking, on the
-        current stream): the steady-state H2D of a serving loop."""
-        if host.n != self.n or host.t != self.t or host.layout != self.layout:
-            raise ValueError("copy_from needs a host batch with the same per-video shapes and fields")
-        self.host = host
-        self.arena.copy_(host.arena, non_blocking=True)                   # one H2D copy
+        current stream): the steady-state H2D of a serving loop.  Without a capacity the batch must have the
+        same per-video shapes; with one, any batch packed for that capacity."""
+        if host.layout != self.layout or host.capacity != self.capacity or \
+                (self.capacity is None and (host.n != self.n or host.t != self.t)):
+            raise ValueError("copy_from needs a host batch of the same capacity (or, without one, the same "
+                             "per-video shapes and fields)")
+        self._adopt(host)
+        if self.capacity is None:
+            self.arena.copy_(host.arena, non_blocking=True)               # one H2D copy
+        else:
+            for off, nbytes in host.used_segments():                      # only what the batch fills
+                self.arena[off:off + nbytes].copy_(host.arena[off:off + nbytes], non_blocking=True)
         self._unpack()
+        return self
+
+    def copy_from_device(self, other: "DeviceBatch") -> "DeviceBatch":
+        """The same refill from a batch that is already resident in HBM (device-to-device)."""
+        if other.layout != self.layout or other.capacity != self.capacity:
+            raise ValueError("copy_from_device needs a batch of the same capacity")
+        self._adopt(other.host)
+        for off, nbytes in other.host.used_segments():
+            self.arena[off:off + nbytes].copy_(other.arena[off:off + nbytes], non_blocking=True)
+        n_boxes = int(self.actual[TOT_BOXES])
+        if self.boxes_u16 is not None and n_boxes:
+            self.boxes[:n_boxes].copy_(other.boxes[:n_boxes], non_blocking=True)
         return self
 
     # sizes -----------------------------------------------------------------------------
@@ -197,6 +346,10 @@ class DeviceBatch:
     @property
     def total_tracklets(self) -> int:
         return self.total(TOT_TRACKLETS)
+
+    @property
+    def actual_pairs(self) -> int:
+        return int(self.actual[TOT_PAIRS])
 
     # per-video views -----------------------------------------------------------------------
     def pair_slice(self, v: int) -> slice:
@@ -224,3 +377,65 @@ class DeviceBatch:
     def geo_view(self, geo: torch.Tensor, v: int) -> torch.Tensor:
         """``[P, 8, T]`` view of video v's geometry (the row pad to Tp is sliced off)."""
         return self.geo_rows(geo, v)[:, :, :self.t[v]]
+
+
+# ---------------------------------------------------------------------------------------------------
+# ragged videos -> batches of a few capacities
+# ---------------------------------------------------------------------------------------------------
+T_CLASSES = (512, 1024, 2048)          # the pair kernel's chunk shapes (tspn_geo_chunk); longer videos: chunk 2048
+
+
+def t_class(t: int) -> int:
+    """The pair kernel's chunk for a video of ``t`` frames: videos are batched with others of their class,
+    because a CTA stages whole chunks of box rows - a 300-frame video in a 2048-frame chunk would read 7x the
+    bytes it uses."""
+    for c in T_CLASSES:
+        if t <= c:
+            return c
+    return T_CLASSES[-1]
+
+
+def pack_batches(shapes: Sequence[Tuple[int, int]], geo_budget_bytes: int = 4 << 30,
+                 max_videos: int = 64) -> List[Tuple[int, List[int]]]:
+    """Split ragged videos ``(N_i, T_i)`` into batches: ``[(t_class, [video indices]), ...]``.
+
+    Videos are grouped by chunk class and, inside a class, taken in descending cost order (first-fit into the
+    open batch) until the batch's geometry output (32 B per pair-frame) would exceed ``geo_budget_bytes`` or it
+    holds ``max_videos`` videos.  A video larger than the budget gets a batch of its own.  Deterministic."""
+    by_class = {}
+    for i, (n, t) in enumerate(shapes):
+        by_class.setdefault(t_class(int(t)), []).append(i)
+    out: List[Tuple[int, List[int]]] = []
+    for c in sorted(by_class):
+        def geo_bytes(i):
+            n, t = shapes[i]
+            return int(n) * max(int(n) - 1, 0) * ((int(t) + 3) // 4 * 4) * 32
+        order = sorted(by_class[c], key=lambda i: (-geo_bytes(i), i))
+        cur, cur_bytes = [], 0
+        for i in order:
+            b = geo_bytes(i)
+            if cur and (cur_bytes + b > geo_budget_bytes or len(cur) >= max_videos):
+                out.append((c, sorted(cur)))
+                cur, cur_bytes = [], 0
+            cur.append(i)
+            cur_bytes += b
+        if cur:
+            out.append((c, sorted(cur)))
+    return out
+
+
+def bucket_capacities(shapes: Sequence[Tuple[int, int]], batches: Iterable[Tuple[int, List[int]]], n_classes: int,
+                      **kw) -> dict:
+    """One ``Capacity`` per chunk class that holds every batch of that class: ``{t_class: Capacity}``."""
+    caps = {}
+    for c, vids in batches:
+        cap = Capacity.for_shapes([shapes[i] for i in vids], n_classes, max_t=c, **kw)   # chunk = the class's
+        old = caps.get(c)
+        if old is None:
+            caps[c] = cap
+        else:
+            caps[c] = Capacity(**{f.name: (max(getattr(old, f.name), getattr(cap, f.name))
+                                           if f.name not in ("n_classes", "boxes_u16", "motion_u8", "has_motion",
+                                                             "geo_chunk")
+                                           else getattr(old, f.name)) for f in dataclasses.fields(Capacity)})
+    return caps

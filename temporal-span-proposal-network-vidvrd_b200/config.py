@@ -78,8 +78,9 @@ def get_default_cfg() -> CfgNode:
                     "PRECISION": "fp32",
                     # [SPEC] s7: run the heads on the top-K survivors only (False = reference, quirk Q3)
                     "SPARSIFY": False,
-                    # [SPEC] mirror predict.py:89's wrong-row object label (quirk Q4) or fix it
-                    "FIX_OBJECT_LABEL": True},
+                    # [SPEC] quirk Q4: predict.py:89 reads the object label from the wrong pair row.  False (default) =
+                    # reference parity, the drop-in behaviour; True = the object tracklet's own label
+                    "FIX_OBJECT_LABEL": False},
         "RELPN": {
             "OBJECT_DIM": 1024,
             "USE_PPN": True,
@@ -90,7 +91,10 @@ def get_default_cfg() -> CfgNode:
                     "NUM_ANCHORS_PER_LOCATION": 4,
                     # defaults.py:66-67 holds placeholders (35 / 132); the only anchors the reference ever
                     # instantiates are anchor_generator.py:118-120: sizes (15,30,45,60), stride 7.5
-                    "ANCHOR_SIZES": [15.0, 30.0, 45.0, 60.0], "ANCHOR_STRIDE": 7.5},
+                    "ANCHOR_SIZES": [15.0, 30.0, 45.0, 60.0], "ANCHOR_STRIDE": 7.5,
+                    # rel_nms.py:10 hard-codes it; [SPEC] s8 applies it (NUM_DURATION_PROPOSALS: 0 = keep every
+                    # decoded span, no suppression)
+                    "NMS_THRESHOLD": 0.5},
         },
         "ETC": {"RANDOM_SEED": 0, "DISPLAY_FREQ": 1, "SAVE_FREQ": 20,
                 "MODEL_DUMP_FILE": "baseline_weights_epoch_100.pt"},

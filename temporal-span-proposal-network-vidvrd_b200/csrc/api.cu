@@ -112,18 +112,26 @@ int tspn_check_device(void) { return tspn::check_arch(); }
 
 int tspn_geo_chunk(int64_t max_t) { return max_t <= 512 ? 512 : (max_t <= 1024 ? 1024 : 2048); }
 
-int tspn_build_video_table(int num_videos, const int32_t* n_tracklets, const int32_t* n_frames,
-                           int64_t* table_host, int64_t* totals) {
+int tspn_build_video_table(int num_videos, const int32_t* n_tracklets, const int32_t* n_frames, int table_rows,
+                           int geo_chunk, int64_t* table_host, int64_t* totals) {
     TSPN_REQUIRE(num_videos >= 0 && (num_videos == 0 || (n_tracklets && n_frames)) && table_host && totals,
                  TSPN_EBADARG, "tspn_build_video_table: null argument");
-    int64_t trk = 0, pairs = 0, geo = 0, items = 0, boxes = 0, scores = 0, max_n = 0, max_t = 0;
+    if (table_rows == 0) table_rows = num_videos;
+    TSPN_REQUIRE(table_rows >= num_videos, TSPN_EBADARG, "tspn_build_video_table: table_rows=%d < num_videos=%d",
+                 table_rows, num_videos);
+    TSPN_REQUIRE(geo_chunk == 0 || geo_chunk == 512 || geo_chunk == 1024 || geo_chunk == 2048, TSPN_EBADARG,
+                 "tspn_build_video_table: geo_chunk=%d (0, 512, 1024 or 2048)", geo_chunk);
+    int64_t trk = 0, pairs = 0, geo = 0, items = 0, boxes = 0, scores = 0, max_n = 0, max_t = 0, max_chunks = 1;
     for (int v = 0; v < num_videos; ++v)
         if (n_frames[v] > max_t) max_t = n_frames[v];
-    const int64_t chunk = tspn_geo_chunk(max_t);
-    for (int v = 0; v < num_videos; ++v) {
-        const int64_t n = n_tracklets[v], t = n_frames[v];
-        TSPN_REQUIRE(n >= 0 && t >= 1, TSPN_ESHAPE, "video %d: need N >= 0 and T >= 1 (got N=%lld T=%lld)", v,
-                     (long long)n, (long long)t);
+    const int64_t chunk = geo_chunk ? geo_chunk : tspn_geo_chunk(max_t);
+    // rows [num_videos, table_rows): empty videos; row table_rows: the sentinel (offset columns = totals)
+    for (int v = 0; v <= table_rows; ++v) {
+        const bool real = v < num_videos;
+        const int64_t n = real ? n_tracklets[v] : 0, t = real ? n_frames[v] : (v < table_rows ? 1 : 0);
+        if (real)
+            TSPN_REQUIRE(n >= 0 && t >= 1, TSPN_ESHAPE, "video %d: need N >= 0 and T >= 1 (got N=%lld T=%lld)", v,
+                         (long long)n, (long long)t);
         const int64_t tp = (t + 3) / 4 * 4, tb = (t + 7) / 8 * 8;
         int64_t* r = table_host + (int64_t)v * TSPN_VT_COLS;
         for (int c = 0; c < TSPN_VT_COLS; ++c) r[c] = 0;
@@ -138,13 +146,15 @@ int tspn_build_video_table(int num_videos, const int32_t* n_tracklets, const int
         r[TSPN_VT_BOX_OFF] = boxes;
         r[TSPN_VT_SCORE_OFF] = scores;
         const int64_t p = n * (n - 1 > 0 ? n - 1 : 0);
+        const int64_t nchunks = (t + chunk - 1) / chunk;
         trk += n;
         pairs += p;
         geo += p * TSPN_GEO_CHANNELS * tp;
-        items += n >= 2 ? n * ((n - 1 + TSPN_GEO_OBJ_GROUP - 1) / TSPN_GEO_OBJ_GROUP) * ((t + chunk - 1) / chunk) : 0;
+        items += n >= 2 ? n * ((n - 1 + TSPN_GEO_OBJ_GROUP - 1) / TSPN_GEO_OBJ_GROUP) * nchunks : 0;
         boxes += n * tb;
         scores += n * n;
         if (n > max_n) max_n = n;
+        if (n >= 2 && nchunks > max_chunks) max_chunks = nchunks;
     }
     totals[TSPN_TOT_TRACKLETS] = trk;
     totals[TSPN_TOT_PAIRS] = pairs;
@@ -155,6 +165,7 @@ int tspn_build_video_table(int num_videos, const int32_t* n_tracklets, const int
     totals[TSPN_TOT_MAX_N] = max_n;
     totals[TSPN_TOT_MAX_T] = max_t;
     totals[TSPN_TOT_GEO_CHUNK] = chunk;
+    totals[TSPN_TOT_MAX_CHUNKS] = max_chunks;
     return TSPN_OK;
 }
 

@@ -56,6 +56,12 @@ __device__ __forceinline__ int find_video(const int64_t* __restrict__ table, int
     return lo;
 }
 
+// True total of an offset column (tracklets, pairs, geo floats, work items, boxes, scores) of the batch: the
+// sentinel row `nv` of the table (include/tspn_b200.h).  The scalar totals a launch was given are upper bounds.
+__device__ __forceinline__ int64_t table_total(const int64_t* __restrict__ table, int nv, int col) {
+    return __ldg(table + (int64_t)nv * TSPN_VT_COLS + col);
+}
+
 // ---- PTX wrappers: mbarrier, TMA ---------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -172,6 +172,7 @@ assemble_kernel(const int64_t* __restrict__ table, int nv, const float* __restri
     __shared__ float s_inv[ASM_INV_TAB];
     const int64_t r = blockIdx.x;
     const int64_t gp = rows ? rows[r] : r;
+    if (!rows && r >= table_total(table, nv, TSPN_VT_PAIR_OFF)) return;      // the grid is sized for a capacity
     float* out = feat ? feat + r * ld_feat : nullptr;
     __nv_bfloat16* outb = BF16 ? feat_bf16 + r * ld_bf16 : nullptr;
     const int C = n_classes;

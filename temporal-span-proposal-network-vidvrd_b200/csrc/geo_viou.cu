@@ -79,18 +79,13 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // ---- pre-kernel: per-tracklet volume (sum over [pstart, pend) of w*h in fp64; one 128-thread CTA per
-// tracklet, four independent loads in flight per thread, fixed combination order) and zeroing of the
-// per-pair fixed-point accumulators (grid-stride) ---------------------------------------------------
+// tracklet, four independent loads in flight per thread, fixed combination order) --------------------
 __global__ void __launch_bounds__(128) tracklet_volume_kernel(const int64_t* __restrict__ table, int nv,
-                                                              int64_t total_tracklets,
                                                               const float4* __restrict__ boxes,
                                                               const int32_t* __restrict__ span,
-                                                              double* __restrict__ vol, bool want_vol,
-                                                              unsigned long long* __restrict__ fx, int64_t n_fx) {
+                                                              double* __restrict__ vol) {
     __shared__ double part[4];
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_fx; i += (int64_t)gridDim.x * blockDim.x)
-        fx[i] = 0ull;
-    if (!want_vol) return;
+    const int64_t total_tracklets = table_total(table, nv, TSPN_VT_TRK_OFF);
     for (int64_t trk = blockIdx.x; trk < total_tracklets; trk += gridDim.x) {
         const int v = find_video(table, nv, TSPN_VT_TRK_OFF, trk);
         const int64_t* row = table + (int64_t)v * TSPN_VT_COLS;
@@ -143,7 +138,7 @@ template <int THREADS, bool WRITE_GEO, bool CLIP, bool DENSE>
 __global__ void __launch_bounds__(THREADS, GeoCfg<THREADS, DENSE>::MIN_CTAS)
 pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __restrict__ table, int nv,
                 const int32_t* __restrict__ span, float* __restrict__ geo, unsigned long long* __restrict__ fx,
-                int32_t* __restrict__ overlap, unsigned int* __restrict__ queue, unsigned int total_items) {
+                int32_t* __restrict__ overlap, unsigned int* __restrict__ queue, int max_chunks) {
     using Cfg = GeoCfg<THREADS, DENSE>;
     constexpr int GEO_CHUNK = Cfg::CHUNK, GEO_WARPS = Cfg::WARPS, GEO_STAGE_BYTES = Cfg::STAGE_BYTES;
     constexpr int GEO_TX_BYTES = Cfg::TX_BYTES, GEO_SPLIT = Cfg::SPLIT, RING = Cfg::RING;
@@ -159,6 +154,8 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
+    // the batch's true work-item count (sentinel row): the grid / queue bound of the launch is only a capacity
+    const unsigned int total_items = (unsigned int)table_total(table, nv, TSPN_VT_ITEM_OFF);
 
     if (tid == 0) {
 #pragma unroll
@@ -187,6 +184,7 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
         if (item >= total_items) break;
     } else {
         item = blockIdx.x;
+        if (item >= total_items) break;
     }
 
     // ---- decode the work item ------------------------------------------------------------------
@@ -296,12 +294,12 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
     }
     g0 += (unsigned int)nobj;
     __syncthreads();
-    // this chunk's contribution to the pair's sums: a video that fits one chunk has exactly one writer per
-    // pair, which stores (no zeroing of the accumulators needed); otherwise integer atomics onto zeroed sums
+    // this chunk's contribution to the pair's sums goes into the pair's own slot for this chunk: one writer per
+    // (pair, chunk), plain stores - nothing is zeroed beforehand and no global atomics; the finalize kernel adds
+    // the slots of a pair in ascending chunk order
     for (int i3 = tid; i3 < nobj * 3; i3 += THREADS) {
-        const unsigned long long val = acc[i3];
-        if (nchunks == 1) fx[pair0 * 3 + i3] = val;
-        else if (val) atomicAdd(fx + pair0 * 3 + i3, val);
+        const int q = i3 / 3, j = i3 - q * 3;
+        fx[((pair0 + q) * max_chunks + c) * 3 + j] = acc[i3];
     }
     // the pairs' temporal overlap windows ([SPEC] s3): written here so that feature assembly and the records
     // do not wait for the per-pair finalize
@@ -317,11 +315,11 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
 // ---- post-kernel: per-pair reductions (vIoU, tIoU; the pair kernel writes the overlap windows) ----------
 template <bool CLIP>
 __global__ void __launch_bounds__(256)
-pair_finalize_kernel(const int64_t* __restrict__ table, int nv, int64_t total_pairs, const int32_t* __restrict__ span,
-                     const double* __restrict__ vol, const unsigned long long* __restrict__ fx,
-                     float* __restrict__ viou, float* __restrict__ tiou) {
+pair_finalize_kernel(const int64_t* __restrict__ table, int nv, const int32_t* __restrict__ span,
+                     const double* __restrict__ vol, const unsigned long long* __restrict__ fx, int geo_chunk,
+                     int max_chunks, float* __restrict__ viou, float* __restrict__ tiou) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= total_pairs) return;
+    if (p >= table_total(table, nv, TSPN_VT_PAIR_OFF)) return;
     const int v = find_video(table, nv, TSPN_VT_PAIR_OFF, p);
     const int64_t* row = table + (int64_t)v * TSPN_VT_COLS;
     const int n1 = (int)row[TSPN_VT_N] - 1;
@@ -334,9 +332,20 @@ pair_finalize_kernel(const int64_t* __restrict__ table, int nv, int64_t total_pa
     const int a = max(ps, qs), b = min(pe, qe);
     const bool has = b > a;
     const double inv_scale = 1.0 / (double)GEO_FX_SCALE;
-    const double inter = (double)fx[p * 3 + 0] * inv_scale;
-    const double vs = CLIP ? (double)fx[p * 3 + 1] * inv_scale : vol[ts];
-    const double vo = CLIP ? (double)fx[p * 3 + 2] * inv_scale : vol[to];
+    // the pair's chunk slots, ascending: integer adds, exact
+    const int nchunks = ((int)row[TSPN_VT_T] + geo_chunk - 1) / geo_chunk;
+    unsigned long long f0 = 0ull, f1 = 0ull, f2 = 0ull;
+    for (int c = 0; c < nchunks; ++c) {
+        const unsigned long long* slot = fx + (p * max_chunks + c) * 3;
+        f0 += slot[0];
+        if (CLIP) {
+            f1 += slot[1];
+            f2 += slot[2];
+        }
+    }
+    const double inter = (double)f0 * inv_scale;
+    const double vs = CLIP ? (double)f1 * inv_scale : vol[ts];
+    const double vo = CLIP ? (double)f2 * inv_scale : vol[to];
     const double den = vs + vo - inter;
     const int ov = has ? b - a : 0;
     const int tden = (pe - ps) + (qe - qs) - ov;
@@ -486,7 +495,7 @@ __global__ void __launch_bounds__(128) viou_pairs_f64_kernel(const float4* __res
 __global__ void __launch_bounds__(256) enumerate_pairs_kernel(const int64_t* __restrict__ table, int nv,
                                                               int64_t total_pairs, int64_t* __restrict__ pairs) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= total_pairs) return;
+    if (p >= total_pairs || p >= table_total(table, nv, TSPN_VT_PAIR_OFF)) return;
     const int v = find_video(table, nv, TSPN_VT_PAIR_OFF, p);
     const int64_t* row = table + (int64_t)v * TSPN_VT_COLS;
     const int64_t n1 = row[TSPN_VT_N] - 1;
@@ -503,7 +512,8 @@ __global__ void reset_queue_kernel(unsigned int* __restrict__ queue) {
 template <int THREADS, bool DENSE>
 static int launch_pair_geo(const int64_t* d_table, int num_videos, int64_t total_items, int64_t total_boxes,
                            const float* d_boxes, const int32_t* d_span, float* d_geo, unsigned long long* fx,
-                           int32_t* d_overlap, unsigned int* d_queue, int reserve, bool clip, cudaStream_t st) {
+                           int32_t* d_overlap, unsigned int* d_queue, int reserve, bool clip, int max_chunks,
+                           cudaStream_t st) {
     using Cfg = GeoCfg<THREADS, DENSE>;
     // boxes viewed as a 2-D tensor: rows of 8 boxes (32 floats = 128 B)
     CUtensorMap map;
@@ -527,7 +537,7 @@ static int launch_pair_geo(const int64_t* d_table, int num_videos, int64_t total
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));      \
         prefer_max_smem(pair_geo_kernel<THREADS, W, C, DENSE>);                                                \
         pair_geo_kernel<THREADS, W, C, DENSE><<<grid, THREADS, Cfg::SMEM_BYTES, st>>>(                         \
-            map, d_table, num_videos, d_span, d_geo, fx, d_overlap, d_queue, (unsigned)total_items);           \
+            map, d_table, num_videos, d_span, d_geo, fx, d_overlap, d_queue, max_chunks);                      \
     } while (0)
     if (d_geo) {
         if (clip) TSPN_LAUNCH_GEO(true, true); else TSPN_LAUNCH_GEO(true, false);
@@ -562,12 +572,13 @@ static inline int64_t geo_ws_vol_bytes(int64_t total_tracklets) {
     return ((total_tracklets > 0 ? total_tracklets : 1) * (int64_t)sizeof(double) + 15) / 16 * 16;
 }
 
-int64_t tspn_pair_geo_workspace_bytes(int64_t total_tracklets, int64_t total_pairs) {
-    // per-tracklet volumes | per-pair fixed-point sums | the persistent kernel's work-item queue
-    return geo_ws_vol_bytes(total_tracklets) + (total_pairs > 0 ? total_pairs : 1) * 3 * (int64_t)sizeof(uint64_t) + 16;
+int64_t tspn_pair_geo_workspace_bytes(int64_t total_tracklets, int64_t total_pairs, int max_chunks) {
+    // per-tracklet volumes | per-(pair, chunk) fixed-point sums | the persistent kernel's work-item queue
+    const int64_t mc = max_chunks > 0 ? max_chunks : 1;
+    return geo_ws_vol_bytes(total_tracklets) + (total_pairs > 0 ? total_pairs : 1) * mc * 3 * (int64_t)sizeof(uint64_t) + 16;
 }
 
-int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_items, int geo_chunk,
+int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_items, int geo_chunk, int max_chunks,
                        int64_t total_tracklets, int64_t total_pairs, int64_t total_boxes, const float* d_boxes, const int32_t* d_span,
                        float* d_geo, float* d_viou, float* d_tiou, int32_t* d_overlap, int flags, void* d_workspace,
                        void* stream) {
@@ -585,6 +596,8 @@ int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_ite
     TSPN_REQUIRE(total_items < (1ll << 31), TSPN_ESHAPE, "tspn_pair_geo_viou: too many work items");
     TSPN_REQUIRE(geo_chunk == 512 || geo_chunk == 1024 || geo_chunk == 2048, TSPN_EBADARG,
                  "tspn_pair_geo_viou: geo_chunk=%d (pass totals[TSPN_TOT_GEO_CHUNK] of tspn_build_video_table)", geo_chunk);
+    TSPN_REQUIRE(max_chunks >= 1, TSPN_EBADARG,
+                 "tspn_pair_geo_viou: max_chunks=%d (pass totals[TSPN_TOT_MAX_CHUNKS] of tspn_build_video_table)", max_chunks);
     cudaStream_t st = (cudaStream_t)stream;
     double* vol = reinterpret_cast<double*>(d_workspace);
     unsigned long long* fx =
@@ -592,34 +605,27 @@ int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_ite
     const bool clip = (flags & TSPN_VIOU_CLIPPED) != 0;
     const int phases = flags & (TSPN_GEO_PHASE_PRE | TSPN_GEO_PHASE_MAIN | TSPN_GEO_PHASE_POST);
     const bool all = phases == 0;
-    // TSPN_GEO_SINGLE_CHUNK: every video fits one chunk, so every pair's sums have exactly one writer, which
-    // stores them: nothing to zero, and PRE (then volumes only) may run concurrently with MAIN
-    const bool single_chunk = (flags & TSPN_GEO_SINGLE_CHUNK) != 0;
-    if ((all || (phases & TSPN_GEO_PHASE_PRE)) && !(single_chunk && clip)) {
-        // volumes (one CTA per tracklet) + zeroing of the fixed-point accumulators (grid-stride)
+    if ((all || (phases & TSPN_GEO_PHASE_PRE)) && !clip && total_tracklets > 0) {
+        // per-tracklet volumes over the full spans (the clipped variant sums them per pair in MAIN)
         const int64_t cap = 16 * (int64_t)num_sms();
-        const int64_t blocks_vol = clip ? 0 : total_tracklets;
-        const int64_t blocks_zero = single_chunk ? 0 : (total_pairs * 3 + 127) / 128;
-        int64_t blocks = blocks_vol > blocks_zero ? blocks_vol : blocks_zero;
-        if (blocks > cap) blocks = cap;                // both loops are grid-stride
-        if (blocks < 1) blocks = 1;
+        const int64_t blocks = total_tracklets < cap ? total_tracklets : cap;          // grid-stride
         prefer_max_smem(tracklet_volume_kernel);
-        tracklet_volume_kernel<<<(unsigned)blocks, 128, 0, st>>>(d_table, num_videos, total_tracklets,
-                                                                reinterpret_cast<const float4*>(d_boxes), d_span, vol,
-                                                                !clip, fx, single_chunk ? 0 : total_pairs * 3);
+        tracklet_volume_kernel<<<(unsigned)blocks, 128, 0, st>>>(d_table, num_videos,
+                                                                reinterpret_cast<const float4*>(d_boxes), d_span, vol);
         TSPN_CUDA_OK(cudaGetLastError());
     }
     if (all || (phases & TSPN_GEO_PHASE_MAIN)) {
         int rc = TSPN_OK;
         const bool dense = (flags & TSPN_GEO_DENSE_CTAS) != 0;
-        unsigned int* queue = (flags & TSPN_GEO_PERSISTENT) ? reinterpret_cast<unsigned int*>(fx + total_pairs * 3)
-                                                            : nullptr;
+        unsigned int* queue = (flags & TSPN_GEO_PERSISTENT)
+                                  ? reinterpret_cast<unsigned int*>(fx + total_pairs * (int64_t)max_chunks * 3)
+                                  : nullptr;
         const int reserve = (flags >> TSPN_GEO_RESERVE_SHIFT) & 0xff;
 #define TSPN_GEO_SHAPE(T)                                                                                          \
     (dense ? launch_pair_geo<T, true>(d_table, num_videos, total_items, total_boxes, d_boxes, d_span, d_geo, fx,   \
-                                      d_overlap, queue, reserve, clip, st)                                         \
+                                      d_overlap, queue, reserve, clip, max_chunks, st)                             \
            : launch_pair_geo<T, false>(d_table, num_videos, total_items, total_boxes, d_boxes, d_span, d_geo, fx,  \
-                                       d_overlap, queue, reserve, clip, st))
+                                       d_overlap, queue, reserve, clip, max_chunks, st))
         if (geo_chunk == 512) rc = TSPN_GEO_SHAPE(128);
         else if (geo_chunk == 1024) rc = TSPN_GEO_SHAPE(256);
         else rc = TSPN_GEO_SHAPE(512);
@@ -631,11 +637,11 @@ int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_ite
         prefer_max_smem(pair_finalize_kernel<true>);
         prefer_max_smem(pair_finalize_kernel<false>);
         if (clip)
-            pair_finalize_kernel<true><<<fblocks, 256, 0, st>>>(d_table, num_videos, total_pairs, d_span, vol, fx,
-                                                                d_viou, d_tiou);
+            pair_finalize_kernel<true><<<fblocks, 256, 0, st>>>(d_table, num_videos, d_span, vol, fx, geo_chunk,
+                                                                max_chunks, d_viou, d_tiou);
         else
-            pair_finalize_kernel<false><<<fblocks, 256, 0, st>>>(d_table, num_videos, total_pairs, d_span, vol, fx,
-                                                                 d_viou, d_tiou);
+            pair_finalize_kernel<false><<<fblocks, 256, 0, st>>>(d_table, num_videos, d_span, vol, fx, geo_chunk,
+                                                                 max_chunks, d_viou, d_tiou);
         TSPN_CUDA_OK(cudaGetLastError());
     }
     return TSPN_OK;

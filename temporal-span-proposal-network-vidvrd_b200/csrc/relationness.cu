@@ -117,6 +117,7 @@ pair_scores_kernel(const int64_t* __restrict__ table, int nv, const float* __res
                    const float* __restrict__ O, int C, float* __restrict__ scores) {
     extern __shared__ float srow[];     // [C]
     const int64_t trk = blockIdx.x;
+    if (trk >= table_total(table, nv, TSPN_VT_TRK_OFF)) return;      // the grid is sized for a capacity
     const int v = find_video(table, nv, TSPN_VT_TRK_OFF, trk);
     const int64_t* row = table + (int64_t)v * TSPN_VT_COLS;
     const int n = (int)row[TSPN_VT_N];

@@ -63,12 +63,6 @@ def enumerate_pairs(batch: DeviceBatch) -> torch.Tensor:
     return out
 
 
-def single_chunk(batch: DeviceBatch) -> bool:
-    """Every video of the batch fits one chunk of the pair kernel (include/tspn_b200.h, TSPN_GEO_SINGLE_CHUNK)."""
-    tot = batch.totals
-    return int(tot[_lib.TOT_MAX_T]) <= int(tot[_lib.TOT_GEO_CHUNK])
-
-
 def pair_geometry_outputs(batch: DeviceBatch, write_geo: bool = True) -> Dict[str, torch.Tensor]:
     """Caller-owned outputs and workspace of ``tspn_pair_geo_viou`` for this batch."""
     dev, tot, p = batch.device, batch.totals, batch.total_pairs
@@ -77,7 +71,8 @@ def pair_geometry_outputs(batch: DeviceBatch, write_geo: bool = True) -> Dict[st
     out["viou"] = torch.empty(p, dtype=torch.float32, device=dev)
     out["tiou"] = torch.empty(p, dtype=torch.float32, device=dev)
     out["overlap"] = torch.empty((p, 2), dtype=torch.int32, device=dev)
-    ws_bytes = load().tspn_pair_geo_workspace_bytes(batch.total_tracklets, batch.total_pairs)
+    ws_bytes = load().tspn_pair_geo_workspace_bytes(batch.total_tracklets, batch.total_pairs,
+                                                    int(tot[_lib.TOT_MAX_CHUNKS]))
     out["workspace"] = torch.empty(ws_bytes // 8, dtype=torch.float64, device=dev)
     return out
 
@@ -85,28 +80,26 @@ def pair_geometry_outputs(batch: DeviceBatch, write_geo: bool = True) -> Dict[st
 def pair_geometry_phase(batch: DeviceBatch, out: Dict[str, torch.Tensor], phase: int, clipped: bool = False,
                         dense_ctas: Optional[bool] = None, persistent: Optional[bool] = None,
                         reserve_sms: int = 0) -> None:
-    """One phase of ``tspn_pair_geo_viou`` on the current stream: ``_lib.GEO_PHASE_PRE`` (per-tracklet volumes,
-    and zeroing of the per-pair sums unless the batch is single-chunk), ``GEO_PHASE_MAIN`` (the pair kernel:
-    geometry rows, fixed-point sums, overlap windows), ``GEO_PHASE_POST`` (vIoU / tIoU), or 0 for all three.
-    On a single-chunk batch PRE may run on another stream concurrently with MAIN; POST needs both.
+    """One phase of ``tspn_pair_geo_viou`` on the current stream: ``_lib.GEO_PHASE_PRE`` (per-tracklet volumes),
+    ``GEO_PHASE_MAIN`` (the pair kernel: geometry rows, per-chunk fixed-point sums, overlap windows),
+    ``GEO_PHASE_POST`` (vIoU / tIoU), or 0 for all three.  PRE may run on another stream concurrently with MAIN
+    (every sum has a single writer, nothing is zeroed); POST needs both.
     ``reserve_sms``: SM slots the persistent pair kernel leaves to concurrent streams (TSPN_GEO_RESERVE_SHIFT)."""
     if dense_ctas is None:
         dense_ctas = os.environ.get("TSPN_GEO_DENSE", "0") == "1"
     tot = batch.totals
     flags = (_lib.VIOU_CLIPPED if clipped else _lib.VIOU_FULL) | (_lib.GEO_DENSE_CTAS if dense_ctas else 0)
-    if single_chunk(batch):
-        flags |= _lib.GEO_SINGLE_CHUNK
     if persistent is None:
         persistent = os.environ.get("TSPN_GEO_PERSISTENT", "1") == "1"
     if persistent and not dense_ctas:
         flags |= _lib.GEO_PERSISTENT | (max(0, min(int(reserve_sms), 255)) << _lib.GEO_RESERVE_SHIFT)
     check(load().tspn_pair_geo_viou(
         ptr(batch.table), batch.num_videos, int(tot[_lib.TOT_ITEMS]), int(tot[_lib.TOT_GEO_CHUNK]),
-        batch.total_tracklets, batch.total_pairs,
+        int(tot[_lib.TOT_MAX_CHUNKS]), batch.total_tracklets, batch.total_pairs,
         int(tot[_lib.TOT_BOXES]), ptr(batch.boxes), ptr(batch.span), ptr(out.get("geo")), ptr(out["viou"]),
         ptr(out["tiou"]), ptr(out["overlap"]), flags | phase, ptr(out["workspace"]), stream_ptr()),
         "tspn_pair_geo_viou")
-    _count(3 if phase == 0 else 1)      # volumes (+ accumulator zeroing), pair kernel, per-pair finalize
+    _count(3 if phase == 0 else 1)      # volumes, pair kernel (+ its queue reset), per-pair finalize
 
 
 def pair_geometry(batch: DeviceBatch, write_geo: bool = True, clipped: bool = False,
@@ -235,13 +228,28 @@ PPN_KEYS = ("sub_emb.0.weight", "sub_emb.0.bias", "sub_emb.2.weight", "sub_emb.2
             "obj_emb.0.weight", "obj_emb.0.bias", "obj_emb.2.weight", "obj_emb.2.bias")
 
 
+def _check_ppn_shapes(w, c: int) -> int:
+    """The relationness kernels contract the two embeddings over the class dimension: they need
+    ``RELPN.PPN.OUT_CHANNELS == RELPN.PPN.IN_CHANNELS == C`` (the reference's defaults, 35/35 and 80/80) and
+    raise otherwise instead of reading the weights out of bounds.  Returns the hidden width."""
+    h = int(w[0].shape[0])
+    want = {0: (h, c), 1: (h,), 2: (c, h), 3: (c,), 4: (h, c), 5: (h,), 6: (c, h), 7: (c,)}
+    for i, shape in want.items():
+        if tuple(w[i].shape) != shape:
+            raise ValueError("PPNHead weight %s has shape %s, expected %s: the CUDA relationness path needs "
+                             "RELPN.PPN.IN_CHANNELS == RELPN.PPN.OUT_CHANNELS == number of classes (%d)"
+                             % (PPN_KEYS[i], tuple(w[i].shape), shape, c))
+    return h
+
+
 def relationness(batch: DeviceBatch, weights, cls: Optional[torch.Tensor] = None) -> torch.Tensor:
     """PPNHead scores of every video, flat ``[sum N*N]`` (ppn.py:92-112).  ``weights`` is the
     8-tuple of ``PPN_KEYS`` tensors."""
     cls = batch.cls if cls is None else cls
     cls = _cuda(cls, torch.float32)
     w = [_cuda(t, torch.float32) for t in weights]
-    c, h = cls.shape[1], w[0].shape[0]
+    c = int(cls.shape[1])
+    h = _check_ppn_shapes(w, c)
     dev = cls.device
     scores = torch.empty(batch.total(_lib.TOT_SCORES), dtype=torch.float32, device=dev)
     ws = torch.empty(load().tspn_relationness_workspace_bytes(batch.total_tracklets, c, h) // 4,
@@ -261,7 +269,8 @@ def relationness_topk(batch: DeviceBatch, weights, k: int, exclude_diagonal: boo
     computed, written and ranked by one CTA.  Returns ``(scores, idx, val, row)``, bit-identical to the two calls."""
     cls = _cuda(batch.cls, torch.float32)
     w = [_cuda(t, torch.float32) for t in weights]
-    c, h = cls.shape[1], w[0].shape[0]
+    c = int(cls.shape[1])
+    h = _check_ppn_shapes(w, c)
     dev, v = cls.device, batch.num_videos
     scores = torch.empty(batch.total(_lib.TOT_SCORES), dtype=torch.float32, device=dev)
     ws = torch.empty(load().tspn_relationness_workspace_bytes(batch.total_tracklets, c, h) // 4,
@@ -518,6 +527,35 @@ def span_decode(reg: torch.Tensor, sizes: torch.Tensor, stride: float) -> torch.
                                   stream_ptr()), "tspn_span_decode")
     _count(1)
     return out
+
+
+def span_select(cands: torch.Tensor, n_anchors: int, stride: float, n_keep: int = 64, nms_threshold: float = 0.5,
+                batch: Optional[DeviceBatch] = None, rows: Optional[torch.Tensor] = None,
+                windows: Optional[torch.Tensor] = None, int16: bool = True):
+    """Temporal NMS + top-``n_keep`` of decoded span proposals ([SPEC] s8; what ``RelNMS``,
+    lib/modeling/relpn/rel_nms.py:6-15, is meant to do).  ``cands [n_rows, M, 2]`` int32.
+
+    With ``batch``: row r scores global pair row ``rows[r]`` (``None`` = r, negative = padding), has
+    ``locations(T_video) * n_anchors`` candidates and - unless ``windows`` is given - the temporal overlap window
+    of its two tracklets.  Without: every row has ``M`` candidates and the window ``windows[r]``.
+    Returns ``(kept [n_rows, n_keep, 2] int16 | int32 zero padded, counts [n_rows] int32)``."""
+    cands = _cuda(cands, torch.int32)
+    n_rows, m = int(cands.shape[0]), int(cands.shape[1])
+    dev = cands.device
+    out = torch.empty((n_rows, n_keep, 2), dtype=torch.int16 if int16 else torch.int32, device=dev)
+    counts = torch.empty(n_rows, dtype=torch.int32, device=dev)
+    if windows is not None:
+        windows = _cuda(windows, torch.int32)
+    if rows is not None:
+        rows = _cuda(rows, torch.int64)
+    check(load().tspn_span_select(
+        ptr(batch.table) if batch is not None else None, batch.num_videos if batch is not None else 0,
+        int(batch.totals[_lib.TOT_MAX_T]) if batch is not None else 0,
+        ptr(batch.span) if batch is not None else None, ptr(rows), n_rows, ptr(windows), ptr(cands), 2 * m, m,
+        int(n_anchors), float(stride), int(n_keep), float(nms_threshold), _lib.SPANS_I16 if int16 else 0, ptr(out),
+        ptr(counts), stream_ptr()), "tspn_span_select")
+    _count(1)
+    return out, counts
 
 
 RECORD_FIELDS = ("score", "s_cls", "pred", "o_cls", "s_tid", "o_tid", "start", "end")

@@ -42,6 +42,9 @@ class StageConfig:
     materialize_features: bool = False  # tensor precision: also build the [rows, F] rows (see PairStage._decomposed)
     geo_reserve_sms: int = 8           # survivor path: SMs the persistent pair kernel leaves to the side branches
                                        # (measured on the bench workload: 0 -> 0.748 ms, 8 -> 0.735 ms, 16 -> 0.751 ms)
+    num_span_proposals: int = 0        # RELPN.DPN.NUM_DURATION_PROPOSALS (defaults.py:62 = 64): temporal NMS + top-n of
+                                       # the decoded spans ([SPEC] s8, tspn_span_select); 0 = all L*A decoded spans
+    nms_threshold: float = 0.5         # rel_nms.py:10
 
     @classmethod
     def from_cfg(cls, cfg) -> "StageConfig":
@@ -65,41 +68,100 @@ class StageConfig:
                    use_ppn=bool(rp.USE_PPN), use_dpn=bool(rp.USE_DPN),
                    sparsify=bool(opt(pr, "SPARSIFY", False)), precision=str(opt(pr, "PRECISION", "fp32")),
                    topk_per_pair=int(pr.TOPK_PER_PAIR), topk_per_video=int(pr.TOPK_PER_SEG),
-                   mirror_q4=not bool(opt(pr, "FIX_OBJECT_LABEL", True)),
-                   anchor_sizes=tuple(float(s) for s in sizes), anchor_stride=float(stride))
+                   mirror_q4=not bool(opt(pr, "FIX_OBJECT_LABEL", False)),
+                   anchor_sizes=tuple(float(s) for s in sizes), anchor_stride=float(stride),
+                   num_span_proposals=int(opt(rp.DPN, "NUM_DURATION_PROPOSALS", 0)),
+                   nms_threshold=float(opt(rp.DPN, "NMS_THRESHOLD", 0.5)))
 
 
-@dataclasses.dataclass
 class StageResult:
-    batch: DeviceBatch
-    geom: Dict[str, torch.Tensor]
-    scores: Optional[torch.Tensor]          # [sum N*N]
-    topk_idx: Optional[torch.Tensor]        # [V, K] int64, -1 padded
-    topk_score: Optional[torch.Tensor]
-    topk_row: Optional[torch.Tensor]        # [V, K] global pair rows, -1 = diagonal / padding
-    features: Optional[torch.Tensor]        # [rows, F] fp32 view
-    features_bf16: Optional[torch.Tensor]
-    rel_logits: Optional[torch.Tensor]      # [rows, R]
-    span_reg: Optional[List[torch.Tensor]]  # per video [K_v, 2A, T_v] (StageConfig.keep_span_reg only)
-    spans: Optional[List[torch.Tensor]]     # per video [K_v, L*A, 2] int32
-    k_eff: List[int]
-    sparsify: bool
-    records: Optional[torch.Tensor] = None      # [V, topk_per_video, 8] int32 (ops.RECORD_FIELDS)
-    record_counts: Optional[torch.Tensor] = None
-    span_buffers: Optional[List[torch.Tensor]] = None   # the contiguous tensors `spans` are views of
+    """Outputs of one step.  The tensors are sized for the batch's launch totals (its capacity, when it has one);
+    the per-video accessors and ``host_outputs`` slice them to what the batch actually holds, reading the sizes
+    from the batch at call time - so the result of a replayed CUDA graph always describes the batch that was
+    replayed last."""
 
-    def host_outputs(self) -> Dict[str, torch.Tensor]:
+    def __init__(self, stage: "PairStage", batch: DeviceBatch, geom: Dict[str, torch.Tensor], scores=None, topk_idx=None,
+                 topk_score=None, topk_row=None, features=None, features_bf16=None, rel_logits=None, span_reg=None,
+                 spans=None, sparsify: bool = False, records=None, record_counts=None, span_buffers=None,
+                 span_sel=None, span_counts=None):
+        self.stage, self.batch, self.geom = stage, batch, geom
+        self.scores = scores                    # [sum N*N]
+        self.topk_idx = topk_idx                # [V, K] int64, -1 padded
+        self.topk_score = topk_score
+        self.topk_row = topk_row                # [V, K] global pair rows, -1 = diagonal / padding
+        self.features = features                # [rows, F] fp32 view
+        self.features_bf16 = features_bf16
+        self.rel_logits = rel_logits            # [rows, R]
+        self.span_reg = span_reg                # per video [K_v, 2A, T_v] (StageConfig.keep_span_reg only)
+        self._spans = spans                     # per video [K_v, L*A, 2] int32 views (stored-rows path)
+        self.sparsify = sparsify
+        self.records = records                  # [V, topk_per_video, 8] int32 (ops.RECORD_FIELDS)
+        self.record_counts = record_counts
+        self.span_buffers = span_buffers        # the contiguous tensors the decoded spans are views of
+        self.span_sel = span_sel                # [rows, n_keep, 2] int16: spans kept by the NMS ([SPEC] s8)
+        self.span_counts = span_counts          # [rows] int32
+
+    @property
+    def k_eff(self) -> List[int]:
+        return self.stage.k_effective(self.batch)
+
+    @property
+    def spans(self) -> Optional[List[torch.Tensor]]:
+        """Per video the decoded spans of its scored rows: ``[K_v, L_v * A, 2]`` int32 (all anchors), or with span
+        selection ``[K_v, n_keep, 2]`` int16 (zero padded; ``span_count(v)`` gives the kept counts)."""
+        b, c = self.batch, self.stage.cfg
+        if self.span_sel is not None:
+            return [self.span_sel[self._span_rows(v)] for v in range(b.num_real)]
+        if self._spans is not None:
+            return self._spans
+        if not self.span_buffers:
+            return None
+        sp = self.span_buffers[0]               # survivor path: [V * K, L_max * A, 2]
+        k, k_eff = self.topk_row.shape[1], self.k_eff
+        a_n = sp.shape[1] // ops.span_num_locations(int(b.totals[_lib.TOT_MAX_T]), c.anchor_stride)
+        return [sp[v * k:v * k + k_eff[v], :ops.span_num_locations(b.t[v], c.anchor_stride) * a_n]
+                for v in range(b.num_real)]
+
+    def span_count(self, v: int) -> Optional[torch.Tensor]:
+        return None if self.span_counts is None else self.span_counts[self._span_rows(v)]
+
+    def _span_rows(self, v: int) -> slice:
+        """Rows of video v in the span outputs: the span head runs on the top-K proposals whenever there are any
+        (also when the predicate head scores all P pairs, quirk Q3), else on every pair."""
+        if self.topk_row is not None:
+            k = self.topk_row.shape[1]
+            return slice(v * k, v * k + self.k_eff[v])
+        return self.batch.pair_slice(v)
+
+    def _rows(self, v: int) -> slice:
+        """Scored rows of video v in the row-indexed outputs (rel_logits, span_sel, ...)."""
+        if self.sparsify:
+            k = self.topk_idx.shape[1]
+            return slice(v * k, v * k + self.k_eff[v])
+        return self.batch.pair_slice(v)
+
+    def host_outputs(self, full: bool = False) -> Dict[str, torch.Tensor]:
         """The tensors a caller reads back: what BaseModel.forward returns (proposals, spans, predicate
-        scores), the per-pair reductions and the triplet records."""
-        out = {"viou": self.geom["viou"], "tiou": self.geom["tiou"], "overlap": self.geom["overlap"]}
+        scores), the per-pair reductions and the triplet records - sliced to the batch's true sizes (``full``:
+        unsliced, i.e. sized for the batch's capacity - what a serving slot sizes its pinned buffers with)."""
+        b = self.batch
+        p, v = (b.total_pairs, b.num_videos) if full else (b.actual_pairs, b.num_real)
+        out = {"viou": self.geom["viou"][:p], "tiou": self.geom["tiou"][:p], "overlap": self.geom["overlap"][:p]}
+        rows = p
         if self.topk_idx is not None:
-            out["topk_idx"], out["topk_score"] = self.topk_idx, self.topk_score
+            out["topk_idx"], out["topk_score"] = self.topk_idx[:v], self.topk_score[:v]
+            if self.sparsify:
+                rows = v * self.topk_idx.shape[1]
         if self.rel_logits is not None:
-            out["rel_logits"] = self.rel_logits
-        for i, b in enumerate(self.span_buffers or []):
-            out["spans%d" % i] = b
+            out["rel_logits"] = self.rel_logits[:rows]
+        if self.span_sel is not None:
+            srows = v * self.topk_row.shape[1] if self.topk_row is not None else p
+            out["spans"], out["span_counts"] = self.span_sel[:srows], self.span_counts[:srows]
+        else:
+            for i, buf in enumerate(self.span_buffers or []):
+                out["spans%d" % i] = buf[:rows] if len(self.span_buffers) == 1 else buf
         if self.records is not None:
-            out["records"], out["record_counts"] = self.records, self.record_counts
+            out["records"], out["record_counts"] = self.records[:v], self.record_counts[:v]
         return out
 
     # per-video views -------------------------------------------------------------------
@@ -107,10 +169,7 @@ class StageResult:
         return None if self.topk_idx is None else self.topk_idx[v, :self.k_eff[v]]
 
     def logits(self, v: int) -> torch.Tensor:
-        if self.sparsify:
-            k = self.topk_idx.shape[1]
-            return self.rel_logits[v * k:v * k + self.k_eff[v]]
-        return self.rel_logits[self.batch.pair_slice(v)]
+        return self.rel_logits[self._rows(v)]
 
 
 def side_priority() -> int:
@@ -221,7 +280,7 @@ class PairStage:
                 scores = ops.relationness(batch, self.ppn_weights())
                 idx, val, row = ops.topk_pairs(batch, scores, c.topk, exclude_diagonal=c.sparsify)
         survivors = self._survivor_path(batch, features, heads)
-        rel16 = sp = row_bias = None
+        rel16 = sp = row_bias = rows_done = None
         if survivors:
             # nothing below reads an output of the pair kernel: relative block and span proposals come from the
             # boxes, the record windows from the spans - the whole chain stays on this branch.  The recomputation
@@ -235,6 +294,11 @@ class PairStage:
                 sw = (self.w[DPN_PREFIX + "conv.weight"], self.w[DPN_PREFIX + "conv.bias"],
                       self.w[DPN_PREFIX + "duration_pred.weight"], self.w[DPN_PREFIX + "duration_pred.bias"])
             rel16, _, sp = ops.survivor_rows(batch, row, span_weights=sw, sizes=self.sizes_dev, stride=c.anchor_stride)
+            if sp is not None and c.num_span_proposals > 0:
+                rows_done = torch.cuda.Event()
+                rows_done.record(cur)
+        terms_done = None
+        sel = sel_counts = None
         with torch.cuda.stream(second):
             if features is None:
                 if self._decomposed(features):
@@ -250,13 +314,26 @@ class PairStage:
             if survivors:
                 second.wait_event(topk_done)          # the bias rows need the terms and the top-K rows only
                 row_bias = ops.gather_pair_terms(batch, row.reshape(-1), mn[0], mn[1])
-        cur.wait_stream(second)                       # join
+                terms_done = torch.cuda.Event()
+                terms_done.record(second)
+                if rows_done is not None:
+                    # temporal NMS + top-n of the survivors' decoded spans ([SPEC] s8), beside the predicate head
+                    # and the records on the other stream; joined by _seg_tail
+                    second.wait_event(rows_done)
+                    sel, sel_counts = ops.span_select(sp, self._n_anchors(), c.anchor_stride, c.num_span_proposals,
+                                                      c.nms_threshold, batch=batch, rows=row.reshape(-1))
+        if terms_done is not None:
+            cur.wait_event(terms_done)                # join the terms; the span selection keeps running
+        else:
+            cur.wait_stream(second)                   # join
         if not torch.cuda.is_current_stream_capturing():
             for u in (mn if isinstance(mn, tuple) else (mn,)) + (row_bias,):
                 if u is not None:
                     u.record_stream(cur)              # allocated on the second side stream, consumed on this one
             if row is not None:
                 row.record_stream(second)
+            if sp is not None:
+                sp.record_stream(second)
         if survivors:
             logits = ops.predicate_head_affine(rel16, self.packed_rel, c.n_predicates, bias=self.w[CLS_PREFIX + "bias"],
                                                row_bias=row_bias, background=True)
@@ -265,8 +342,12 @@ class PairStage:
                 records, counts = ops.postprocess(batch, logits, None, c.topk_per_pair, c.topk_per_video,
                                                   rows=row.reshape(-1), row_video_off=self._row_offsets(batch),
                                                   mirror_q4=c.mirror_q4)
-            early = {"logits": logits, "records": records, "counts": counts, "spans": sp}
+            early = {"logits": logits, "records": records, "counts": counts, "spans": sp, "sel": sel,
+                     "sel_counts": sel_counts}
         return scores, idx, val, row, mn, early
+
+    def _n_anchors(self) -> int:
+        return int(self.w[DPN_PREFIX + "duration_pred.weight"].shape[0]) // 2
 
     def _row_offsets(self, batch: DeviceBatch) -> torch.Tensor:
         """First scored row of every video in sparsify mode ([V + 1] int64: v * K); built once, outside any capture."""
@@ -320,27 +401,27 @@ class PairStage:
     def _seg_tail(self, batch: DeviceBatch, features, heads, side, geom, post_done: bool = False) -> StageResult:
         c = self.cfg
         scores, idx, val, row, mn, early = side
-        k_eff = self.k_effective(batch)
+        k_eff = self.k_effective(batch)[:batch.num_real]
         sparsify = c.sparsify and c.use_ppn
         if early is not None:
             # survivor path: the heads already ran on the side branch; only the per-pair finalize is left
             if not post_done:
                 self._seg_post(batch, geom)
             torch.cuda.current_stream(batch.device).wait_stream(self._side_stream(batch.device, 1))
-            spans = span_bufs = None
             sp = early["spans"]
-            if sp is not None:
-                k, a_n = row.shape[1], sp.shape[1] // ops.span_num_locations(max(batch.t), c.anchor_stride)
-                spans = [sp[v * k:v * k + k_eff[v], :ops.span_num_locations(batch.t[v], c.anchor_stride) * a_n]
-                         for v in range(batch.num_videos)]
-                span_bufs = [sp]
-            return StageResult(batch, geom, scores, idx, val, row, None, None, early["logits"], None, spans, k_eff,
-                               sparsify, early["records"], early["counts"], span_bufs)
+            if not torch.cuda.is_current_stream_capturing():
+                for u in (early["sel"], early["sel_counts"]):
+                    if u is not None:
+                        u.record_stream(torch.cuda.current_stream(batch.device))
+            return StageResult(self, batch, geom, scores, idx, val, row, rel_logits=early["logits"], sparsify=sparsify,
+                               records=early["records"], record_counts=early["counts"],
+                               span_buffers=[sp] if sp is not None else None, span_sel=early["sel"],
+                               span_counts=early["sel_counts"])
         feats32 = feats16 = logits = None
         tensor = c.precision == "tensor"
         # The span head (HBM-bound reads of the surviving geometry rows) runs on the side stream underneath
         # the feature-row -> predicate-head chain (issue- / latency-bound), joined before the records.
-        span_reg = spans = span_bufs = None
+        span_reg = spans = span_bufs = sel = sel_counts = None
         main = torch.cuda.current_stream(batch.device)
         side_stream = self._side_stream(batch.device)
         fork_spans = heads and c.use_dpn
@@ -348,7 +429,7 @@ class PairStage:
         with torch.cuda.stream(side_stream):
             ops.pair_geometry_phase(batch, geom, _lib.GEO_PHASE_POST, clipped=c.viou_clipped)
             if fork_spans:
-                span_reg, spans, span_bufs = self._span_heads(batch, geom, row, k_eff)
+                span_reg, spans, span_bufs, sel, sel_counts = self._span_heads(batch, geom, row, k_eff)
         decomposed = self._decomposed(features)
         if decomposed:
             rows = row.reshape(-1) if sparsify else None
@@ -380,10 +461,10 @@ class PairStage:
                                                   mirror_q4=c.mirror_q4)
         main.wait_stream(side_stream)
         if fork_spans and not torch.cuda.is_current_stream_capturing():
-            for tns in (span_bufs or []) + (span_reg or []):
+            for tns in (span_bufs or []) + (span_reg or []) + [u for u in (sel, sel_counts) if u is not None]:
                 tns.record_stream(main)          # allocated on the side stream, read on the caller's
-        return StageResult(batch, geom, scores, idx, val, row, feats32, feats16, logits, span_reg, spans, k_eff,
-                           sparsify, records, counts, span_bufs)
+        return StageResult(self, batch, geom, scores, idx, val, row, feats32, feats16, logits, span_reg, spans,
+                           sparsify, records, counts, span_bufs, sel, sel_counts)
 
     def forward(self, batch: DeviceBatch, features: Optional[torch.Tensor] = None,
                 heads: bool = True, timers: Optional[dict] = None) -> StageResult:
@@ -393,7 +474,7 @@ class PairStage:
         main = torch.cuda.current_stream(batch.device)
         side_stream = self._side_stream(batch.device)
         geom = self._geo_alloc(batch, features)
-        pre_aside = ops.single_chunk(batch)           # PRE under MAIN (see _seg_geo)
+        pre_aside = True                              # PRE under MAIN: every sum has a single writer (see _seg_geo)
         side_stream.wait_stream(main)                 # fork: inputs are ready on the caller's stream
         with torch.cuda.stream(side_stream):
             if pre_aside:
@@ -421,7 +502,8 @@ class PairStage:
         return GraphedStage(self, batch, features, heads, single=single)
 
     def _span_heads(self, batch: DeviceBatch, geom, row, k_eff):
-        """DPNHead + decode on the surviving pairs of every video (rows gathered inside the kernel)."""
+        """DPNHead + decode on the scored pairs of every video (rows gathered inside the kernel), from the stored
+        geometry rows; with ``num_span_proposals`` the decoded spans then go through the temporal NMS + top-n."""
         c = self.cfg
         cw, cb = self.w[DPN_PREFIX + "conv.weight"], self.w[DPN_PREFIX + "conv.bias"]
         pw, pb = self.w[DPN_PREFIX + "duration_pred.weight"], self.w[DPN_PREFIX + "duration_pred.bias"]
@@ -429,10 +511,11 @@ class PairStage:
             raise ValueError("the pair stage feeds the span head with the %d geometry channels; "
                              "RELPN.DPN.IN_CHANNELS must be %d (got %d)" % (_lib.GEO_CHANNELS, _lib.GEO_CHANNELS,
                                                                             cw.shape[1]))
-        regs, spans, bufs = [], [], []
+        regs, spans, bufs, sels, sel_counts = [], [], [], [], []
         th = batch.table_host
-        same_t = len(set(batch.t)) == 1
-        groups = [list(range(batch.num_videos))] if same_t else [[v] for v in range(batch.num_videos)]
+        real = list(range(batch.num_real))
+        same_t = len(set(batch.t[v] for v in real)) == 1
+        groups = [real] if same_t else [[v] for v in real]
         geo = geom["geo"]
         for vids in groups:
             v0 = vids[0]
@@ -451,6 +534,16 @@ class PairStage:
                 sp = ops.span_proposals(x, cw, cb, pw, pb, self.sizes_dev, c.anchor_stride, rows=rsel, t=t,
                                         row_base=p0)
             bufs.append(sp)
+            if c.num_span_proposals > 0 and sp.shape[0] > 0:
+                grows = rsel if rsel is not None else torch.arange(p0, p0 + p_cnt, dtype=torch.int64,
+                                                                   device=batch.device)
+                so, sc = ops.span_select(sp, pw.shape[0] // 2, c.anchor_stride, c.num_span_proposals, c.nms_threshold,
+                                         batch=batch, rows=grows, windows=geom["overlap"][grows.clamp_min(0)])
+                sels.append(so)
+                sel_counts.append(sc)
+            elif c.num_span_proposals > 0:
+                sels.append(torch.zeros((0, c.num_span_proposals, 2), dtype=torch.int16, device=batch.device))
+                sel_counts.append(torch.zeros(0, dtype=torch.int32, device=batch.device))
             if row is not None:
                 k = row.shape[1]
                 for j, v in enumerate(vids):
@@ -465,7 +558,9 @@ class PairStage:
                         regs.append(reg[off:off + pv])
                     spans.append(sp[off:off + pv])
                     off += pv
-        return (regs if c.keep_span_reg else None), spans, bufs
+        sel = torch.cat(sels, dim=0) if sels else None
+        cnt = torch.cat(sel_counts, dim=0) if sel_counts else None
+        return (regs if c.keep_span_reg else None), spans, bufs, sel, cnt
 
 
 class GraphedStage:
@@ -501,7 +596,7 @@ class GraphedStage:
         # the geometry outputs are allocated outside the graphs: the PRE phase (side branch) and the pair kernel
         # (main branch) both write into them
         geom = stage._geo_alloc(batch, features)
-        pre_aside = ops.single_chunk(batch)
+        pre_aside = True
         if self.single:
             self.graph = torch.cuda.CUDAGraph()
             fork = stage._side_stream(dev)

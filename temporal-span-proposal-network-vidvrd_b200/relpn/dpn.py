@@ -39,8 +39,9 @@ class DPNHead(nn.Module):
 
 class DPN(nn.Module):
     """dpn.py:9-52.  The reference's ``forward`` raises NameError (quirk Q5) and its NMS is a stub;
-    eval here is [SPEC] s5: DPNHead on the per-frame geometry of every pair of the PairList
-    (``boxes``/``span`` fields), decoded to ``[P, L*A, 2]`` integer frame bounds."""
+    eval here is [SPEC] s5 + s8: DPNHead on the per-frame geometry of every pair of the PairList
+    (``boxes``/``span`` fields), decoded to integer frame bounds, then ``RelNMS``: ``[P, NUM_DURATION_PROPOSALS,
+    2]`` int16 (``[P, L*A, 2]`` int32, every decoded span, when ``NUM_DURATION_PROPOSALS`` is 0)."""
 
     def __init__(self, cfg, in_channels, num_windows):
         super().__init__()
@@ -52,6 +53,7 @@ class DPN(nn.Module):
             sizes, stride = [15.0 * (i + 1) for i in range(num_windows)], 7.5
         self.anchor_sizes = tuple(float(s) for s in sizes)
         self.anchor_stride = float(stride)
+        self.rel_nms.n_anchors, self.rel_nms.anchor_stride = int(num_windows), self.anchor_stride
 
     def forward(self, pair_list, target_list=None):
         if self.training:
@@ -74,6 +76,8 @@ class DPN(nn.Module):
         for v in range(batch.num_videos):
             sp = ops.span_proposals(batch.geo_rows(geom["geo"], v), cw, cb, pw, pb, sizes, self.anchor_stride,
                                     t=batch.t[v])
+            if sp.shape[0]:
+                sp = self.rel_nms(None, sp, windows=geom["overlap"][batch.pair_slice(v)])
             out.append(like_input(sp, ref.is_cuda))
         return out, {}
 

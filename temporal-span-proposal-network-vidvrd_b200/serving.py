@@ -10,19 +10,31 @@ launch- and PCIe-latency-bound, so the serving loop works on *batches of videos*
                      alternate, so the end of step i overlaps the start of step i+1
     d2h stream    :  D2H(i-1) ......................
 
-Every slot owns its device input buffers, its captured graphs (and therefore its output buffers) and
-its pinned host result buffers, so nothing is allocated in steady state.  With ``group`` the per-video
-triplet records are all-gathered across ranks after the kernels of each step (the one collective of
-the path, sharding.py) on a stream of their own: only the D2H copy of the gathered records waits for it.
+Batches are ragged in practice (every video has its own tracklet and frame count).  The loop therefore
+owns one *bucket* per ``batch.Capacity`` (normally one per chunk class of the pair kernel, see
+``batch.pack_batches``): ``depth`` slots, each with its device input buffers, its captured graph (and
+therefore its output buffers) and its pinned host result buffers.  Any batch packed for a bucket's
+capacity replays that bucket's graph - no re-capture, nothing allocated in steady state; a batch
+without a capacity gets a bucket for its exact per-video shapes.  With ``group`` the per-video triplet
+records of each step are all-gathered across ranks (the one collective of the path, sharding.py) on a
+stream of their own: only the D2H copy of the gathered records waits for it (every rank must then
+submit the same sequence of buckets).
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional
+from typing import Dict, Iterable, List, Optional, Sequence
 
 import torch
 
-from .batch import DeviceBatch, HostBatch
+from .batch import Capacity, DeviceBatch, HostBatch, bucket_capacities, pack_batches
 from .pipeline import GraphedStage, PairStage
+
+
+def bucket_key(host: HostBatch):
+    if host.capacity is not None:
+        return host.capacity
+    return ("exact", tuple(host.n), tuple(host.t), host.boxes_compact, host.motion_compact,
+            tuple(sorted(k for k in host.layout if k != "bytes")))
 
 
 class _Slot:
@@ -33,20 +45,30 @@ class _Slot:
         self.h2d_done = torch.cuda.Event()
         self.kernels_done = torch.cuda.Event()
         self.d2h_done = torch.cuda.Event()
-        self.host_out: Optional[Dict[str, torch.Tensor]] = None
+        self.pinned: Optional[Dict[str, torch.Tensor]] = None      # capacity-sized pinned result buffers
+        self.host_out: Optional[Dict[str, torch.Tensor]] = None    # views of them for the batch in flight
+        self.gathered: Optional[torch.Tensor] = None
         self.keep = None
         self.busy = False
+
+
+class _Bucket:
+    def __init__(self, slots: List[_Slot]):
+        self.slots = slots
+        self.next = 0
 
 
 class PipelinedStage:
     """``submit(host_batch)`` enqueues H2D -> kernels -> D2H for one batch and returns a ticket;
     ``wait(ticket)`` blocks until that batch's results are in pinned host memory and returns them
-    (valid until ``depth`` further submits).  All batches must have the per-video shapes of
-    ``template`` (the graphs are captured for them)."""
+    (valid until ``depth`` further submits to the same bucket).  ``templates``: one host batch per bucket
+    (a single batch is accepted too); further buckets are created on first use (which captures a graph:
+    milliseconds - pass every capacity up front to keep the steady state capture-free)."""
 
-    def __init__(self, stage: PairStage, template: HostBatch, device="cuda", depth: int = 2, graphs: bool = True,
+    def __init__(self, stage: PairStage, templates, device="cuda", depth: int = 2, graphs: bool = True,
                  group=None, compute_streams: int = 2, single_graph: bool = True):
         self.stage, self.device, self.depth, self.group = stage, torch.device(device), int(depth), group
+        self.graphs, self.single_graph = bool(graphs), bool(single_graph)
         self.main = torch.cuda.current_stream(self.device)
         # Two compute streams, used alternately: the latency-bound tail of step i (feature rows, heads,
         # records - it leaves most of the HBM bandwidth idle) runs underneath the HBM-bound geometry kernel
@@ -57,41 +79,73 @@ class PipelinedStage:
         # it would hold up the next step behind an NCCL kernel that cannot co-reside with the persistent pair
         # kernel of the step running on the other compute stream.
         self.s_comm = torch.cuda.Stream(self.device) if group is not None else None
-        self.slots: List[_Slot] = [_Slot(stage, template, self.device, graphs, single_graph) for _ in range(self.depth)]
-        self._next = 0
-        self._gathered: List[Optional[torch.Tensor]] = [None] * self.depth
+        self.buckets: Dict[object, _Bucket] = {}
+        self._submits = 0
+        self._d2h_bytes = 0
+        if isinstance(templates, HostBatch):
+            templates = [templates]
+        for t in templates:
+            self._bucket(t)
+
+    def _bucket(self, host: HostBatch) -> _Bucket:
+        key = bucket_key(host)
+        b = self.buckets.get(key)
+        if b is None:
+            b = _Bucket([_Slot(self.stage, host, self.device, self.graphs, self.single_graph)
+                         for _ in range(self.depth)])
+            self.buckets[key] = b
+        return b
+
+    @property
+    def slots(self) -> List[_Slot]:
+        """Slots of the first bucket (the only one of a fixed-shape loop)."""
+        return next(iter(self.buckets.values())).slots
 
     # ------------------------------------------------------------------------------------------
-    def submit(self, host: HostBatch) -> int:
-        i = self._next
-        self._next = (i + 1) % self.depth
-        slot = self.slots[i]
+    def submit(self, host: HostBatch, post=None):
+        """``post(result)``: optional callable run on the step's compute stream right behind its kernels (e.g. to
+        stash the records of a sharded run for the collective at the end of a pass)."""
+        bucket = self._bucket(host)
+        i = bucket.next
+        bucket.next = (i + 1) % self.depth
+        slot = bucket.slots[i]
         if slot.busy:
-            raise RuntimeError("PipelinedStage: %d batches already in flight; wait() for a ticket first" % self.depth)
+            raise RuntimeError("PipelinedStage: %d batches of this bucket already in flight; wait() for a ticket first"
+                               % self.depth)
         with torch.cuda.stream(self.s_h2d):
             self.s_h2d.wait_event(slot.kernels_done)     # the slot's previous kernels have consumed its inputs
             slot.batch.copy_from(host)
             slot.h2d_done.record(self.s_h2d)
-        main = self.compute[i % len(self.compute)]
+        main = self.compute[self._submits % len(self.compute)]
+        self._submits += 1
         with torch.cuda.stream(main):
             main.wait_event(slot.h2d_done)
             main.wait_event(slot.d2h_done)               # the slot's previous results have left the device
             res = slot.graphed.replay() if slot.graphed is not None else self.stage.forward(slot.batch)
             outs = res.host_outputs()
+            if post is not None:
+                post(res)
             slot.kernels_done.record(main)
         work = None
         if self.group is not None:                       # the one collective: top-K triplet records
             import torch.distributed as dist
             world = dist.get_world_size(self.group)
-            if self._gathered[i] is None:
-                self._gathered[i] = torch.empty((world,) + tuple(res.records.shape), dtype=res.records.dtype,
-                                                device=self.device)
+            if slot.gathered is None:
+                slot.gathered = torch.empty((world,) + tuple(res.records.shape), dtype=res.records.dtype,
+                                            device=self.device)
             with torch.cuda.stream(self.s_comm):
                 self.s_comm.wait_event(slot.kernels_done)
-                work = dist.all_gather_into_tensor(self._gathered[i], res.records, group=self.group, async_op=True)
-            outs["records_all_ranks"] = self._gathered[i]
-        if slot.host_out is None:
-            slot.host_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in outs.items()}
+                work = dist.all_gather_into_tensor(slot.gathered, res.records, group=self.group, async_op=True)
+            outs["records_all_ranks"] = slot.gathered
+        if slot.graphed is None or slot.pinned is None:
+            # first use (or eager mode, whose outputs are fresh tensors): pinned buffers of the bucket's full size
+            full = res.host_outputs(full=True)
+            if self.group is not None:
+                full["records_all_ranks"] = slot.gathered
+            if slot.pinned is None or any(k not in slot.pinned or slot.pinned[k].shape != v.shape
+                                          for k, v in full.items()):
+                slot.pinned = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in full.items()}
+        slot.host_out = {}
         with torch.cuda.stream(self.s_d2h):
             self.s_d2h.wait_event(slot.kernels_done)
             if work is not None:
@@ -99,29 +153,55 @@ class PipelinedStage:
             for k, src in outs.items():
                 if slot.graphed is None:
                     src.record_stream(self.s_d2h)
-                slot.host_out[k].copy_(src, non_blocking=True)
+                dst = slot.pinned[k][:src.shape[0]]
+                dst.copy_(src, non_blocking=True)
+                slot.host_out[k] = dst
+                self._d2h_bytes += src.numel() * src.element_size()
             slot.d2h_done.record(self.s_d2h)
         slot.keep = (res, outs)
         slot.busy = True
-        return i
+        return (bucket, i)
 
-    def wait(self, ticket: int) -> Dict[str, torch.Tensor]:
-        slot = self.slots[ticket]
+    def wait(self, ticket) -> Dict[str, torch.Tensor]:
+        bucket, i = ticket
+        slot = bucket.slots[i]
         slot.d2h_done.synchronize()
         slot.busy = False
         return slot.host_out
 
-    def run(self, hosts):
-        """Generator: results of every host batch in order, ``depth`` batches in flight."""
-        pending: List[int] = []
-        for host in hosts:
-            if len(pending) == self.depth:
+    def run(self, hosts: Iterable[HostBatch], post=None):
+        """Generator: results of every host batch in order, up to ``depth`` batches in flight.  ``post(q, result)``
+        is called for the q-th batch on its compute stream right behind its kernels (see ``submit``)."""
+        pending: List = []
+        for q, host in enumerate(hosts):
+            b = self._bucket(host)
+            # at most `depth` batches in flight, and the slot this batch will take must be free
+            while pending and (len(pending) >= self.depth or b.slots[b.next].busy):
                 yield self.wait(pending.pop(0))
-            pending.append(self.submit(host))
+            pending.append(self.submit(host, post=(lambda res, q=q: post(q, res)) if post is not None else None))
         for t in pending:
             yield self.wait(t)
 
     # ------------------------------------------------------------------------------------------
+    def d2h_total_bytes(self) -> int:
+        """Bytes copied device -> host by every batch submitted so far."""
+        return int(self._d2h_bytes)
+
     def d2h_bytes(self) -> int:
-        out = self.slots[0].host_out or {}
-        return int(sum(b.numel() * b.element_size() for b in out.values()))
+        """Bytes the last batch submitted to the first bucket's first used slot copied device -> host."""
+        for b in self.buckets.values():
+            for s in b.slots:
+                if s.host_out:
+                    return int(sum(t.numel() * t.element_size() for t in s.host_out.values()))
+        return 0
+
+
+def host_batches_for(videos: Sequence, n_classes: int, geo_budget_bytes: int = 4 << 30, max_videos: int = 64,
+                     capacities: Optional[Dict[int, Capacity]] = None, pin: bool = True):
+    """Ragged videos -> ``(host batches, [video indices of each batch], {t_class: Capacity})``: the videos are packed
+    into batches per chunk class (``batch.pack_batches``), one capacity per class holds all of them."""
+    shapes = [(int(v.boxes.shape[0]), int(v.boxes.shape[1])) for v in videos]
+    batches = pack_batches(shapes, geo_budget_bytes, max_videos)
+    caps = capacities or bucket_capacities(shapes, batches, n_classes)
+    hosts = [HostBatch.from_videos([videos[i] for i in vids], pin=pin, capacity=caps[c]) for c, vids in batches]
+    return hosts, [vids for _, vids in batches], caps

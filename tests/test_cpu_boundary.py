@@ -33,7 +33,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert re.search(r"\bT %s\b" % name, exported), name
         getattr(lib, name)
-    assert lib.tspn_version() == 4
+    assert lib.tspn_version() == _lib.ABI_VERSION == 5
 
 
 def test_sass_is_blackwell_native():
@@ -48,7 +48,7 @@ def test_sass_is_blackwell_native():
 def test_video_table_layout():
     n, t = [20, 1, 0, 5, 2, 40], [300, 10, 7, 37, 1, 1200]
     table, tot = _lib.build_video_table(n, t)
-    assert table.shape == (6, _lib.VT_COLS)
+    assert table.shape == (6 + 1, _lib.VT_COLS)             # the videos + the sentinel row
     trk = pairs = geo = boxes = scores = items = 0
     for v in range(6):
         row = table[v]
@@ -62,6 +62,21 @@ def test_video_table_layout():
         groups, chunks = -(-(n[v] - 1) // _lib.GEO_OBJ_GROUP), -(-t[v] // chunk)
         items += n[v] * groups * chunks if n[v] >= 2 else 0
     assert list(tot[:6]) == [trk, pairs, geo, items, boxes, scores] and tot[6] == 40 and tot[7] == 1200 and tot[8] == 2048
+    # the sentinel carries the totals in the offset columns (what the kernels read as the batch's true sizes)
+    sent = table[6]
+    assert [sent[c] for c in (_lib.VT_TRK_OFF, _lib.VT_PAIR_OFF, _lib.VT_GEO_OFF, _lib.VT_ITEM_OFF, _lib.VT_BOX_OFF,
+                              _lib.VT_SCORE_OFF)] == [trk, pairs, geo, items, boxes, scores]
+    assert sent[_lib.VT_N] == 0 and tot[_lib.TOT_MAX_CHUNKS] == 1
+    # padded to a capacity of 9 table rows with a fixed chunk: empty videos, then the sentinel; same offsets
+    padded, tot_p = _lib.build_video_table(n, t, table_rows=9, geo_chunk=2048)
+    assert padded.shape == (10, _lib.VT_COLS) and np.array_equal(padded[:6], table[:6]) and np.array_equal(tot_p, tot)
+    assert all(padded[v][_lib.VT_N] == 0 and padded[v][_lib.VT_PAIR_OFF] == pairs for v in (6, 7, 8, 9))
+    # a smaller chunk than the longest video: more work items and chunk slots, same everything else
+    _, tot_c = _lib.build_video_table(n, t, geo_chunk=512)
+    assert tot_c[_lib.TOT_GEO_CHUNK] == 512 and tot_c[_lib.TOT_MAX_CHUNKS] == 3 and tot_c[_lib.TOT_ITEMS] > items
+    assert _lib.build_video_table([256], [4096])[1][_lib.TOT_MAX_CHUNKS] == 2
+    with pytest.raises(RuntimeError, match="TSPN_EBADARG"):
+        _lib.build_video_table(n, t, table_rows=3)
     assert [_lib.load().tspn_geo_chunk(x) for x in (1, 512, 513, 1024, 1025, 5000)] == [512, 512, 1024, 1024, 2048, 2048]
     assert _lib.build_video_table([70, 3], [300, 20])[1][_lib.TOT_ITEMS] == 70 * 3 + 3      # three groups of <= 32
     assert boxes % 8 == 0

@@ -1,0 +1,97 @@
+"""Host logic of the ragged-batch path: capacities, packing, the span-selection oracle, CPU placement.
+No GPU: the library is only used for its host-side table builder."""
+import numpy as np
+import pytest
+
+from oracle import heads as oheads
+from tspn_b200 import _lib, affinity, synth
+from tspn_b200.batch import Capacity, HostBatch, bucket_capacities, pack_batches, t_class
+
+
+def test_pack_batches_respects_classes_and_budget():
+    shapes = synth.config_shapes("vidor_val", 0, 200)
+    batches = pack_batches(shapes, geo_budget_bytes=1 << 30, max_videos=32)
+    seen = sorted(i for _, vids in batches for i in vids)
+    assert seen == list(range(len(shapes)))                              # every video exactly once
+    for c, vids in batches:
+        assert all(t_class(shapes[i][1]) == c for i in vids) and len(vids) <= 32
+        geo = sum(shapes[i][0] * (shapes[i][0] - 1) * ((shapes[i][1] + 3) // 4 * 4) * 32 for i in vids)
+        assert geo <= (1 << 30) or len(vids) == 1                        # only a single oversized video may exceed
+    assert pack_batches(shapes, 1 << 30, 32) == batches                  # deterministic
+    assert [t_class(t) for t in (1, 512, 513, 1024, 1025, 2048, 4096)] == [512, 512, 1024, 1024, 2048, 2048, 2048]
+
+
+def test_capacity_holds_every_batch_of_its_class():
+    shapes = synth.config_shapes("vidvrd_test", 0, 60)
+    batches = pack_batches(shapes, geo_budget_bytes=64 << 20, max_videos=8)
+    caps = bucket_capacities(shapes, batches, 35)
+    for c, vids in batches:
+        cap = caps[c]
+        _, tot = _lib.build_video_table([shapes[i][0] for i in vids], [shapes[i][1] for i in vids], geo_chunk=c)
+        assert cap.geo_chunk == c and cap.fits(tot, len(vids))
+        assert cap.max_chunks == 1 and cap.max_t == c
+
+
+def test_host_batch_with_capacity_layout_and_errors():
+    c = 35
+    vids = [synth.make_video(5, 40, c, seed=1), synth.make_video(3, 70, c, seed=2)]
+    cap = Capacity.for_shapes([(9, 100), (6, 100), (4, 30)], c, videos=4)
+    a = HostBatch.from_videos(vids, pin=False, capacity=cap)
+    b = HostBatch.from_videos(vids[:1], pin=False, capacity=cap)
+    assert a.layout == b.layout and a.num_videos == b.num_videos == 4 and (a.num_real, b.num_real) == (2, 1)
+    assert a.table.shape == (5, _lib.VT_COLS) and a.n == [5, 3, 0, 0] and list(a.totals) == list(cap.totals())
+    assert a.table[4][_lib.VT_PAIR_OFF] == 5 * 4 + 3 * 2 == a.actual[_lib.TOT_PAIRS]
+    assert a.h2d_bytes() > b.h2d_bytes() and a.h2d_bytes() < a.arena.numel()
+    # the transport dtypes belong to the capacity: data that does not fit raises instead of changing the layout
+    frac = synth.make_video(4, 30, c, seed=3, integer_boxes=False)
+    with pytest.raises(ValueError, match="u16"):
+        HostBatch.from_videos([frac], pin=False, capacity=cap)
+    HostBatch.from_videos([frac], pin=False, capacity=cap.grown(boxes_u16=False))
+    big = synth.make_video(4, 30, c, seed=4)
+    big.motion[0, 0] = 300.0
+    with pytest.raises(ValueError, match="u8"):
+        HostBatch.from_videos([big], pin=False, capacity=cap)
+    with pytest.raises(ValueError, match="does not fit"):
+        HostBatch.from_videos([synth.make_video(12, 100, c, seed=5)], pin=False, capacity=cap)
+
+
+def _brute_select(c, w, n_keep, thr_q10):
+    wa, wb = (int(w[0]), int(w[1])) if w[1] > w[0] else (0, 0)
+    cand = []
+    for i, (s, e) in enumerate(c):
+        s, e = int(s), int(e)
+        inter = max(0, min(e, wb) - max(s, wa))
+        uni = (e - s) + (wb - wa) - inter
+        cand.append((-((inter << 15) // uni), i, s, e))
+    cand.sort()
+    kept = []
+    for _, i, s, e in cand:
+        if all(not (min(e, ke) - max(s, ks) > 0 and (min(e, ke) - max(s, ks)) * 1024 >
+                    thr_q10 * ((e - s) + (ke - ks) - (min(e, ke) - max(s, ks)))) for ks, ke in kept):
+            kept.append((s, e))
+            if len(kept) == n_keep:
+                break
+    return kept
+
+
+@pytest.mark.parametrize("thr", [0.3, 0.5, 0.7, 1.0])
+def test_select_spans_oracle_is_greedy_nms(thr):
+    """The vectorised oracle against a literal sort-then-scan greedy NMS."""
+    rng = np.random.Generator(np.random.PCG64(7))
+    r_n, m = 12, 200
+    s = rng.integers(0, 900, (r_n, m))
+    c = np.stack([s, s + rng.integers(1, 300, (r_n, m))], axis=-1)
+    w = np.stack([rng.integers(0, 500, r_n), rng.integers(300, 1100, r_n)], axis=1)
+    w[3] = (50, 50)                                                      # an empty window: ranked by index only
+    n_cand = rng.integers(1, m + 1, r_n)
+    out, cnt = oheads.select_spans(c, w, 16, thr, n_cand=n_cand)
+    for r in range(r_n):
+        want = _brute_select(c[r, :n_cand[r]], w[r], 16, int(thr * 1024 + 0.5))
+        assert cnt[r] == len(want)
+        np.testing.assert_array_equal(out[r, :cnt[r]], np.array(want).reshape(-1, 2))
+        assert (out[r, cnt[r]:] == 0).all()
+
+
+def test_cpulist_parsing_and_even_share(monkeypatch):
+    assert affinity._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert affinity._parse_cpulist("") == []

@@ -22,6 +22,7 @@ def _cfg(c, r, fdim, use_ppn, use_dpn, **kw):
     cfg.RELPN.PPN.IN_CHANNELS = cfg.RELPN.PPN.OUT_CHANNELS = c
     cfg.RELPN.USE_PPN, cfg.RELPN.USE_DPN = use_ppn, use_dpn
     cfg.RELPN.DPN.IN_CHANNELS = 8
+    cfg.RELPN.DPN.NUM_DURATION_PROPOSALS = kw.pop("NUM_SPANS", 0)       # 0: every decoded span, no suppression
     for k, v in kw.items():
         cfg.PREDICT[k] = v
     return cfg
@@ -124,6 +125,26 @@ def test_basemodel_full_pair_stage(sparsify):
         assert got_sp.shape == want_sp.shape and got_sp.dtype == np.int32
         np.testing.assert_array_equal(got_sp[valid], want_sp[valid])               # frame bounds bit-exact
         np.testing.assert_allclose(res.geom["viou"][res.batch.pair_slice(i)].cpu().numpy(), viou, rtol=1e-5)
+    # the same call with RelNMS active (defaults.py:62: 64 proposals, rel_nms.py:10: threshold 0.5): the kept spans
+    # are the oracle's greedy temporal NMS of the decoded spans above, bit for bit ([SPEC] s8)
+    nms = BaseModel(_cfg(c, r, fdim, True, True, SPARSIFY=sparsify, NUM_SPANS=64)).eval()
+    nms.load_state_dict(sd)
+    with torch.no_grad():
+        pp2, dp2, logits2 = nms(pls)
+    for i, v in enumerate(vids):
+        n = v.n_tracklets
+        assert torch.equal(pp2[i], pp[i]) and torch.equal(logits2[i], logits[i])
+        order = pp[i].numpy()
+        s, o = order // n, order % n
+        valid = s != o
+        rows = np.where(valid, s * (n - 1) + o - (o > s), 0)
+        ov = model.last_result.geom["overlap"][model.last_result.batch.pair_slice(i)].cpu().numpy()
+        want, want_cnt = oheads.select_spans(dp[i].numpy(), ov[rows], 64, 0.5)
+        got = dp2[i].numpy()
+        assert got.shape == (len(order), 64, 2) and got.dtype == np.int16
+        np.testing.assert_array_equal(got[valid], want[valid])
+        np.testing.assert_array_equal(nms.last_result.span_count(i).cpu().numpy()[valid], want_cnt[valid])
+        assert (got[~valid] == 0).all()
 
 
 @pytest.mark.parametrize("sparsify", [False, True])

@@ -119,8 +119,8 @@ def test_dense_and_sparse_kernel_shapes_are_bit_identical(shapes, clip):
 @pytest.mark.parametrize("clip", [False, True])
 def test_pair_geometry_phases_on_two_streams_and_stale_sums(shapes, clip):
     """The three phases of tspn_pair_geo_viou issued the way the pipeline issues them - PRE on a side stream under
-    MAIN when every video fits one chunk (TSPN_GEO_SINGLE_CHUNK: single-writer sums are stored, nothing is
-    zeroed), POST on the side stream after both - onto outputs that still hold another batch's sums and
+    MAIN (every (pair, chunk) sum has a single writer, which stores it: nothing is zeroed, also when a row spans
+    several chunks), POST on the side stream after both - onto outputs that still hold another batch's sums and
     windows: bit-identical to the one-call form on fresh outputs."""
     vids = [synth.make_video(n, t, 35, seed=s) for n, t, s in shapes]
     batch = _batch(vids)
@@ -132,13 +132,9 @@ def test_pair_geometry_phases_on_two_streams_and_stale_sums(shapes, clip):
     out["workspace"].view(torch.int64).fill_(0x0123456789abcdef)         # stale volumes and per-pair sums
     torch.cuda.synchronize()
     main, side = torch.cuda.current_stream(), torch.cuda.Stream()
-    aside = ops.single_chunk(batch)
-    assert aside == all(t <= 2048 for _, t, _ in shapes)
+    assert int(batch.totals[_lib.TOT_MAX_CHUNKS]) == max(-(-t // 2048) for _, t, _ in shapes)
     side.wait_stream(main)
-    if aside:
-        with torch.cuda.stream(side):
-            ops.pair_geometry_phase(batch, out, _lib.GEO_PHASE_PRE, clipped=clip)
-    else:
+    with torch.cuda.stream(side):
         ops.pair_geometry_phase(batch, out, _lib.GEO_PHASE_PRE, clipped=clip)
     ops.pair_geometry_phase(batch, out, _lib.GEO_PHASE_MAIN, clipped=clip)
     side.wait_stream(main)
@@ -411,7 +407,8 @@ def test_c_abi_error_codes_on_the_device():
     out = ops.pair_geometry(batch, write_geo=True)
     torch.cuda.synchronize()
     tot = batch.totals
-    args = [batch.table.data_ptr(), 1, int(tot[_lib.TOT_ITEMS]), int(tot[_lib.TOT_GEO_CHUNK]), batch.total_tracklets,
+    args = [batch.table.data_ptr(), 1, int(tot[_lib.TOT_ITEMS]), int(tot[_lib.TOT_GEO_CHUNK]),
+            int(tot[_lib.TOT_MAX_CHUNKS]), batch.total_tracklets,
             batch.total_pairs, int(tot[_lib.TOT_BOXES]), batch.boxes.data_ptr(), batch.span.data_ptr(),
             out["geo"].data_ptr(), out["viou"].data_ptr(), out["tiou"].data_ptr(), out["overlap"].data_ptr(), 0,
             out["workspace"].data_ptr(), _lib.stream_ptr()]
@@ -422,14 +419,15 @@ def test_c_abi_error_codes_on_the_device():
             a[int(i[1:])] = val
         return lib.tspn_pair_geo_viou(*a)
     assert call() == _lib.TSPN_OK
-    assert call(_7=None) == _lib.TSPN_EBADARG and "null pointer" in _lib.last_error()
-    assert call(_7=batch.boxes.data_ptr() + 4) == _lib.TSPN_EALIGN
-    assert call(_6=int(tot[_lib.TOT_BOXES]) + 1) == _lib.TSPN_ESHAPE
+    assert call(_8=None) == _lib.TSPN_EBADARG and "null pointer" in _lib.last_error()
+    assert call(_8=batch.boxes.data_ptr() + 4) == _lib.TSPN_EALIGN
+    assert call(_7=int(tot[_lib.TOT_BOXES]) + 1) == _lib.TSPN_ESHAPE
     assert call(_3=777) == _lib.TSPN_EBADARG and "geo_chunk" in _lib.last_error()
+    assert call(_4=0) == _lib.TSPN_EBADARG and "max_chunks" in _lib.last_error()
     assert call(_2=-1) == _lib.TSPN_EBADARG
     assert call(_2=0) == _lib.TSPN_OK                                   # empty batch: nothing to do
     with pytest.raises(RuntimeError, match="TSPN_EBADARG"):
-        _lib.check(call(_8=None), "tspn_pair_geo_viou")
+        _lib.check(call(_9=None), "tspn_pair_geo_viou")
     # top-K: k beyond the supported block size, predicate head: tensor precision without packed weights
     scores = torch.rand(16, device="cuda")
     idx = torch.empty((1, 2000), dtype=torch.int64, device="cuda")

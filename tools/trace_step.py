@@ -27,12 +27,14 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--eager", action="store_true")
     ap.add_argument("--no-dpn", action="store_true", help="without the span head")
+    ap.add_argument("--span-proposals", type=int, default=64, help="spans kept per pair by the NMS (0 = none)")
     args = ap.parse_args()
     spec = synth.CONFIGS["vidor_single"]
     c, r, k = spec["classes"], spec["predicates"], spec["topk"]
     n, t = spec["n"][0], spec["t"][0]
     cfg = StageConfig(n_classes=c, n_predicates=r, topk=k, use_ppn=True, use_dpn=not args.no_dpn, sparsify=True,
-                      precision="tensor", anchor_sizes=(16.0, 64.0, 256.0, 1024.0), anchor_stride=16.0)
+                      precision="tensor", anchor_sizes=(16.0, 64.0, 256.0, 1024.0), anchor_stride=16.0,
+                      num_span_proposals=args.span_proposals)
     stage = PairStage(cfg)
     stage.load_weights(synth.make_weights(c, r, synth.feature_dim(c), dpn_in=8, seed=0), "cuda")
     host = HostBatch.from_videos([synth.make_video(n, t, c, seed=i) for i in range(args.videos)], compact=True)
