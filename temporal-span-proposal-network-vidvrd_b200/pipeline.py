@@ -623,6 +623,7 @@ class GraphedStage:
                 if pre_aside:
                     stage._seg_pre(batch, geom)
                 side = stage._seg_side(batch, features, heads)
+                torch.cuda.current_stream(dev).wait_stream(stage._side_stream(dev, 1))   # the span selection's join
             with torch.cuda.graph(self.g_geo, stream=self._cap_stream):
                 stage._seg_geo(batch, geom, events=self.ev_geo, with_pre=not pre_aside,
                                reserve_sms=stage.cfg.geo_reserve_sms if side[5] is not None else 0)
