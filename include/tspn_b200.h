@@ -225,13 +225,19 @@ int tspn_assemble_features(const int64_t* d_table, int num_videos, int64_t total
  * diagonal included).  weights: sub_emb.0 [H][C],[H]; sub_emb.2 [C][H],[C]; obj_emb likewise
  * (state_dict order).  d_workspace: tspn_relationness_workspace_bytes(). */
 int64_t tspn_relationness_workspace_bytes(int64_t total_tracklets, int n_classes, int hidden);
-int tspn_relationness(const int64_t* d_table, int num_videos, int64_t total_tracklets,
+/* precision: TSPN_PREC_FP32_EXACT = CUDA cores, fixed k-ascending fma order (scores bit-identical to oracle/exact,
+ * hence a bit-exact top-K); TSPN_PREC_TENSOR = the three contractions (two MLP layers, S O^T) as tcgen05.mma with
+ * fp32 accumulators in TMEM, operands tf32 on the fp32 storage (scores within 1e-2 of the float64 definition; bf16
+ * operands measure 1.4e-2 on the test weights - see csrc/relationness_tc.cu).  max_tracklets =
+ * totals[TSPN_TOT_MAX_N]; tspn_relationness_tc_supported: N <= 256, C <= 128, H <= 128, H % 8 == 0. */
+int tspn_relationness_tc_supported(int max_tracklets, int n_classes, int hidden);
+int tspn_relationness(const int64_t* d_table, int num_videos, int64_t total_tracklets, int max_tracklets,
                       const float* d_cls, int n_classes, int hidden,
                       const float* d_sub_w0, const float* d_sub_b0,
                       const float* d_sub_w2, const float* d_sub_b2,
                       const float* d_obj_w0, const float* d_obj_b0,
                       const float* d_obj_w2, const float* d_obj_b2,
-                      float* d_scores, void* d_workspace, void* stream);
+                      float* d_scores, int precision, void* d_workspace, void* stream);
 /* PPN._forward_test (lib/modeling/relpn/ppn.py:79-90): per video the first min(K, N*N)
  * flat indices s*N+o in descending score order, ties to the lower index ([SPEC] s6).
  * d_topk_idx int64 [V][K] (-1 beyond K_eff), d_topk_score float [V][K],
@@ -243,8 +249,9 @@ int tspn_topk_pairs(const int64_t* d_table, int num_videos, const float* d_score
 /* a8 + a9 in two launches instead of three: the embedding kernel, then one CTA per video that computes the
  * video's N x N scores from the embeddings in shared memory, writes them and selects the top K from the keys it
  * has just produced.  Same outputs, bit for bit, as tspn_relationness followed by tspn_topk_pairs (k == 0: scores
- * are NOT produced - use tspn_relationness).  Supported when max_tracklets^2 <= 8192 (max_tracklets =
- * totals[TSPN_TOT_MAX_N]); otherwise use the two entry points above. */
+ * are NOT produced - use tspn_relationness).  TSPN_PREC_FP32_EXACT: supported when max_tracklets^2 <= 8192
+ * (max_tracklets = totals[TSPN_TOT_MAX_N]); otherwise use the two entry points above.  TSPN_PREC_TENSOR: see
+ * tspn_relationness_tc_supported (videos of more than 128 tracklets take a third launch for the top-K). */
 int tspn_relationness_topk_supported(int max_tracklets, int n_classes);
 int tspn_relationness_topk(const int64_t* d_table, int num_videos, int64_t total_tracklets, int max_tracklets,
                            const float* d_cls, int n_classes, int hidden,
@@ -252,8 +259,8 @@ int tspn_relationness_topk(const int64_t* d_table, int num_videos, int64_t total
                            const float* d_sub_w2, const float* d_sub_b2,
                            const float* d_obj_w0, const float* d_obj_b0,
                            const float* d_obj_w2, const float* d_obj_b2,
-                           float* d_scores, int k, int flags, int64_t* d_topk_idx, float* d_topk_score,
-                           int64_t* d_topk_row, void* d_workspace, void* stream);
+                           float* d_scores, int k, int flags, int precision, int64_t* d_topk_idx,
+                           float* d_topk_score, int64_t* d_topk_row, void* d_workspace, void* stream);
 
 /* ---- a14: predicate classifier -----------------------------------------------------------
  * RelationPredictor.forward (lib/modeling/model.py:76-88): y = sigmoid(x W^T + b).

@@ -61,11 +61,12 @@ SIGNATURES = {
     "tspn_unpack_boxes_u16": (c_int, [P, c_int64, P, P]),
     "tspn_assemble_features": (c_int, [P, c_int, c_int64, c_int, P, c_int, P, P, P, P, c_int64, P, c_int64, P, c_int64, P]),
     "tspn_relationness_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
-    "tspn_relationness": (c_int, [P, c_int, c_int64, P, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P]),
+    "tspn_relationness_tc_supported": (c_int, [c_int, c_int, c_int]),
+    "tspn_relationness": (c_int, [P, c_int, c_int64, c_int, P, c_int, c_int, P, P, P, P, P, P, P, P, P, c_int, P, P]),
     "tspn_topk_pairs": (c_int, [P, c_int, P, c_int, c_int, P, P, P, P]),
     "tspn_relationness_topk_supported": (c_int, [c_int, c_int]),
     "tspn_relationness_topk": (c_int, [P, c_int, c_int64, c_int, P, c_int, c_int, P, P, P, P, P, P, P, P, P, c_int, c_int,
-                                       P, P, P, P, P]),
+                                       c_int, P, P, P, P, P]),
     "tspn_predicate_packed_bytes": (c_int64, [c_int, c_int]),
     "tspn_pack_predicate_weights": (c_int, [P, c_int, c_int, P, P]),
     "tspn_predicate_workspace_bytes": (c_int64, [c_int64, c_int, c_int, c_int]),

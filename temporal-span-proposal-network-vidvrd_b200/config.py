@@ -76,6 +76,9 @@ def get_default_cfg() -> CfgNode:
                     # [SPEC] arithmetic of the heads: "fp32" = fixed-order CUDA cores (bit-reproducible),
                     # "tensor" = tcgen05 (bf16 / tf32 operands, fp32 accumulate)
                     "PRECISION": "fp32",
+                    # [SPEC] PPNHead arithmetic: "fp32" keeps the top-K selection bit-exact whatever PRECISION is;
+                    # "tensor" runs the relationness MLPs and S O^T on tcgen05 (scores within 1e-2)
+                    "RELATIONNESS_PRECISION": "fp32",
                     # [SPEC] s7: run the heads on the top-K survivors only (False = reference, quirk Q3)
                     "SPARSIFY": False,
                     # [SPEC] quirk Q4: predict.py:89 reads the object label from the wrong pair row.  False (default) =

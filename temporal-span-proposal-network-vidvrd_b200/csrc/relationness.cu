@@ -260,6 +260,14 @@ static int launch_embeddings(int64_t total_tracklets, const float* d_cls, int n_
     return TSPN_OK;
 }
 
+// relationness_tc.cu: the tensor-core form (TSPN_PREC_TENSOR)
+int relationness_tc_supported(int max_tracklets, int n_classes, int hidden);
+int launch_relationness_tc(const int64_t* d_table, int num_videos, int64_t total_tracklets, int max_tracklets,
+                           const float* d_cls, int C, int H, const float* sw0, const float* sb0, const float* sw2,
+                           const float* sb2, const float* ow0, const float* ob0, const float* ow2, const float* ob2,
+                           float* S, float* O, float* d_scores, int k, int exclude_diag, int64_t* d_idx,
+                           float* d_val, int64_t* d_row, bool* fused_topk, cudaStream_t st);
+
 }  // namespace tspn
 
 using namespace tspn;
@@ -272,11 +280,15 @@ int64_t tspn_relationness_workspace_bytes(int64_t total_tracklets, int n_classes
     return 2 * t * (int64_t)n_classes * (int64_t)sizeof(float);
 }
 
-int tspn_relationness(const int64_t* d_table, int num_videos, int64_t total_tracklets, const float* d_cls,
-                      int n_classes, int hidden, const float* d_sub_w0, const float* d_sub_b0,
+int tspn_relationness_tc_supported(int max_tracklets, int n_classes, int hidden) {
+    return relationness_tc_supported(max_tracklets, n_classes, hidden);
+}
+
+int tspn_relationness(const int64_t* d_table, int num_videos, int64_t total_tracklets, int max_tracklets,
+                      const float* d_cls, int n_classes, int hidden, const float* d_sub_w0, const float* d_sub_b0,
                       const float* d_sub_w2, const float* d_sub_b2, const float* d_obj_w0, const float* d_obj_b0,
-                      const float* d_obj_w2, const float* d_obj_b2, float* d_scores, void* d_workspace,
-                      void* stream) {
+                      const float* d_obj_w2, const float* d_obj_b2, float* d_scores, int precision,
+                      void* d_workspace, void* stream) {
     TSPN_ARCH_OK();
     TSPN_REQUIRE(num_videos >= 0 && total_tracklets >= 0 && n_classes > 0 && hidden > 0, TSPN_EBADARG,
                  "tspn_relationness: bad size");
@@ -288,6 +300,15 @@ int tspn_relationness(const int64_t* d_table, int num_videos, int64_t total_trac
     cudaStream_t st = (cudaStream_t)stream;
     float* S = reinterpret_cast<float*>(d_workspace);
     float* O = S + total_tracklets * n_classes;
+    if (precision == TSPN_PREC_TENSOR) {
+        TSPN_REQUIRE(relationness_tc_supported(max_tracklets, n_classes, hidden), TSPN_ESHAPE,
+                     "tspn_relationness: tensor precision needs N <= 256, C <= 128, H <= 128 and H %% 8 == 0 "
+                     "(got N=%d C=%d H=%d)", max_tracklets, n_classes, hidden);
+        bool fused = false;
+        return launch_relationness_tc(d_table, num_videos, total_tracklets, max_tracklets, d_cls, n_classes, hidden,
+                                      d_sub_w0, d_sub_b0, d_sub_w2, d_sub_b2, d_obj_w0, d_obj_b0, d_obj_w2, d_obj_b2, S,
+                                      O, d_scores, 0, 0, nullptr, nullptr, nullptr, &fused, st);
+    }
     {
         const int rc = launch_embeddings(total_tracklets, d_cls, n_classes, hidden, d_sub_w0, d_sub_b0, d_sub_w2, d_sub_b2,
                                          d_obj_w0, d_obj_b0, d_obj_w2, d_obj_b2, S, O, st);
@@ -309,14 +330,38 @@ int tspn_relationness_topk(const int64_t* d_table, int num_videos, int64_t total
                            const float* d_cls, int n_classes, int hidden, const float* d_sub_w0,
                            const float* d_sub_b0, const float* d_sub_w2, const float* d_sub_b2, const float* d_obj_w0,
                            const float* d_obj_b0, const float* d_obj_w2, const float* d_obj_b2, float* d_scores, int k,
-                           int flags, int64_t* d_topk_idx, float* d_topk_score, int64_t* d_topk_row, void* d_workspace,
-                           void* stream) {
+                           int flags, int precision, int64_t* d_topk_idx, float* d_topk_score, int64_t* d_topk_row,
+                           void* d_workspace, void* stream) {
     TSPN_ARCH_OK();
     TSPN_REQUIRE(num_videos >= 0 && total_tracklets >= 0 && n_classes > 0 && hidden > 0 && k >= 0, TSPN_EBADARG,
                  "tspn_relationness_topk: bad size");
     TSPN_REQUIRE(k <= TOPK_MAX_K, TSPN_ESHAPE, "tspn_relationness_topk: K=%d exceeds the supported maximum %d", k,
                  TOPK_MAX_K);
     if (num_videos == 0) return TSPN_OK;
+    if (precision == TSPN_PREC_TENSOR) {
+        // tcgen05 form: embeddings, then scores (+ top-K in the same CTA when every video fits one: N <= 128;
+        // larger videos: the block top-K as a third launch on the stored scores)
+        TSPN_REQUIRE(relationness_tc_supported(max_tracklets, n_classes, hidden), TSPN_ESHAPE,
+                     "tspn_relationness_topk: tensor precision needs N <= 256, C <= 128, H <= 128 and H %% 8 == 0 "
+                     "(got N=%d C=%d H=%d)", max_tracklets, n_classes, hidden);
+        TSPN_REQUIRE(d_table && d_workspace && d_topk_idx && d_topk_score && (total_tracklets == 0 || (d_cls && d_scores)),
+                     TSPN_EBADARG, "tspn_relationness_topk: null pointer");
+        cudaStream_t st = (cudaStream_t)stream;
+        float* S = reinterpret_cast<float*>(d_workspace);
+        float* O = S + total_tracklets * n_classes;
+        bool fused = false;
+        if (total_tracklets > 0) {
+            const int rc = launch_relationness_tc(d_table, num_videos, total_tracklets, max_tracklets, d_cls, n_classes,
+                                                  hidden, d_sub_w0, d_sub_b0, d_sub_w2, d_sub_b2, d_obj_w0, d_obj_b0,
+                                                  d_obj_w2, d_obj_b2, S, O, d_scores, k,
+                                                  (flags & TSPN_TOPK_EXCLUDE_DIAGONAL) ? 1 : 0, d_topk_idx, d_topk_score,
+                                                  d_topk_row, &fused, st);
+            if (rc != TSPN_OK) return rc;
+        }
+        if (!fused && k > 0)
+            return tspn_topk_pairs(d_table, num_videos, d_scores, k, flags, d_topk_idx, d_topk_score, d_topk_row, stream);
+        return TSPN_OK;
+    }
     TSPN_REQUIRE(tspn_relationness_topk_supported(max_tracklets, n_classes), TSPN_ESHAPE,
                  "tspn_relationness_topk: max_tracklets=%d not supported (use tspn_relationness + tspn_topk_pairs)",
                  max_tracklets);

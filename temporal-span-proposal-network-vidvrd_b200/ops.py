@@ -242,9 +242,16 @@ def _check_ppn_shapes(w, c: int) -> int:
     return h
 
 
-def relationness(batch: DeviceBatch, weights, cls: Optional[torch.Tensor] = None) -> torch.Tensor:
+def relationness_tc_supported(batch: DeviceBatch, hidden: int = 64) -> bool:
+    return bool(load().tspn_relationness_tc_supported(int(batch.totals[_lib.TOT_MAX_N]), int(batch.cls.shape[1]),
+                                                      int(hidden)))
+
+
+def relationness(batch: DeviceBatch, weights, cls: Optional[torch.Tensor] = None,
+                 precision: str = "fp32") -> torch.Tensor:
     """PPNHead scores of every video, flat ``[sum N*N]`` (ppn.py:92-112).  ``weights`` is the
-    8-tuple of ``PPN_KEYS`` tensors."""
+    8-tuple of ``PPN_KEYS`` tensors.  ``precision``: ``"fp32"`` (exact order, bit-reproducible) or ``"tensor"``
+    (tcgen05, tf32 operands, fp32 accumulate: within 1e-2 of the float64 definition)."""
     cls = batch.cls if cls is None else cls
     cls = _cuda(cls, torch.float32)
     w = [_cuda(t, torch.float32) for t in weights]
@@ -254,19 +261,23 @@ def relationness(batch: DeviceBatch, weights, cls: Optional[torch.Tensor] = None
     scores = torch.empty(batch.total(_lib.TOT_SCORES), dtype=torch.float32, device=dev)
     ws = torch.empty(load().tspn_relationness_workspace_bytes(batch.total_tracklets, c, h) // 4,
                      dtype=torch.float32, device=dev)
-    check(load().tspn_relationness(ptr(batch.table), batch.num_videos, batch.total_tracklets, ptr(cls), c, h,
-                                   *[ptr(t) for t in w], ptr(scores), ptr(ws), stream_ptr()), "tspn_relationness")
+    check(load().tspn_relationness(ptr(batch.table), batch.num_videos, batch.total_tracklets,
+                                   int(batch.totals[_lib.TOT_MAX_N]), ptr(cls), c, h, *[ptr(t) for t in w],
+                                   ptr(scores), PREC[precision], ptr(ws), stream_ptr()), "tspn_relationness")
     _count(2)
     return scores
 
 
-def relationness_topk_supported(batch: DeviceBatch) -> bool:
+def relationness_topk_supported(batch: DeviceBatch, precision: str = "fp32", hidden: int = 64) -> bool:
+    if PREC[precision] == _lib.PREC_TENSOR:
+        return relationness_tc_supported(batch, hidden)
     return bool(load().tspn_relationness_topk_supported(int(batch.totals[_lib.TOT_MAX_N]), int(batch.cls.shape[1])))
 
 
-def relationness_topk(batch: DeviceBatch, weights, k: int, exclude_diagonal: bool = False):
+def relationness_topk(batch: DeviceBatch, weights, k: int, exclude_diagonal: bool = False, precision: str = "fp32"):
     """``relationness`` + ``topk_pairs`` in two launches (``tspn_relationness_topk``): the scores of a video are
-    computed, written and ranked by one CTA.  Returns ``(scores, idx, val, row)``, bit-identical to the two calls."""
+    computed, written and ranked by one CTA.  Returns ``(scores, idx, val, row)``; in ``"fp32"`` precision
+    bit-identical to the two calls."""
     cls = _cuda(batch.cls, torch.float32)
     w = [_cuda(t, torch.float32) for t in weights]
     c = int(cls.shape[1])
@@ -281,9 +292,9 @@ def relationness_topk(batch: DeviceBatch, weights, k: int, exclude_diagonal: boo
     check(load().tspn_relationness_topk(
         ptr(batch.table), v, batch.total_tracklets, int(batch.totals[_lib.TOT_MAX_N]), ptr(cls), c, h,
         *[ptr(t) for t in w], ptr(scores), k,
-        _lib.TOPK_EXCLUDE_DIAGONAL if exclude_diagonal else _lib.TOPK_KEEP_DIAGONAL, ptr(idx), ptr(val), ptr(row),
-        ptr(ws), stream_ptr()), "tspn_relationness_topk")
-    _count(2)
+        _lib.TOPK_EXCLUDE_DIAGONAL if exclude_diagonal else _lib.TOPK_KEEP_DIAGONAL, PREC[precision], ptr(idx),
+        ptr(val), ptr(row), ptr(ws), stream_ptr()), "tspn_relationness_topk")
+    _count(2 if PREC[precision] != _lib.PREC_TENSOR or int(batch.totals[_lib.TOT_MAX_N]) <= 128 else 3)
     return scores, idx, val, row
 
 

@@ -30,6 +30,8 @@ class StageConfig:
     use_dpn: bool = True
     sparsify: bool = False
     precision: str = "fp32"            # "fp32" (exact order) | "tensor" (tcgen05)
+    relationness_precision: str = "fp32"   # PPNHead: "fp32" = exact order, hence a bit-exact top-K selection (also
+                                           # when the heads run in tensor precision); "tensor" = tcgen05 (tf32 operands)
     write_geo: bool = True
     anchor_sizes: tuple = (15.0, 30.0, 45.0, 60.0)
     anchor_stride: float = 7.5
@@ -67,6 +69,7 @@ class StageConfig:
                    hidden=int(rp.PPN.HIDDEN_CHANNELS), topk=int(rp.PPN.NUM_PAIR_PROPOSALS),
                    use_ppn=bool(rp.USE_PPN), use_dpn=bool(rp.USE_DPN),
                    sparsify=bool(opt(pr, "SPARSIFY", False)), precision=str(opt(pr, "PRECISION", "fp32")),
+                   relationness_precision=str(opt(pr, "RELATIONNESS_PRECISION", "fp32")),
                    topk_per_pair=int(pr.TOPK_PER_PAIR), topk_per_video=int(pr.TOPK_PER_SEG),
                    mirror_q4=not bool(opt(pr, "FIX_OBJECT_LABEL", False)),
                    anchor_sizes=tuple(float(s) for s in sizes), anchor_stride=float(stride),
@@ -188,8 +191,7 @@ class PairStage:
         self.w: Dict[str, torch.Tensor] = {}
         self.packed_cls: Optional[torch.Tensor] = None
         self.sizes_dev: Optional[torch.Tensor] = None
-        self._row_off: Optional[torch.Tensor] = None
-        self._row_off_k = None
+        self._row_off: Dict[tuple, torch.Tensor] = {}
         self._side: Dict[str, torch.cuda.Stream] = {}
 
     # ---- weights -------------------------------------------------------------------------
@@ -272,12 +274,15 @@ class PairStage:
         second = self._side_stream(batch.device, 1)
         second.wait_stream(cur)                       # fork
         if c.use_ppn:
-            if c.topk > 0 and batch.cls is not None and ops.relationness_topk_supported(batch) \
+            rp = c.relationness_precision
+            if rp != "fp32" and not (batch.cls is not None and ops.relationness_tc_supported(batch, c.hidden)):
+                rp = "fp32"                           # shapes the tensor-core form does not cover: exact order
+            if c.topk > 0 and batch.cls is not None and ops.relationness_topk_supported(batch, rp, c.hidden) \
                     and os.environ.get("TSPN_FUSED_TOPK", "1") == "1":
                 scores, idx, val, row = ops.relationness_topk(batch, self.ppn_weights(), c.topk,
-                                                              exclude_diagonal=c.sparsify)
+                                                              exclude_diagonal=c.sparsify, precision=rp)
             else:
-                scores = ops.relationness(batch, self.ppn_weights())
+                scores = ops.relationness(batch, self.ppn_weights(), precision=rp)
                 idx, val, row = ops.topk_pairs(batch, scores, c.topk, exclude_diagonal=c.sparsify)
         survivors = self._survivor_path(batch, features, heads)
         rel16 = sp = row_bias = rows_done = None
@@ -350,12 +355,17 @@ class PairStage:
         return int(self.w[DPN_PREFIX + "duration_pred.weight"].shape[0]) // 2
 
     def _row_offsets(self, batch: DeviceBatch) -> torch.Tensor:
-        """First scored row of every video in sparsify mode ([V + 1] int64: v * K); built once, outside any capture."""
+        """First scored row of every video in sparsify mode ([V + 1] int64: v * K); one tensor per (table rows, K,
+        device), kept for the life of the stage: captured graphs hold its address, and different capacity buckets
+        have different numbers of table rows."""
         key = (batch.num_videos, self.cfg.topk, str(batch.device))
-        if self._row_off is None or self._row_off_k != key:
-            self._row_off = torch.arange(batch.num_videos + 1, dtype=torch.int64, device=batch.device) * self.cfg.topk
-            self._row_off_k = key
-        return self._row_off
+        off = self._row_off.get(key)
+        if off is None:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("row offsets must be created before capture (GraphedStage warms the stage up first)")
+            off = torch.arange(batch.num_videos + 1, dtype=torch.int64, device=batch.device) * self.cfg.topk
+            self._row_off[key] = off
+        return off
 
     def _decomposed(self, features) -> bool:
         """Tensor precision with features built on the GPU: the classifier is evaluated as
