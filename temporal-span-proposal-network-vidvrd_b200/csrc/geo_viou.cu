@@ -135,10 +135,10 @@ __device__ __forceinline__ unsigned long long warp_sum_fx(float v) {
 
 
 template <int THREADS, bool WRITE_GEO, bool CLIP, bool DENSE>
-__global__ void __launch_bounds__(THREADS, GeoCfg<THREADS, DENSE>::MIN_CTAS)
-pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __restrict__ table, int nv,
-                const int32_t* __restrict__ span, float* __restrict__ geo, unsigned long long* __restrict__ fx,
-                int32_t* __restrict__ overlap, unsigned int* __restrict__ queue, int max_chunks) {
+__device__ __forceinline__ void
+pair_geo_body(const CUtensorMap& box_map, const int64_t* __restrict__ table, int nv,
+              const int32_t* __restrict__ span, float* __restrict__ geo, unsigned long long* __restrict__ fx,
+              int32_t* __restrict__ overlap, unsigned int* __restrict__ queue, int max_chunks) {
     using Cfg = GeoCfg<THREADS, DENSE>;
     constexpr int GEO_CHUNK = Cfg::CHUNK, GEO_WARPS = Cfg::WARPS, GEO_STAGE_BYTES = Cfg::STAGE_BYTES;
     constexpr int GEO_TX_BYTES = Cfg::TX_BYTES, GEO_SPLIT = Cfg::SPLIT, RING = Cfg::RING;
@@ -154,9 +154,6 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    // the batch's true work-item count (sentinel row): the grid / queue bound of the launch is only a capacity
-    const unsigned int total_items = (unsigned int)table_total(table, nv, TSPN_VT_ITEM_OFF);
-
     if (tid == 0) {
 #pragma unroll
         for (int i = 0; i < RING; ++i) {
@@ -181,11 +178,12 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
         if (tid == 0) *s_item = atomicAdd(queue, 1u);
         __syncthreads();
         item = *s_item;
-        if (item >= total_items) break;
     } else {
         item = blockIdx.x;
-        if (item >= total_items) break;
     }
+    // the batch's true work-item count (sentinel row): the grid / queue bound of the launch is only a capacity
+    // (re-read per item rather than held in a register: the kernel sits exactly at its register budget)
+    if (item >= (unsigned int)table_total(table, nv, TSPN_VT_ITEM_OFF)) break;
 
     // ---- decode the work item ------------------------------------------------------------------
     const int v = find_video(table, nv, TSPN_VT_ITEM_OFF, (int64_t)item);
@@ -310,6 +308,27 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
     }
     if (!queue) break;
     }
+}
+
+template <int THREADS, bool WRITE_GEO, bool CLIP, bool DENSE>
+__global__ void __launch_bounds__(THREADS, GeoCfg<THREADS, DENSE>::MIN_CTAS)
+pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __restrict__ table, int nv,
+                const int32_t* __restrict__ span, float* __restrict__ geo, unsigned long long* __restrict__ fx,
+                int32_t* __restrict__ overlap, unsigned int* __restrict__ queue, int max_chunks) {
+    pair_geo_body<THREADS, WRITE_GEO, CLIP, DENSE>(box_map, table, nv, span, geo, fx, overlap, queue, max_chunks);
+}
+
+// The 512-thread shape with the register count PINNED at 104: 16 warps x 104 registers leave exactly the 12 288
+// registers one 128-thread x 96-register CTA of the side branch (survivor_rows) needs to co-reside on the SM
+// (DESIGN.md section 4).  Under __launch_bounds__(512, 1) ptxas is free to take up to 128 and lands on 104 or 105
+// depending on unrelated edits - and 105 is allocated as 112, which locks the side branch out of 140 of the 148
+// SMs (measured: survivor_rows 0.42 -> 0.58 ms, step 0.74 -> 0.97 ms).
+template <bool WRITE_GEO, bool CLIP>
+__global__ void __maxnreg__(104)
+pair_geo_kernel_r104(const __grid_constant__ CUtensorMap box_map, const int64_t* __restrict__ table, int nv,
+                     const int32_t* __restrict__ span, float* __restrict__ geo, unsigned long long* __restrict__ fx,
+                     int32_t* __restrict__ overlap, unsigned int* __restrict__ queue, int max_chunks) {
+    pair_geo_body<512, WRITE_GEO, CLIP, false>(box_map, table, nv, span, geo, fx, overlap, queue, max_chunks);
 }
 
 // ---- post-kernel: per-pair reductions (vIoU, tIoU; the pair kernel writes the overlap windows) ----------
@@ -533,11 +552,19 @@ static int launch_pair_geo(const int64_t* d_table, int num_videos, int64_t total
     }
 #define TSPN_LAUNCH_GEO(W, C)                                                                                  \
     do {                                                                                                       \
-        TSPN_CUDA_OK(cudaFuncSetAttribute(pair_geo_kernel<THREADS, W, C, DENSE>,                               \
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));      \
-        prefer_max_smem(pair_geo_kernel<THREADS, W, C, DENSE>);                                                \
-        pair_geo_kernel<THREADS, W, C, DENSE><<<grid, THREADS, Cfg::SMEM_BYTES, st>>>(                         \
-            map, d_table, num_videos, d_span, d_geo, fx, d_overlap, d_queue, max_chunks);                      \
+        if (THREADS == 512 && !DENSE) {                                                                        \
+            TSPN_CUDA_OK(cudaFuncSetAttribute(pair_geo_kernel_r104<W, C>,                                      \
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));  \
+            prefer_max_smem(pair_geo_kernel_r104<W, C>);                                                       \
+            pair_geo_kernel_r104<W, C><<<grid, THREADS, Cfg::SMEM_BYTES, st>>>(                                \
+                map, d_table, num_videos, d_span, d_geo, fx, d_overlap, d_queue, max_chunks);                  \
+        } else {                                                                                               \
+            TSPN_CUDA_OK(cudaFuncSetAttribute(pair_geo_kernel<THREADS, W, C, DENSE>,                           \
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));  \
+            prefer_max_smem(pair_geo_kernel<THREADS, W, C, DENSE>);                                            \
+            pair_geo_kernel<THREADS, W, C, DENSE><<<grid, THREADS, Cfg::SMEM_BYTES, st>>>(                     \
+                map, d_table, num_videos, d_span, d_geo, fx, d_overlap, d_queue, max_chunks);                  \
+        }                                                                                                      \
     } while (0)
     if (d_geo) {
         if (clip) TSPN_LAUNCH_GEO(true, true); else TSPN_LAUNCH_GEO(true, false);

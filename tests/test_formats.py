@@ -64,6 +64,7 @@ def test_segment_through_basemodel_reference_mode(tmp_path):
     np.testing.assert_allclose(pl_gpu.features.numpy(), pl_cpu.features.numpy(), rtol=1e-6, atol=0)
     cfg = tspn_b200.get_default_cfg()
     cfg.RELPN.USE_PPN = cfg.RELPN.USE_DPN = False
+    cfg.RELPN.DPN.IN_CHANNELS = 8                         # the synthetic checkpoint's span-head width
     sd_np = synth.make_weights(35, 132, 11070, seed=1)
     model = BaseModel(cfg).eval()
     model.load_state_dict({k: torch.from_numpy(v) for k, v in sd_np.items()})
