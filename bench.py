@@ -73,6 +73,8 @@ def parse_args():
     ap.add_argument("--compute-streams", type=int, default=2, choices=[1, 2],
                     help="compute streams of the serving loop (2: the tail of step i overlaps the geometry of i+1)")
     ap.add_argument("--no-affinity", action="store_true", help="do not bind the rank to its GPU's CPU cores")
+    ap.add_argument("--relationness", default="fp32", choices=["fp32", "tensor"],
+                    help="PPNHead arithmetic: fp32 exact order (bit-exact top-K) or tcgen05 (tf32 operands)")
     return ap.parse_args()
 
 
@@ -374,7 +376,7 @@ def run_ours(args, rank, world, local_rank):
     sparsify = not args.no_sparsify
     cfg = StageConfig(n_classes=c, n_predicates=r, topk=k, use_ppn=True, use_dpn=True, sparsify=sparsify,
                       precision=args.precision, anchor_sizes=sizes, anchor_stride=stride,
-                      num_span_proposals=args.span_proposals)
+                      num_span_proposals=args.span_proposals, relationness_precision=args.relationness)
     sd = synth.make_weights(c, r, synth.feature_dim(c), dpn_in=8, seed=0)
     stage = PairStage(cfg)
     stage.load_weights(sd, dev)
@@ -436,18 +438,36 @@ def run_ours(args, rank, world, local_rank):
             return sharding.gather_records(rec_local[:n_local], cnt_local[:n_local], shards)
         return rec_local, cnt_local
 
+    # Resident refill: a bucket's slots are shared by every batch of its capacity, so a batch's inputs (already in
+    # HBM) are copied device-to-device into the slot it will replay on - on a copy stream, up to `depth` batches
+    # ahead, so the refill of batch j+1 runs under the kernels of batch j.  A workload of one batch per step keeps
+    # its inputs in the slot: nothing is copied.
+    s_copy = torch.cuda.Stream(dev)
+    holds = {}                                          # slot -> the resident batch its inputs currently are
+
     def one_step():
-        used = {}
+        main = torch.cuda.current_stream(dev)
+        used, plan = {}, []
         for j, (resident, host) in enumerate(zip(residents, hosts)):
             bucket = pipe._bucket(host)
             i = used.get(id(bucket), 0)
             used[id(bucket)] = i + 1
-            slot = bucket.slots[i % len(bucket.slots)]
+            plan.append((j, resident, bucket.slots[i % len(bucket.slots)]))
+        for j, resident, slot in plan:
+            if holds.get(slot) is not resident:
+                with torch.cuda.stream(s_copy):
+                    s_copy.wait_event(slot.kernels_done)        # the slot's previous replay has read its inputs
+                    slot.batch.copy_from_device(resident)
+                    slot.h2d_done.record(s_copy)
+                holds[slot] = resident
+                main.wait_event(slot.h2d_done)
+            else:
+                slot.batch._adopt(resident.host)
             read_geo(slot)                              # its events are re-recorded by the next replay
-            slot.batch.copy_from_device(resident)
             timers = {}
             res = slot.graphed.replay(timers=timers) if slot.graphed is not None else \
                 stage.forward(slot.batch, timers=timers)
+            slot.kernels_done.record(main)
             pending[slot] = timers["geo"]
             if shards is not None:
                 nr = len(batch_vids[j])
@@ -591,7 +611,7 @@ def run_ours(args, rank, world, local_rank):
         "capacities": {str(cc): {"videos": cap.videos, "pairs": cap.pairs, "geo_gb": cap.geo_floats * 4 / 1e9,
                                  "geo_chunk": cap.geo_chunk, "max_n": cap.max_n, "max_t": cap.max_t}
                        for cc, cap in caps.items()},
-        "precision": args.precision,
+        "precision": args.precision, "relationness_precision": args.relationness,
         "sharding": ("per video, LPT on N(N-1)T (imbalance %.4f); NCCL all-gather of the [V,200,8] int32 triplet "
                      "records inside the timed region" % imbalance) if shards is not None else
                     "per video, every rank its own videos; no data-path collective in `value`, all-gather of the "

@@ -320,12 +320,16 @@ class DeviceBatch:
         return self
 
     def copy_from_device(self, other: "DeviceBatch") -> "DeviceBatch":
-        """The same refill from a batch that is already resident in HBM (device-to-device)."""
+        """The same refill from a batch that is already resident in HBM (device-to-device, current stream): the
+        fields the kernels read - table, spans, class logits, motion rows and the fp32 boxes (the u16 transport
+        image of the boxes is not copied: it only feeds the expansion)."""
         if other.layout != self.layout or other.capacity != self.capacity:
             raise ValueError("copy_from_device needs a batch of the same capacity")
         self._adopt(other.host)
+        skip = self.layout["boxes"][0] if self.boxes_u16 is not None else None
         for off, nbytes in other.host.used_segments():
-            self.arena[off:off + nbytes].copy_(other.arena[off:off + nbytes], non_blocking=True)
+            if off != skip:
+                self.arena[off:off + nbytes].copy_(other.arena[off:off + nbytes], non_blocking=True)
         n_boxes = int(self.actual[TOT_BOXES])
         if self.boxes_u16 is not None and n_boxes:
             self.boxes[:n_boxes].copy_(other.boxes[:n_boxes], non_blocking=True)

@@ -28,27 +28,58 @@ def main():
     ap.add_argument("--eager", action="store_true")
     ap.add_argument("--no-dpn", action="store_true", help="without the span head")
     ap.add_argument("--span-proposals", type=int, default=64, help="spans kept per pair by the NMS (0 = none)")
+    ap.add_argument("--workload", default="vidor_single", help="synth.CONFIGS key; ragged workloads trace their first "
+                                                               "batches (capacity graphs, as the bench replays them)")
+    ap.add_argument("--batches", type=int, default=3, help="ragged workloads: batches to trace")
+    ap.add_argument("--relationness", default="fp32", choices=["fp32", "tensor"])
     args = ap.parse_args()
-    spec = synth.CONFIGS["vidor_single"]
+    spec = synth.CONFIGS[args.workload]
     c, r, k = spec["classes"], spec["predicates"], spec["topk"]
-    n, t = spec["n"][0], spec["t"][0]
+    n, t = spec["n"][1], spec["t"][1]
+    vidvrd = c == 35
     cfg = StageConfig(n_classes=c, n_predicates=r, topk=k, use_ppn=True, use_dpn=not args.no_dpn, sparsify=True,
-                      precision="tensor", anchor_sizes=(16.0, 64.0, 256.0, 1024.0), anchor_stride=16.0,
-                      num_span_proposals=args.span_proposals)
+                      precision="tensor", relationness_precision=args.relationness,
+                      anchor_sizes=(15.0, 30.0, 45.0, 60.0) if vidvrd else (16.0, 64.0, 256.0, 1024.0),
+                      anchor_stride=7.5 if vidvrd else 16.0, num_span_proposals=args.span_proposals)
     stage = PairStage(cfg)
     stage.load_weights(synth.make_weights(c, r, synth.feature_dim(c), dpn_in=8, seed=0), "cuda")
-    host = HostBatch.from_videos([synth.make_video(n, t, c, seed=i) for i in range(args.videos)], compact=True)
-    batch = host.to_device("cuda")
-    graphed = None if args.eager else stage.capture(batch)
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device="cuda")
+    if spec["videos"] == 1:
+        count = args.videos if args.workload != "stress" else 1
+        host = HostBatch.from_videos([synth.make_video(n, t, c, seed=i) for i in range(count)], compact=True)
+        batch = host.to_device("cuda")
+        graphed = None if args.eager else stage.capture(batch)
 
-    def step():
-        flush.zero_()
-        if graphed is not None:
-            graphed.replay()
-        else:
-            stage.forward(batch)
-        torch.cuda.synchronize()
+        def step():
+            flush.zero_()
+            if graphed is not None:
+                graphed.replay()
+            else:
+                stage.forward(batch)
+            torch.cuda.synchronize()
+    else:
+        from tspn_b200.serving import host_batches_for
+        shapes = synth.config_shapes(args.workload, 0, 160)
+        vids = [synth.make_video(a, b, c, seed=i) for i, (a, b) in enumerate(shapes)]
+        hosts, _, caps = host_batches_for(vids, c)
+        hosts = hosts[:args.batches]
+        graphs = {}
+        for h in hosts:
+            if h.capacity not in graphs:
+                b = h.to_device("cuda")
+                graphs[h.capacity] = (b, None if args.eager else stage.capture(b))
+        print("# %d batches: %s" % (len(hosts), [(h.num_real, int(h.actual[1]), h.capacity.geo_chunk) for h in hosts]))
+
+        def step():
+            for h in hosts:                       # one flush per batch: every batch prints as its own "step"
+                flush.zero_()
+                b, g = graphs[h.capacity]
+                b.copy_from(h)
+                if g is not None:
+                    g.replay()
+                else:
+                    stage.forward(b)
+                torch.cuda.synchronize()
 
     for _ in range(3):
         step()
@@ -72,7 +103,8 @@ def main():
         cur.append(e)
     if cur:
         steps.append(cur)
-    for si, evs in enumerate(steps[-args.steps:]):
+    n_show = args.steps if spec["videos"] == 1 else args.steps * args.batches
+    for si, evs in enumerate(steps[-n_show:]):
         if not evs:
             continue
         t0 = evs[0]["ts"]
