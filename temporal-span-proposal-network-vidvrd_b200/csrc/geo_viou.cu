@@ -543,6 +543,11 @@ static int launch_pair_geo(const int64_t* d_table, int num_videos, int64_t total
                                CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != TSPN_OK) return rc;
     unsigned grid = (unsigned)total_items;
+    // Shared memory: one CTA per item pins its occupancy with the request (SMEM_BYTES); persistent CTAs are
+    // counted out by the grid instead and ask only for what they use, so that on every SM the rest (95 KB beside
+    // two 256-thread CTAs, 127 KB beside three 128-thread CTAs) is there for the side branches - with the pin the
+    // side branch of a 512- / 1024-frame batch ran on the reserved SMs only (embedding kernel 36 -> 307 us).
+    const int smem_bytes = d_queue ? Cfg::SMEM_USED : Cfg::SMEM_BYTES;
     if (d_queue) {                      // persistent: one CTA per SM slot, items from the queue
         int64_t slots = (int64_t)num_sms() * Cfg::MIN_CTAS - reserve;      // SM slots left to concurrent streams
         if (slots < 1) slots = 1;
@@ -556,13 +561,13 @@ static int launch_pair_geo(const int64_t* d_table, int num_videos, int64_t total
             TSPN_CUDA_OK(cudaFuncSetAttribute(pair_geo_kernel_r104<W, C>,                                      \
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));  \
             prefer_max_smem(pair_geo_kernel_r104<W, C>);                                                       \
-            pair_geo_kernel_r104<W, C><<<grid, THREADS, Cfg::SMEM_BYTES, st>>>(                                \
+            pair_geo_kernel_r104<W, C><<<grid, THREADS, smem_bytes, st>>>(                                     \
                 map, d_table, num_videos, d_span, d_geo, fx, d_overlap, d_queue, max_chunks);                  \
         } else {                                                                                               \
             TSPN_CUDA_OK(cudaFuncSetAttribute(pair_geo_kernel<THREADS, W, C, DENSE>,                           \
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));  \
             prefer_max_smem(pair_geo_kernel<THREADS, W, C, DENSE>);                                            \
-            pair_geo_kernel<THREADS, W, C, DENSE><<<grid, THREADS, Cfg::SMEM_BYTES, st>>>(                     \
+            pair_geo_kernel<THREADS, W, C, DENSE><<<grid, THREADS, smem_bytes, st>>>(                          \
                 map, d_table, num_videos, d_span, d_geo, fx, d_overlap, d_queue, max_chunks);                  \
         }                                                                                                      \
     } while (0)

@@ -88,23 +88,27 @@ span_select_kernel(const int64_t* __restrict__ table, int nv, const int32_t* __r
 #pragma unroll
     for (int u = 0; u < GPL; ++u) { gkey[u] = 0u; g_smin[u] = 0x7fffffff; g_emax[u] = 0; g_lmin[u] = 0x7fffffff; g_lmax[u] = 0; }
     const int32_t* crow = cand + r * ld_cand;
+    // pass 1: every load of the lane in flight at once (the row's candidates sit in L2: one round trip, not G)
     for (int j = 0; j < G; ++j) {
         const int a = j / gpa, l = (j - a * gpa) * 32 + lane;
         uint32_t key = 0u, pack = 0u;
-        int s = 0x7fffffff, e = 0, len_lo = 0x7fffffff, len_hi = 0;
         if (l < n_loc) {
             const int i = l * A + a;
             const int2 c = __ldg(reinterpret_cast<const int2*>(crow) + i);
-            s = c.x; e = c.y;
-            const int inter = max(0, min(e, wb) - max(s, wa));
-            const int uni = (e - s) + wlen - inter;
+            const int inter = max(0, min(c.y, wb) - max(c.x, wa));
+            const int uni = (c.y - c.x) + wlen - inter;
             const uint32_t q = uni > 0 ? ((uint32_t)inter << 15) / (uint32_t)uni : 0u;
             key = (1u << 28) | (q << 12) | (uint32_t)(4095 - i);
-            pack = (uint32_t)s | ((uint32_t)e << 16);
-            len_lo = len_hi = e - s;
+            pack = (uint32_t)c.x | ((uint32_t)c.y << 16);
         }
         keys[j * 32 + lane] = key;
         se[j * 32 + lane] = pack;
+    }
+    // pass 2: the groups' bounds and best keys (each lane re-reads its own slots: no barrier needed)
+    for (int j = 0; j < G; ++j) {
+        const uint32_t key = keys[j * 32 + lane], pack = se[j * 32 + lane];
+        const int s = key ? (int)(pack & 0xffffu) : 0x7fffffff, e = key ? (int)(pack >> 16) : 0;
+        const int len_lo = key ? e - s : 0x7fffffff, len_hi = key ? e - s : 0;
         const uint32_t gk = __reduce_max_sync(0xffffffffu, key);
         const int smin = __reduce_min_sync(0xffffffffu, s), emax = __reduce_max_sync(0xffffffffu, e);
         const int lmin = __reduce_min_sync(0xffffffffu, len_lo), lmax = __reduce_max_sync(0xffffffffu, len_hi);
@@ -125,7 +129,7 @@ span_select_kernel(const int64_t* __restrict__ table, int nv, const int32_t* __r
         m = __reduce_max_sync(0xffffffffu, m);
         if (m == 0u) break;
         const int i = 4095 - (int)(m & 4095u);
-        const int l = i / A, a = i - l * A;
+        const int l = A == 4 ? i >> 2 : i / A, a = i - l * A;
         const int jw = a * gpa + (l >> 5);
         const int pw = jw * 32 + (l & 31);
         const uint32_t w = se[pw];
@@ -139,8 +143,7 @@ span_select_kernel(const int64_t* __restrict__ table, int nv, const int32_t* __r
 #pragma unroll
         for (int u = 0; u < GPL; ++u) {
             const bool hit = gkey[u] != 0u && ew > g_smin[u] && sw < g_emax[u] &&
-                             (int64_t)g_lmax[u] * 1024 > (int64_t)thr_q10 * lw &&
-                             (int64_t)lw * 1024 > (int64_t)thr_q10 * g_lmin[u];
+                             g_lmax[u] * 1024 > thr_q10 * lw && lw * 1024 > thr_q10 * min(g_lmin[u], 65536);
             uint32_t mask = __ballot_sync(0xffffffffu, hit);
             if (u == (jw >> 5)) mask |= 1u << (jw & 31);                       // the winner's own group
             while (mask) {
@@ -153,7 +156,7 @@ span_select_kernel(const int64_t* __restrict__ table, int nv, const int32_t* __r
                     const int s = (int)(c & 0xffffu), e = (int)(c >> 16);
                     const int inter = min(e, ew) - max(s, sw);
                     const int uni = (e - s) + lw - inter;
-                    if (inter > 0 && (int64_t)inter * 1024 > (int64_t)thr_q10 * uni) {
+                    if (inter > 0 && inter * 1024 > thr_q10 * uni) {          // frames < 2^16: products < 2^27
                         key = 0u;
                         keys[j * 32 + lane] = 0u;
                     }
