@@ -73,6 +73,8 @@ def parse_args():
     ap.add_argument("--compute-streams", type=int, default=2, choices=[1, 2],
                     help="compute streams of the serving loop (2: the tail of step i overlaps the geometry of i+1)")
     ap.add_argument("--no-affinity", action="store_true", help="do not bind the rank to its GPU's CPU cores")
+    ap.add_argument("--reserve-sms", type=int, default=None,
+                    help="SMs the persistent all-pairs kernel leaves to the side branches (default: StageConfig's)")
     ap.add_argument("--relationness", default="fp32", choices=["fp32", "tensor"],
                     help="PPNHead arithmetic: fp32 exact order (bit-exact top-K) or tcgen05 (tf32 operands)")
     return ap.parse_args()
@@ -377,6 +379,8 @@ def run_ours(args, rank, world, local_rank):
     cfg = StageConfig(n_classes=c, n_predicates=r, topk=k, use_ppn=True, use_dpn=True, sparsify=sparsify,
                       precision=args.precision, anchor_sizes=sizes, anchor_stride=stride,
                       num_span_proposals=args.span_proposals, relationness_precision=args.relationness)
+    if args.reserve_sms is not None:
+        cfg.geo_reserve_sms = args.reserve_sms
     sd = synth.make_weights(c, r, synth.feature_dim(c), dpn_in=8, seed=0)
     stage = PairStage(cfg)
     stage.load_weights(sd, dev)
@@ -612,6 +616,7 @@ def run_ours(args, rank, world, local_rank):
                                  "geo_chunk": cap.geo_chunk, "max_n": cap.max_n, "max_t": cap.max_t}
                        for cc, cap in caps.items()},
         "precision": args.precision, "relationness_precision": args.relationness,
+        "geo_reserve_sms": cfg.geo_reserve_sms,
         "sharding": ("per video, LPT on N(N-1)T (imbalance %.4f); NCCL all-gather of the [V,200,8] int32 triplet "
                      "records inside the timed region" % imbalance) if shards is not None else
                     "per video, every rank its own videos; no data-path collective in `value`, all-gather of the "
