@@ -206,6 +206,13 @@ int tspn_normalize_motion(const float* d_motion, int64_t n_tracklets, float* d_o
  * exact), boxes as u16 pixel coordinates [n_boxes][4] expanded to the fp32 layout the kernels read. */
 int tspn_normalize_motion_u8(const uint8_t* d_motion, int64_t n_tracklets, float* d_out, void* stream);
 int tspn_unpack_boxes_u16(const uint16_t* d_src, int64_t n_boxes, float* d_dst, void* stream);
+/* The same with the boxes SPAN-PACKED: a tracklet only has boxes on [pstart, pend) (lib/modeling/trajectory.py:21-22;
+ * nothing on the path reads a box outside its tracklet's span), so only those travel - tracklet n's at
+ * d_packed[d_packed_off[n] ...] (int64 [total_tracklets], units of boxes, in tracklet order) - and the expansion
+ * writes them at frames pstart .. of the dense row and zeros everywhere else.  total_tracklets is an upper bound
+ * (the sentinel row carries the true count). */
+int tspn_unpack_boxes_spans(const int64_t* d_table, int num_videos, int64_t total_tracklets, const int32_t* d_span,
+                            const int64_t* d_packed_off, const uint16_t* d_packed, float* d_dst, void* stream);
 /* Build rows [2C | 8000 motion | 3000 relative] (lib/dataset/vrdataset.py:219-243); the last
  * 3000 columns are the adaptive-average-pooled geometry ([SPEC] s4).  d_rows: global pair rows
  * to build (int64, NULL = all total_pairs rows in order).  Output row stride ld_feat floats

@@ -59,6 +59,7 @@ SIGNATURES = {
     "tspn_normalize_motion": (c_int, [P, c_int64, P, P]),
     "tspn_normalize_motion_u8": (c_int, [P, c_int64, P, P]),
     "tspn_unpack_boxes_u16": (c_int, [P, c_int64, P, P]),
+    "tspn_unpack_boxes_spans": (c_int, [P, c_int, c_int64, P, P, P, P, P]),
     "tspn_assemble_features": (c_int, [P, c_int, c_int64, c_int, P, c_int, P, P, P, P, c_int64, P, c_int64, P, c_int64, P]),
     "tspn_relationness_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
     "tspn_relationness_tc_supported": (c_int, [c_int, c_int, c_int]),

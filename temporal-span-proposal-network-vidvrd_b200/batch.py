@@ -135,7 +135,9 @@ class HostBatch:
         histograms as u8 counts when every value is exactly representable (integer boxes in [0, 65535],
         integer counts in [0, 255]) - lossless, expanded on the device by ``tspn_unpack_boxes_u16`` /
         ``tspn_normalize_motion_u8``; otherwise (or with ``compact=False``) the fields travel as fp32.  The
-        serving loop is PCIe-bound, and these two fields are 99 % of a batch's bytes.
+        serving loop is PCIe-bound, and these two fields are 99 % of a batch's bytes.  Compact boxes are also
+        SPAN-PACKED: only the frames ``[pstart, pend)`` of each tracklet travel (nothing on the path reads a box
+        outside its tracklet's span), expanded into the dense zero-padded rows by ``tspn_unpack_boxes_spans``.
 
         ``capacity``: pack for that capacity instead (serving: every batch of a capacity shares one arena
         layout and one captured graph).  The transport dtypes are then the capacity's; data that does not fit
@@ -195,6 +197,7 @@ class HostBatch:
         self.layout = _arena_layout([
             ("table", (rows + 1, VT_COLS), torch.int64),
             ("boxes", (int(tot[TOT_BOXES]), 4), torch.int16 if self.boxes_compact else torch.float32),
+            ("box_off", (n_trk,), torch.int64) if self.boxes_compact else None,
             ("span", (n_trk, 2), torch.int32),
             ("cls", (n_trk, n_cls), torch.float32) if has_cls else None,
             ("motion", (n_trk, _lib.MOTION_DIM), torch.uint8 if self.motion_compact else torch.float32)
@@ -204,17 +207,30 @@ class HostBatch:
         if use_pin:
             self.arena = self.arena.pin_memory()
         views = _arena_views(self.arena, self.layout)
-        self.boxes, self.span = views["boxes"], views["span"]     # boxes: fp32, or the u16 bit patterns (int16 view)
+        self.boxes, self.span = views["boxes"], views["span"]     # boxes: fp32 dense rows, or span-packed u16
+        self.box_off = views.get("box_off")                       # first packed box of every tracklet (compact)
         bview = self.boxes.numpy().view(np.uint16) if self.boxes_compact else self.boxes.numpy()
         sview = self.span.numpy()
+        packed = 0
         for v, (b, s) in enumerate(zip(boxes, span)):
             row = self.table[v]
             n, t, tb = int(row[VT_N]), int(row[VT_T]), int(row[VT_TB])
             if n == 0:
                 continue
-            dst = bview[int(row[VT_BOX_OFF]):int(row[VT_BOX_OFF]) + n * tb].reshape(n, tb, 4)
-            dst[:, :t] = b
-            sview[int(row[VT_TRK_OFF]):int(row[VT_TRK_OFF]) + n] = s
+            trk0 = int(row[VT_TRK_OFF])
+            sview[trk0:trk0 + n] = s
+            if self.boxes_compact:
+                frame = np.arange(t, dtype=np.int32)[None, :]
+                alive = (frame >= s[:, :1]) & (frame < s[:, 1:2])              # [N, T]: tracklet-major packing
+                lens = (s[:, 1] - s[:, 0]).astype(np.int64)
+                self.box_off.numpy()[trk0:trk0 + n] = packed + np.concatenate([[0], np.cumsum(lens)[:-1]])
+                cnt = int(lens.sum())
+                bview[packed:packed + cnt] = b[alive]
+                packed += cnt
+            else:
+                dst = bview[int(row[VT_BOX_OFF]):int(row[VT_BOX_OFF]) + n * tb].reshape(n, tb, 4)
+                dst[:, :t] = b
+        self.packed_boxes = packed                                # boxes that travel (compact transport)
         self.cls = views.get("cls")
         self.motion = views.get("motion")
         n_act_trk = int(self.actual[TOT_TRACKLETS])
@@ -240,7 +256,8 @@ class HostBatch:
     def used_segments(self) -> List[Tuple[int, int]]:
         """``(offset, bytes)`` of the part of every arena field the batch actually fills: what a step copies."""
         act = self.actual
-        used = {"table": None, "boxes": int(act[TOT_BOXES]), "span": int(act[TOT_TRACKLETS]),
+        used = {"table": None, "boxes": self.packed_boxes if self.boxes_compact else int(act[TOT_BOXES]),
+                "box_off": int(act[TOT_TRACKLETS]), "span": int(act[TOT_TRACKLETS]),
                 "cls": int(act[TOT_TRACKLETS]), "motion": int(act[TOT_TRACKLETS])}
         segs = []
         for name, spec in self.layout.items():
@@ -254,9 +271,7 @@ class HostBatch:
         return segs
 
     def h2d_bytes(self) -> int:
-        """Bytes one step copies host -> device."""
-        if self.capacity is None:
-            return int(self.arena.numel())              # the whole arena in one copy, alignment padding included
+        """Bytes one step copies host -> device (the part of every arena field the batch fills)."""
         return int(sum(b for _, b in self.used_segments()))
 
     def to_device(self, device="cuda", non_blocking: bool = True) -> "DeviceBatch":
@@ -277,8 +292,9 @@ class DeviceBatch:
         views = _arena_views(self.arena, self.layout)
         self.table, self.span = views["table"], views["span"]
         self.cls, self.motion = views.get("cls"), views.get("motion")     # motion: fp32, or u8 counts (compact)
+        self.box_off = views.get("box_off")
         if host.boxes_compact:
-            # u16 coordinates in the arena, expanded right behind the copy (same stream) into this fp32 buffer -
+            # span-packed u16 coordinates in the arena, expanded right behind the copy (same stream) into this fp32 buffer -
             # the layout the kernels and the TMA tensor map read.  The expansion belongs to the upload, not to
             # the step: in the serving loop it runs on the H2D stream, off the kernels' critical path.
             self.boxes_u16 = views["boxes"]
@@ -295,12 +311,12 @@ class DeviceBatch:
         self.table_host, self.actual = host.table, host.actual
 
     def _unpack(self) -> None:
-        n_boxes = int(self.actual[TOT_BOXES])
-        if self.boxes_u16 is not None and n_boxes > 0:
+        if self.boxes_u16 is not None and int(self.actual[TOT_TRACKLETS]) > 0:
             with torch.cuda.device(self.device):
-                _lib.check(_lib.load().tspn_unpack_boxes_u16(self.boxes_u16.data_ptr(), n_boxes, self.boxes.data_ptr(),
-                                                             torch.cuda.current_stream(self.device).cuda_stream),
-                           "tspn_unpack_boxes_u16")
+                _lib.check(_lib.load().tspn_unpack_boxes_spans(
+                    self.table.data_ptr(), len(self.n), int(self.totals[TOT_TRACKLETS]), self.span.data_ptr(),
+                    self.box_off.data_ptr(), self.boxes_u16.data_ptr(), self.boxes.data_ptr(),
+                    torch.cuda.current_stream(self.device).cuda_stream), "tspn_unpack_boxes_spans")
 
     def copy_from(self, host: HostBatch) -> "DeviceBatch":
         """Refill the device buffers from another host batch of the same layout (non-blocking, on the
@@ -311,11 +327,8 @@ class DeviceBatch:
             raise ValueError("copy_from needs a host batch of the same capacity (or, without one, the same "
                              "per-video shapes and fields)")
         self._adopt(host)
-        if self.capacity is None:
-            self.arena.copy_(host.arena, non_blocking=True)               # one H2D copy
-        else:
-            for off, nbytes in host.used_segments():                      # only what the batch fills
-                self.arena[off:off + nbytes].copy_(host.arena[off:off + nbytes], non_blocking=True)
+        for off, nbytes in host.used_segments():                          # only what the batch fills
+            self.arena[off:off + nbytes].copy_(host.arena[off:off + nbytes], non_blocking=True)
         self._unpack()
         return self
 
@@ -326,9 +339,9 @@ class DeviceBatch:
         if other.layout != self.layout or other.capacity != self.capacity:
             raise ValueError("copy_from_device needs a batch of the same capacity")
         self._adopt(other.host)
-        skip = self.layout["boxes"][0] if self.boxes_u16 is not None else None
+        skip = (self.layout["boxes"][0], self.layout["box_off"][0]) if self.boxes_u16 is not None else ()
         for off, nbytes in other.host.used_segments():
-            if off != skip:
+            if off not in skip:
                 self.arena[off:off + nbytes].copy_(other.arena[off:off + nbytes], non_blocking=True)
         n_boxes = int(self.actual[TOT_BOXES])
         if self.boxes_u16 is not None and n_boxes:

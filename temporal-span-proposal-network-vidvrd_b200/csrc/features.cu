@@ -67,6 +67,33 @@ __global__ void __launch_bounds__(256) unpack_boxes_u16_kernel(const uint2* __re
     }
 }
 
+// span-packed u16 boxes -> dense fp32 rows: tracklet n's packed boxes (frames [pstart, pend) only, at
+// packed[pk_off[n] ...]) go to its dense row at frames pstart .., every other frame of the row is written as zero.
+// One CTA per tracklet; the dense row is box_off(video) + n_local * Tb.
+__global__ void __launch_bounds__(256) unpack_boxes_spans_kernel(const int64_t* __restrict__ table, int nv,
+                                                                 const int32_t* __restrict__ span,
+                                                                 const int64_t* __restrict__ pk_off,
+                                                                 const uint2* __restrict__ packed,
+                                                                 float4* __restrict__ dst) {
+    const int64_t n_trk = table_total(table, nv, TSPN_VT_TRK_OFF);
+    for (int64_t trk = blockIdx.x; trk < n_trk; trk += gridDim.x) {
+        const int v = find_video(table, nv, TSPN_VT_TRK_OFF, trk);
+        const int64_t* row = table + (int64_t)v * TSPN_VT_COLS;
+        const int tb = (int)row[TSPN_VT_TB];
+        float4* out = dst + row[TSPN_VT_BOX_OFF] + (trk - row[TSPN_VT_TRK_OFF]) * tb;
+        const int ps = __ldg(span + 2 * trk), pe = __ldg(span + 2 * trk + 1);
+        const uint2* src = packed + __ldg(pk_off + trk) - ps;
+        for (int f = threadIdx.x; f < tb; f += 256) {
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (f >= ps && f < pe) {
+                const uint2 w = __ldg(src + f);
+                b = make_float4((float)(w.x & 0xffffu), (float)(w.x >> 16), (float)(w.y & 0xffffu), (float)(w.y >> 16));
+            }
+            out[f] = b;
+        }
+    }
+}
+
 // Tracklet rows for the decomposed predicate head: [cls (C) | L1-normalised motion (4000) | 0-pad] in bf16,
 // one CTA of 128 threads per tracklet (warp w normalises BoW block w).  MOTION_U8: compact transport.
 template <bool MOTION_U8>
@@ -327,6 +354,25 @@ int tspn_unpack_boxes_u16(const uint16_t* d_src, int64_t n_boxes, float* d_dst, 
     if (blocks > cap) blocks = cap;
     unpack_boxes_u16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const uint2*>(d_src), n_boxes, reinterpret_cast<float4*>(d_dst));
+    TSPN_CUDA_OK(cudaGetLastError());
+    return TSPN_OK;
+}
+
+int tspn_unpack_boxes_spans(const int64_t* d_table, int num_videos, int64_t total_tracklets, const int32_t* d_span,
+                            const int64_t* d_packed_off, const uint16_t* d_packed, float* d_dst, void* stream) {
+    TSPN_ARCH_OK();
+    TSPN_REQUIRE(num_videos >= 0 && total_tracklets >= 0, TSPN_EBADARG, "tspn_unpack_boxes_spans: negative size");
+    if (total_tracklets == 0) return TSPN_OK;
+    TSPN_REQUIRE(d_table && d_span && d_packed_off && d_packed && d_dst, TSPN_EBADARG,
+                 "tspn_unpack_boxes_spans: null pointer");
+    TSPN_REQUIRE((reinterpret_cast<uintptr_t>(d_packed) & 7u) == 0 && aligned16(d_dst), TSPN_EALIGN,
+                 "tspn_unpack_boxes_spans: src must be 8-byte and dst 16-byte aligned");
+    int64_t blocks = total_tracklets;
+    const int64_t cap = 16 * (int64_t)num_sms();
+    if (blocks > cap) blocks = cap;
+    unpack_boxes_spans_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        d_table, num_videos, d_span, d_packed_off, reinterpret_cast<const uint2*>(d_packed),
+        reinterpret_cast<float4*>(d_dst));
     TSPN_CUDA_OK(cudaGetLastError());
     return TSPN_OK;
 }

@@ -323,8 +323,11 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
 // (DESIGN.md section 4).  Under __launch_bounds__(512, 1) ptxas is free to take up to 128 and lands on 104 or 105
 // depending on unrelated edits - and 105 is allocated as 112, which locks the side branch out of 140 of the 148
 // SMs (measured: survivor_rows 0.42 -> 0.58 ms, step 0.74 -> 0.97 ms).
+#ifndef TSPN_GEO_MAXNREG
+#define TSPN_GEO_MAXNREG 104
+#endif
 template <bool WRITE_GEO, bool CLIP>
-__global__ void __maxnreg__(104)
+__global__ void __maxnreg__(TSPN_GEO_MAXNREG)
 pair_geo_kernel_r104(const __grid_constant__ CUtensorMap box_map, const int64_t* __restrict__ table, int nv,
                      const int32_t* __restrict__ span, float* __restrict__ geo, unsigned long long* __restrict__ fx,
                      int32_t* __restrict__ overlap, unsigned int* __restrict__ queue, int max_chunks) {

@@ -32,10 +32,11 @@ constexpr int SV_CHUNK = SV_THREADS * GEO_FPT;          // frames per pass = fra
 constexpr int SV_BLOCK_BYTES = SV_CHUNK * 32;           // a block: 512 subject boxes | 512 object boxes (16 KB), later
                                                         // overwritten in place by its [8 channels][512 frames] tile
 constexpr int SV_HALF = SV_CHUNK * 16;                  // offset of the object boxes inside a block
-constexpr int SV_HALO_BYTES = SV_HALF + 128;            // one more (subject, object) frame behind the last block
 constexpr int SV_CIN = TSPN_GEO_CHANNELS;
 constexpr int SV_INV_TAB = 32;
-constexpr int SV_SMEM_MAX = 200 * 1024;
+constexpr int SV_MAX_PASSES = 128;                      // 65 536 frames
+// dynamic shared memory: two blocks (the pass being computed | the next pass's boxes in flight)
+constexpr int SV_SMEM_BYTES = 2 * SV_BLOCK_BYTES;
 
 __host__ __device__ __forceinline__ int span_locations(int t, float stride) {
     // len(torch.arange(0, T+1, step=stride)) = ceil((T+1)/stride), anchor_generator.py:50-52
@@ -45,16 +46,20 @@ __host__ __device__ __forceinline__ int span_locations(int t, float stride) {
     return n;
 }
 
-// column `col` (= frame - a4) of channel `ch` in the blocked tile
-__device__ __forceinline__ float& tile_at(float* tile, int ch, int col) {
-    return tile[(col >> 9) * (SV_BLOCK_BYTES / 4) + ch * SV_CHUNK + (col & (SV_CHUNK - 1))];
-}
 // 16-byte async copy global -> shared (SASS: LDGSTS), L2 only
 __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ uint32_t swizzle128(uint32_t lin) { return lin ^ (((lin >> 7) & 7u) << 4); }
 
+// The window is STREAMED through shared memory 512 frames (one pass) at a time: while pass p is computed, the
+// boxes of pass p+1 are in flight into the other block; the pass's [8][512] tile overwrites its boxes in place and
+// is consumed at once - every pooled bin adds the frames of its range that lie in the pass (a bin that straddles
+// two passes keeps its partial sums in registers; frames are still added in ascending order, so the result is the
+// one-tile result bit for bit), and every anchor location is evaluated in the pass that holds its right-hand tap
+// (the two taps before it come from the tile or from the last two columns of the previous pass, carried over).
+// 32 KB of shared memory per CTA whatever the video length, instead of 16 KB per 512 frames of the LONGEST video of
+// the batch (72 KB at T = 2000): two CTAs fit beside the all-pairs kernel's CTA where one did.
 template <int A>
 __global__ void __launch_bounds__(SV_THREADS, 5)
 survivor_rows_kernel(const int64_t* __restrict__ table, int nv, const float4* __restrict__ boxes,
@@ -66,11 +71,12 @@ survivor_rows_kernel(const int64_t* __restrict__ table, int nv, const float4* __
                      const float* __restrict__ sizes, float stride, int32_t* __restrict__ spans, int64_t ld_spans) {
     constexpr int A2 = 2 * A;
     extern __shared__ __align__(128) uint8_t smem[];
-    float* const tile = reinterpret_cast<float*>(smem);       // [block][8][512]: column = frame - a4 (see tile_at)
     __shared__ __align__(16) float4 w_conv[SV_CIN * SV_CIN];                      // [co][ci] -> (w0, w1, w2, -)
     __shared__ __align__(16) float w_pred[SV_CIN * A2];                           // [co][j]
     __shared__ float b_conv[SV_CIN], b_pred[A2];
     __shared__ float s_inv[SV_INV_TAB];
+    __shared__ __align__(16) float4 s_halo[2][2];        // [buffer][subject | object]: the box right behind the pass
+    __shared__ float s_carry[2][2][SV_CIN];              // [pass & 1][col 510 | 511]: a pass's last two tile columns
 
     const int tid = threadIdx.x;
     const int64_t r = blockIdx.x;
@@ -124,61 +130,71 @@ survivor_rows_kernel(const int64_t* __restrict__ table, int nv, const float4* __
     const int a = max(ps, qs), b = min(pe, qe);                 // temporal overlap window [a, b)
     const uint32_t len = b > a ? (uint32_t)(b - a) : 0u;
     const int a4 = a & ~3;
+    const int w0 = a - a4;                                      // tile column of the window's first frame
 
-    // ---- the eight channels over the window, 512 frames per pass, into the shared-memory tile ----
-    // All boxes of the window (both tracklets, + one halo frame) are fetched up front with 16-byte async copies:
-    // one memory round trip per row instead of one per pass - under the all-pairs kernel's store stream an L2 hit
-    // takes microseconds, and the 4 warps of this CTA cannot hide four of them in a row.  Block p of shared
-    // memory holds the 512 subject and 512 object boxes of pass p (128-byte swizzle, as the all-pairs kernel's
-    // TMA stages: conflict-free LDS.128 at a 64-byte thread stride); once every thread has its boxes in
-    // registers, the block is overwritten in place by the pass's [8][512] tile - same 16 KB.
     const float4* bs = boxes + row[TSPN_VT_BOX_OFF] + (int64_t)s * tb;
     const float4* bo = boxes + row[TSPN_VT_BOX_OFF] + (int64_t)o * tb;
     const int last = (int)tb - 1;                               // frames >= b are masked: any in-row box will do
     const int n_pass = len ? (b - a4 + SV_CHUNK - 1) / SV_CHUNK : 0;
     const uint32_t base = smem_u32(smem);
-    if (n_pass) {
-        for (int idx = tid; idx < n_pass * SV_CHUNK + 1; idx += SV_THREADS) {
-            const int f = min(a4 + idx, last);
-            const uint32_t lin = base + (uint32_t)(idx >> 9) * SV_BLOCK_BYTES + (uint32_t)(idx & (SV_CHUNK - 1)) * 16u;
+
+    // boxes of pass q (both tracklets, 512 frames + the halo box behind them) -> block q & 1, 128-byte swizzle as
+    // the all-pairs kernel's TMA stages (conflict-free LDS.128 at a 64-byte thread stride)
+    auto prefetch = [&](int q) {
+        const uint32_t blk = base + (uint32_t)(q & 1) * SV_BLOCK_BYTES;
+        const int f0 = a4 + q * SV_CHUNK;
+        for (int idx = tid; idx < SV_CHUNK; idx += SV_THREADS) {
+            const int f = min(f0 + idx, last);
+            const uint32_t lin = blk + (uint32_t)idx * 16u;
             cp_async16(swizzle128(lin), bs + f);
             cp_async16(swizzle128(lin + SV_HALF), bo + f);
         }
+        if (tid < 2) cp_async16(smem_u32(&s_halo[q & 1][tid]), (tid ? bo : bs) + min(f0 + SV_CHUNK, last));
         asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();
+    };
+
+    // ---- per-thread streaming state ---------------------------------------------------------------------
+    // pooled bins tid, tid + 128, ...: bin index, next frame (window-relative) to add, partial sums
+    int bin = tid;
+    uint32_t bin_f = len ? ((uint32_t)bin * len) / TSPN_REL_BINS : 0u;
+    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (len == 0) {                                // no temporal overlap: every pooled bin is zero
+        for (int i = tid; i < TSPN_REL_BINS; i += SV_THREADS)
+#pragma unroll
+            for (int c = 0; c < 6; ++c) outb[c * TSPN_REL_BINS + i] = __float2bfloat16(0.0f);
     }
+    if (n_pass) prefetch(0);
     for (int pass = 0; pass < n_pass; ++pass) {
+        const uint32_t blk = base + (uint32_t)(pass & 1) * SV_BLOCK_BYTES;
+        float* const tile = reinterpret_cast<float*>(smem + (size_t)(pass & 1) * SV_BLOCK_BYTES);   // [8][512]
+        if (pass + 1 < n_pass) {
+            prefetch(pass + 1);                     // the other block: its tile (pass - 1) was consumed before the
+            asm volatile("cp.async.wait_group 1;" ::: "memory");    // barrier that ended the previous iteration
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
         const int j0 = tid * GEO_FPT;
         float out[TSPN_GEO_CHANNELS][GEO_FPT];
         float fi, fs, fo;
-        // box j of this pass: j = 512 is the first frame of the next block (or the halo slot)
-        auto load_s = [base, pass](int j) {
-            return ld_box(base + (uint32_t)(pass + (j >> 9)) * SV_BLOCK_BYTES, j & (SV_CHUNK - 1));
-        };
-        auto load_o = [base, pass](int j) {
-            return ld_box(base + (uint32_t)(pass + (j >> 9)) * SV_BLOCK_BYTES + SV_HALF, j & (SV_CHUNK - 1));
-        };
+        const float4 halo_s = s_halo[pass & 1][0], halo_o = s_halo[pass & 1][1];
+        auto load_s = [blk, halo_s](int j) { return j < SV_CHUNK ? ld_box(blk, j) : halo_s; };
+        auto load_o = [blk, halo_o](int j) { return j < SV_CHUNK ? ld_box(blk + SV_HALF, j) : halo_o; };
         geo_step<false>(load_s, load_o, j0, a4 + pass * SV_CHUNK + j0, a, b, out, fi, fs, fo);
         __syncthreads();                                        // every thread of the pass holds its boxes
 #pragma unroll
         for (int ch = 0; ch < TSPN_GEO_CHANNELS; ++ch)
-            *reinterpret_cast<float4*>(&tile_at(tile, ch, pass * SV_CHUNK + j0)) =
-                make_float4(out[ch][0], out[ch][1], out[ch][2], out[ch][3]);
-    }
-    __syncthreads();
+            *reinterpret_cast<float4*>(tile + ch * SV_CHUNK + j0) = make_float4(out[ch][0], out[ch][1], out[ch][2], out[ch][3]);
+        __syncthreads();
 
-    // ---- relative block: bin i of the six pooled channels (0,1 | 2,3 | 5,6) shares its frame range ----
-    const int w0 = a - a4;                                      // column of the window's first frame
-    for (int i = tid; i < TSPN_REL_BINS; i += SV_THREADS) {
-        float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (len > 0) {
-            const uint32_t st = ((uint32_t)i * len) / TSPN_REL_BINS;              // len < 2^22: fits 32 bits
-            const uint32_t en = ((uint32_t)(i + 1) * len + TSPN_REL_BINS - 1) / TSPN_REL_BINS;
-            const uint32_t width = en - st;
-            const float inv = width < SV_INV_TAB ? s_inv[width] : 1.0f / (float)width;
-            for (uint32_t f = st; f < en; ++f) {                                  // ascending frames
-                const float* x = &tile_at(tile, 0, w0 + (int)f);
+        // ---- relative block: the frames of this pass, added to the bins they belong to, ascending ----
+        const uint32_t f_end = (uint32_t)min((int)len, (pass + 1) * SV_CHUNK - w0);    // first frame NOT in this tile
+        const int col0 = pass * SV_CHUNK - w0;                  // frame f sits in tile column f - col0
+        while (bin < TSPN_REL_BINS) {
+            const uint32_t en = ((uint32_t)(bin + 1) * len + TSPN_REL_BINS - 1) / TSPN_REL_BINS;
+            const uint32_t stop = min(en, f_end);
+            for (uint32_t f = bin_f; f < stop; ++f) {           // ascending frames
+                const float* x = tile + ((int)f - col0);
                 acc[0] += x[0];
                 acc[1] += x[SV_CHUNK];
                 acc[2] += x[2 * SV_CHUNK];
@@ -186,11 +202,50 @@ survivor_rows_kernel(const int64_t* __restrict__ table, int nv, const float4* __
                 acc[4] += x[5 * SV_CHUNK];
                 acc[5] += x[6 * SV_CHUNK];
             }
+            if (stop < en) {                                    // the bin continues in the next pass
+                bin_f = max(bin_f, stop);
+                break;
+            }
+            const uint32_t st = ((uint32_t)bin * len) / TSPN_REL_BINS;
+            const uint32_t width = en - st;
+            const float inv = width < SV_INV_TAB ? s_inv[width] : 1.0f / (float)width;
 #pragma unroll
-            for (int c = 0; c < 6; ++c) acc[c] *= inv;
+            for (int c = 0; c < 6; ++c) {
+                outb[c * TSPN_REL_BINS + bin] = __float2bfloat16(acc[c] * inv);
+                acc[c] = 0.0f;
+            }
+            bin += SV_THREADS;
+            bin_f = bin < TSPN_REL_BINS ? ((uint32_t)bin * len) / TSPN_REL_BINS : 0u;
+            if (bin < TSPN_REL_BINS && bin_f >= f_end) break;   // its first frame is in a later pass
         }
+
+        // ---- span proposals: the locations whose right-hand tap lies in this pass ----
+        for (int l = tid; l < n_loc; l += SV_THREADS) {
+            const float ac = __fmul_rn((float)l, stride);
+            const int t = min((int)floorf(ac), t_len - 1);
+            int home = (t + 1 - a4) >> 9;                       // pass of frame t + 1 (floor division by 512)
+            home = max(0, min(home, n_pass - 1));
+            if (home != pass) continue;
+            const bool has_m = t > 0, has_p = t + 1 < t_len;
+            float xv[SV_CIN][3];
 #pragma unroll
-        for (int c = 0; c < 6; ++c) outb[c * TSPN_REL_BINS + i] = __float2bfloat16(acc[c]);
+            for (int d = 0; d < 3; ++d) {
+                const int f = t - 1 + d;
+                const bool in = f >= a && f < b;                 // every channel is 0 outside the window
+                const int col = f - a4 - pass * SV_CHUNK;        // >= -2 for an in-window frame of this location
+#pragma unroll
+                for (int ci = 0; ci < SV_CIN; ++ci)
+                    xv[ci][d] = !in ? 0.0f : (col >= 0 ? tile[ci * SV_CHUNK + col] : s_carry[(pass - 1) & 1][col + 2][ci]);
+            }
+            int32_t res[A2];
+            span_location<SV_CIN, A>(xv, has_m, has_p, w_conv, w_pred, b_conv, b_pred, sizes, ac, t_len, res);
+#pragma unroll
+            for (int j = 0; j < A2; ++j) sp_row[l * A2 + j] = res[j];
+        }
+        // this pass's last two columns for the next pass's left-hand taps (its own copy: the readers of this pass
+        // use the other one), before the barrier after which the block may be refilled
+        if (tid < 2 * SV_CIN) s_carry[pass & 1][tid >> 3][tid & 7] = tile[(tid & 7) * SV_CHUNK + SV_CHUNK - 2 + (tid >> 3)];
+        __syncthreads();                                        // tile consumed: the next iteration refills this block
     }
     for (int64_t q = TSPN_REL_DIM + tid; q < ld_rel; q += SV_THREADS) outb[q] = __float2bfloat16(0.0f);
     if (row_bias) {
@@ -198,24 +253,19 @@ survivor_rows_kernel(const int64_t* __restrict__ table, int nv, const float4* __
         const float* a_o = terms_o + to * n_out;                 // A_o of the object tracklet
         for (int c = tid; c < n_out; c += SV_THREADS) bias_row[c] = __ldg(a_s + c) + __ldg(a_o + c);
     }
-
-    // ---- span proposals: the head at the anchor columns floor(l * stride), decoded in registers ----
-    for (int l = tid; l < n_loc; l += SV_THREADS) {
-        const float ac = __fmul_rn((float)l, stride);
-        const int t = min((int)floorf(ac), t_len - 1);
-        const bool has_m = t > 0, has_p = t + 1 < t_len;
-        float xv[SV_CIN][3];
+    if (n_pass == 0) {
+        // no temporal overlap: every input of the span head is zero (the window is empty)
+        for (int l = tid; l < n_loc; l += SV_THREADS) {
+            const float ac = __fmul_rn((float)l, stride);
+            const int t = min((int)floorf(ac), t_len - 1);
+            float xv[SV_CIN][3];
 #pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            const int f = t - 1 + d;
-            const bool in = f >= a && f < b;                     // every channel is 0 outside the window
+            for (int ci = 0; ci < SV_CIN; ++ci) xv[ci][0] = xv[ci][1] = xv[ci][2] = 0.0f;
+            int32_t res[A2];
+            span_location<SV_CIN, A>(xv, t > 0, t + 1 < t_len, w_conv, w_pred, b_conv, b_pred, sizes, ac, t_len, res);
 #pragma unroll
-            for (int ci = 0; ci < SV_CIN; ++ci) xv[ci][d] = in ? tile_at(tile, ci, f - a4) : 0.0f;
+            for (int j = 0; j < A2; ++j) sp_row[l * A2 + j] = res[j];
         }
-        int32_t res[A2];
-        span_location<SV_CIN, A>(xv, has_m, has_p, w_conv, w_pred, b_conv, b_pred, sizes, ac, t_len, res);
-#pragma unroll
-        for (int j = 0; j < A2; ++j) sp_row[l * A2 + j] = res[j];
     }
 }
 
@@ -252,13 +302,8 @@ using namespace tspn;
 
 extern "C" {
 
-// shared memory of one CTA: the blocks that cover a window of up to max_frames + 3 frames + the halo slot
-static int64_t sv_smem_bytes(int max_frames) {
-    return (((int64_t)max_frames + 3 + SV_CHUNK - 1) / SV_CHUNK) * SV_BLOCK_BYTES + SV_HALO_BYTES;
-}
-
 int tspn_survivor_rows_supported(int max_frames, int n_anchors) {
-    return n_anchors == 4 && max_frames > 0 && sv_smem_bytes(max_frames) <= SV_SMEM_MAX;
+    return n_anchors == 4 && max_frames > 0 && max_frames <= SV_MAX_PASSES * SV_CHUNK;
 }
 
 int tspn_gather_pair_terms(const int64_t* d_table, int num_videos, const int64_t* d_rows, int64_t n_rows,
@@ -301,7 +346,7 @@ int tspn_survivor_rows(const int64_t* d_table, int num_videos, int max_frames, c
         TSPN_REQUIRE(ld_spans >= (int64_t)span_locations(max_frames, stride) * 2 * n_anchors, TSPN_ESHAPE,
                      "tspn_survivor_rows: ld_spans=%lld < locations(max_frames) * 2A", (long long)ld_spans);
     }
-    const int smem = (int)sv_smem_bytes(max_frames);
+    const int smem = SV_SMEM_BYTES;
     TSPN_CUDA_OK(cudaFuncSetAttribute(survivor_rows_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     prefer_max_smem(survivor_rows_kernel<4>);
     survivor_rows_kernel<4><<<(unsigned)n_rows, SV_THREADS, smem, (cudaStream_t)stream>>>(

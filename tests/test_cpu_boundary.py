@@ -97,7 +97,16 @@ def test_host_batch_packing():
     # compact transport: integer boxes as u16, integer motion counts as u8 - lossless, fewer bytes
     hc = HostBatch.from_videos(vids, pin=False)
     assert hc.boxes_compact and hc.motion_compact and hc.h2d_bytes() < hb.h2d_bytes() // 2
-    np.testing.assert_array_equal(hc.boxes.numpy().view(np.uint16).astype(np.float32), b)
+    # ... and span-packed: only the frames [pstart, pend) of every tracklet travel, tracklet after tracklet
+    packed = hc.boxes.numpy().view(np.uint16).astype(np.float32)
+    off = hc.box_off.numpy()
+    trk = 0
+    for v in (vids[0], vids[2]):
+        for n in range(v.n_tracklets):
+            ps, pe = v.span[n]
+            np.testing.assert_array_equal(packed[off[trk]:off[trk] + pe - ps], v.boxes[n, ps:pe])
+            trk += 1
+    assert hc.packed_boxes == sum(int((v.span[:, 1] - v.span[:, 0]).sum()) for v in vids) < b.shape[0]
     np.testing.assert_array_equal(hc.motion.numpy().astype(np.float32), hb.motion.numpy())
     np.testing.assert_array_equal(hc.cls.numpy(), hb.cls.numpy())
     # values that are not exactly representable travel as fp32
