@@ -60,8 +60,11 @@ __device__ __forceinline__ uint32_t swizzle128(uint32_t lin) { return lin ^ (((l
 // (the two taps before it come from the tile or from the last two columns of the previous pass, carried over).
 // 32 KB of shared memory per CTA whatever the video length, instead of 16 KB per 512 frames of the LONGEST video of
 // the batch (72 KB at T = 2000): two CTAs fit beside the all-pairs kernel's CTA where one did.
+#ifndef TSPN_SV_MIN_CTAS
+#define TSPN_SV_MIN_CTAS 6          // 6 CTAs of 128 threads per SM: <= 80 registers (16 bytes of spills) - two CTAs fit in
+#endif                              // the 20 480 registers a pair kernel at 88 leaves; 5 gives 96 registers, no spills
 template <int A>
-__global__ void __launch_bounds__(SV_THREADS, 5)
+__global__ void __launch_bounds__(SV_THREADS, TSPN_SV_MIN_CTAS)
 survivor_rows_kernel(const int64_t* __restrict__ table, int nv, const float4* __restrict__ boxes,
                      const int32_t* __restrict__ span, const int64_t* __restrict__ rows, int64_t rows_per_video,
                      __nv_bfloat16* __restrict__ rel, int64_t ld_rel, const float* __restrict__ terms_s,
@@ -102,6 +105,8 @@ survivor_rows_kernel(const int64_t* __restrict__ table, int nv, const float4* __
         for (int64_t i = (int64_t)n_loc * A2 + tid; i < ld_spans; i += SV_THREADS) sp_row[i] = 0;
     }
     if (tid < SV_INV_TAB) s_inv[tid] = 1.0f / (float)(tid ? tid : 1);
+    __syncthreads();                               // weights and tables staged (a row without a window never reaches
+                                                   // the barriers of the pass loop)
 
     if (gp < 0) {                                  // padding row (K_eff < K): zero block, zero bias, zero regressions
         for (int64_t q = tid; q < ld_rel; q += SV_THREADS) outb[q] = __float2bfloat16(0.0f);

@@ -201,5 +201,47 @@ def main():
     print("size", os.path.getsize(path))
 
 
+def main_headline():
+    """The same functions of the unmodified reference at the HEADLINE shape (BASELINE.json configs[2]: N=64, T=2000,
+    80 classes, 50 predicates, F=11160) -> reference_outputs_headline.npz (kept in its own file so that
+    reference_outputs.npz regenerates bit for bit)."""
+    _install_stubs()
+    import torch
+    from lib.modeling.trajectory import cubic_iou
+    from lib.evaluation.common import viou
+    from lib.modeling.model import RelationPredictor
+    from lib.modeling.relpn.ppn import PPNHead
+    from tspn_b200 import synth
+    from oracle.geometry import enumerate_pairs
+
+    torch.set_num_threads(1)
+    n, t, c, r, seed = 64, 2000, 80, 50, 0
+    out = {}
+    v = synth.make_video(n, t, c, seed=seed, full_span=True)
+    out["cubic_iou_f32_C"] = cubic_iou(v.boxes, v.boxes)                      # [64, 64], V1
+    vr = synth.make_video(n, t, c, seed=seed + 1)                             # ragged spans: V2 on a sample of pairs
+    pairs = enumerate_pairs(n)
+    sel = np.sort(np.random.Generator(np.random.PCG64(5)).choice(pairs.shape[0], size=96, replace=False))
+    lists = [[tuple(int(q) for q in row) for row in vr.boxes[i, vr.span[i, 0]:vr.span[i, 1]]] for i in range(n)]
+    out["viou_v2_C_rows"] = sel.astype(np.int64)
+    out["viou_v2_C"] = np.array([viou(lists[s], tuple(vr.span[s]), lists[o], tuple(vr.span[o])) for s, o in pairs[sel]])
+    fdim = synth.feature_dim(c)
+    sd = {k: torch.from_numpy(vv) for k, vv in synth.make_weights(c, r, fdim, dpn_in=8, n_anchors=4, seed=seed).items()}
+    head = PPNHead(c, 64, c)
+    head.load_state_dict({k.split("ppn_head.")[1]: vv for k, vv in sd.items() if "ppn_head" in k})
+    with torch.no_grad():
+        out["ppn_scores_C"] = head(torch.from_numpy(v.cls), torch.from_numpy(v.cls)).numpy()
+    clf = RelationPredictor(fdim, r)
+    clf.load_state_dict({k.split("classifier.")[1]: vv for k, vv in sd.items() if k.startswith("classifier.")})
+    with torch.no_grad():
+        out["rel_logits_C"] = clf(torch.from_numpy(synth_features(n * (n - 1), fdim, seed))).numpy()    # [4032, 50]
+    path = os.path.join(HERE, "reference_outputs_headline.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, {k: getattr(vv, "shape", None) for k, vv in out.items()}, "size", os.path.getsize(path))
+
+
 if __name__ == "__main__":
-    main()
+    if "--headline" in sys.argv:
+        main_headline()
+    else:
+        main()
