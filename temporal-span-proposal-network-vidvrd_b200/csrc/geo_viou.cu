@@ -324,7 +324,7 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
 // depending on unrelated edits - and 105 is allocated as 112, which locks the side branch out of 140 of the 148
 // SMs (measured: survivor_rows 0.42 -> 0.58 ms, step 0.74 -> 0.97 ms).
 #ifndef TSPN_GEO_MAXNREG
-#define TSPN_GEO_MAXNREG 104
+#define TSPN_GEO_MAXNREG 88
 #endif
 template <bool WRITE_GEO, bool CLIP>
 __global__ void __maxnreg__(TSPN_GEO_MAXNREG)
