@@ -412,21 +412,29 @@ def t_class(t: int) -> int:
     return T_CLASSES[-1]
 
 
-def pack_batches(shapes: Sequence[Tuple[int, int]], geo_budget_bytes: int = 4 << 30,
-                 max_videos: int = 64) -> List[Tuple[int, List[int]]]:
+def pack_batches(shapes: Sequence[Tuple[int, int]], geo_budget_bytes: int = 4 << 30, max_videos: int = 64,
+                 merge_below_bytes: int = 512 << 20) -> List[Tuple[int, List[int]]]:
     """Split ragged videos ``(N_i, T_i)`` into batches: ``[(t_class, [video indices]), ...]``.
 
     Videos are grouped by chunk class and, inside a class, taken in descending cost order (first-fit into the
     open batch) until the batch's geometry output (32 B per pair-frame) would exceed ``geo_budget_bytes`` or it
-    holds ``max_videos`` videos.  A video larger than the budget gets a batch of its own.  Deterministic."""
+    holds ``max_videos`` videos.  A video larger than the budget gets a batch of its own.  A class whose videos
+    add up to less than ``merge_below_bytes`` of geometry is merged into the next larger class: a batch has a fixed
+    cost (its side chain is latency-bound, ~0.5 ms however small the batch), which outweighs staging short videos in
+    a longer chunk when there is little of them - the case of a rank's shard in a many-GPU run.  Deterministic."""
+    def geo_bytes(i):
+        n, t = shapes[i]
+        return int(n) * max(int(n) - 1, 0) * ((int(t) + 3) // 4 * 4) * 32
     by_class = {}
     for i, (n, t) in enumerate(shapes):
         by_class.setdefault(t_class(int(t)), []).append(i)
+    classes = sorted(by_class)
+    for k, c in enumerate(classes[:-1]):
+        if by_class[c] and sum(geo_bytes(i) for i in by_class[c]) < merge_below_bytes:
+            by_class[classes[k + 1]].extend(by_class[c])
+            by_class[c] = []
     out: List[Tuple[int, List[int]]] = []
-    for c in sorted(by_class):
-        def geo_bytes(i):
-            n, t = shapes[i]
-            return int(n) * max(int(n) - 1, 0) * ((int(t) + 3) // 4 * 4) * 32
+    for c in classes:
         order = sorted(by_class[c], key=lambda i: (-geo_bytes(i), i))
         cur, cur_bytes = [], 0
         for i in order:

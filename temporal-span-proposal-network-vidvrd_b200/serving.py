@@ -197,11 +197,12 @@ class PipelinedStage:
 
 
 def host_batches_for(videos: Sequence, n_classes: int, geo_budget_bytes: int = 4 << 30, max_videos: int = 64,
-                     capacities: Optional[Dict[int, Capacity]] = None, pin: bool = True):
+                     capacities: Optional[Dict[int, Capacity]] = None, pin: bool = True,
+                     merge_below_bytes: int = 512 << 20):
     """Ragged videos -> ``(host batches, [video indices of each batch], {t_class: Capacity})``: the videos are packed
     into batches per chunk class (``batch.pack_batches``), one capacity per class holds all of them."""
     shapes = [(int(v.boxes.shape[0]), int(v.boxes.shape[1])) for v in videos]
-    batches = pack_batches(shapes, geo_budget_bytes, max_videos)
+    batches = pack_batches(shapes, geo_budget_bytes, max_videos, merge_below_bytes)
     caps = capacities or bucket_capacities(shapes, batches, n_classes)
     hosts = [HostBatch.from_videos([videos[i] for i in vids], pin=pin, capacity=caps[c]) for c, vids in batches]
     return hosts, [vids for _, vids in batches], caps

@@ -10,20 +10,25 @@ from tspn_b200.batch import Capacity, HostBatch, bucket_capacities, pack_batches
 
 def test_pack_batches_respects_classes_and_budget():
     shapes = synth.config_shapes("vidor_val", 0, 200)
-    batches = pack_batches(shapes, geo_budget_bytes=1 << 30, max_videos=32)
+    batches = pack_batches(shapes, geo_budget_bytes=1 << 30, max_videos=32, merge_below_bytes=0)
     seen = sorted(i for _, vids in batches for i in vids)
     assert seen == list(range(len(shapes)))                              # every video exactly once
     for c, vids in batches:
         assert all(t_class(shapes[i][1]) == c for i in vids) and len(vids) <= 32
         geo = sum(shapes[i][0] * (shapes[i][0] - 1) * ((shapes[i][1] + 3) // 4 * 4) * 32 for i in vids)
         assert geo <= (1 << 30) or len(vids) == 1                        # only a single oversized video may exceed
-    assert pack_batches(shapes, 1 << 30, 32) == batches                  # deterministic
+    assert pack_batches(shapes, 1 << 30, 32, 0) == batches               # deterministic
+    # a class with little geometry joins the next larger one (fewer, fuller batches): still every video once,
+    # never in a smaller chunk than its own
+    merged = pack_batches(shapes[:40], geo_budget_bytes=1 << 30, max_videos=32, merge_below_bytes=1 << 40)
+    assert sorted(i for _, vids in merged for i in vids) == list(range(40))
+    assert {c for c, _ in merged} == {2048} and all(t_class(shapes[i][1]) <= c for c, vids in merged for i in vids)
     assert [t_class(t) for t in (1, 512, 513, 1024, 1025, 2048, 4096)] == [512, 512, 1024, 1024, 2048, 2048, 2048]
 
 
 def test_capacity_holds_every_batch_of_its_class():
     shapes = synth.config_shapes("vidvrd_test", 0, 60)
-    batches = pack_batches(shapes, geo_budget_bytes=64 << 20, max_videos=8)
+    batches = pack_batches(shapes, geo_budget_bytes=64 << 20, max_videos=8, merge_below_bytes=0)
     caps = bucket_capacities(shapes, batches, 35)
     for c, vids in batches:
         cap = caps[c]

@@ -153,7 +153,7 @@ def test_serving_loop_over_buckets_matches_eager():
     shapes = [(n, t) for n, t in synth.config_shapes("vidvrd_test", 3, 40)]
     vids = [synth.make_video(n, t, C, seed=200 + i) for i, (n, t) in enumerate(shapes)]
     st = _stage("tensor", anchor_sizes=VIDVRD[0], anchor_stride=VIDVRD[1])
-    hosts, batch_vids, caps = host_batches_for(vids, C, geo_budget_bytes=48 << 20, max_videos=6)
+    hosts, batch_vids, caps = host_batches_for(vids, C, geo_budget_bytes=48 << 20, max_videos=6, merge_below_bytes=0)
     assert len(caps) >= 2 and len(hosts) > len(caps)
     want = [_outputs(st.forward(HostBatch.from_videos([vids[i] for i in ids]).to_device("cuda"))) for ids in batch_vids]
     pipe = PipelinedStage(st, [hosts[[h.capacity for h in hosts].index(c)] for c in caps.values()], depth=2)

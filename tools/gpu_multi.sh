@@ -9,5 +9,5 @@ TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr
 timeout 900 $TR bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_single_n$N.json 2> gpurun_out/${TAG}_bench_single_n$N.err; echo "rc=$?"; tail -2 gpurun_out/${TAG}_bench_single_n$N.err
 timeout 900 $TR bench.py --gpus $N --workload vidor_val --steps 5 --warmup 3 > gpurun_out/${TAG}_bench_val_n$N.json 2> gpurun_out/${TAG}_bench_val_n$N.err; echo "rc=$?"; tail -2 gpurun_out/${TAG}_bench_val_n$N.err
 timeout 900 $TR tools/e2e_limiter.py --steps 200 > gpurun_out/${TAG}_limiter_n$N.jsonl 2> gpurun_out/${TAG}_limiter_n$N.err; echo "rc=$?"; tail -2 gpurun_out/${TAG}_limiter_n$N.err
-timeout 900 $TR tools/e2e_limiter.py --steps 200 --no-affinity > gpurun_out/${TAG}_limiter_noaff_n$N.jsonl 2>> gpurun_out/${TAG}_limiter_n$N.err
+
 cat gpurun_out/${TAG}_bench_single_n$N.json gpurun_out/${TAG}_bench_val_n$N.json gpurun_out/${TAG}_limiter_n$N.jsonl | cut -c1-700
