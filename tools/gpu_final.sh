@@ -7,9 +7,10 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv
 timeout 1700 python -m pytest tests -m gpu -q > $O/r2_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 $O/r2_pytest.log
 timeout 600 python bench.py --steps 20 --warmup 5 > $O/r2_bench_vidor_single.json 2> $O/r2_bench_vidor_single.err; echo "bench rc=$?"; tail -2 $O/r2_bench_vidor_single.err
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $O/r2_bench_reference_arm.json 2> $O/r2_bench_reference_arm.err
-for W in vidvrd_single vidvrd_test vidor_val stress; do
+for W in vidvrd_single vidvrd_test vidor_val stress baseline_yaml; do
   timeout 900 python bench.py --workload $W --steps 5 --warmup 3 > $O/r2_bench_$W.json 2> $O/r2_bench_$W.err; echo "bench $W rc=$?"
 done
+timeout 600 python bench.py --workload baseline_yaml --precision tensor --steps 5 --warmup 3 > $O/r2_bench_baseline_yaml_tensor.json 2>/dev/null
 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --span-proposals 0 > $O/r2_bench_vidor_single_no_nms.json 2>/dev/null
 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --relationness tensor > $O/r2_bench_vidor_single_tc_relationness.json 2>/dev/null
 timeout 600 python bench.py --steps 2000 --warmup 20 --no-cpu-baseline > $O/r2_bench_vidor_single_sustained.json 2>/dev/null
