@@ -54,6 +54,10 @@ class RelationPredictor(nn.Module):
         if self.training:
             return torch.sigmoid(self.rel_predictor(reloi_feats))
         dev = compute_device(reloi_feats)
+        with torch.cuda.device(dev):            # the library launches on the current device's current stream
+            return self._forward_cuda(reloi_feats, dev)
+
+    def _forward_cuda(self, reloi_feats, dev):
         x = reloi_feats.detach().to(dev)
         if x.dtype not in (torch.float32, torch.bfloat16):
             x = x.float()
@@ -129,6 +133,10 @@ class BaseModel(nn.Module):
                              "boxes/span/track_cls_logits/motion")
         if cfg.use_dpn and not have_trk:
             raise ValueError("RELPN.USE_DPN needs the tracklet fields 'boxes' and 'span' on every PairList")
+        with torch.cuda.device(dev):            # the library launches on the current device's current stream
+            return self._forward_cuda(pair_list, dev, on_cuda, have_feats, cfg)
+
+    def _forward_cuda(self, pair_list, dev, on_cuda, have_feats, cfg):
         stage = self.stage(dev)
         batch = batch_from_pair_lists(pair_list, dev, need_motion=not have_feats)
         feats = None

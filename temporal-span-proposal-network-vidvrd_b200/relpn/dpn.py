@@ -31,10 +31,11 @@ class DPNHead(nn.Module):
         if self.training:
             return self.duration_pred(F.relu(self.conv(feats)))
         dev = compute_device(feats)
-        x = feats.detach().to(dev, torch.float32)
-        cw, cb, pw, pb = self.device_weights(dev)
-        out = ops.span_head(x, cw, cb, pw, pb, precision=self.precision)
-        return like_input(out, feats.is_cuda)
+        with torch.cuda.device(dev):            # the library launches on the current device's current stream
+            x = feats.detach().to(dev, torch.float32)
+            cw, cb, pw, pb = self.device_weights(dev)
+            out = ops.span_head(x, cw, cb, pw, pb, precision=self.precision)
+            return like_input(out, feats.is_cuda)
 
 
 class DPN(nn.Module):
@@ -65,6 +66,10 @@ class DPN(nn.Module):
             raise ValueError("DPN needs the dense tracklet fields 'boxes' and 'span' on every PairList")
         ref = pair_list[0].get_field("boxes")
         dev = compute_device(ref)
+        with torch.cuda.device(dev):
+            return self._forward_cuda(pair_list, ref, dev)
+
+    def _forward_cuda(self, pair_list, ref, dev):
         batch = batch_from_pair_lists(pair_list, dev, need_motion=False)
         geom = ops.pair_geometry(batch, write_geo=True)
         cw, cb, pw, pb = self.dpn_head.device_weights(dev)

@@ -30,6 +30,10 @@ class PPNHead(nn.Module):
         if self.training:       # training is outside the CUDA path
             return torch.sigmoid(torch.mm(self.sub_emb(sub_logits), self.obj_emb(obj_logits).t()))
         dev = compute_device(sub_logits, obj_logits)
+        with torch.cuda.device(dev):            # the library launches on the current device's current stream
+            return self._forward_cuda(sub_logits, obj_logits, dev)
+
+    def _forward_cuda(self, sub_logits, obj_logits, dev):
         same = sub_logits is obj_logits or (sub_logits.data_ptr() == obj_logits.data_ptr()
                                              and sub_logits.shape == obj_logits.shape)
         ns, no = int(sub_logits.shape[0]), int(obj_logits.shape[0])
@@ -63,6 +67,10 @@ class PPN(nn.Module):
     def _forward_test(self, pair_list):
         cls0 = pair_list[0].get_field("track_cls_logits")
         dev = compute_device(cls0)
+        with torch.cuda.device(dev):
+            return self._forward_cuda(pair_list, cls0, dev)
+
+    def _forward_cuda(self, pair_list, cls0, dev):
         batch = batch_from_pair_lists(pair_list, dev, need_motion=False)
         scores = ops.relationness(batch, self.ppn_head.device_weights(dev))
         idx, _, _ = ops.topk_pairs(batch, scores, int(self.num_pair_proposals), exclude_diagonal=False)

@@ -34,7 +34,8 @@ class RelNMS(nn.Module):
         if not duration_proposals.is_cuda:
             ops.require_device()
             dev = torch.device("cuda", torch.cuda.current_device())
-        kept, _ = ops.span_select(duration_proposals.to(dev, torch.int32), self.n_anchors, self.anchor_stride,
-                                  int(self.top_k_proposals), self.nms_threshold,
-                                  windows=windows.to(dev, torch.int32))
+        with torch.cuda.device(dev):            # the library launches on the current device's current stream
+            kept, _ = ops.span_select(duration_proposals.to(dev, torch.int32), self.n_anchors, self.anchor_stride,
+                                      int(self.top_k_proposals), self.nms_threshold,
+                                      windows=windows.to(dev, torch.int32))
         return kept if duration_proposals.is_cuda else kept.cpu()

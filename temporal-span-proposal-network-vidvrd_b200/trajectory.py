@@ -138,8 +138,10 @@ def viou_batch(trajs, durations, pairs, clipped: bool = False, f64: bool = False
 
 
 def viou(traj_1, duration_1, traj_2, duration_2) -> float:
-    """Voluminal IoU of two trajectories with durations (evaluation/common.py:65-106)."""
-    return float(viou_batch([traj_1, traj_2], [duration_1, duration_2], [(0, 1)])[0])
+    """Voluminal IoU of two trajectories with durations (evaluation/common.py:65-106).  Goes through the fp64
+    entry point: it accepts box lists longer than their duration (common.py:100-105 sums the volume over the whole
+    list, and association emits such relations) and returns python's float arithmetic bit for bit on integer boxes."""
+    return float(viou_batch([traj_1, traj_2], [duration_1, duration_2], [(0, 1)], f64=True)[0])
 
 
 def _traj_iou(traj_1: Trajectory, traj_2: Trajectory) -> float:
