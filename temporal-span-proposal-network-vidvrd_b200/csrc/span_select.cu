@@ -33,7 +33,9 @@ __host__ __device__ __forceinline__ int ss_locations(int t, float stride) {
     return n;
 }
 
-template <int GPL, bool OUT16>
+// AFIX: the anchor count as a compile-time constant (4, the reference's NUM_ANCHORS_PER_LOCATION) or 0 = run time:
+// the candidate index is split into (location, anchor) once per iteration, and the kernel is issue-bound
+template <int GPL, bool OUT16, int AFIX>
 __global__ void __launch_bounds__(SS_WARPS * 32)
 span_select_kernel(const int64_t* __restrict__ table, int nv, const int32_t* __restrict__ trk_span,
                    const int64_t* __restrict__ rows, int64_t n_rows,
@@ -50,7 +52,8 @@ span_select_kernel(const int64_t* __restrict__ table, int nv, const int32_t* __r
 
     // ---- the row: its pair, its video, its window, its candidate count -------------------------------
     const int64_t gp = rows ? rows[r] : r;
-    int wa = 0, wb = 0, n_loc = 0, A = n_anchors;
+    int wa = 0, wb = 0, n_loc = 0;
+    const int A = AFIX ? AFIX : n_anchors;
     bool live = gp >= 0;
     if (table) {
         if (live && gp >= table_total(table, nv, TSPN_VT_PAIR_OFF)) live = false;      // beyond the batch (capacity grid)
@@ -89,20 +92,21 @@ span_select_kernel(const int64_t* __restrict__ table, int nv, const int32_t* __r
     for (int u = 0; u < GPL; ++u) { gkey[u] = 0u; g_smin[u] = 0x7fffffff; g_emax[u] = 0; g_lmin[u] = 0x7fffffff; g_lmax[u] = 0; }
     const int32_t* crow = cand + r * ld_cand;
     // pass 1: every load of the lane in flight at once (the row's candidates sit in L2: one round trip, not G)
-    for (int j = 0; j < G; ++j) {
-        const int a = j / gpa, l = (j - a * gpa) * 32 + lane;
-        uint32_t key = 0u, pack = 0u;
-        if (l < n_loc) {
-            const int i = l * A + a;
-            const int2 c = __ldg(reinterpret_cast<const int2*>(crow) + i);
-            const int inter = max(0, min(c.y, wb) - max(c.x, wa));
-            const int uni = (c.y - c.x) + wlen - inter;
-            const uint32_t q = uni > 0 ? ((uint32_t)inter << 15) / (uint32_t)uni : 0u;
-            key = (1u << 28) | (q << 12) | (uint32_t)(4095 - i);
-            pack = (uint32_t)c.x | ((uint32_t)c.y << 16);
+    for (int a = 0, j = 0; a < (G ? A : 0); ++a) {
+        for (int l = lane; l < gpa * 32; l += 32, ++j) {      // group j = a * gpa + l / 32 (no division: issue-bound)
+            uint32_t key = 0u, pack = 0u;
+            if (l < n_loc) {
+                const int i = l * A + a;
+                const int2 c = __ldg(reinterpret_cast<const int2*>(crow) + i);
+                const int inter = max(0, min(c.y, wb) - max(c.x, wa));
+                const int uni = (c.y - c.x) + wlen - inter;
+                const uint32_t q = uni > 0 ? ((uint32_t)inter << 15) / (uint32_t)uni : 0u;
+                key = (1u << 28) | (q << 12) | (uint32_t)(4095 - i);
+                pack = (uint32_t)c.x | ((uint32_t)c.y << 16);
+            }
+            keys[j * 32 + lane] = key;
+            se[j * 32 + lane] = pack;
         }
-        keys[j * 32 + lane] = key;
-        se[j * 32 + lane] = pack;
     }
     // pass 2: the groups' bounds and best keys (each lane re-reads its own slots: no barrier needed)
     for (int j = 0; j < G; ++j) {
@@ -129,7 +133,7 @@ span_select_kernel(const int64_t* __restrict__ table, int nv, const int32_t* __r
         m = __reduce_max_sync(0xffffffffu, m);
         if (m == 0u) break;
         const int i = 4095 - (int)(m & 4095u);
-        const int l = A == 4 ? i >> 2 : i / A, a = i - l * A;
+        const int l = i / A, a = i - l * A;               // shifts when A is the compile-time 4
         const int jw = a * gpa + (l >> 5);
         const int pw = jw * 32 + (l & 31);
         const uint32_t w = se[pw];
@@ -217,18 +221,19 @@ int tspn_span_select(const int64_t* d_table, int num_videos, int max_frames, con
     const bool out16 = (flags & TSPN_SPANS_I16) != 0;
     const unsigned blocks = (unsigned)((n_rows + SS_WARPS - 1) / SS_WARPS);
     cudaStream_t st = (cudaStream_t)stream;
-#define TSPN_LAUNCH_SS(GPLV, O16)                                                                                     \
+#define TSPN_LAUNCH_SS(GPLV, O16, AF)                                                                                 \
     do {                                                                                                             \
-        TSPN_CUDA_OK(cudaFuncSetAttribute(span_select_kernel<GPLV, O16>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                          (int)smem));                                                               \
-        prefer_max_smem(span_select_kernel<GPLV, O16>);                                                              \
-        span_select_kernel<GPLV, O16><<<blocks, SS_WARPS * 32, smem, st>>>(                                          \
+        TSPN_CUDA_OK(cudaFuncSetAttribute(span_select_kernel<GPLV, O16, AF>,                                         \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                  \
+        prefer_max_smem(span_select_kernel<GPLV, O16, AF>);                                                          \
+        span_select_kernel<GPLV, O16, AF><<<blocks, SS_WARPS * 32, smem, st>>>(                                      \
             d_table, num_videos, d_span, d_rows, n_rows, d_windows, d_cand, ld_cand, n_cand,                        \
             n_anchors, stride, n_keep, thr_q10, slots, d_out, d_counts);                                             \
     } while (0)
-    if (gpl == 1) { if (out16) TSPN_LAUNCH_SS(1, true); else TSPN_LAUNCH_SS(1, false); }
-    else if (gpl == 2) { if (out16) TSPN_LAUNCH_SS(2, true); else TSPN_LAUNCH_SS(2, false); }
-    else { if (out16) TSPN_LAUNCH_SS(4, true); else TSPN_LAUNCH_SS(4, false); }
+    if (gpl == 1 && n_anchors == 4) { if (out16) TSPN_LAUNCH_SS(1, true, 4); else TSPN_LAUNCH_SS(1, false, 4); }
+    else if (gpl == 1) { if (out16) TSPN_LAUNCH_SS(1, true, 0); else TSPN_LAUNCH_SS(1, false, 0); }
+    else if (gpl == 2) { if (out16) TSPN_LAUNCH_SS(2, true, 0); else TSPN_LAUNCH_SS(2, false, 0); }
+    else { if (out16) TSPN_LAUNCH_SS(4, true, 0); else TSPN_LAUNCH_SS(4, false, 0); }
 #undef TSPN_LAUNCH_SS
     TSPN_CUDA_OK(cudaGetLastError());
     return TSPN_OK;
