@@ -198,8 +198,9 @@ assemble_kernel(const int64_t* __restrict__ table, int nv, const float* __restri
     __shared__ __align__(16) float s_rel[TSPN_REL_DIM];
     __shared__ float s_inv[ASM_INV_TAB];
     const int64_t r = blockIdx.x;
-    const int64_t gp = rows ? rows[r] : r;
-    if (!rows && r >= table_total(table, nv, TSPN_VT_PAIR_OFF)) return;      // the grid is sized for a capacity
+    // the grid is sized for a capacity: rows beyond the batch's pairs are padding rows (written as zeros, so that
+    // whatever runs over the whole buffer behind this kernel reads initialised memory)
+    const int64_t gp = rows ? rows[r] : (r < table_total(table, nv, TSPN_VT_PAIR_OFF) ? r : -1);
     float* out = feat ? feat + r * ld_feat : nullptr;
     __nv_bfloat16* outb = BF16 ? feat_bf16 + r * ld_bf16 : nullptr;
     const int C = n_classes;

@@ -282,8 +282,8 @@ gather_pair_terms_kernel(const int64_t* __restrict__ table, int nv, const int64_
     const int64_t r = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (r >= n_rows) return;
     const int lane = threadIdx.x & 31;
-    const int64_t gp = rows ? rows[r] : r;
-    if (!rows && r >= table_total(table, nv, TSPN_VT_PAIR_OFF)) return;      // the grid is sized for a capacity
+    // the grid is sized for a capacity: rows beyond the batch's pairs are padding rows (zeros)
+    const int64_t gp = rows ? rows[r] : (r < table_total(table, nv, TSPN_VT_PAIR_OFF) ? r : -1);
     float* dst = row_bias + r * n_out;
     if (gp < 0) {
         for (int c = lane; c < n_out; c += 32) dst[c] = 0.0f;
