@@ -273,4 +273,14 @@ def test_stage_survivor_path_equals_stored_row_path(use_dpn, monkeypatch):
         assert torch.equal(a.record_counts, b.record_counts)
         assert (sa - sb).abs().max().item() <= 5e-6
         same = (a.records[..., 1:] == b.records[..., 1:]).all(dim=-1)
-        assert same.float().mean().item() > 0.98
+        # ... and every slot that differs must sit in a near-tie: a neighbouring rank of the same video scores within
+        # the summation-order noise of it (then the two orders are both valid sorts of their own scores)
+        gap = torch.full_like(sa, float("inf"))
+        gap[:, 1:] = torch.minimum(gap[:, 1:], (sa[:, 1:] - sa[:, :-1]).abs())
+        gap[:, :-1] = torch.minimum(gap[:, :-1], (sa[:, 1:] - sa[:, :-1]).abs())
+        last = torch.zeros_like(same)                   # the cut at rank topk_per_video is a near-tie with rank + 1,
+        cnt = a.record_counts.long()                    # which is not in the records: the last kept slot is exempt
+        vid = torch.nonzero(cnt > 0).flatten()
+        last[vid, cnt[vid] - 1] = True
+        assert bool((same | (gap <= 1e-5) | last).all()), "records differ outside near-ties"
+        assert same.float().mean().item() > 0.9
