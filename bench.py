@@ -78,6 +78,12 @@ def parse_args():
     ap.add_argument("--no-affinity", action="store_true", help="do not bind the rank to its GPU's CPU cores")
     ap.add_argument("--reserve-sms", type=int, default=None,
                     help="SMs the persistent all-pairs kernel leaves to the side branches (default: StageConfig's)")
+    ap.add_argument("--collective", default="nccl", choices=["nccl", "peer"],
+                    help="the per-step exchange of the triplet records in the e2e loop (N > 1, weak scaling): one NCCL "
+                         "all-gather, or plain stores into every peer's gather buffer over NVLink (csrc/peer_records.cu)")
+    ap.add_argument("--geo-layout", default="dense", choices=["dense", "windowed"],
+                    help="layout of the per-frame geometry rows: dense [P, 8, Tp] (the parity layout) or windowed "
+                         "(per pair only its overlap window's frames, 7 channels: tspn_pair_geo_viou_windowed)")
     ap.add_argument("--relationness", default="fp32", choices=["fp32", "tensor"],
                     help="PPNHead arithmetic: fp32 exact order (bit-exact top-K) or tcgen05 (tf32 operands)")
     return ap.parse_args()
@@ -409,6 +415,21 @@ def alg_bytes_of(shapes) -> int:
     return tot
 
 
+def alg_bytes_windowed(videos) -> int:
+    """The same for the WINDOWED layout (tspn_pair_geo_viou_windowed): per pair 7 channels x the frames of its overlap
+    window rounded out to multiples of 4, plus the row offset it reads (8 B)."""
+    tot = 0
+    for v in videos:
+        n, t = v.n_tracklets, v.n_frames
+        tb, p = (t + 7) // 8 * 8, n * max(n - 1, 0)
+        a = np.maximum(v.span[:, None, 0], v.span[None, :, 0]).astype(np.int64)
+        b = np.minimum(v.span[:, None, 1], v.span[None, :, 1]).astype(np.int64)
+        lw = np.where(b > a, ((b + 3) & ~3) - (a & ~3), 0)
+        np.fill_diagonal(lw, 0)
+        tot += 28 * int(lw.sum()) + 24 * p + 16 * n * tb + 8 * n
+    return tot
+
+
 def run_baseline_yaml(args, rank, world, local_rank):
     """configs/baseline.yaml as shipped: both proposal nets off, the [P, F] rows precomputed (vrdataset.py:190-217),
     BaseModel = RelationPredictor over every pair (model.py:53-65) + the records of predict.py:66-117."""
@@ -530,7 +551,8 @@ def run_ours(args, rank, world, local_rank):
     sparsify = not args.no_sparsify
     cfg = StageConfig(n_classes=c, n_predicates=r, topk=k, use_ppn=True, use_dpn=True, sparsify=sparsify,
                       precision=args.precision, anchor_sizes=sizes, anchor_stride=stride,
-                      num_span_proposals=args.span_proposals, relationness_precision=args.relationness)
+                      num_span_proposals=args.span_proposals, relationness_precision=args.relationness,
+                      geo_layout=args.geo_layout)
     if args.reserve_sms is not None:
         cfg.geo_reserve_sms = args.reserve_sms
     sd = synth.make_weights(c, r, synth.feature_dim(c), dpn_in=8, seed=0)
@@ -565,7 +587,8 @@ def run_ours(args, rank, world, local_rank):
     # refill of the slot's input arena).
     group = dist.group.WORLD if (world > 1 and scaling == "weak") else None
     pipe = PipelinedStage(stage, templates, device=dev, depth=args.depth, graphs=not args.eager, group=group,
-                          compute_streams=args.compute_streams, single_graph=not args.three_graphs)
+                          compute_streams=args.compute_streams, single_graph=not args.three_graphs,
+                          collective=args.collective)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)    # > 126 MB L2
     n_local = len(videos)
     tpv = cfg.topk_per_video
@@ -662,7 +685,8 @@ def run_ours(args, rank, world, local_rank):
     big = max(range(len(hosts)), key=lambda j: int(hosts[j].actual[_lib.TOT_GEO_FLOATS]))
     bslot = pipe._bucket(hosts[big]).slots[0]
     bslot.batch.copy_from_device(residents[big])
-    geom_alone = bslot.graphed.result.geom if bslot.graphed is not None else ops.pair_geometry_outputs(bslot.batch)
+    geom_alone = bslot.graphed.result.geom if bslot.graphed is not None else \
+        ops.pair_geometry_outputs(bslot.batch, windowed=args.geo_layout == "windowed")
     alone_ms = []
     for i in range(3 + min(args.steps, 10)):
         flush.zero_()
@@ -756,18 +780,20 @@ def run_ours(args, rank, world, local_rank):
         return
     # ---- roofline of the dominant kernel (all-pairs geometry + vIoU) ------------------------------
     my_shapes = [(v.n_tracklets, v.n_frames) for v in videos]
-    alg_bytes = alg_bytes_of(my_shapes)                 # per step of this rank
+    windowed = args.geo_layout == "windowed"
+    alg_bytes = alg_bytes_windowed(videos) if windowed else alg_bytes_of(my_shapes)      # per step of this rank
     geo_ms_step = geo_ms_total / args.steps
     achieved = alg_bytes / (geo_ms_step / 1e3) / 1e9
     peak, peak_src = measured_peak()
-    alone_bytes = alg_bytes_of([my_shapes[i] for i in batch_vids[big]])
+    alone_bytes = alg_bytes_windowed([videos[i] for i in batch_vids[big]]) if windowed else \
+        alg_bytes_of([my_shapes[i] for i in batch_vids[big]])
     alone_gbs = alone_bytes / (float(np.mean(alone_ms)) / 1e3) / 1e9
     cfgd.update({
         "batches_per_step_per_gpu": len(hosts), "pairs_per_step": pairs_global,
         "capacities": {str(cc): {"videos": cap.videos, "pairs": cap.pairs, "geo_gb": cap.geo_floats * 4 / 1e9,
                                  "geo_chunk": cap.geo_chunk, "max_n": cap.max_n, "max_t": cap.max_t}
                        for cc, cap in caps.items()},
-        "precision": args.precision, "relationness_precision": args.relationness,
+        "precision": args.precision, "relationness_precision": args.relationness, "geo_layout": args.geo_layout,
         "geo_reserve_sms": cfg.geo_reserve_sms,
         "sharding": ("per video, LPT on N(N-1)T (imbalance %.4f); NCCL all-gather of the [V,200,8] int32 triplet "
                      "records inside the timed region" % imbalance) if shards is not None else
@@ -785,7 +811,7 @@ def run_ours(args, rank, world, local_rank):
                         "of the pinned input arena goes H2D, results D2H; warm-up and timed steps run back to back, "
                         "the clock covers exactly the timed steps" % (args.depth, args.compute_streams),
         "h2d_transport": "u16 boxes + u8 motion counts (lossless for these inputs), expanded on the device",
-        "cpu_affinity": bound,
+        "cpu_affinity": bound, "collective": args.collective if group is not None else None,
     })
     line = {
         "metric": "tracklet pairs scored/sec", "value": value, "unit": "pairs/s", "n_gpus": world,
@@ -796,7 +822,8 @@ def run_ours(args, rank, world, local_rank):
         "data": "synthetic", "config": cfgd,
         "roofline": {"bound": "hbm", "kernel": "pair_geo_kernel (CUDA events immediately around each launch)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": measured_traffic(args.workload, cfgd["videos"]), "peak_source": peak_src,
+                     "traffic": None if windowed else measured_traffic(args.workload, cfgd["videos"]),
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_step": alg_bytes, "launches_per_step": geo_launches / args.steps,
                      "avg_launch_ms": geo_ms_total / max(geo_launches, 1),
                      "share_of_step": geo_ms_step / float(np.mean(step_ms)),

@@ -170,6 +170,24 @@ int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_ite
                        float* d_geo, float* d_viou, float* d_tiou, int32_t* d_overlap,
                        int flags, void* d_workspace, void* stream);
 
+/* ---- opt-in WINDOWED geometry layout --------------------------------------------------------------------
+ * Every channel of a pair's dense row is zero outside the pair's temporal overlap window [a, b) and channel 7 is the
+ * window's indicator, so the dense [P][8][Tp] tensor is mostly zeros (60 % on the bench workload).  The windowed
+ * layout stores, per pair, only the frames [a & ~3, (b + 3) & ~3) (length Lw, a multiple of 4) of channels 0..6:
+ * [7][Lw] floats at d_geo + d_geo_off[p] - bit-identical to the dense rows on those frames; d_overlap gives [a, b).
+ * tspn_geo_window_offsets fills d_geo_off (int64 [total_pairs], floats, exclusive prefix sum of 7 * Lw in pair
+ * order) and *d_total (the floats the batch needs; at most 7/8 of totals[TSPN_TOT_GEO_FLOATS]) from the tracklet
+ * spans - once per batch upload, not per step.  tspn_pair_geo_viou_windowed = tspn_pair_geo_viou writing that layout
+ * (same phases, flags and reductions).  The dense layout stays the parity layout; the kernels that read stored rows
+ * (tspn_assemble_features, tspn_assemble_relative, tspn_span_head, tspn_span_proposals) read the dense one. */
+int tspn_geo_window_offsets(const int64_t* d_table, int num_videos, int64_t total_pairs, const int32_t* d_span,
+                            int64_t* d_geo_off, int64_t* d_total, void* stream);
+int tspn_pair_geo_viou_windowed(const int64_t* d_table, int num_videos, int64_t total_items, int geo_chunk,
+                                int max_chunks, int64_t total_tracklets, int64_t total_pairs, int64_t total_boxes,
+                                const float* d_boxes, const int32_t* d_span, float* d_geo, const int64_t* d_geo_off,
+                                float* d_viou, float* d_tiou, int32_t* d_overlap, int flags, void* d_workspace,
+                                void* stream);
+
 /* ---- a4 matrix form: cubic_iou(bboxes1, bboxes2) -----------------------------------------
  * lib/modeling/trajectory.py:127-141.  b1 [n1][t][4], b2 [n2][t][4] -> out [n1][n2]. */
 int tspn_cubic_iou(const float* d_b1, int n1, const float* d_b2, int n2, int t,
@@ -401,6 +419,29 @@ int tspn_postprocess(const int64_t* d_table, int num_videos, const float* d_logi
                      int n_predicates, const float* d_cls, int n_classes, const int32_t* d_overlap,
                      const int32_t* d_span, int topk_per_pair, int topk_per_video, int flags,
                      int32_t* d_records, int32_t* d_counts, void* d_workspace, void* stream);
+
+/* ---- the exchange step over peer memory (multi-GPU serving) ---------------------------------------
+ * The path's one exchange - every rank's per-video triplet records to every rank, what lib/utils/comm.py:48-88
+ * (pickle + two all-gathers) would do - as plain stores into peer-mapped gather buffers over NVLink instead of a
+ * collective launch per step.  Buffers (symmetric across ranks, allocated and exchanged by the caller, e.g.
+ * torch.distributed._symmetric_memory): gather buffer int32 [ring][world][n_int32] and flags int32 [2][ring][world]
+ * (zeroed) on every rank; d_peer_bufs / d_peer_flags: device arrays [world] of the ranks' base pointers (own rank
+ * included); d_local_flags = this rank's flags; d_state: int32 [2 + ring], zeroed {error word, reserved, one CTA
+ * counter per slot}.  `step` = 1, 2, 3, ... is the caller's count of exchanges (the same sequence on every rank; an
+ * explicit argument because consecutive steps launched on different streams may execute in either order); step s uses
+ * slot s % ring, and ring must exceed the steps in flight between a scatter and its release.
+ *   tspn_records_scatter  producer, on the compute stream behind tspn_postprocess: waits for the slot's credits,
+ *                         stores d_records into slot[rank] of every rank, publishes written[slot][rank] = s
+ *   tspn_records_wait     consumer, before reading its gather buffer's slot: waits for written[slot][p] >= s, all p
+ *   tspn_records_release  consumer, after the slot was read: credit[slot][rank] = s on every rank
+ * Waits are bounded spins (max_spin polls of ~0.2 us): on expiry d_state[0] becomes non-zero (1 = credits, 2 =
+ * records) and the kernel returns - check it on the host; the device is never left spinning. */
+int tspn_records_scatter(const int32_t* d_records, int64_t n_int32, const uint64_t* d_peer_bufs,
+                         const uint64_t* d_peer_flags, const int32_t* d_local_flags, int world, int rank, int ring,
+                         int step, int32_t* d_state, int max_spin, void* stream);
+int tspn_records_wait(const int32_t* d_local_flags, int world, int ring, int step, int32_t* d_state, int max_spin,
+                      void* stream);
+int tspn_records_release(const uint64_t* d_peer_flags, int world, int rank, int ring, int step, void* stream);
 
 #ifdef __cplusplus
 }

@@ -52,6 +52,9 @@ SIGNATURES = {
     "tspn_geo_chunk": (c_int, [c_int64]),
     "tspn_pair_geo_viou": (c_int, [P, c_int, c_int64, c_int, c_int, c_int64, c_int64, c_int64, P, P, P, P, P, P, c_int,
                                    P, P]),
+    "tspn_geo_window_offsets": (c_int, [P, c_int, c_int64, P, P, P, P]),
+    "tspn_pair_geo_viou_windowed": (c_int, [P, c_int, c_int64, c_int, c_int, c_int64, c_int64, c_int64, P, P, P, P, P, P,
+                                            P, c_int, P, P]),
     "tspn_cubic_iou": (c_int, [P, c_int, P, c_int, c_int, P, P]),
     "tspn_viou_pairs": (c_int, [P, P, P, P, P, c_int64, c_int, P, P]),
     "tspn_viou_pairs_workspace_bytes": (c_int64, [c_int64]),
@@ -85,6 +88,9 @@ SIGNATURES = {
                                  c_int, P, P, P]),
     "tspn_postprocess_workspace_bytes": (c_int64, [c_int64, c_int]),
     "tspn_postprocess": (c_int, [P, c_int, P, P, P, c_int64, c_int, P, c_int, P, P, c_int, c_int, c_int, P, P, P, P]),
+    "tspn_records_scatter": (c_int, [P, c_int64, P, P, P, c_int, c_int, c_int, c_int, P, c_int, P]),
+    "tspn_records_wait": (c_int, [P, c_int, c_int, c_int, P, c_int, P]),
+    "tspn_records_release": (c_int, [P, c_int, c_int, c_int, c_int, P]),
     "tspn_survivor_rows_supported": (c_int, [c_int, c_int]),
     "tspn_gather_pair_terms": (c_int, [P, c_int, P, c_int64, P, P, c_int, P, P]),
     "tspn_survivor_rows": (c_int, [P, c_int, c_int, P, P, P, c_int64, c_int64, P, c_int64, P, P, c_int, P, P, P, P, P,

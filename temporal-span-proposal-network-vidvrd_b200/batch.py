@@ -293,6 +293,7 @@ class DeviceBatch:
         self.table, self.span = views["table"], views["span"]
         self.cls, self.motion = views.get("cls"), views.get("motion")     # motion: fp32, or u8 counts (compact)
         self.box_off = views.get("box_off")
+        self.geo_off = self.geo_total = None         # WINDOWED geometry layout: see enable_windows()
         if host.boxes_compact:
             # span-packed u16 coordinates in the arena, expanded right behind the copy (same stream) into this fp32 buffer -
             # the layout the kernels and the TMA tensor map read.  The expansion belongs to the upload, not to
@@ -318,6 +319,26 @@ class DeviceBatch:
                     self.box_off.data_ptr(), self.boxes_u16.data_ptr(), self.boxes.data_ptr(),
                     torch.cuda.current_stream(self.device).cuda_stream), "tspn_unpack_boxes_spans")
 
+    def enable_windows(self):
+        """Row offsets of the opt-in WINDOWED geometry layout (``tspn_geo_window_offsets``): ``geo_off`` int64
+        ``[sum P]`` and ``geo_total`` int64 ``[1]`` (floats), computed from the spans on the current stream now and
+        again behind every refill (``copy_from`` / ``copy_from_device``) - part of the upload, like the box expansion,
+        not of the step.  The tensors keep their addresses (captured graphs read them)."""
+        if self.geo_off is None:
+            p = max(int(self.totals[TOT_PAIRS]), 1)
+            self.geo_off = torch.zeros(p, dtype=torch.int64, device=self.device)
+            self.geo_total = torch.zeros(1, dtype=torch.int64, device=self.device)
+            self._windows()
+        return self.geo_off, self.geo_total
+
+    def _windows(self) -> None:
+        if self.geo_off is not None:
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.load().tspn_geo_window_offsets(
+                    self.table.data_ptr(), len(self.n), int(self.totals[TOT_PAIRS]), self.span.data_ptr(),
+                    self.geo_off.data_ptr(), self.geo_total.data_ptr(),
+                    torch.cuda.current_stream(self.device).cuda_stream), "tspn_geo_window_offsets")
+
     def copy_from(self, host: HostBatch) -> "DeviceBatch":
         """Refill the device buffers from another host batch of the same layout (non-blocking, on the
         current stream): the steady-state H2D of a serving loop.  Without a capacity the batch must have the
@@ -330,6 +351,7 @@ class DeviceBatch:
         for off, nbytes in host.used_segments():                          # only what the batch fills
             self.arena[off:off + nbytes].copy_(host.arena[off:off + nbytes], non_blocking=True)
         self._unpack()
+        self._windows()
         return self
 
     def copy_from_device(self, other: "DeviceBatch") -> "DeviceBatch":
@@ -346,6 +368,7 @@ class DeviceBatch:
         n_boxes = int(self.actual[TOT_BOXES])
         if self.boxes_u16 is not None and n_boxes:
             self.boxes[:n_boxes].copy_(other.boxes[:n_boxes], non_blocking=True)
+        self._windows()
         return self
 
     # sizes -----------------------------------------------------------------------------

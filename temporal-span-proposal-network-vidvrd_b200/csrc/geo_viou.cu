@@ -62,7 +62,7 @@ struct GeoCfg {
     static constexpr int STAGE_BYTES = ROWS * 128;                // stages are packed (128-byte aligned)
     static constexpr int MIN_CTAS = DENSE ? 1024 / THREADS : (THREADS >= 512 ? 1 : (THREADS == 256 ? 2 : 3));
     // barriers, per-object fixed-point sums, per-object overlap windows
-    static constexpr int TAIL_BYTES = (2 * RING * 8 + GEO_OG * (3 * 8 + 8) + 16 + 127) / 128 * 128;
+    static constexpr int TAIL_BYTES = (2 * RING * 8 + GEO_OG * (3 * 8 + 8 + 8) + 16 + 127) / 128 * 128;
     static constexpr int SMEM_USED = STAGES * STAGE_BYTES + TAIL_BYTES;
     // the 512-thread shape is already limited to one CTA per SM by its registers (16 warps x 104): no padding,
     // every byte it does not use is left to co-resident kernels of the side stream
@@ -134,11 +134,15 @@ __device__ __forceinline__ unsigned long long warp_sum_fx(float v) {
 }
 
 
-template <int THREADS, bool WRITE_GEO, bool CLIP, bool DENSE>
+// WRITE_GEO: 0 = reductions only, 1 = the dense [P][8][Tp] rows, 2 = WINDOWED rows (TSPN_GEO_WINDOWED): per pair only
+// the frames of its overlap window, rounded out to multiples of 4 - [7][Lw] floats at geo + geo_off[pair], channels
+// 0..6 (the mask channel is implied by the window); same values as the dense rows on those frames.
+template <int THREADS, int WRITE_GEO, bool CLIP, bool DENSE>
 __device__ __forceinline__ void
 pair_geo_body(const CUtensorMap& box_map, const int64_t* __restrict__ table, int nv,
               const int32_t* __restrict__ span, float* __restrict__ geo, unsigned long long* __restrict__ fx,
-              int32_t* __restrict__ overlap, unsigned int* __restrict__ queue, int max_chunks) {
+              int32_t* __restrict__ overlap, unsigned int* __restrict__ queue, int max_chunks,
+              const int64_t* __restrict__ geo_off) {
     using Cfg = GeoCfg<THREADS, DENSE>;
     constexpr int GEO_CHUNK = Cfg::CHUNK, GEO_WARPS = Cfg::WARPS, GEO_STAGE_BYTES = Cfg::STAGE_BYTES;
     constexpr int GEO_TX_BYTES = Cfg::TX_BYTES, GEO_SPLIT = Cfg::SPLIT, RING = Cfg::RING;
@@ -149,7 +153,8 @@ pair_geo_body(const CUtensorMap& box_map, const int64_t* __restrict__ table, int
     uint64_t* const empty = full + RING;                                                       // [RING]
     unsigned long long* const acc = reinterpret_cast<unsigned long long*>(empty + RING);       // [OG][3]
     int2* const owin = reinterpret_cast<int2*>(acc + GEO_OG * 3);                              // [OG] overlap windows
-    unsigned int* const s_item = reinterpret_cast<unsigned int*>(owin + GEO_OG);               // next work item
+    int64_t* const ooff = reinterpret_cast<int64_t*>(owin + GEO_OG);                           // [OG] windowed row offsets
+    unsigned int* const s_item = reinterpret_cast<unsigned int*>(ooff + GEO_OG);               // next work item
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -210,6 +215,7 @@ pair_geo_body(const CUtensorMap& box_map, const int64_t* __restrict__ table, int
         const int o = k + (k >= s ? 1 : 0);
         const int qs = __ldg(span + 2 * (trk_off + o)), qe = __ldg(span + 2 * (trk_off + o) + 1);
         owin[tid] = make_int2(max(ps, qs), min(pe, qe));
+        if (WRITE_GEO == 2) ooff[tid] = __ldg(geo_off + pair0 + tid);
     }
     for (int i = tid; i < GEO_OG * 3; i += THREADS) acc[i] = 0ull;
     __syncthreads();
@@ -236,9 +242,9 @@ pair_geo_body(const CUtensorMap& box_map, const int64_t* __restrict__ table, int
         for (int q = 0; q < RING && q < nobj; ++q) issue(q);
     }
 
-    float* g = WRITE_GEO ? geo + row[TSPN_VT_GEO_OFF] + ((int64_t)(s * (n - 1) + k0) * TSPN_GEO_CHANNELS) * tp +
-                               (int64_t)c * GEO_CHUNK
-                         : nullptr;
+    float* g = WRITE_GEO == 1 ? geo + row[TSPN_VT_GEO_OFF] + ((int64_t)(s * (n - 1) + k0) * TSPN_GEO_CHANNELS) * tp +
+                                    (int64_t)c * GEO_CHUNK
+                              : nullptr;
     int st = (int)(g0 % RING);                               // ring stage of step q and its phase parity
     int ph = (int)((g0 / RING) & 1u);
     for (int q = 0; q < nobj; ++q) {
@@ -264,7 +270,18 @@ pair_geo_body(const CUtensorMap& box_map, const int64_t* __restrict__ table, int
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[st]);
 
-        if (WRITE_GEO) {
+        if (WRITE_GEO == 2) {
+            const int a4 = a & ~3;
+            const int lw = b > a ? ((b + 3) & ~3) - a4 : 0;          // row length: the window rounded out to 4 frames
+            const int rel = t0 - a4;
+            if (rel >= 0 && rel < lw) {
+                float* gr = geo + ooff[q] + rel;
+#pragma unroll
+                for (int ch = 0; ch < TSPN_GEO_CHANNELS - 1; ++ch)
+                    st_stream_f4(gr + (int64_t)ch * lw, make_float4(out[ch][0], out[ch][1], out[ch][2], out[ch][3]));
+            }
+        }
+        if (WRITE_GEO == 1) {
             if (t0 < tp) {
 #pragma unroll
                 for (int ch = 0; ch < TSPN_GEO_CHANNELS; ++ch)
@@ -310,12 +327,14 @@ pair_geo_body(const CUtensorMap& box_map, const int64_t* __restrict__ table, int
     }
 }
 
-template <int THREADS, bool WRITE_GEO, bool CLIP, bool DENSE>
+template <int THREADS, int WRITE_GEO, bool CLIP, bool DENSE>
 __global__ void __launch_bounds__(THREADS, GeoCfg<THREADS, DENSE>::MIN_CTAS)
 pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __restrict__ table, int nv,
                 const int32_t* __restrict__ span, float* __restrict__ geo, unsigned long long* __restrict__ fx,
-                int32_t* __restrict__ overlap, unsigned int* __restrict__ queue, int max_chunks) {
-    pair_geo_body<THREADS, WRITE_GEO, CLIP, DENSE>(box_map, table, nv, span, geo, fx, overlap, queue, max_chunks);
+                int32_t* __restrict__ overlap, unsigned int* __restrict__ queue, int max_chunks,
+                const int64_t* __restrict__ geo_off) {
+    pair_geo_body<THREADS, WRITE_GEO, CLIP, DENSE>(box_map, table, nv, span, geo, fx, overlap, queue, max_chunks,
+                                                   geo_off);
 }
 
 // The 512-thread shape with the register count PINNED at 104: 16 warps x 104 registers leave exactly the 12 288
@@ -326,12 +345,13 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
 #ifndef TSPN_GEO_MAXNREG
 #define TSPN_GEO_MAXNREG 88
 #endif
-template <bool WRITE_GEO, bool CLIP>
+template <int WRITE_GEO, bool CLIP>
 __global__ void __maxnreg__(TSPN_GEO_MAXNREG)
 pair_geo_kernel_r104(const __grid_constant__ CUtensorMap box_map, const int64_t* __restrict__ table, int nv,
                      const int32_t* __restrict__ span, float* __restrict__ geo, unsigned long long* __restrict__ fx,
-                     int32_t* __restrict__ overlap, unsigned int* __restrict__ queue, int max_chunks) {
-    pair_geo_body<512, WRITE_GEO, CLIP, false>(box_map, table, nv, span, geo, fx, overlap, queue, max_chunks);
+                     int32_t* __restrict__ overlap, unsigned int* __restrict__ queue, int max_chunks,
+                     const int64_t* __restrict__ geo_off) {
+    pair_geo_body<512, WRITE_GEO, CLIP, false>(box_map, table, nv, span, geo, fx, overlap, queue, max_chunks, geo_off);
 }
 
 // ---- post-kernel: per-pair reductions (vIoU, tIoU; the pair kernel writes the overlap windows) ----------
@@ -527,6 +547,65 @@ __global__ void __launch_bounds__(256) enumerate_pairs_kernel(const int64_t* __r
     pairs[2 * p + 1] = k + (k >= s ? 1 : 0);
 }
 
+// ---- offsets of the windowed rows: geo_off[p] = 7 * sum of Lw over the pairs before p (floats, a multiple of 4),
+// Lw = the pair's overlap window rounded out to multiples of 4 frames.  One CTA walks the pairs in tiles of
+// WO_THREADS * 4 with a block scan per tile: a few tens of microseconds per batch, run once per upload (beside the
+// box expansion), not in the step.
+constexpr int WO_THREADS = 1024;
+__global__ void __launch_bounds__(WO_THREADS)
+geo_window_offsets_kernel(const int64_t* __restrict__ table, int nv, int64_t total_pairs_cap,
+                          const int32_t* __restrict__ span, int64_t* __restrict__ geo_off, int64_t* __restrict__ total) {
+    __shared__ int64_t warp_sum[WO_THREADS / 32];
+    __shared__ int64_t s_running;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t n_pairs = min(total_pairs_cap, table_total(table, nv, TSPN_VT_PAIR_OFF));
+    if (tid == 0) s_running = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n_pairs; base += WO_THREADS * 4) {
+        int64_t len[4];
+        int64_t mine = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int64_t p = base + (int64_t)tid * 4 + e;
+            len[e] = 0;
+            if (p < n_pairs) {
+                const int v = find_video(table, nv, TSPN_VT_PAIR_OFF, p);
+                const int64_t* row = table + (int64_t)v * TSPN_VT_COLS;
+                const int n1 = (int)row[TSPN_VT_N] - 1;
+                const int loc = (int)(p - row[TSPN_VT_PAIR_OFF]);
+                const int s = loc / n1, k = loc - s * n1;
+                const int o = k + (k >= s ? 1 : 0);
+                const int64_t ts = row[TSPN_VT_TRK_OFF] + s, to = row[TSPN_VT_TRK_OFF] + o;
+                const int a = max(__ldg(span + 2 * ts), __ldg(span + 2 * to));
+                const int b = min(__ldg(span + 2 * ts + 1), __ldg(span + 2 * to + 1));
+                if (b > a) len[e] = (int64_t)(TSPN_GEO_CHANNELS - 1) * (((b + 3) & ~3) - (a & ~3));
+            }
+            mine += len[e];
+        }
+        int64_t incl = mine;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int64_t up = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += up;
+        }
+        if (lane == 31) warp_sum[warp] = incl;
+        __syncthreads();
+        int64_t before = s_running;
+        for (int w = 0; w < warp; ++w) before += warp_sum[w];
+        int64_t run = before + incl - mine;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int64_t p = base + (int64_t)tid * 4 + e;
+            if (p < n_pairs) geo_off[p] = run;
+            run += len[e];
+        }
+        __syncthreads();
+        if (tid == WO_THREADS - 1) s_running = run;
+        __syncthreads();
+    }
+    if (tid == 0) *total = s_running;
+}
+
 __global__ void reset_queue_kernel(unsigned int* __restrict__ queue) {
     if (threadIdx.x == 0) *queue = 0u;
 }
@@ -535,7 +614,7 @@ template <int THREADS, bool DENSE>
 static int launch_pair_geo(const int64_t* d_table, int num_videos, int64_t total_items, int64_t total_boxes,
                            const float* d_boxes, const int32_t* d_span, float* d_geo, unsigned long long* fx,
                            int32_t* d_overlap, unsigned int* d_queue, int reserve, bool clip, int max_chunks,
-                           cudaStream_t st) {
+                           const int64_t* d_geo_off, cudaStream_t st) {
     using Cfg = GeoCfg<THREADS, DENSE>;
     // boxes viewed as a 2-D tensor: rows of 8 boxes (32 floats = 128 B)
     CUtensorMap map;
@@ -565,19 +644,21 @@ static int launch_pair_geo(const int64_t* d_table, int num_videos, int64_t total
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));  \
             prefer_max_smem(pair_geo_kernel_r104<W, C>);                                                       \
             pair_geo_kernel_r104<W, C><<<grid, THREADS, smem_bytes, st>>>(                                     \
-                map, d_table, num_videos, d_span, d_geo, fx, d_overlap, d_queue, max_chunks);                  \
+                map, d_table, num_videos, d_span, d_geo, fx, d_overlap, d_queue, max_chunks, d_geo_off);       \
         } else {                                                                                               \
             TSPN_CUDA_OK(cudaFuncSetAttribute(pair_geo_kernel<THREADS, W, C, DENSE>,                           \
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));  \
             prefer_max_smem(pair_geo_kernel<THREADS, W, C, DENSE>);                                            \
             pair_geo_kernel<THREADS, W, C, DENSE><<<grid, THREADS, smem_bytes, st>>>(                          \
-                map, d_table, num_videos, d_span, d_geo, fx, d_overlap, d_queue, max_chunks);                  \
+                map, d_table, num_videos, d_span, d_geo, fx, d_overlap, d_queue, max_chunks, d_geo_off);       \
         }                                                                                                      \
     } while (0)
-    if (d_geo) {
-        if (clip) TSPN_LAUNCH_GEO(true, true); else TSPN_LAUNCH_GEO(true, false);
+    if (d_geo && d_geo_off) {
+        if (clip) TSPN_LAUNCH_GEO(2, true); else TSPN_LAUNCH_GEO(2, false);
+    } else if (d_geo) {
+        if (clip) TSPN_LAUNCH_GEO(1, true); else TSPN_LAUNCH_GEO(1, false);
     } else {
-        if (clip) TSPN_LAUNCH_GEO(false, true); else TSPN_LAUNCH_GEO(false, false);
+        if (clip) TSPN_LAUNCH_GEO(0, true); else TSPN_LAUNCH_GEO(0, false);
     }
 #undef TSPN_LAUNCH_GEO
     TSPN_CUDA_OK(cudaGetLastError());
@@ -613,10 +694,10 @@ int64_t tspn_pair_geo_workspace_bytes(int64_t total_tracklets, int64_t total_pai
     return geo_ws_vol_bytes(total_tracklets) + (total_pairs > 0 ? total_pairs : 1) * mc * 3 * (int64_t)sizeof(uint64_t) + 16;
 }
 
-int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_items, int geo_chunk, int max_chunks,
-                       int64_t total_tracklets, int64_t total_pairs, int64_t total_boxes, const float* d_boxes, const int32_t* d_span,
-                       float* d_geo, float* d_viou, float* d_tiou, int32_t* d_overlap, int flags, void* d_workspace,
-                       void* stream) {
+static int pair_geo_viou_impl(const int64_t* d_table, int num_videos, int64_t total_items, int geo_chunk, int max_chunks,
+                              int64_t total_tracklets, int64_t total_pairs, int64_t total_boxes, const float* d_boxes,
+                              const int32_t* d_span, float* d_geo, const int64_t* d_geo_off, float* d_viou, float* d_tiou,
+                              int32_t* d_overlap, int flags, void* d_workspace, void* stream) {
     TSPN_ARCH_OK();
     TSPN_REQUIRE(num_videos >= 0 && total_items >= 0 && total_tracklets >= 0 && total_boxes >= 0 && total_pairs >= 0,
                  TSPN_EBADARG, "tspn_pair_geo_viou: negative size");
@@ -658,9 +739,9 @@ int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_ite
         const int reserve = (flags >> TSPN_GEO_RESERVE_SHIFT) & 0xff;
 #define TSPN_GEO_SHAPE(T)                                                                                          \
     (dense ? launch_pair_geo<T, true>(d_table, num_videos, total_items, total_boxes, d_boxes, d_span, d_geo, fx,   \
-                                      d_overlap, queue, reserve, clip, max_chunks, st)                             \
+                                      d_overlap, queue, reserve, clip, max_chunks, nullptr, st)                    \
            : launch_pair_geo<T, false>(d_table, num_videos, total_items, total_boxes, d_boxes, d_span, d_geo, fx,  \
-                                       d_overlap, queue, reserve, clip, max_chunks, st))
+                                       d_overlap, queue, reserve, clip, max_chunks, d_geo_off, st))
         if (geo_chunk == 512) rc = TSPN_GEO_SHAPE(128);
         else if (geo_chunk == 1024) rc = TSPN_GEO_SHAPE(256);
         else rc = TSPN_GEO_SHAPE(512);
@@ -679,6 +760,37 @@ int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_ite
                                                                  max_chunks, d_viou, d_tiou);
         TSPN_CUDA_OK(cudaGetLastError());
     }
+    return TSPN_OK;
+}
+
+int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_items, int geo_chunk, int max_chunks,
+                       int64_t total_tracklets, int64_t total_pairs, int64_t total_boxes, const float* d_boxes, const int32_t* d_span,
+                       float* d_geo, float* d_viou, float* d_tiou, int32_t* d_overlap, int flags, void* d_workspace,
+                       void* stream) {
+    return pair_geo_viou_impl(d_table, num_videos, total_items, geo_chunk, max_chunks, total_tracklets, total_pairs,
+                              total_boxes, d_boxes, d_span, d_geo, nullptr, d_viou, d_tiou, d_overlap, flags, d_workspace,
+                              stream);
+}
+
+int tspn_pair_geo_viou_windowed(const int64_t* d_table, int num_videos, int64_t total_items, int geo_chunk, int max_chunks,
+                                int64_t total_tracklets, int64_t total_pairs, int64_t total_boxes, const float* d_boxes,
+                                const int32_t* d_span, float* d_geo, const int64_t* d_geo_off, float* d_viou,
+                                float* d_tiou, int32_t* d_overlap, int flags, void* d_workspace, void* stream) {
+    TSPN_REQUIRE(d_geo && d_geo_off, TSPN_EBADARG, "tspn_pair_geo_viou_windowed: geo and geo_off are required");
+    TSPN_REQUIRE(!(flags & TSPN_GEO_DENSE_CTAS), TSPN_EBADARG, "tspn_pair_geo_viou_windowed: no dense-CTA shape");
+    return pair_geo_viou_impl(d_table, num_videos, total_items, geo_chunk, max_chunks, total_tracklets, total_pairs,
+                              total_boxes, d_boxes, d_span, d_geo, d_geo_off, d_viou, d_tiou, d_overlap, flags,
+                              d_workspace, stream);
+}
+
+int tspn_geo_window_offsets(const int64_t* d_table, int num_videos, int64_t total_pairs, const int32_t* d_span,
+                            int64_t* d_geo_off, int64_t* d_total, void* stream) {
+    TSPN_ARCH_OK();
+    TSPN_REQUIRE(num_videos >= 0 && total_pairs >= 0, TSPN_EBADARG, "tspn_geo_window_offsets: negative size");
+    TSPN_REQUIRE(d_table && d_span && d_geo_off && d_total, TSPN_EBADARG, "tspn_geo_window_offsets: null pointer");
+    geo_window_offsets_kernel<<<1, WO_THREADS, 0, (cudaStream_t)stream>>>(d_table, num_videos, total_pairs, d_span,
+                                                                          d_geo_off, d_total);
+    TSPN_CUDA_OK(cudaGetLastError());
     return TSPN_OK;
 }
 

@@ -63,11 +63,31 @@ def enumerate_pairs(batch: DeviceBatch) -> torch.Tensor:
     return out
 
 
-def pair_geometry_outputs(batch: DeviceBatch, write_geo: bool = True) -> Dict[str, torch.Tensor]:
-    """Caller-owned outputs and workspace of ``tspn_pair_geo_viou`` for this batch."""
+def geo_window_offsets(batch: DeviceBatch, geo_off: Optional[torch.Tensor] = None,
+                       total: Optional[torch.Tensor] = None):
+    """Row offsets of the WINDOWED geometry layout (``tspn_geo_window_offsets``): ``geo_off`` int64 ``[sum P]`` (floats)
+    and ``total`` int64 ``[1]``, from the tracklet spans of the batch as it is in HBM now; current stream."""
+    if geo_off is None:
+        geo_off = torch.zeros(max(batch.total_pairs, 1), dtype=torch.int64, device=batch.device)
+        total = torch.zeros(1, dtype=torch.int64, device=batch.device)
+    check(load().tspn_geo_window_offsets(ptr(batch.table), batch.num_videos, batch.total_pairs, ptr(batch.span),
+                                         ptr(geo_off), ptr(total), stream_ptr()), "tspn_geo_window_offsets")
+    _count(1)
+    return geo_off, total
+
+
+def pair_geometry_outputs(batch: DeviceBatch, write_geo: bool = True, windowed: bool = False) -> Dict[str, torch.Tensor]:
+    """Caller-owned outputs and workspace of ``tspn_pair_geo_viou`` for this batch.  ``windowed``: the opt-in
+    WINDOWED layout of the rows (``tspn_pair_geo_viou_windowed``: per pair only its overlap window's frames, 7
+    channels) - ``out["geo_off"]`` are the batch's row offsets, which ``DeviceBatch.enable_windows`` keeps current
+    across refills; the buffer holds 7/8 of the dense floats, the layout's upper bound."""
     dev, tot, p = batch.device, batch.totals, batch.total_pairs
     out = {}
-    out["geo"] = torch.empty(int(tot[_lib.TOT_GEO_FLOATS]), dtype=torch.float32, device=dev) if write_geo else None
+    n_geo = int(tot[_lib.TOT_GEO_FLOATS])
+    if windowed and write_geo:
+        out["geo_off"], out["geo_total"] = batch.enable_windows()
+        n_geo = n_geo // _lib.GEO_CHANNELS * (_lib.GEO_CHANNELS - 1)
+    out["geo"] = torch.empty(n_geo, dtype=torch.float32, device=dev) if write_geo else None
     out["viou"] = torch.empty(p, dtype=torch.float32, device=dev)
     out["tiou"] = torch.empty(p, dtype=torch.float32, device=dev)
     out["overlap"] = torch.empty((p, 2), dtype=torch.int32, device=dev)
@@ -93,19 +113,27 @@ def pair_geometry_phase(batch: DeviceBatch, out: Dict[str, torch.Tensor], phase:
         persistent = os.environ.get("TSPN_GEO_PERSISTENT", "1") == "1"
     if persistent and not dense_ctas:
         flags |= _lib.GEO_PERSISTENT | (max(0, min(int(reserve_sms), 255)) << _lib.GEO_RESERVE_SHIFT)
-    check(load().tspn_pair_geo_viou(
-        ptr(batch.table), batch.num_videos, int(tot[_lib.TOT_ITEMS]), int(tot[_lib.TOT_GEO_CHUNK]),
-        int(tot[_lib.TOT_MAX_CHUNKS]), batch.total_tracklets, batch.total_pairs,
-        int(tot[_lib.TOT_BOXES]), ptr(batch.boxes), ptr(batch.span), ptr(out.get("geo")), ptr(out["viou"]),
-        ptr(out["tiou"]), ptr(out["overlap"]), flags | phase, ptr(out["workspace"]), stream_ptr()),
-        "tspn_pair_geo_viou")
+    if out.get("geo_off") is not None:
+        check(load().tspn_pair_geo_viou_windowed(
+            ptr(batch.table), batch.num_videos, int(tot[_lib.TOT_ITEMS]), int(tot[_lib.TOT_GEO_CHUNK]),
+            int(tot[_lib.TOT_MAX_CHUNKS]), batch.total_tracklets, batch.total_pairs,
+            int(tot[_lib.TOT_BOXES]), ptr(batch.boxes), ptr(batch.span), ptr(out["geo"]), ptr(out["geo_off"]),
+            ptr(out["viou"]), ptr(out["tiou"]), ptr(out["overlap"]), flags | phase, ptr(out["workspace"]),
+            stream_ptr()), "tspn_pair_geo_viou_windowed")
+    else:
+        check(load().tspn_pair_geo_viou(
+            ptr(batch.table), batch.num_videos, int(tot[_lib.TOT_ITEMS]), int(tot[_lib.TOT_GEO_CHUNK]),
+            int(tot[_lib.TOT_MAX_CHUNKS]), batch.total_tracklets, batch.total_pairs,
+            int(tot[_lib.TOT_BOXES]), ptr(batch.boxes), ptr(batch.span), ptr(out.get("geo")), ptr(out["viou"]),
+            ptr(out["tiou"]), ptr(out["overlap"]), flags | phase, ptr(out["workspace"]), stream_ptr()),
+            "tspn_pair_geo_viou")
     _count(3 if phase == 0 else 1)      # volumes, pair kernel (+ its queue reset), per-pair finalize
 
 
 def pair_geometry(batch: DeviceBatch, write_geo: bool = True, clipped: bool = False,
                   out: Optional[Dict[str, torch.Tensor]] = None,
                   dense_ctas: Optional[bool] = None, events=None,
-                  persistent: Optional[bool] = None) -> Dict[str, torch.Tensor]:
+                  persistent: Optional[bool] = None, windowed: bool = False) -> Dict[str, torch.Tensor]:
     """All-pairs per-frame geometry + vIoU/tIoU/overlap (trajectory.py:85-141, common.py:65-106).
     ``events``: a pair of CUDA events recorded immediately before and after the pair kernel itself (the
     volume pre-kernel and the per-pair finalize are issued as separate phases around them).
@@ -114,7 +142,7 @@ def pair_geometry(batch: DeviceBatch, write_geo: bool = True, clipped: bool = Fa
     the environment variable TSPN_GEO_DENSE).  ``persistent``: the pair kernel as persistent CTAs pulling work
     items from a queue (default, TSPN_GEO_PERSISTENT) or one CTA per work item; bit-identical."""
     if out is None:
-        out = pair_geometry_outputs(batch, write_geo)
+        out = pair_geometry_outputs(batch, write_geo, windowed=windowed)
     if events is None:
         pair_geometry_phase(batch, out, 0, clipped, dense_ctas, persistent)
     else:

@@ -33,6 +33,10 @@ class StageConfig:
     relationness_precision: str = "fp32"   # PPNHead: "fp32" = exact order, hence a bit-exact top-K selection (also
                                            # when the heads run in tensor precision); "tensor" = tcgen05 (tf32 operands)
     write_geo: bool = True
+    geo_layout: str = "dense"          # "dense" = [P, 8, Tp] rows (the parity layout) | "windowed" = per pair only the
+                                       # frames of its overlap window, 7 channels (tspn_pair_geo_viou_windowed); the
+                                       # windowed rows are an output only, so they need the survivor path (heads from
+                                       # the boxes: precision "tensor" + sparsify)
     anchor_sizes: tuple = (15.0, 30.0, 45.0, 60.0)
     anchor_stride: float = 7.5
     viou_clipped: bool = False
@@ -166,6 +170,22 @@ class StageResult:
         if self.records is not None:
             out["records"], out["record_counts"] = self.records[:v], self.record_counts[:v]
         return out
+
+    def geo_window_rows(self, v: int) -> List[torch.Tensor]:
+        """WINDOWED layout (``StageConfig.geo_layout='windowed'``): per pair of video v the ``[7, Lw]`` view of its rows
+        - frames ``[a & ~3, (b + 3) & ~3)`` of channels 0..6, ``[a, b)`` = the pair's overlap window (``[7, 0]`` when
+        the pair has none).  Synchronises (reads the offsets and windows back)."""
+        if self.geom.get("geo_off") is None:
+            raise ValueError("the step wrote the dense layout: use batch.geo_view(result.geom['geo'], v)")
+        sl = self.batch.pair_slice(v)
+        off = self.geom["geo_off"][sl].cpu().tolist()
+        win = self.geom["overlap"][sl].cpu().tolist()
+        ch = _lib.GEO_CHANNELS - 1
+        rows = []
+        for o, (a, b) in zip(off, win):
+            lw = ((b + 3) & ~3) - (a & ~3) if b > a else 0
+            rows.append(self.geom["geo"][o:o + ch * lw].view(ch, lw))
+        return rows
 
     # per-video views -------------------------------------------------------------------
     def pair_proposals(self, v: int) -> Optional[torch.Tensor]:
@@ -379,10 +399,16 @@ class PairStage:
     # MAIN is on the critical path: on a single-chunk batch PRE runs on the side stream under MAIN, and POST
     # always runs on the side stream under the tail (feature rows and records read the overlap windows, which
     # MAIN writes; vIoU / tIoU are outputs only).
-    def _geo_alloc(self, batch: DeviceBatch, features: Optional[torch.Tensor]):
+    def _geo_alloc(self, batch: DeviceBatch, features: Optional[torch.Tensor], heads: bool = True):
         c = self.cfg
         need_geo = features is None or c.use_dpn
-        return ops.pair_geometry_outputs(batch, write_geo=need_geo and c.write_geo)
+        if c.geo_layout not in ("dense", "windowed"):
+            raise ValueError("geo_layout must be 'dense' or 'windowed' (got %r)" % (c.geo_layout,))
+        windowed = c.geo_layout == "windowed" and need_geo and c.write_geo
+        if windowed and heads and not self._survivor_path(batch, features, heads):
+            raise ValueError("geo_layout='windowed': the kernels that read stored geometry rows read the dense layout; "
+                             "the windowed rows need the survivor path (precision='tensor', sparsify, PPN on)")
+        return ops.pair_geometry_outputs(batch, write_geo=need_geo and c.write_geo, windowed=windowed)
 
     def _seg_pre(self, batch: DeviceBatch, geom) -> None:
         ops.pair_geometry_phase(batch, geom, _lib.GEO_PHASE_PRE, clipped=self.cfg.viou_clipped)
@@ -483,7 +509,7 @@ class PairStage:
         ``timers``: receives ``{"geo": (start, end)}`` CUDA events around the geometry kernel."""
         main = torch.cuda.current_stream(batch.device)
         side_stream = self._side_stream(batch.device)
-        geom = self._geo_alloc(batch, features)
+        geom = self._geo_alloc(batch, features, heads)
         pre_aside = True                              # PRE under MAIN: every sum has a single writer (see _seg_geo)
         side_stream.wait_stream(main)                 # fork: inputs are ready on the caller's stream
         with torch.cuda.stream(side_stream):
@@ -605,7 +631,7 @@ class GraphedStage:
                        torch.cuda.Event(enable_timing=True, external=True))
         # the geometry outputs are allocated outside the graphs: the PRE phase (side branch) and the pair kernel
         # (main branch) both write into them
-        geom = stage._geo_alloc(batch, features)
+        geom = stage._geo_alloc(batch, features, heads)
         pre_aside = True
         if self.single:
             self.graph = torch.cuda.CUDAGraph()

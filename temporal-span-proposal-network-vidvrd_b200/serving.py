@@ -66,8 +66,13 @@ class PipelinedStage:
     milliseconds - pass every capacity up front to keep the steady state capture-free)."""
 
     def __init__(self, stage: PairStage, templates, device="cuda", depth: int = 2, graphs: bool = True,
-                 group=None, compute_streams: int = 2, single_graph: bool = True):
+                 group=None, compute_streams: int = 2, single_graph: bool = True, collective: str = "nccl"):
+        """``collective`` (with ``group``): ``"nccl"`` = one ``all_gather_into_tensor`` of the records per step on a
+        stream of its own; ``"peer"`` = every rank stores its records into every rank's gather buffer over NVLink
+        (``sharding.PeerRecords``: no collective launch; needs peer-mappable memory, one bucket)."""
         self.stage, self.device, self.depth, self.group = stage, torch.device(device), int(depth), group
+        self.collective = collective if group is not None else None
+        self.peer = None
         self.graphs, self.single_graph = bool(graphs), bool(single_graph)
         self.main = torch.cuda.current_stream(self.device)
         # Two compute streams, used alternately: the latency-bound tail of step i (feature rows, heads,
@@ -127,7 +132,15 @@ class PipelinedStage:
                 post(res)
             slot.kernels_done.record(main)
         work = None
-        if self.group is not None:                       # the one collective: top-K triplet records
+        if self.group is not None and self.collective == "peer":
+            if self.peer is None:                        # first step: symmetric buffers + rendezvous (collective call)
+                from .sharding import PeerRecords
+                with torch.cuda.stream(main):
+                    self.peer = PeerRecords(res.records.shape, self.group, self.device, ring=self.depth + 2)
+            with torch.cuda.stream(main):                # behind the step's kernels: plain stores into the peers
+                self.peer.scatter(res.records)
+                slot.kernels_done.record(main)
+        elif self.group is not None:                     # the one collective: top-K triplet records
             import torch.distributed as dist
             world = dist.get_world_size(self.group)
             if slot.gathered is None:
@@ -137,11 +150,17 @@ class PipelinedStage:
                 self.s_comm.wait_event(slot.kernels_done)
                 work = dist.all_gather_into_tensor(slot.gathered, res.records, group=self.group, async_op=True)
             outs["records_all_ranks"] = slot.gathered
+        peer_view = None
+        if self.peer is not None:
+            with torch.cuda.stream(self.s_d2h):
+                self.s_d2h.wait_event(slot.kernels_done)
+                peer_view = self.peer.gather()           # waits (on this stream only) for every rank's step
+            outs["records_all_ranks"] = peer_view
         if slot.graphed is None or slot.pinned is None:
             # first use (or eager mode, whose outputs are fresh tensors): pinned buffers of the bucket's full size
             full = res.host_outputs(full=True)
             if self.group is not None:
-                full["records_all_ranks"] = slot.gathered
+                full["records_all_ranks"] = peer_view if peer_view is not None else slot.gathered
             if slot.pinned is None or any(k not in slot.pinned or slot.pinned[k].shape != v.shape
                                           for k, v in full.items()):
                 slot.pinned = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in full.items()}
@@ -157,6 +176,8 @@ class PipelinedStage:
                 dst.copy_(src, non_blocking=True)
                 slot.host_out[k] = dst
                 self._d2h_bytes += src.numel() * src.element_size()
+            if peer_view is not None:
+                self.peer.release()                      # the slot of the gather buffer may be overwritten again
             slot.d2h_done.record(self.s_d2h)
         slot.keep = (res, outs)
         slot.busy = True

@@ -78,3 +78,104 @@ def gather_records(records: torch.Tensor, counts: torch.Tensor, shards: List[Lis
             out_r[idx] = recv[r, :len(vids), :m * 8].reshape(len(vids), m, 8)
             out_c[idx] = recv[r, :len(vids), m * 8]
     return out_r, out_c
+
+
+class PeerRecords:
+    """The per-step exchange of the triplet records over peer memory (``csrc/peer_records.cu``): every rank stores its
+    ``[V, M, 8]`` records straight into every rank's gather buffer over NVLink and publishes a flag; no collective is
+    launched.  Buffers are ``torch.distributed._symmetric_memory`` allocations (peer-mapped by ``rendezvous``).
+
+        peer = PeerRecords(records_shape, group, device, ring=depth + 2)
+        peer.scatter(records)          # producer, on the stream that produced `records`
+        gathered = peer.gather()       # consumer, on the stream that reads them out: waits for every rank's step,
+        ...copy `gathered` out...      # returns this step's [world, V, M, 8] view
+        peer.release()                 # consumer, after the copy: the slot may be overwritten ``ring`` steps later
+
+    Every rank must run the same sequence of steps.  ``check()`` raises if a bounded wait on the device expired.
+    ``PeerRecords.available(group)`` tells whether the ranks of ``group`` can map each other's memory; the caller
+    falls back to ``all_gather_into_tensor`` otherwise."""
+
+    MAX_SPIN = 5_000_000            # x ~0.2 us: a second before a wait gives up
+
+    def __init__(self, records_shape, group, device, ring: int = 5):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        self._lib = _lib
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.ring = int(ring)
+        self.shape = tuple(int(x) for x in records_shape)
+        self.n_int32 = 1
+        for x in self.shape:
+            self.n_int32 *= x
+        if self.n_int32 % 4:
+            raise ValueError("records must be a multiple of 16 bytes")
+        dev = torch.device(device)
+        enable = getattr(symm, "enable_symm_mem_for_group", None)
+        if enable is not None:
+            try:
+                enable(self.group.group_name)
+            except Exception:  # noqa: BLE001  (newer torch: not needed / deprecated)
+                pass
+        self.buf = symm.empty((self.ring, self.world, self.n_int32), dtype=torch.int32, device=dev)
+        self.flags = symm.empty((2, self.ring, self.world), dtype=torch.int32, device=dev)
+        self.buf.zero_()
+        self.flags.zero_()
+        h_buf = symm.rendezvous(self.buf, self.group)
+        h_flg = symm.rendezvous(self.flags, self.group)
+        bufs = [h_buf.get_buffer(r, tuple(self.buf.shape), torch.int32).data_ptr() for r in range(self.world)]
+        flgs = [h_flg.get_buffer(r, tuple(self.flags.shape), torch.int32).data_ptr() for r in range(self.world)]
+        self.peer_bufs = torch.tensor(bufs, dtype=torch.int64, device=dev)
+        self.peer_flags = torch.tensor(flgs, dtype=torch.int64, device=dev)
+        self.state = torch.zeros(2 + self.ring, dtype=torch.int32, device=dev)
+        self._h = (h_buf, h_flg)
+        self.produced = self.consumed = 0           # exchanges issued so far (host counters: the kernels' step numbers)
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=self.group)              # every rank's flags are zero before anyone publishes
+
+    @staticmethod
+    def available(group=None) -> bool:
+        try:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory  # noqa: F401
+            return dist.is_initialized() and dist.get_backend(group) == "nccl" and torch.cuda.is_available()
+        except Exception:  # noqa: BLE001
+            return False
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.buf.device).cuda_stream
+
+    def scatter(self, records: torch.Tensor) -> None:
+        records = records.contiguous()
+        if records.numel() != self.n_int32 or records.dtype != torch.int32:
+            raise ValueError("records %s do not match the exchange's shape %s" % (tuple(records.shape), self.shape))
+        if self.produced - self.consumed >= self.ring - 1:
+            raise RuntimeError("peer record exchange: %d steps in flight on a ring of %d" % (self.produced - self.consumed,
+                                                                                          self.ring))
+        self.produced += 1
+        self._lib.check(self._lib.load().tspn_records_scatter(
+            records.data_ptr(), self.n_int32, self.peer_bufs.data_ptr(), self.peer_flags.data_ptr(),
+            self.flags.data_ptr(), self.world, self.rank, self.ring, self.produced, self.state.data_ptr(), self.MAX_SPIN,
+            self._stream()), "tspn_records_scatter")
+
+    def gather(self) -> torch.Tensor:
+        """Wait (on the current stream) for every rank's records of the next step; returns their ``[world, *shape]``
+        view in the gather buffer - valid until ``release()`` and ``ring - 1`` further steps."""
+        self.consumed += 1
+        self._lib.check(self._lib.load().tspn_records_wait(self.flags.data_ptr(), self.world, self.ring, self.consumed,
+                                                           self.state.data_ptr(), self.MAX_SPIN, self._stream()),
+                        "tspn_records_wait")
+        return self.buf[self.consumed % self.ring].view((self.world,) + self.shape)
+
+    def release(self) -> None:
+        """The step returned by the last ``gather()`` has been read (on the current stream): its slot may be reused."""
+        self._lib.check(self._lib.load().tspn_records_release(self.peer_flags.data_ptr(), self.world, self.rank,
+                                                              self.ring, self.consumed, self._stream()),
+                        "tspn_records_release")
+
+    def check(self) -> None:
+        err = int(self.state[0].item())
+        if err:
+            raise RuntimeError("peer record exchange: a bounded wait expired on the device (%s)"
+                               % ("credits of a slot" if err == 1 else "records of a step"))

@@ -72,3 +72,86 @@ def test_sharded_records_over_nccl_equal_single_gpu(tmp_path):
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
     assert json.loads(line)["ok"]
+
+
+PEER_WORKER = r'''
+import json, os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np, torch, torch.distributed as dist
+from tspn_b200 import sharding, synth
+from tspn_b200.batch import HostBatch
+from tspn_b200.pipeline import PairStage, StageConfig
+from tspn_b200.serving import PipelinedStage
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+torch.cuda.set_device(dev)
+dist.init_process_group("nccl", device_id=dev)
+ok, info = True, {}
+
+# 1. the exchange alone: 40 steps on a ring of 4, random records, two producer streams used alternately (so steps may
+#    execute out of order), every gathered step compared with NCCL's all-gather of the same records
+peer = sharding.PeerRecords((6, 200, 8), dist.group.WORLD, dev, ring=4)
+streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+consumer = torch.cuda.Stream(dev)
+g = torch.Generator(device="cuda").manual_seed(1000 + rank)
+for s in range(40):
+    rec = torch.randint(-2**31, 2**31 - 1, (6, 200, 8), dtype=torch.int32, device=dev, generator=g)
+    want = torch.empty((world, 6, 200, 8), dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(want, rec)
+    torch.cuda.synchronize()
+    st = streams[s %% 2]
+    with torch.cuda.stream(st):
+        peer.scatter(rec)
+        done = torch.cuda.Event(); done.record(st)
+    with torch.cuda.stream(consumer):
+        consumer.wait_event(done)
+        got = peer.gather().clone()
+        peer.release()
+    consumer.synchronize()
+    ok = ok and bool(torch.equal(got, want))
+peer.check()
+info["exchange_steps"] = 40
+
+# 2. the serving loop: the same batches through collective="nccl" and collective="peer"
+C, R = 35, 132
+sd = synth.make_weights(C, R, synth.feature_dim(C), dpn_in=8, seed=0)
+stage = PairStage(StageConfig(n_classes=C, n_predicates=R, topk=64, sparsify=True, precision="tensor",
+                              num_span_proposals=16))
+stage.load_weights(sd, dev)
+hosts = [HostBatch.from_videos([synth.make_video(10, 300, C, seed=1000 * rank + 10 * q + j) for j in range(3)])
+         for q in range(7)]
+outs = {}
+for coll in ("nccl", "peer"):
+    pipe = PipelinedStage(stage, hosts[0], device=dev, depth=3, group=dist.group.WORLD, collective=coll)
+    outs[coll] = [{k: v.clone() for k, v in o.items()} for o in pipe.run(iter(hosts))]
+    if coll == "peer":
+        pipe.peer.check()
+    torch.cuda.synchronize()
+    dist.barrier()
+for a, b in zip(outs["nccl"], outs["peer"]):
+    ok = ok and a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
+    ok = ok and bool(torch.equal(b["records_all_ranks"][rank], b["records"]))
+    ok = ok and int(b["record_counts"].sum()) > 0
+flag = torch.tensor([1 if ok else 0], device=dev)
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print(json.dumps({"ok": bool(flag.item()), **info}))
+dist.destroy_process_group()
+sys.exit(0 if bool(flag.item()) else 1)
+'''
+
+
+def test_peer_record_exchange_equals_nccl_all_gather(tmp_path):
+    """csrc/peer_records.cu on two GPUs: stores into the peers' gather buffers + flags give, step for step, what
+    all_gather_into_tensor gives - alone (ring reuse, out-of-order producer streams) and inside the serving loop."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    script = tmp_path / "peer_worker.py"
+    script.write_text(PEER_WORKER % {"root": ROOT})
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29733", str(script)],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+    assert json.loads(line)["ok"]

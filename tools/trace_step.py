@@ -32,6 +32,7 @@ def main():
                                                                "batches (capacity graphs, as the bench replays them)")
     ap.add_argument("--batches", type=int, default=3, help="ragged workloads: batches to trace")
     ap.add_argument("--relationness", default="fp32", choices=["fp32", "tensor"])
+    ap.add_argument("--geo-layout", default="dense", choices=["dense", "windowed"])
     args = ap.parse_args()
     spec = synth.CONFIGS[args.workload]
     c, r, k = spec["classes"], spec["predicates"], spec["topk"]
@@ -40,7 +41,8 @@ def main():
     cfg = StageConfig(n_classes=c, n_predicates=r, topk=k, use_ppn=True, use_dpn=not args.no_dpn, sparsify=True,
                       precision="tensor", relationness_precision=args.relationness,
                       anchor_sizes=(15.0, 30.0, 45.0, 60.0) if vidvrd else (16.0, 64.0, 256.0, 1024.0),
-                      anchor_stride=7.5 if vidvrd else 16.0, num_span_proposals=args.span_proposals)
+                      anchor_stride=7.5 if vidvrd else 16.0, num_span_proposals=args.span_proposals,
+                      geo_layout=args.geo_layout)
     stage = PairStage(cfg)
     stage.load_weights(synth.make_weights(c, r, synth.feature_dim(c), dpn_in=8, seed=0), "cuda")
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device="cuda")
