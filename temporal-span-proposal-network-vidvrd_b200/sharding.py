@@ -112,12 +112,6 @@ class PeerRecords:
         if self.n_int32 % 4:
             raise ValueError("records must be a multiple of 16 bytes")
         dev = torch.device(device)
-        enable = getattr(symm, "enable_symm_mem_for_group", None)
-        if enable is not None:
-            try:
-                enable(self.group.group_name)
-            except Exception:  # noqa: BLE001  (newer torch: not needed / deprecated)
-                pass
         self.buf = symm.empty((self.ring, self.world, self.n_int32), dtype=torch.int32, device=dev)
         self.flags = symm.empty((2, self.ring, self.world), dtype=torch.int32, device=dev)
         self.buf.zero_()
