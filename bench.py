@@ -84,6 +84,8 @@ def parse_args():
     ap.add_argument("--geo-layout", default="dense", choices=["dense", "windowed"],
                     help="layout of the per-frame geometry rows: dense [P, 8, Tp] (the parity layout) or windowed "
                          "(per pair only its overlap window's frames, 7 channels: tspn_pair_geo_viou_windowed)")
+    ap.add_argument("--no-layout-extra", action="store_true",
+                    help="skip the extra run of the same workload with the windowed layout (`windowed_layout` in the line)")
     ap.add_argument("--relationness", default="fp32", choices=["fp32", "tensor"],
                     help="PPNHead arithmetic: fp32 exact order (bit-exact top-K) or tcgen05 (tf32 operands)")
     return ap.parse_args()
@@ -837,8 +839,12 @@ def run_ours(args, rank, world, local_rank):
         "launches_per_step": int(launches_per_step),
         "clocks": clocks,
     }
+    if windowed:
+        line["roofline"]["kernel"] = "pair_geo_windowed_kernel (CUDA events immediately around each launch)"
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline_subprocess(args)
+    if world == 1 and not windowed and not args.no_layout_extra and args.precision == "tensor" and sparsify:
+        line["windowed_layout"] = windowed_subprocess(args)
     emit(line)
 
 
@@ -853,6 +859,28 @@ def cpu_baseline_subprocess(args):
         return json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]
     except Exception as e:  # noqa: BLE001
         return {"value": None, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (e,)}
+
+
+def windowed_subprocess(args):
+    """The same workload with the opt-in WINDOWED geometry layout (tspn_pair_geo_viou_windowed), in a child process
+    after this one's measurements: reported beside the dense (parity layout) numbers, never instead of them."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--geo-layout", "windowed", "--no-cpu-baseline",
+           "--workload", args.workload, "--steps", str(args.steps), "--warmup", str(args.warmup),
+           "--span-proposals", str(args.span_proposals), "--precision", args.precision, "--depth", str(args.depth),
+           "--relationness", args.relationness, "--geo-budget-gb", str(args.geo_budget_gb)]
+    if args.videos:
+        cmd += ["--videos", str(args.videos)]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        d = json.loads(out.stdout.strip().splitlines()[-1])
+        r = d["roofline"]
+        return {"value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"], "e2e": d["e2e"],
+                "roofline": {k: r[k] for k in ("kernel", "achieved", "peak", "unit", "frac", "algorithmic_bytes_per_step",
+                                               "avg_launch_ms", "share_of_step", "alone")},
+                "note": "geo rows as [7][Lw] per pair (only the overlap window's frames; bit-identical to the dense rows "
+                        "there, tests/test_gpu_windowed.py); every other output of the step is the same tensor"}
+    except Exception as e:  # noqa: BLE001
+        return {"value": None, "note": "failed: %r" % (e,)}
 
 
 _JSON_OUT = None

@@ -177,8 +177,10 @@ int tspn_pair_geo_viou(const int64_t* d_table, int num_videos, int64_t total_ite
  * [7][Lw] floats at d_geo + d_geo_off[p] - bit-identical to the dense rows on those frames; d_overlap gives [a, b).
  * tspn_geo_window_offsets fills d_geo_off (int64 [total_pairs], floats, exclusive prefix sum of 7 * Lw in pair
  * order) and *d_total (the floats the batch needs; at most 7/8 of totals[TSPN_TOT_GEO_FLOATS]) from the tracklet
- * spans - once per batch upload, not per step.  tspn_pair_geo_viou_windowed = tspn_pair_geo_viou writing that layout
- * (same phases, flags and reductions).  The dense layout stays the parity layout; the kernels that read stored rows
+ * spans - once per batch upload, not per step.  tspn_pair_geo_viou_windowed = tspn_pair_geo_viou writing that layout:
+ * same phases, same flags (TSPN_GEO_DENSE_CTAS is rejected), same vIoU / tIoU / overlap bit for bit; its MAIN phase is
+ * a kernel of its own (csrc/geo_windowed.cu: a warp per pair walking only the window; TSPN_GEO_RESERVE_SHIFT counts
+ * CTA slots of two per SM).  The dense layout stays the parity layout; the kernels that read stored rows
  * (tspn_assemble_features, tspn_assemble_relative, tspn_span_head, tspn_span_proposals) read the dense one. */
 int tspn_geo_window_offsets(const int64_t* d_table, int num_videos, int64_t total_pairs, const int32_t* d_span,
                             int64_t* d_geo_off, int64_t* d_total, void* stream);

@@ -150,4 +150,10 @@ int encode_tensor_map(CUtensorMap* map, CUtensorMapDataType dtype, uint32_t rank
                       const uint64_t* dims, const uint64_t* strides_bytes /* rank-1 */,
                       const uint32_t* box, CUtensorMapSwizzle swizzle);
 
+// ---- the windowed all-pairs kernel (geo_windowed.cu), launched by the MAIN phase of tspn_pair_geo_viou_windowed ----
+int launch_pair_geo_windowed(const int64_t* d_table, int num_videos, int64_t total_pairs, const float* d_boxes,
+                             const int32_t* d_span, float* d_geo, const int64_t* d_geo_off, unsigned long long* fx,
+                             int32_t* d_overlap, unsigned int* d_queue, int geo_chunk, int max_chunks, int reserve,
+                             bool clip, cudaStream_t st);
+
 }  // namespace tspn

@@ -49,16 +49,22 @@ __device__ __forceinline__ float log_ratio(float a, float b, float rb) {
 // per-thread partial sums stay in fp32: 4 integer-valued products <= 4 * 2^21 < 2^24 are exact
 // load_s(j) / load_o(j): box j of the subject / object chunk (j0 <= j <= j0 + GEO_FPT; shared-memory stages in
 // the all-pairs kernel, global memory in the surviving-pairs kernel - the arithmetic is the same code)
-template <bool CLIP, typename LoadS, typename LoadO>
+// INTERIOR: the caller guarantees a <= t0 and t0 + GEO_FPT < b - all four frames and their forward differences lie
+// inside the window, so every predicate below is true and is dropped at compile time.  The arithmetic is the same
+// instruction sequence (no product feeds an add without an explicit rounding point: nothing for the compiler to
+// contract differently), hence the same bits.
+template <bool CLIP, bool INTERIOR = false, typename LoadS, typename LoadO>
 __device__ __forceinline__ void geo_step(LoadS load_s, LoadO load_o, int j0, int t0, int a, int b,
                                          float (&out)[TSPN_GEO_CHANNELS][GEO_FPT], float& fsum_i, float& fsum_s,
                                          float& fsum_o) {
     fsum_i = 0.0f; fsum_s = 0.0f; fsum_o = 0.0f;
+    if (!INTERIOR) {
 #pragma unroll
-    for (int ch = 0; ch < TSPN_GEO_CHANNELS; ++ch)
+        for (int ch = 0; ch < TSPN_GEO_CHANNELS; ++ch)
 #pragma unroll
-        for (int i = 0; i < GEO_FPT; ++i) out[ch][i] = 0.0f;
-    if (!(t0 < b && t0 + GEO_FPT > a)) return;
+            for (int i = 0; i < GEO_FPT; ++i) out[ch][i] = 0.0f;
+        if (!(t0 < b && t0 + GEO_FPT > a)) return;
+    }
     float dcx[GEO_FPT + 1], dcy[GEO_FPT + 1], wo[GEO_FPT + 1], ho[GEO_FPT + 1];
     float rwo[GEO_FPT + 1], rho[GEO_FPT + 1];
 #pragma unroll
@@ -75,7 +81,7 @@ __device__ __forceinline__ void geo_step(LoadS load_s, LoadO load_o, int j0, int
         dcy[i] = 0.5f * ((sb.y - ob.y) + (sb.w - ob.w));
         if (i < GEO_FPT) {
             const int t = t0 + i;
-            const bool in = (t >= a) && (t < b);
+            const bool in = INTERIOR || ((t >= a) && (t < b));
             const float ws = (sb.z - sb.x) + 1.0f, hs = (sb.w - sb.y) + 1.0f;
             const float iw = fmaxf((fminf(sb.z, ob.z) - fmaxf(sb.x, ob.x)) + 1.0f, 0.0f);
             const float ih = fmaxf((fminf(sb.w, ob.w) - fmaxf(sb.y, ob.y)) + 1.0f, 0.0f);
@@ -104,7 +110,7 @@ __device__ __forceinline__ void geo_step(LoadS load_s, LoadO load_o, int j0, int
 #pragma unroll
     for (int i = 0; i < GEO_FPT; ++i) {
         const int t = t0 + i;
-        if (t >= a && t + 1 < b) {
+        if (INTERIOR || (t >= a && t + 1 < b)) {
             float p = dcx[i] * wo[i + 1];
             float e = fmaf(dcx[i], wo[i + 1], -p);
             out[5][i] = (fmaf(dcx[i + 1], wo[i], -p) - e) * (rwo[i] * rwo[i + 1]);

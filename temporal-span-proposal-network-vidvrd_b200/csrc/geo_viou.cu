@@ -62,7 +62,7 @@ struct GeoCfg {
     static constexpr int STAGE_BYTES = ROWS * 128;                // stages are packed (128-byte aligned)
     static constexpr int MIN_CTAS = DENSE ? 1024 / THREADS : (THREADS >= 512 ? 1 : (THREADS == 256 ? 2 : 3));
     // barriers, per-object fixed-point sums, per-object overlap windows
-    static constexpr int TAIL_BYTES = (2 * RING * 8 + GEO_OG * (3 * 8 + 8 + 8) + 16 + 127) / 128 * 128;
+    static constexpr int TAIL_BYTES = (2 * RING * 8 + GEO_OG * (3 * 8 + 8) + 16 + 127) / 128 * 128;
     static constexpr int SMEM_USED = STAGES * STAGE_BYTES + TAIL_BYTES;
     // the 512-thread shape is already limited to one CTA per SM by its registers (16 warps x 104): no padding,
     // every byte it does not use is left to co-resident kernels of the side stream
@@ -134,15 +134,11 @@ __device__ __forceinline__ unsigned long long warp_sum_fx(float v) {
 }
 
 
-// WRITE_GEO: 0 = reductions only, 1 = the dense [P][8][Tp] rows, 2 = WINDOWED rows (TSPN_GEO_WINDOWED): per pair only
-// the frames of its overlap window, rounded out to multiples of 4 - [7][Lw] floats at geo + geo_off[pair], channels
-// 0..6 (the mask channel is implied by the window); same values as the dense rows on those frames.
-template <int THREADS, int WRITE_GEO, bool CLIP, bool DENSE>
+template <int THREADS, bool WRITE_GEO, bool CLIP, bool DENSE>
 __device__ __forceinline__ void
 pair_geo_body(const CUtensorMap& box_map, const int64_t* __restrict__ table, int nv,
               const int32_t* __restrict__ span, float* __restrict__ geo, unsigned long long* __restrict__ fx,
-              int32_t* __restrict__ overlap, unsigned int* __restrict__ queue, int max_chunks,
-              const int64_t* __restrict__ geo_off) {
+              int32_t* __restrict__ overlap, unsigned int* __restrict__ queue, int max_chunks) {
     using Cfg = GeoCfg<THREADS, DENSE>;
     constexpr int GEO_CHUNK = Cfg::CHUNK, GEO_WARPS = Cfg::WARPS, GEO_STAGE_BYTES = Cfg::STAGE_BYTES;
     constexpr int GEO_TX_BYTES = Cfg::TX_BYTES, GEO_SPLIT = Cfg::SPLIT, RING = Cfg::RING;
@@ -153,8 +149,7 @@ pair_geo_body(const CUtensorMap& box_map, const int64_t* __restrict__ table, int
     uint64_t* const empty = full + RING;                                                       // [RING]
     unsigned long long* const acc = reinterpret_cast<unsigned long long*>(empty + RING);       // [OG][3]
     int2* const owin = reinterpret_cast<int2*>(acc + GEO_OG * 3);                              // [OG] overlap windows
-    int64_t* const ooff = reinterpret_cast<int64_t*>(owin + GEO_OG);                           // [OG] windowed row offsets
-    unsigned int* const s_item = reinterpret_cast<unsigned int*>(ooff + GEO_OG);               // next work item
+    unsigned int* const s_item = reinterpret_cast<unsigned int*>(owin + GEO_OG);               // next work item
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -215,7 +210,6 @@ pair_geo_body(const CUtensorMap& box_map, const int64_t* __restrict__ table, int
         const int o = k + (k >= s ? 1 : 0);
         const int qs = __ldg(span + 2 * (trk_off + o)), qe = __ldg(span + 2 * (trk_off + o) + 1);
         owin[tid] = make_int2(max(ps, qs), min(pe, qe));
-        if (WRITE_GEO == 2) ooff[tid] = __ldg(geo_off + pair0 + tid);
     }
     for (int i = tid; i < GEO_OG * 3; i += THREADS) acc[i] = 0ull;
     __syncthreads();
@@ -242,9 +236,9 @@ pair_geo_body(const CUtensorMap& box_map, const int64_t* __restrict__ table, int
         for (int q = 0; q < RING && q < nobj; ++q) issue(q);
     }
 
-    float* g = WRITE_GEO == 1 ? geo + row[TSPN_VT_GEO_OFF] + ((int64_t)(s * (n - 1) + k0) * TSPN_GEO_CHANNELS) * tp +
-                                    (int64_t)c * GEO_CHUNK
-                              : nullptr;
+    float* g = WRITE_GEO ? geo + row[TSPN_VT_GEO_OFF] + ((int64_t)(s * (n - 1) + k0) * TSPN_GEO_CHANNELS) * tp +
+                               (int64_t)c * GEO_CHUNK
+                         : nullptr;
     int st = (int)(g0 % RING);                               // ring stage of step q and its phase parity
     int ph = (int)((g0 / RING) & 1u);
     for (int q = 0; q < nobj; ++q) {
@@ -270,18 +264,7 @@ pair_geo_body(const CUtensorMap& box_map, const int64_t* __restrict__ table, int
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[st]);
 
-        if (WRITE_GEO == 2) {
-            const int a4 = a & ~3;
-            const int lw = b > a ? ((b + 3) & ~3) - a4 : 0;          // row length: the window rounded out to 4 frames
-            const int rel = t0 - a4;
-            if (rel >= 0 && rel < lw) {
-                float* gr = geo + ooff[q] + rel;
-#pragma unroll
-                for (int ch = 0; ch < TSPN_GEO_CHANNELS - 1; ++ch)
-                    st_stream_f4(gr + (int64_t)ch * lw, make_float4(out[ch][0], out[ch][1], out[ch][2], out[ch][3]));
-            }
-        }
-        if (WRITE_GEO == 1) {
+        if (WRITE_GEO) {
             if (t0 < tp) {
 #pragma unroll
                 for (int ch = 0; ch < TSPN_GEO_CHANNELS; ++ch)
@@ -327,14 +310,12 @@ pair_geo_body(const CUtensorMap& box_map, const int64_t* __restrict__ table, int
     }
 }
 
-template <int THREADS, int WRITE_GEO, bool CLIP, bool DENSE>
+template <int THREADS, bool WRITE_GEO, bool CLIP, bool DENSE>
 __global__ void __launch_bounds__(THREADS, GeoCfg<THREADS, DENSE>::MIN_CTAS)
 pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __restrict__ table, int nv,
                 const int32_t* __restrict__ span, float* __restrict__ geo, unsigned long long* __restrict__ fx,
-                int32_t* __restrict__ overlap, unsigned int* __restrict__ queue, int max_chunks,
-                const int64_t* __restrict__ geo_off) {
-    pair_geo_body<THREADS, WRITE_GEO, CLIP, DENSE>(box_map, table, nv, span, geo, fx, overlap, queue, max_chunks,
-                                                   geo_off);
+                int32_t* __restrict__ overlap, unsigned int* __restrict__ queue, int max_chunks) {
+    pair_geo_body<THREADS, WRITE_GEO, CLIP, DENSE>(box_map, table, nv, span, geo, fx, overlap, queue, max_chunks);
 }
 
 // The 512-thread shape with the register count PINNED at 104: 16 warps x 104 registers leave exactly the 12 288
@@ -345,13 +326,12 @@ pair_geo_kernel(const __grid_constant__ CUtensorMap box_map, const int64_t* __re
 #ifndef TSPN_GEO_MAXNREG
 #define TSPN_GEO_MAXNREG 88
 #endif
-template <int WRITE_GEO, bool CLIP>
+template <bool WRITE_GEO, bool CLIP>
 __global__ void __maxnreg__(TSPN_GEO_MAXNREG)
 pair_geo_kernel_r104(const __grid_constant__ CUtensorMap box_map, const int64_t* __restrict__ table, int nv,
                      const int32_t* __restrict__ span, float* __restrict__ geo, unsigned long long* __restrict__ fx,
-                     int32_t* __restrict__ overlap, unsigned int* __restrict__ queue, int max_chunks,
-                     const int64_t* __restrict__ geo_off) {
-    pair_geo_body<512, WRITE_GEO, CLIP, false>(box_map, table, nv, span, geo, fx, overlap, queue, max_chunks, geo_off);
+                     int32_t* __restrict__ overlap, unsigned int* __restrict__ queue, int max_chunks) {
+    pair_geo_body<512, WRITE_GEO, CLIP, false>(box_map, table, nv, span, geo, fx, overlap, queue, max_chunks);
 }
 
 // ---- post-kernel: per-pair reductions (vIoU, tIoU; the pair kernel writes the overlap windows) ----------
@@ -614,7 +594,7 @@ template <int THREADS, bool DENSE>
 static int launch_pair_geo(const int64_t* d_table, int num_videos, int64_t total_items, int64_t total_boxes,
                            const float* d_boxes, const int32_t* d_span, float* d_geo, unsigned long long* fx,
                            int32_t* d_overlap, unsigned int* d_queue, int reserve, bool clip, int max_chunks,
-                           const int64_t* d_geo_off, cudaStream_t st) {
+                           cudaStream_t st) {
     using Cfg = GeoCfg<THREADS, DENSE>;
     // boxes viewed as a 2-D tensor: rows of 8 boxes (32 floats = 128 B)
     CUtensorMap map;
@@ -644,21 +624,19 @@ static int launch_pair_geo(const int64_t* d_table, int num_videos, int64_t total
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));  \
             prefer_max_smem(pair_geo_kernel_r104<W, C>);                                                       \
             pair_geo_kernel_r104<W, C><<<grid, THREADS, smem_bytes, st>>>(                                     \
-                map, d_table, num_videos, d_span, d_geo, fx, d_overlap, d_queue, max_chunks, d_geo_off);       \
+                map, d_table, num_videos, d_span, d_geo, fx, d_overlap, d_queue, max_chunks);                  \
         } else {                                                                                               \
             TSPN_CUDA_OK(cudaFuncSetAttribute(pair_geo_kernel<THREADS, W, C, DENSE>,                           \
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));  \
             prefer_max_smem(pair_geo_kernel<THREADS, W, C, DENSE>);                                            \
             pair_geo_kernel<THREADS, W, C, DENSE><<<grid, THREADS, smem_bytes, st>>>(                          \
-                map, d_table, num_videos, d_span, d_geo, fx, d_overlap, d_queue, max_chunks, d_geo_off);       \
+                map, d_table, num_videos, d_span, d_geo, fx, d_overlap, d_queue, max_chunks);                  \
         }                                                                                                      \
     } while (0)
-    if (d_geo && d_geo_off) {
-        if (clip) TSPN_LAUNCH_GEO(2, true); else TSPN_LAUNCH_GEO(2, false);
-    } else if (d_geo) {
-        if (clip) TSPN_LAUNCH_GEO(1, true); else TSPN_LAUNCH_GEO(1, false);
+    if (d_geo) {
+        if (clip) TSPN_LAUNCH_GEO(true, true); else TSPN_LAUNCH_GEO(true, false);
     } else {
-        if (clip) TSPN_LAUNCH_GEO(0, true); else TSPN_LAUNCH_GEO(0, false);
+        if (clip) TSPN_LAUNCH_GEO(false, true); else TSPN_LAUNCH_GEO(false, false);
     }
 #undef TSPN_LAUNCH_GEO
     TSPN_CUDA_OK(cudaGetLastError());
@@ -737,16 +715,24 @@ static int pair_geo_viou_impl(const int64_t* d_table, int num_videos, int64_t to
                                   ? reinterpret_cast<unsigned int*>(fx + total_pairs * (int64_t)max_chunks * 3)
                                   : nullptr;
         const int reserve = (flags >> TSPN_GEO_RESERVE_SHIFT) & 0xff;
+        if (d_geo_off) {
+            // the windowed layout's own kernel: a warp per pair over the pair's window (geo_windowed.cu)
+            rc = launch_pair_geo_windowed(d_table, num_videos, total_pairs, d_boxes, d_span, d_geo, d_geo_off, fx,
+                                          d_overlap, reinterpret_cast<unsigned int*>(fx + total_pairs * (int64_t)max_chunks * 3),
+                                          geo_chunk, max_chunks, reserve, clip, st);
+            if (rc != TSPN_OK) return rc;
+        } else {
 #define TSPN_GEO_SHAPE(T)                                                                                          \
     (dense ? launch_pair_geo<T, true>(d_table, num_videos, total_items, total_boxes, d_boxes, d_span, d_geo, fx,   \
-                                      d_overlap, queue, reserve, clip, max_chunks, nullptr, st)                    \
+                                      d_overlap, queue, reserve, clip, max_chunks, st)                             \
            : launch_pair_geo<T, false>(d_table, num_videos, total_items, total_boxes, d_boxes, d_span, d_geo, fx,  \
-                                       d_overlap, queue, reserve, clip, max_chunks, d_geo_off, st))
+                                       d_overlap, queue, reserve, clip, max_chunks, st))
         if (geo_chunk == 512) rc = TSPN_GEO_SHAPE(128);
         else if (geo_chunk == 1024) rc = TSPN_GEO_SHAPE(256);
         else rc = TSPN_GEO_SHAPE(512);
 #undef TSPN_GEO_SHAPE
         if (rc != TSPN_OK) return rc;
+        }
     }
     if (all || (phases & TSPN_GEO_PHASE_POST)) {
         const unsigned fblocks = (unsigned)((total_pairs + 255) / 256);
