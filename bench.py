@@ -84,6 +84,11 @@ def parse_args():
     ap.add_argument("--geo-layout", default="dense", choices=["dense", "windowed"],
                     help="layout of the per-frame geometry rows: dense [P, 8, Tp] (the parity layout) or windowed "
                          "(per pair only its overlap window's frames, 7 channels: tspn_pair_geo_viou_windowed)")
+    ap.add_argument("--serial-batches", action="store_true",
+                    help="`value`: run the batches of a step one after the other on one stream (A/B; default: the "
+                         "serving loop's two compute streams alternate, so a batch's side chain overlaps the next "
+                         "batch's all-pairs kernel)")
+    ap.add_argument("--max-videos", type=int, default=64, help="videos per batch at most")
     ap.add_argument("--no-layout-extra", action="store_true",
                     help="skip the extra run of the same workload with the windowed layout (`windowed_layout` in the line)")
     ap.add_argument("--relationness", default="fp32", choices=["fp32", "tensor"],
@@ -576,7 +581,8 @@ def run_ours(args, rank, world, local_rank):
         my_ids = shards[rank]
         videos = [synth.make_video(all_shapes[i][0], all_shapes[i][1], c, seed=i) for i in my_ids]
     pairs_global = sum(n * max(n - 1, 0) for n, _ in all_shapes)
-    hosts, batch_vids, caps = host_batches_for(videos, c, geo_budget_bytes=int(args.geo_budget_gb * (1 << 30)))
+    hosts, batch_vids, caps = host_batches_for(videos, c, geo_budget_bytes=int(args.geo_budget_gb * (1 << 30)),
+                                               max_videos=args.max_videos)
     residents = [h.to_device(dev) for h in hosts]            # the step's inputs, resident in HBM
     templates, seen = [], set()
     for h in hosts:
@@ -626,6 +632,12 @@ def run_ours(args, rank, world, local_rank):
     s_copy = torch.cuda.Stream(dev)
     holds = {}                                          # slot -> the resident batch its inputs currently are
 
+    # A step of several batches alternates the serving loop's two compute streams, exactly as PipelinedStage.submit
+    # does: batches are independent (different slots, different buffers), so the latency-bound side chain of batch j
+    # (survivor rows -> heads -> records) runs underneath the all-pairs kernel of batch j + 1 instead of in front of
+    # it.  The step's clock (events on the caller's stream) starts before the fork and stops after the join.
+    lanes = pipe.compute if (len(hosts) > 1 and len(pipe.compute) > 1 and not args.serial_batches) else None
+
     def one_step():
         main = torch.cuda.current_stream(dev)
         used, plan = {}, []
@@ -634,26 +646,35 @@ def run_ours(args, rank, world, local_rank):
             i = used.get(id(bucket), 0)
             used[id(bucket)] = i + 1
             plan.append((j, resident, bucket.slots[i % len(bucket.slots)]))
+        if lanes is not None:
+            for st in lanes:
+                st.wait_stream(main)                    # fork
         for j, resident, slot in plan:
-            if holds.get(slot) is not resident:
-                with torch.cuda.stream(s_copy):
-                    s_copy.wait_event(slot.kernels_done)        # the slot's previous replay has read its inputs
-                    slot.batch.copy_from_device(resident)
-                    slot.h2d_done.record(s_copy)
-                holds[slot] = resident
-                main.wait_event(slot.h2d_done)
-            else:
-                slot.batch._adopt(resident.host)
-            read_geo(slot)                              # its events are re-recorded by the next replay
-            timers = {}
-            res = slot.graphed.replay(timers=timers) if slot.graphed is not None else \
-                stage.forward(slot.batch, timers=timers)
-            slot.kernels_done.record(main)
-            pending[slot] = timers["geo"]
-            if shards is not None:
-                nr = len(batch_vids[j])
-                rec_local.index_copy_(0, batch_idx[j], res.records[:nr])
-                cnt_local.index_copy_(0, batch_idx[j], res.record_counts[:nr])
+            st = lanes[j % len(lanes)] if lanes is not None else main
+            with torch.cuda.stream(st):
+                if holds.get(slot) is not resident:
+                    with torch.cuda.stream(s_copy):
+                        s_copy.wait_event(slot.kernels_done)    # the slot's previous replay has read its inputs
+                        slot.batch.copy_from_device(resident)
+                        slot.h2d_done.record(s_copy)
+                    holds[slot] = resident
+                    st.wait_event(slot.h2d_done)
+                else:
+                    slot.batch._adopt(resident.host)
+                st.wait_event(slot.kernels_done)        # the slot's previous replay (the other lane's, possibly)
+                read_geo(slot)                          # its events are re-recorded by the next replay
+                timers = {}
+                res = slot.graphed.replay(timers=timers) if slot.graphed is not None else \
+                    stage.forward(slot.batch, timers=timers)
+                pending[slot] = timers["geo"]
+                if shards is not None:
+                    nr = len(batch_vids[j])
+                    rec_local.index_copy_(0, batch_idx[j], res.records[:nr])
+                    cnt_local.index_copy_(0, batch_idx[j], res.record_counts[:nr])
+                slot.kernels_done.record(st)
+        if lanes is not None:
+            for st in lanes:
+                main.wait_stream(st)                    # join
         return gather_step()
 
     def drain_geo():
@@ -804,6 +825,7 @@ def run_ours(args, rank, world, local_rank):
         "l2": "256 MiB buffer zeroed between timed iterations (untimed); each step also writes %.2f GB of outputs"
               % (alg_bytes / 1e9),
         "wall_s_timed_region": t_wall,
+        "batch_lanes": len(lanes) if lanes is not None else 1,
         "launch": "eager C-ABI calls" if args.eager else
                   ("one CUDA-graph launch per batch; the graph was captured once per capacity bucket and serves "
                    "every ragged batch packed for it; three branches inside: the persistent all-pairs kernel | "

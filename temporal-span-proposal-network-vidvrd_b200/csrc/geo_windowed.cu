@@ -90,24 +90,27 @@ pair_geo_windowed_kernel(const int64_t* __restrict__ table, int nv, const float4
     for (int i = 0; i <= GEO_FPT; ++i) rd_off[i] = box_off(j0 + i);
 
     // Work unit = GW_UNIT consecutive pairs, pulled by the warp from a global queue (pairs cost anything between
-    // nothing and T / 128 iterations: a static split leaves warps idle at the end).  The next unit's number is
-    // requested before the current unit is worked on, so the atomic's latency is never waited for.  Inside a unit the
-    // video's table row stays in registers: one search per unit (or per video boundary) instead of one per pair.
-    auto next_unit = [&]() {
-        unsigned int u = 0;
-        if (lane == 0) u = atomicAdd(queue, 1u);
-        return __shfl_sync(0xffffffffu, u, 0);
-    };
-    unsigned int unit = next_unit();
-    while ((int64_t)unit * GW_UNIT < n_pairs) {
-    const unsigned int unit_after = next_unit();
-    const int64_t p_end = min((int64_t)(unit + 1) * GW_UNIT, n_pairs);
+    // nothing and T / 128 iterations: a static split leaves warps idle at the end).  Lane 0 requests the next unit's
+    // number before the current unit is worked on and the warp reads it (the shuffle is what waits for the atomic)
+    // only when the unit is done.  The video's table row stays in registers: the queue hands out increasing pair
+    // numbers, so a warp's next pair lies in the same video or, usually, the next one - one dependent load instead of
+    // a binary search.
+    unsigned int pulled = 0;
+    if (lane == 0) pulled = atomicAdd(queue, 1u);
+    unsigned int unit = __shfl_sync(0xffffffffu, pulled, 0);
+    int v = -1;
     int64_t pair_lo = 0, pair_hi = 0, trk_off = 0, box_off0 = 0;     // the current video's row
     int n1 = 1, tb = 0, nchunks = 1;
+    while ((int64_t)unit * GW_UNIT < n_pairs) {
+    if (lane == 0) pulled = atomicAdd(queue, 1u);
+    const int64_t p_end = min((int64_t)(unit + 1) * GW_UNIT, n_pairs);
     for (int64_t p = (int64_t)unit * GW_UNIT; p < p_end; ++p) {
         // ---- the pair (warp-uniform) -----------------------------------------------------------------------
         if (p >= pair_hi) {
-            const int v = find_video(table, nv, TSPN_VT_PAIR_OFF, p);
+            int64_t hi2 = -1;
+            if (v >= 0 && v + 1 < nv) hi2 = __ldg(table + (int64_t)(v + 2) * TSPN_VT_COLS + TSPN_VT_PAIR_OFF);
+            if (p < hi2) ++v;                                          // the next video (pair_hi <= p < its end)
+            else v = find_video(table, nv, TSPN_VT_PAIR_OFF, p);
             const int64_t* row = table + (int64_t)v * TSPN_VT_COLS;
             n1 = (int)__ldg(row + TSPN_VT_N) - 1;
             tb = (int)__ldg(row + TSPN_VT_TB);
@@ -207,7 +210,7 @@ pair_geo_windowed_kernel(const int64_t* __restrict__ table, int nv, const float4
             *reinterpret_cast<int2*>(overlap + 2 * p) = make_int2(has ? a : 0, has ? b : 0);
         }
     }
-    unit = unit_after;
+    unit = __shfl_sync(0xffffffffu, pulled, 0);
     }
 }
 

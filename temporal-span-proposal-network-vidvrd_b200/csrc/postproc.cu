@@ -33,47 +33,50 @@ pair_top_predicates_kernel(const float* __restrict__ logits, const int64_t* __re
         }
         return;
     }
-    float v[SLOTS];
+    // Scores as order-preserving unsigned keys (larger float <=> larger key): a round is then the lane's best key,
+    // ONE warp REDUX.MAX, and one REDUX.MIN over the predicate indices of the lanes that hold that key (ties to the
+    // lower index) - instead of five rounds of two shuffles and a three-way compare.  0 = "no predicate left"
+    // (below the key of -inf).
+    uint32_t key[SLOTS];
 #pragma unroll
     for (int j = 0; j < SLOTS; ++j) {
         const int c = lane + 32 * j;
-        v[j] = c < r ? __ldg(logits + row * r + c) : NEG_INF;
+        uint32_t u = 0u;
+        if (c < r) {
+            uint32_t b = __float_as_uint(__ldg(logits + row * r + c));
+            if (b == 0x80000000u) b = 0u;        // -0.0 ties with +0.0, as in a float compare
+            u = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+            if (u == 0u) u = 1u;                 // (only -NaN with all mantissa bits set maps to 0)
+        }
+        key[j] = u;
     }
     for (int it = 0; it < tpp; ++it) {
-        float best = NEG_INF;
-        int bi = 0x7fffffff;
+        uint32_t best = 0u;
+        int bj = 0;
 #pragma unroll
-        for (int j = 0; j < SLOTS; ++j) {
-            const int c = lane + 32 * j;
-            if (c < r && (v[j] > best || (v[j] == best && c < bi))) {
-                best = v[j];
-                bi = c;
+        for (int j = 0; j < SLOTS; ++j)
+            if (key[j] > best) {                 // ascending j = ascending index: the first maximum wins
+                best = key[j];
+                bj = j;
             }
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const float ob = __shfl_xor_sync(0xffffffffu, best, off);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-            if (ob > best || (ob == best && oi < bi)) {
-                best = ob;
-                bi = oi;
+        const uint32_t top = __reduce_max_sync(0xffffffffu, best);
+        if (top == 0u) {                         // fewer than tpp predicates
+            for (int j = it + lane; j < tpp; j += 32) {
+                cs[j] = NEG_INF;
+                cp[j] = -1;
             }
+            break;
         }
-        if (bi == 0x7fffffff) {                 // fewer than tpp predicates
-            if (lane == 0) {
-                cs[it] = NEG_INF;
-                cp[it] = -1;
-            }
-            continue;
-        }
+        const int bi = (int)__reduce_min_sync(0xffffffffu, best == top ? (unsigned)(lane + 32 * bj) : 0xffffffffu);
         if (lane == 0) {
-            cs[it] = best;
+            const uint32_t b = (top & 0x80000000u) ? (top & 0x7fffffffu) : ~top;
+            cs[it] = __uint_as_float(b);
             cp[it] = bi;
         }
         if ((bi & 31) == lane) {
 #pragma unroll
             for (int j = 0; j < SLOTS; ++j)
-                if (j == (bi >> 5)) v[j] = NEG_INF;
+                if (j == (bi >> 5)) key[j] = 0u;
         }
     }
 }
