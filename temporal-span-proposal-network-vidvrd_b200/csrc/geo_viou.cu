@@ -36,6 +36,12 @@ constexpr int GEO_RING = TSPN_GEO_RING;               // object-chunk stages in 
 #define TSPN_GEO_ROTATE 1
 #endif
 constexpr bool GEO_ROTATE = TSPN_GEO_ROTATE != 0;     // rotate the warps' frame blocks with the object index
+#ifndef TSPN_GEO_CTAS256
+#define TSPN_GEO_CTAS256 2                            // CTAs per SM of the 256-thread (1024-frame chunk) shape
+#endif
+#ifndef TSPN_GEO_CTAS128
+#define TSPN_GEO_CTAS128 3                            // ... and of the 128-thread (512-frame chunk) shape
+#endif
 
 // Shape of one CTA: THREADS threads cover a chunk of 4*THREADS frames (512 / 1024 / 2048, chosen per
 // batch by tspn_geo_chunk).  HBM absorbs this kernel's store stream best as few, wide streams
@@ -60,7 +66,8 @@ struct GeoCfg {
     static constexpr int BOX_ROWS = SPLIT == 1 ? ROWS : CHUNK / 16 + 1;   // the second box re-reads one row
     static constexpr int TX_BYTES = SPLIT * BOX_ROWS * 128;       // bytes landing per staged chunk
     static constexpr int STAGE_BYTES = ROWS * 128;                // stages are packed (128-byte aligned)
-    static constexpr int MIN_CTAS = DENSE ? 1024 / THREADS : (THREADS >= 512 ? 1 : (THREADS == 256 ? 2 : 3));
+    static constexpr int MIN_CTAS = DENSE ? 1024 / THREADS
+                                          : (THREADS >= 512 ? 1 : (THREADS == 256 ? TSPN_GEO_CTAS256 : TSPN_GEO_CTAS128));
     // barriers, per-object fixed-point sums, per-object overlap windows
     static constexpr int TAIL_BYTES = (2 * RING * 8 + GEO_OG * (3 * 8 + 8) + 16 + 127) / 128 * 128;
     static constexpr int SMEM_USED = STAGES * STAGE_BYTES + TAIL_BYTES;

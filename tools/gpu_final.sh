@@ -14,6 +14,8 @@ timeout 600 python bench.py --workload baseline_yaml --precision tensor --steps 
 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --span-proposals 0 > $O/r2_bench_vidor_single_no_nms.json 2>/dev/null
 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --relationness tensor > $O/r2_bench_vidor_single_tc_relationness.json 2>/dev/null
 timeout 600 python bench.py --steps 2000 --warmup 20 --no-cpu-baseline > $O/r2_bench_vidor_single_sustained.json 2>/dev/null
+timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --geo-layout windowed > $O/r2_bench_vidor_single_windowed.json 2>/dev/null
+timeout 300 python tools/trace_step.py --steps 1 --geo-layout windowed 2>/dev/null | grep -v arn > $O/r2_timeline_vidor_single_windowed.txt
 timeout 300 python tools/trace_step.py --steps 2 2>/dev/null | grep -v arn > $O/r2_timeline_vidor_single.txt
 timeout 300 python tools/trace_step.py --steps 1 --relationness tensor 2>/dev/null | grep -v arn > $O/r2_timeline_vidor_single_tc.txt
 timeout 300 python tools/trace_step.py --steps 1 --workload vidor_val --batches 3 2>/dev/null | grep -v arn > $O/r2_timeline_vidor_val.txt
@@ -24,8 +26,9 @@ timeout 600 python tools/bench_predicate.py > $O/r2_predicate.jsonl 2> $O/r2_pre
 timeout 600 python tools/bench_span_head.py 256 1024 300 > $O/r2_span_head.jsonl 2> $O/r2_span_head.err
 timeout 600 python tools/bench_span_head.py 1024 1024 2000 >> $O/r2_span_head.jsonl 2>> $O/r2_span_head.err; cat $O/r2_span_head.jsonl
 # launch list of the bench command (eager launches: every kernel is a launch), full captures of the hot kernels
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r2_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --eager > $O/r2_launches.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'pair_geo_kernel|span_select|survivor_rows|scores_topk|ppn_embed|pair_top_predicates|predicate_tc' -s 20 -c 9 -o $O/r2_prof python bench.py --steps 2 --warmup 1 --no-cpu-baseline --eager > $O/r2_prof.log 2>&1; echo "ncu rc=$?"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r2_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-layout-extra --eager > $O/r2_launches.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'pair_geo_kernel|span_select|survivor_rows|scores_topk|ppn_embed|pair_top_predicates|predicate_tc' -s 20 -c 9 -o $O/r2_prof python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-layout-extra --eager > $O/r2_prof.log 2>&1; echo "ncu rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'pair_geo_windowed' -s 3 -c 1 -o $O/r2_prof_windowed python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-layout-extra --eager --geo-layout windowed > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none -k regex:'predicate_tc' -c 2 -o $O/r2_prof_predicate python tools/bench_predicate.py > /dev/null 2>&1
 timeout 900 ncu --set full --clock-control none -k regex:'span_head_tc' -c 1 -o $O/r2_prof_span_head python tools/bench_span_head.py 256 1024 300 > /dev/null 2>&1
 ls -la $O | head -60
