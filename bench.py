@@ -115,15 +115,16 @@ def workload_config(args, world: int) -> dict:
             "anchor_sizes": list(sizes), "anchor_stride": stride}
 
 
-def measured_traffic(workload, videos):
+def measured_traffic(workload, videos, layout="dense"):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this
-    workload (profiles/*_geo_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum); None when no
+    workload (profiles/*_geo_traffic*.json: dram__bytes_read.sum + dram__bytes_write.sum); None when no
     capture describes the requested batch."""
-    for name in ("r2_geo_traffic.json", "r1_geo_traffic.json"):
+    for name in ("r2_geo_traffic_windowed.json", "r2_geo_traffic.json", "r1_geo_traffic.json"):
         try:
             with open(os.path.join(ROOT, "profiles", name)) as f:
                 t = json.load(f)
-            if t.get("workload", "vidor_single") != workload or int(t["videos_per_launch"]) != int(videos):
+            if t.get("workload", "vidor_single") != workload or int(t["videos_per_launch"]) != int(videos) or \
+                    t.get("geo_layout", "dense") != layout:
                 continue
             return float(t["dram_bytes_read"]) + float(t["dram_bytes_write"])
         except Exception:  # noqa: BLE001
@@ -846,7 +847,7 @@ def run_ours(args, rank, world, local_rank):
         "data": "synthetic", "config": cfgd,
         "roofline": {"bound": "hbm", "kernel": "pair_geo_kernel (CUDA events immediately around each launch)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None if windowed else measured_traffic(args.workload, cfgd["videos"]),
+                     "traffic": measured_traffic(args.workload, cfgd["videos"], args.geo_layout),
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_step": alg_bytes, "launches_per_step": geo_launches / args.steps,
                      "avg_launch_ms": geo_ms_total / max(geo_launches, 1),
@@ -897,8 +898,8 @@ def windowed_subprocess(args):
         d = json.loads(out.stdout.strip().splitlines()[-1])
         r = d["roofline"]
         return {"value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"], "e2e": d["e2e"],
-                "roofline": {k: r[k] for k in ("kernel", "achieved", "peak", "unit", "frac", "algorithmic_bytes_per_step",
-                                               "avg_launch_ms", "share_of_step", "alone")},
+                "roofline": {k: r[k] for k in ("kernel", "achieved", "peak", "unit", "frac", "traffic",
+                                               "algorithmic_bytes_per_step", "avg_launch_ms", "share_of_step", "alone")},
                 "note": "geo rows as [7][Lw] per pair (only the overlap window's frames; bit-identical to the dense rows "
                         "there, tests/test_gpu_windowed.py); every other output of the step is the same tensor"}
     except Exception as e:  # noqa: BLE001

@@ -5,12 +5,12 @@
 // the channels of [SPEC] s2) - the values come from the same device function (geo_math.cuh: geo_step), the volume sums
 // are the same 64-bit fixed-point integers - but the rows are stored as [7][Lw] per pair (include/tspn_b200.h).
 //
-// Why another kernel shape: every channel is zero outside the window, so the windowed layout has ~2.5x fewer bytes to
+// Why another kernel shape: every channel is zero outside the window, so the windowed layout has ~2.9x fewer bytes to
 // write than the dense one on the bench workload.  The dense kernel's shape (a CTA per subject x 32 objects x chunk,
 // whole chunks of both tracklets staged by TMA, a thread per 4 frames of the CHUNK) then spends its time on frames that
 // produce nothing: 60 % of its warps fall through every object step while the others - 6 of 16 per SM on average -
 // carry the latency of the step alone, and all 2048 frames of every object still cross L2 -> shared memory (measured:
-// 0.495 ms for 1.7 GB = 0.45 of the HBM peak).  Here the unit of work is the window itself:
+// 0.495 ms for 1.45 GB = 0.45 of the HBM peak).  Here the unit of work is the window itself:
 //   * a warp owns a pair (pairs are handed out one at a time from a global queue: they cost anything from nothing
 //     to T / 128 iterations, and a static split leaves warps idle at the end - 8 pairs per pull: 0.364 ms, 1: 0.323 ms):
 //     it reads the two spans, and walks the window [a & ~3, (b + 3) & ~3) in blocks of 128 frames,
