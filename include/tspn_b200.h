@@ -230,7 +230,12 @@ int tspn_unpack_boxes_u16(const uint16_t* d_src, int64_t n_boxes, float* d_dst, 
  * nothing on the path reads a box outside its tracklet's span), so only those travel - tracklet n's at
  * d_packed[d_packed_off[n] ...] (int64 [total_tracklets], units of boxes, in tracklet order) - and the expansion
  * writes them at frames pstart .. of the dense row and zeros everywhere else.  total_tracklets is an upper bound
- * (the sentinel row carries the true count). */
+ * (the sentinel row carries the true count).  Per tracklet two encodings, chosen by the packer: RAW - one 8-byte slot
+ * (4 x u16) per frame - or, with TSPN_PACKED_DELTA set in d_packed_off[n], DELTA - slot 0 = the first frame's 4 x u16,
+ * then 4 x i8 per further frame (two frames per slot): each coordinate's difference to the previous frame, for
+ * tracklets whose boxes never move by more than [-128, 127] pixels per frame (half the bytes).  The expansion of a
+ * delta tracklet is an integer prefix sum over its frames: the boxes are the packer's integers exactly. */
+#define TSPN_PACKED_DELTA (1ll << 62)
 int tspn_unpack_boxes_spans(const int64_t* d_table, int num_videos, int64_t total_tracklets, const int32_t* d_span,
                             const int64_t* d_packed_off, const uint16_t* d_packed, float* d_dst, void* stream);
 /* Build rows [2C | 8000 motion | 3000 relative] (lib/dataset/vrdataset.py:219-243); the last

@@ -31,6 +31,7 @@ GEO_DENSE_CTAS = 2
 GEO_PHASE_PRE, GEO_PHASE_MAIN, GEO_PHASE_POST = 8, 16, 32
 GEO_PERSISTENT = 128
 GEO_RESERVE_SHIFT = 16
+PACKED_DELTA = 1 << 62     # include/tspn_b200.h TSPN_PACKED_DELTA: box_off bit of a delta-coded tracklet
 TOPK_KEEP_DIAGONAL, TOPK_EXCLUDE_DIAGONAL = 0, 1
 PREC_FP32_EXACT, PREC_TENSOR = 0, 1
 AFFINE_RAW = 1

@@ -18,6 +18,7 @@ list of ragged videos into such batches.
 from __future__ import annotations
 
 import dataclasses
+import os
 from typing import Iterable, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -130,7 +131,7 @@ class HostBatch:
 
     def __init__(self, boxes: Sequence, span: Sequence, cls: Optional[Sequence] = None,
                  motion: Optional[Sequence] = None, pin: bool = True, compact: bool = True,
-                 capacity: Optional[Capacity] = None):
+                 capacity: Optional[Capacity] = None, delta: Optional[bool] = None):
         """``compact`` (batches without a capacity): ship boxes as u16 pixel coordinates and motion
         histograms as u8 counts when every value is exactly representable (integer boxes in [0, 65535],
         integer counts in [0, 255]) - lossless, expanded on the device by ``tspn_unpack_boxes_u16`` /
@@ -138,6 +139,10 @@ class HostBatch:
         serving loop is PCIe-bound, and these two fields are 99 % of a batch's bytes.  Compact boxes are also
         SPAN-PACKED: only the frames ``[pstart, pend)`` of each tracklet travel (nothing on the path reads a box
         outside its tracklet's span), expanded into the dense zero-padded rows by ``tspn_unpack_boxes_spans``.
+        ``delta`` (default on; environment ``TSPN_BOX_DELTA=0`` turns it off): span-packed tracklets whose boxes move
+        by at most [-128, 127] pixels per frame travel as a first box + 4 x i8 differences per frame - half the
+        bytes, decoded by an integer prefix sum on the device; any other tracklet stays raw u16 (decided per
+        tracklet, so the arena layout - sized for raw - does not depend on the data).
 
         ``capacity``: pack for that capacity instead (serving: every batch of a capacity shares one arena
         layout and one captured graph).  The transport dtypes are then the capacity's; data that does not fit
@@ -145,6 +150,8 @@ class HostBatch:
         boxes = [_np(b, np.float32) for b in boxes]
         span = [_np(s, np.int32).reshape(-1, 2) for s in span]
         assert len(boxes) == len(span)
+        if delta is None:
+            delta = os.environ.get("TSPN_BOX_DELTA", "1") != "0"
         n_act = [int(b.shape[0]) for b in boxes]
         t_act = [int(b.shape[1]) if b.ndim == 3 else 1 for b in boxes]
         for b, s in zip(boxes, span):
@@ -220,13 +227,7 @@ class HostBatch:
             trk0 = int(row[VT_TRK_OFF])
             sview[trk0:trk0 + n] = s
             if self.boxes_compact:
-                frame = np.arange(t, dtype=np.int32)[None, :]
-                alive = (frame >= s[:, :1]) & (frame < s[:, 1:2])              # [N, T]: tracklet-major packing
-                lens = (s[:, 1] - s[:, 0]).astype(np.int64)
-                self.box_off.numpy()[trk0:trk0 + n] = packed + np.concatenate([[0], np.cumsum(lens)[:-1]])
-                cnt = int(lens.sum())
-                bview[packed:packed + cnt] = b[alive]
-                packed += cnt
+                packed += self._pack_span_boxes(b, s, trk0, packed, bview, delta)
             else:
                 dst = bview[int(row[VT_BOX_OFF]):int(row[VT_BOX_OFF]) + n * tb].reshape(n, tb, 4)
                 dst[:, :t] = b
@@ -241,12 +242,79 @@ class HostBatch:
         self.table_t = views["table"]
         self.table_t.numpy()[:] = np.ascontiguousarray(self.table).reshape(-1, VT_COLS)
 
+    def _pack_span_boxes(self, b: np.ndarray, s: np.ndarray, trk0: int, slot0: int, bview: np.ndarray,
+                         delta: bool) -> int:
+        """Span-packed transport of one video's boxes into the u16 arena, from 8-byte slot ``slot0`` on; returns the
+        slots used.  Tracklet-major; per tracklet either RAW (a slot of 4 x u16 per frame) or, when every coordinate
+        moves by at most [-128, 127] pixels per frame, DELTA (the first frame's slot, then 4 x i8 per further frame,
+        two frames per slot; ``_lib.PACKED_DELTA`` set in its ``box_off``) - see ``tspn_unpack_boxes_spans``."""
+        n, t = b.shape[0], b.shape[1]
+        frame = np.arange(t, dtype=np.int32)[None, :]
+        alive = (frame >= s[:, :1]) & (frame < s[:, 1:2])                  # [N, T]
+        lens = (s[:, 1] - s[:, 0]).astype(np.int64)
+        cnt = int(lens.sum())
+        flat = b[alive].astype(np.int32)                                   # [cnt, 4], tracklet-major
+        first = np.concatenate([[0], np.cumsum(lens)[:-1]])                # row of every tracklet's first frame
+        trk_of = np.repeat(np.arange(n), lens)
+        f_in = np.arange(cnt, dtype=np.int64) - first[trk_of]              # frame index inside its tracklet's span
+        d = np.zeros_like(flat)
+        if cnt > 1:
+            d[1:] = flat[1:] - flat[:-1]
+        d[f_in == 0] = 0
+        is_delta = np.zeros(n, dtype=bool)
+        if delta and cnt:
+            bad = ((d < -128) | (d > 127)).any(axis=1)
+            is_delta = (np.bincount(trk_of, weights=bad, minlength=n) == 0) & (lens > 0)
+        slots = np.where(is_delta, 1 + lens // 2, lens)                    # 1 + ceil((L - 1) / 2) = 1 + L // 2
+        off = slot0 + np.concatenate([[0], np.cumsum(slots)[:-1]])
+        self.box_off.numpy()[trk0:trk0 + n] = off | np.where(is_delta, np.int64(_lib.PACKED_DELTA), np.int64(0))
+        used = int(slots.sum())
+        row_delta = is_delta[trk_of]
+        raw = ~row_delta
+        bview[(off[trk_of] + f_in)[raw]] = flat[raw]
+        head = row_delta & (f_in == 0)
+        bview[off[trk_of][head]] = flat[head]
+        tail = row_delta & (f_in > 0)
+        if tail.any():
+            i8 = bview[slot0:slot0 + used].view(np.int8).reshape(-1, 4)    # 4-byte records, two per slot
+            i8[((off[trk_of] - slot0 + 1) * 2 + f_in - 1)[tail]] = d[tail].astype(np.int8)
+        return used
+
+    def unpacked_boxes(self) -> List[np.ndarray]:
+        """Host-side decode of the box transport (what ``tspn_unpack_boxes_spans`` does on the device): the dense
+        ``[N, T, 4]`` float32 boxes of every real video.  For tests of the packer; nothing on the product path uses it."""
+        out = []
+        sview = self.span.numpy()
+        for v in range(self.num_real):
+            row = self.table[v]
+            n, t, tb, trk0 = int(row[VT_N]), int(row[VT_T]), int(row[VT_TB]), int(row[VT_TRK_OFF])
+            dense = np.zeros((n, t, 4), dtype=np.float32)
+            if not self.boxes_compact:
+                b0 = int(row[VT_BOX_OFF])
+                dense[:] = self.boxes.numpy()[b0:b0 + n * tb].reshape(n, tb, 4)[:, :t]
+            else:
+                u16 = self.boxes.numpy().view(np.uint16)
+                for i in range(n):
+                    ps, pe = int(sview[trk0 + i, 0]), int(sview[trk0 + i, 1])
+                    po = int(self.box_off.numpy()[trk0 + i])
+                    slot, length = po & ~_lib.PACKED_DELTA, pe - ps
+                    if length <= 0:
+                        continue
+                    if not (po & _lib.PACKED_DELTA):
+                        dense[i, ps:pe] = u16[slot:slot + length]
+                    else:
+                        dl = u16[slot + 1:slot + 1 + length // 2].view(np.int8).reshape(-1, 4)[:length - 1]
+                        dense[i, ps:pe] = np.concatenate([u16[slot:slot + 1].astype(np.int64),
+                                                          dl.astype(np.int64)]).cumsum(axis=0)
+            out.append(dense)
+        return out
+
     @classmethod
     def from_videos(cls, videos, pin: bool = True, compact: bool = True,
-                    capacity: Optional[Capacity] = None) -> "HostBatch":
+                    capacity: Optional[Capacity] = None, delta: Optional[bool] = None) -> "HostBatch":
         """From ``tspn_b200.synth.VideoTracklets`` (or anything with boxes/span/cls/motion)."""
         return cls([v.boxes for v in videos], [v.span for v in videos], [v.cls for v in videos],
-                   [v.motion for v in videos], pin=pin, compact=compact, capacity=capacity)
+                   [v.motion for v in videos], pin=pin, compact=compact, capacity=capacity, delta=delta)
 
     @property
     def num_videos(self) -> int:

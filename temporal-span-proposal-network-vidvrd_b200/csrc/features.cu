@@ -67,14 +67,23 @@ __global__ void __launch_bounds__(256) unpack_boxes_u16_kernel(const uint2* __re
     }
 }
 
-// span-packed u16 boxes -> dense fp32 rows: tracklet n's packed boxes (frames [pstart, pend) only, at
-// packed[pk_off[n] ...]) go to its dense row at frames pstart .., every other frame of the row is written as zero.
+// span-packed u16 boxes -> dense fp32 rows: tracklet n's packed boxes (frames [pstart, pend) only, at 8-byte slot
+// pk_off[n] of `packed`) go to its dense row at frames pstart .., every other frame of the row is written as zero.
+// Two encodings per tracklet (bit 62 of pk_off[n], TSPN_PACKED_DELTA):
+//   raw    one slot per frame: 4 x u16 pixel coordinates;
+//   delta  slot 0 = the first frame's 4 x u16, then 4 x i8 per further frame (two frames per slot): the coordinate
+//          differences to the previous frame - what the host emits for every tracklet whose boxes move by at most
+//          [-128, 127] pixels per frame (half the bytes; tracked objects do).  Decoding is a prefix sum over the
+//          frames: tiles of 256 frames, a warp scan per coordinate + the warps' totals through shared memory + the
+//          running box carried from tile to tile - integer adds, so the boxes are the host's integers exactly.
 // One CTA per tracklet; the dense row is box_off(video) + n_local * Tb.
 __global__ void __launch_bounds__(256) unpack_boxes_spans_kernel(const int64_t* __restrict__ table, int nv,
                                                                  const int32_t* __restrict__ span,
                                                                  const int64_t* __restrict__ pk_off,
                                                                  const uint2* __restrict__ packed,
                                                                  float4* __restrict__ dst) {
+    __shared__ int4 warp_tot[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t n_trk = table_total(table, nv, TSPN_VT_TRK_OFF);
     for (int64_t trk = blockIdx.x; trk < n_trk; trk += gridDim.x) {
         const int v = find_video(table, nv, TSPN_VT_TRK_OFF, trk);
@@ -82,14 +91,56 @@ __global__ void __launch_bounds__(256) unpack_boxes_spans_kernel(const int64_t* 
         const int tb = (int)row[TSPN_VT_TB];
         float4* out = dst + row[TSPN_VT_BOX_OFF] + (trk - row[TSPN_VT_TRK_OFF]) * tb;
         const int ps = __ldg(span + 2 * trk), pe = __ldg(span + 2 * trk + 1);
-        const uint2* src = packed + __ldg(pk_off + trk) - ps;
-        for (int f = threadIdx.x; f < tb; f += 256) {
-            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (f >= ps && f < pe) {
-                const uint2 w = __ldg(src + f);
-                b = make_float4((float)(w.x & 0xffffu), (float)(w.x >> 16), (float)(w.y & 0xffffu), (float)(w.y >> 16));
+        const int64_t po = __ldg(pk_off + trk);
+        const int64_t slot = po & ~TSPN_PACKED_DELTA;
+        if (!(po & TSPN_PACKED_DELTA)) {
+            const uint2* src = packed + slot - ps;
+            for (int f = threadIdx.x; f < tb; f += 256) {
+                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (f >= ps && f < pe) {
+                    const uint2 w = __ldg(src + f);
+                    b = make_float4((float)(w.x & 0xffffu), (float)(w.x >> 16), (float)(w.y & 0xffffu), (float)(w.y >> 16));
+                }
+                out[f] = b;
             }
-            out[f] = b;
+            continue;
+        }
+        for (int f = threadIdx.x; f < tb; f += 256)
+            if (f < ps || f >= pe) out[f] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int n_delta = pe - ps - 1;                          // frames after the first
+        if (n_delta < 0) continue;
+        const uint2 w0 = __ldg(packed + slot);
+        int4 run = make_int4((int)(w0.x & 0xffffu), (int)(w0.x >> 16), (int)(w0.y & 0xffffu), (int)(w0.y >> 16));
+        if (threadIdx.x == 0) out[ps] = make_float4((float)run.x, (float)run.y, (float)run.z, (float)run.w);
+        const int32_t* dl = reinterpret_cast<const int32_t*>(packed + slot + 1);
+        for (int j0 = 0; j0 < n_delta; j0 += 256) {               // uniform trip count: barriers inside
+            const int j = j0 + threadIdx.x;
+            int4 d = make_int4(0, 0, 0, 0);
+            if (j < n_delta) {
+                const int32_t w = __ldg(dl + j);
+                d = make_int4((int)(int8_t)(w & 0xff), (int)(int8_t)((w >> 8) & 0xff), (int)(int8_t)((w >> 16) & 0xff),
+                              (int)(int8_t)((w >> 24) & 0xff));
+            }
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int ux = __shfl_up_sync(0xffffffffu, d.x, off), uy = __shfl_up_sync(0xffffffffu, d.y, off);
+                const int uz = __shfl_up_sync(0xffffffffu, d.z, off), uw = __shfl_up_sync(0xffffffffu, d.w, off);
+                if (lane >= off) { d.x += ux; d.y += uy; d.z += uz; d.w += uw; }
+            }
+            if (lane == 31) warp_tot[warp] = d;
+            __syncthreads();
+            int4 pre = run, tot = run;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                const int4 t = warp_tot[w];
+                if (w < warp) { pre.x += t.x; pre.y += t.y; pre.z += t.z; pre.w += t.w; }
+                tot.x += t.x; tot.y += t.y; tot.z += t.z; tot.w += t.w;
+            }
+            if (j < n_delta)
+                out[ps + 1 + j] = make_float4((float)(pre.x + d.x), (float)(pre.y + d.y), (float)(pre.z + d.z),
+                                              (float)(pre.w + d.w));
+            __syncthreads();                                      // warp_tot is rewritten by the next tile
+            run = tot;
         }
     }
 }

@@ -100,3 +100,62 @@ def test_select_spans_oracle_is_greedy_nms(thr):
 def test_cpulist_parsing_and_even_share(monkeypatch):
     assert affinity._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
     assert affinity._parse_cpulist("") == []
+
+
+# ---------------------------------------------------------------------------------------------------------
+# box transport: span-packed u16, per tracklet raw or delta-coded (HostBatch._pack_span_boxes)
+# ---------------------------------------------------------------------------------------------------------
+def _edge_video():
+    """Spans of 0, 1, 2, 3 frames, a span at frame 0, one up to T, a tracklet that jumps by more than 127 pixels
+    (raw fallback), one that moves by exactly -128 / +127 (still delta), and coordinates at the u16 limits."""
+    from tspn_b200 import synth
+    v = synth.make_video(9, 40, 35, seed=5, full_span=True)
+    v.span[:] = [(0, 40), (7, 7), (3, 4), (10, 12), (20, 23), (0, 1), (39, 40), (5, 35), (2, 38)]
+    v.boxes[7, 20:, 0] += 500.0                       # a jump: this tracklet cannot be delta-coded
+    v.boxes[7, 20:, 2] += 500.0
+    step = np.where(np.arange(40) % 2 == 0, 127.0, -128.0)
+    v.boxes[8, :, 0] = 1000.0 + np.cumsum(step)
+    v.boxes[8, :, 2] = 65535.0 - np.arange(40)
+    t = np.arange(40)[None, :, None]
+    v.boxes[:] = np.where((t >= v.span[:, :1, None]) & (t < v.span[:, 1:, None]), v.boxes, 0.0)
+    return v
+
+
+@pytest.mark.parametrize("delta", [True, False])
+def test_box_transport_round_trip_on_the_host(delta):
+    from tspn_b200 import _lib, synth
+    vids = [synth.make_video(12, 300, 35, seed=1), _edge_video(), synth.make_video(3, 5, 35, seed=2)]
+    host = HostBatch.from_videos(vids, pin=False, delta=delta)
+    assert host.boxes_compact
+    for v, got in zip(vids, host.unpacked_boxes()):
+        np.testing.assert_array_equal(got, v.boxes)
+    off = host.box_off.numpy()
+    is_delta = (off & _lib.PACKED_DELTA) != 0
+    if not delta:
+        assert not is_delta.any()
+        assert host.packed_boxes == sum(int((v.span[:, 1] - v.span[:, 0]).sum()) for v in vids)
+    else:
+        edge0 = 12                                    # first tracklet of the edge video
+        assert is_delta[:12].all()                    # smooth synthetic tracklets
+        assert not is_delta[edge0 + 1]                # empty span: nothing to code
+        assert not is_delta[edge0 + 7]                # the jump: raw
+        assert is_delta[edge0 + 8]                    # -128 / +127 per frame still fits
+        lens = np.concatenate([v.span[:, 1] - v.span[:, 0] for v in vids])
+        want = np.where(is_delta, 1 + lens // 2, lens).sum()
+        assert host.packed_boxes == want
+        raw = HostBatch.from_videos(vids, pin=False, delta=False)
+        assert host.h2d_bytes() < raw.h2d_bytes()
+        assert host.layout == raw.layout              # the arena does not depend on the coding
+
+
+def test_box_transport_with_a_capacity_and_fractional_boxes():
+    from tspn_b200 import synth
+    vids = [synth.make_video(6, 120, 35, seed=3), _edge_video()]
+    cap = Capacity.for_shapes([(12, 128), (9, 64)], 35, videos=3)
+    host = HostBatch.from_videos(vids, pin=False, capacity=cap)
+    for v, got in zip(vids, host.unpacked_boxes()):
+        np.testing.assert_array_equal(got, v.boxes)
+    frac = synth.make_video(4, 50, 35, seed=4, integer_boxes=False)
+    host = HostBatch.from_videos([frac], pin=False)
+    assert not host.boxes_compact
+    np.testing.assert_array_equal(host.unpacked_boxes()[0], frac.boxes)

@@ -266,3 +266,35 @@ def test_compact_transport_is_lossless():
         assert torch.equal(outs[0][1], outs[1][1])
         for k in outs[1][0]:
             assert torch.equal(outs[0][0][k], outs[1][0][k]), k
+
+
+@pytest.mark.parametrize("with_capacity", [False, True])
+def test_delta_coded_boxes_expand_to_the_same_rows(with_capacity):
+    """Span-packed boxes, raw u16 against delta-coded (first box + i8 differences, ``TSPN_PACKED_DELTA``): the dense
+    fp32 rows ``tspn_unpack_boxes_spans`` writes are the host's boxes bit for bit either way - spans of 0..3 frames,
+    spans longer than several 256-frame scan tiles, a tracklet that cannot be delta-coded between ones that can, steps
+    of exactly -128 / +127 - and the refill of a device batch switches coding per tracklet without a new layout."""
+    from tests.test_cpu_ragged import _edge_video
+    from tspn_b200 import _lib
+    from tspn_b200.batch import VT_BOX_OFF, VT_N, VT_T, VT_TB, Capacity, HostBatch
+    vids = [synth.make_video(12, 2000, 35, seed=1), _edge_video(), synth.make_video(3, 5, 35, seed=2),
+            synth.make_video(5, 777, 35, seed=3, full_span=True)]
+    vids[3].boxes[2, 300:, 1] += 300.0                 # raw tracklet in a video of delta tracklets
+    vids[3].boxes[2, 300:, 3] += 300.0
+    cap = Capacity.for_shapes([(12, 2048), (9, 64), (5, 1024)], 35, videos=5) if with_capacity else None
+
+    hosts = {d: HostBatch.from_videos(vids, capacity=cap, delta=d) for d in (True, False)}
+    assert hosts[True].h2d_bytes() < hosts[False].h2d_bytes()
+    off = hosts[True].box_off.numpy()
+    assert ((off & _lib.PACKED_DELTA) != 0).sum() >= 12 + 5 + 4
+    dev = hosts[False].to_device("cuda")
+    for d in (False, True, False, True):
+        dev.copy_from(hosts[d])
+        torch.cuda.synchronize()
+        rows = dev.boxes.cpu().numpy().reshape(-1, 4)
+        for v, vid in enumerate(vids):
+            r = hosts[d].table[v]
+            n, t, tb, b0 = int(r[VT_N]), int(r[VT_T]), int(r[VT_TB]), int(r[VT_BOX_OFF])
+            got = rows[b0:b0 + n * tb].reshape(n, tb, 4)
+            np.testing.assert_array_equal(got[:, :t], vid.boxes, err_msg=f"delta={d} video {v}")
+            np.testing.assert_array_equal(got[:, t:], 0)
