@@ -281,7 +281,7 @@ def test_delta_coded_boxes_expand_to_the_same_rows(with_capacity):
             synth.make_video(5, 777, 35, seed=3, full_span=True)]
     vids[3].boxes[2, 300:, 1] += 300.0                 # raw tracklet in a video of delta tracklets
     vids[3].boxes[2, 300:, 3] += 300.0
-    cap = Capacity.for_shapes([(12, 2048), (9, 64), (5, 1024)], 35, videos=5) if with_capacity else None
+    cap = Capacity.for_shapes([(12, 2048), (9, 64), (3, 8), (5, 1024)], 35, videos=5) if with_capacity else None
 
     hosts = {d: HostBatch.from_videos(vids, capacity=cap, delta=d) for d in (True, False)}
     assert hosts[True].h2d_bytes() < hosts[False].h2d_bytes()
