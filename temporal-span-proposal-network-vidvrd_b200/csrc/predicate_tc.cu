@@ -83,21 +83,26 @@ predicate_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 
     if (warp == 0) {
         if (lane == 0) {
+            // ring position kept incrementally: no division by the run-time stage count in a one-thread role
+            int s = 0;
+            uint32_t ph = 0;
+            bool first_lap = true;
             for (int i = 0; i < nkb; ++i) {
-                const int s = i % stages, use = i / stages;
-                if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
+                if (!first_lap) mbar_wait(&empty[s], ph ^ 1u);
                 uint8_t* a = smem + (size_t)s * stage_bytes;
                 mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
                 tma_load_2d(a, &map_x, (kb0 + i) * K_ELEMS, m_tile * PT_BM, &full[s]);
                 tma_load_2d(a + stage_a, &map_w, (kb0 + i) * K_ELEMS, 0, &full[s]);
+                if (++s == stages) { s = 0; ph ^= 1u; first_lap = false; }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = umma_idesc(BF16 ? UMMA_FMT_BF16 : UMMA_FMT_TF32, PT_BM, (uint32_t)rpad, 0, 0);
+            int s = 0;
+            uint32_t ph = 0;
             for (int i = 0; i < nkb; ++i) {
-                const int s = i % stages, use = i / stages;
-                mbar_wait(&full[s], use & 1);
+                mbar_wait(&full[s], ph);
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
                 const uint64_t adesc = umma_smem_desc(a_addr, 16, 1024);
@@ -109,6 +114,7 @@ predicate_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                     else      umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (i | k) != 0);
                 }
                 umma_commit(&empty[s]);          // frees the stage once these MMAs have read it
+                if (++s == stages) { s = 0; ph ^= 1u; }
             }
             umma_commit(tmem_full);              // accumulator complete
         }

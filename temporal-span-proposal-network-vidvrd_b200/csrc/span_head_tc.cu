@@ -25,7 +25,16 @@
 //   * with several channel chunks the per-chunk partial outputs are summed in chunk order by
 //     span_finish_kernel (deterministic), which also adds b2 and writes the [k][2A][T] layout.
 // Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue.
+//
+// Cin >= 256 runs the CTA-PAIR form (span_head_tc2_kernel, cta_group::2): the one-CTA form re-reads (128 + 256) x 64
+// bf16 from L2 per 128 x 256 x 64 MMA block and sits on the L2 -> SM limit (ncu, [256, 1024, 300]: 5.7 GB over the
+// crossbar in 0.49 ms = 5900 B per clock, the chip's measured LTS ceiling, with the tensor pipe 51 % busy).  A pair of
+// CTAs on the two SMs of a TPC shares one M = 256 x N = 256 MMA: each CTA stages its own 128 rows of A and only HALF of
+// the weight tile (128 of the 256 output channels), the tensor cores of both SMs read both halves - (128 + 128) x 64
+// per CTA for the same math, 2/3 of the L2 traffic.  The leader CTA issues the MMAs; both CTAs load (signalling the
+// leader's mbarrier), both run the epilogue on their own 128 accumulator rows.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "tc_common.cuh"
 
@@ -35,7 +44,7 @@ constexpr int ST_BM = 128;                 // rows (pair-frames) per tile = UMMA
 constexpr int ST_SLAB = 64;                // bf16 elements of K per stage row (128 bytes)
 constexpr int ST_THREADS = 192;
 constexpr int ST_MAX_CHUNK = 256;          // output channels per unit = UMMA N
-constexpr int ST_SMEM_BUDGET = 208 * 1024;
+constexpr int ST_SMEM_BUDGET = 224 * 1024;    // stages + the epilogue's slice (227 KB per CTA on sm_100)
 
 static inline int64_t st_round(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 static inline int st_chunk(int cin) { return cin >= ST_MAX_CHUNK ? ST_MAX_CHUNK : (int)st_round(cin, 16); }
@@ -51,7 +60,7 @@ struct StLayout {
 static StLayout st_layout(int64_t k, int cin, int t, int a2) {
     StLayout L;
     L.rows = k * ((int64_t)t + 2);
-    L.tiles = (L.rows + ST_BM - 1) / ST_BM;
+    L.tiles = (L.rows + 2 * ST_BM - 1) / (2 * ST_BM) * 2;      // even: a CTA pair works on two row tiles at once
     L.chunk = st_chunk(cin);
     L.chunks = (cin + L.chunk - 1) / L.chunk;
     L.a2p = st_a2p(a2);
@@ -132,13 +141,70 @@ span_pack_x_kernel(const float* __restrict__ x, const int64_t* __restrict__ rows
     }
 }
 
+// ---- epilogue pieces shared by both kernel forms --------------------------------------------------------------------
+// The four epilogue warps (threads 64..191) stage the unit's slice of the 1x1 conv - w2t[co0 .. co0 + chunk) and the
+// conv bias - in shared memory once per unit, zero padded to `chunk` columns (columns beyond Cin read accumulators that
+// are exactly zero: their weight rows are TMA out-of-bounds fill): the column loop then has no guards and its operands
+// are warp-uniform LDS broadcasts.  (First version: three global loads per column behind a `co < cin` branch, which
+// ptxas left as 256 serialised load -> use round trips per unit: 24 us of epilogue per unit against 13 us of MMA.)
+__device__ __forceinline__ void st_named_bar(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+constexpr int ST_EPI_THREADS = 128;
+static inline size_t st_epi_bytes(int chunk, int a2p) { return (size_t)chunk * (a2p + 1) * sizeof(float); }
+
+template <int A2P>
+__device__ __forceinline__ void st_stage_slice(float* __restrict__ s_w, float* __restrict__ s_b, int chunk, int co0,
+                                               int cin, const float* __restrict__ conv_b,
+                                               const float* __restrict__ w2t) {
+    const int et = (int)threadIdx.x - 64;
+    const int ncols = min(chunk, cin - co0);
+    st_named_bar(1, ST_EPI_THREADS);                     // every warp is done with the previous slice
+    const float4* src = reinterpret_cast<const float4*>(w2t + (int64_t)co0 * A2P);
+    float4* dst = reinterpret_cast<float4*>(s_w);
+    for (int i = et; i < chunk * (A2P / 4); i += ST_EPI_THREADS)
+        dst[i] = i < ncols * (A2P / 4) ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = et; i < chunk; i += ST_EPI_THREADS) s_b[i] = (conv_b && i < ncols) ? __ldg(conv_b + co0 + i) : 0.0f;
+    st_named_bar(1, ST_EPI_THREADS);
+}
+
+// acc[j] = sum over the chunk's columns of W2[j][co] * relu(accumulator[row][co] + b[co]) for this lane's row
+template <int A2P>
+__device__ __forceinline__ void st_fold_columns(uint32_t taddr, int chunk, const float* __restrict__ s_w,
+                                                const float* __restrict__ s_b, float (&acc)[A2P]) {
+#pragma unroll
+    for (int j = 0; j < A2P; ++j) acc[j] = 0.0f;
+    for (int c0 = 0; c0 < chunk; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + (uint32_t)c0, v);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const float4 b4 = *reinterpret_cast<const float4*>(s_b + c0 + 4 * g);
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float h = fmaxf(v[4 * g + e] + bb[e], 0.0f);
+                const float4* wq = reinterpret_cast<const float4*>(s_w + (c0 + 4 * g + e) * A2P);
+#pragma unroll
+                for (int q = 0; q < A2P / 4; ++q) {
+                    const float4 w = wq[q];
+                    acc[4 * q + 0] = fmaf(w.x, h, acc[4 * q + 0]);
+                    acc[4 * q + 1] = fmaf(w.y, h, acc[4 * q + 1]);
+                    acc[4 * q + 2] = fmaf(w.z, h, acc[4 * q + 2]);
+                    acc[4 * q + 3] = fmaf(w.w, h, acc[4 * q + 3]);
+                }
+            }
+        }
+    }
+}
+
 // ---- the implicit-GEMM kernel ---------------------------------------------------------------------------
 template <int A2P>
 __global__ void __launch_bounds__(ST_THREADS, 1)
 span_head_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                     int64_t tiles, int cin, int chunk, int chunks, int kslabs, int stages, uint32_t tmem_cols,
                     const float* __restrict__ conv_b, const float* __restrict__ w2t,
-                    float* __restrict__ partial) {
+                    float* __restrict__ partial, int dbg) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int stage_a = ST_BM * 128;
     const int stage_bytes = stage_a + chunk * 128;
@@ -147,6 +213,8 @@ span_head_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     uint64_t* const acc_full = empty + stages;          // [2]
     uint64_t* const acc_empty = acc_full + 2;           // [2]
     uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    float* const s_w = reinterpret_cast<float*>(tmem_slot + 4);          // [chunk][A2P], 16-byte aligned
+    float* const s_b = s_w + (size_t)chunk * A2P;                        // [chunk]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t units = tiles * chunks;
@@ -176,44 +244,56 @@ span_head_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 
     if (warp == 0) {
         if (lane == 0) {
-            int64_t it = 0;                             // global K-block counter -> stage / parity
+            // ring position kept incrementally (stage s, phase bit ph): a division by the run-time stage count per K
+            // block - two 64-bit ones in the first version - is a ~400-cycle serial chain in a one-thread role, more
+            // than the 512 cycles of MMA a block feeds
+            int s = 0;
+            uint32_t ph = 0;
+            bool first_lap = true;
             for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
                 const int64_t tile = u / chunks;
                 const int co0 = (int)(u - tile * chunks) * chunk;
-                for (int i = 0; i < nkb; ++i, ++it) {
-                    const int s = (int)(it % stages);
-                    const int64_t use = it / stages;
-                    if (use > 0) mbar_wait(&empty[s], (uint32_t)((use - 1) & 1));
-                    const int tap = i / kslabs, ci0 = (i - tap * kslabs) * ST_SLAB;
-                    uint8_t* a = smem + (size_t)s * stage_bytes;
-                    mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
-                    // output row r reads xt rows (1 + r) + tap - 1 = r + tap
-                    tma_load_2d(a, &map_x, ci0, (int)(tile * ST_BM + tap), &full[s]);
-                    tma_load_3d(a + stage_a, &map_w, ci0, co0, tap, &full[s]);
+                for (int tap = 0; tap < 3; ++tap) {
+                    for (int ci0 = 0; ci0 < kslabs * ST_SLAB; ci0 += ST_SLAB) {
+                        if (!first_lap) mbar_wait(&empty[s], ph ^ 1u);
+                        uint8_t* a = smem + (size_t)s * stage_bytes;
+                        if ((dbg & 1) && !first_lap) {                   // limiter experiment: no loads
+                            mbar_arrive(&full[s]);
+                        } else {
+                            mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
+                            // output row r reads xt rows (1 + r) + tap - 1 = r + tap
+                            tma_load_2d(a, &map_x, ci0, (int)(tile * ST_BM + tap), &full[s]);
+                            tma_load_3d(a + stage_a, &map_w, ci0, co0, tap, &full[s]);
+                        }
+                        if (++s == stages) { s = 0; ph ^= 1u; first_lap = false; }
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = umma_idesc(UMMA_FMT_BF16, ST_BM, (uint32_t)chunk, 0, 0);
-            int64_t it = 0, ul = 0;
+            int64_t ul = 0;
+            int s = 0;
+            uint32_t ph = 0;
             for (int64_t u = blockIdx.x; u < units; u += gridDim.x, ++ul) {
                 const int b = (int)(ul & 1);
                 const int64_t buse = ul >> 1;
                 if (buse > 0) mbar_wait(&acc_empty[b], (uint32_t)((buse - 1) & 1));
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(b * chunk);
-                for (int i = 0; i < nkb; ++i, ++it) {
-                    const int s = (int)(it % stages);
-                    mbar_wait(&full[s], (uint32_t)((it / stages) & 1));
+                for (int i = 0; i < nkb; ++i) {
+                    mbar_wait(&full[s], ph);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
                     const uint64_t adesc = umma_smem_desc(a_addr, 16, 1024);
                     const uint64_t bdesc = umma_smem_desc(a_addr + stage_a, 16, 1024);
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk)       // 4 x (K = 16 bf16 = 32 bytes) per 128-byte slab
-                        umma_f16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (i | kk) != 0);
+                        if (!(dbg & 2) || i == 0)        // (limiter experiment: no math after the first block)
+                            umma_f16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (i | kk) != 0);
                     umma_commit(&empty[s]);
+                    if (++s == stages) { s = 0; ph ^= 1u; }
                 }
                 umma_commit(&acc_full[b]);
             }
@@ -227,33 +307,12 @@ span_head_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             const int64_t tile = u / chunks;
             const int cidx = (int)(u - tile * chunks);
             const int co0 = cidx * chunk;
+            st_stage_slice<A2P>(s_w, s_b, chunk, co0, cin, conv_b, w2t);     // (under this unit's MMAs)
             mbar_wait(&acc_full[b], (uint32_t)((ul >> 1) & 1));
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * chunk);
             float acc[A2P];
-#pragma unroll
-            for (int j = 0; j < A2P; ++j) acc[j] = 0.0f;
-            const int ncols = min(chunk, cin - co0);
-            for (int c0 = 0; c0 < ncols; c0 += 16) {
-                float v[16];
-                tmem_ld16(taddr + (uint32_t)c0, v);
-#pragma unroll
-                for (int jj = 0; jj < 16; ++jj) {
-                    const int co = co0 + c0 + jj;
-                    if (co < cin) {
-                        const float h = fmaxf(v[jj] + (conv_b ? __ldg(conv_b + co) : 0.0f), 0.0f);
-                        const float4* wq = reinterpret_cast<const float4*>(w2t + (int64_t)co * A2P);
-#pragma unroll
-                        for (int q = 0; q < A2P / 4; ++q) {
-                            const float4 w = __ldg(wq + q);
-                            acc[4 * q + 0] = fmaf(w.x, h, acc[4 * q + 0]);
-                            acc[4 * q + 1] = fmaf(w.y, h, acc[4 * q + 1]);
-                            acc[4 * q + 2] = fmaf(w.z, h, acc[4 * q + 2]);
-                            acc[4 * q + 3] = fmaf(w.w, h, acc[4 * q + 3]);
-                        }
-                    }
-                }
-            }
+            st_fold_columns<A2P>(taddr, chunk, s_w, s_b, acc);
             // the accumulator has been read: hand the TMEM buffer back to the MMA warp
             tc_fence_before();
             __syncwarp();
@@ -269,6 +328,153 @@ span_head_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// ---- the same, by CTA pairs (cta_group::2, Cin >= 256: chunk = 256) ---------------------------------------------------
+// Work unit = (pair of row tiles 2 u', 2 u' + 1, chunk of 256 output channels); cluster c of the persistent grid walks
+// units c, c + clusters, ...  CTA r of the pair owns row tile 2 u' + r (A rows, accumulator rows, epilogue) and stages
+// output channels [co0 + 128 r, +128) of the weight tile.  Barriers: full[s] lives in the leader (both CTAs' TMA bytes
+// are expected there), empty[s] and acc_full[b] are signalled in both CTAs by the leader's multicast commits,
+// acc_empty[b] lives in the leader and counts the epilogue warps of both CTAs.  Every wait is bounded (trap, no hang).
+constexpr int ST_PAIR_HALF = ST_MAX_CHUNK / 2;       // weight rows per CTA
+constexpr int ST_PAIR_STAGE = ST_BM * 128 + ST_PAIR_HALF * 128;
+
+template <int A2P>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ST_THREADS, 1)
+span_head_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                     int64_t tiles, int cin, int chunks, int kslabs, int stages,
+                     const float* __restrict__ conv_b, const float* __restrict__ w2t,
+                     float* __restrict__ partial, int dbg) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr int stage_a = ST_BM * 128;
+    constexpr int stage_bytes = ST_PAIR_STAGE;
+    constexpr int chunk = ST_MAX_CHUNK;
+    uint64_t* const full = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
+    uint64_t* const empty = full + stages;
+    uint64_t* const acc_full = empty + stages;          // [2]
+    uint64_t* const acc_empty = acc_full + 2;           // [2]
+    uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    float* const s_w = reinterpret_cast<float*>(tmem_slot + 4);
+    float* const s_b = s_w + (size_t)chunk * A2P;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();            // 0 = leader
+    const int64_t cluster = blockIdx.x >> 1, clusters = gridDim.x >> 1;
+    const int64_t units = (tiles >> 1) * chunks;
+    const int nkb = 3 * kslabs;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_x);
+        tma_prefetch_desc(&map_w);
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(&full[s], 1);                     // the leader's producer (expect_tx of both CTAs' bytes)
+            mbar_init(&empty[s], 1);                    // the leader's multicast commit
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_empty[b], 8);                // four epilogue warps of each CTA (used in the leader only)
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc_pair(tmem_slot, 2 * chunk);
+        tmem_relinquish_pair();
+    }
+    __syncwarp();
+    tc_fence_before();
+    cluster_sync_all();                                 // both CTAs' barriers are initialised before anyone signals them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            bool first_lap = true;
+            const uint32_t full0 = mapa_rank(smem_u32(&full[0]), 0);             // the leader's full[] barriers
+            for (int64_t u = cluster; u < units; u += clusters) {
+                const int64_t tp = u / chunks;
+                const int co0 = (int)(u - tp * chunks) * chunk + (int)rank * ST_PAIR_HALF;
+                const int64_t tile = 2 * tp + rank;
+                for (int tap = 0; tap < 3; ++tap) {
+                    for (int ci0 = 0; ci0 < kslabs * ST_SLAB; ci0 += ST_SLAB) {
+                        if (!first_lap) mbar_wait_bounded(&empty[s], ph ^ 1u);
+                        uint8_t* a = smem + (size_t)s * stage_bytes;
+                        if ((dbg & 1) && !first_lap) {                           // limiter experiment: no loads
+                            if (rank == 0) mbar_arrive(&full[s]);
+                        } else {
+                            if (rank == 0) mbar_expect_tx(&full[s], 2u * (uint32_t)stage_bytes);
+                            const uint32_t bar = full0 + 8u * (uint32_t)s;
+                            tma_load_2d_pair(a, &map_x, ci0, (int)(tile * ST_BM + tap), bar);
+                            tma_load_3d_pair(a + stage_a, &map_w, ci0, co0, tap, bar);
+                        }
+                        if (++s == stages) { s = 0; ph ^= 1u; first_lap = false; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            const uint32_t idesc = umma_idesc(UMMA_FMT_BF16, 2 * ST_BM, (uint32_t)chunk, 0, 0);
+            int64_t ul = 0;
+            int s = 0;
+            uint32_t ph = 0;
+            for (int64_t u = cluster; u < units; u += clusters, ++ul) {
+                const int b = (int)(ul & 1);
+                const int64_t buse = ul >> 1;
+                if (buse > 0) mbar_wait_bounded(&acc_empty[b], (uint32_t)((buse - 1) & 1));
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(b * chunk);
+                for (int i = 0; i < nkb; ++i) {
+                    mbar_wait_bounded(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint64_t adesc = umma_smem_desc(a_addr, 16, 1024);
+                    const uint64_t bdesc = umma_smem_desc(a_addr + stage_a, 16, 1024);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        if (!(dbg & 2) || i == 0)
+                            umma_f16_pair(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (i | kk) != 0);
+                    umma_commit_pair(&empty[s]);        // the stage is free in both CTAs
+                    if (++s == stages) { s = 0; ph ^= 1u; }
+                }
+                umma_commit_pair(&acc_full[b]);         // both CTAs' halves of the accumulator are complete
+            }
+        }
+    } else {
+        const int quad = warp & 3;
+        const uint32_t acc_empty_leader = mapa_rank(smem_u32(&acc_empty[0]), 0);
+        int64_t ul = 0;
+        for (int64_t u = cluster; u < units; u += clusters, ++ul) {
+            const int b = (int)(ul & 1);
+            const int64_t tp = u / chunks;
+            const int cidx = (int)(u - tp * chunks);
+            const int co0 = cidx * chunk;
+            const int64_t tile = 2 * tp + rank;
+            st_stage_slice<A2P>(s_w, s_b, chunk, co0, cin, conv_b, w2t);
+            mbar_wait_bounded(&acc_full[b], (uint32_t)((ul >> 1) & 1));
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * chunk);
+            float acc[A2P];
+            st_fold_columns<A2P>(taddr, chunk, s_w, s_b, acc);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc_empty_leader + (uint32_t)b * 8u);
+            const int64_t row = tile * ST_BM + quad * 32 + lane;
+            float4* dst = reinterpret_cast<float4*>(partial + ((int64_t)cidx * tiles * ST_BM + row) * A2P);
+#pragma unroll
+            for (int q = 0; q < A2P / 4; ++q)
+                dst[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+        }
+    }
+    // neither CTA leaves (or frees its TMEM) while the other may still read its shared memory or signal its barriers
+    __syncwarp();
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, 2 * chunk);
     }
 }
 
@@ -318,10 +524,11 @@ int span_head_tensor(const float* d_x, const int64_t* d_rows, int64_t row_base, 
 
     const int kslabs = (cin + ST_SLAB - 1) / ST_SLAB;
     const int stage_bytes = ST_BM * 128 + L.chunk * 128;
-    int stages = ST_SMEM_BUDGET / stage_bytes;
+    int stages = (int)((ST_SMEM_BUDGET - st_epi_bytes(L.chunk, L.a2p)) / stage_bytes);
     if (stages > 6) stages = 6;
     if (stages < 2) stages = 2;
-    const size_t smem_bytes = (size_t)stages * stage_bytes + (2 * stages + 4) * sizeof(uint64_t) + 16;
+    const size_t smem_bytes = (size_t)stages * stage_bytes + (2 * stages + 4) * sizeof(uint64_t) + 16 +
+                              st_epi_bytes(L.chunk, L.a2p);
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < 2 * L.chunk) tmem_cols <<= 1;
 
@@ -342,8 +549,46 @@ int span_head_tensor(const float* d_x, const int64_t* d_rows, int64_t row_base, 
                                    CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc != TSPN_OK) return rc;
     }
-    const int64_t units = L.tiles * L.chunks;
     const int sms = num_sms();
+    static const bool one_cta = getenv("TSPN_SPAN_HEAD_ONE_CTA") != nullptr;          // A/B switch
+    static const int dbg = getenv("TSPN_SPAN_HEAD_DEBUG") ? atoi(getenv("TSPN_SPAN_HEAD_DEBUG")) : 0;   // limiter experiments
+    if (L.chunk == ST_MAX_CHUNK && !one_cta) {
+        // CTA pairs: half of the weight tile per CTA
+        CUtensorMap map_wh;
+        const uint64_t dims[3] = {(uint64_t)cin, (uint64_t)cin, 3};
+        const uint64_t strides[2] = {(uint64_t)cin * 2, (uint64_t)cin * cin * 2};
+        const uint32_t box[3] = {(uint32_t)ST_SLAB, (uint32_t)ST_PAIR_HALF, 1};
+        int rc = encode_tensor_map(&map_wh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, wb, dims, strides, box,
+                                   CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc != TSPN_OK) return rc;
+        int pstages = (int)((ST_SMEM_BUDGET - st_epi_bytes(ST_MAX_CHUNK, L.a2p)) / ST_PAIR_STAGE);
+        if (pstages > 6) pstages = 6;
+        const size_t psmem = (size_t)pstages * ST_PAIR_STAGE + (2 * pstages + 4) * sizeof(uint64_t) + 16 +
+                             st_epi_bytes(ST_MAX_CHUNK, L.a2p);
+        const int64_t punits = (L.tiles / 2) * L.chunks;
+        const int64_t clusters = punits < sms / 2 ? punits : sms / 2;
+#define TSPN_LAUNCH_ST2(A2P)                                                                                      \
+    do {                                                                                                          \
+        TSPN_CUDA_OK(cudaFuncSetAttribute(span_head_tc2_kernel<A2P>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          (int)psmem));                                                           \
+        span_head_tc2_kernel<A2P><<<(unsigned)(2 * clusters), ST_THREADS, psmem, st>>>(                           \
+            map_x, map_wh, L.tiles, cin, L.chunks, kslabs, pstages, d_conv_b, w2t, partial, dbg);                 \
+    } while (0)
+        switch (L.a2p) {
+            case 4: TSPN_LAUNCH_ST2(4); break;
+            case 8: TSPN_LAUNCH_ST2(8); break;
+            case 12: TSPN_LAUNCH_ST2(12); break;
+            default: TSPN_LAUNCH_ST2(16); break;
+        }
+#undef TSPN_LAUNCH_ST2
+        TSPN_CUDA_OK(cudaGetLastError());
+        dim3 fgrid2((unsigned)((t + 255) / 256), (unsigned)k);
+        span_finish_kernel<<<fgrid2, 256, 0, st>>>(partial, L.chunks, L.tiles * ST_BM, L.a2p, a2, t, d_rows, d_pred_b,
+                                                   d_out);
+        TSPN_CUDA_OK(cudaGetLastError());
+        return TSPN_OK;
+    }
+    const int64_t units = L.tiles * L.chunks;
     const unsigned grid = (unsigned)(units < sms ? units : sms);
 #define TSPN_LAUNCH_ST(A2P)                                                                                       \
     do {                                                                                                          \
@@ -351,7 +596,7 @@ int span_head_tensor(const float* d_x, const int64_t* d_rows, int64_t row_base, 
                                           (int)smem_bytes));                                                      \
         span_head_tc_kernel<A2P><<<grid, ST_THREADS, smem_bytes, st>>>(map_x, map_w, L.tiles, cin, L.chunk,       \
                                                                        L.chunks, kslabs, stages, tmem_cols,       \
-                                                                       d_conv_b, w2t, partial);                   \
+                                                                       d_conv_b, w2t, partial, dbg);              \
     } while (0)
     switch (L.a2p) {
         case 4: TSPN_LAUNCH_ST(4); break;
