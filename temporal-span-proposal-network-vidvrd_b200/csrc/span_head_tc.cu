@@ -26,13 +26,20 @@
 //     span_finish_kernel (deterministic), which also adds b2 and writes the [k][2A][T] layout.
 // Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue.
 //
-// Cin >= 256 runs the CTA-PAIR form (span_head_tc2_kernel, cta_group::2): the one-CTA form re-reads (128 + 256) x 64
-// bf16 from L2 per 128 x 256 x 64 MMA block and sits on the L2 -> SM limit (ncu, [256, 1024, 300]: 5.7 GB over the
-// crossbar in 0.49 ms = 5900 B per clock, the chip's measured LTS ceiling, with the tensor pipe 51 % busy).  A pair of
-// CTAs on the two SMs of a TPC shares one M = 256 x N = 256 MMA: each CTA stages its own 128 rows of A and only HALF of
-// the weight tile (128 of the 256 output channels), the tensor cores of both SMs read both halves - (128 + 128) x 64
-// per CTA for the same math, 2/3 of the L2 traffic.  The leader CTA issues the MMAs; both CTAs load (signalling the
-// leader's mbarrier), both run the epilogue on their own 128 accumulator rows.
+// What bounded the first version of this kernel (profiles/r2_contraction_kernels.md, limiter experiments with the loads,
+// the MMAs and the epilogue switched off one at a time): not L2 and not the tensor pipe (51 % busy) but two serial
+// chains in one-thread roles - 256 global-load -> use round trips per unit in the epilogue (three `__ldg` per column
+// behind a `co < cin` branch; now one staged slice per unit and LDS broadcasts), and two 64-bit divisions by the
+// run-time stage count per K block in the producer and MMA threads (~800 cycles against the 512 cycles of MMA a block
+// feeds; now incremental stage / phase counters).  [256, 1024, 300]: main kernel 0.494 -> 0.31 ms.
+//
+// CTA-PAIR form (span_head_tc2_kernel, cta_group::2, Cin >= 256, opt-in: TSPN_SPAN_HEAD_PAIR=1): a pair of CTAs on the
+// two SMs of a TPC shares one M = 256 x N = 256 MMA: each CTA stages its own 128 rows of A and only HALF of the weight
+// tile (128 of the 256 output channels), the tensor cores of both SMs read both halves - (128 + 128) x 64 per CTA for
+// the same math, 2/3 of the L2 -> SM traffic.  The leader CTA issues the MMAs; both CTAs load (signalling the leader's
+// mbarrier), both run the epilogue on their own 128 accumulator rows.  Same results bit for bit; measured 3-7 % SLOWER
+// than the one-CTA form at both benchmark shapes once the serial chains were gone (the one-CTA main kernel then runs
+// at the rate of the measured cuBLAS bf16 burst), so it stays the opt-in.
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
@@ -204,7 +211,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1)
 span_head_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                     int64_t tiles, int cin, int chunk, int chunks, int kslabs, int stages, uint32_t tmem_cols,
                     const float* __restrict__ conv_b, const float* __restrict__ w2t,
-                    float* __restrict__ partial, int dbg) {
+                    float* __restrict__ partial) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int stage_a = ST_BM * 128;
     const int stage_bytes = stage_a + chunk * 128;
@@ -257,14 +264,10 @@ span_head_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                     for (int ci0 = 0; ci0 < kslabs * ST_SLAB; ci0 += ST_SLAB) {
                         if (!first_lap) mbar_wait(&empty[s], ph ^ 1u);
                         uint8_t* a = smem + (size_t)s * stage_bytes;
-                        if ((dbg & 1) && !first_lap) {                   // limiter experiment: no loads
-                            mbar_arrive(&full[s]);
-                        } else {
-                            mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
-                            // output row r reads xt rows (1 + r) + tap - 1 = r + tap
-                            tma_load_2d(a, &map_x, ci0, (int)(tile * ST_BM + tap), &full[s]);
-                            tma_load_3d(a + stage_a, &map_w, ci0, co0, tap, &full[s]);
-                        }
+                        mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
+                        // output row r reads xt rows (1 + r) + tap - 1 = r + tap
+                        tma_load_2d(a, &map_x, ci0, (int)(tile * ST_BM + tap), &full[s]);
+                        tma_load_3d(a + stage_a, &map_w, ci0, co0, tap, &full[s]);
                         if (++s == stages) { s = 0; ph ^= 1u; first_lap = false; }
                     }
                 }
@@ -290,8 +293,7 @@ span_head_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                     const uint64_t bdesc = umma_smem_desc(a_addr + stage_a, 16, 1024);
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk)       // 4 x (K = 16 bf16 = 32 bytes) per 128-byte slab
-                        if (!(dbg & 2) || i == 0)        // (limiter experiment: no math after the first block)
-                            umma_f16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (i | kk) != 0);
+                        umma_f16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (i | kk) != 0);
                     umma_commit(&empty[s]);
                     if (++s == stages) { s = 0; ph ^= 1u; }
                 }
@@ -345,7 +347,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ST_THREADS, 1)
 span_head_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                      int64_t tiles, int cin, int chunks, int kslabs, int stages,
                      const float* __restrict__ conv_b, const float* __restrict__ w2t,
-                     float* __restrict__ partial, int dbg) {
+                     float* __restrict__ partial) {
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr int stage_a = ST_BM * 128;
     constexpr int stage_bytes = ST_PAIR_STAGE;
@@ -401,14 +403,10 @@ span_head_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                     for (int ci0 = 0; ci0 < kslabs * ST_SLAB; ci0 += ST_SLAB) {
                         if (!first_lap) mbar_wait_bounded(&empty[s], ph ^ 1u);
                         uint8_t* a = smem + (size_t)s * stage_bytes;
-                        if ((dbg & 1) && !first_lap) {                           // limiter experiment: no loads
-                            if (rank == 0) mbar_arrive(&full[s]);
-                        } else {
-                            if (rank == 0) mbar_expect_tx(&full[s], 2u * (uint32_t)stage_bytes);
-                            const uint32_t bar = full0 + 8u * (uint32_t)s;
-                            tma_load_2d_pair(a, &map_x, ci0, (int)(tile * ST_BM + tap), bar);
-                            tma_load_3d_pair(a + stage_a, &map_w, ci0, co0, tap, bar);
-                        }
+                        if (rank == 0) mbar_expect_tx(&full[s], 2u * (uint32_t)stage_bytes);
+                        const uint32_t bar = full0 + 8u * (uint32_t)s;
+                        tma_load_2d_pair(a, &map_x, ci0, (int)(tile * ST_BM + tap), bar);
+                        tma_load_3d_pair(a + stage_a, &map_w, ci0, co0, tap, bar);
                         if (++s == stages) { s = 0; ph ^= 1u; first_lap = false; }
                     }
                 }
@@ -434,8 +432,7 @@ span_head_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                     const uint64_t bdesc = umma_smem_desc(a_addr + stage_a, 16, 1024);
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk)
-                        if (!(dbg & 2) || i == 0)
-                            umma_f16_pair(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (i | kk) != 0);
+                        umma_f16_pair(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (i | kk) != 0);
                     umma_commit_pair(&empty[s]);        // the stage is free in both CTAs
                     if (++s == stages) { s = 0; ph ^= 1u; }
                 }
@@ -550,9 +547,8 @@ int span_head_tensor(const float* d_x, const int64_t* d_rows, int64_t row_base, 
         if (rc != TSPN_OK) return rc;
     }
     const int sms = num_sms();
-    static const bool one_cta = getenv("TSPN_SPAN_HEAD_ONE_CTA") != nullptr;          // A/B switch
-    static const int dbg = getenv("TSPN_SPAN_HEAD_DEBUG") ? atoi(getenv("TSPN_SPAN_HEAD_DEBUG")) : 0;   // limiter experiments
-    if (L.chunk == ST_MAX_CHUNK && !one_cta) {
+    const char* pair_env = getenv("TSPN_SPAN_HEAD_PAIR");                  // opt-in (read per call: tests run both forms)
+    if (L.chunk == ST_MAX_CHUNK && pair_env && pair_env[0] == '1') {
         // CTA pairs: half of the weight tile per CTA
         CUtensorMap map_wh;
         const uint64_t dims[3] = {(uint64_t)cin, (uint64_t)cin, 3};
@@ -572,7 +568,7 @@ int span_head_tensor(const float* d_x, const int64_t* d_rows, int64_t row_base, 
         TSPN_CUDA_OK(cudaFuncSetAttribute(span_head_tc2_kernel<A2P>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                           (int)psmem));                                                           \
         span_head_tc2_kernel<A2P><<<(unsigned)(2 * clusters), ST_THREADS, psmem, st>>>(                           \
-            map_x, map_wh, L.tiles, cin, L.chunks, kslabs, pstages, d_conv_b, w2t, partial, dbg);                 \
+            map_x, map_wh, L.tiles, cin, L.chunks, kslabs, pstages, d_conv_b, w2t, partial);                      \
     } while (0)
         switch (L.a2p) {
             case 4: TSPN_LAUNCH_ST2(4); break;
@@ -596,7 +592,7 @@ int span_head_tensor(const float* d_x, const int64_t* d_rows, int64_t row_base, 
                                           (int)smem_bytes));                                                      \
         span_head_tc_kernel<A2P><<<grid, ST_THREADS, smem_bytes, st>>>(map_x, map_w, L.tiles, cin, L.chunk,       \
                                                                        L.chunks, kslabs, stages, tmem_cols,       \
-                                                                       d_conv_b, w2t, partial, dbg);              \
+                                                                       d_conv_b, w2t, partial);                   \
     } while (0)
     switch (L.a2p) {
         case 4: TSPN_LAUNCH_ST(4); break;

@@ -44,10 +44,12 @@ def test_predicate_head_tensor(m, c, r, seed, dtype):
 
 @pytest.mark.parametrize("cin,k,t,a", [(64, 3, 50, 4), (128, 5, 300, 4), (320, 2, 131, 4), (1024, 4, 300, 4),
                                        (72, 3, 9, 2), (256, 2, 1, 4), (512, 7, 257, 8)])
-def test_span_head_tensor(cin, k, t, a):
+def test_span_head_tensor(cin, k, t, a, monkeypatch):
     """DPNHead (dpn.py:55-73) as a tcgen05 implicit GEMM: bf16 operands, fp32 accumulation.  Channel
     counts cover one chunk, several chunks, a ragged last chunk (320 = 256 + 64) and a ragged K slab
-    (72); row tiles straddle pairs for every T here."""
+    (72); row tiles straddle pairs for every T here.  Cin >= 256 also runs the opt-in CTA-pair form
+    (cta_group::2, ``TSPN_SPAN_HEAD_PAIR=1``): the same bits as the one-CTA form."""
+    monkeypatch.delenv("TSPN_SPAN_HEAD_PAIR", raising=False)
     sd = synth.make_weights(35, 132, 16, dpn_in=cin, n_anchors=a, seed=cin + t)
     rng = np.random.Generator(np.random.PCG64(cin * 1000 + t))
     p = "relpn.duration_proposal_network.dpn_head."
@@ -74,6 +76,11 @@ def test_span_head_tensor(cin, k, t, a):
     np.testing.assert_array_equal(sub[0], got[k - 1])
     np.testing.assert_array_equal(sub[1], 0)
     np.testing.assert_array_equal(sub[2], got[0])
+    if cin >= 256:
+        monkeypatch.setenv("TSPN_SPAN_HEAD_PAIR", "1")
+        pair = ops.span_head(xd, *args, precision="tensor").cpu().numpy()
+        np.testing.assert_array_equal(pair, got)
+        np.testing.assert_array_equal(ops.span_head(buf, *args, rows=rows, t=t, precision="tensor").cpu().numpy(), sub)
 
 
 def test_decomposed_predicate_head_pieces():

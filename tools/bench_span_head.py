@@ -2,7 +2,9 @@
 
     python tools/bench_span_head.py [K] [Cin] [T]
 
-Prints per-kernel CUDA-event times and the achieved bf16 TFLOP/s against MEASURED_PEAKS.json.
+Prints the CUDA-event time of the whole call (weight + input pre-passes, the implicit-GEMM kernel, the finish pass) and
+the achieved bf16 TFLOP/s against MEASURED_PEAKS.json, for the one-CTA form (default) and the opt-in CTA-pair form
+(``TSPN_SPAN_HEAD_PAIR=1``).
 """
 import json
 import os
@@ -25,7 +27,9 @@ args = [torch.from_numpy(sd[p + n]).cuda() for n in ("conv.weight", "conv.bias",
                                                      "duration_pred.bias")]
 x = torch.randn((k, cin, t), device="cuda")
 flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device="cuda")
-for prec in ("tensor",):
+for form in ("one_cta", "cta_pair"):
+    prec = "tensor"
+    os.environ["TSPN_SPAN_HEAD_PAIR"] = "1" if form == "cta_pair" else "0"
     for _ in range(3):
         ops.span_head(x, *args, precision=prec)
     times = []
@@ -40,8 +44,10 @@ for prec in ("tensor",):
     ms = float(np.median(times))
     flop = 2.0 * k * t * (3 * cin * cin + 2 * a * cin)
     try:
-        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak, sustained = pk["bf16_tflops"], pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
     except Exception:  # noqa: BLE001
-        peak = 1590.0
-    print(json.dumps({"op": "span_head", "precision": prec, "k": k, "cin": cin, "t": t, "ms": ms,
-                      "tflops": flop / ms / 1e9, "peak_tflops": peak, "frac": flop / ms / 1e9 / peak}))
+        peak = sustained = 1590.0
+    print(json.dumps({"op": "span_head", "precision": prec, "form": form, "k": k, "cin": cin, "t": t, "ms": ms,
+                      "tflops": flop / ms / 1e9, "peak_tflops": peak, "frac": flop / ms / 1e9 / peak,
+                      "frac_of_sustained": flop / ms / 1e9 / sustained}))
