@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define TSPN_ABI_VERSION 5
+#define TSPN_ABI_VERSION 6
 
 /* error codes */
 #define TSPN_OK 0
@@ -238,6 +238,14 @@ int tspn_unpack_boxes_u16(const uint16_t* d_src, int64_t n_boxes, float* d_dst, 
 #define TSPN_PACKED_DELTA (1ll << 62)
 int tspn_unpack_boxes_spans(const int64_t* d_table, int num_videos, int64_t total_tracklets, const int32_t* d_span,
                             const int64_t* d_packed_off, const uint16_t* d_packed, float* d_dst, void* stream);
+/* HOST side of that transport (plain CPU code, no device access; serving.host_batches_for packs pinned batches
+ * with it).  tspn_host_pack_boxes_spans: one video's boxes [n][t][4] fp32
+ * (host) -> slots from slot0 on in dst (the arena's u16 box field, dst_slots slots of 8 bytes in all), tracklet after
+ * tracklet, frames [pstart, pend) only, raw or - allow_delta and every frame-to-frame difference in [-128, 127] - delta
+ * coded; writes box_off[n] (host, with TSPN_PACKED_DELTA) and *slots_used.  A coordinate inside a span that is not an
+ * integer in [0, 65535], a span outside [0, t] or more slots than the arena holds -> TSPN_ESHAPE. */
+int tspn_host_pack_boxes_spans(const float* boxes, int n_tracklets, int n_frames, const int32_t* span, int allow_delta,
+                               uint16_t* dst, int64_t dst_slots, int64_t slot0, int64_t* box_off, int64_t* slots_used);
 /* Build rows [2C | 8000 motion | 3000 relative] (lib/dataset/vrdataset.py:219-243); the last
  * 3000 columns are the adaptive-average-pooled geometry ([SPEC] s4).  d_rows: global pair rows
  * to build (int64, NULL = all total_pairs rows in order).  Output row stride ld_feat floats

@@ -21,7 +21,7 @@ TOT_COLS = 10
 (TOT_TRACKLETS, TOT_PAIRS, TOT_GEO_FLOATS, TOT_ITEMS, TOT_BOXES, TOT_SCORES, TOT_MAX_N, TOT_MAX_T, TOT_GEO_CHUNK,
  TOT_MAX_CHUNKS) = range(10)
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 GEO_OBJ_GROUP = 32        # include/tspn_b200.h: objects per work item of the pair-geometry kernel
 GEO_CHANNELS = 8
 MOTION_DIM = 4000
@@ -64,6 +64,7 @@ SIGNATURES = {
     "tspn_normalize_motion_u8": (c_int, [P, c_int64, P, P]),
     "tspn_unpack_boxes_u16": (c_int, [P, c_int64, P, P]),
     "tspn_unpack_boxes_spans": (c_int, [P, c_int, c_int64, P, P, P, P, P]),
+    "tspn_host_pack_boxes_spans": (c_int, [P, c_int, c_int, P, c_int, P, c_int64, c_int64, P, P]),
     "tspn_assemble_features": (c_int, [P, c_int, c_int64, c_int, P, c_int, P, P, P, P, c_int64, P, c_int64, P, c_int64, P]),
     "tspn_relationness_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
     "tspn_relationness_tc_supported": (c_int, [c_int, c_int, c_int]),

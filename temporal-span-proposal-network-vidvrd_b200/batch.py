@@ -17,6 +17,7 @@ list of ragged videos into such batches.
 """
 from __future__ import annotations
 
+import ctypes
 import dataclasses
 import os
 from typing import Iterable, List, Optional, Sequence, Tuple
@@ -247,38 +248,20 @@ class HostBatch:
         """Span-packed transport of one video's boxes into the u16 arena, from 8-byte slot ``slot0`` on; returns the
         slots used.  Tracklet-major; per tracklet either RAW (a slot of 4 x u16 per frame) or, when every coordinate
         moves by at most [-128, 127] pixels per frame, DELTA (the first frame's slot, then 4 x i8 per further frame,
-        two frames per slot; ``_lib.PACKED_DELTA`` set in its ``box_off``) - see ``tspn_unpack_boxes_spans``."""
-        n, t = b.shape[0], b.shape[1]
-        frame = np.arange(t, dtype=np.int32)[None, :]
-        alive = (frame >= s[:, :1]) & (frame < s[:, 1:2])                  # [N, T]
-        lens = (s[:, 1] - s[:, 0]).astype(np.int64)
-        cnt = int(lens.sum())
-        flat = b[alive].astype(np.int32)                                   # [cnt, 4], tracklet-major
-        first = np.concatenate([[0], np.cumsum(lens)[:-1]])                # row of every tracklet's first frame
-        trk_of = np.repeat(np.arange(n), lens)
-        f_in = np.arange(cnt, dtype=np.int64) - first[trk_of]              # frame index inside its tracklet's span
-        d = np.zeros_like(flat)
-        if cnt > 1:
-            d[1:] = flat[1:] - flat[:-1]
-        d[f_in == 0] = 0
-        is_delta = np.zeros(n, dtype=bool)
-        if delta and cnt:
-            bad = ((d < -128) | (d > 127)).any(axis=1)
-            is_delta = (np.bincount(trk_of, weights=bad, minlength=n) == 0) & (lens > 0)
-        slots = np.where(is_delta, 1 + lens // 2, lens)                    # 1 + ceil((L - 1) / 2) = 1 + L // 2
-        off = slot0 + np.concatenate([[0], np.cumsum(slots)[:-1]])
-        self.box_off.numpy()[trk0:trk0 + n] = off | np.where(is_delta, np.int64(_lib.PACKED_DELTA), np.int64(0))
-        used = int(slots.sum())
-        row_delta = is_delta[trk_of]
-        raw = ~row_delta
-        bview[(off[trk_of] + f_in)[raw]] = flat[raw]
-        head = row_delta & (f_in == 0)
-        bview[off[trk_of][head]] = flat[head]
-        tail = row_delta & (f_in > 0)
-        if tail.any():
-            i8 = bview[slot0:slot0 + used].view(np.int8).reshape(-1, 4)    # 4-byte records, two per slot
-            i8[((off[trk_of] - slot0 + 1) * 2 + f_in - 1)[tail]] = d[tail].astype(np.int8)
-        return used
+        two frames per slot; ``_lib.PACKED_DELTA`` set in its ``box_off``) - see ``tspn_unpack_boxes_spans``.  The
+        loops run in the library (``tspn_host_pack_boxes_spans``, csrc/host_pack.cu: CPU code): the numpy form of this
+        method took 11 ms per VidOR video - 250 GPU steps per packed batch (kept as the reference in
+        tests/test_cpu_ragged.py)."""
+        n = int(b.shape[0])
+        b = np.ascontiguousarray(b, dtype=np.float32)
+        s = np.ascontiguousarray(s, dtype=np.int32)
+        off = self.box_off.numpy()
+        used = ctypes.c_int64(0)
+        _lib.check(_lib.load().tspn_host_pack_boxes_spans(
+            b.ctypes.data, n, int(b.shape[1]), s.ctypes.data, int(bool(delta)), bview.ctypes.data,
+            int(bview.shape[0]), int(slot0), off[trk0:].ctypes.data, ctypes.addressof(used)),
+            "tspn_host_pack_boxes_spans")
+        return int(used.value)
 
     def unpacked_boxes(self) -> List[np.ndarray]:
         """Host-side decode of the box transport (what ``tspn_unpack_boxes_spans`` does on the device): the dense

@@ -33,7 +33,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert re.search(r"\bT %s\b" % name, exported), name
         getattr(lib, name)
-    assert lib.tspn_version() == _lib.ABI_VERSION == 5
+    assert lib.tspn_version() == _lib.ABI_VERSION == 6
 
 
 def test_sass_is_blackwell_native():

@@ -159,3 +159,92 @@ def test_box_transport_with_a_capacity_and_fractional_boxes():
     host = HostBatch.from_videos([frac], pin=False)
     assert not host.boxes_compact
     np.testing.assert_array_equal(host.unpacked_boxes()[0], frac.boxes)
+
+
+def _pack_span_boxes_numpy(b, s, trk0, slot0, bview, box_off, delta):
+    """The numpy form of ``HostBatch._pack_span_boxes`` (the first implementation; the product runs the same loops in the
+    library, ``tspn_host_pack_boxes_spans``): the reference the native packer is compared with, byte for byte."""
+    from tspn_b200 import _lib
+    n, t = b.shape[0], b.shape[1]
+    frame = np.arange(t, dtype=np.int32)[None, :]
+    alive = (frame >= s[:, :1]) & (frame < s[:, 1:2])                  # [N, T]
+    lens = (s[:, 1] - s[:, 0]).astype(np.int64)
+    cnt = int(lens.sum())
+    flat = b[alive].astype(np.int32)                                   # [cnt, 4], tracklet-major
+    first = np.concatenate([[0], np.cumsum(lens)[:-1]])                # row of every tracklet's first frame
+    trk_of = np.repeat(np.arange(n), lens)
+    f_in = np.arange(cnt, dtype=np.int64) - first[trk_of]              # frame index inside its tracklet's span
+    d = np.zeros_like(flat)
+    if cnt > 1:
+        d[1:] = flat[1:] - flat[:-1]
+    d[f_in == 0] = 0
+    is_delta = np.zeros(n, dtype=bool)
+    if delta and cnt:
+        bad = ((d < -128) | (d > 127)).any(axis=1)
+        is_delta = (np.bincount(trk_of, weights=bad, minlength=n) == 0) & (lens > 0)
+    slots = np.where(is_delta, 1 + lens // 2, lens)                    # 1 + ceil((L - 1) / 2) = 1 + L // 2
+    off = slot0 + np.concatenate([[0], np.cumsum(slots)[:-1]])
+    box_off[trk0:trk0 + n] = off | np.where(is_delta, np.int64(_lib.PACKED_DELTA), np.int64(0))
+    used = int(slots.sum())
+    row_delta = is_delta[trk_of]
+    raw = ~row_delta
+    bview[(off[trk_of] + f_in)[raw]] = flat[raw]
+    head = row_delta & (f_in == 0)
+    bview[off[trk_of][head]] = flat[head]
+    tail = row_delta & (f_in > 0)
+    if tail.any():
+        i8 = bview[slot0:slot0 + used].view(np.int8).reshape(-1, 4)    # 4-byte records, two per slot
+        i8[((off[trk_of] - slot0 + 1) * 2 + f_in - 1)[tail]] = d[tail].astype(np.int8)
+    return used
+
+
+@pytest.mark.parametrize("delta", [True, False])
+def test_native_packer_equals_the_numpy_reference(delta):
+    from tspn_b200 import synth
+    rng = np.random.default_rng(7)
+    vids = [synth.make_video(12, 300, 35, seed=1), _edge_video(), synth.make_video(3, 5, 35, seed=2),
+            synth.make_video(20, 1200, 35, seed=9)]
+    vids[3].boxes[5, 400:, :] += 200.0                       # one raw tracklet between delta tracklets
+    jump = rng.integers(-140, 141, size=(1200, 4)).cumsum(axis=0) + 30000     # steps around the int8 limits
+    vids[3].boxes[7] = np.where((np.arange(1200)[:, None] >= vids[3].span[7, 0]) &
+                                (np.arange(1200)[:, None] < vids[3].span[7, 1]), jump, 0).astype(np.float32)
+    tt = np.arange(1200)[None, :, None]
+    vids[3].boxes[:] = np.where((tt >= vids[3].span[:, :1, None]) & (tt < vids[3].span[:, 1:, None]), vids[3].boxes, 0.0)
+    host = HostBatch.from_videos(vids, pin=False, delta=delta)
+    got = host.boxes.numpy().view(np.uint16)
+    want = np.zeros_like(got)
+    want_off = np.zeros_like(host.box_off.numpy())
+    slot, trk = 0, 0
+    for v in vids:
+        slot += _pack_span_boxes_numpy(v.boxes, v.span, trk, slot, want, want_off, delta)
+        trk += v.n_tracklets
+    assert host.packed_boxes == slot
+    np.testing.assert_array_equal(host.box_off.numpy(), want_off)
+    np.testing.assert_array_equal(got, want)
+    for v, dense in zip(vids, host.unpacked_boxes()):
+        np.testing.assert_array_equal(dense, v.boxes)
+
+
+def test_native_packer_rejects_what_it_cannot_ship():
+    import ctypes
+    from tspn_b200 import _lib
+    lib = _lib.load()
+    boxes = np.zeros((2, 6, 4), dtype=np.float32)
+    boxes[:, :, 2:] = 10.0
+    span = np.array([[0, 6], [2, 5]], dtype=np.int32)
+    dst = np.zeros((9, 4), dtype=np.uint16)
+    off = np.zeros(2, dtype=np.int64)
+    used = ctypes.c_int64(-1)
+
+    def pack(b, s, slots=9, slot0=0):
+        return lib.tspn_host_pack_boxes_spans(b.ctypes.data, 2, 6, s.ctypes.data, 0, dst.ctypes.data, slots, slot0,
+                                              off.ctypes.data, ctypes.addressof(used))
+    assert pack(boxes, span) == _lib.TSPN_OK and used.value == 9 and off.tolist() == [0, 6]
+    assert pack(boxes, span, slots=8) == _lib.TSPN_ESHAPE and "exceed the arena" in _lib.last_error()
+    bad = boxes.copy()
+    bad[1, 3, 0] = 0.5                                       # inside tracklet 1's span
+    assert pack(bad, span) == _lib.TSPN_ESHAPE and "fractional" in _lib.last_error()
+    bad[1, 3, 0] = 0.0
+    bad[1, 0, 0] = 0.5                                       # outside its span: never read, never shipped
+    assert pack(bad, span) == _lib.TSPN_OK
+    assert pack(boxes, np.array([[0, 7], [2, 5]], dtype=np.int32)) == _lib.TSPN_ESHAPE
