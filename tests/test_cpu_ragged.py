@@ -248,3 +248,28 @@ def test_native_packer_rejects_what_it_cannot_ship():
     bad[1, 0, 0] = 0.5                                       # outside its span: never read, never shipped
     assert pack(bad, span) == _lib.TSPN_OK
     assert pack(boxes, np.array([[0, 7], [2, 5]], dtype=np.int32)) == _lib.TSPN_ESHAPE
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_native_packer_on_random_tracklets(seed):
+    """Random spans (empty, one frame, whole video), random walks whose steps straddle the int8 limits, coordinates at
+    both ends of the u16 range: native packer = numpy reference byte for byte, and the host decode returns the boxes."""
+    rng = np.random.default_rng(100 + seed)
+    n, t = int(rng.integers(1, 9)), int(rng.integers(1, 70))
+    span = np.sort(rng.integers(0, t + 1, size=(n, 2)), axis=1).astype(np.int32)
+    span[rng.integers(0, n)] = (0, t)
+    step_hi = int(rng.choice([3, 127, 128, 129, 400]))
+    walk = rng.integers(-step_hi, step_hi + 1, size=(n, t, 4)).cumsum(axis=1)
+    boxes = np.clip(walk + rng.choice([0, 300, 65535 - 300]), 0, 65535).astype(np.float32)
+    tt = np.arange(t)[None, :, None]
+    boxes = np.where((tt >= span[:, :1, None]) & (tt < span[:, 1:, None]), boxes, 0.0).astype(np.float32)
+    for delta in (True, False):
+        host = HostBatch([boxes], [span], pin=False, delta=delta)
+        assert host.boxes_compact
+        got = host.boxes.numpy().view(np.uint16)
+        want, want_off = np.zeros_like(got), np.zeros_like(host.box_off.numpy())
+        used = _pack_span_boxes_numpy(boxes, span, 0, 0, want, want_off, delta)
+        assert host.packed_boxes == used
+        np.testing.assert_array_equal(host.box_off.numpy(), want_off)
+        np.testing.assert_array_equal(got[:used], want[:used])
+        np.testing.assert_array_equal(host.unpacked_boxes()[0], boxes)
