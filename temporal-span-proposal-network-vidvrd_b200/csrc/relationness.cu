@@ -77,15 +77,32 @@ ppn_embed_tiled_kernel(const float* __restrict__ cls, int64_t n_trk, int C, int 
     const int tid = threadIdx.x;
     const int64_t trk0 = (int64_t)blockIdx.x * EMB_G;
     const int g_cnt = (int)min((int64_t)EMB_G, n_trk - trk0);
-    for (int e = tid; e < 2 * C * H; e += EMB_THREADS) {
-        const int br = e / (C * H), rem = e - br * C * H;
-        {   // W0_br is [H][C] row-major: element rem = j*C + i
-            const int j = rem / C, i = rem - j * C;
-            w0t[br * C * HP + i * HP + j] = __ldg((br ? ow0 : sw0) + rem);
+    // Staging walks the matrices with (row, column) advanced incrementally: the flat-index form of this loop spent three
+    // integer divisions per element - ~80 instructions for every word staged, ten times the fma chains below - in the
+    // kernel that heads the side chain.  Both branches' words of an iteration are in flight together.
+    const int CH = C * H;
+    {   // W0_br is [H][C] row-major: element rem = j * C + i  ->  w0t[br][i][j]
+        const int dj = EMB_THREADS / C, di = EMB_THREADS - dj * C;
+        int j = tid / C, i = tid - j * C;
+        for (int rem = tid; rem < CH; rem += EMB_THREADS) {
+            const float ws = __ldg(sw0 + rem), wo = __ldg(ow0 + rem);
+            w0t[i * HP + j] = ws;
+            w0t[C * HP + i * HP + j] = wo;
+            j += dj;
+            i += di;
+            if (i >= C) { i -= C; ++j; }
         }
-        {   // W2_br is [C][H] row-major: element rem = c*H + j
-            const int c = rem / H, j = rem - c * H;
-            w2t[br * H * CP + j * CP + c] = __ldg((br ? ow2 : sw2) + rem);
+    }
+    {   // W2_br is [C][H] row-major: element rem = c * H + j  ->  w2t[br][j][c]
+        const int dc = EMB_THREADS / H, dj = EMB_THREADS - dc * H;
+        int c = tid / H, j = tid - c * H;
+        for (int rem = tid; rem < CH; rem += EMB_THREADS) {
+            const float ws = __ldg(sw2 + rem), wo = __ldg(ow2 + rem);
+            w2t[j * CP + c] = ws;
+            w2t[H * CP + j * CP + c] = wo;
+            c += dc;
+            j += dj;
+            if (j >= H) { j -= H; ++c; }
         }
     }
     for (int e = tid; e < g_cnt * C; e += EMB_THREADS) x[e] = __ldg(cls + trk0 * C + e);
