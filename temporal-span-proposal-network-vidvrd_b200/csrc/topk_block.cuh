@@ -34,7 +34,9 @@ struct TopkSmem {
 // min(k, number of candidates).  Must be called by all TOPK_THREADS threads of the block.
 constexpr int TOPK_EPT = 4;        // consecutive candidates per thread in the collect pass
 
-template <typename ValueOf>
+// UNCACHED_BATCH: loads a thread keeps in flight per step of a radix pass when the candidates do not fit the key cache
+// (1 for callers whose candidates always fit: their value_of is then not replicated in the code).
+template <int UNCACHED_BATCH = 8, typename ValueOf>
 __device__ int block_topk(TopkSmem& sm, int64_t total, int k, ValueOf value_of) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // The candidates are read five times (four radix passes + the collect pass).  Up to TOPK_CACHE of them
@@ -60,8 +62,7 @@ __device__ int block_topk(TopkSmem& sm, int64_t total, int k, ValueOf value_of) 
         // run-length aggregation: neighbouring scores usually share their leading digits, which
         // would otherwise serialise the shared-memory atomics on one bin
         uint32_t run_bin = 0xffffffffu, run_cnt = 0;
-        for (int64_t i = tid; i < total; i += TOPK_THREADS) {
-            const uint32_t key = key_of(i);
+        auto count_key = [&](uint32_t key) {
             if (key != KEY_NEG_INF && (key & prefix_mask) == prefix) {
                 const uint32_t bin = (key >> shift) & 0xffu;
                 if (bin == run_bin) {
@@ -71,6 +72,23 @@ __device__ int block_topk(TopkSmem& sm, int64_t total, int k, ValueOf value_of) 
                     run_bin = bin;
                     run_cnt = 1;
                 }
+            }
+        };
+        if (cached) {
+            for (int64_t i = tid; i < total; i += TOPK_THREADS) count_key(sm.keys[i]);
+        } else {
+            // candidates in global memory: UNCACHED_BATCH independent loads in flight per thread, then the (serial)
+            // run-length bookkeeping - one load -> use round trip per candidate made a pass over one stress video's
+            // 65 536 scores 200 us under the all-pairs kernel (same candidates in the same order: same histogram)
+            for (int64_t i0 = tid; i0 < total; i0 += (int64_t)TOPK_THREADS * UNCACHED_BATCH) {
+                uint32_t kk[UNCACHED_BATCH];
+#pragma unroll
+                for (int u = 0; u < UNCACHED_BATCH; ++u) {
+                    const int64_t i = i0 + (int64_t)u * TOPK_THREADS;
+                    kk[u] = i < total ? order_key(value_of(i)) : KEY_NEG_INF;
+                }
+#pragma unroll
+                for (int u = 0; u < UNCACHED_BATCH; ++u) count_key(kk[u]);
             }
         }
         if (run_cnt) atomicAdd(&sm.hist[run_bin], run_cnt);
@@ -124,9 +142,13 @@ __device__ int block_topk(TopkSmem& sm, int64_t total, int k, ValueOf value_of) 
         uint32_t keys[TOPK_EPT];
         uint32_t n_tie = 0;
 #pragma unroll
-        for (int e = 0; e < TOPK_EPT; ++e) {
+        for (int e = 0; e < TOPK_EPT; ++e) {          // the thread's loads first, all in flight together
             const int64_t i = base + (int64_t)tid * TOPK_EPT + e;
             keys[e] = i < total ? key_of(i) : KEY_NEG_INF;
+        }
+#pragma unroll
+        for (int e = 0; e < TOPK_EPT; ++e) {
+            const int64_t i = base + (int64_t)tid * TOPK_EPT + e;
             if (keys[e] > thr) sm.sel[atomicAdd(&sm.count, 1u)] = ((uint64_t)(~keys[e]) << 32) | (uint32_t)i;
             n_tie += keys[e] == thr;                  // thr > KEY_NEG_INF, so -inf is never collected
         }
