@@ -167,9 +167,9 @@ topk_kernel(const int64_t* __restrict__ table, int nv, const float* __restrict__
     // the diagonal (flat index a multiple of n + 1) is not a candidate.  Divisibility without a division per candidate
     // (Lemire & Kaser: for 32-bit u, d:  u % d == 0  <=>  u * M <= M - 1 in 64-bit arithmetic, M = 2^64 / d rounded up)
     const uint64_t diag_m = ~0ull / (uint64_t)(n + 1u) + 1ull;
-    const int k_eff = block_topk(sm, total, K, [&](int64_t i) -> float {
-        if (exclude_diag && (uint64_t)(uint32_t)i * diag_m <= diag_m - 1ull) return NEG_INF;
-        return __ldg(sc + i);
+    const int k_eff = block_topk<32, 16>(sm, total, K, [&](int64_t i) -> float {     // big videos: few, deep round trips
+        const float val = __ldg(sc + i);                             // (load first: no branch around it)
+        return (exclude_diag && (uint64_t)(uint32_t)i * diag_m <= diag_m - 1ull) ? NEG_INF : val;
     });
 
     int64_t* oi = out_idx + (int64_t)v * K;
@@ -223,7 +223,7 @@ scores_topk_kernel(const int64_t* __restrict__ table, int nv, const float* __res
     float* const sc = scores + row[TSPN_VT_SCORE_OFF];
     const float NEG_INF = __uint_as_float(0xff800000u);
 
-    const int k_eff = block_topk<1>(sm, total, K, [&](int64_t i) -> float {       // n * n <= TOPK_CACHE: always cached
+    const int k_eff = block_topk<1, 4>(sm, total, K, [&](int64_t i) -> float {       // n * n <= TOPK_CACHE: always cached
         const uint32_t u = (uint32_t)i;
         const uint32_t s = u / n, o = u - s * n;
         const float* sr = ss + s * CP;

@@ -32,11 +32,12 @@ struct TopkSmem {
 // Candidate i in [0, total) has value value_of(i); values equal to -inf are not candidates.
 // On return sm.sel[0 .. k_eff) holds the winners sorted (low 32 bits = index); returns k_eff =
 // min(k, number of candidates).  Must be called by all TOPK_THREADS threads of the block.
-constexpr int TOPK_EPT = 4;        // consecutive candidates per thread in the collect pass
 
 // UNCACHED_BATCH: loads a thread keeps in flight per step of a radix pass when the candidates do not fit the key cache
 // (1 for callers whose candidates always fit: their value_of is then not replicated in the code).
-template <int UNCACHED_BATCH = 8, typename ValueOf>
+// TOPK_EPT: consecutive candidates per thread and step of the collect pass (each step costs a memory round trip and three
+// block barriers: kernels that run UNDER the all-pairs kernel see several microseconds per round trip).
+template <int UNCACHED_BATCH = 8, int TOPK_EPT = 4, typename ValueOf>
 __device__ int block_topk(TopkSmem& sm, int64_t total, int k, ValueOf value_of) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // The candidates are read five times (four radix passes + the collect pass).  Up to TOPK_CACHE of them
@@ -84,8 +85,11 @@ __device__ int block_topk(TopkSmem& sm, int64_t total, int k, ValueOf value_of) 
                 uint32_t kk[UNCACHED_BATCH];
 #pragma unroll
                 for (int u = 0; u < UNCACHED_BATCH; ++u) {
+                    // no branch around the load (a clamped index, a select afterwards): loads behind branches sit in
+                    // separate basic blocks, and ptxas then waits for each one before it issues the next
                     const int64_t i = i0 + (int64_t)u * TOPK_THREADS;
-                    kk[u] = i < total ? order_key(value_of(i)) : KEY_NEG_INF;
+                    const uint32_t key = order_key(value_of(i < total ? i : total - 1));
+                    kk[u] = i < total ? key : KEY_NEG_INF;
                 }
 #pragma unroll
                 for (int u = 0; u < UNCACHED_BATCH; ++u) count_key(kk[u]);
@@ -144,7 +148,8 @@ __device__ int block_topk(TopkSmem& sm, int64_t total, int k, ValueOf value_of) 
 #pragma unroll
         for (int e = 0; e < TOPK_EPT; ++e) {          // the thread's loads first, all in flight together
             const int64_t i = base + (int64_t)tid * TOPK_EPT + e;
-            keys[e] = i < total ? key_of(i) : KEY_NEG_INF;
+            const uint32_t key = key_of(i < total ? i : total - 1);
+            keys[e] = i < total ? key : KEY_NEG_INF;
         }
 #pragma unroll
         for (int e = 0; e < TOPK_EPT; ++e) {
