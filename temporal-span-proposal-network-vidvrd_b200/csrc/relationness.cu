@@ -60,6 +60,7 @@ ppn_embed_kernel(const float* __restrict__ cls, int C, int H, const float* __res
 #endif
 constexpr int EMB_G = TSPN_EMB_G;
 constexpr int EMB_THREADS = 256;
+constexpr int EMB_LD = 5;                  // staging: iterations whose loads (4 each) are in flight together
 __global__ void __launch_bounds__(EMB_THREADS)
 ppn_embed_tiled_kernel(const float* __restrict__ cls, int64_t n_trk, int C, int H, const float* __restrict__ sw0,
                        const float* __restrict__ sb0, const float* __restrict__ sw2,
@@ -74,45 +75,70 @@ ppn_embed_tiled_kernel(const float* __restrict__ cls, int64_t n_trk, int C, int 
     float* w2t = w0t + 2 * C * HP;        // [2][H][CP]  w2t[br][j][c] = W2_br[c][j]
     float* x = w2t + 2 * H * CP;          // [G][C]
     float* hid = x + EMB_G * C;           // [G][2][H]
+    float* bias = hid + EMB_G * 2 * H;    // [sb0 (H) | ob0 (H) | sb2 (C) | ob2 (C)]
     const int tid = threadIdx.x;
     const int64_t trk0 = (int64_t)blockIdx.x * EMB_G;
     const int g_cnt = (int)min((int64_t)EMB_G, n_trk - trk0);
-    // Staging walks the matrices with (row, column) advanced incrementally: the flat-index form of this loop spent three
-    // integer divisions per element - ~80 instructions for every word staged, ten times the fma chains below - in the
-    // kernel that heads the side chain.  Both branches' words of an iteration are in flight together.
+    // Staging.  Two things make this kernel's time under the all-pairs kernel (it heads the side chain): (1) index
+    // arithmetic - the flat-index form spent three integer divisions per word staged; (row, column) now advance
+    // incrementally; (2) memory round trips, several microseconds each there - every global load of the kernel is issued
+    // here, in batches of EMB_LD x 4 independent branch-free loads per thread (was: one pair of loads per loop iteration,
+    // plus one bias load at the head of every fma chain: ~50 exposed round trips per thread).
     const int CH = C * H;
-    {   // W0_br is [H][C] row-major: element rem = j * C + i  ->  w0t[br][i][j]
+    for (int e = tid; e < 2 * H + 2 * C; e += EMB_THREADS) {       // [sb0 | ob0 | sb2 | ob2]
+        const float* src = e < H ? sb0 + e : e < 2 * H ? ob0 + (e - H) : e < 2 * H + C ? sb2 + (e - 2 * H)
+                                                                                       : ob2 + (e - 2 * H - C);
+        bias[e] = __ldg(src);
+    }
+    for (int e0 = tid; e0 < g_cnt * C; e0 += EMB_THREADS * 4) {
+        float xv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) xv[u] = __ldg(cls + trk0 * C + min(e0 + u * EMB_THREADS, g_cnt * C - 1));
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (e0 + u * EMB_THREADS < g_cnt * C) x[e0 + u * EMB_THREADS] = xv[u];
+    }
+    {
+        // W0_br is [H][C] row-major: element rem = j * C + i  ->  w0t[br][i][j]
+        // W2_br is [C][H] row-major: element rem = c * H + j2 ->  w2t[br][j2][c]
         const int dj = EMB_THREADS / C, di = EMB_THREADS - dj * C;
+        const int dc = EMB_THREADS / H, dj2 = EMB_THREADS - dc * H;
         int j = tid / C, i = tid - j * C;
-        for (int rem = tid; rem < CH; rem += EMB_THREADS) {
-            const float ws = __ldg(sw0 + rem), wo = __ldg(ow0 + rem);
-            w0t[i * HP + j] = ws;
-            w0t[C * HP + i * HP + j] = wo;
-            j += dj;
-            i += di;
-            if (i >= C) { i -= C; ++j; }
+        int c = tid / H, j2 = tid - c * H;
+        for (int rem0 = tid; rem0 < CH; rem0 += EMB_THREADS * EMB_LD) {
+            float a0[EMB_LD], a1[EMB_LD], a2[EMB_LD], a3[EMB_LD];
+#pragma unroll
+            for (int u = 0; u < EMB_LD; ++u) {
+                const int rc = min(rem0 + u * EMB_THREADS, CH - 1);
+                a0[u] = __ldg(sw0 + rc);
+                a1[u] = __ldg(ow0 + rc);
+                a2[u] = __ldg(sw2 + rc);
+                a3[u] = __ldg(ow2 + rc);
+            }
+#pragma unroll
+            for (int u = 0; u < EMB_LD; ++u) {
+                if (rem0 + u * EMB_THREADS < CH) {
+                    w0t[i * HP + j] = a0[u];
+                    w0t[C * HP + i * HP + j] = a1[u];
+                    w2t[j2 * CP + c] = a2[u];
+                    w2t[H * CP + j2 * CP + c] = a3[u];
+                }
+                j += dj;
+                i += di;
+                if (i >= C) { i -= C; ++j; }
+                c += dc;
+                j2 += dj2;
+                if (j2 >= H) { j2 -= H; ++c; }
+            }
         }
     }
-    {   // W2_br is [C][H] row-major: element rem = c * H + j  ->  w2t[br][j][c]
-        const int dc = EMB_THREADS / H, dj = EMB_THREADS - dc * H;
-        int c = tid / H, j = tid - c * H;
-        for (int rem = tid; rem < CH; rem += EMB_THREADS) {
-            const float ws = __ldg(sw2 + rem), wo = __ldg(ow2 + rem);
-            w2t[j * CP + c] = ws;
-            w2t[H * CP + j * CP + c] = wo;
-            c += dc;
-            j += dj;
-            if (j >= H) { j -= H; ++c; }
-        }
-    }
-    for (int e = tid; e < g_cnt * C; e += EMB_THREADS) x[e] = __ldg(cls + trk0 * C + e);
     __syncthreads();
     for (int u = tid; u < g_cnt * 2 * H; u += EMB_THREADS) {
         const int g = u / (2 * H), j2 = u - g * 2 * H;
         const int br = j2 / H, j = j2 - br * H;
         const float* w = w0t + br * C * HP + j;
         const float* xg = x + g * C;
-        float acc = __ldg((br ? ob0 : sb0) + j);
+        float acc = bias[br * H + j];
         for (int i = 0; i < C; ++i) acc = __fmaf_rn(xg[i], w[i * HP], acc);
         hid[u] = fmaxf(acc, 0.0f);
     }
@@ -122,7 +148,7 @@ ppn_embed_tiled_kernel(const float* __restrict__ cls, int64_t n_trk, int C, int 
         const int br = c2 / C, c = c2 - br * C;
         const float* w = w2t + br * H * CP + c;
         const float* h = hid + (g * 2 + br) * H;
-        float acc = __ldg((br ? ob2 : sb2) + c);
+        float acc = bias[2 * H + br * C + c];
         for (int j = 0; j < H; ++j) acc = __fmaf_rn(h[j], w[j * CP], acc);
         (br ? O : S)[(trk0 + g) * C + c] = acc;
     }
@@ -214,10 +240,24 @@ scores_topk_kernel(const int64_t* __restrict__ table, int nv, const float* __res
     const int CP = C + 1;
     float* const ss = emb;
     float* const oo = emb + (size_t)n * CP;
-    for (int e = tid; e < (int)n * C; e += TOPK_THREADS) {
-        const int r = e / C, c = e - r * C;
-        ss[r * CP + c] = S[trk0 * C + e];
-        oo[r * CP + c] = O[trk0 * C + e];
+    const int n_emb = (int)n * C;
+    for (int e0 = tid; e0 < n_emb; e0 += TOPK_THREADS * 4) {       // eight independent loads in flight per thread
+        float a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int ec = min(e0 + u * TOPK_THREADS, n_emb - 1);
+            a[u] = S[trk0 * C + ec];
+            b[u] = O[trk0 * C + ec];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * TOPK_THREADS;
+            if (e < n_emb) {
+                const int r = e / C, c = e - r * C;
+                ss[r * CP + c] = a[u];
+                oo[r * CP + c] = b[u];
+            }
+        }
     }
     __syncthreads();
     float* const sc = scores + row[TSPN_VT_SCORE_OFF];
@@ -261,7 +301,7 @@ static int launch_embeddings(int64_t total_tracklets, const float* d_cls, int n_
                              float* S, float* O, cudaStream_t st) {
     if ((int64_t)n_classes * hidden <= 12288) {
         const size_t smt = (size_t)(2 * n_classes * (hidden + 1) + 2 * hidden * (n_classes + 1) + EMB_G * n_classes +
-                                    EMB_G * 2 * hidden) * sizeof(float);
+                                    EMB_G * 2 * hidden + 2 * hidden + 2 * n_classes) * sizeof(float);
         TSPN_CUDA_OK(cudaFuncSetAttribute(ppn_embed_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)smt));
         prefer_max_smem(ppn_embed_tiled_kernel);

@@ -84,7 +84,9 @@ survivor_rows_kernel(const int64_t* __restrict__ table, int nv, const float4* __
     const int tid = threadIdx.x;
     const int64_t r = blockIdx.x;
     const int64_t gp = rows[r];
-    const int v = gp >= 0 ? find_video(table, nv, TSPN_VT_PAIR_OFF, gp) : (int)(r / rows_per_video);
+    // rows are laid out [V][rows_per_video] (include/tspn_b200.h): the video is the row's position - no binary search
+    // through the table (four dependent global loads at the head of every CTA, under the all-pairs kernel)
+    const int v = (int)(r / rows_per_video);
     const int64_t* row = table + (int64_t)v * TSPN_VT_COLS;
     const int t_len = (int)row[TSPN_VT_T];
     __nv_bfloat16* outb = rel + r * ld_rel;
